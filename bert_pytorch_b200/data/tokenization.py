@@ -1,0 +1,176 @@
+"""Tokenisers.
+
+* ``get_wordpiece_tokenizer`` / ``get_bpe_tokenizer`` -- thin factories over the HuggingFace
+  ``tokenizers`` package (src/tokenization.py:42-57; Rust, kept as a dependency because it is
+  offline tooling, not a hot path -- SURVEY.md N12).
+* ``BasicTokenizer`` / ``WordpieceTokenizer`` / ``BertTokenizer`` -- pure-Python versions
+  (src/tokenization.py:60-277); the SQuAD answer post-processing still needs the basic
+  tokenizer to align predicted text with the original (run_squad.py:614).
+"""
+from __future__ import annotations
+
+import collections
+import unicodedata
+from typing import Dict, Iterable, List, Optional
+
+
+def get_wordpiece_tokenizer(vocab_file: str, uppercase: bool = False):
+    import tokenizers
+    return tokenizers.BertWordPieceTokenizer(vocab_file, clean_text=True, handle_chinese_chars=True,
+                                             lowercase=not uppercase)
+
+
+def get_bpe_tokenizer(vocab_file: str, uppercase: bool = False):
+    import tokenizers
+    merges = vocab_file.replace("vocab.json", "merges.txt") if vocab_file.endswith("vocab.json") else None
+    try:
+        return tokenizers.ByteLevelBPETokenizer(vocab_file, merges, lowercase=not uppercase)
+    except TypeError:
+        return tokenizers.ByteLevelBPETokenizer(vocab_file, lowercase=not uppercase)
+
+
+def load_vocab(vocab_file: str) -> "collections.OrderedDict[str, int]":
+    vocab: "collections.OrderedDict[str, int]" = collections.OrderedDict()
+    with open(vocab_file, "r", encoding="utf-8") as f:
+        for i, line in enumerate(f):
+            tok = line.rstrip("\n")
+            if tok == "" and i > 0 and not line:
+                break
+            vocab[tok.strip()] = i
+    return vocab
+
+
+def whitespace_tokenize(text: str) -> List[str]:
+    text = text.strip()
+    return text.split() if text else []
+
+
+def _is_whitespace(ch: str) -> bool:
+    return ch in " \t\n\r" or unicodedata.category(ch) == "Zs"
+
+
+def _is_control(ch: str) -> bool:
+    if ch in "\t\n\r":
+        return False
+    return unicodedata.category(ch).startswith("C")
+
+
+def _is_punctuation(ch: str) -> bool:
+    cp = ord(ch)
+    if 33 <= cp <= 47 or 58 <= cp <= 64 or 91 <= cp <= 96 or 123 <= cp <= 126:
+        return True
+    return unicodedata.category(ch).startswith("P")
+
+
+def _is_cjk(cp: int) -> bool:
+    return (0x4E00 <= cp <= 0x9FFF or 0x3400 <= cp <= 0x4DBF or 0x20000 <= cp <= 0x2A6DF
+            or 0x2A700 <= cp <= 0x2B73F or 0x2B740 <= cp <= 0x2B81F or 0x2B820 <= cp <= 0x2CEAF
+            or 0xF900 <= cp <= 0xFAFF or 0x2F800 <= cp <= 0x2FA1F)
+
+
+class BasicTokenizer:
+    """Whitespace + punctuation splitting, optional lower-casing/accent stripping, CJK
+    characters isolated; tokens in ``never_split`` pass through untouched."""
+
+    def __init__(self, do_lower_case: bool = True,
+                 never_split: Iterable[str] = ("[UNK]", "[SEP]", "[PAD]", "[CLS]", "[MASK]")):
+        self.do_lower_case = do_lower_case
+        self.never_split = set(never_split)
+
+    def tokenize(self, text: str) -> List[str]:
+        cleaned = []
+        for ch in text:
+            cp = ord(ch)
+            if cp == 0 or cp == 0xFFFD or _is_control(ch):
+                continue
+            if _is_whitespace(ch):
+                cleaned.append(" ")
+            elif _is_cjk(cp):
+                cleaned.extend((" ", ch, " "))
+            else:
+                cleaned.append(ch)
+        out: List[str] = []
+        for tok in whitespace_tokenize("".join(cleaned)):
+            if tok in self.never_split:
+                out.append(tok)
+                continue
+            if self.do_lower_case:
+                tok = "".join(c for c in unicodedata.normalize("NFD", tok.lower())
+                              if unicodedata.category(c) != "Mn")
+            out.extend(self._split_punct(tok))
+        return whitespace_tokenize(" ".join(out))
+
+    @staticmethod
+    def _split_punct(tok: str) -> List[str]:
+        pieces: List[List[str]] = []
+        new_word = True
+        for ch in tok:
+            if _is_punctuation(ch):
+                pieces.append([ch])
+                new_word = True
+            else:
+                if new_word:
+                    pieces.append([])
+                    new_word = False
+                pieces[-1].append(ch)
+        return ["".join(p) for p in pieces]
+
+
+class WordpieceTokenizer:
+    """Greedy longest-match-first sub-word split with the ``##`` continuation prefix."""
+
+    def __init__(self, vocab: Dict[str, int], unk_token: str = "[UNK]", max_input_chars_per_word: int = 100):
+        self.vocab, self.unk_token, self.max_chars = vocab, unk_token, max_input_chars_per_word
+
+    def tokenize(self, text: str) -> List[str]:
+        out: List[str] = []
+        for word in whitespace_tokenize(text):
+            if len(word) > self.max_chars:
+                out.append(self.unk_token)
+                continue
+            start, pieces, bad = 0, [], False
+            while start < len(word):
+                end, cur = len(word), None
+                while start < end:
+                    sub = word[start:end]
+                    if start > 0:
+                        sub = "##" + sub
+                    if sub in self.vocab:
+                        cur = sub
+                        break
+                    end -= 1
+                if cur is None:
+                    bad = True
+                    break
+                pieces.append(cur)
+                start = end
+            out.extend([self.unk_token] if bad else pieces)
+        return out
+
+
+class BertTokenizer:
+    """End-to-end basic + wordpiece tokenizer (kept for API compatibility)."""
+
+    def __init__(self, vocab_file: str, do_lower_case: bool = True, max_len: Optional[int] = None,
+                 never_split=("[UNK]", "[SEP]", "[PAD]", "[CLS]", "[MASK]")):
+        self.vocab = load_vocab(vocab_file)
+        self.ids_to_tokens = collections.OrderedDict((i, t) for t, i in self.vocab.items())
+        self.basic_tokenizer = BasicTokenizer(do_lower_case=do_lower_case, never_split=never_split)
+        self.wordpiece_tokenizer = WordpieceTokenizer(self.vocab)
+        self.max_len = max_len if max_len is not None else int(1e12)
+
+    def tokenize(self, text: str) -> List[str]:
+        return [sub for tok in self.basic_tokenizer.tokenize(text)
+                for sub in self.wordpiece_tokenizer.tokenize(tok)]
+
+    def convert_tokens_to_ids(self, tokens: Iterable[str]) -> List[int]:
+        ids = [self.vocab[t] for t in tokens]
+        if len(ids) > self.max_len:
+            raise ValueError(f"sequence length {len(ids)} exceeds the model maximum {self.max_len}")
+        return ids
+
+    def convert_ids_to_tokens(self, ids: Iterable[int]) -> List[str]:
+        return [self.ids_to_tokens[i] for i in ids]
+
+    def token_to_id(self, token: str) -> Optional[int]:
+        return self.vocab.get(token)

@@ -1,0 +1,83 @@
+"""Loader for the host-side native helper ``_host.so`` (ops/csrc/host.cpp): multi-threaded
+HDF5 chunk inflate + vectorised dynamic masking.  Pure C++ (no CUDA), built in-tree by
+:mod:`bert_pytorch_b200.ops.build`.  Everything that uses it has a NumPy fallback, so a
+missing build only costs speed on the CPU side."""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import numpy as np
+
+_LIB = None
+_TRIED = False
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "_host.so")
+
+
+class _Host:
+    def __init__(self, lib: ctypes.CDLL):
+        self.lib = lib
+        i64p = ctypes.POINTER(ctypes.c_int64)
+        lib.h5_inflate_rows.restype = ctypes.c_int
+        lib.h5_inflate_rows.argtypes = [ctypes.c_void_p, ctypes.c_int64, i64p, i64p, i64p, ctypes.c_int64,
+                                        ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
+                                        ctypes.c_int]
+        lib.mask_batch_i32.restype = None
+        lib.mask_batch_i32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32,
+                                       ctypes.c_int32, ctypes.c_double, ctypes.c_int32, ctypes.c_double,
+                                       ctypes.c_double, ctypes.c_uint64, ctypes.c_int]
+
+    def inflate_rows(self, raw: bytes, offs: np.ndarray, sizes: np.ndarray, rows0: np.ndarray,
+                     chunk_rows: int, total_rows: int, row_bytes: int, out: np.ndarray,
+                     threads: int = 0) -> None:
+        if not isinstance(raw, bytes):
+            raw = bytes(raw)
+        src = ctypes.cast(ctypes.c_char_p(raw), ctypes.c_void_p)   # no copy
+        i64p = ctypes.POINTER(ctypes.c_int64)
+        rc = self.lib.h5_inflate_rows(src, len(raw), offs.ctypes.data_as(i64p), sizes.ctypes.data_as(i64p),
+                                      rows0.ctypes.data_as(i64p), len(offs), chunk_rows, total_rows,
+                                      row_bytes, out.ctypes.data_as(ctypes.c_void_p), threads)
+        if rc != 0:
+            raise IOError(f"native HDF5 chunk inflate failed (zlib rc={rc})")
+
+
+def load():
+    global _LIB, _TRIED
+    if _LIB is None:
+        if not os.path.exists(lib_path()):
+            raise ImportError(f"{lib_path()} is not built (python -m bert_pytorch_b200.ops.build)")
+        _LIB = _Host(ctypes.CDLL(lib_path()))
+    return _LIB
+
+
+def load_or_none() -> Optional[_Host]:
+    global _TRIED
+    if _LIB is not None:
+        return _LIB
+    if _TRIED:
+        return None
+    _TRIED = True
+    try:
+        return load()
+    except Exception:
+        return None
+
+
+def mask_batch(host: _Host, ids: np.ndarray, sp: np.ndarray, *, seed: int, mask_token_index: int,
+               max_pred_per_seq: int, masked_lm_prob: float, vocab_size: int,
+               original_token_prob: float, random_token_prob: float, threads: int = 0):
+    ids = np.ascontiguousarray(ids, dtype=np.int32)
+    sp = np.ascontiguousarray(sp, dtype=np.int32)
+    out_ids = np.empty_like(ids)
+    labels = np.empty_like(ids)
+    B, S = ids.shape
+    host.lib.mask_batch_i32(ids.ctypes.data, sp.ctypes.data, out_ids.ctypes.data, labels.ctypes.data,
+                            B, S, sp.shape[1], mask_token_index, max_pred_per_seq, masked_lm_prob,
+                            vocab_size, original_token_prob, random_token_prob, seed, threads)
+    return out_ids, labels
