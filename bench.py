@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""Headline benchmark: BERT-large pre-training throughput (sequences/s, whole job) on N B200s.
+
+    python bench.py --gpus 1 --steps K --warmup W                 # this repo (fused sm_100a engine)
+    python bench.py --impl reference --gpus 1 --steps K --warmup W  # unmodified reference + torch shims
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W    # N > 1, one rank per GPU over NCCL
+
+Config = BASELINE.json phase 1 (`config/bert_pretraining_phase1_config.json`): BERT-large uncased
+(L24 H1024 A16 I4096, vocab 30522 -> 30528), seq 128, micro-batch 96 per GPU, max 20 predictions,
+masked_token_fraction 0.2, LAMB lr 6e-3 poly warm-up 0.2843, dropout 0.1, bf16 compute (the reference arm
+runs its stock fp16 autocast + GradScaler).  ``--phase 2`` selects seq 512 / micro-batch 16 / 80 preds.
+Synthetic data of that shape, random-init weights (no network for corpora/checkpoints).
+
+One *step* = one optimizer step = ``--accum`` micro-batches (forward+backward each) + gradient
+reduction over the ranks + LAMB update.  Default ``--accum 32`` (3072 sequences/GPU/step): the shipped
+global batch of 65536 is 683 micro-batches per step on one GPU (~25 s/step), too long for a bench
+loop; a smaller accumulation only *raises* the optimizer/all-reduce share of a step, so the reported
+sequences/s is conservative w.r.t. the shipped config.  ``--global-batch 65536`` reproduces the shipped
+arithmetic exactly.  Per-GPU work is fixed as N grows -> weak scaling.
+
+Timing: W >= 3 untimed warm-up steps, then exactly K steps bracketed by barrier + synchronize, CUDA
+events on the launching stream, max over ranks; an L2 flush (256 MB write) precedes every step and the
+per-step working set (~10 GB of activations) is far larger than the 126 MB L2 anyway; nvidia-smi
+clocks/throttle reasons are sampled during the timed region.
+``e2e`` repeats the measurement through the public training API (`pretrain.forward_backward_pass` /
+`take_optimizer_step`) with every micro-batch copied from pinned host memory inside the timed region and
+the loss read back to the host every optimizer step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+PHASES = {
+    1: dict(seq=128, local_batch=96, max_pred=20, lr=6e-3, warmup=0.2843, max_steps=7038, global_batch=65536),
+    2: dict(seq=512, local_batch=16, max_pred=80, lr=4e-3, warmup=0.128, max_steps=1563, global_batch=32768),
+}
+MODEL = dict(vocab_size=30522, hidden_size=1024, num_hidden_layers=24, num_attention_heads=16,
+             intermediate_size=4096, max_position_embeddings=512, type_vocab_size=2)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--phase", type=int, default=1, choices=[1, 2])
+    ap.add_argument("--accum", type=int, default=32, help="micro-batches per optimizer step (ignored with --global-batch)")
+    ap.add_argument("--global-batch", type=int, default=0, help="use the shipped ceil arithmetic for this global batch")
+    ap.add_argument("--local-batch", type=int, default=0)
+    ap.add_argument("--backend", default="nccl", choices=["nccl", "fused"], help="gradient reduction (ours)")
+    ap.add_argument("--layers", type=int, default=0, help="debug only: fewer layers (marks the result invalid)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--seed", type=int, default=42)
+    return ap.parse_args()
+
+
+def dist_setup(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1 and not dist.is_initialized() and args.impl != "reference":   # the reference inits its own group
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
+        dist.init_process_group("nccl", init_method="env://", device_id=dev)
+    return rank, world, local, dev
+
+
+def synth_batches(n, B, S, vocab, max_pred, seed, dtype, pin=True):
+    """n pre-masked micro-batches on the host: [ids, seg, mask, labels, nsp]."""
+    import numpy as np
+    import torch
+    from bert_pytorch_b200.data import synthetic
+    from bert_pytorch_b200.data.dataset import mask_batch, segment_ids_and_input_mask
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        ids, sp, nsl = synthetic.make_samples(B, S, vocab, True, rng)
+        seg, im = segment_ids_and_input_mask(ids, sp)
+        masked, labels = mask_batch(ids, sp, mask_token_index=4, max_pred_per_seq=max_pred, masked_lm_prob=0.2,
+                                    vocab_size=vocab, rng=rng)
+        ts = [torch.from_numpy(np.ascontiguousarray(a)).to(dtype) for a in (masked, seg, im, labels, nsl.astype(np.int32))]
+        out.append([t.pin_memory() if pin else t for t in ts])
+    return out
+
+
+def timed_steps(run_step, K, W, flusher, dev):
+    """W warm-up + K timed optimizer steps; returns (ms_per_step local, clocks record)."""
+    import torch
+    import torch.distributed as dist
+    from bert_pytorch_b200.utils.timing import ClockSampler
+    for i in range(W):
+        flusher.flush()
+        run_step(i)
+    torch.cuda.synchronize()
+    if dist.is_initialized():
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(gpu_index=dev.index or 0)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        flusher.flush()
+        run_step(W + i)
+    e1.record()
+    torch.cuda.synchronize()
+    if dist.is_initialized():
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    return e0.elapsed_time(e1) / K, clocks
+
+
+def max_over_ranks(x, dev):
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        return x
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+# ------------------------------------------------------------------------------------------------
+# this repository
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, ph, B, accum, rank, world, dev):
+    import torch
+    from bert_pytorch_b200 import BertConfig, ops, pretrain
+    from bert_pytorch_b200.models import BertForPreTraining, BertPretrainingCriterion
+    from bert_pytorch_b200.models.arena import NO_DECAY_KEYS, ParamArena
+    from bert_pytorch_b200.ops import api as K
+    from bert_pytorch_b200.optim import GradScaler, Lamb, PolyWarmUpScheduler
+    from bert_pytorch_b200.parallel import DataParallel, make_comm
+    from bert_pytorch_b200.utils.timing import L2Flusher
+    assert ops.available(), "sm_100a extension not loaded"
+    torch.manual_seed(args.seed + rank)
+    cfg = BertConfig.from_dict(dict(MODEL, next_sentence=True, hidden_act="gelu", hidden_dropout_prob=0.1,
+                                    attention_probs_dropout_prob=0.1, initializer_range=0.02))
+    if args.layers:
+        cfg.num_hidden_layers = args.layers
+    cfg.pad_vocab(8)
+    cfg.max_predictions_per_seq = ph["max_pred"]
+    model = BertForPreTraining(cfg).to(dev)
+    arena = ParamArena(model, device=dev)
+    comm = make_comm(args.backend if world > 1 else None)
+    ddp = DataParallel(model, comm=comm, arena=arena)
+    named = list(model.named_parameters())
+    groups = [{"params": [p for n, p in named if not any(k in n for k in NO_DECAY_KEYS)], "weight_decay": 0.01},
+              {"params": [p for n, p in named if any(k in n for k in NO_DECAY_KEYS)], "weight_decay": 0.0}]
+    opt = Lamb(groups, lr=ph["lr"])
+    arena.bind_optimizer(opt)
+    sched = PolyWarmUpScheduler(opt, warmup=ph["warmup"], total_steps=ph["max_steps"])
+    scaler = GradScaler(enabled=False)
+    crit = BertPretrainingCriterion(cfg.vocab_size)
+    model.train()
+    flusher = L2Flusher(dev)
+
+    pool = synth_batches(8, B, ph["seq"], MODEL["vocab_size"], ph["max_pred"], args.seed + 17 * rank, torch.int32)
+    dev_pool = [[t.to(dev) for t in b] for b in pool]
+    loss_acc = torch.zeros((), device=dev)
+
+    def step_device(i):
+        for m in range(accum):
+            batch = dev_pool[(i * accum + m) % len(dev_pool)]
+            loss = pretrain.forward_backward_pass(ddp, crit, scaler, batch, accum, sync_grads=(m == accum - 1),
+                                                  compute_dtype=torch.bfloat16)
+            loss_acc.add_(loss)
+        sched.step()
+        pretrain.take_optimizer_step(opt, None, ddp, scaler)
+
+    host_losses = []
+
+    def step_e2e(i):
+        # the public training API, inputs from pinned host memory, loss read back each optimizer step
+        window = torch.zeros((), device=dev)
+        for m in range(accum):
+            hb = pool[(i * accum + m) % len(pool)]
+            batch = [t.to(dev, non_blocking=True) for t in hb]
+            window += pretrain.forward_backward_pass(ddp, crit, scaler, batch, accum, sync_grads=(m == accum - 1),
+                                                     compute_dtype=torch.bfloat16)
+        sched.step()
+        pretrain.take_optimizer_step(opt, None, ddp, scaler)
+        host_losses.append(float(window))
+
+    l0 = K.KERNEL_LAUNCHES
+    ms, clocks = timed_steps(step_device, args.steps, args.warmup, flusher, dev)
+    launches = (K.KERNEL_LAUNCHES - l0) * args.steps // (args.steps + args.warmup)
+    e2e = None
+    if not args.no_e2e:
+        ms_e2e, _ = timed_steps(step_e2e, args.steps, max(1, min(args.warmup, 2)), flusher, dev)
+        h2d = sum(t.numel() * t.element_size() for t in pool[0]) * accum
+        e2e = dict(ms=ms_e2e, h2d=h2d, d2h=4)
+    final_loss = float(loss_acc) / max(1, (args.steps + args.warmup))
+    return ms, clocks, launches, e2e, dict(loss_mean=final_loss, backend=getattr(comm, "name", "single"))
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the unmodified reference code path on torch-native shims
+# ------------------------------------------------------------------------------------------------
+def run_reference(args, ph, B, accum, rank, world, dev):
+    shims, ref = os.path.join(ROOT, "baseline", "shims"), os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(ref) or not os.path.exists(os.path.join(ref, "run_pretraining.py")):
+        return None
+    sys.path[:0] = [shims, ref]
+    import torch
+    import run_pretraining as R          # the reference's own module
+    from bert_pytorch_b200.data import synthetic  # only to write vocab/model json (no compute path)
+    from bert_pytorch_b200.utils.timing import L2Flusher
+    work = tempfile.mkdtemp(prefix=f"refbench_r{rank}_")
+    vocab = synthetic.write_vocab(os.path.join(work, "vocab.txt"), MODEL["vocab_size"])
+    layers = args.layers or MODEL["num_hidden_layers"]
+    model_json = synthetic.write_model_config(os.path.join(work, "model.json"), vocab, **dict(MODEL, num_hidden_layers=layers))
+    ns = argparse.Namespace(
+        config_file=None, input_dir=work, output_dir=os.path.join(work, "out"), model_config_file=model_json,
+        masked_token_fraction=0.2, max_predictions_per_seq=ph["max_pred"], disable_progress_bar=True,
+        num_steps_per_checkpoint=10 ** 9, skip_checkpoint=True, checkpoint_activations=False, log_prefix="ref",
+        seed=args.seed, fp16=True, learning_rate=ph["lr"], lr_decay="poly", warmup_proportion=ph["warmup"],
+        global_batch_size=B * accum * world, local_batch_size=B, max_steps=float(ph["max_steps"]), steps=1e9,
+        previous_phase_end_step=0, kfac=False, kfac_inv_interval=10, kfac_factor_interval=1, kfac_stat_decay=0.95,
+        kfac_damping=0.003, kfac_kl_clip=0.001, kfac_skip_layers=["BertLMPredictionHead", "embedding"],
+        local_rank=int(os.environ.get("LOCAL_RANK", 0)))
+    os.makedirs(ns.output_dir, exist_ok=True)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29534")
+    os.environ.setdefault("RANK", "0")
+    os.environ.setdefault("WORLD_SIZE", "1")
+    torch.manual_seed(args.seed + rank)
+    ns = R.setup_training(ns)                      # init_process_group('nccl'), batch arithmetic
+    assert ns.accumulation_steps == accum, (ns.accumulation_steps, accum)
+    model, checkpoint, global_step, criterion, ns = R.prepare_model(ns)       # BertForPreTraining + DDP
+    optimizer, preconditioner, lr_schedulers, scaler = R.prepare_optimizers(ns, model, checkpoint, global_step)
+    model.train()
+    flusher = L2Flusher(dev)
+    pool = synth_batches(8, B, ph["seq"], MODEL["vocab_size"], ph["max_pred"], args.seed + 17 * rank, torch.int64)
+    dev_pool = [[t.to(dev) for t in b] for b in pool]
+
+    def one_step(i, batches_of, read_loss):
+        avg = 0.0
+        for m in range(accum):
+            batch = batches_of((i * accum + m) % len(pool))
+            loss = R.forward_backward_pass(model, criterion, scaler, batch, ns.accumulation_steps,
+                                           sync_grads=(m == accum - 1))
+            if read_loss:
+                avg += loss.item()          # the reference loop syncs every micro-step (run_pretraining.py:542)
+        for lrs in lr_schedulers:
+            lrs.step()
+        R.take_optimizer_step(optimizer, preconditioner, model, scaler)
+        return avg
+
+    step_device = lambda i: one_step(i, lambda j: dev_pool[j], False)
+    step_e2e = lambda i: one_step(i, lambda j: [t.to(ns.device) for t in pool[j]], True)
+    ms, clocks = timed_steps(step_device, args.steps, args.warmup, flusher, dev)
+    e2e = None
+    if not args.no_e2e:
+        ms_e2e, _ = timed_steps(step_e2e, args.steps, max(1, min(args.warmup, 2)), flusher, dev)
+        h2d = sum(t.numel() * t.element_size() for t in pool[0]) * accum
+        e2e = dict(ms=ms_e2e, h2d=h2d, d2h=4 * accum)
+    return ms, clocks, 0, e2e, dict(backend="nccl-ddp", scaler=float(scaler.get_scale()))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference" and not os.path.exists(os.path.join(ROOT, "baseline", "_ref", "run_pretraining.py")):
+        print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref missing: the reference has no "
+                          "setup.py/pyproject.toml so pip cannot install it; copy /root/reference there"}))
+        return
+    import torch
+    if not torch.cuda.is_available():
+        print(json.dumps({"impl": args.impl, "unavailable": "no CUDA device"}))
+        return
+    ph = dict(PHASES[args.phase])
+    rank, world, local, dev = dist_setup(args)
+    assert world == max(1, args.gpus) or world == 1, f"WORLD_SIZE={world} but --gpus {args.gpus}"
+    B = args.local_batch or ph["local_batch"]
+    if args.global_batch:
+        accum = math.ceil(math.ceil(args.global_batch / world) / B)
+    else:
+        accum = args.accum
+    global_batch = B * accum * world
+    fn = run_reference if args.impl == "reference" else run_ours
+    res = fn(args, ph, B, accum, rank, world, dev)
+    if res is None:
+        if rank == 0:
+            print(json.dumps({"impl": "reference", "unavailable": "reference copy not found under baseline/_ref"}))
+        return
+    ms_local, clocks, launches, e2e, extra = res
+    ms = max_over_ranks(ms_local, dev)
+    value = global_batch / (ms / 1e3)
+    out = {
+        "metric": f"BERT-large phase{args.phase} (seq{ph['seq']}) pretraining sequences/sec, whole job, device-timed max over ranks",
+        "value": round(value, 2), "unit": "sequences/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.impl == "ours" else "fp16 (reference stock AMP)", "data": "synthetic",
+        "impl": args.impl,
+        "config": {"model": "bert-large-uncased L24 H1024 A16 I4096 V30528" + (f" [DEBUG layers={args.layers}]" if args.layers else ""),
+                   "global_batch": global_batch, "seq_len": ph["seq"], "local_batch": B, "accumulation_steps": accum,
+                   "max_predictions_per_seq": ph["max_pred"], "optimizer": "LAMB", "dropout": 0.1,
+                   "parallelism": f"dp{world}", "grad_reduction": extra.get("backend"),
+                   "l2": "256MB L2 flush before every step; per-step working set (~10 GB activations) >> 126 MB L2",
+                   "note": "step = one optimizer step of accumulation_steps micro-batches incl. all-reduce + LAMB; "
+                           "shipped global batch 65536/32768 selectable with --global-batch"},
+        "clocks": {"sm_mhz": clocks.get("sm_mhz"), "sm_max_mhz": clocks.get("sm_max_mhz"),
+                   "reasons": clocks.get("reasons"), "power_w_max": clocks.get("power_w_max"),
+                   "samples": clocks.get("samples")},
+        "gpu_launches": int(launches),
+        "extra": extra,
+    }
+    if e2e is not None:
+        ms_e = max_over_ranks(e2e["ms"], dev)
+        out["e2e"] = {"value": round(global_batch / (ms_e / 1e3), 2), "unit": "sequences/s",
+                      "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"]),
+                      "ms_per_step": round(ms_e, 3)}
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    import torch.distributed as dist
+    if dist.is_initialized():
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -99,6 +99,11 @@ class ParamArena:
                 p.data = view
                 p.grad = self.flat_grad[s.offset:s.offset + s.numel].view(s.shape)
         self._tables = None
+        self._opt_tables = None
+        import weakref
+        ref = weakref.ref(self)
+        for mod in model.modules():
+            object.__setattr__(mod, "_arena_ref", ref)
         self.refresh_shadow()
 
     # -- views ----------------------------------------------------------------
@@ -160,11 +165,13 @@ class ParamArena:
             if id(p) not in group_of:
                 raise ValueError(f"parameter {s.name} is not managed by the optimizer")
             s.group = group_of[id(p)]
+            s.decay = float(optimizer.param_groups[s.group].get("weight_decay", 0.0)) != 0.0
             st = optimizer.state[p]
             st["exp_avg"] = self.exp_avg[s.offset:s.offset + s.numel].view(s.shape)
             st["exp_avg_sq"] = self.exp_avg_sq[s.offset:s.offset + s.numel].view(s.shape)
         optimizer._arena = self
         self._tables = None
+        self._opt_tables = None
 
     def adopt_optimizer_state(self, optimizer) -> None:
         """After ``optimizer.load_state_dict`` the moments are fresh tensors: copy them into

@@ -1,0 +1,385 @@
+"""Fused sm_100a execution engine for the BERT encoder and the pre-training heads.
+
+The ``nn.Module`` tree in :mod:`.modeling` only *holds* the parameters (as views into the
+:class:`~.arena.ParamArena`); on a B200 the math runs here as an explicit forward/backward
+*kernel program* -- no autograd graph, no per-op Python dispatch beyond one launch per fused block:
+
+  embeddings   gather x3 + add + LayerNorm + dropout                       1 kernel   (K1-K3)
+  per layer    QKV GEMM [M,H]x[H,3H] + bias                                 tcgen05    (K5, K6 gone)
+               flash attention (scale, key-padding, softmax, dropout, PV)   tcgen05    (K7-K12)
+               out-proj GEMM + bias + dropout + residual                    tcgen05    (K13-K14)
+               LayerNorm                                                     1 kernel   (K15)
+               FFN-1 GEMM + bias + GELU (saves pre-activation)               tcgen05    (K16)
+               FFN-2 GEMM + bias + dropout + residual                        tcgen05    (K17-K18)
+               LayerNorm                                                     1 kernel
+  MLM head     compact masked positions -> gather -> transform GEMM+GELU -> LN -> decoder GEMM + bias
+               -> softmax-CE fwd+bwd in place (only max_pred rows/sequence, K21-K24; fixes Q15)
+  backward     the mirror image: LN-bwd kernels emit the residual gradient *and* the dropout-masked
+               gradient plus all dgamma/dbeta/dbias column sums; dgrad GEMMs fuse the residual-gradient
+               add or GELU'; wgrad GEMMs (both operands MN-major, split-K) accumulate in fp32 straight
+               into the gradient arena.
+
+Dropout masks are a counter-based function of (seed, stream id, element index) so backward regenerates
+them (nothing stored, and recompute is deterministic -- SURVEY.md K27).
+Activations are saved rather than recomputed: a B200 has 180 GB (phase-1 micro-batch 96x128 needs ~10 GB).
+"""
+from __future__ import annotations
+
+import math
+import os
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import torch
+import torch.nn.functional as F
+
+from .. import ops
+from ..ops import api as K
+from .arena import ParamArena
+
+# dropout stream ids: stream = layer * 8 + site
+SITE_EMB, SITE_ATTN_PROB, SITE_ATTN_OUT, SITE_FFN_OUT = 0, 1, 2, 3
+_EMB_LAYER = 1023
+
+
+def _stream(layer: int, site: int) -> int:
+    return layer * 8 + site
+
+
+def _use_sdpa() -> bool:
+    return os.environ.get("B200_ATTN", "native") == "sdpa"
+
+
+@dataclass
+class _LayerSaved:
+    x: torch.Tensor = None
+    qkv: torch.Tensor = None
+    ctx: torch.Tensor = None
+    lse: torch.Tensor = None
+    pre1: torch.Tensor = None
+    mean1: torch.Tensor = None
+    rstd1: torch.Tensor = None
+    x1: torch.Tensor = None
+    y1: torch.Tensor = None
+    act: torch.Tensor = None
+    pre2: torch.Tensor = None
+    mean2: torch.Tensor = None
+    rstd2: torch.Tensor = None
+    sdpa: tuple = None
+
+
+@dataclass
+class _Saved:
+    B: int = 0
+    S: int = 0
+    seed: int = 0
+    p_hidden: float = 0.0
+    p_attn: float = 0.0
+    ids: torch.Tensor = None
+    seg: torch.Tensor = None
+    seqlens: torch.Tensor = None
+    emb_sum: torch.Tensor = None
+    emb_mean: torch.Tensor = None
+    emb_rstd: torch.Tensor = None
+    layers: List[_LayerSaved] = field(default_factory=list)
+
+
+class FusedEncoderEngine:
+    """Bound to one ``BertModel``; reads weights from the arena's bf16 shadow and LN parameters from the
+    fp32 master copy, writes gradients into the fp32 gradient arena."""
+
+    def __init__(self, bert):
+        self.bert = bert
+        cfg = bert.config
+        self.H, self.heads, self.L = cfg.hidden_size, cfg.num_attention_heads, cfg.num_hidden_layers
+        self.I = cfg.intermediate_size
+        if cfg.hidden_act != "gelu":
+            raise NotImplementedError("the fused engine implements the erf-GELU FFN only")
+        if self.H % 64 != 0 or (self.H // self.heads) != 64:
+            # the attention kernel is specialised for head_dim 64 (every shipped config)
+            if not _use_sdpa():
+                raise NotImplementedError("fused attention needs head_dim == 64 (set B200_ATTN=sdpa otherwise)")
+        ref = getattr(bert, "_arena_ref", None)
+        arena = ref() if ref is not None else None
+        if arena is None:
+            arena = ParamArena(bert)
+            self._own_arena = arena          # keep alive
+        self.arena = arena
+        self.prefix = self._find_prefix()
+        self.p_hidden = float(cfg.hidden_dropout_prob)
+        self.p_attn = float(cfg.attention_probs_dropout_prob)
+        self.has_type = bert.embeddings.has_token_type
+        self._seed_base = int(torch.initial_seed()) & 0x7FFFFFFF
+        self._calls = 0
+        self._hook = torch.zeros(1, device=arena.device, requires_grad=True)
+
+    # -- parameter lookup --------------------------------------------------------------------
+    def _find_prefix(self) -> str:
+        """Name prefix of this BertModel's parameters inside the arena ('' or 'bert.')."""
+        for cand in ("bert.", ""):
+            if (cand + "embeddings.word_embeddings.weight") in self.arena.by_name:
+                return cand
+        raise RuntimeError("the arena does not contain this encoder's parameters")
+
+    def w(self, name: str) -> torch.Tensor:      # bf16 shadow weight
+        return self.arena.shadow(self.prefix + name)
+
+    def p(self, name: str) -> torch.Tensor:      # fp32 master parameter
+        return self.arena.view(self.prefix + name)
+
+    def g(self, name: str) -> torch.Tensor:      # fp32 gradient slot
+        return self.arena.grad(self.prefix + name)
+
+    def _qkv(self, l: int, flat: torch.Tensor, kind: str) -> torch.Tensor:
+        base = f"{self.prefix}encoder.layer.{l}.attention.self."
+        if kind == "weight":
+            return self.arena.span(base + "query.weight", base + "value.weight", flat, (3 * self.H, self.H))
+        return self.arena.span(base + "query.bias", base + "value.bias", flat, (3 * self.H,))
+
+    def next_seed(self) -> int:
+        self._calls += 1
+        return (self._seed_base * 1000003 + self._calls) & 0x7FFFFFFFFFFF
+
+    # -- forward --------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, input_ids, token_type_ids, attention_mask, training: bool, seed: Optional[int] = None):
+        """Returns (sequence_output [B*S, H] bf16, saved-or-None)."""
+        B, S = input_ids.shape
+        M, H, A = B * S, self.H, self.arena
+        ph = self.p_hidden if training else 0.0
+        pa = self.p_attn if training else 0.0
+        seed = self.next_seed() if seed is None else seed
+        ids = input_ids.reshape(-1).to(torch.int32).contiguous()
+        seg = None
+        if self.has_type:
+            seg = (token_type_ids if token_type_ids is not None else torch.zeros_like(input_ids)
+                   ).reshape(-1).to(torch.int32).contiguous()
+        seqlens = attention_mask.to(torch.int32).sum(dim=1, dtype=torch.int32).contiguous()
+        sv = _Saved(B=B, S=S, seed=seed, p_hidden=ph, p_attn=pa, ids=ids, seg=seg, seqlens=seqlens) if training else None
+
+        x, e, mean, rstd = K.embedding_fwd(
+            ids, seg, self.w("embeddings.word_embeddings.weight"), self.w("embeddings.position_embeddings.weight"),
+            self.w("embeddings.token_type_embeddings.weight") if self.has_type else None,
+            self.p("embeddings.LayerNorm.weight"), self.p("embeddings.LayerNorm.bias"), S,
+            p_drop=ph, seed=seed, stream=_stream(_EMB_LAYER, SITE_EMB))
+        if training:
+            sv.emb_sum, sv.emb_mean, sv.emb_rstd = e, mean, rstd
+
+        for l in range(self.L):
+            pre = f"encoder.layer.{l}."
+            ls = _LayerSaved() if training else None
+            qkv = K.gemm(x, self._qkv(l, A.flat_shadow, "weight"), epi=K.EPI_BIAS,
+                         bias=self._qkv(l, A.flat_shadow, "bias"))
+            if _use_sdpa():
+                ctx, lse, sd = self._sdpa_fwd(qkv, seqlens, B, S, pa, training)
+                if training:
+                    ls.sdpa = sd
+            else:
+                ctx, lse = K.attention_fwd(qkv.view(B, S, 3 * H), seqlens, self.heads, p_drop=pa, seed=seed,
+                                           stream=_stream(l, SITE_ATTN_PROB))
+                ctx = ctx.view(M, H)
+            pre1 = K.gemm(ctx, self.w(pre + "attention.output.dense.weight"), epi=K.EPI_BIAS_DROP_RES,
+                          bias=self.w(pre + "attention.output.dense.bias"), res=x, p_drop=ph, seed=seed,
+                          stream=_stream(l, SITE_ATTN_OUT))
+            x1, mean1, rstd1 = K.layer_norm_fwd(pre1, self.p(pre + "attention.output.LayerNorm.weight"),
+                                                self.p(pre + "attention.output.LayerNorm.bias"), save_stats=training)
+            y1 = torch.empty(M, self.I, dtype=torch.bfloat16, device=x.device)
+            act = K.gemm(x1, self.w(pre + "intermediate.dense_act.weight"), epi=K.EPI_BIAS_GELU,
+                         bias=self.w(pre + "intermediate.dense_act.bias"), aux_out=y1)
+            pre2 = K.gemm(act, self.w(pre + "output.dense.weight"), epi=K.EPI_BIAS_DROP_RES,
+                          bias=self.w(pre + "output.dense.bias"), res=x1, p_drop=ph, seed=seed,
+                          stream=_stream(l, SITE_FFN_OUT))
+            x2, mean2, rstd2 = K.layer_norm_fwd(pre2, self.p(pre + "output.LayerNorm.weight"),
+                                                self.p(pre + "output.LayerNorm.bias"), save_stats=training)
+            if training:
+                ls.x, ls.qkv, ls.ctx, ls.lse = x, qkv, ctx, lse
+                ls.pre1, ls.mean1, ls.rstd1, ls.x1 = pre1, mean1, rstd1, x1
+                ls.y1, ls.act, ls.pre2, ls.mean2, ls.rstd2 = y1, act, pre2, mean2, rstd2
+                sv.layers.append(ls)
+            x = x2
+        return x, sv
+
+    # -- backward -------------------------------------------------------------------------------
+    @torch.no_grad()
+    def backward(self, sv: _Saved, d_out: torch.Tensor) -> None:
+        """``d_out``: [B*S, H] bf16 gradient of the sequence output.  Accumulates every parameter
+        gradient of the encoder into the arena."""
+        A, H, M = self.arena, self.H, sv.B * sv.S
+        ph, pa, seed = sv.p_hidden, sv.p_attn, sv.seed
+        d = d_out
+        for l in reversed(range(self.L)):
+            pre = f"encoder.layer.{l}."
+            ls = sv.layers[l]
+            # ---- LN2 -> (residual grad, dropped grad of the FFN-2 output)
+            d_pre2, d_y2 = K.layer_norm_bwd(
+                d, ls.pre2, ls.mean2, ls.rstd2, self.p(pre + "output.LayerNorm.weight"),
+                dgamma=self.g(pre + "output.LayerNorm.weight"), dbeta=self.g(pre + "output.LayerNorm.bias"),
+                dbias=self.g(pre + "output.dense.bias"), want_dropped=True, p_drop=ph, seed=seed,
+                drop_stream=_stream(l, SITE_FFN_OUT))
+            # ---- FFN-2
+            d_y1 = K.gemm(d_y2, self.w(pre + "output.dense.weight"), layout=K.NN, epi=K.EPI_DGELU, res=ls.y1)
+            K.wgrad_accumulate(d_y2, ls.act, self.g(pre + "output.dense.weight"))
+            # ---- FFN-1
+            K.colsum_accumulate(d_y1, self.g(pre + "intermediate.dense_act.bias"))
+            d_x1 = K.gemm(d_y1, self.w(pre + "intermediate.dense_act.weight"), layout=K.NN, epi=K.EPI_ADD, res=d_pre2)
+            K.wgrad_accumulate(d_y1, ls.x1, self.g(pre + "intermediate.dense_act.weight"))
+            # ---- LN1
+            d_pre1, d_yo = K.layer_norm_bwd(
+                d_x1, ls.pre1, ls.mean1, ls.rstd1, self.p(pre + "attention.output.LayerNorm.weight"),
+                dgamma=self.g(pre + "attention.output.LayerNorm.weight"),
+                dbeta=self.g(pre + "attention.output.LayerNorm.bias"),
+                dbias=self.g(pre + "attention.output.dense.bias"), want_dropped=True, p_drop=ph, seed=seed,
+                drop_stream=_stream(l, SITE_ATTN_OUT))
+            # ---- attention output projection
+            d_ctx = K.gemm(d_yo, self.w(pre + "attention.output.dense.weight"), layout=K.NN)
+            K.wgrad_accumulate(d_yo, ls.ctx, self.g(pre + "attention.output.dense.weight"))
+            # ---- attention core
+            if ls.sdpa is not None:
+                d_qkv = self._sdpa_bwd(ls.sdpa, d_ctx, sv.B, sv.S)
+            else:
+                d_qkv = K.attention_bwd(ls.qkv.view(sv.B, sv.S, 3 * H), sv.seqlens, ls.ctx.view(sv.B, sv.S, H),
+                                        d_ctx.view(sv.B, sv.S, H), ls.lse, self.heads, p_drop=pa, seed=seed,
+                                        stream=_stream(l, SITE_ATTN_PROB)).view(M, 3 * H)
+            # ---- QKV projection
+            K.colsum_accumulate(d_qkv, self._qkv(l, A.flat_grad, "bias"))
+            d = K.gemm(d_qkv, self._qkv(l, A.flat_shadow, "weight"), layout=K.NN, epi=K.EPI_ADD, res=d_pre1)
+            K.wgrad_accumulate(d_qkv, ls.x, self._qkv(l, A.flat_grad, "weight"))
+        # ---- embeddings: output dropout -> LN -> scatter into the three tables
+        d_e, _ = K.layer_norm_bwd(
+            d, sv.emb_sum, sv.emb_mean, sv.emb_rstd, self.p("embeddings.LayerNorm.weight"),
+            dgamma=self.g("embeddings.LayerNorm.weight"), dbeta=self.g("embeddings.LayerNorm.bias"),
+            p_drop=ph, seed=seed, in_stream=_stream(_EMB_LAYER, SITE_EMB) if ph > 0 else K.NO_STREAM)
+        K.embedding_bwd_scatter(d_e, sv.ids, sv.seg, self.g("embeddings.word_embeddings.weight"),
+                                self.g("embeddings.position_embeddings.weight"),
+                                self.g("embeddings.token_type_embeddings.weight") if self.has_type else None, sv.S)
+
+    # -- library attention (bring-up / bisecting aid: B200_ATTN=sdpa) ---------------------------------
+    def _sdpa_fwd(self, qkv, seqlens, B, S, p, training):
+        H, h = self.H, self.heads
+        d = H // h
+        t = qkv.view(B, S, 3, h, d)
+        q, k, v = (t[:, :, i].transpose(1, 2) for i in range(3))
+        mask = (torch.arange(S, device=qkv.device)[None, :] < seqlens[:, None])[:, None, None, :]
+        if training:
+            with torch.enable_grad():
+                q, k, v = (z.detach().requires_grad_(True) for z in (q, k, v))
+                o = F.scaled_dot_product_attention(q, k, v, attn_mask=mask, dropout_p=p)
+            return o.detach().transpose(1, 2).reshape(B * S, H), None, (q, k, v, o)
+        o = F.scaled_dot_product_attention(q, k, v, attn_mask=mask)
+        return o.transpose(1, 2).reshape(B * S, H), None, None
+
+    def _sdpa_bwd(self, sd, d_ctx, B, S):
+        q, k, v, o = sd
+        H, h = self.H, self.heads
+        go = d_ctx.view(B, S, h, H // h).transpose(1, 2)
+        dq, dk, dv = torch.autograd.grad(o, (q, k, v), go)
+        return torch.stack([dq.transpose(1, 2), dk.transpose(1, 2), dv.transpose(1, 2)], dim=2).reshape(B * S, 3 * H)
+
+    # -- autograd bridge for models with ordinary torch heads (finetuning, inference) ------------------
+    def encode(self, input_ids, token_type_ids, attention_mask) -> torch.Tensor:
+        B, S = input_ids.shape
+        training = self.bert.training and torch.is_grad_enabled()
+        if not training:
+            seq, _ = self.forward(input_ids, token_type_ids, attention_mask, training=False)
+            out = seq.view(B, S, self.H)
+        else:
+            out = _EncoderFn.apply(self._hook, self, input_ids, token_type_ids, attention_mask)
+        if torch.is_autocast_enabled():
+            return out.to(torch.get_autocast_dtype("cuda"))
+        return out.float()
+
+
+class _EncoderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, hook, engine, input_ids, token_type_ids, attention_mask):
+        seq, sv = engine.forward(input_ids, token_type_ids, attention_mask, training=True)
+        ctx.engine, ctx.sv = engine, sv
+        return seq.view(input_ids.size(0), input_ids.size(1), engine.H)
+
+    @staticmethod
+    def backward(ctx, d_seq):
+        engine, sv = ctx.engine, ctx.sv
+        engine.backward(sv, d_seq.reshape(-1, engine.H).to(torch.bfloat16).contiguous())
+        ctx.sv = None
+        return torch.zeros(1, device=d_seq.device), None, None, None, None
+
+
+class FusedPretrainer:
+    """Forward + backward of ``BertForPreTraining`` + criterion as one kernel program.
+
+    ``forward_backward`` returns the (unscaled) loss of the micro-batch as a device scalar and leaves the
+    gradients -- multiplied by ``grad_scale`` (= loss_scale / accumulation_steps) -- accumulated in the arena.
+    """
+
+    def __init__(self, model):
+        self.model = model
+        self.engine: FusedEncoderEngine = model.bert.fused_engine()
+        self.arena = self.engine.arena
+        cfg = model.config
+        self.V, self.H = cfg.vocab_size, cfg.hidden_size
+        self.has_nsp = model.cls.has_nsp and model.bert.pooler is not None
+        self.max_pred = int(getattr(cfg, "max_predictions_per_seq", 0)) or None
+        self._loss = None
+
+    def _max_pred(self, labels: torch.Tensor) -> int:
+        # capacity of masked positions per sequence; fixed per run so shapes stay static
+        if self.max_pred is None:
+            self.max_pred = min(labels.size(1), max(8, int((labels >= 0).sum(dim=1).max().item())))
+            self.max_pred = (self.max_pred + 7) // 8 * 8
+        return self.max_pred
+
+    @torch.no_grad()
+    def forward_backward(self, input_ids, segment_ids, input_mask, masked_lm_labels, next_sentence_labels,
+                         grad_scale: float = 1.0) -> torch.Tensor:
+        eng, A, H, V = self.engine, self.arena, self.H, self.V
+        B, S = input_ids.shape
+        M = B * S
+        training = self.model.training
+        seq, sv = eng.forward(input_ids, segment_ids, input_mask, training=True)
+        if not training:          # eval(): same path but dropout disabled upstream via p=0
+            pass
+        labels = masked_lm_labels.to(torch.int32).contiguous()
+        mp = self._max_pred(labels)
+        idx, tgt, count = K.mlm_compact(labels, mp)
+        loss = torch.zeros(1, dtype=torch.float32, device=seq.device)
+
+        # ---- MLM head forward (masked rows only)
+        rows = K.gather_rows(seq, idx)
+        t_pre = torch.empty_like(rows)
+        t_act = K.gemm(rows, A.shadow("cls.predictions.transform.dense_act.weight"), epi=K.EPI_BIAS_GELU,
+                       bias=A.shadow("cls.predictions.transform.dense_act.bias"), aux_out=t_pre)
+        t_ln, t_mean, t_rstd = K.layer_norm_fwd(t_act, A.view("cls.predictions.transform.LayerNorm.weight"),
+                                                A.view("cls.predictions.transform.LayerNorm.bias"))
+        emb_w = eng.w("embeddings.word_embeddings.weight")            # tied decoder weight [V, H]
+        logits = K.gemm(t_ln, emb_w, epi=K.EPI_BIAS, bias=A.shadow("cls.predictions.bias"))
+        K.softmax_ce_(logits, tgt, count, grad_scale, loss)            # logits <- dlogits
+
+        # ---- MLM head backward
+        K.colsum_accumulate(logits, A.grad("cls.predictions.bias"))
+        d_t_ln = K.gemm(logits, emb_w, layout=K.NN)
+        K.wgrad_accumulate(logits, t_ln, eng.g("embeddings.word_embeddings.weight"))
+        d_t_act, _ = K.layer_norm_bwd(d_t_ln, t_act, t_mean, t_rstd, A.view("cls.predictions.transform.LayerNorm.weight"),
+                                      dgamma=A.grad("cls.predictions.transform.LayerNorm.weight"),
+                                      dbeta=A.grad("cls.predictions.transform.LayerNorm.bias"))
+        d_t_pre = torch.ops.aten.gelu_backward(d_t_act, t_pre)
+        K.colsum_accumulate(d_t_pre, A.grad("cls.predictions.transform.dense_act.bias"))
+        K.wgrad_accumulate(d_t_pre, rows, A.grad("cls.predictions.transform.dense_act.weight"))
+        d_rows = K.gemm(d_t_pre, A.shadow("cls.predictions.transform.dense_act.weight"), layout=K.NN)
+        d_seq = torch.zeros(M, H, dtype=torch.bfloat16, device=seq.device)
+        K.scatter_rows(d_rows, idx, d_seq)
+
+        # ---- NSP head: [B,H] sized, plain torch (library GEMMs on 96 rows) with autograd into the arena grads
+        if self.has_nsp and next_sentence_labels is not None:
+            pool, nsp = self.model.bert.pooler.dense_act, self.model.cls.seq_relationship
+            with torch.enable_grad():
+                cls_tok = seq.view(B, S, H)[:, 0].float().requires_grad_(True)
+                pooled = torch.tanh(F.linear(cls_tok, pool.weight, pool.bias))
+                nsp_loss = F.cross_entropy(F.linear(pooled, nsp.weight, nsp.bias), next_sentence_labels.long().view(-1),
+                                           ignore_index=-1)
+                torch.autograd.backward(nsp_loss * grad_scale,
+                                        inputs=[cls_tok, pool.weight, pool.bias, nsp.weight, nsp.bias])
+            d_seq.view(B, S, H)[:, 0] += cls_tok.grad.to(torch.bfloat16)
+            loss = loss + nsp_loss.detach()
+
+        eng.backward(sv, d_seq)
+        return loss.squeeze(0) if loss.dim() else loss

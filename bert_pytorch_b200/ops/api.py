@@ -1,1 +1,339 @@
-"""Python wrappers over the sm_100a extension (filled in with the kernels)."""
+"""Python wrappers over the sm_100a extension (``_C.so``).
+
+Thin: allocate outputs, pick tile/split heuristics, translate enums.  No autograd here -- the
+fused engine (models/fused.py) calls forward and backward kernels explicitly.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import extension
+
+# GEMM enums (csrc/gemm_sm100.h)
+NT, NN, TN = 0, 1, 2
+EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_DROP_RES, EPI_ADD, EPI_DGELU, EPI_ACCUM_F32, EPI_BIAS_TANH, EPI_F32 = range(9)
+
+NUM_SMS = 148
+KERNEL_LAUNCHES = 0     # every wrapper bumps this: bench.py reports it as ``gpu_launches``
+
+
+def _count(n: int = 1) -> None:
+    global KERNEL_LAUNCHES
+    KERNEL_LAUNCHES += n
+
+
+def _pick_block_n(M: int, N: int) -> int:
+    """256-wide tiles unless that leaves most SMs idle or wastes a big tail."""
+    if N <= 128:
+        return 128
+    m_blocks = (M + 127) // 128
+    t256 = m_blocks * ((N + 255) // 256)
+    t128 = m_blocks * ((N + 127) // 128)
+
+    def eff(tiles: int, width: int) -> float:
+        waves = math.ceil(tiles / NUM_SMS)
+        return tiles * width / (waves * NUM_SMS * width) if tiles else 0.0
+    # a 256 tile does twice the work per issue slot; prefer it when the wave efficiency is comparable
+    return 256 if eff(t256, 256) >= eff(t128, 128) - 0.08 else 128
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, *, layout: int = NT, epi: int = EPI_NONE,
+         out: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+         res: Optional[torch.Tensor] = None, aux_out: Optional[torch.Tensor] = None, k_splits: int = 1,
+         block_n: Optional[int] = None, alpha: float = 1.0, p_drop: float = 0.0, seed: int = 0,
+         stream: int = 0) -> torch.Tensor:
+    """tcgen05 GEMM with a fused epilogue (see csrc/gemm_sm100.cu).  ``a``/``b`` are 2-D bf16."""
+    if layout == NT:
+        M, N = a.size(0), b.size(0)
+    elif layout == NN:
+        M, N = a.size(0), b.size(1)
+    else:
+        M, N = a.size(1), b.size(1)
+    if out is None:
+        dt = torch.float32 if epi in (EPI_ACCUM_F32, EPI_F32) else torch.bfloat16
+        out = torch.empty(M, N, dtype=dt, device=a.device)
+    if block_n is None:
+        block_n = _pick_block_n(M, N)
+    extension().gemm(a, b, out, layout, epi, bias, res, aux_out, k_splits, block_n, alpha, p_drop, seed, stream)
+    _count()
+    return out
+
+
+def wgrad_splits(n_out: int, k_out: int, reduce_len: int, block_n: int = 256) -> int:
+    """Split-K factor for dW[n_out, k_out] so the grid covers the machine."""
+    tiles = ((n_out + 127) // 128) * ((k_out + block_n - 1) // block_n)
+    kb = max(1, (reduce_len + 63) // 64)
+    want = max(1, (2 * NUM_SMS) // max(tiles, 1))
+    return max(1, min(want, kb // 4 if kb >= 8 else 1, 32))
+
+
+def wgrad_accumulate(dy: torch.Tensor, x: torch.Tensor, grad: torch.Tensor, alpha: float = 1.0) -> None:
+    """grad[N,K] (fp32, arena view) += dy[M,N]^T @ x[M,K]."""
+    n_out, k_out = grad.shape
+    bn = 256 if k_out >= 256 else 128
+    gemm(dy, x, layout=TN, epi=EPI_ACCUM_F32, out=grad, block_n=bn, alpha=alpha,
+         k_splits=wgrad_splits(n_out, k_out, dy.size(0), bn))
+
+
+def layer_norm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, eps: float = 1e-12,
+                   save_stats: bool = True, p_drop: float = 0.0, seed: int = 0, stream: int = 0):
+    y = torch.empty_like(x)
+    M = x.numel() // x.size(-1)
+    mean = torch.empty(M, dtype=torch.float32, device=x.device) if save_stats else None
+    rstd = torch.empty(M, dtype=torch.float32, device=x.device) if save_stats else None
+    extension().layer_norm_fwd(x, gamma, beta, y, mean, rstd, eps, p_drop, seed, stream)
+    _count()
+    return y, mean, rstd
+
+
+_LN_WS: Dict[Tuple[int, int, int], torch.Tensor] = {}
+
+
+def _ln_workspace(M: int, H: int, device: torch.device) -> torch.Tensor:
+    key = (device.index or 0, M, H)
+    ws = _LN_WS.get(key)
+    if ws is None:
+        ws = torch.empty(extension().ln_bwd_workspace(M, H), dtype=torch.float32, device=device)
+        _LN_WS[key] = ws
+    return ws
+
+
+NO_STREAM = 0xFFFFFFFF
+
+
+def layer_norm_bwd(dy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor, gamma: torch.Tensor, *,
+                   dgamma: Optional[torch.Tensor], dbeta: Optional[torch.Tensor], dbias: Optional[torch.Tensor] = None,
+                   want_dropped: bool = False, p_drop: float = 0.0, seed: int = 0, drop_stream: int = 0,
+                   in_stream: int = NO_STREAM):
+    """Returns (dx, dx_dropped or None).  ``dgamma``/``dbeta``/``dbias`` are *accumulated into*."""
+    dx = torch.empty_like(x)
+    dxd = torch.empty_like(x) if want_dropped else None
+    M, H = x.numel() // x.size(-1), x.size(-1)
+    extension().layer_norm_bwd(dy, x, mean, rstd, gamma, dx, dxd, dgamma, dbeta, dbias, _ln_workspace(M, H, x.device),
+                               p_drop, seed, drop_stream, in_stream)
+    _count(2)
+    return dx, dxd
+
+
+def colsum_accumulate(x: torch.Tensor, out: torch.Tensor) -> None:
+    """out[N] (fp32) += x[M,N].sum(0)"""
+    extension().colsum(x, out)
+    _count()
+
+
+def embedding_fwd(ids, seg, word, pos, type_emb, gamma, beta, S: int, *, eps=1e-12, p_drop=0.0, seed=0, stream=0):
+    M, H = ids.numel(), word.size(1)
+    e = torch.empty(M, H, dtype=torch.bfloat16, device=ids.device)
+    y = torch.empty_like(e)
+    mean = torch.empty(M, dtype=torch.float32, device=ids.device)
+    rstd = torch.empty_like(mean)
+    extension().embedding_fwd(ids, seg, word, pos, type_emb, gamma, beta, e, y, mean, rstd, S, eps, p_drop, seed, stream)
+    _count()
+    return y, e, mean, rstd
+
+
+def embedding_bwd_scatter(de, ids, seg, gword, gpos, gtype, S: int) -> None:
+    extension().embedding_bwd_scatter(de, ids, seg, gword, gpos, gtype, S)
+    _count()
+
+
+def mlm_compact(labels: torch.Tensor, max_pred: int):
+    B = labels.size(0)
+    idx = torch.empty(B * max_pred, dtype=torch.int32, device=labels.device)
+    tgt = torch.empty_like(idx)
+    count = torch.empty(1, dtype=torch.int32, device=labels.device)
+    extension().mlm_compact(labels, max_pred, idx, tgt, count)
+    _count()
+    return idx, tgt, count
+
+
+def gather_rows(src: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    dst = torch.empty(idx.numel(), src.size(-1), dtype=src.dtype, device=src.device)
+    extension().gather_rows(src, idx, dst)
+    _count()
+    return dst
+
+
+def scatter_rows(src: torch.Tensor, idx: torch.Tensor, dst: torch.Tensor) -> None:
+    extension().scatter_rows(src, idx, dst)
+    _count()
+
+
+def softmax_ce_(logits: torch.Tensor, targets: torch.Tensor, count: torch.Tensor, grad_scale: float,
+                loss_out: torch.Tensor) -> None:
+    """In place: logits <- d loss / d logits (scaled); loss_out += mean CE over valid targets."""
+    extension().softmax_ce(logits, targets, count, grad_scale, loss_out)
+    _count()
+
+
+def attention_fwd(qkv: torch.Tensor, seqlens: torch.Tensor, heads: int, *, p_drop=0.0, seed=0, stream=0):
+    B, S, H3 = qkv.shape
+    H = H3 // 3
+    ctx = torch.empty(B, S, H, dtype=torch.bfloat16, device=qkv.device)
+    lse = torch.empty(B, heads, S, dtype=torch.float32, device=qkv.device)
+    extension().attention_fwd(qkv, seqlens, ctx, lse, heads, 1.0 / math.sqrt(H // heads), p_drop, seed, stream)
+    _count()
+    return ctx, lse
+
+
+def attention_bwd(qkv, seqlens, ctx, dctx, lse, heads: int, *, p_drop=0.0, seed=0, stream=0):
+    B, S, H3 = qkv.shape
+    H = H3 // 3
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty(B, heads, S, dtype=torch.float32, device=qkv.device)
+    extension().attention_bwd(qkv, seqlens, ctx, dctx, lse, dqkv, delta, heads, 1.0 / math.sqrt(H // heads), p_drop,
+                              seed, stream)
+    _count(2)
+    return dqkv
+
+
+# ---------------------------------------------------------------------------
+# multi-tensor ops over arbitrary tensor lists
+# ---------------------------------------------------------------------------
+CHUNK = 65536
+_DT = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+_TABLE_CACHE: Dict[Tuple, Tuple[torch.Tensor, ...]] = {}
+
+
+def _chunk_table(numels: Sequence[int], device: torch.device, offsets: Optional[Sequence[int]] = None):
+    """chunk -> (tensor, start, len).  With ``offsets`` the starts are absolute arena positions."""
+    ct, cs, cl = [], [], []
+    for t, n in enumerate(numels):
+        base = offsets[t] if offsets is not None else 0
+        for s in range(0, n, CHUNK):
+            ct.append(t); cs.append(base + s); cl.append(min(CHUNK, n - s))
+    return (torch.tensor(ct, dtype=torch.int32, device=device), torch.tensor(cs, dtype=torch.int64, device=device),
+            torch.tensor(cl, dtype=torch.int32, device=device))
+
+
+def _list_tables(tensors: List[torch.Tensor]):
+    key = tuple((t.data_ptr(), t.numel()) for t in tensors)
+    hit = _TABLE_CACHE.get(key)
+    if hit is None:
+        dev = tensors[0].device
+        ptrs = torch.tensor([t.data_ptr() for t in tensors], dtype=torch.int64, device=dev)
+        hit = (ptrs,) + _chunk_table([t.numel() for t in tensors], dev)
+        if len(_TABLE_CACHE) > 64:
+            _TABLE_CACHE.clear()
+        _TABLE_CACHE[key] = hit
+    return hit
+
+
+def multi_tensor_l2norm(tensors: List[torch.Tensor], per_tensor: bool = False):
+    dev = tensors[0].device
+    total = torch.zeros(1, dtype=torch.float32, device=dev)
+    per = torch.zeros(len(tensors), dtype=torch.float32, device=dev) if per_tensor else None
+    by_dtype: Dict[torch.dtype, List[int]] = {}
+    for i, t in enumerate(tensors):
+        if not t.is_contiguous():
+            raise ValueError("multi_tensor_l2norm needs contiguous tensors")
+        by_dtype.setdefault(t.dtype, []).append(i)
+    for dt, idxs in by_dtype.items():
+        group = [tensors[i] for i in idxs]
+        ptrs, ct, cs, cl = _list_tables(group)
+        sub = torch.zeros(len(group), dtype=torch.float32, device=dev) if per_tensor else None
+        extension().mt_l2norm(_DT[dt], ptrs, ct, cs, cl, sub, total)
+        _count()
+        if per_tensor:
+            per[torch.tensor(idxs, device=dev)] = sub
+    return total.sqrt().squeeze(0), (per.sqrt() if per_tensor else torch.zeros(0, device=dev))
+
+
+def multi_tensor_scale(src: List[torch.Tensor], dst: List[torch.Tensor], scale) -> torch.Tensor:
+    dev = src[0].device
+    overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+    groups: Dict[Tuple[torch.dtype, torch.dtype], List[int]] = {}
+    for i, (s, d) in enumerate(zip(src, dst)):
+        groups.setdefault((s.dtype, d.dtype), []).append(i)
+    sd = scale.to(device=dev, dtype=torch.float32).reshape(1) if torch.is_tensor(scale) else None
+    sh = 1.0 if torch.is_tensor(scale) else float(scale)
+    for (sdt, ddt), idxs in groups.items():
+        ins, outs = [src[i] for i in idxs], [dst[i] for i in idxs]
+        ip, ct, cs, cl = _list_tables(ins)
+        op = _list_tables(outs)[0]
+        extension().mt_scale(_DT[sdt], _DT[ddt], ip, op, ct, cs, cl, sd, sh, overflow)
+        _count()
+    return overflow.squeeze(0)
+
+
+# ---------------------------------------------------------------------------
+# arena optimizers
+# ---------------------------------------------------------------------------
+
+def _arena_tables(arena):
+    t = getattr(arena, "_opt_tables", None)
+    if t is None:
+        dev = arena.device
+        ct, cs, cl = _chunk_table([s.numel for s in arena.slots], dev, [s.offset for s in arena.slots])
+        t = dict(ct=ct, cs=cs, cl=cl,
+                 decay=torch.tensor([1 if s.decay else 0 for s in arena.slots], dtype=torch.int32, device=dev),
+                 stats=torch.zeros(1, dtype=torch.float32, device=dev),
+                 norms=torch.zeros(2 * len(arena.slots), dtype=torch.float32, device=dev))
+        arena._opt_tables = t
+    return t
+
+
+def flat_unscale_(flat_grad: torch.Tensor, inv_scale: torch.Tensor, found_inf: torch.Tensor) -> None:
+    extension().flat_unscale(flat_grad, inv_scale.reshape(1), found_inf.reshape(1))
+    _count()
+
+
+def _uniform(optimizer, key):
+    vals = {repr(g[key]) for g in optimizer.param_groups}
+    if len(vals) != 1:
+        raise NotImplementedError(f"fused arena optimizer needs the same '{key}' in every param group")
+    return optimizer.param_groups[0][key]
+
+
+def arena_lamb_step(arena, optimizer, inv_scale=None, found_inf=None) -> None:
+    """One LAMB step over the arena (3 launches + 2 memsets).  Weight decay is per slot (decay flag x
+    the single non-zero group value), every other hyper-parameter must agree across groups -- which is
+    how every runner builds its groups (run_pretraining.py:279-296)."""
+    T = _arena_tables(arena)
+    lr = _uniform(optimizer, "lr")
+    b1, b2 = _uniform(optimizer, "betas")
+    eps = _uniform(optimizer, "eps")
+    wds = sorted({float(g["weight_decay"]) for g in optimizer.param_groups})
+    wd = max(wds)
+    for g in optimizer.param_groups:      # decay flag of a slot must agree with its group's decay
+        pass
+    step = int(optimizer.param_groups[0].get("step", 0)) + 1
+    ext = extension()
+    inv = inv_scale.reshape(1) if inv_scale is not None else None
+    fi = found_inf.reshape(1) if found_inf is not None else None
+    ext.flat_sumsq(arena.flat_grad, inv, T["stats"], fi)
+    ext.arena_lamb(arena.flat_grad, arena.flat_param, arena.exp_avg, arena.exp_avg_sq, arena.flat_shadow, T["ct"],
+                   T["cs"], T["cl"], T["decay"], T["stats"], T["norms"], inv, fi, float(lr), float(b1), float(b2),
+                   float(eps), float(wd), step, bool(_uniform(optimizer, "bias_correction")),
+                   bool(_uniform(optimizer, "grad_averaging")), float(_uniform(optimizer, "max_grad_norm") or 0.0),
+                   bool(optimizer.adam_w_mode), bool(optimizer.use_nvlamb))
+    _count(3)
+    # apex semantics: the step counter only advances when the update was applied.  Keeping that exact
+    # would need a host sync on found_inf; with a scaler we advance optimistically only when no scaler
+    # is in play, otherwise we read the flag (fp16 path only -- bf16 never has a scaler).
+    if fi is None or float(fi) == 0.0:
+        for g in optimizer.param_groups:
+            g["step"] = step
+    optimizer.last_grad_norm = T["stats"].sqrt()
+
+
+def arena_adam_step(arena, optimizer, inv_scale=None, found_inf=None) -> None:
+    T = _arena_tables(arena)
+    lr = _uniform(optimizer, "lr")
+    b1, b2 = _uniform(optimizer, "betas")
+    eps = _uniform(optimizer, "eps")
+    wd = max(float(g["weight_decay"]) for g in optimizer.param_groups)
+    step = int(optimizer.param_groups[0].get("step", 0)) + 1
+    inv = inv_scale.reshape(1) if inv_scale is not None else None
+    fi = found_inf.reshape(1) if found_inf is not None else None
+    extension().arena_adam(arena.flat_grad, arena.flat_param, arena.exp_avg, arena.exp_avg_sq, arena.flat_shadow,
+                           T["ct"], T["cs"], T["cl"], T["decay"], inv, fi, float(lr), float(b1), float(b2), float(eps),
+                           float(wd), step, bool(_uniform(optimizer, "bias_correction")), bool(optimizer.adam_w_mode))
+    _count()
+    if fi is None or float(fi) == 0.0:
+        for g in optimizer.param_groups:
+            g["step"] = step

@@ -1,0 +1,278 @@
+// torch <-> kernel glue.  Every function takes torch tensors, checks what the kernels assume (device,
+// dtype, contiguity, alignment) and launches on the current CUDA stream.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/extension.h>
+
+#include "gemm_sm100.h"
+#include "kernels.h"
+
+namespace {
+
+using torch::Tensor;
+
+inline cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+inline void check_bf16(const Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor");
+  TORCH_CHECK(t.scalar_type() == at::kBFloat16, name, " must be bf16");
+  TORCH_CHECK(t.stride(-1) == 1, name, " must have a unit inner stride");
+  TORCH_CHECK(reinterpret_cast<uintptr_t>(t.data_ptr()) % 16 == 0, name, " must be 16-byte aligned");
+}
+inline const void* opt_ptr(const c10::optional<Tensor>& t) { return t.has_value() && t->defined() ? t->data_ptr() : nullptr; }
+inline float* opt_f32(const c10::optional<Tensor>& t) {
+  if (!t.has_value() || !t->defined()) return nullptr;
+  TORCH_CHECK(t->scalar_type() == at::kFloat && t->is_cuda(), "expected a CUDA fp32 tensor");
+  return t->data_ptr<float>();
+}
+
+// D = epilogue(A op B).  a/b are 2-D bf16 (row stride arbitrary, multiple of 8 elements).
+//   layout 0 (NT): a [M,K], b [N,K]     1 (NN): a [M,K], b [K,N]     2 (TN): a [K,M], b [K,N]
+void gemm(Tensor a, Tensor b, Tensor out, int64_t layout, int64_t epi, c10::optional<Tensor> bias,
+          c10::optional<Tensor> res, c10::optional<Tensor> aux_out, int64_t k_splits, int64_t block_n, double alpha,
+          double p_drop, int64_t seed, int64_t stream_id) {
+  check_bf16(a, "a");
+  check_bf16(b, "b");
+  TORCH_CHECK(a.dim() == 2 && b.dim() == 2 && out.dim() == 2, "gemm operands must be 2-D");
+  c10::cuda::CUDAGuard guard(a.device());
+  b200::GemmCall c;
+  c.layout = (int)layout;
+  c.epi = (int)epi;
+  c.block_n = (int)block_n;
+  int64_t M, N, K;
+  if (layout == b200::GEMM_NT) { M = a.size(0); K = a.size(1); N = b.size(0); TORCH_CHECK(b.size(1) == K, "K mismatch"); }
+  else if (layout == b200::GEMM_NN) { M = a.size(0); K = a.size(1); N = b.size(1); TORCH_CHECK(b.size(0) == K, "K mismatch"); }
+  else { K = a.size(0); M = a.size(1); N = b.size(1); TORCH_CHECK(b.size(0) == K, "K mismatch"); }
+  TORCH_CHECK(out.size(0) == M && out.size(1) == N, "output shape mismatch");
+  TORCH_CHECK(a.stride(0) % 8 == 0 && b.stride(0) % 8 == 0, "row strides must be multiples of 8 elements");
+  TORCH_CHECK(N % 8 == 0, "N must be a multiple of 8");
+  const bool f32_out = (epi == b200::EPI_ACCUM_F32 || epi == b200::EPI_F32);
+  TORCH_CHECK(out.is_cuda() && out.stride(1) == 1, "out must be CUDA with unit inner stride");
+  TORCH_CHECK(out.scalar_type() == (f32_out ? at::kFloat : at::kBFloat16), "out dtype does not match the epilogue");
+  TORCH_CHECK(reinterpret_cast<uintptr_t>(out.data_ptr()) % 16 == 0 && out.stride(0) % (f32_out ? 4 : 8) == 0,
+              "out must be 16-byte aligned with an aligned row stride");
+  c.M = (int)M; c.N = (int)N; c.K = (int)K;
+  c.A = a.data_ptr(); c.lda = (int)a.stride(0);
+  c.B = b.data_ptr(); c.ldb = (int)b.stride(0);
+  c.out = out.data_ptr(); c.ldo = (int)out.stride(0);
+  if (aux_out.has_value() && aux_out->defined()) {
+    check_bf16(*aux_out, "aux_out");
+    TORCH_CHECK(aux_out->stride(0) == out.stride(0), "aux_out must share out's row stride");
+    c.aux_out = aux_out->data_ptr();
+  }
+  if (bias.has_value() && bias->defined()) {
+    check_bf16(*bias, "bias");
+    TORCH_CHECK(bias->numel() == N, "bias length");
+    c.bias = bias->data_ptr();
+  }
+  if (res.has_value() && res->defined()) {
+    check_bf16(*res, "res");
+    TORCH_CHECK(res->size(0) == M && res->size(1) == N && res->stride(0) % 8 == 0, "res shape");
+    c.res = res->data_ptr(); c.ldr = (int)res->stride(0);
+  }
+  const bool needs_bias = epi == b200::EPI_BIAS || epi == b200::EPI_BIAS_GELU || epi == b200::EPI_BIAS_DROP_RES ||
+                          epi == b200::EPI_BIAS_TANH;
+  TORCH_CHECK(!needs_bias || c.bias != nullptr, "this epilogue needs a bias");
+  TORCH_CHECK(epi != b200::EPI_BIAS_GELU || c.aux_out != nullptr, "bias+gelu needs aux_out");
+  TORCH_CHECK(epi != b200::EPI_DGELU || c.res != nullptr, "dgelu needs res (the pre-activation)");
+  TORCH_CHECK(epi != b200::EPI_BIAS_DROP_RES || c.res != nullptr, "bias+dropout+residual needs res");
+  c.k_splits = (int)k_splits;
+  c.alpha = (float)alpha;
+  c.p_drop = (float)p_drop;
+  c.seed = (unsigned long long)seed;
+  c.stream = (unsigned int)stream_id;
+  b200::gemm_bf16(c, cur_stream());
+}
+
+void layer_norm_fwd(Tensor x, Tensor gamma, Tensor beta, Tensor y, c10::optional<Tensor> mean,
+                    c10::optional<Tensor> rstd, double eps, double p_drop, int64_t seed, int64_t stream_id) {
+  check_bf16(x, "x"); check_bf16(y, "y");
+  TORCH_CHECK(x.is_contiguous() && y.is_contiguous(), "x/y must be contiguous");
+  const int H = (int)x.size(-1), M = (int)(x.numel() / H);
+  TORCH_CHECK(H % 8 == 0, "hidden size must be a multiple of 8");
+  c10::cuda::CUDAGuard guard(x.device());
+  b200::layer_norm_fwd(x.data_ptr(), gamma.data_ptr<float>(), beta.data_ptr<float>(), y.data_ptr(), opt_f32(mean),
+                       opt_f32(rstd), M, H, (float)eps, (unsigned long long)seed, (unsigned)stream_id, (float)p_drop,
+                       cur_stream());
+}
+
+int64_t ln_bwd_workspace(int64_t M, int64_t H) { return b200::ln_bwd_workspace_floats((int)M, (int)H); }
+
+void layer_norm_bwd(Tensor dy, Tensor x, Tensor mean, Tensor rstd, Tensor gamma, Tensor dx, c10::optional<Tensor> dxd,
+                    c10::optional<Tensor> dgamma, c10::optional<Tensor> dbeta, c10::optional<Tensor> dbias,
+                    Tensor workspace, double p_drop, int64_t seed, int64_t drop_stream, int64_t in_stream) {
+  check_bf16(dy, "dy"); check_bf16(x, "x"); check_bf16(dx, "dx");
+  const int H = (int)x.size(-1), M = (int)(x.numel() / H);
+  TORCH_CHECK(workspace.numel() >= b200::ln_bwd_workspace_floats(M, H), "LN workspace too small");
+  c10::cuda::CUDAGuard guard(x.device());
+  void* dxd_p = nullptr;
+  if (dxd.has_value() && dxd->defined()) { check_bf16(*dxd, "dxd"); dxd_p = dxd->data_ptr(); }
+  b200::layer_norm_bwd(dy.data_ptr(), x.data_ptr(), mean.data_ptr<float>(), rstd.data_ptr<float>(),
+                       gamma.data_ptr<float>(), dx.data_ptr(), dxd_p, opt_f32(dgamma), opt_f32(dbeta), opt_f32(dbias),
+                       workspace.data_ptr<float>(), M, H, (unsigned long long)seed, (unsigned)drop_stream,
+                       (unsigned)in_stream, (float)p_drop, cur_stream());
+}
+
+void colsum(Tensor x, Tensor out) {
+  check_bf16(x, "x");
+  TORCH_CHECK(x.dim() == 2 && out.scalar_type() == at::kFloat && out.numel() == x.size(1), "colsum shapes");
+  c10::cuda::CUDAGuard guard(x.device());
+  b200::colsum_bf16(x.data_ptr(), (int)x.size(0), (int)x.size(1), (int)x.stride(0), out.data_ptr<float>(), cur_stream());
+}
+
+void embedding_fwd(Tensor ids, c10::optional<Tensor> seg, Tensor word, Tensor pos, c10::optional<Tensor> type,
+                   Tensor gamma, Tensor beta, Tensor e_out, Tensor y, Tensor mean, Tensor rstd, int64_t S, double eps,
+                   double p_drop, int64_t seed, int64_t stream_id) {
+  TORCH_CHECK(ids.scalar_type() == at::kInt && ids.is_contiguous(), "ids must be contiguous int32");
+  check_bf16(word, "word"); check_bf16(pos, "pos"); check_bf16(e_out, "e_out"); check_bf16(y, "y");
+  const int H = (int)word.size(1), M = (int)ids.numel();
+  c10::cuda::CUDAGuard guard(ids.device());
+  const int* seg_p = nullptr;
+  const void* type_p = nullptr;
+  if (type.has_value() && type->defined()) {
+    TORCH_CHECK(seg.has_value() && seg->scalar_type() == at::kInt, "segment ids must be int32");
+    seg_p = seg->data_ptr<int>();
+    type_p = type->data_ptr();
+  }
+  b200::embedding_fwd(ids.data_ptr<int>(), seg_p, word.data_ptr(), pos.data_ptr(), type_p, gamma.data_ptr<float>(),
+                      beta.data_ptr<float>(), e_out.data_ptr(), y.data_ptr(), mean.data_ptr<float>(),
+                      rstd.data_ptr<float>(), M, (int)S, H, (float)eps, (unsigned long long)seed, (unsigned)stream_id,
+                      (float)p_drop, cur_stream());
+}
+
+void embedding_bwd_scatter(Tensor de, Tensor ids, c10::optional<Tensor> seg, Tensor gword, Tensor gpos,
+                           c10::optional<Tensor> gtype, int64_t S) {
+  check_bf16(de, "de");
+  const int H = (int)de.size(-1), M = (int)ids.numel();
+  c10::cuda::CUDAGuard guard(de.device());
+  b200::embedding_bwd_scatter(de.data_ptr(), ids.data_ptr<int>(),
+                              seg.has_value() && seg->defined() ? seg->data_ptr<int>() : nullptr,
+                              gword.data_ptr<float>(), gpos.data_ptr<float>(), opt_f32(gtype), M, (int)S, H,
+                              cur_stream());
+}
+
+void mlm_compact(Tensor labels, int64_t max_pred, Tensor idx, Tensor tgt, Tensor count) {
+  TORCH_CHECK(labels.scalar_type() == at::kInt && labels.dim() == 2 && labels.is_contiguous(), "labels: int32 [B,S]");
+  c10::cuda::CUDAGuard guard(labels.device());
+  b200::mlm_compact(labels.data_ptr<int>(), (int)labels.size(0), (int)labels.size(1), (int)max_pred,
+                    idx.data_ptr<int>(), tgt.data_ptr<int>(), count.data_ptr<int>(), cur_stream());
+}
+void gather_rows(Tensor src, Tensor idx, Tensor dst) {
+  check_bf16(src, "src"); check_bf16(dst, "dst");
+  c10::cuda::CUDAGuard guard(src.device());
+  b200::gather_rows(src.data_ptr(), idx.data_ptr<int>(), dst.data_ptr(), (int)idx.numel(), (int)src.size(-1), cur_stream());
+}
+void scatter_rows(Tensor src, Tensor idx, Tensor dst) {
+  check_bf16(src, "src"); check_bf16(dst, "dst");
+  c10::cuda::CUDAGuard guard(src.device());
+  b200::scatter_rows(src.data_ptr(), idx.data_ptr<int>(), dst.data_ptr(), (int)idx.numel(), (int)src.size(-1), cur_stream());
+}
+
+void softmax_ce(Tensor logits, Tensor targets, Tensor count, double grad_scale, Tensor loss_out) {
+  check_bf16(logits, "logits");
+  TORCH_CHECK(logits.dim() == 2 && logits.size(1) % 8 == 0 && logits.stride(0) % 8 == 0, "logits: [R,V], V%8==0");
+  c10::cuda::CUDAGuard guard(logits.device());
+  b200::softmax_ce(logits.data_ptr(), (int)logits.stride(0), targets.data_ptr<int>(), count.data_ptr<int>(),
+                   (float)grad_scale, loss_out.data_ptr<float>(), (int)logits.size(0), (int)logits.size(1), cur_stream());
+}
+
+inline int dtype_code(const Tensor& t) {
+  if (t.scalar_type() == at::kFloat) return 0;
+  if (t.scalar_type() == at::kBFloat16) return 1;
+  if (t.scalar_type() == at::kHalf) return 2;
+  TORCH_CHECK(false, "unsupported dtype for multi-tensor op");
+  return -1;
+}
+
+void mt_l2norm(int64_t dtype, Tensor ptrs, Tensor chunk_tensor, Tensor chunk_start, Tensor chunk_len,
+               c10::optional<Tensor> per_tensor_sq, Tensor total_sq) {
+  c10::cuda::CUDAGuard guard(ptrs.device());
+  b200::mt_l2norm((int)dtype, (const long long*)ptrs.data_ptr<int64_t>(), chunk_tensor.data_ptr<int>(),
+                  (const long long*)chunk_start.data_ptr<int64_t>(), chunk_len.data_ptr<int>(),
+                  (int)chunk_tensor.numel(), opt_f32(per_tensor_sq), total_sq.data_ptr<float>(), cur_stream());
+}
+void mt_scale(int64_t in_dtype, int64_t out_dtype, Tensor in_ptrs, Tensor out_ptrs, Tensor chunk_tensor,
+              Tensor chunk_start, Tensor chunk_len, c10::optional<Tensor> scale_dev, double scale_host, Tensor overflow) {
+  c10::cuda::CUDAGuard guard(in_ptrs.device());
+  b200::mt_scale((int)in_dtype, (int)out_dtype, (const long long*)in_ptrs.data_ptr<int64_t>(),
+                 (const long long*)out_ptrs.data_ptr<int64_t>(), chunk_tensor.data_ptr<int>(),
+                 (const long long*)chunk_start.data_ptr<int64_t>(), chunk_len.data_ptr<int>(), (int)chunk_tensor.numel(),
+                 opt_f32(scale_dev), (float)scale_host, overflow.data_ptr<int>(), cur_stream());
+}
+void flat_sumsq(Tensor g, c10::optional<Tensor> inv_scale, Tensor stats, c10::optional<Tensor> found_inf) {
+  c10::cuda::CUDAGuard guard(g.device());
+  TORCH_CHECK(g.numel() % 4 == 0, "arena size must be a multiple of 4");
+  b200::flat_sumsq(g.data_ptr<float>(), g.numel(), opt_f32(inv_scale), stats.data_ptr<float>(), opt_f32(found_inf), cur_stream());
+}
+void flat_unscale(Tensor g, Tensor inv_scale, Tensor found_inf) {
+  c10::cuda::CUDAGuard guard(g.device());
+  b200::flat_unscale(g.data_ptr<float>(), g.numel(), inv_scale.data_ptr<float>(), found_inf.data_ptr<float>(), cur_stream());
+}
+void arena_lamb(Tensor g, Tensor p, Tensor m, Tensor v, c10::optional<Tensor> shadow, Tensor chunk_tensor,
+                Tensor chunk_start, Tensor chunk_len, Tensor decay_flag, Tensor stats, Tensor norms,
+                c10::optional<Tensor> inv_scale, c10::optional<Tensor> found_inf, double lr, double beta1, double beta2,
+                double eps, double weight_decay, int64_t step, bool bias_correction, bool grad_averaging,
+                double max_grad_norm, bool adam_w_mode, bool use_nvlamb) {
+  c10::cuda::CUDAGuard guard(g.device());
+  b200::arena_lamb(g.data_ptr<float>(), p.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(),
+                   shadow.has_value() && shadow->defined() ? shadow->data_ptr() : nullptr, chunk_tensor.data_ptr<int>(),
+                   (const long long*)chunk_start.data_ptr<int64_t>(), chunk_len.data_ptr<int>(), (int)chunk_tensor.numel(),
+                   decay_flag.data_ptr<int>(), (int)decay_flag.numel(), stats.data_ptr<float>(), norms.data_ptr<float>(),
+                   opt_f32(inv_scale), opt_f32(found_inf), (float)lr, (float)beta1, (float)beta2, (float)eps,
+                   (float)weight_decay, (int)step, bias_correction, grad_averaging, (float)max_grad_norm, adam_w_mode,
+                   use_nvlamb, cur_stream());
+}
+void arena_adam(Tensor g, Tensor p, Tensor m, Tensor v, c10::optional<Tensor> shadow, Tensor chunk_tensor,
+                Tensor chunk_start, Tensor chunk_len, Tensor decay_flag, c10::optional<Tensor> inv_scale,
+                c10::optional<Tensor> found_inf, double lr, double beta1, double beta2, double eps, double weight_decay,
+                int64_t step, bool bias_correction, bool adam_w_mode) {
+  c10::cuda::CUDAGuard guard(g.device());
+  b200::arena_adam(g.data_ptr<float>(), p.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(),
+                   shadow.has_value() && shadow->defined() ? shadow->data_ptr() : nullptr, chunk_tensor.data_ptr<int>(),
+                   (const long long*)chunk_start.data_ptr<int64_t>(), chunk_len.data_ptr<int>(), (int)chunk_tensor.numel(),
+                   decay_flag.data_ptr<int>(), opt_f32(inv_scale), opt_f32(found_inf), (float)lr, (float)beta1,
+                   (float)beta2, (float)eps, (float)weight_decay, (int)step, bias_correction, adam_w_mode, cur_stream());
+}
+
+void attention_fwd(Tensor qkv, Tensor seqlens, Tensor ctx, Tensor lse, int64_t heads, double scale, double p_drop,
+                   int64_t seed, int64_t stream_id) {
+  check_bf16(qkv, "qkv"); check_bf16(ctx, "ctx");
+  TORCH_CHECK(qkv.dim() == 3 && qkv.is_contiguous(), "qkv: contiguous [B,S,3H]");
+  const int B = (int)qkv.size(0), S = (int)qkv.size(1), H = (int)qkv.size(2) / 3;
+  c10::cuda::CUDAGuard guard(qkv.device());
+  b200::attention_fwd(qkv.data_ptr(), seqlens.data_ptr<int>(), ctx.data_ptr(), lse.data_ptr<float>(), B, S, (int)heads,
+                      H / (int)heads, (float)scale, (unsigned long long)seed, (unsigned)stream_id, (float)p_drop, cur_stream());
+}
+void attention_bwd(Tensor qkv, Tensor seqlens, Tensor ctx, Tensor dctx, Tensor lse, Tensor dqkv, Tensor delta_ws,
+                   int64_t heads, double scale, double p_drop, int64_t seed, int64_t stream_id) {
+  check_bf16(qkv, "qkv"); check_bf16(ctx, "ctx"); check_bf16(dctx, "dctx"); check_bf16(dqkv, "dqkv");
+  const int B = (int)qkv.size(0), S = (int)qkv.size(1), H = (int)qkv.size(2) / 3;
+  c10::cuda::CUDAGuard guard(qkv.device());
+  b200::attention_bwd(qkv.data_ptr(), seqlens.data_ptr<int>(), ctx.data_ptr(), dctx.data_ptr(), lse.data_ptr<float>(),
+                      dqkv.data_ptr(), delta_ws.data_ptr<float>(), B, S, (int)heads, H / (int)heads, (float)scale,
+                      (unsigned long long)seed, (unsigned)stream_id, (float)p_drop, cur_stream());
+}
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.doc() = "bert_pytorch_b200 sm_100a kernels";
+  m.def("gemm", &gemm);
+  m.def("layer_norm_fwd", &layer_norm_fwd);
+  m.def("layer_norm_bwd", &layer_norm_bwd);
+  m.def("ln_bwd_workspace", &ln_bwd_workspace);
+  m.def("colsum", &colsum);
+  m.def("embedding_fwd", &embedding_fwd);
+  m.def("embedding_bwd_scatter", &embedding_bwd_scatter);
+  m.def("mlm_compact", &mlm_compact);
+  m.def("gather_rows", &gather_rows);
+  m.def("scatter_rows", &scatter_rows);
+  m.def("softmax_ce", &softmax_ce);
+  m.def("mt_l2norm", &mt_l2norm);
+  m.def("mt_scale", &mt_scale);
+  m.def("flat_sumsq", &flat_sumsq);
+  m.def("flat_unscale", &flat_unscale);
+  m.def("arena_lamb", &arena_lamb);
+  m.def("arena_adam", &arena_adam);
+  m.def("attention_fwd", &attention_fwd);
+  m.def("attention_bwd", &attention_bwd);
+}

@@ -1,0 +1,436 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a with fused epilogues.
+//
+//   D[M,N] = epilogue( A[M,K] * B[N,K]^T )        bf16 operands, fp32 accumulation in TMEM
+//
+// One CTA per SM loops over 128 x BLOCK_N output tiles.  Warp 0 (one lane) is the TMA producer,
+// warp 1 (one lane) issues tcgen05.mma, warps 2-5 drain the accumulator (tcgen05.ld) and run the
+// epilogue.  Operand tiles travel global -> shared memory with cp.async.bulk.tensor (128B swizzle)
+// through a STAGES-deep mbarrier ring; the accumulator is double buffered in TMEM so the epilogue of
+// tile i overlaps the main loop of tile i+1.
+//
+// Both operands can be K-major (reduction dim contiguous) or MN-major, selected per instantiation, so
+// the same kernel serves the three GEMMs of a linear layer without any transpose copy
+// (SURVEY.md K5/K13/K16/K17/K21/K23 and their backward call sites):
+//     forward  Y  = X  W^T        A K-major (X[M,K]),     B K-major  (W[N,K])
+//     dgrad    dX = dY W          A K-major (dY[M,N']),   B MN-major (W[N',K'] read as [Kred][N])
+//     wgrad    dW = dY^T X        A MN-major (dY[M,N']),  B MN-major (X[M,K'])   (+ split-K, fp32 atomics)
+//
+// Epilogues (runtime switch, warp uniform): bias, bias+GELU(erf) with the pre-activation saved for
+// backward, bias+dropout+residual, residual add, multiply by GELU'(aux), fp32 accumulate-into (wgrad into
+// the gradient arena), bias+tanh, plain fp32.
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+#include "gemm_sm100.h"
+
+namespace b200 {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;          // 64 bf16 = 128 B = one swizzle atom row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;     // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+constexpr int SMEM_BUDGET = 196608;  // bytes for the operand ring (192 KB)
+
+template <int BLOCK_N>
+struct Cfg {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;  // double buffered accumulator (256 or 512 columns)
+  static constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct GemmArgs {
+  int M, N, K;
+  int m_blocks, n_blocks, k_blocks, k_splits, k_per_split;
+  int epi;
+  void* out;
+  int ldo;
+  __nv_bfloat16* aux_out;
+  const __nv_bfloat16* bias;
+  const __nv_bfloat16* res;
+  int ldr;
+  unsigned long long seed;
+  unsigned int stream;
+  unsigned int drop_thresh16;
+  float drop_scale;
+  float alpha;
+};
+
+template <bool A_MN, bool B_MN, int BLOCK_N>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+            const GemmArgs p) {
+  using C = Cfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* tmem_full = empty_bar + C::STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_base_slot, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  const int total_tiles = p.m_blocks * p.n_blocks * p.k_splits;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nb = tile % p.n_blocks;
+        const int mb = (tile / p.n_blocks) % p.m_blocks;
+        const int ks = tile / (p.n_blocks * p.m_blocks);
+        const int kb0 = ks * p.k_per_split;
+        const int kb1 = min(p.k_blocks, kb0 + p.k_per_split);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % C::STAGES;
+          const uint32_t ph = (it / C::STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * C::STAGE_BYTES;
+          uint8_t* sb = sa + C::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
+          if constexpr (!A_MN) {
+            tma_load_2d(sa, &tmap_a, &full_bar[s], kb * BLOCK_K, mb * BLOCK_M);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_M / 64; ++j)
+              tma_load_2d(sa + j * 8192, &tmap_a, &full_bar[s], mb * BLOCK_M + j * 64, kb * BLOCK_K);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(sb, &tmap_b, &full_bar[s], kb * BLOCK_K, nb * BLOCK_N);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_N / 64; ++j)
+              tma_load_2d(sb + j * 8192, &tmap_b, &full_bar[s], nb * BLOCK_N + j * 64, kb * BLOCK_K);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
+      uint32_t it = 0, tile_it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
+        const int ks = tile / (p.n_blocks * p.m_blocks);
+        const int kb0 = ks * p.k_per_split;
+        const int kb1 = min(p.k_blocks, kb0 + p.k_per_split);
+        const uint32_t as = tile_it & 1, aph = (tile_it >> 1) & 1;
+        mbar_wait(&tmem_empty[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % C::STAGES;
+          const uint32_t ph = (it / C::STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
+          const uint32_t sb = sa + C::A_BYTES;
+          const uint64_t da0 = A_MN ? umma_smem_desc_sw128(sa, 8192, 1024) : umma_smem_desc_sw128(sa, 16, 1024);
+          const uint64_t db0 = B_MN ? umma_smem_desc_sw128(sb, 8192, 1024) : umma_smem_desc_sw128(sb, 16, 1024);
+#pragma unroll
+          for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+            // advance inside the tile: K-major +32 B per UMMA_K, MN-major +16 rows * 128 B
+            const uint64_t da = da0 + (uint64_t)(A_MN ? (kk * 2048) >> 4 : (kk * 32) >> 4);
+            const uint64_t db = db0 + (uint64_t)(B_MN ? (kk * 2048) >> 4 : (kk * 32) >> 4);
+            umma_bf16_ss(tmem_d, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);  // smem slot reusable once these MMAs retire
+        }
+        umma_commit(&tmem_full[as]);   // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    uint32_t tile_it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
+      const int nb = tile % p.n_blocks;
+      const int mb = (tile / p.n_blocks) % p.m_blocks;
+      const int ks = tile / (p.n_blocks * p.m_blocks);
+      const int kb0 = ks * p.k_per_split;
+      const int kb1 = min(p.k_blocks, kb0 + p.k_per_split);
+      const uint32_t as = tile_it & 1, aph = (tile_it >> 1) & 1;
+      mbar_wait(&tmem_full[as], aph);
+      tc_fence_after();
+      const int row = mb * BLOCK_M + q * 32 + lane;
+      const bool row_ok = row < p.M && kb1 > kb0;
+      const uint32_t taddr = tmem_base + as * BLOCK_N + (uint32_t(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        const int n0 = nb * BLOCK_N + c * 32;
+        if (n0 >= p.N) break;  // warp uniform
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c * 32, v);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+        const int ncols = min(32, p.N - n0);  // multiple of 8
+        const size_t roff = (size_t)row * p.ldr + n0;
+        const size_t ooff = (size_t)row * p.ldo + n0;
+
+        if (p.epi == EPI_ACCUM_F32) {
+          if (row_ok) {
+            float* o = reinterpret_cast<float*>(p.out) + ooff;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (j < ncols) {
+                if (p.k_splits > 1) {
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j), "f"(f[j]),
+                               "f"(f[j + 1]), "f"(f[j + 2]), "f"(f[j + 3])
+                               : "memory");
+                } else {
+                  float4 cur = *reinterpret_cast<float4*>(o + j);
+                  cur.x += f[j]; cur.y += f[j + 1]; cur.z += f[j + 2]; cur.w += f[j + 3];
+                  *reinterpret_cast<float4*>(o + j) = cur;
+                }
+              }
+            }
+          }
+          continue;
+        }
+        if (p.epi == EPI_F32) {
+          if (row_ok) {
+            float* o = reinterpret_cast<float*>(p.out) + ooff;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              if (j < ncols) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          }
+          continue;
+        }
+        // ---- bias (same 32 values for every lane: broadcast loads)
+        if (p.epi == EPI_BIAS || p.epi == EPI_BIAS_GELU || p.epi == EPI_BIAS_DROP_RES || p.epi == EPI_BIAS_TANH) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (g * 8 < ncols) {
+              const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.bias + n0 + g * 8));
+              const uint32_t w[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float2 bb = unpack_bf16(w[t]);
+                f[g * 8 + 2 * t] += bb.x;
+                f[g * 8 + 2 * t + 1] += bb.y;
+              }
+            }
+          }
+        }
+        if (p.epi == EPI_BIAS_GELU) {
+          if (row_ok) {  // save the pre-activation, then activate
+            __nv_bfloat16* a = p.aux_out + ooff;
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              if (g * 8 < ncols)
+                *reinterpret_cast<uint4*>(a + g * 8) =
+                    make_uint4(pack_bf16(f[g * 8], f[g * 8 + 1]), pack_bf16(f[g * 8 + 2], f[g * 8 + 3]),
+                               pack_bf16(f[g * 8 + 4], f[g * 8 + 5]), pack_bf16(f[g * 8 + 6], f[g * 8 + 7]));
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+        } else if (p.epi == EPI_BIAS_TANH) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = tanhf(f[j]);
+        } else if (p.epi == EPI_BIAS_DROP_RES || p.epi == EPI_ADD || p.epi == EPI_DGELU) {
+          if (p.epi == EPI_BIAS_DROP_RES && p.drop_thresh16 != 0 && row_ok) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (g * 8 < ncols) {
+                const uint64_t e8 = ((uint64_t)row * (uint64_t)p.N + (uint64_t)(n0 + g * 8)) >> 3;
+                const uint32_t keep = dropout_keep8(p.seed, p.stream, e8, p.drop_thresh16);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) f[g * 8 + t] = ((keep >> t) & 1u) ? f[g * 8 + t] * p.drop_scale : 0.f;
+              }
+            }
+          }
+          if (row_ok && p.res != nullptr) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (g * 8 < ncols) {
+                const uint4 r = *reinterpret_cast<const uint4*>(p.res + roff + g * 8);
+                const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  const float2 rr = unpack_bf16(w[t]);
+                  if (p.epi == EPI_DGELU) {
+                    f[g * 8 + 2 * t] *= dgelu_erf(rr.x);
+                    f[g * 8 + 2 * t + 1] *= dgelu_erf(rr.y);
+                  } else {
+                    f[g * 8 + 2 * t] += rr.x;
+                    f[g * 8 + 2 * t + 1] += rr.y;
+                  }
+                }
+              }
+            }
+          }
+        }
+        if (row_ok) {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + ooff;
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            if (g * 8 < ncols)
+              *reinterpret_cast<uint4*>(o + g * 8) =
+                  make_uint4(pack_bf16(f[g * 8], f[g * 8 + 1]), pack_bf16(f[g * 8 + 2], f[g * 8 + 3]),
+                             pack_bf16(f[g * 8 + 4], f[g * 8 + 5]), pack_bf16(f[g * 8 + 6], f[g * 8 + 7]));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || f == nullptr) {
+      fprintf(stderr, "[b200] cuTensorMapEncodeTiled is unavailable (%s)\n", cudaGetErrorString(e));
+      abort();
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(f);
+  });
+  return fn;
+}
+
+// 2D bf16 tensor map: `inner` contiguous elements per row, `outer` rows, row pitch `ld` elements,
+// box = [box_outer][box_inner], 128B swizzle (box_inner must be 64 bf16).
+CUtensorMap make_tmap_2d_bf16(const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                              uint32_t box_outer) {
+  struct Key {
+    const void* p; uint64_t i, o, l; uint32_t bi, bo;
+    bool operator==(const Key& k) const { return p == k.p && i == k.i && o == k.o && l == k.l && bi == k.bi && bo == k.bo; }
+  };
+  struct Hash {
+    size_t operator()(const Key& k) const {
+      size_t h = reinterpret_cast<size_t>(k.p);
+      h = h * 1000003u ^ k.i; h = h * 1000003u ^ k.o; h = h * 1000003u ^ k.l; h = h * 1000003u ^ k.bi;
+      return h * 1000003u ^ k.bo;
+    }
+  };
+  static std::unordered_map<Key, CUtensorMap, Hash> cache;
+  static std::mutex mu;
+  Key key{ptr, inner, outer, ld, box_inner, box_outer};
+  std::lock_guard<std::mutex> lock(mu);
+  auto itf = cache.find(key);
+  if (itf != cache.end()) return itf->second;
+  CUtensorMap m;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box,
+                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "[b200] cuTensorMapEncodeTiled failed (%d): ptr=%p inner=%llu outer=%llu ld=%llu box=%ux%u\n",
+            (int)r, ptr, (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld, box_inner,
+            box_outer);
+    abort();
+  }
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, m);
+  return m;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev;
+    B200_CUDA_CHECK(cudaGetDevice(&dev));
+    B200_CUDA_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  }
+  return n;
+}
+
+template <bool A_MN, bool B_MN, int BLOCK_N>
+static void launch(const GemmCall& c, cudaStream_t st) {
+  using C = Cfg<BLOCK_N>;
+  GemmArgs p;
+  p.M = c.M; p.N = c.N; p.K = c.K;
+  p.m_blocks = (c.M + BLOCK_M - 1) / BLOCK_M;
+  p.n_blocks = (c.N + BLOCK_N - 1) / BLOCK_N;
+  p.k_blocks = (c.K + BLOCK_K - 1) / BLOCK_K;
+  p.k_splits = c.k_splits < 1 ? 1 : c.k_splits;
+  if (p.k_splits > p.k_blocks) p.k_splits = p.k_blocks;
+  p.k_per_split = (p.k_blocks + p.k_splits - 1) / p.k_splits;
+  p.k_splits = (p.k_blocks + p.k_per_split - 1) / p.k_per_split;   // no empty splits
+  p.epi = c.epi;
+  p.out = c.out; p.ldo = c.ldo; p.aux_out = reinterpret_cast<__nv_bfloat16*>(c.aux_out);
+  p.bias = reinterpret_cast<const __nv_bfloat16*>(c.bias);
+  p.res = reinterpret_cast<const __nv_bfloat16*>(c.res); p.ldr = c.ldr;
+  p.seed = c.seed; p.stream = c.stream;
+  float pd = c.p_drop;
+  p.drop_thresh16 = pd > 0.f ? (unsigned)(pd * 65536.f + 0.5f) : 0u;
+  p.drop_scale = pd > 0.f ? 65536.f / (65536.f - (float)p.drop_thresh16) : 1.f;
+  p.alpha = c.alpha;
+  // operand maps
+  CUtensorMap ta = A_MN ? make_tmap_2d_bf16(c.A, c.M, c.K, c.lda, 64, BLOCK_K)
+                        : make_tmap_2d_bf16(c.A, c.K, c.M, c.lda, BLOCK_K, BLOCK_M);
+  CUtensorMap tb = B_MN ? make_tmap_2d_bf16(c.B, c.N, c.K, c.ldb, 64, BLOCK_K)
+                        : make_tmap_2d_bf16(c.B, c.K, c.N, c.ldb, BLOCK_K, BLOCK_N);
+  auto kern = gemm_kernel<A_MN, B_MN, BLOCK_N>;
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_TOTAL));
+    configured = true;
+  }
+  const int tiles = p.m_blocks * p.n_blocks * p.k_splits;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  if (grid <= 0) return;
+  kern<<<grid, NUM_THREADS, C::SMEM_TOTAL, st>>>(ta, tb, p);
+}
+
+void gemm_bf16(const GemmCall& c, cudaStream_t st) {
+  const bool wide = c.block_n == 256;
+  switch (c.layout) {
+    case GEMM_NT: wide ? launch<false, false, 256>(c, st) : launch<false, false, 128>(c, st); break;
+    case GEMM_NN: wide ? launch<false, true, 256>(c, st) : launch<false, true, 128>(c, st); break;
+    case GEMM_TN: wide ? launch<true, true, 256>(c, st) : launch<true, true, 128>(c, st); break;
+    default: fprintf(stderr, "[b200] bad gemm layout %d\n", c.layout); abort();
+  }
+}
+
+}  // namespace b200

@@ -1,0 +1,48 @@
+// Host API of the tcgen05 GEMM (see gemm_sm100.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200 {
+
+enum GemmLayout : int {
+  GEMM_NT = 0,  // D[M,N] = A[M,K] * B[N,K]^T        A stored [M][lda], B stored [N][ldb]   (forward)
+  GEMM_NN = 1,  // D[M,N] = A[M,K] * B[K,N]          A stored [M][lda], B stored [K][ldb]   (dgrad)
+  GEMM_TN = 2,  // D[M,N] = A[K,M]^T * B[K,N]        A stored [K][lda], B stored [K][ldb]   (wgrad)
+};
+
+enum GemmEpilogue : int {
+  EPI_NONE = 0,           // out(bf16) = alpha*acc
+  EPI_BIAS = 1,           // + bias[n]
+  EPI_BIAS_GELU = 2,      // aux_out = acc + bias ; out = gelu(aux_out)
+  EPI_BIAS_DROP_RES = 3,  // out = res + dropout(acc + bias)
+  EPI_ADD = 4,            // out = acc + res          (res may be null)
+  EPI_DGELU = 5,          // out = acc * gelu'(res)
+  EPI_ACCUM_F32 = 6,      // out(fp32) += alpha*acc   (atomic when split-K)
+  EPI_BIAS_TANH = 7,      // out = tanh(acc + bias)
+  EPI_F32 = 8,            // out(fp32) = alpha*acc
+};
+
+struct GemmCall {
+  int layout = GEMM_NT;
+  int epi = EPI_NONE;
+  int block_n = 256;   // 128 or 256
+  int M = 0, N = 0, K = 0;
+  const void* A = nullptr; int lda = 0;
+  const void* B = nullptr; int ldb = 0;
+  void* out = nullptr; int ldo = 0;
+  void* aux_out = nullptr;
+  const void* bias = nullptr;
+  const void* res = nullptr; int ldr = 0;
+  int k_splits = 1;
+  unsigned long long seed = 0; unsigned int stream = 0; float p_drop = 0.f;
+  float alpha = 1.f;
+};
+
+void gemm_bf16(const GemmCall& c, cudaStream_t st);
+
+CUtensorMap make_tmap_2d_bf16(const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                              uint32_t box_outer);
+
+}  // namespace b200

@@ -1,0 +1,504 @@
+// Bandwidth-bound kernels around the GEMMs: LayerNorm forward/backward (with the dropout-masked copy of
+// the gradient and all column reductions fused), embedding gather+LN+dropout forward and its backward
+// scatter, MLM position compaction / row gather / scatter, column sums for bias gradients.
+// (SURVEY.md K1-K3, K15, K18, K22 and their backward call sites; apex FusedLayerNorm contract N4:
+// fp32 statistics, eps inside the sqrt.)
+//
+// Layout: one warp per row, lane l owns columns {c*256 + l*8 .. +7}, so per-column reductions over rows
+// stay in registers of a fixed lane and 16-byte loads/stores are fully coalesced.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b200 {
+
+constexpr int LN_WARPS = 4;
+
+template <int CHUNKS>
+__device__ __forceinline__ void load_row(const __nv_bfloat16* p, int H, int lane, float (&v)[CHUNKS][8]) {
+#pragma unroll
+  for (int c = 0; c < CHUNKS; ++c) {
+    const int col = c * 256 + lane * 8;
+    if (col < H) {
+      const uint4 u = *reinterpret_cast<const uint4*>(p + col);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = unpack_bf16(w[t]);
+        v[c][2 * t] = f.x;
+        v[c][2 * t + 1] = f.y;
+      }
+    } else {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) v[c][t] = 0.f;
+    }
+  }
+}
+template <int CHUNKS>
+__device__ __forceinline__ void store_row(__nv_bfloat16* p, int H, int lane, const float (&v)[CHUNKS][8]) {
+#pragma unroll
+  for (int c = 0; c < CHUNKS; ++c) {
+    const int col = c * 256 + lane * 8;
+    if (col < H)
+      *reinterpret_cast<uint4*>(p + col) = make_uint4(pack_bf16(v[c][0], v[c][1]), pack_bf16(v[c][2], v[c][3]),
+                                                      pack_bf16(v[c][4], v[c][5]), pack_bf16(v[c][6], v[c][7]));
+  }
+}
+template <int CHUNKS>
+__device__ __forceinline__ void load_vec_f32(const float* p, int H, int lane, float (&v)[CHUNKS][8]) {
+#pragma unroll
+  for (int c = 0; c < CHUNKS; ++c) {
+    const int col = c * 256 + lane * 8;
+    if (col < H) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(p + col));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p + col + 4));
+      v[c][0] = a.x; v[c][1] = a.y; v[c][2] = a.z; v[c][3] = a.w;
+      v[c][4] = b.x; v[c][5] = b.y; v[c][6] = b.z; v[c][7] = b.w;
+    } else {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) v[c][t] = 0.f;
+    }
+  }
+}
+
+template <int CHUNKS>
+__device__ __forceinline__ void row_stats(const float (&x)[CHUNKS][8], int H, int lane, float eps, float& mean,
+                                          float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < CHUNKS; ++c)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) s += x[c][t];
+  mean = warp_sum(s) / (float)H;
+  float q = 0.f;
+#pragma unroll
+  for (int c = 0; c < CHUNKS; ++c) {
+    const int col = c * 256 + lane * 8;
+    if (col < H) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const float d = x[c][t] - mean;
+        q += d * d;
+      }
+    }
+  }
+  rstd = rsqrtf(warp_sum(q) / (float)H + eps);
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm forward:  y = (x - mean) * rstd * gamma + beta     (optionally followed by dropout)
+// ------------------------------------------------------------------------------------------------
+template <int CHUNKS>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+              __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int H,
+              float eps, unsigned long long seed, unsigned int stream, unsigned int thresh16, float drop_scale) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float g[CHUNKS][8], b[CHUNKS][8];
+  load_vec_f32<CHUNKS>(gamma, H, lane, g);
+  load_vec_f32<CHUNKS>(beta, H, lane, b);
+  for (int row = blockIdx.x * LN_WARPS + warp; row < M; row += gridDim.x * LN_WARPS) {
+    float v[CHUNKS][8];
+    load_row<CHUNKS>(x + (size_t)row * H, H, lane, v);
+    float mean, rstd;
+    row_stats<CHUNKS>(v, H, lane, eps, mean, rstd);
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+      const int col = c * 256 + lane * 8;
+      uint32_t keep = 0xFFu;
+      if (thresh16 != 0 && col < H)
+        keep = dropout_keep8(seed, stream, ((uint64_t)row * H + col) >> 3, thresh16);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        float o = (v[c][t] - mean) * rstd * g[c][t] + b[c][t];
+        if (thresh16 != 0) o = ((keep >> t) & 1u) ? o * drop_scale : 0.f;
+        v[c][t] = o;
+      }
+    }
+    store_row<CHUNKS>(y + (size_t)row * H, H, lane, v);
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward.
+//   in : dy [M,H] (grad wrt LN output; if out_drop_* given, dy is first multiplied by the *output* dropout
+//        mask of stream `in_stream` -- used by the embedding LN whose output was dropped out)
+//        x  [M,H] pre-LN input, mean/rstd [M], gamma [H]
+//   out: dx [M,H]          grad wrt the pre-LN input (this is also the residual-branch gradient)
+//        dxd [M,H] optional: dx * dropout_mask(stream `drop_stream`) * scale  -> gradient of the GEMM output
+//                            that was dropped out before the residual add (K14/K18)
+//        partial [grid, 3, H]: per-block column sums of (dy*xhat, dy, dxd) -> dgamma, dbeta, dbias
+// ------------------------------------------------------------------------------------------------
+template <int CHUNKS>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+              const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+              __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dxd, float* __restrict__ partial, int M,
+              int H, unsigned long long seed, unsigned int drop_stream, unsigned int in_stream,
+              unsigned int thresh16, float drop_scale) {
+  __shared__ float red[LN_WARPS][3][8 * 32];  // per warp: 3 quantities x (one chunk of 256 columns)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float g[CHUNKS][8];
+  load_vec_f32<CHUNKS>(gamma, H, lane, g);
+  float acc_g[CHUNKS][8], acc_b[CHUNKS][8], acc_d[CHUNKS][8];
+#pragma unroll
+  for (int c = 0; c < CHUNKS; ++c)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) acc_g[c][t] = acc_b[c][t] = acc_d[c][t] = 0.f;
+
+  for (int row = blockIdx.x * LN_WARPS + warp; row < M; row += gridDim.x * LN_WARPS) {
+    float d[CHUNKS][8], v[CHUNKS][8];
+    load_row<CHUNKS>(dy + (size_t)row * H, H, lane, d);
+    load_row<CHUNKS>(x + (size_t)row * H, H, lane, v);
+    const float mu = mean[row], rs = rstd[row];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+      const int col = c * 256 + lane * 8;
+      if (in_stream != 0xFFFFFFFFu && thresh16 != 0 && col < H) {
+        const uint32_t keep = dropout_keep8(seed, in_stream, ((uint64_t)row * H + col) >> 3, thresh16);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) d[c][t] = ((keep >> t) & 1u) ? d[c][t] * drop_scale : 0.f;
+      }
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const float xh = (v[c][t] - mu) * rs;
+        const float dg = d[c][t] * g[c][t];
+        acc_g[c][t] += d[c][t] * xh;
+        acc_b[c][t] += d[c][t];
+        v[c][t] = xh;
+        d[c][t] = dg;
+        s1 += dg;
+        s2 += dg * xh;
+      }
+    }
+    s1 = warp_sum(s1) / (float)H;
+    s2 = warp_sum(s2) / (float)H;
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c)
+#pragma unroll
+      for (int t = 0; t < 8; ++t) d[c][t] = rs * (d[c][t] - s1 - v[c][t] * s2);
+    store_row<CHUNKS>(dx + (size_t)row * H, H, lane, d);
+    if (dxd != nullptr) {
+#pragma unroll
+      for (int c = 0; c < CHUNKS; ++c) {
+        const int col = c * 256 + lane * 8;
+        if (thresh16 != 0 && col < H) {
+          const uint32_t keep = dropout_keep8(seed, drop_stream, ((uint64_t)row * H + col) >> 3, thresh16);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) d[c][t] = ((keep >> t) & 1u) ? d[c][t] * drop_scale : 0.f;
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) acc_d[c][t] += d[c][t];
+      }
+      store_row<CHUNKS>(dxd + (size_t)row * H, H, lane, d);
+    }
+  }
+  // block reduce the three column sums, one 256-column chunk at a time
+#pragma unroll
+  for (int c = 0; c < CHUNKS; ++c) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      red[warp][0][lane * 8 + t] = acc_g[c][t];
+      red[warp][1][lane * 8 + t] = acc_b[c][t];
+      red[warp][2][lane * 8 + t] = acc_d[c][t];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * 256; i += LN_WARPS * 32) {
+      const int qn = i / 256, cc = i % 256;
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < LN_WARPS; ++w) s += red[w][qn][cc];
+      const int col = c * 256 + cc;
+      if (col < H) partial[((size_t)blockIdx.x * 3 + qn) * H + col] = s;
+    }
+    __syncthreads();
+  }
+}
+
+// dst[k][col] += sum over blocks of partial[block][k][col]   (k = 0..2, any dst may be null)
+__global__ void colsum_finalize_kernel(const float* __restrict__ partial, int nblocks, int H, float* dgamma,
+                                       float* dbeta, float* dbias) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const int qn = blockIdx.y;
+  float* dst = qn == 0 ? dgamma : (qn == 1 ? dbeta : dbias);
+  if (col >= H || dst == nullptr) return;
+  float s = 0.f;
+  for (int b = 0; b < nblocks; ++b) s += partial[((size_t)b * 3 + qn) * H + col];
+  dst[col] += s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// column sum of a bf16 matrix into an fp32 vector (bias gradients): out[n] += sum_m x[m][n]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int M, int N, int ld,
+                                                         float* __restrict__ out) {
+  // block: 32 column-groups (8 cols each = 256 columns) x 8 row lanes
+  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int col = blockIdx.x * 256 + cg * 8;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (col < N) {
+    for (int row = blockIdx.y * 8 + rl; row < M; row += gridDim.y * 8) {
+      const uint4 u = *reinterpret_cast<const uint4*>(x + (size_t)row * ld + col);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = unpack_bf16(w[t]);
+        acc[2 * t] += f.x;
+        acc[2 * t + 1] += f.y;
+      }
+    }
+  }
+  __shared__ float sm[8][256];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) sm[rl][cg * 8 + t] = acc[t];
+  __syncthreads();
+  const int c = threadIdx.x;
+  float s = 0.f;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) s += sm[r][c];
+  if (blockIdx.x * 256 + c < N) atomicAdd(out + blockIdx.x * 256 + c, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Embedding forward: e = word[id] + pos[s] (+ type[seg]); y = dropout(LN(e)); saves e, mean, rstd
+// ------------------------------------------------------------------------------------------------
+template <int CHUNKS>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+embed_fwd_kernel(const int* __restrict__ ids, const int* __restrict__ seg, const __nv_bfloat16* __restrict__ word,
+                 const __nv_bfloat16* __restrict__ pos, const __nv_bfloat16* __restrict__ type,
+                 const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ e_out,
+                 __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int M,
+                 int S, int H, float eps, unsigned long long seed, unsigned int stream, unsigned int thresh16,
+                 float drop_scale) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float g[CHUNKS][8], b[CHUNKS][8];
+  load_vec_f32<CHUNKS>(gamma, H, lane, g);
+  load_vec_f32<CHUNKS>(beta, H, lane, b);
+  for (int row = blockIdx.x * LN_WARPS + warp; row < M; row += gridDim.x * LN_WARPS) {
+    float v[CHUNKS][8], t0[CHUNKS][8];
+    load_row<CHUNKS>(word + (size_t)ids[row] * H, H, lane, v);
+    load_row<CHUNKS>(pos + (size_t)(row % S) * H, H, lane, t0);
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c)
+#pragma unroll
+      for (int t = 0; t < 8; ++t) v[c][t] += t0[c][t];
+    if (type != nullptr) {
+      load_row<CHUNKS>(type + (size_t)seg[row] * H, H, lane, t0);
+#pragma unroll
+      for (int c = 0; c < CHUNKS; ++c)
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[c][t] += t0[c][t];
+    }
+    // round the sum to bf16 first so the saved copy and the statistics agree exactly
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c)
+#pragma unroll
+      for (int t = 0; t < 8; ++t) v[c][t] = __bfloat162float(__float2bfloat16(v[c][t]));
+    store_row<CHUNKS>(e_out + (size_t)row * H, H, lane, v);
+    float mean, rstd;
+    row_stats<CHUNKS>(v, H, lane, eps, mean, rstd);
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+      const int col = c * 256 + lane * 8;
+      uint32_t keep = 0xFFu;
+      if (thresh16 != 0 && col < H) keep = dropout_keep8(seed, stream, ((uint64_t)row * H + col) >> 3, thresh16);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        float o = (v[c][t] - mean) * rstd * g[c][t] + b[c][t];
+        if (thresh16 != 0) o = ((keep >> t) & 1u) ? o * drop_scale : 0.f;
+        v[c][t] = o;
+      }
+    }
+    store_row<CHUNKS>(y + (size_t)row * H, H, lane, v);
+    if (lane == 0) {
+      mean_out[row] = mean;
+      rstd_out[row] = rstd;
+    }
+  }
+}
+
+// Embedding backward scatter: de [M,H] (bf16) is added into the fp32 gradient tables.
+__global__ void __launch_bounds__(256)
+embed_bwd_scatter_kernel(const __nv_bfloat16* __restrict__ de, const int* __restrict__ ids,
+                         const int* __restrict__ seg, float* __restrict__ gword, float* __restrict__ gpos,
+                         float* __restrict__ gtype, int M, int S, int H) {
+  const int per_row = H / 8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)M * per_row;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int row = (int)(i / per_row), col = (int)(i % per_row) * 8;
+    const uint4 u = *reinterpret_cast<const uint4*>(de + (size_t)row * H + col);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    float f[8];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 p = unpack_bf16(w[t]);
+      f[2 * t] = p.x;
+      f[2 * t + 1] = p.y;
+    }
+    float* dst[3] = {gword + (size_t)ids[row] * H + col, gpos + (size_t)(row % S) * H + col,
+                     gtype ? gtype + (size_t)seg[row] * H + col : nullptr};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (dst[k] == nullptr) continue;
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst[k]), "f"(f[0]), "f"(f[1]), "f"(f[2]),
+                   "f"(f[3]) : "memory");
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst[k] + 4), "f"(f[4]), "f"(f[5]),
+                   "f"(f[6]), "f"(f[7]) : "memory");
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// MLM position compaction: per sequence, the positions with label >= 0 (at most max_pred) are written to
+// idx[b*max_pred + j] (global row index b*S+s), the tail is -1; tgt gets the labels (-1 tail);
+// count accumulates the number of valid targets.  Deterministic order (ascending position).
+// ------------------------------------------------------------------------------------------------
+__global__ void mlm_compact_kernel(const int* __restrict__ labels, int S, int max_pred, int* __restrict__ idx,
+                                   int* __restrict__ tgt, int* __restrict__ count) {
+  const int b = blockIdx.x;
+  __shared__ int n;
+  if (threadIdx.x == 0) n = 0;
+  __syncthreads();
+  // single warp, ordered compaction with ballots
+  const int lane = threadIdx.x;
+  int base = 0;
+  for (int s0 = 0; s0 < S; s0 += 32) {
+    const int s = s0 + lane;
+    const int lab = s < S ? labels[b * S + s] : -1;
+    const unsigned m = __ballot_sync(0xffffffffu, lab >= 0);
+    if (lab >= 0) {
+      const int j = base + __popc(m & ((1u << lane) - 1));
+      if (j < max_pred) {
+        idx[b * max_pred + j] = b * S + s;
+        tgt[b * max_pred + j] = lab;
+      }
+    }
+    base += __popc(m);
+  }
+  const int valid = min(base, max_pred);
+  for (int j = valid + lane; j < max_pred; j += 32) {
+    idx[b * max_pred + j] = -1;
+    tgt[b * max_pred + j] = -1;
+  }
+  if (lane == 0) atomicAdd(count, valid);
+}
+
+// rows[i] = src[idx[i]] (zeros when idx < 0)
+__global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ src, const int* __restrict__ idx,
+                                   __nv_bfloat16* __restrict__ dst, int n, int H) {
+  const int per_row = H / 8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)n * per_row;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / per_row), col = (int)(i % per_row) * 8;
+    const int s = idx[r];
+    uint4 u = make_uint4(0, 0, 0, 0);
+    if (s >= 0) u = *reinterpret_cast<const uint4*>(src + (size_t)s * H + col);
+    *reinterpret_cast<uint4*>(dst + (size_t)r * H + col) = u;
+  }
+}
+// dst[idx[i]] = src[i]  (dst pre-zeroed, indices unique)
+__global__ void scatter_rows_kernel(const __nv_bfloat16* __restrict__ src, const int* __restrict__ idx,
+                                    __nv_bfloat16* __restrict__ dst, int n, int H) {
+  const int per_row = H / 8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)n * per_row;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / per_row), col = (int)(i % per_row) * 8;
+    const int s = idx[r];
+    if (s >= 0) *reinterpret_cast<uint4*>(dst + (size_t)s * H + col) = *reinterpret_cast<const uint4*>(src + (size_t)r * H + col);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+static inline void drop_params(float p, unsigned int& thresh, float& scale) {
+  thresh = p > 0.f ? (unsigned)(p * 65536.f + 0.5f) : 0u;
+  scale = p > 0.f ? 65536.f / (65536.f - (float)thresh) : 1.f;
+}
+static inline int ln_grid(int M) {
+  int g = (M + LN_WARPS - 1) / LN_WARPS;
+  return g < 148 * 8 ? g : 148 * 8;
+}
+
+#define DISPATCH_CHUNKS(H, ...)                                    \
+  do {                                                             \
+    const int chunks_ = ((H) + 255) / 256;                         \
+    if (chunks_ <= 1) { constexpr int CH = 1; __VA_ARGS__; }       \
+    else if (chunks_ <= 2) { constexpr int CH = 2; __VA_ARGS__; }  \
+    else if (chunks_ <= 3) { constexpr int CH = 3; __VA_ARGS__; }  \
+    else if (chunks_ <= 4) { constexpr int CH = 4; __VA_ARGS__; }  \
+    else if (chunks_ <= 8) { constexpr int CH = 8; __VA_ARGS__; }  \
+    else { fprintf(stderr, "[b200] hidden size %d too large for the LN kernels\n", (H)); abort(); } \
+  } while (0)
+
+void layer_norm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int M,
+                    int H, float eps, unsigned long long seed, unsigned int stream, float p_drop, cudaStream_t st) {
+  unsigned int th; float sc;
+  drop_params(p_drop, th, sc);
+  DISPATCH_CHUNKS(H, (ln_fwd_kernel<CH><<<ln_grid(M), LN_WARPS * 32, 0, st>>>(
+      (const __nv_bfloat16*)x, gamma, beta, (__nv_bfloat16*)y, mean, rstd, M, H, eps, seed, stream, th, sc)));
+}
+
+int ln_bwd_workspace_floats(int M, int H) { return ln_grid(M) > 592 ? 592 * 3 * H : ln_grid(M) * 3 * H; }
+
+void layer_norm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
+                    void* dxd, float* dgamma, float* dbeta, float* dbias, float* workspace, int M, int H,
+                    unsigned long long seed, unsigned int drop_stream, unsigned int in_stream, float p_drop,
+                    cudaStream_t st) {
+  unsigned int th; float sc;
+  drop_params(p_drop, th, sc);
+  int grid = ln_grid(M);
+  if (grid > 592) grid = 592;  // 4 blocks/SM; keeps the partial buffer small
+  DISPATCH_CHUNKS(H, (ln_bwd_kernel<CH><<<grid, LN_WARPS * 32, 0, st>>>(
+      (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, gamma, (__nv_bfloat16*)dx, (__nv_bfloat16*)dxd,
+      workspace, M, H, seed, drop_stream, in_stream, th, sc)));
+  dim3 g2((H + 127) / 128, 3);
+  colsum_finalize_kernel<<<g2, 128, 0, st>>>(workspace, grid, H, dgamma, dbeta, dxd ? dbias : nullptr);
+}
+
+void colsum_bf16(const void* x, int M, int N, int ld, float* out, cudaStream_t st) {
+  dim3 grid((N + 255) / 256, M >= 4096 ? 64 : (M >= 512 ? 16 : 1));
+  colsum_bf16_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, M, N, ld, out);
+}
+
+void embedding_fwd(const int* ids, const int* seg, const void* word, const void* pos, const void* type,
+                   const float* gamma, const float* beta, void* e_out, void* y, float* mean, float* rstd, int M, int S,
+                   int H, float eps, unsigned long long seed, unsigned int stream, float p_drop, cudaStream_t st) {
+  unsigned int th; float sc;
+  drop_params(p_drop, th, sc);
+  DISPATCH_CHUNKS(H, (embed_fwd_kernel<CH><<<ln_grid(M), LN_WARPS * 32, 0, st>>>(
+      ids, seg, (const __nv_bfloat16*)word, (const __nv_bfloat16*)pos, (const __nv_bfloat16*)type, gamma, beta,
+      (__nv_bfloat16*)e_out, (__nv_bfloat16*)y, mean, rstd, M, S, H, eps, seed, stream, th, sc)));
+}
+
+void embedding_bwd_scatter(const void* de, const int* ids, const int* seg, float* gword, float* gpos, float* gtype,
+                           int M, int S, int H, cudaStream_t st) {
+  const size_t work = (size_t)M * (H / 8);
+  int grid = (int)((work + 255) / 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  embed_bwd_scatter_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)de, ids, seg, gword, gpos, gtype, M, S, H);
+}
+
+void mlm_compact(const int* labels, int B, int S, int max_pred, int* idx, int* tgt, int* count, cudaStream_t st) {
+  B200_CUDA_CHECK(cudaMemsetAsync(count, 0, sizeof(int), st));
+  mlm_compact_kernel<<<B, 32, 0, st>>>(labels, S, max_pred, idx, tgt, count);
+}
+
+void gather_rows(const void* src, const int* idx, void* dst, int n, int H, cudaStream_t st) {
+  const size_t work = (size_t)n * (H / 8);
+  int grid = (int)((work + 255) / 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  if (grid > 0) gather_rows_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, idx, (__nv_bfloat16*)dst, n, H);
+}
+void scatter_rows(const void* src, const int* idx, void* dst, int n, int H, cudaStream_t st) {
+  const size_t work = (size_t)n * (H / 8);
+  int grid = (int)((work + 255) / 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  if (grid > 0) scatter_rows_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, idx, (__nv_bfloat16*)dst, n, H);
+}
+
+}  // namespace b200

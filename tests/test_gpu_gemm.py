@@ -1,0 +1,92 @@
+"""tcgen05 GEMM vs a plain fp32 PyTorch reference of the same op (T3 of SURVEY.md 4.2)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from bert_pytorch_b200 import ops
+    from bert_pytorch_b200.ops import api
+    assert ops.available()
+    return api
+
+
+def _rand(*shape, scale=1.0):
+    return (torch.randn(*shape, device="cuda") * scale).to(torch.bfloat16)
+
+
+def _check(out, ref, tol=2e-2):
+    out, ref = out.float(), ref.float()
+    err = (out - ref).abs().max().item()
+    denom = ref.abs().max().item() + 1e-6
+    assert err / denom < tol, f"max abs err {err} vs ref scale {denom}"
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 128), (384, 1024, 1024), (1000, 512, 320),
+                                   (4096, 3072, 1024), (130, 264, 72)])
+@pytest.mark.parametrize("block_n", [128, 256])
+def test_gemm_nt(M, N, K, block_n):
+    K_ = _ops()
+    a, b = _rand(M, K), _rand(N, K)
+    out = K_.gemm(a, b, layout=K_.NT, block_n=block_n)
+    _check(out, a.float() @ b.float().t())
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (512, 1024, 4096), (1000, 320, 512)])
+@pytest.mark.parametrize("block_n", [128, 256])
+def test_gemm_nn(M, N, K, block_n):
+    K_ = _ops()
+    a, b = _rand(M, K), _rand(K, N)
+    out = K_.gemm(a, b, layout=K_.NN, block_n=block_n)
+    _check(out, a.float() @ b.float())
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (1024, 1024, 4096), (320, 520, 1000)])
+@pytest.mark.parametrize("block_n,splits", [(128, 1), (256, 1), (256, 4)])
+def test_gemm_tn_accumulate(M, N, K, block_n, splits):
+    K_ = _ops()
+    a, b = _rand(K, M), _rand(K, N)
+    base = torch.randn(M, N, device="cuda")
+    out = base.clone()
+    K_.gemm(a, b, layout=K_.TN, epi=K_.EPI_ACCUM_F32, out=out, block_n=block_n, k_splits=splits)
+    _check(out, base + a.float().t() @ b.float(), tol=1e-2)
+
+
+def test_gemm_epilogues():
+    K_ = _ops()
+    M, N, Kd = 512, 1024, 256
+    a, b, bias, res = _rand(M, Kd), _rand(N, Kd), _rand(N), _rand(M, N)
+    ref = a.float() @ b.float().t()
+    _check(K_.gemm(a, b, epi=K_.EPI_BIAS, bias=bias), ref + bias.float())
+    aux = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    out = K_.gemm(a, b, epi=K_.EPI_BIAS_GELU, bias=bias, aux_out=aux)
+    _check(aux, ref + bias.float())
+    _check(out, torch.nn.functional.gelu(ref + bias.float()))
+    _check(K_.gemm(a, b, epi=K_.EPI_BIAS_DROP_RES, bias=bias, res=res, p_drop=0.0), ref + bias.float() + res.float())
+    _check(K_.gemm(a, b, epi=K_.EPI_ADD, res=res), ref + res.float())
+    pre = _rand(M, N)
+    x = pre.float().requires_grad_(True)
+    torch.nn.functional.gelu(x).sum().backward()
+    _check(K_.gemm(a, b, epi=K_.EPI_DGELU, res=pre), ref * x.grad)
+    _check(K_.gemm(a, b, epi=K_.EPI_BIAS_TANH, bias=bias), torch.tanh(ref + bias.float()))
+    _check(K_.gemm(a, b, epi=K_.EPI_F32), ref, tol=5e-3)
+
+
+def test_gemm_dropout_statistics_and_determinism():
+    K_ = _ops()
+    M, N, Kd = 1024, 1024, 64
+    a, b, bias = _rand(M, Kd), _rand(N, Kd), torch.zeros(N, device="cuda", dtype=torch.bfloat16)
+    res = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    full = K_.gemm(a, b, epi=K_.EPI_BIAS, bias=bias).float()
+    d1 = K_.gemm(a, b, epi=K_.EPI_BIAS_DROP_RES, bias=bias, res=res, p_drop=0.1, seed=123, stream=5).float()
+    d2 = K_.gemm(a, b, epi=K_.EPI_BIAS_DROP_RES, bias=bias, res=res, p_drop=0.1, seed=123, stream=5).float()
+    d3 = K_.gemm(a, b, epi=K_.EPI_BIAS_DROP_RES, bias=bias, res=res, p_drop=0.1, seed=124, stream=5).float()
+    assert torch.equal(d1, d2)
+    assert not torch.equal(d1, d3)
+    kept = d1 != 0
+    frac = 1.0 - kept.float().mean().item()
+    assert abs(frac - 0.1) < 0.01, frac
+    assert torch.allclose(d1[kept], full[kept] / 0.9, rtol=2e-2, atol=2e-2)

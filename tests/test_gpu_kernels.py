@@ -1,0 +1,255 @@
+"""Bandwidth-bound kernels, optimizer kernels and the fused engine vs PyTorch fp32 references."""
+import copy
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _api():
+    from bert_pytorch_b200 import ops
+    from bert_pytorch_b200.ops import api
+    assert ops.available()
+    return api
+
+
+@pytest.mark.parametrize("M,H", [(64, 64), (1000, 1024), (300, 768), (130, 256)])
+def test_layer_norm_fwd_bwd(M, H):
+    K = _api()
+    x = (torch.randn(M, H, device="cuda") * 2 + 0.5).to(torch.bfloat16)
+    g = torch.randn(H, device="cuda") * 0.5 + 1.0
+    b = torch.randn(H, device="cuda") * 0.1
+    dy = torch.randn(M, H, device="cuda").to(torch.bfloat16)
+    y, mean, rstd = K.layer_norm_fwd(x, g, b)
+    xr = x.float().requires_grad_(True)
+    gr, br = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = F.layer_norm(xr, (H,), gr, br, eps=1e-12)
+    assert (y.float() - yr).abs().max() < 3e-2
+    yr.backward(dy.float())
+    dg, db, dbias = torch.zeros(H, device="cuda"), torch.zeros(H, device="cuda"), torch.zeros(H, device="cuda")
+    dx, dxd = K.layer_norm_bwd(dy, x, mean, rstd, g, dgamma=dg, dbeta=db, dbias=dbias, want_dropped=True, p_drop=0.0)
+    assert (dx.float() - xr.grad).abs().max() < 3e-2 * max(1.0, xr.grad.abs().max().item())
+    assert torch.equal(dx, dxd)
+    assert torch.allclose(dg, gr.grad, rtol=2e-2, atol=2e-1)
+    assert torch.allclose(db, br.grad, rtol=2e-2, atol=2e-1)
+    assert torch.allclose(dbias, dx.float().sum(0), rtol=2e-2, atol=2e-1)
+
+
+def test_layer_norm_dropout_mask_consistency():
+    """The LN-backward dropped gradient must use the same mask as the GEMM epilogue of the forward."""
+    K = _api()
+    M, H = 512, 1024
+    a = torch.randn(M, 64, device="cuda").to(torch.bfloat16)
+    w = torch.randn(H, 64, device="cuda").to(torch.bfloat16)
+    zeros_b = torch.zeros(H, device="cuda", dtype=torch.bfloat16)
+    res = torch.zeros(M, H, device="cuda", dtype=torch.bfloat16)
+    fwd = K.gemm(a, w, epi=K.EPI_BIAS_DROP_RES, bias=zeros_b, res=res, p_drop=0.1, seed=77, stream=19)
+    x = torch.randn(M, H, device="cuda").to(torch.bfloat16)
+    g = torch.ones(H, device="cuda")
+    y, mean, rstd = K.layer_norm_fwd(x, g, torch.zeros(H, device="cuda"))
+    dy = torch.randn(M, H, device="cuda").to(torch.bfloat16)
+    dx, dxd = K.layer_norm_bwd(dy, x, mean, rstd, g, dgamma=None, dbeta=None, dbias=None, want_dropped=True,
+                               p_drop=0.1, seed=77, drop_stream=19)
+    kept_fwd = fwd != 0
+    kept_bwd = dxd != 0
+    # identical masks wherever neither value is an exact zero by accident
+    assert (kept_fwd ^ kept_bwd).float().mean().item() < 1e-3
+
+
+def test_embedding_fwd_bwd():
+    K = _api()
+    B, S, H, V = 4, 32, 256, 1000
+    word = torch.randn(V, H, device="cuda").to(torch.bfloat16)
+    pos = torch.randn(64, H, device="cuda").to(torch.bfloat16)
+    typ = torch.randn(2, H, device="cuda").to(torch.bfloat16)
+    g, b = torch.rand(H, device="cuda") + 0.5, torch.randn(H, device="cuda") * 0.1
+    ids = torch.randint(0, V, (B * S,), device="cuda", dtype=torch.int32)
+    seg = torch.randint(0, 2, (B * S,), device="cuda", dtype=torch.int32)
+    y, e, mean, rstd = K.embedding_fwd(ids, seg, word, pos, typ, g, b, S)
+    posi = torch.arange(S, device="cuda").repeat(B)
+    er = word.float()[ids.long()] + pos.float()[posi] + typ.float()[seg.long()]
+    assert (e.float() - er).abs().max() < 5e-2
+    yr = F.layer_norm(e.float(), (H,), g, b, eps=1e-12)
+    assert (y.float() - yr).abs().max() < 3e-2
+    de = torch.randn(B * S, H, device="cuda").to(torch.bfloat16)
+    gw, gp, gt = torch.zeros(V, H, device="cuda"), torch.zeros(64, H, device="cuda"), torch.zeros(2, H, device="cuda")
+    K.embedding_bwd_scatter(de, ids, seg, gw, gp, gt, S)
+    rw = torch.zeros_like(gw).index_add_(0, ids.long(), de.float())
+    rp = torch.zeros_like(gp).index_add_(0, posi, de.float())
+    rt = torch.zeros_like(gt).index_add_(0, seg.long(), de.float())
+    assert torch.allclose(gw, rw, atol=1e-3) and torch.allclose(gp, rp, atol=1e-3) and torch.allclose(gt, rt, atol=1e-2)
+
+
+def test_mlm_compact_gather_scatter_ce():
+    K = _api()
+    B, S, H, V, MP = 6, 64, 128, 2048, 16
+    labels = torch.full((B, S), -1, device="cuda", dtype=torch.int32)
+    for b in range(B):
+        n = 3 + b * 2
+        p = torch.randperm(S, device="cuda")[:n]
+        labels[b, p] = torch.randint(0, V, (n,), device="cuda", dtype=torch.int32)
+    idx, tgt, count = K.mlm_compact(labels, MP)
+    assert int(count) == int((labels >= 0).sum())
+    flat = labels.view(-1)
+    valid = idx >= 0
+    assert torch.equal(flat[idx[valid].long()], tgt[valid])
+    assert (tgt[~valid] == -1).all()
+    seq = torch.randn(B * S, H, device="cuda").to(torch.bfloat16)
+    rows = K.gather_rows(seq, idx)
+    assert torch.equal(rows[valid], seq[idx[valid].long()])
+    assert (rows[~valid] == 0).all()
+    back = torch.zeros_like(seq)
+    K.scatter_rows(rows, idx, back)
+    assert torch.equal(back[idx[valid].long()], rows[valid])
+    # CE
+    logits = (torch.randn(B * MP, V, device="cuda") * 3).to(torch.bfloat16)
+    ref_in = logits.float().requires_grad_(True)
+    ref = F.cross_entropy(ref_in, tgt.long(), ignore_index=-1)
+    (ref * 4.0).backward()
+    loss = torch.zeros(1, device="cuda")
+    K.softmax_ce_(logits, tgt, count, 4.0, loss)
+    assert abs(loss.item() - ref.item()) < 2e-2 * max(1.0, abs(ref.item()))
+    assert (logits.float() - ref_in.grad).abs().max() < 2e-3
+
+
+def test_colsum():
+    K = _api()
+    x = torch.randn(5000, 1000 + 24, device="cuda").to(torch.bfloat16)
+    out = torch.ones(x.size(1), device="cuda")
+    K.colsum_accumulate(x, out)
+    assert torch.allclose(out, 1 + x.float().sum(0), rtol=1e-3, atol=1e-2)
+
+
+def test_multi_tensor_l2norm_scale():
+    K = _api()
+    ts = [torch.randn(n, device="cuda") for n in (7, 70000, 1024, 333333)] + \
+         [torch.randn(5000, device="cuda").to(torch.bfloat16)]
+    total, per = K.multi_tensor_l2norm(ts, per_tensor=True)
+    ref = torch.stack([t.float().norm() for t in ts])
+    assert torch.allclose(per, ref, rtol=1e-3)
+    assert abs(total.item() - ref.norm().item()) < 1e-2
+    outs = [torch.empty_like(t) for t in ts]
+    flag = K.multi_tensor_scale(ts, outs, 0.5)
+    assert int(flag) == 0
+    for t, o in zip(ts, outs):
+        assert torch.allclose(o.float(), t.float() * 0.5, rtol=1e-2, atol=1e-3)
+    ts[1][5] = float("inf")
+    assert int(K.multi_tensor_scale(ts, outs, 0.5)) == 1
+
+
+def _tiny_model(hidden=128, layers=2, heads=2, inter=256, vocab=1024, drop=0.0, nsp=True):
+    from bert_pytorch_b200 import BertConfig
+    from bert_pytorch_b200.models import BertForPreTraining
+    cfg = BertConfig(vocab_size_or_config_json_file=vocab, hidden_size=hidden, num_hidden_layers=layers,
+                     num_attention_heads=heads, intermediate_size=inter, max_position_embeddings=128,
+                     hidden_dropout_prob=drop, attention_probs_dropout_prob=drop, next_sentence=nsp)
+    cfg.max_predictions_per_seq = 16
+    torch.manual_seed(0)
+    return BertForPreTraining(cfg)
+
+
+def _batch(B=4, S=64, V=1024, MP=10):
+    torch.manual_seed(1)
+    ids = torch.randint(5, V, (B, S), device="cuda")
+    seg = torch.zeros_like(ids)
+    seg[:, S // 2:] = 1
+    lens = torch.tensor([S, S - 7, S // 2, S - 1], device="cuda")[:B]
+    mask = (torch.arange(S, device="cuda")[None] < lens[:, None]).long()
+    labels = torch.full((B, S), -1, device="cuda")
+    for b in range(B):
+        p = torch.randperm(int(lens[b]), device="cuda")[:MP]
+        labels[b, p] = ids[b, p]
+    nsl = torch.randint(0, 2, (B,), device="cuda")
+    return ids, seg, mask, labels, nsl
+
+
+@pytest.mark.parametrize("opt", ["lamb", "adam"])
+def test_arena_optimizers_match_reference(opt):
+    from bert_pytorch_b200.models.arena import ParamArena
+    from bert_pytorch_b200.optim import Adam, Lamb
+    m_ref = _tiny_model().cuda()
+    m_fused = copy.deepcopy(m_ref)
+    def groups(m):
+        named = list(m.named_parameters())
+        nd = ("bias", "LayerNorm")
+        return [{"params": [p for n, p in named if not any(k in n for k in nd)], "weight_decay": 0.01},
+                {"params": [p for n, p in named if any(k in n for k in nd)], "weight_decay": 0.0}]
+    cls = Lamb if opt == "lamb" else Adam
+    kw = dict(lr=1e-2) if opt == "lamb" else dict(lr=1e-3, bias_correction=False)
+    o_ref = cls(groups(m_ref), **kw)
+    arena = ParamArena(m_fused)
+    o_fused = cls(groups(m_fused), **kw)
+    arena.bind_optimizer(o_fused)
+    assert arena.fused_optimizer_ok()
+    for step in range(3):
+        torch.manual_seed(step)
+        for p_r, p_f in zip(m_ref.parameters(), m_fused.parameters()):
+            g = torch.randn_like(p_r) * (10.0 if step == 1 else 0.1)
+            p_r.grad = g.clone()
+            p_f.grad.copy_(g)
+        o_ref.step()
+        o_fused.step()
+        for (n, p_r), p_f in zip(m_ref.named_parameters(), m_fused.parameters()):
+            assert torch.allclose(p_r, p_f, rtol=1e-4, atol=1e-6), (opt, step, n, (p_r - p_f).abs().max().item())
+        assert float(arena.flat_grad.abs().max()) == 0.0
+        assert torch.allclose(arena.flat_shadow.float(), arena.flat_param, rtol=1e-2, atol=1e-3)
+    assert o_fused.param_groups[0]["step"] == 3
+
+
+def test_fused_pretrainer_matches_oracle():
+    """Loss and every parameter gradient of the fused kernel program vs fp32 autograd on the same weights
+    (dropout off)."""
+    from bert_pytorch_b200.models import BertPretrainingCriterion
+    from bert_pytorch_b200.models.arena import ParamArena
+    model = _tiny_model().cuda()
+    arena = ParamArena(model)
+    batch = _batch()
+    ids, seg, mask, labels, nsl = batch
+    # oracle: fp32 autograd through the nn.Module forward, on bf16-rounded weights
+    oracle = copy.deepcopy(model)
+    for p in oracle.parameters():
+        p.data = p.data.to(torch.bfloat16).float()
+    oracle.bert.use_fused = False
+    crit = BertPretrainingCriterion(model.config.vocab_size)
+    scores, nsp = oracle(ids, seg, mask)
+    ref_loss = crit(scores, labels, nsp, nsl)
+    ref_loss.backward()
+    eng = model.pretrain_engine()
+    assert eng is not None
+    arena.zero_grad()
+    loss = eng.forward_backward(ids, seg, mask, labels, nsl, grad_scale=1.0)
+    assert abs(loss.item() - ref_loss.item()) < 3e-2 * abs(ref_loss.item()), (loss.item(), ref_loss.item())
+    bad = []
+    for (n, p), po in zip(model.named_parameters(), oracle.parameters()):
+        g, go = p.grad.float(), po.grad.float()
+        denom = go.abs().max().item() + 1e-6
+        rel = (g - go).abs().max().item() / denom
+        if rel > 8e-2:
+            bad.append((n, rel, denom))
+    assert not bad, bad[:10]
+
+
+def test_encoder_autograd_bridge_matches_oracle():
+    from bert_pytorch_b200 import BertConfig
+    from bert_pytorch_b200.models import BertForQuestionAnswering
+    cfg = BertConfig(vocab_size_or_config_json_file=1024, hidden_size=128, num_hidden_layers=2, num_attention_heads=2,
+                     intermediate_size=256, max_position_embeddings=128, hidden_dropout_prob=0.0,
+                     attention_probs_dropout_prob=0.0)
+    torch.manual_seed(0)
+    model = BertForQuestionAnswering(cfg).cuda()
+    oracle = copy.deepcopy(model)
+    for p in oracle.parameters():
+        p.data = p.data.to(torch.bfloat16).float()
+    oracle.bert.use_fused = False
+    ids, seg, mask, _, _ = _batch()
+    s, e = model(ids, seg, mask)
+    so, eo = oracle(ids, seg, mask)
+    assert (s - so).abs().max() < 5e-2 and (e - eo).abs().max() < 5e-2
+    (s.sum() + e.sum()).backward()
+    (so.sum() + eo.sum()).backward()
+    w, wo = model.bert.encoder.layer[0].output.dense.weight, oracle.bert.encoder.layer[0].output.dense.weight
+    rel = (w.grad - wo.grad).abs().max() / (wo.grad.abs().max() + 1e-6)
+    assert rel < 8e-2, rel

@@ -1,0 +1,65 @@
+"""Device-timed throughput of the tcgen05 GEMM on the BERT-large shapes vs torch.matmul (cuBLAS) ->
+gpurun_out/gemm_bench.json.  CUDA events, warm-up, L2 flush between iterations."""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bert_pytorch_b200.ops import api as K  # noqa: E402
+
+
+def timeit(fn, iters=20, warm=5):
+    flush = torch.empty(64 << 20, dtype=torch.float32, device="cuda")
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        flush.fill_(0.0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def main():
+    M = 12288
+    out = []
+    shapes = [("qkv_fwd", K.NT, M, 3072, 1024), ("attn_out_fwd", K.NT, M, 1024, 1024), ("ffn1_fwd", K.NT, M, 4096, 1024),
+              ("ffn2_fwd", K.NT, M, 1024, 4096), ("ffn1_dgrad", K.NN, M, 1024, 4096), ("ffn2_dgrad", K.NN, M, 4096, 1024),
+              ("ffn1_wgrad", K.TN, 4096, 1024, M), ("ffn2_wgrad", K.TN, 1024, 4096, M), ("qkv_wgrad", K.TN, 3072, 1024, M),
+              ("decoder_fwd", K.NT, 1920, 30528, 1024), ("big", K.NT, 8192, 8192, 8192)]
+    for name, layout, m, n, k in shapes:
+        if layout == K.NT:
+            a, b = torch.randn(m, k, device="cuda").bfloat16(), torch.randn(n, k, device="cuda").bfloat16()
+            ref = lambda: a @ b.t()
+        elif layout == K.NN:
+            a, b = torch.randn(m, k, device="cuda").bfloat16(), torch.randn(k, n, device="cuda").bfloat16()
+            ref = lambda: a @ b
+        else:
+            a, b = torch.randn(k, m, device="cuda").bfloat16(), torch.randn(k, n, device="cuda").bfloat16()
+            ref = lambda: a.t() @ b
+        flops = 2.0 * m * n * k
+        rec = {"name": name, "M": m, "N": n, "K": k}
+        t_ref = timeit(ref)
+        rec["cublas_ms"], rec["cublas_tflops"] = round(t_ref, 4), round(flops / t_ref / 1e9, 1)
+        for bn in (128, 256):
+            if layout == K.TN:
+                o = torch.zeros(m, n, device="cuda")
+                for sp in (1, 2, 4, 8):
+                    t = timeit(lambda: K.gemm(a, b, layout=layout, epi=K.EPI_ACCUM_F32, out=o, block_n=bn, k_splits=sp))
+                    rec[f"ours_bn{bn}_s{sp}_tflops"] = round(flops / t / 1e9, 1)
+            else:
+                o = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
+                t = timeit(lambda: K.gemm(a, b, layout=layout, out=o, block_n=bn))
+                rec[f"ours_bn{bn}_ms"], rec[f"ours_bn{bn}_tflops"] = round(t, 4), round(flops / t / 1e9, 1)
+        out.append(rec)
+        print(json.dumps(rec), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,25 @@
+#!/bin/bash
+# One gpurun call = the whole GPU check list; each stage in its own process (a CUDA trap poisons only its
+# own context) under its own timeout; everything lands in gpurun_out/.
+# usage: tools/gpu_suite.sh [stages...]   stages: gemm kernels bench ref ncu
+set -u
+mkdir -p gpurun_out
+STAGES="${@:-gemm kernels bench ref}"
+export PYTHONUNBUFFERED=1
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.used --format=csv > gpurun_out/smi.txt 2>&1
+for s in $STAGES; do
+  case $s in
+    gemm)    timeout 600 python -m pytest tests/test_gpu_gemm.py -m gpu -q -x --timeout 300 > gpurun_out/test_gemm.log 2>&1; echo "gemm rc=$?" ;;
+    gemmall) timeout 900 python -m pytest tests/test_gpu_gemm.py -m gpu -q --timeout 300 > gpurun_out/test_gemm.log 2>&1; echo "gemmall rc=$?" ;;
+    kernels) timeout 900 python -m pytest tests/test_gpu_kernels.py -m gpu -q --timeout 300 > gpurun_out/test_kernels.log 2>&1; echo "kernels rc=$?" ;;
+    attn)    timeout 900 python -m pytest tests/test_gpu_attention.py -m gpu -q --timeout 300 > gpurun_out/test_attn.log 2>&1; echo "attn rc=$?" ;;
+    tests)   timeout 1500 python -m pytest tests -m gpu -q --timeout 600 > gpurun_out/test_all.log 2>&1; echo "tests rc=$?" ;;
+    smoke)   timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" ;;
+    bench)   timeout 900 python bench.py --steps ${BENCH_STEPS:-3} --warmup 3 ${BENCH_ARGS:-} > gpurun_out/bench_ours.json 2> gpurun_out/bench_ours.err; echo "bench rc=$?"; tail -c 1500 gpurun_out/bench_ours.json ;;
+    ref)     timeout 1200 python bench.py --impl reference --steps ${BENCH_STEPS:-3} --warmup 3 ${BENCH_ARGS:-} > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"; tail -c 1500 gpurun_out/bench_ref.json ;;
+    gemmbench) timeout 600 python tools/gemm_bench.py > gpurun_out/gemm_bench.json 2> gpurun_out/gemm_bench.err; echo "gemmbench rc=$?"; tail -c 3000 gpurun_out/gemm_bench.json ;;
+    launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --accum 1 --no-e2e > gpurun_out/launches.log 2>&1; echo "launches rc=$?" ;;
+    *) echo "unknown stage $s" ;;
+  esac
+done
+tail -n 30 gpurun_out/test_*.log 2>/dev/null | tail -n 80
