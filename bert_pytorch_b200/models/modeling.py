@@ -698,9 +698,9 @@ class BertPretrainingCriterion(nn.Module):
 def count_parameters(model: nn.Module) -> Tuple[int, int]:
     """(number of elements, number of tensors), tied tensors counted once."""
     seen, n = set(), 0
-    for p in model.parameters():
-        if p.data_ptr() in seen:
+    for p in model.parameters():          # parameters() already yields tied tensors once
+        if id(p) in seen:
             continue
-        seen.add(p.data_ptr())
+        seen.add(id(p))
         n += p.numel()
     return n, len(seen)

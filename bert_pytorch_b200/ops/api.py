@@ -185,7 +185,8 @@ def attention_bwd(qkv, seqlens, ctx, dctx, lse, heads: int, *, p_drop=0.0, seed=
     H = H3 // 3
     dqkv = torch.empty_like(qkv)
     delta = torch.empty(B, heads, S, dtype=torch.float32, device=qkv.device)
-    extension().attention_bwd(qkv, seqlens, ctx, dctx, lse, dqkv, delta, heads, 1.0 / math.sqrt(H // heads), p_drop,
+    dq_acc = torch.empty(B * S, H, dtype=torch.float32, device=qkv.device) if S > 128 else None
+    extension().attention_bwd(qkv, seqlens, ctx, dctx, lse, dqkv, delta, dq_acc, heads, 1.0 / math.sqrt(H // heads), p_drop,
                               seed, stream)
     _count(2)
     return dqkv

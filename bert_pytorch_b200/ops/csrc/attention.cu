@@ -1,9 +1,565 @@
-// placeholder: replaced by the tcgen05 flash-attention kernels
+// Fused multi-head attention for BERT (non-causal, key-padding mask given as per-sequence valid length,
+// head_dim 64, S <= 512 in blocks of 128) on tcgen05 tensor cores -- forward and backward.
+// Replaces the reference's QK^T / scale / mask / softmax / dropout / PV chain that materialises three
+// [B,h,S,S] tensors per layer (src/modeling.py:404-428).
+//
+// Data layout: qkv is the QKV-GEMM output [B*S, 3H] (token-major, q|k|v, head-major inside), so Q/K/V
+// tiles of one head are plain 2-D TMA boxes of that matrix -- no permute/contiguous copies (K6 is gone);
+// the context is written as [B*S, H], ready for the output projection.
+//
+// Forward, one CTA per (batch, head, 128-query block):
+//   warp 4 lane 0 : TMA loads (Q once, K/V blocks through a 2-stage ring) and all tcgen05.mma issue
+//   warps 0-3     : one thread per query row: S row from TMEM -> online softmax (fp32, exp2) ->
+//                   dropout (Philox counter RNG, regenerated in backward) -> P (bf16) into shared memory in
+//                   the 128B-swizzled K-major layout the second MMA reads -> O += P V accumulated in
+//                   registers from the TMEM result of each key block.
+// Backward, one CTA per (batch, head, 128-key block), looping over query blocks:
+//   S = Q K^T and dPd = dO V^T into TMEM; threads form P, dS (and the dropped P) -> shared memory;
+//   dV += Pd^T dO, dK += dS^T Q (accumulated in TMEM over the query loop; the transposes are free: the
+//   same shared-memory tile is read through an MN-major descriptor), dQ = dS K per query block
+//   (direct store when S == 128, fp32 atomics + a conversion pass otherwise).
 #include "common.cuh"
+#include "gemm_sm100.h"
 #include "kernels.h"
+
 namespace b200 {
-void attention_fwd(const void*, const int*, void*, float*, int, int, int, int, float, unsigned long long, unsigned int,
-                   float, cudaStream_t) { fprintf(stderr, "[b200] attention_fwd not built\n"); abort(); }
-void attention_bwd(const void*, const int*, const void*, const void*, const float*, void*, float*, int, int, int, int,
-                   float, unsigned long long, unsigned int, float, cudaStream_t) { fprintf(stderr, "[b200] attention_bwd not built\n"); abort(); }
+
+constexpr int ATT_THREADS = 160;   // 4 softmax warps + 1 control warp
+constexpr int TILE = 128;          // query rows / key rows per block
+constexpr int HD = 64;             // head dim
+constexpr float LOG2E = 1.4426950408889634f;
+
+struct AttnArgs {
+  int B, S, h, H;
+  const int* seqlens;
+  __nv_bfloat16* ctx;      // fwd out [B*S, H]
+  float* lse;              // [B, h, S] natural-log LSE of the scaled scores
+  float scale;
+  unsigned long long seed;
+  unsigned int stream;
+  unsigned int thresh16;
+  float inv_keep;
+  // backward
+  const float* delta;      // [B, h, S]
+  __nv_bfloat16* dqkv;     // [B*S, 3H]
+  float* dq_acc;           // [B*S, H] fp32 (only when more than one key block)
+};
+
+// address of the 16-byte chunk holding columns [col8*8, col8*8+8) of row r inside a [128 x 128] bf16 tile
+// stored as two [128 x 64] 128B-swizzled sub-tiles (the layout TMA/UMMA call SWIZZLE_128B)
+__device__ __forceinline__ uint32_t p_chunk_offset(int r, int col8) {
+  const int sub = col8 >> 3, ck = col8 & 7;
+  return (uint32_t)(sub * 16384 + r * 128 + ((ck ^ (r & 7)) << 4));
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                    // 16 KB
+  uint8_t* sK = smem + 16384;            // 2 x 16 KB
+  uint8_t* sV = smem + 16384 * 3;        // 2 x 16 KB
+  uint8_t* sP = smem + 16384 * 5;        // 32 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 16384 * 7);
+  uint64_t* q_full = bars;               // 1
+  uint64_t* kv_full = bars + 1;          // 2
+  uint64_t* kv_empty = bars + 3;         // 2
+  uint64_t* s_ready = bars + 5;
+  uint64_t* p_ready = bars + 6;
+  uint64_t* pv_done = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qb = blockIdx.x, bh = blockIdx.y;
+  const int b = bh / p.h, head = bh % p.h;
+  const int seqlen = min(p.seqlens[b], p.S);
+  const int nkb = max(1, (seqlen + TILE - 1) / TILE);   // key blocks that contain valid keys
+  const int row0 = b * p.S;
+
+  if (threadIdx.x == 128) {
+    tma_prefetch_desc(&tmap_qkv);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    mbar_init(s_ready, 1);
+    mbar_init(p_ready, 128);
+    mbar_init(pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tS = tmem, tO = tmem + 128;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      const int cq = head * HD, ck = p.H + head * HD, cv = 2 * p.H + head * HD;
+      mbar_arrive_expect_tx(q_full, 16384);
+      tma_load_2d(sQ, &tmap_qkv, q_full, cq, row0 + qb * TILE);
+      for (int j = 0; j < min(2, nkb); ++j) {
+        mbar_arrive_expect_tx(&kv_full[j], 32768);
+        tma_load_2d(sK + j * 16384, &tmap_qkv, &kv_full[j], ck, row0 + j * TILE);
+        tma_load_2d(sV + j * 16384, &tmap_qkv, &kv_full[j], cv, row0 + j * TILE);
+      }
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);  // Q K^T : both K-major
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, false, true);    // P V   : V is MN-major
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < nkb; ++j) {
+        const int st = j & 1;
+        mbar_wait(&kv_full[st], (j >> 1) & 1);
+        tc_fence_after();
+        const uint64_t dq = umma_smem_desc_sw128(smem_u32(sQ), 16, 1024);
+        const uint64_t dk = umma_smem_desc_sw128(smem_u32(sK + st * 16384), 16, 1024);
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) umma_bf16_ss(tS, dq + 2 * kk, dk + 2 * kk, idesc_s, kk > 0);
+        umma_commit(s_ready);
+        mbar_wait(p_ready, j & 1);
+        tc_fence_after();
+        const uint32_t ap = smem_u32(sP), av = smem_u32(sV + st * 16384);
+#pragma unroll
+        for (int kk = 0; kk < TILE / 16; ++kk) {
+          const uint64_t da = umma_smem_desc_sw128(ap + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024);
+          const uint64_t db = umma_smem_desc_sw128(av + kk * 2048, 8192, 1024);
+          umma_bf16_ss(tO, da, db, idesc_o, kk > 0);
+        }
+        umma_commit(pv_done);
+        umma_commit(&kv_empty[st]);
+        if (j + 2 < nkb) {
+          mbar_wait(&kv_empty[st], (j >> 1) & 1);
+          mbar_arrive_expect_tx(&kv_full[st], 32768);
+          tma_load_2d(sK + st * 16384, &tmap_qkv, &kv_full[st], ck, row0 + (j + 2) * TILE);
+          tma_load_2d(sV + st * 16384, &tmap_qkv, &kv_full[st], cv, row0 + (j + 2) * TILE);
+        }
+      }
+    }
+  } else {
+    const int r = warp * 32 + lane;            // query row inside the tile == TMEM lane
+    const int q = qb * TILE + r;               // query position in the sequence
+    const uint32_t lane_base = uint32_t(warp * 32) << 16;
+    const float c_scale = p.scale * LOG2E;
+    float m = -INFINITY, l = 0.f;
+    float o[HD];
+#pragma unroll
+    for (int t = 0; t < HD; ++t) o[t] = 0.f;
+    const uint64_t erow = ((uint64_t)bh * p.S + (uint64_t)q) * (uint64_t)p.S;   // dropout element index base
+    for (int j = 0; j < nkb; ++j) {
+      mbar_wait(s_ready, j & 1);
+      tc_fence_after();
+      // pass 1: row max over the valid keys of this block
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tS + lane_base + c * 32, v);
+        tmem_ld_wait();
+        const int k0 = j * TILE + c * 32;
+#pragma unroll
+        for (int t = 0; t < 32; ++t)
+          if (k0 + t < seqlen) mx = fmaxf(mx, __uint_as_float(v[t]) * c_scale);
+      }
+      const float m_new = fmaxf(m, mx);
+      const float alpha = (m == -INFINITY) ? 0.f : exp2f(m - m_new);
+      float rowsum = 0.f;
+      // pass 2: probabilities, dropout, P -> shared memory
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tS + lane_base + c * 32, v);
+        tmem_ld_wait();
+        const int k0 = j * TILE + c * 32;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float pr[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const int key = k0 + g * 8 + t;
+            const float e = (key < seqlen) ? exp2f(__uint_as_float(v[g * 8 + t]) * c_scale - m_new) : 0.f;
+            rowsum += e;
+            pr[t] = e;
+          }
+          if (p.thresh16 != 0) {
+            const uint32_t keep = dropout_keep8(p.seed, p.stream, (erow + (uint64_t)(k0 + g * 8)) >> 3, p.thresh16);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) pr[t] = ((keep >> t) & 1u) ? pr[t] * p.inv_keep : 0.f;
+          }
+          const uint4 pk = make_uint4(pack_bf16(pr[0], pr[1]), pack_bf16(pr[2], pr[3]), pack_bf16(pr[4], pr[5]),
+                                      pack_bf16(pr[6], pr[7]));
+          *reinterpret_cast<uint4*>(sP + p_chunk_offset(r, c * 4 + g)) = pk;
+        }
+      }
+      l = l * alpha + rowsum;
+      m = m_new;
+#pragma unroll
+      for (int t = 0; t < HD; ++t) o[t] *= alpha;
+      fence_proxy_async();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      mbar_arrive(p_ready);
+      mbar_wait(pv_done, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tO + lane_base + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int t = 0; t < 32; ++t) o[c * 32 + t] += __uint_as_float(v[t]);
+      }
+    }
+    if (q < p.S) {
+      const float inv_l = 1.f / l;
+      __nv_bfloat16* dst = p.ctx + (size_t)(row0 + q) * p.H + head * HD;
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        *reinterpret_cast<uint4*>(dst + g * 8) =
+            make_uint4(pack_bf16(o[g * 8] * inv_l, o[g * 8 + 1] * inv_l), pack_bf16(o[g * 8 + 2] * inv_l, o[g * 8 + 3] * inv_l),
+                       pack_bf16(o[g * 8 + 4] * inv_l, o[g * 8 + 5] * inv_l), pack_bf16(o[g * 8 + 6] * inv_l, o[g * 8 + 7] * inv_l));
+      p.lse[(size_t)bh * p.S + q] = (m + log2f(l)) * 0.6931471805599453f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout, float* __restrict__ delta,
+                  int B, int S, int h, int H) {
+  // one 8-lane group per (token, head): 64 elements = 8 x 16 B
+  const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const int sub = threadIdx.x & 7;
+  const long long total = (long long)B * S * h;
+  if (gid >= total) return;
+  const int head = (int)(gid % h);
+  const long long tok = gid / h;
+  const size_t off = (size_t)tok * H + head * HD + sub * 8;
+  const uint4 a = *reinterpret_cast<const uint4*>(o + off), d = *reinterpret_cast<const uint4*>(dout + off);
+  const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
+  float s = 0.f;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float2 x = unpack_bf16(aw[t]), y = unpack_bf16(dw[t]);
+    s += x.x * y.x + x.y * y.y;
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  if (sub == 0) {
+    const int bb = (int)(tok / S), ss = (int)(tok % S);
+    delta[((size_t)bb * h + head) * S + ss] = s;
+  }
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
+                const AttnArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;                      // 16 KB
+  uint8_t* sV = smem + 16384;              // 16 KB
+  uint8_t* sQ = smem + 16384 * 2;          // 2 x 16 KB
+  uint8_t* sDO = smem + 16384 * 4;         // 2 x 16 KB
+  uint8_t* sPd = smem + 16384 * 6;         // 32 KB
+  uint8_t* sDS = smem + 16384 * 8;         // 32 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 16384 * 10);
+  uint64_t* kv_full = bars;
+  uint64_t* qdo_full = bars + 1;           // 2
+  uint64_t* qdo_empty = bars + 3;          // 2
+  uint64_t* sdp_ready = bars + 5;
+  uint64_t* ds_ready = bars + 6;
+  uint64_t* dq_ready = bars + 7;
+  uint64_t* fin = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kb = blockIdx.x, bh = blockIdx.y;
+  const int b = bh / p.h, head = bh % p.h;
+  const int seqlen = min(p.seqlens[b], p.S);
+  const int nqb = (p.S + TILE - 1) / TILE;
+  const int nkb_total = gridDim.x;
+  const int row0 = b * p.S;
+  const bool dead = kb * TILE >= seqlen;     // every key of this block is padding: dK = dV = 0
+
+  if (dead) {
+    if (warp < 4) {
+      const int key = kb * TILE + warp * 32 + lane;
+      if (key < p.S) {
+        __nv_bfloat16* dk = p.dqkv + (size_t)(row0 + key) * 3 * p.H + p.H + head * HD;
+        __nv_bfloat16* dv = dk + p.H;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          *reinterpret_cast<uint4*>(dk + g * 8) = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(dv + g * 8) = make_uint4(0, 0, 0, 0);
+        }
+      }
+    }
+    return;
+  }
+
+  if (threadIdx.x == 128) {
+    tma_prefetch_desc(&tmap_qkv);
+    tma_prefetch_desc(&tmap_do);
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
+    mbar_init(sdp_ready, 1);
+    mbar_init(ds_ready, 128);
+    mbar_init(dq_ready, 1);
+    mbar_init(fin, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tS = tmem, tDP = tmem + 128, tDV = tmem + 256, tDK = tmem + 320, tDQ = tmem + 384;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      const int cq = head * HD, ck = p.H + head * HD, cv = 2 * p.H + head * HD;
+      mbar_arrive_expect_tx(kv_full, 32768);
+      tma_load_2d(sK, &tmap_qkv, kv_full, ck, row0 + kb * TILE);
+      tma_load_2d(sV, &tmap_qkv, kv_full, cv, row0 + kb * TILE);
+      for (int i = 0; i < min(2, nqb); ++i) {
+        mbar_arrive_expect_tx(&qdo_full[i], 32768);
+        tma_load_2d(sQ + i * 16384, &tmap_qkv, &qdo_full[i], cq, row0 + i * TILE);
+        tma_load_2d(sDO + i * 16384, &tmap_do, &qdo_full[i], head * HD, row0 + i * TILE);
+      }
+      constexpr uint32_t id_kk = umma_idesc_bf16(128, 128, false, false);  // [q x keys], both K-major
+      constexpr uint32_t id_tt = umma_idesc_bf16(128, 64, true, true);     // [keys x d] = X^T Y, both MN-major
+      constexpr uint32_t id_kt = umma_idesc_bf16(128, 64, false, true);    // [q x d] = dS K, A K-major, B MN-major
+      mbar_wait(kv_full, 0);
+      for (int i = 0; i < nqb; ++i) {
+        const int st = i & 1;
+        mbar_wait(&qdo_full[st], (i >> 1) & 1);
+        tc_fence_after();
+        const uint32_t aq = smem_u32(sQ + st * 16384), ado = smem_u32(sDO + st * 16384);
+        const uint32_t ak = smem_u32(sK), av = smem_u32(sV), apd = smem_u32(sPd), ads = smem_u32(sDS);
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk)   // S = Q K^T
+          umma_bf16_ss(tS, umma_smem_desc_sw128(aq + kk * 32, 16, 1024), umma_smem_desc_sw128(ak + kk * 32, 16, 1024),
+                       id_kk, kk > 0);
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk)   // dPd = dO V^T
+          umma_bf16_ss(tDP, umma_smem_desc_sw128(ado + kk * 32, 16, 1024), umma_smem_desc_sw128(av + kk * 32, 16, 1024),
+                       id_kk, kk > 0);
+        umma_commit(sdp_ready);
+        mbar_wait(ds_ready, i & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < TILE / 16; ++kk) {   // reduction over the 128 query rows of this block
+          // A^T tiles: [q rows][keys] read MN-major (M = keys: two 64-wide blocks 16 KB apart)
+          const uint64_t a_pd = umma_smem_desc_sw128(apd + kk * 2048, 16384, 1024);
+          const uint64_t a_ds = umma_smem_desc_sw128(ads + kk * 2048, 16384, 1024);
+          const uint64_t b_do = umma_smem_desc_sw128(ado + kk * 2048, 8192, 1024);
+          const uint64_t b_q = umma_smem_desc_sw128(aq + kk * 2048, 8192, 1024);
+          umma_bf16_ss(tDV, a_pd, b_do, id_tt, (i > 0 || kk > 0));   // dV += Pd^T dO
+          umma_bf16_ss(tDK, a_ds, b_q, id_tt, (i > 0 || kk > 0));    // dK += dS^T Q
+        }
+#pragma unroll
+        for (int kk = 0; kk < TILE / 16; ++kk) {   // dQ = dS K   (reduction over the 128 keys)
+          const uint64_t a_ds = umma_smem_desc_sw128(ads + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024);
+          const uint64_t b_k = umma_smem_desc_sw128(ak + kk * 2048, 8192, 1024);
+          umma_bf16_ss(tDQ, a_ds, b_k, id_kt, kk > 0);
+        }
+        umma_commit(dq_ready);
+        umma_commit(&qdo_empty[st]);
+        if (i + 2 < nqb) {
+          mbar_wait(&qdo_empty[st], (i >> 1) & 1);
+          mbar_arrive_expect_tx(&qdo_full[st], 32768);
+          tma_load_2d(sQ + st * 16384, &tmap_qkv, &qdo_full[st], cq, row0 + (i + 2) * TILE);
+          tma_load_2d(sDO + st * 16384, &tmap_do, &qdo_full[st], head * HD, row0 + (i + 2) * TILE);
+        }
+      }
+      umma_commit(fin);
+    }
+  } else {
+    const int r = warp * 32 + lane;
+    const uint32_t lane_base = uint32_t(warp * 32) << 16;
+    const float c_scale = p.scale * LOG2E;
+    for (int i = 0; i < nqb; ++i) {
+      const int q = i * TILE + r;
+      const bool q_ok = q < p.S;
+      const float lse2 = q_ok ? p.lse[(size_t)bh * p.S + q] * LOG2E : 0.f;
+      const float dlt = q_ok ? p.delta[(size_t)bh * p.S + q] : 0.f;
+      const uint64_t erow = ((uint64_t)bh * p.S + (uint64_t)q) * (uint64_t)p.S;
+      mbar_wait(sdp_ready, i & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t sv[32], dv[32];
+        tmem_ld_32x32(tS + lane_base + c * 32, sv);
+        tmem_ld_32x32(tDP + lane_base + c * 32, dv);
+        tmem_ld_wait();
+        const int k0 = kb * TILE + c * 32;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t keep = 0xFFu;
+          if (p.thresh16 != 0)
+            keep = dropout_keep8(p.seed, p.stream, (erow + (uint64_t)(k0 + g * 8)) >> 3, p.thresh16);
+          float pd[8], ds[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const int key = k0 + g * 8 + t;
+            const bool ok = q_ok && key < seqlen;
+            const float pr = ok ? exp2f(__uint_as_float(sv[g * 8 + t]) * c_scale - lse2) : 0.f;
+            const bool kp = (keep >> t) & 1u;
+            const float dp = kp ? __uint_as_float(dv[g * 8 + t]) * p.inv_keep : 0.f;
+            pd[t] = kp ? pr * p.inv_keep : 0.f;
+            ds[t] = pr * (dp - dlt) * p.scale;
+          }
+          const uint32_t off = p_chunk_offset(r, c * 4 + g);
+          *reinterpret_cast<uint4*>(sPd + off) = make_uint4(pack_bf16(pd[0], pd[1]), pack_bf16(pd[2], pd[3]),
+                                                            pack_bf16(pd[4], pd[5]), pack_bf16(pd[6], pd[7]));
+          *reinterpret_cast<uint4*>(sDS + off) = make_uint4(pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]),
+                                                            pack_bf16(ds[4], ds[5]), pack_bf16(ds[6], ds[7]));
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(ds_ready);
+      mbar_wait(dq_ready, i & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tDQ + lane_base + c * 32, v);
+        tmem_ld_wait();
+        if (q_ok) {
+          if (nkb_total == 1) {
+            __nv_bfloat16* dq = p.dqkv + (size_t)(row0 + q) * 3 * p.H + head * HD + c * 32;
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              *reinterpret_cast<uint4*>(dq + g * 8) = make_uint4(
+                  pack_bf16(__uint_as_float(v[g * 8]), __uint_as_float(v[g * 8 + 1])),
+                  pack_bf16(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3])),
+                  pack_bf16(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5])),
+                  pack_bf16(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7])));
+          } else {
+            float* dq = p.dq_acc + (size_t)(row0 + q) * p.H + head * HD + c * 32;
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dq + g * 4),
+                           "f"(__uint_as_float(v[g * 4])), "f"(__uint_as_float(v[g * 4 + 1])),
+                           "f"(__uint_as_float(v[g * 4 + 2])), "f"(__uint_as_float(v[g * 4 + 3]))
+                           : "memory");
+          }
+        }
+      }
+      tc_fence_before();   // dQ TMEM reads done before the next block's MMA may overwrite it
+    }
+    // dK / dV of this key block
+    mbar_wait(fin, 0);
+    tc_fence_after();
+    const int key = kb * TILE + r;
+#pragma unroll 1
+    for (int w = 0; w < 2; ++w) {       // 0: dK, 1: dV
+      const uint32_t src = w == 0 ? tDK : tDV;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(src + lane_base + c * 32, v);
+        tmem_ld_wait();
+        if (key < p.S) {
+          __nv_bfloat16* dst = p.dqkv + (size_t)(row0 + key) * 3 * p.H + (w + 1) * p.H + head * HD + c * 32;
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<uint4*>(dst + g * 8) = make_uint4(
+                pack_bf16(__uint_as_float(v[g * 8]), __uint_as_float(v[g * 8 + 1])),
+                pack_bf16(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3])),
+                pack_bf16(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5])),
+                pack_bf16(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7])));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// dq_acc (fp32 [B*S, H]) -> q slots of dqkv (bf16 [B*S, 3H])
+__global__ void __launch_bounds__(256)
+attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, long long rows, int H) {
+  const int per_row = H / 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows * per_row;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / per_row;
+    const int col = (int)(i % per_row) * 8;
+    const float4 a = *reinterpret_cast<const float4*>(acc + row * H + col);
+    const float4 c = *reinterpret_cast<const float4*>(acc + row * H + col + 4);
+    *reinterpret_cast<uint4*>(dqkv + row * 3 * H + col) =
+        make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(c.x, c.y), pack_bf16(c.z, c.w));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+static void fill_args(AttnArgs& a, int B, int S, int h, int d, const int* seqlens, float scale,
+                      unsigned long long seed, unsigned int stream, float p_drop) {
+  if (d != HD) { fprintf(stderr, "[b200] attention kernels need head_dim 64 (got %d)\n", d); abort(); }
+  if (S > 512 || S % 8 != 0) { fprintf(stderr, "[b200] attention kernels need S <= 512 and S %% 8 == 0 (got %d)\n", S); abort(); }
+  a.B = B; a.S = S; a.h = h; a.H = h * d; a.seqlens = seqlens; a.scale = scale; a.seed = seed; a.stream = stream;
+  a.thresh16 = p_drop > 0.f ? (unsigned)(p_drop * 65536.f + 0.5f) : 0u;
+  a.inv_keep = p_drop > 0.f ? 65536.f / (65536.f - (float)a.thresh16) : 1.f;
+  a.ctx = nullptr; a.lse = nullptr; a.delta = nullptr; a.dqkv = nullptr; a.dq_acc = nullptr;
+}
+
+void attention_fwd(const void* qkv, const int* seqlens, void* ctx, float* lse, int B, int S, int h, int d,
+                   float scale, unsigned long long seed, unsigned int stream, float p_drop, cudaStream_t st) {
+  AttnArgs a;
+  fill_args(a, B, S, h, d, seqlens, scale, seed, stream, p_drop);
+  a.ctx = (__nv_bfloat16*)ctx; a.lse = lse;
+  const int H = h * d;
+  CUtensorMap tm = make_tmap_2d_bf16(qkv, 3 * H, (uint64_t)B * S, 3 * H, 64, TILE);
+  constexpr int SMEM = 16384 * 7 + 1024 + 128;
+  static bool once = false;
+  if (!once) { B200_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); once = true; }
+  dim3 grid((S + TILE - 1) / TILE, B * h);
+  attn_fwd_kernel<<<grid, ATT_THREADS, SMEM, st>>>(tm, a);
+}
+
+void attention_bwd(const void* qkv, const int* seqlens, const void* ctx, const void* dctx, const float* lse,
+                   void* dqkv, float* delta_ws, float* dq_acc, int B, int S, int h, int d, float scale,
+                   unsigned long long seed, unsigned int stream, float p_drop, cudaStream_t st) {
+  AttnArgs a;
+  fill_args(a, B, S, h, d, seqlens, scale, seed, stream, p_drop);
+  const int H = h * d;
+  a.lse = const_cast<float*>(lse); a.delta = delta_ws; a.dqkv = (__nv_bfloat16*)dqkv; a.dq_acc = dq_acc;
+  const long long groups = (long long)B * S * h;
+  attn_delta_kernel<<<(unsigned)((groups * 8 + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)ctx,
+                                                                       (const __nv_bfloat16*)dctx, delta_ws, B, S, h, H);
+  const int nkb = (S + TILE - 1) / TILE;
+  if (nkb > 1) {
+    if (dq_acc == nullptr) { fprintf(stderr, "[b200] attention_bwd needs a dq accumulation buffer when S > 128\n"); abort(); }
+    B200_CUDA_CHECK(cudaMemsetAsync(dq_acc, 0, sizeof(float) * (size_t)B * S * H, st));
+  }
+  CUtensorMap tq = make_tmap_2d_bf16(qkv, 3 * H, (uint64_t)B * S, 3 * H, 64, TILE);
+  CUtensorMap td = make_tmap_2d_bf16(dctx, H, (uint64_t)B * S, H, 64, TILE);
+  constexpr int SMEM = 16384 * 10 + 1024 + 128;
+  static bool once = false;
+  if (!once) { B200_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); once = true; }
+  dim3 grid(nkb, B * h);
+  attn_bwd_kernel<<<grid, ATT_THREADS, SMEM, st>>>(tq, td, a);
+  if (nkb > 1) {
+    const long long work = (long long)B * S * (H / 8);
+    int g = (int)((work + 255) / 256);
+    if (g > 148 * 16) g = 148 * 16;
+    attn_dq_convert_kernel<<<g, 256, 0, st>>>(dq_acc, (__nv_bfloat16*)dqkv, (long long)B * S, H);
+  }
+}
+
 }  // namespace b200

@@ -243,12 +243,13 @@ void attention_fwd(Tensor qkv, Tensor seqlens, Tensor ctx, Tensor lse, int64_t h
                       H / (int)heads, (float)scale, (unsigned long long)seed, (unsigned)stream_id, (float)p_drop, cur_stream());
 }
 void attention_bwd(Tensor qkv, Tensor seqlens, Tensor ctx, Tensor dctx, Tensor lse, Tensor dqkv, Tensor delta_ws,
-                   int64_t heads, double scale, double p_drop, int64_t seed, int64_t stream_id) {
+                   c10::optional<Tensor> dq_acc, int64_t heads, double scale, double p_drop, int64_t seed, int64_t stream_id) {
   check_bf16(qkv, "qkv"); check_bf16(ctx, "ctx"); check_bf16(dctx, "dctx"); check_bf16(dqkv, "dqkv");
+  TORCH_CHECK(qkv.is_contiguous() && ctx.is_contiguous() && dctx.is_contiguous() && dqkv.is_contiguous(), "attention_bwd needs contiguous tensors");
   const int B = (int)qkv.size(0), S = (int)qkv.size(1), H = (int)qkv.size(2) / 3;
   c10::cuda::CUDAGuard guard(qkv.device());
   b200::attention_bwd(qkv.data_ptr(), seqlens.data_ptr<int>(), ctx.data_ptr(), dctx.data_ptr(), lse.data_ptr<float>(),
-                      dqkv.data_ptr(), delta_ws.data_ptr<float>(), B, S, (int)heads, H / (int)heads, (float)scale,
+                      dqkv.data_ptr(), delta_ws.data_ptr<float>(), opt_f32(dq_acc), B, S, (int)heads, H / (int)heads, (float)scale,
                       (unsigned long long)seed, (unsigned)stream_id, (float)p_drop, cur_stream());
 }
 

@@ -48,7 +48,7 @@ void arena_adam(float* g, float* p, float* m, float* v, void* shadow, const int*
 void attention_fwd(const void* qkv, const int* seqlens, void* ctx, float* lse, int B, int S, int h, int d,
                    float scale, unsigned long long seed, unsigned int stream, float p_drop, cudaStream_t st);
 void attention_bwd(const void* qkv, const int* seqlens, const void* ctx, const void* dctx, const float* lse,
-                   void* dqkv, float* delta_ws, int B, int S, int h, int d, float scale, unsigned long long seed,
-                   unsigned int stream, float p_drop, cudaStream_t st);
+                   void* dqkv, float* delta_ws, float* dq_acc, int B, int S, int h, int d, float scale,
+                   unsigned long long seed, unsigned int stream, float p_drop, cudaStream_t st);
 
 }  // namespace b200

@@ -27,7 +27,7 @@ def test_layer_norm_fwd_bwd(M, H):
     xr = x.float().requires_grad_(True)
     gr, br = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
     yr = F.layer_norm(xr, (H,), gr, br, eps=1e-12)
-    assert (y.float() - yr).abs().max() < 3e-2
+    assert ((y.float() - yr).abs() / (yr.abs() + 1.0)).max() < 1.6e-2     # bf16 output rounding
     yr.backward(dy.float())
     dg, db, dbias = torch.zeros(H, device="cuda"), torch.zeros(H, device="cuda"), torch.zeros(H, device="cuda")
     dx, dxd = K.layer_norm_bwd(dy, x, mean, rstd, g, dgamma=dg, dbeta=db, dbias=dbias, want_dropped=True, p_drop=0.0)
@@ -223,9 +223,11 @@ def test_fused_pretrainer_matches_oracle():
     loss = eng.forward_backward(ids, seg, mask, labels, nsl, grad_scale=1.0)
     assert abs(loss.item() - ref_loss.item()) < 3e-2 * abs(ref_loss.item()), (loss.item(), ref_loss.item())
     bad = []
+    gmax = max(po.grad.abs().max().item() for po in oracle.parameters())
     for (n, p), po in zip(model.named_parameters(), oracle.parameters()):
         g, go = p.grad.float(), po.grad.float()
-        denom = go.abs().max().item() + 1e-6
+        # key.bias has an exactly-zero true gradient (softmax shift invariance): floor the scale
+        denom = max(go.abs().max().item(), 1e-3 * gmax)
         rel = (g - go).abs().max().item() / denom
         if rel > 8e-2:
             bad.append((n, rel, denom))

@@ -1,0 +1,143 @@
+"""T2: multi-rank plumbing without GPUs -- the in-process fake backend verifies the partitioned
+all-reduce+LAMB algorithm against the unfused reference; gloo multi-process verifies the real torch path."""
+import copy
+import os
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from bert_pytorch_b200 import BertConfig
+from bert_pytorch_b200 import models as M
+from bert_pytorch_b200.models.arena import ParamArena
+from bert_pytorch_b200.optim import Lamb
+from bert_pytorch_b200.parallel import DataParallel, FakeComm, ShardedLamb
+from bert_pytorch_b200.parallel.sharded_lamb import slot_segments
+
+
+def _model():
+    torch.manual_seed(0)
+    cfg = BertConfig(vocab_size_or_config_json_file=256, hidden_size=32, num_hidden_layers=1, num_attention_heads=2,
+                     intermediate_size=64, max_position_embeddings=32, hidden_dropout_prob=0.0,
+                     attention_probs_dropout_prob=0.0)
+    return M.BertForPreTraining(cfg)
+
+
+def test_fake_comm_collectives():
+    def fn(comm):
+        t = torch.full((4,), float(comm.rank + 1))
+        comm.all_reduce_(t)
+        mx = torch.tensor([float(comm.rank)])
+        comm.all_reduce_(mx, op="max")
+        b = torch.tensor([float(comm.rank)])
+        comm.broadcast_(b, src=2)
+        full = torch.arange(8.0) * (comm.rank + 1)
+        out = torch.zeros(2)
+        comm.reduce_scatter(full.clone(), out, comm.rank * 2, comm.rank * 2 + 2)
+        gathered = torch.zeros(8)
+        comm.all_gather_into(gathered, out, comm.rank * 2, comm.rank * 2 + 2)
+        return t, mx, b, gathered
+    res = FakeComm.spawn(4, fn)
+    for t, mx, b, g in res:
+        assert t.tolist() == [10.0] * 4 and mx.item() == 3.0 and b.item() == 2.0
+        assert torch.equal(g, torch.arange(8.0) * 10)
+
+
+def test_slot_segments_straddle():
+    segs = slot_segments([0, 10, 64], [10, 50, 30], 5, 70)
+    assert segs == [(0, 5, 10), (1, 10, 60), (2, 64, 70)]
+
+
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_sharded_lamb_equals_unfused_reference(world):
+    """reduce-scatter + partitioned LAMB (two-phase norms) + all-gather == all-reduce(avg) + full LAMB."""
+    base = _model()
+    grads = []
+    for r in range(world):
+        torch.manual_seed(100 + r)
+        grads.append([torch.randn_like(p) * (5.0 if r == 0 else 0.2) for p in base.parameters()])
+    # unfused reference on one rank: averaged grads, plain LAMB
+    ref = copy.deepcopy(base)
+    named = list(ref.named_parameters())
+    nd = ("bias", "LayerNorm")
+    opt = Lamb([{"params": [p for n, p in named if not any(k in n for k in nd)], "weight_decay": 0.01},
+                {"params": [p for n, p in named if any(k in n for k in nd)], "weight_decay": 0.0}], lr=5e-3)
+    for step in range(2):
+        for i, p in enumerate(ref.parameters()):
+            p.grad = sum(g[i] for g in grads) / world * (1.0 + step)
+        opt.step()
+
+    def fn(comm):
+        m = copy.deepcopy(base)
+        arena = ParamArena(m)
+        sl = ShardedLamb(arena, comm, lr=5e-3, weight_decay=0.01, granule=64)
+        for step in range(2):
+            for i, p in enumerate(m.parameters()):
+                p.grad.copy_(grads[comm.rank][i] * (1.0 + step))
+            assert sl.step(loss_scale=1.0)
+        return [p.detach().clone() for p in m.parameters()], sl.last_grad_norm
+    outs = FakeComm.spawn(world, fn)
+    for params, gnorm in outs:
+        for (n, pr), pf in zip(ref.named_parameters(), params):
+            assert torch.allclose(pr, pf, rtol=2e-5, atol=2e-6), (world, n, (pr - pf).abs().max().item())
+    assert all(torch.equal(a, b) for a, b in zip(outs[0][0], outs[-1][0]))       # ranks agree bit for bit
+
+
+def test_sharded_lamb_overflow_skips_everywhere():
+    base = _model()
+
+    def fn(comm):
+        m = copy.deepcopy(base)
+        arena = ParamArena(m)
+        before = arena.flat_param.clone()
+        sl = ShardedLamb(arena, comm, lr=1e-2, granule=64)
+        for p in m.parameters():
+            p.grad.fill_(1.0)
+        if comm.rank == 1:
+            arena.flat_grad[3] = float("inf")      # only one rank overflows
+        applied = sl.step(loss_scale=128.0)
+        return applied, torch.equal(arena.flat_param, before), float(arena.flat_grad.abs().sum())
+    for applied, unchanged, gsum in FakeComm.spawn(3, fn):
+        assert applied is False and unchanged and gsum == 0.0
+
+
+def _gloo_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method="env://")
+    from bert_pytorch_b200.parallel import TorchComm
+    m = _model()
+    if rank != 0:
+        for p in m.parameters():
+            p.data.add_(1.0)                      # diverge; ctor must broadcast rank 0's weights
+    arena = ParamArena(m)
+    ddp = DataParallel(m, comm=TorchComm(), arena=arena)
+    w0 = arena.flat_param.clone()
+    torch.manual_seed(5)
+    ids = torch.randint(0, 256, (2 * world, 16))
+    mine = ids[rank * 2:(rank + 1) * 2]
+    with ddp.no_sync():
+        s, n = ddp(mine)
+        (s.float().mean() + n.float().mean()).backward()
+        ddp.sync_gradients()                      # suppressed inside no_sync
+    g_local = arena.flat_grad.clone()
+    ddp.sync_gradients()
+    q.put((rank, w0, g_local, arena.flat_grad.clone()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gloo_data_parallel_broadcast_nosync_and_average():
+    world, port = 2, 29655
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+    (_, w0a, ga, sa), (_, w0b, gb, sb) = res
+    assert torch.equal(w0a, w0b)                                   # broadcast at construction
+    assert not torch.equal(ga, gb)                                 # no_sync kept gradients local
+    assert torch.allclose(sa, (ga + gb) / 2, atol=1e-7) and torch.equal(sa, sb)

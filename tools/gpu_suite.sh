@@ -12,7 +12,7 @@ for s in $STAGES; do
     gemm)    timeout 600 python -m pytest tests/test_gpu_gemm.py -m gpu -q -x --timeout 300 > gpurun_out/test_gemm.log 2>&1; echo "gemm rc=$?" ;;
     gemmall) timeout 900 python -m pytest tests/test_gpu_gemm.py -m gpu -q --timeout 300 > gpurun_out/test_gemm.log 2>&1; echo "gemmall rc=$?" ;;
     kernels) timeout 900 python -m pytest tests/test_gpu_kernels.py -m gpu -q --timeout 300 > gpurun_out/test_kernels.log 2>&1; echo "kernels rc=$?" ;;
-    attn)    timeout 900 python -m pytest tests/test_gpu_attention.py -m gpu -q --timeout 300 > gpurun_out/test_attn.log 2>&1; echo "attn rc=$?" ;;
+    attn)    timeout 600 python -m pytest tests/test_gpu_attention.py -m gpu -q --timeout 300 > gpurun_out/test_attn.log 2>&1; echo "attn rc=$?" ;;
     tests)   timeout 1500 python -m pytest tests -m gpu -q --timeout 600 > gpurun_out/test_all.log 2>&1; echo "tests rc=$?" ;;
     smoke)   timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" ;;
     bench)   timeout 900 python bench.py --steps ${BENCH_STEPS:-3} --warmup 3 ${BENCH_ARGS:-} > gpurun_out/bench_ours.json 2> gpurun_out/bench_ours.err; echo "bench rc=$?"; tail -c 1500 gpurun_out/bench_ours.json ;;
