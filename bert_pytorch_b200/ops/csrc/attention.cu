@@ -55,15 +55,19 @@ __device__ __forceinline__ uint32_t p_chunk_offset(int r, int col8) {
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
+// KV_STAGES = 1: the whole key range is one block (S <= 128): 80 KB of shared memory and 128 TMEM columns
+// (the PV result reuses the S columns) -> two CTAs per SM.  KV_STAGES = 2: K/V blocks stream through a ring.
+template <int KV_STAGES>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                    // 16 KB
-  uint8_t* sK = smem + 16384;            // 2 x 16 KB
-  uint8_t* sV = smem + 16384 * 3;        // 2 x 16 KB
-  uint8_t* sP = smem + 16384 * 5;        // 32 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 16384 * 7);
+  uint8_t* sQ = smem;                                  // 16 KB
+  uint8_t* sK = smem + 16384;                          // KV_STAGES x 16 KB
+  uint8_t* sV = sK + 16384 * KV_STAGES;                // KV_STAGES x 16 KB
+  uint8_t* sP = sV + 16384 * KV_STAGES;                // 32 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 32768);
+  constexpr uint32_t TMEM_COLS = KV_STAGES == 1 ? 128 : 256;
   uint64_t* q_full = bars;               // 1
   uint64_t* kv_full = bars + 1;          // 2
   uint64_t* kv_empty = bars + 3;         // 2
@@ -88,19 +92,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs p) 
     mbar_init(pv_done, 1);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(tmem_slot, 256);
+  if (warp == 4) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tS = tmem, tO = tmem + 128;
+  const uint32_t tS = tmem, tO = KV_STAGES == 1 ? tmem : tmem + 128;
 
   if (warp == 4) {
     if (lane == 0) {
       const int cq = head * HD, ck = p.H + head * HD, cv = 2 * p.H + head * HD;
       mbar_arrive_expect_tx(q_full, 16384);
       tma_load_2d(sQ, &tmap_qkv, q_full, cq, row0 + qb * TILE);
-      for (int j = 0; j < min(2, nkb); ++j) {
+      for (int j = 0; j < min(KV_STAGES, nkb); ++j) {
         mbar_arrive_expect_tx(&kv_full[j], 32768);
         tma_load_2d(sK + j * 16384, &tmap_qkv, &kv_full[j], ck, row0 + j * TILE);
         tma_load_2d(sV + j * 16384, &tmap_qkv, &kv_full[j], cv, row0 + j * TILE);
@@ -109,7 +113,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs p) 
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, false, true);    // P V   : V is MN-major
       mbar_wait(q_full, 0);
       for (int j = 0; j < nkb; ++j) {
-        const int st = j & 1;
+        const int st = KV_STAGES == 1 ? 0 : (j & 1);
         mbar_wait(&kv_full[st], (j >> 1) & 1);
         tc_fence_after();
         const uint64_t dq = umma_smem_desc_sw128(smem_u32(sQ), 16, 1024);
@@ -128,7 +132,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs p) 
         }
         umma_commit(pv_done);
         umma_commit(&kv_empty[st]);
-        if (j + 2 < nkb) {
+        if (KV_STAGES == 2 && j + 2 < nkb) {
           mbar_wait(&kv_empty[st], (j >> 1) & 1);
           mbar_arrive_expect_tx(&kv_full[st], 32768);
           tma_load_2d(sK + st * 16384, &tmap_qkv, &kv_full[st], ck, row0 + (j + 2) * TILE);
@@ -224,7 +228,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs p) 
   __syncthreads();
   if (warp == 4) {
     tc_fence_after();
-    tmem_dealloc(tmem, 256);
+    tmem_dealloc(tmem, TMEM_COLS);
   }
 }
 
@@ -525,11 +529,18 @@ void attention_fwd(const void* qkv, const int* seqlens, void* ctx, float* lse, i
   a.ctx = (__nv_bfloat16*)ctx; a.lse = lse;
   const int H = h * d;
   CUtensorMap tm = make_tmap_2d_bf16(qkv, 3 * H, (uint64_t)B * S, 3 * H, 64, TILE);
-  constexpr int SMEM = 16384 * 7 + 1024 + 128;
-  static bool once = false;
-  if (!once) { B200_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); once = true; }
   dim3 grid((S + TILE - 1) / TILE, B * h);
-  attn_fwd_kernel<<<grid, ATT_THREADS, SMEM, st>>>(tm, a);
+  if (S <= TILE) {
+    constexpr int SMEM = 16384 * 5 + 1024 + 128;
+    static bool once = false;
+    if (!once) { B200_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); once = true; }
+    attn_fwd_kernel<1><<<grid, ATT_THREADS, SMEM, st>>>(tm, a);
+  } else {
+    constexpr int SMEM = 16384 * 7 + 1024 + 128;
+    static bool once = false;
+    if (!once) { B200_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); once = true; }
+    attn_fwd_kernel<2><<<grid, ATT_THREADS, SMEM, st>>>(tm, a);
+  }
 }
 
 void attention_bwd(const void* qkv, const int* seqlens, const void* ctx, const void* dctx, const float* lse,

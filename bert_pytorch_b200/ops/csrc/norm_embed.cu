@@ -220,15 +220,30 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
 }
 
 // dst[k][col] += sum over blocks of partial[block][k][col]   (k = 0..2, any dst may be null)
-__global__ void colsum_finalize_kernel(const float* __restrict__ partial, int nblocks, int H, float* dgamma,
-                                       float* dbeta, float* dbias) {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+// grid (ceil(H/32), 3), 256 threads: warp w sums rows w, w+8, ... of a 32-column strip (coalesced 128 B
+// per row), then the 8 warps are combined through shared memory.
+__global__ void __launch_bounds__(256)
+colsum_finalize_kernel(const float* __restrict__ partial, int nblocks, int H, float* dgamma, float* dbeta,
+                       float* dbias) {
   const int qn = blockIdx.y;
   float* dst = qn == 0 ? dgamma : (qn == 1 ? dbeta : dbias);
-  if (col >= H || dst == nullptr) return;
+  if (dst == nullptr) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col = blockIdx.x * 32 + lane;
   float s = 0.f;
-  for (int b = 0; b < nblocks; ++b) s += partial[((size_t)b * 3 + qn) * H + col];
-  dst[col] += s;
+  if (col < H) {
+#pragma unroll 4
+    for (int b = warp; b < nblocks; b += 8) s += partial[((size_t)b * 3 + qn) * H + col];
+  }
+  __shared__ float sm[8][32];
+  sm[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && col < H) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sm[w][lane];
+    dst[col] += t;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -456,8 +471,8 @@ void layer_norm_bwd(const void* dy, const void* x, const float* mean, const floa
   DISPATCH_CHUNKS(H, (ln_bwd_kernel<CH><<<grid, LN_WARPS * 32, 0, st>>>(
       (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, gamma, (__nv_bfloat16*)dx, (__nv_bfloat16*)dxd,
       workspace, M, H, seed, drop_stream, in_stream, th, sc)));
-  dim3 g2((H + 127) / 128, 3);
-  colsum_finalize_kernel<<<g2, 128, 0, st>>>(workspace, grid, H, dgamma, dbeta, dxd ? dbias : nullptr);
+  dim3 g2((H + 31) / 32, 3);
+  colsum_finalize_kernel<<<g2, 256, 0, st>>>(workspace, grid, H, dgamma, dbeta, dxd ? dbias : nullptr);
 }
 
 void colsum_bf16(const void* x, int M, int N, int ld, float* out, cudaStream_t st) {

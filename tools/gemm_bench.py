@@ -27,6 +27,7 @@ def timeit(fn, iters=20, warm=5):
 
 
 def main():
+    only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
     M = 12288
     out = []
     shapes = [("qkv_fwd", K.NT, M, 3072, 1024), ("attn_out_fwd", K.NT, M, 1024, 1024), ("ffn1_fwd", K.NT, M, 4096, 1024),
@@ -34,6 +35,8 @@ def main():
               ("ffn1_wgrad", K.TN, 4096, 1024, M), ("ffn2_wgrad", K.TN, 1024, 4096, M), ("qkv_wgrad", K.TN, 3072, 1024, M),
               ("decoder_fwd", K.NT, 1920, 30528, 1024), ("big", K.NT, 8192, 8192, 8192)]
     for name, layout, m, n, k in shapes:
+        if only is not None and name != only:
+            continue
         if layout == K.NT:
             a, b = torch.randn(m, k, device="cuda").bfloat16(), torch.randn(n, k, device="cuda").bfloat16()
             ref = lambda: a @ b.t()
