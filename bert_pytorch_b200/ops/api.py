@@ -6,6 +6,7 @@ fused engine (models/fused.py) calls forward and backward kernels explicitly.
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -18,6 +19,7 @@ NT, NN, TN = 0, 1, 2
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_DROP_RES, EPI_ADD, EPI_DGELU, EPI_ACCUM_F32, EPI_BIAS_TANH, EPI_F32 = range(9)
 
 NUM_SMS = 148
+_PAIR_ENABLED = os.environ.get("B200_GEMM_PAIR", "1") != "0"
 KERNEL_LAUNCHES = 0     # every wrapper bumps this: bench.py reports it as ``gpu_launches``
 
 
@@ -27,7 +29,10 @@ def _count(n: int = 1) -> None:
 
 
 def _pick_block_n(M: int, N: int) -> int:
-    """256-wide tiles unless that leaves most SMs idle or wastes a big tail."""
+    """512 = CTA-pair kernel (256 x 256 tile per 2-CTA cluster, tcgen05 cta_group::2): the default for the
+    large GEMMs; 256 / 128 = single-CTA 128 x N tiles for small or skinny problems."""
+    if M > 128 and N > 128 and _PAIR_ENABLED:
+        return 512
     if N <= 128:
         return 128
     m_blocks = (M + 127) // 128
@@ -37,7 +42,6 @@ def _pick_block_n(M: int, N: int) -> int:
     def eff(tiles: int, width: int) -> float:
         waves = math.ceil(tiles / NUM_SMS)
         return tiles * width / (waves * NUM_SMS * width) if tiles else 0.0
-    # a 256 tile does twice the work per issue slot; prefer it when the wave efficiency is comparable
     return 256 if eff(t256, 256) >= eff(t128, 128) - 0.08 else 128
 
 
@@ -65,16 +69,23 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, layout: int = NT, epi: int = EPI_N
 
 def wgrad_splits(n_out: int, k_out: int, reduce_len: int, block_n: int = 256) -> int:
     """Split-K factor for dW[n_out, k_out] so the grid covers the machine."""
-    tiles = ((n_out + 127) // 128) * ((k_out + block_n - 1) // block_n)
+    if block_n == 512:
+        tiles = ((n_out + 255) // 256) * ((k_out + 255) // 256)
+        units = NUM_SMS // 2
+    else:
+        tiles = ((n_out + 127) // 128) * ((k_out + block_n - 1) // block_n)
+        units = NUM_SMS
     kb = max(1, (reduce_len + 63) // 64)
-    want = max(1, (2 * NUM_SMS) // max(tiles, 1))
+    want = max(1, round(2 * units / max(tiles, 1)))
     return max(1, min(want, kb // 4 if kb >= 8 else 1, 32))
 
 
 def wgrad_accumulate(dy: torch.Tensor, x: torch.Tensor, grad: torch.Tensor, alpha: float = 1.0) -> None:
     """grad[N,K] (fp32, arena view) += dy[M,N]^T @ x[M,K]."""
     n_out, k_out = grad.shape
-    bn = 256 if k_out >= 256 else 128
+    bn = _pick_block_n(n_out, k_out)
+    if bn == 128 and k_out >= 256:
+        bn = 256
     gemm(dy, x, layout=TN, epi=EPI_ACCUM_F32, out=grad, block_n=bn, alpha=alpha,
          k_splits=wgrad_splits(n_out, k_out, dy.size(0), bn))
 

@@ -61,6 +61,129 @@ struct GemmArgs {
   float alpha;
 };
 
+// Drain one 128 x BLOCK_N fp32 accumulator tile (this warp's 32 TMEM lanes) through the selected epilogue.
+// `taddr` already carries the lane quarter; `row` is this thread's global output row.
+template <int BLOCK_N>
+__device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint32_t taddr, int row, bool row_ok, int n_base) {
+  #pragma unroll 1
+  for (int c = 0; c < BLOCK_N / 32; ++c) {
+    const int n0 = n_base + c * 32;
+    if (n0 >= p.N) break;  // warp uniform
+    uint32_t v[32];
+    tmem_ld_32x32(taddr + c * 32, v);
+    tmem_ld_wait();
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+    const int ncols = min(32, p.N - n0);  // multiple of 8
+    const size_t roff = (size_t)row * p.ldr + n0;
+    const size_t ooff = (size_t)row * p.ldo + n0;
+
+    if (p.epi == EPI_ACCUM_F32) {
+      if (row_ok) {
+        float* o = reinterpret_cast<float*>(p.out) + ooff;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (j < ncols) {
+            if (p.k_splits > 1) {
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j), "f"(f[j]),
+                           "f"(f[j + 1]), "f"(f[j + 2]), "f"(f[j + 3])
+                           : "memory");
+            } else {
+              float4 cur = *reinterpret_cast<float4*>(o + j);
+              cur.x += f[j]; cur.y += f[j + 1]; cur.z += f[j + 2]; cur.w += f[j + 3];
+              *reinterpret_cast<float4*>(o + j) = cur;
+            }
+          }
+        }
+      }
+      continue;
+    }
+    if (p.epi == EPI_F32) {
+      if (row_ok) {
+        float* o = reinterpret_cast<float*>(p.out) + ooff;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          if (j < ncols) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+      }
+      continue;
+    }
+    // ---- bias (same 32 values for every lane: broadcast loads)
+    if (p.epi == EPI_BIAS || p.epi == EPI_BIAS_GELU || p.epi == EPI_BIAS_DROP_RES || p.epi == EPI_BIAS_TANH) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        if (g * 8 < ncols) {
+          const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.bias + n0 + g * 8));
+          const uint32_t w[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 bb = unpack_bf16(w[t]);
+            f[g * 8 + 2 * t] += bb.x;
+            f[g * 8 + 2 * t + 1] += bb.y;
+          }
+        }
+      }
+    }
+    if (p.epi == EPI_BIAS_GELU) {
+      if (row_ok) {  // save the pre-activation, then activate
+        __nv_bfloat16* a = p.aux_out + ooff;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          if (g * 8 < ncols)
+            *reinterpret_cast<uint4*>(a + g * 8) =
+                make_uint4(pack_bf16(f[g * 8], f[g * 8 + 1]), pack_bf16(f[g * 8 + 2], f[g * 8 + 3]),
+                           pack_bf16(f[g * 8 + 4], f[g * 8 + 5]), pack_bf16(f[g * 8 + 6], f[g * 8 + 7]));
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+    } else if (p.epi == EPI_BIAS_TANH) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = tanhf(f[j]);
+    } else if (p.epi == EPI_BIAS_DROP_RES || p.epi == EPI_ADD || p.epi == EPI_DGELU) {
+      if (p.epi == EPI_BIAS_DROP_RES && p.drop_thresh16 != 0 && row_ok) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (g * 8 < ncols) {
+            const uint64_t e8 = ((uint64_t)row * (uint64_t)p.N + (uint64_t)(n0 + g * 8)) >> 3;
+            const uint32_t keep = dropout_keep8(p.seed, p.stream, e8, p.drop_thresh16);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) f[g * 8 + t] = ((keep >> t) & 1u) ? f[g * 8 + t] * p.drop_scale : 0.f;
+          }
+        }
+      }
+      if (row_ok && p.res != nullptr) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (g * 8 < ncols) {
+            const uint4 r = *reinterpret_cast<const uint4*>(p.res + roff + g * 8);
+            const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 rr = unpack_bf16(w[t]);
+              if (p.epi == EPI_DGELU) {
+                f[g * 8 + 2 * t] *= dgelu_erf(rr.x);
+                f[g * 8 + 2 * t + 1] *= dgelu_erf(rr.y);
+              } else {
+                f[g * 8 + 2 * t] += rr.x;
+                f[g * 8 + 2 * t + 1] += rr.y;
+              }
+            }
+          }
+        }
+      }
+    }
+    if (row_ok) {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + ooff;
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        if (g * 8 < ncols)
+          *reinterpret_cast<uint4*>(o + g * 8) =
+              make_uint4(pack_bf16(f[g * 8], f[g * 8 + 1]), pack_bf16(f[g * 8 + 2], f[g * 8 + 3]),
+                         pack_bf16(f[g * 8 + 4], f[g * 8 + 5]), pack_bf16(f[g * 8 + 6], f[g * 8 + 7]));
+    }
+  }
+}
+
 template <bool A_MN, bool B_MN, int BLOCK_N>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -182,123 +305,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const int row = mb * BLOCK_M + q * 32 + lane;
       const bool row_ok = row < p.M && kb1 > kb0;
       const uint32_t taddr = tmem_base + as * BLOCK_N + (uint32_t(q * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        const int n0 = nb * BLOCK_N + c * 32;
-        if (n0 >= p.N) break;  // warp uniform
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + c * 32, v);
-        tmem_ld_wait();
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
-        const int ncols = min(32, p.N - n0);  // multiple of 8
-        const size_t roff = (size_t)row * p.ldr + n0;
-        const size_t ooff = (size_t)row * p.ldo + n0;
-
-        if (p.epi == EPI_ACCUM_F32) {
-          if (row_ok) {
-            float* o = reinterpret_cast<float*>(p.out) + ooff;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (j < ncols) {
-                if (p.k_splits > 1) {
-                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j), "f"(f[j]),
-                               "f"(f[j + 1]), "f"(f[j + 2]), "f"(f[j + 3])
-                               : "memory");
-                } else {
-                  float4 cur = *reinterpret_cast<float4*>(o + j);
-                  cur.x += f[j]; cur.y += f[j + 1]; cur.z += f[j + 2]; cur.w += f[j + 3];
-                  *reinterpret_cast<float4*>(o + j) = cur;
-                }
-              }
-            }
-          }
-          continue;
-        }
-        if (p.epi == EPI_F32) {
-          if (row_ok) {
-            float* o = reinterpret_cast<float*>(p.out) + ooff;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              if (j < ncols) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-          }
-          continue;
-        }
-        // ---- bias (same 32 values for every lane: broadcast loads)
-        if (p.epi == EPI_BIAS || p.epi == EPI_BIAS_GELU || p.epi == EPI_BIAS_DROP_RES || p.epi == EPI_BIAS_TANH) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if (g * 8 < ncols) {
-              const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.bias + n0 + g * 8));
-              const uint32_t w[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const float2 bb = unpack_bf16(w[t]);
-                f[g * 8 + 2 * t] += bb.x;
-                f[g * 8 + 2 * t + 1] += bb.y;
-              }
-            }
-          }
-        }
-        if (p.epi == EPI_BIAS_GELU) {
-          if (row_ok) {  // save the pre-activation, then activate
-            __nv_bfloat16* a = p.aux_out + ooff;
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-              if (g * 8 < ncols)
-                *reinterpret_cast<uint4*>(a + g * 8) =
-                    make_uint4(pack_bf16(f[g * 8], f[g * 8 + 1]), pack_bf16(f[g * 8 + 2], f[g * 8 + 3]),
-                               pack_bf16(f[g * 8 + 4], f[g * 8 + 5]), pack_bf16(f[g * 8 + 6], f[g * 8 + 7]));
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-        } else if (p.epi == EPI_BIAS_TANH) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = tanhf(f[j]);
-        } else if (p.epi == EPI_BIAS_DROP_RES || p.epi == EPI_ADD || p.epi == EPI_DGELU) {
-          if (p.epi == EPI_BIAS_DROP_RES && p.drop_thresh16 != 0 && row_ok) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              if (g * 8 < ncols) {
-                const uint64_t e8 = ((uint64_t)row * (uint64_t)p.N + (uint64_t)(n0 + g * 8)) >> 3;
-                const uint32_t keep = dropout_keep8(p.seed, p.stream, e8, p.drop_thresh16);
-#pragma unroll
-                for (int t = 0; t < 8; ++t) f[g * 8 + t] = ((keep >> t) & 1u) ? f[g * 8 + t] * p.drop_scale : 0.f;
-              }
-            }
-          }
-          if (row_ok && p.res != nullptr) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              if (g * 8 < ncols) {
-                const uint4 r = *reinterpret_cast<const uint4*>(p.res + roff + g * 8);
-                const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                  const float2 rr = unpack_bf16(w[t]);
-                  if (p.epi == EPI_DGELU) {
-                    f[g * 8 + 2 * t] *= dgelu_erf(rr.x);
-                    f[g * 8 + 2 * t + 1] *= dgelu_erf(rr.y);
-                  } else {
-                    f[g * 8 + 2 * t] += rr.x;
-                    f[g * 8 + 2 * t + 1] += rr.y;
-                  }
-                }
-              }
-            }
-          }
-        }
-        if (row_ok) {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + ooff;
-#pragma unroll
-          for (int g = 0; g < 4; ++g)
-            if (g * 8 < ncols)
-              *reinterpret_cast<uint4*>(o + g * 8) =
-                  make_uint4(pack_bf16(f[g * 8], f[g * 8 + 1]), pack_bf16(f[g * 8 + 2], f[g * 8 + 3]),
-                             pack_bf16(f[g * 8 + 4], f[g * 8 + 5]), pack_bf16(f[g * 8 + 6], f[g * 8 + 7]));
-        }
-      }
+      epilogue_tile<BLOCK_N>(p, taddr, row, row_ok, nb * BLOCK_N);
       tc_fence_before();
       mbar_arrive(&tmem_empty[as]);
     }
@@ -309,6 +316,146 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant: a 2-CTA cluster (the two SMs of a TPC) computes one 256 x 256 tile with
+// tcgen05.mma.cta_group::2.  Each CTA stages its own 128 rows of A and its own 128 columns of B per
+// k-block (32 KB -> a 6-deep ring) and the tensor cores of both SMs read both halves, so the L2 -> SM
+// operand traffic per FLOP is half that of the single-CTA 128 x 256 tile -- which is what limits that
+// kernel (ncu: lts throughput ~42%, nothing else saturated).  Only the leader CTA (cluster rank 0)
+// issues MMAs; completion is multicast to both CTAs' barriers; both CTAs run the epilogue on their own
+// 128 accumulator rows (TMEM lanes).
+// ------------------------------------------------------------------------------------------------
+constexpr int PAIR_M = 256, PAIR_N = 256, PAIR_STAGE = 32768, PAIR_STAGES = 6;
+constexpr int PAIR_SMEM = PAIR_STAGES * PAIR_STAGE + 1024 + 256;
+
+template <bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const GemmArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + PAIR_STAGES * PAIR_STAGE);
+  uint64_t* empty_bar = full_bar + PAIR_STAGES;
+  uint64_t* tmem_full = empty_bar + PAIR_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < PAIR_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 256);   // 128 epilogue threads in each CTA of the pair
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc_2sm(tmem_base_slot, 512);
+  tc_fence_before();
+  cluster_sync_all();                    // peer barriers are initialised before anything remote touches them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+  const int total_tiles = p.m_blocks * p.n_blocks * p.k_splits;
+
+  if (warp == 0) {
+    if (lane == 0) {                     // ---------------- TMA producer (both CTAs)
+      uint32_t it = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += nclusters) {
+        const int nb = tile % p.n_blocks;
+        const int mb = (tile / p.n_blocks) % p.m_blocks;
+        const int ks = tile / (p.n_blocks * p.m_blocks);
+        const int kb0 = ks * p.k_per_split;
+        const int kb1 = min(p.k_blocks, kb0 + p.k_per_split);
+        const int m0 = mb * PAIR_M + (int)rank * 128, n0 = nb * PAIR_N + (int)rank * 128;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % PAIR_STAGES;
+          const uint32_t ph = (it / PAIR_STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * PAIR_STAGE;
+          uint8_t* sb = sa + 16384;
+          if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * PAIR_STAGE);
+          const uint32_t fb = mapa_shared(smem_u32(&full_bar[s]), 0);
+          if constexpr (!A_MN) {
+            tma_load_2d_2sm(sa, &tmap_a, fb, kb * BLOCK_K, m0);
+          } else {
+            tma_load_2d_2sm(sa, &tmap_a, fb, m0, kb * BLOCK_K);
+            tma_load_2d_2sm(sa + 8192, &tmap_a, fb, m0 + 64, kb * BLOCK_K);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d_2sm(sb, &tmap_b, fb, kb * BLOCK_K, n0);
+          } else {
+            tma_load_2d_2sm(sb, &tmap_b, fb, n0, kb * BLOCK_K);
+            tma_load_2d_2sm(sb + 8192, &tmap_b, fb, n0 + 64, kb * BLOCK_K);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {           // ---------------- MMA issuer (leader CTA only)
+      constexpr uint32_t idesc = umma_idesc_bf16(PAIR_M, PAIR_N, A_MN, B_MN);
+      uint32_t it = 0, tile_it = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += nclusters, ++tile_it) {
+        const int ks = tile / (p.n_blocks * p.m_blocks);
+        const int kb0 = ks * p.k_per_split;
+        const int kb1 = min(p.k_blocks, kb0 + p.k_per_split);
+        const uint32_t as = tile_it & 1, aph = (tile_it >> 1) & 1;
+        mbar_wait(&tmem_empty[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * PAIR_N;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % PAIR_STAGES;
+          const uint32_t ph = (it / PAIR_STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * PAIR_STAGE);
+          const uint32_t sb = sa + 16384;
+          const uint64_t da0 = A_MN ? umma_smem_desc_sw128(sa, 8192, 1024) : umma_smem_desc_sw128(sa, 16, 1024);
+          const uint64_t db0 = B_MN ? umma_smem_desc_sw128(sb, 8192, 1024) : umma_smem_desc_sw128(sb, 16, 1024);
+#pragma unroll
+          for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+            const uint64_t da = da0 + (uint64_t)(A_MN ? (kk * 2048) >> 4 : (kk * 32) >> 4);
+            const uint64_t db = db0 + (uint64_t)(B_MN ? (kk * 2048) >> 4 : (kk * 32) >> 4);
+            umma_bf16_ss_2sm(tmem_d, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty_bar[s], 3);     // both CTAs may refill this slot
+        }
+        umma_commit_2sm(&tmem_full[as], 3);      // both CTAs' epilogues may drain
+      }
+    }
+  } else {                               // ---------------- epilogue (both CTAs, own 128 rows)
+    const int q = warp & 3;
+    uint32_t tile_it = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += nclusters, ++tile_it) {
+      const int nb = tile % p.n_blocks;
+      const int mb = (tile / p.n_blocks) % p.m_blocks;
+      const uint32_t as = tile_it & 1, aph = (tile_it >> 1) & 1;
+      mbar_wait(&tmem_full[as], aph);
+      tc_fence_after();
+      const int row = mb * PAIR_M + (int)rank * 128 + q * 32 + lane;
+      const uint32_t taddr = tmem_base + as * PAIR_N + (uint32_t(q * 32) << 16);
+      epilogue_tile<PAIR_N>(p, taddr, row, row < p.M, nb * PAIR_N);
+      tc_fence_before();
+      mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), 0));
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();                    // nobody exits while the peer can still signal or read its smem
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
   }
 }
 
@@ -423,7 +570,53 @@ static void launch(const GemmCall& c, cudaStream_t st) {
   kern<<<grid, NUM_THREADS, C::SMEM_TOTAL, st>>>(ta, tb, p);
 }
 
+template <bool A_MN, bool B_MN>
+static void launch_pair(const GemmCall& c, cudaStream_t st) {
+  GemmArgs p;
+  p.M = c.M; p.N = c.N; p.K = c.K;
+  p.m_blocks = (c.M + PAIR_M - 1) / PAIR_M;
+  p.n_blocks = (c.N + PAIR_N - 1) / PAIR_N;
+  p.k_blocks = (c.K + BLOCK_K - 1) / BLOCK_K;
+  p.k_splits = c.k_splits < 1 ? 1 : c.k_splits;
+  if (p.k_splits > p.k_blocks) p.k_splits = p.k_blocks;
+  p.k_per_split = (p.k_blocks + p.k_splits - 1) / p.k_splits;
+  p.k_splits = (p.k_blocks + p.k_per_split - 1) / p.k_per_split;
+  p.epi = c.epi;
+  p.out = c.out; p.ldo = c.ldo; p.aux_out = reinterpret_cast<__nv_bfloat16*>(c.aux_out);
+  p.bias = reinterpret_cast<const __nv_bfloat16*>(c.bias);
+  p.res = reinterpret_cast<const __nv_bfloat16*>(c.res); p.ldr = c.ldr;
+  p.seed = c.seed; p.stream = c.stream;
+  float pd = c.p_drop;
+  p.drop_thresh16 = pd > 0.f ? (unsigned)(pd * 65536.f + 0.5f) : 0u;
+  p.drop_scale = pd > 0.f ? 65536.f / (65536.f - (float)p.drop_thresh16) : 1.f;
+  p.alpha = c.alpha;
+  // each CTA loads 128-row boxes of A and 128-column boxes of B
+  CUtensorMap ta = A_MN ? make_tmap_2d_bf16(c.A, c.M, c.K, c.lda, 64, BLOCK_K)
+                        : make_tmap_2d_bf16(c.A, c.K, c.M, c.lda, BLOCK_K, 128);
+  CUtensorMap tb = B_MN ? make_tmap_2d_bf16(c.B, c.N, c.K, c.ldb, 64, BLOCK_K)
+                        : make_tmap_2d_bf16(c.B, c.K, c.N, c.ldb, BLOCK_K, 128);
+  auto kern = gemm_pair_kernel<A_MN, B_MN>;
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
+    configured = true;
+  }
+  const int tiles = p.m_blocks * p.n_blocks * p.k_splits;
+  const int pairs = num_sms() / 2;
+  const int grid = 2 * (tiles < pairs ? tiles : pairs);
+  if (grid <= 0) return;
+  kern<<<grid, NUM_THREADS, PAIR_SMEM, st>>>(ta, tb, p);
+}
+
 void gemm_bf16(const GemmCall& c, cudaStream_t st) {
+  if (c.block_n == 512) {   // CTA-pair 256 x 256 tiles
+    switch (c.layout) {
+      case GEMM_NT: launch_pair<false, false>(c, st); return;
+      case GEMM_NN: launch_pair<false, true>(c, st); return;
+      case GEMM_TN: launch_pair<true, true>(c, st); return;
+      default: fprintf(stderr, "[b200] bad gemm layout %d\n", c.layout); abort();
+    }
+  }
   const bool wide = c.block_n == 256;
   switch (c.layout) {
     case GEMM_NT: wide ? launch<false, false, 256>(c, st) : launch<false, false, 128>(c, st); break;

@@ -27,7 +27,7 @@ def _check(out, ref, tol=2e-2):
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 128), (384, 1024, 1024), (1000, 512, 320),
                                    (4096, 3072, 1024), (130, 264, 72)])
-@pytest.mark.parametrize("block_n", [128, 256])
+@pytest.mark.parametrize("block_n", [128, 256, 512])
 def test_gemm_nt(M, N, K, block_n):
     K_ = _ops()
     a, b = _rand(M, K), _rand(N, K)
@@ -36,7 +36,7 @@ def test_gemm_nt(M, N, K, block_n):
 
 
 @pytest.mark.parametrize("M,N,K", [(256, 256, 128), (512, 1024, 4096), (1000, 320, 512)])
-@pytest.mark.parametrize("block_n", [128, 256])
+@pytest.mark.parametrize("block_n", [128, 256, 512])
 def test_gemm_nn(M, N, K, block_n):
     K_ = _ops()
     a, b = _rand(M, K), _rand(K, N)
@@ -45,7 +45,7 @@ def test_gemm_nn(M, N, K, block_n):
 
 
 @pytest.mark.parametrize("M,N,K", [(256, 256, 128), (1024, 1024, 4096), (320, 520, 1000)])
-@pytest.mark.parametrize("block_n,splits", [(128, 1), (256, 1), (256, 4)])
+@pytest.mark.parametrize("block_n,splits", [(128, 1), (256, 1), (256, 4), (512, 1), (512, 3)])
 def test_gemm_tn_accumulate(M, N, K, block_n, splits):
     K_ = _ops()
     a, b = _rand(K, M), _rand(K, N)
@@ -55,8 +55,13 @@ def test_gemm_tn_accumulate(M, N, K, block_n, splits):
     _check(out, base + a.float().t() @ b.float(), tol=1e-2)
 
 
-def test_gemm_epilogues():
+@pytest.mark.parametrize("bn", [256, 512])
+def test_gemm_epilogues(bn):
+    import functools
     K_ = _ops()
+    real_gemm = K_.gemm
+    K_ = type("Bn", (), {k: getattr(K_, k) for k in dir(K_) if k.startswith("EPI_") or k in ("NT", "NN", "TN")})
+    K_.gemm = staticmethod(functools.partial(real_gemm, block_n=bn))
     M, N, Kd = 512, 1024, 256
     a, b, bias, res = _rand(M, Kd), _rand(N, Kd), _rand(N), _rand(M, N)
     ref = a.float() @ b.float().t()
@@ -90,3 +95,12 @@ def test_gemm_dropout_statistics_and_determinism():
     frac = 1.0 - kept.float().mean().item()
     assert abs(frac - 0.1) < 0.01, frac
     assert torch.allclose(d1[kept], full[kept] / 0.9, rtol=2e-2, atol=2e-2)
+
+
+def test_gemm_pair_many_tiles_and_tails():
+    """More tiles than clusters (persistent loop, TMEM double buffering, ring wrap) and ragged M/N edges."""
+    K_ = _ops()
+    for (M, N, Kd) in [(12288, 1024, 1024), (1000, 1000, 520), (257, 264, 64), (4096, 30528, 256)]:
+        a, b = _rand(M, Kd), _rand(N, Kd)
+        out = K_.gemm(a, b, layout=K_.NT, block_n=512)
+        _check(out, a.float() @ b.float().t())

@@ -50,7 +50,7 @@ def main():
         rec = {"name": name, "M": m, "N": n, "K": k}
         t_ref = timeit(ref)
         rec["cublas_ms"], rec["cublas_tflops"] = round(t_ref, 4), round(flops / t_ref / 1e9, 1)
-        for bn in (128, 256):
+        for bn in (256, 512):
             if layout == K.TN:
                 o = torch.zeros(m, n, device="cuda")
                 for sp in (1, 2, 4, 8):
