@@ -253,6 +253,43 @@ void attention_bwd(Tensor qkv, Tensor seqlens, Tensor ctx, Tensor dctx, Tensor l
                       (unsigned long long)seed, (unsigned)stream_id, (float)p_drop, cur_stream());
 }
 
+void fused_allreduce_lamb(int64_t rank, int64_t world, bool use_multicast, std::vector<int64_t> grad_ptrs,
+                          std::vector<int64_t> param_ptrs, std::vector<int64_t> shadow_ptrs, std::vector<int64_t> pad_ptrs,
+                          std::vector<int64_t> flag_ptrs, int64_t grad_mc, int64_t param_mc, int64_t shadow_mc, Tensor m,
+                          Tensor v, int64_t numel, int64_t lo, int64_t hi, Tensor chunk_tensor, Tensor chunk_start,
+                          Tensor chunk_len, Tensor decay_flag, Tensor stats, Tensor norms, Tensor grid_bar, int64_t epoch,
+                          double grad_mul, double lr, double beta1, double beta2, double eps, double weight_decay,
+                          double max_grad_norm, int64_t step, bool bias_correction, bool grad_averaging,
+                          bool adam_w_mode, bool use_nvlamb) {
+  TORCH_CHECK((int64_t)grad_ptrs.size() == world && world <= 16, "peer pointer lists must have `world` (<= 16) entries");
+  TORCH_CHECK(lo % 4 == 0 && hi % 4 == 0 && numel % 4 == 0, "shard bounds must be multiples of 4 elements");
+  c10::cuda::CUDAGuard guard(m.device());
+  b200::FusedLambLaunch L;
+  L.rank = (int)rank; L.world = (int)world; L.use_multicast = use_multicast ? 1 : 0;
+  for (int p = 0; p < world; ++p) {
+    L.grad_ptrs[p] = reinterpret_cast<const void*>(grad_ptrs[p]);
+    L.param_ptrs[p] = reinterpret_cast<const void*>(param_ptrs[p]);
+    L.shadow_ptrs[p] = reinterpret_cast<const void*>(shadow_ptrs[p]);
+    L.pad_ptrs[p] = reinterpret_cast<const void*>(pad_ptrs[p]);
+    L.flag_ptrs[p] = reinterpret_cast<const void*>(flag_ptrs[p]);
+  }
+  L.grad_mc = reinterpret_cast<void*>(grad_mc); L.param_mc = reinterpret_cast<void*>(param_mc);
+  L.shadow_mc = reinterpret_cast<void*>(shadow_mc);
+  L.m = m.data_ptr<float>(); L.v = v.data_ptr<float>();
+  L.numel = numel; L.lo = lo; L.hi = hi;
+  L.chunk_tensor = chunk_tensor.data_ptr<int>(); L.chunk_start = (const long long*)chunk_start.data_ptr<int64_t>();
+  L.chunk_len = chunk_len.data_ptr<int>(); L.nchunks = (int)chunk_tensor.numel(); L.ntensors = (int)decay_flag.numel();
+  L.decay_flag = decay_flag.data_ptr<int>();
+  L.stats = stats.data_ptr<float>(); L.norms = norms.data_ptr<float>();
+  L.grid_bar = reinterpret_cast<unsigned int*>(grid_bar.data_ptr<int>());
+  L.epoch = (unsigned int)epoch;
+  L.grad_mul = (float)grad_mul; L.lr = (float)lr; L.beta1 = (float)beta1; L.beta2 = (float)beta2; L.eps = (float)eps;
+  L.weight_decay = (float)weight_decay; L.max_grad_norm = (float)max_grad_norm; L.step = (int)step;
+  L.bias_correction = bias_correction; L.grad_averaging = grad_averaging; L.adam_w_mode = adam_w_mode;
+  L.use_nvlamb = use_nvlamb;
+  b200::fused_allreduce_lamb(L, cur_stream());
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -276,4 +313,5 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("arena_adam", &arena_adam);
   m.def("attention_fwd", &attention_fwd);
   m.def("attention_bwd", &attention_bwd);
+  m.def("fused_allreduce_lamb", &fused_allreduce_lamb);
 }

@@ -1,0 +1,308 @@
+// Fused gradient all-reduce + unscale + partitioned LAMB + parameter all-gather over NVLink peer memory.
+// ONE persistent cooperative kernel per optimizer step and rank; no NCCL call on this path
+// (algorithm spec: parallel/sharded_lamb.py).
+//
+// Every rank maps every peer's gradient arena, fp32 parameter arena, bf16 shadow arena and a small
+// scratch/flag pad (CUDA VMM symmetric memory; the handles are exchanged by the host once).  Rank r owns the
+// contiguous shard [lo_r, hi_r) of the flat arena.  Phases (grid barriers inside the kernel, cross-GPU
+// barriers through release/acquire flags in peer memory):
+//   0  cross-GPU barrier: every rank's backward has finished writing its gradient arena
+//   A  reduce-scatter: g[i] = (sum_p grad_p[i]) / (world * loss_scale) for i in the own shard, read from the
+//      peers with plain P2P loads (or one multimem.ld_reduce through the NVLS multicast mapping);
+//      inf/nan flag + partial sum of squares
+//   1  all ranks exchange {sum g^2, found_inf} (P2P stores into the peers' pads) -> global grad norm; a set
+//      found_inf makes every rank skip the update identically (GradScaler semantics, decided on device)
+//   B  LAMB moments + update direction u on the shard, partial per-tensor ||p||^2, ||u||^2 (tensors may
+//      straddle shard boundaries -> per-tensor partials)
+//   2  exchange of the per-tensor partial norms
+//   C  p -= lr * trust_ratio * u on the shard; new fp32 values and bf16 shadow are stored straight into every
+//      peer's arenas (all-gather by P2P / multimem stores); the whole local gradient arena is zeroed
+//   3  cross-GPU barrier: all pushes have landed before anyone's next forward reads the weights
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b200 {
+
+constexpr int FUSED_THREADS = 512;
+constexpr int MAX_WORLD = 16;
+
+struct FusedLambArgs {
+  int rank, world, use_multicast;
+  float* grad[MAX_WORLD];                 // peers' gradient arenas (grad[rank] is local)
+  float* param[MAX_WORLD];                // peers' fp32 parameter arenas
+  __nv_bfloat16* shadow[MAX_WORLD];       // peers' bf16 shadow arenas
+  float* pad[MAX_WORLD];                  // peers' scratch pads: [world][2 + 2*T] floats of exchange space
+  unsigned int* flags[MAX_WORLD];         // peers' flag arrays: [4][world] epoch counters
+  float* grad_mc;                         // multicast mappings (nullptr when unavailable)
+  float* param_mc;
+  __nv_bfloat16* shadow_mc;
+  float* m;                               // local moments (arena sized; only the shard is touched)
+  float* v;
+  long long numel, lo, hi;
+  const int* chunk_tensor;                // chunk table of the arena restricted to [lo, hi)
+  const long long* chunk_start;
+  const int* chunk_len;
+  int nchunks, ntensors;
+  const int* decay_flag;
+  float* stats;                           // local [4]: sumsq, found_inf, global sumsq, global inf
+  float* norms;                           // local [2T] partial norms
+  unsigned int* grid_bar;                 // local grid barrier counter (zeroed before launch)
+  unsigned int epoch;
+  float grad_mul;                         // 1 / (world * loss_scale)
+  float lr, beta1, beta2, beta3, eps, weight_decay, bc1, bc2, max_grad_norm;
+  int adam_w_mode, use_nvlamb;
+};
+
+__device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int& gen) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    const unsigned int target = (gen + 1) * gridDim.x;
+    const uint64_t t0 = globaltimer_ns();
+    unsigned int cur;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(bar) : "memory");
+      if (globaltimer_ns() - t0 > B200_WATCHDOG_NS) { printf("[b200] grid barrier watchdog (block %d)\n", blockIdx.x); __trap(); }
+    } while (cur < target);
+  }
+  __syncthreads();
+  ++gen;
+}
+
+// full barrier across the ranks, executed by block 0 (callers follow it with a grid_sync)
+__device__ __forceinline__ void peer_barrier(const FusedLambArgs& a, int slot) {
+  if (blockIdx.x == 0) {
+    __syncthreads();
+    if (threadIdx.x < a.world) {
+      const int peer = threadIdx.x;
+      __threadfence_system();
+      unsigned int* dst = a.flags[peer] + slot * a.world + a.rank;
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(a.epoch) : "memory");
+      const unsigned int* src = a.flags[a.rank] + slot * a.world + peer;
+      const uint64_t t0 = globaltimer_ns();
+      unsigned int cur;
+      do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(cur) : "l"(src) : "memory");
+        if (globaltimer_ns() - t0 > 4 * B200_WATCHDOG_NS) {
+          printf("[b200] peer barrier watchdog: rank %d waits for rank %d slot %d epoch %u (saw %u)\n", a.rank, peer,
+                 slot, a.epoch, cur);
+          __trap();
+        }
+      } while ((int)(cur - a.epoch) < 0);
+    }
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ float block_sum_f(float v, float* sm) {
+  v = warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) sm[warp] = v;
+  __syncthreads();
+  float r = 0.f;
+  if (warp == 0) {
+    r = lane < (blockDim.x >> 5) ? sm[lane] : 0.f;
+    r = warp_sum(r);
+  }
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(FUSED_THREADS, 1) fused_allreduce_lamb_kernel(const FusedLambArgs a) {
+  __shared__ float sm[32];
+  __shared__ float s_bcast[4];
+  unsigned int gen = 0;
+  const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long gstride = (long long)gridDim.x * blockDim.x;
+  float* lgrad = a.grad[a.rank];
+  float* lparam = a.param[a.rank];
+
+  // ---- phase 0: everyone's gradients are complete
+  if (gtid < 2 * a.ntensors) a.norms[gtid] = 0.f;
+  if (gtid < 2) a.stats[gtid] = 0.f;
+  peer_barrier(a, 0);
+  grid_sync(a.grid_bar, gen);
+
+  // ---- phase A: reduce-scatter the own shard
+  {
+    const long long n4 = (a.hi - a.lo) >> 2;
+    float sq = 0.f;
+    bool bad = false;
+    for (long long i = gtid; i < n4; i += gstride) {
+      const long long off = a.lo + (i << 2);
+      float4 acc;
+      if (a.use_multicast) {
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(acc.x), "=f"(acc.y), "=f"(acc.z), "=f"(acc.w) : "l"(a.grad_mc + off) : "memory");
+      } else {
+        acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+        for (int p = 0; p < a.world; ++p) {           // fixed rank order: bitwise identical on every rank
+          float4 g;
+          asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(g.x), "=f"(g.y), "=f"(g.z), "=f"(g.w) : "l"(a.grad[p] + off) : "memory");
+          acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+        }
+      }
+      acc.x *= a.grad_mul; acc.y *= a.grad_mul; acc.z *= a.grad_mul; acc.w *= a.grad_mul;
+      const float q = acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
+      bad |= !isfinite(q);
+      sq += q;
+      *reinterpret_cast<float4*>(lgrad + off) = acc;   // own shard: no peer reads this region
+    }
+    sq = block_sum_f(sq, sm);
+    if (threadIdx.x == 0) atomicAdd(a.stats, sq);
+    if (bad) a.stats[1] = 1.f;
+  }
+  grid_sync(a.grid_bar, gen);
+
+  // ---- sync 1: exchange {sumsq, inf}
+  if (blockIdx.x == 0 && threadIdx.x < a.world) {
+    float* dst = a.pad[threadIdx.x] + a.rank * 2;
+    const float s0 = a.stats[0], s1 = a.stats[1];
+    asm volatile("st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(dst), "f"(s0), "f"(s1) : "memory");
+  }
+  peer_barrier(a, 1);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    float sq = 0.f, inf = 0.f;
+    const float* mine = a.pad[a.rank];
+    for (int p = 0; p < a.world; ++p) {
+      float x, y;
+      asm volatile("ld.relaxed.sys.global.v2.f32 {%0, %1}, [%2];" : "=f"(x), "=f"(y) : "l"(mine + p * 2) : "memory");
+      sq += x; inf += y;
+    }
+    a.stats[2] = sq;
+    a.stats[3] = inf;
+  }
+  grid_sync(a.grid_bar, gen);
+  const float gsumsq = a.stats[2];
+  const bool skip = a.stats[3] != 0.f || !isfinite(gsumsq);
+
+  // ---- phase B: moments + update direction on the shard, per-tensor partial norms
+  if (!skip) {
+    const float gnorm = sqrtf(gsumsq);
+    const float clip = (a.max_grad_norm > 0.f && gnorm > a.max_grad_norm) ? gnorm / a.max_grad_norm : 1.f;
+    const float inv_clip = 1.f / clip;
+    for (int c = blockIdx.x; c < a.nchunks; c += gridDim.x) {
+      const int t = a.chunk_tensor[c];
+      const long long off = a.chunk_start[c];
+      const int n = a.chunk_len[c];
+      const float wd = a.decay_flag[t] ? a.weight_decay : 0.f;
+      float sp = 0.f, su = 0.f;
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        float g = lgrad[off + i] * inv_clip;
+        const float pp = lparam[off + i];
+        if (!a.adam_w_mode) g += wd * pp;
+        const float mm = a.beta1 * a.m[off + i] + a.beta3 * g;
+        const float vv = a.beta2 * a.v[off + i] + (1.f - a.beta2) * g * g;
+        float u = (mm / a.bc1) / (sqrtf(vv / a.bc2) + a.eps);
+        if (a.adam_w_mode) u += wd * pp;
+        a.m[off + i] = mm; a.v[off + i] = vv;
+        lgrad[off + i] = u;
+        sp += pp * pp; su += u * u;
+      }
+      sp = block_sum_f(sp, sm);
+      su = block_sum_f(su, sm);
+      if (threadIdx.x == 0) {
+        atomicAdd(a.norms + 2 * t, sp);
+        atomicAdd(a.norms + 2 * t + 1, su);
+      }
+    }
+  }
+  grid_sync(a.grid_bar, gen);
+
+  // ---- sync 2: exchange the per-tensor partial norms
+  if (!skip && blockIdx.x == 0) {
+    const int per = 2 * a.ntensors;
+    for (int idx = threadIdx.x; idx < per * a.world; idx += blockDim.x) {
+      const int p = idx / per, j = idx % per;
+      float* dst = a.pad[p] + 2 * a.world + a.rank * per + j;
+      asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(dst), "f"(a.norms[j]) : "memory");
+    }
+  }
+  peer_barrier(a, 2);
+  grid_sync(a.grid_bar, gen);
+
+  // ---- phase C: apply on the shard, push fp32 + bf16 to every rank, zero the local gradients
+  if (!skip) {
+    const int per = 2 * a.ntensors;
+    const float* mine = a.pad[a.rank] + 2 * a.world;
+    for (int c = blockIdx.x; c < a.nchunks; c += gridDim.x) {
+      const int t = a.chunk_tensor[c];
+      const long long off = a.chunk_start[c];
+      const int n = a.chunk_len[c];
+      if (threadIdx.x == 0) {
+        float ratio = a.lr;
+        if (a.use_nvlamb || (a.decay_flag[t] && a.weight_decay != 0.f)) {
+          float pn = 0.f, un = 0.f;
+          for (int p = 0; p < a.world; ++p) {
+            float x, y;
+            asm volatile("ld.relaxed.sys.global.v2.f32 {%0, %1}, [%2];" : "=f"(x), "=f"(y)
+                         : "l"(mine + p * per + 2 * t) : "memory");
+            pn += x; un += y;
+          }
+          pn = sqrtf(pn); un = sqrtf(un);
+          if (pn > 0.f && un > 0.f) ratio = a.lr * pn / un;
+        }
+        s_bcast[0] = ratio;
+      }
+      __syncthreads();
+      const float ratio = s_bcast[0];
+      // chunks start on multiples of 4 elements except at tensor tails: scalar path keeps it simple and the
+      // stores still coalesce (consecutive threads -> consecutive addresses)
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float np = lparam[off + i] - ratio * lgrad[off + i];
+        const __nv_bfloat16 nb = __float2bfloat16(np);
+        if (a.use_multicast) {
+          asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(a.param_mc + off + i), "f"(np) : "memory");
+        } else {
+#pragma unroll 1
+          for (int p = 0; p < a.world; ++p) a.param[p][off + i] = np;
+        }
+#pragma unroll 1
+        for (int p = 0; p < a.world; ++p) a.shadow[p][off + i] = nb;
+      }
+      __syncthreads();
+    }
+  }
+  // zero the whole local gradient arena (all peers finished reading it: they passed barrier 1)
+  {
+    float4* g4 = reinterpret_cast<float4*>(lgrad);
+    const long long n4 = a.numel >> 2;
+    for (long long i = gtid; i < n4; i += gstride) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  grid_sync(a.grid_bar, gen);
+  peer_barrier(a, 3);
+}
+
+void fused_allreduce_lamb(const FusedLambLaunch& L, cudaStream_t st) {
+  FusedLambArgs a;
+  a.rank = L.rank; a.world = L.world; a.use_multicast = L.use_multicast;
+  if (L.world > MAX_WORLD) { fprintf(stderr, "[b200] fused all-reduce supports <= %d ranks\n", MAX_WORLD); abort(); }
+  for (int p = 0; p < L.world; ++p) {
+    a.grad[p] = (float*)L.grad_ptrs[p]; a.param[p] = (float*)L.param_ptrs[p];
+    a.shadow[p] = (__nv_bfloat16*)L.shadow_ptrs[p]; a.pad[p] = (float*)L.pad_ptrs[p];
+    a.flags[p] = (unsigned int*)L.flag_ptrs[p];
+  }
+  a.grad_mc = (float*)L.grad_mc; a.param_mc = (float*)L.param_mc; a.shadow_mc = (__nv_bfloat16*)L.shadow_mc;
+  a.m = L.m; a.v = L.v; a.numel = L.numel; a.lo = L.lo; a.hi = L.hi;
+  a.chunk_tensor = L.chunk_tensor; a.chunk_start = L.chunk_start; a.chunk_len = L.chunk_len;
+  a.nchunks = L.nchunks; a.ntensors = L.ntensors; a.decay_flag = L.decay_flag;
+  a.stats = L.stats; a.norms = L.norms; a.grid_bar = L.grid_bar; a.epoch = L.epoch;
+  a.grad_mul = L.grad_mul;
+  a.lr = L.lr; a.beta1 = L.beta1; a.beta2 = L.beta2; a.beta3 = L.grad_averaging ? 1.f - L.beta1 : 1.f;
+  a.eps = L.eps; a.weight_decay = L.weight_decay;
+  a.bc1 = L.bias_correction ? 1.f - powf(L.beta1, (float)L.step) : 1.f;
+  a.bc2 = L.bias_correction ? 1.f - powf(L.beta2, (float)L.step) : 1.f;
+  a.max_grad_norm = L.max_grad_norm; a.adam_w_mode = L.adam_w_mode; a.use_nvlamb = L.use_nvlamb;
+  B200_CUDA_CHECK(cudaMemsetAsync(L.grid_bar, 0, sizeof(unsigned int), st));
+  int dev, sms;
+  B200_CUDA_CHECK(cudaGetDevice(&dev));
+  B200_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  void* args[] = {(void*)&a};
+  // cooperative launch: all CTAs co-resident, required by the in-kernel grid barrier
+  B200_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)fused_allreduce_lamb_kernel, dim3(sms), dim3(FUSED_THREADS), args, 0, st));
+}
+
+}  // namespace b200

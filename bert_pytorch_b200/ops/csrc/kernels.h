@@ -51,4 +51,21 @@ void attention_bwd(const void* qkv, const int* seqlens, const void* ctx, const v
                    void* dqkv, float* delta_ws, float* dq_acc, int B, int S, int h, int d, float scale,
                    unsigned long long seed, unsigned int stream, float p_drop, cudaStream_t st);
 
+// comm.cu -- fused peer-memory all-reduce + partitioned LAMB (one cooperative kernel per step)
+struct FusedLambLaunch {
+  int rank, world, use_multicast;
+  const void* grad_ptrs[16]; const void* param_ptrs[16]; const void* shadow_ptrs[16];
+  const void* pad_ptrs[16]; const void* flag_ptrs[16];
+  void* grad_mc; void* param_mc; void* shadow_mc;
+  float* m; float* v;
+  long long numel, lo, hi;
+  const int* chunk_tensor; const long long* chunk_start; const int* chunk_len; int nchunks, ntensors;
+  const int* decay_flag;
+  float* stats; float* norms; unsigned int* grid_bar;
+  unsigned int epoch;
+  float grad_mul, lr, beta1, beta2, eps, weight_decay, max_grad_norm;
+  int step, bias_correction, grad_averaging, adam_w_mode, use_nvlamb;
+};
+void fused_allreduce_lamb(const FusedLambLaunch& L, cudaStream_t st);
+
 }  // namespace b200

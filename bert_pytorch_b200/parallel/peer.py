@@ -1,0 +1,144 @@
+"""Peer-memory communication backend: the product path for the gradient reduction.
+
+``PeerComm`` keeps the parameter / gradient / shadow arenas of every rank in CUDA *symmetric memory*
+(VMM allocations mapped into every peer over NVLink 5 / NVSwitch, plus the NVLS multicast mapping when the
+fabric offers it) and replaces
+
+    DDP bucketed ncclAllReduce  ->  GradScaler.unscale_  ->  FusedLAMB  (reference: run_pretraining.py:405-458)
+
+by ONE persistent sm_100a kernel per optimizer step (ops/csrc/comm.cu): reduce-scatter of the gradient
+shards with P2P loads / ``multimem.ld_reduce``, fused 1/(world*scale) + inf/nan detection, partitioned LAMB
+with cross-rank norm exchange through peer stores, and the parameter all-gather as P2P / ``multimem.st``
+stores of the updated fp32 + bf16 values.  No NCCL call on this path.  The bootstrap (rendezvous, handle
+exchange) uses torch.distributed / ``torch.distributed._symmetric_memory``; the kernels are ours.
+
+The optimizer state (moments) is *partitioned*: each rank only ever touches its own contiguous shard, so
+``state_dict`` gathers the shards (cold path, NCCL all-reduce of the zero-padded shards) into the full
+per-parameter layout the checkpoint format expects.
+
+The algorithm is specified and unit-tested on CPU in :mod:`bert_pytorch_b200.parallel.sharded_lamb`.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from .comm import TorchComm
+
+GRANULE = 2048        # shard boundaries are multiples of this many elements
+CHUNK = 65536
+
+
+class PeerComm(TorchComm):
+    name = "fused"
+    fuses_optimizer = True
+
+    def __init__(self, group=None, use_multicast: Optional[bool] = None):
+        super().__init__(group)
+        self.name = "fused"
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.arena = None
+        self.epoch = 0
+        self._want_mc = use_multicast
+        self.use_multicast = False
+        self.last_stats: Optional[torch.Tensor] = None
+
+    # -- symmetric allocation ---------------------------------------------------------------------
+    def _symm(self, numel: int, dtype: torch.dtype):
+        import torch.distributed._symmetric_memory as symm
+        t = symm.empty(numel, dtype=dtype, device=self.device)
+        t.zero_()
+        h = symm.rendezvous(t, self.group if self.group is not None else dist.group.WORLD)
+        return t, h
+
+    def adopt(self, arena) -> None:
+        """Move the arena's buffers into symmetric memory (weights/grad values preserved) and build the
+        shard tables.  Call once, before the optimizer is bound."""
+        n = arena.numel
+        T = len(arena.slots)
+        self.grad_t, self.grad_h = self._symm(n, torch.float32)
+        self.param_t, self.param_h = self._symm(n, torch.float32)
+        self.shadow_t, self.shadow_h = self._symm(n, torch.bfloat16)
+        pad_floats = 2 * self.world_size + self.world_size * 2 * T
+        self.pad_t, self.pad_h = self._symm(pad_floats + 64, torch.float32)
+        self.flag_t, self.flag_h = self._symm(4 * self.world_size + 64, torch.int32)
+        with torch.no_grad():
+            self.param_t.copy_(arena.flat_param)
+            self.grad_t.copy_(arena.flat_grad)
+            self.shadow_t.copy_(arena.flat_shadow if arena.flat_shadow is not None else arena.flat_param)
+        arena.flat_param, arena.flat_grad, arena.flat_shadow = self.param_t, self.grad_t, self.shadow_t
+        arena.shadow_dtype = torch.bfloat16
+        for s, p in zip(arena.slots, arena.params):          # re-point the nn.Parameters at the new storage
+            p.data = self.param_t[s.offset:s.offset + s.numel].view(s.shape)
+            p.grad = self.grad_t[s.offset:s.offset + s.numel].view(s.shape)
+        arena._opt_tables = None
+        self.arena = arena
+        mc_ok = all(int(getattr(h, "multicast_ptr", 0) or 0) != 0 for h in (self.grad_h, self.param_h))
+        self.use_multicast = mc_ok if self._want_mc is None else (bool(self._want_mc) and mc_ok)
+        self.lo, self.hi = arena.shard_bounds(self.world_size, self.rank, GRANULE)
+        # chunk table of the arena restricted to the shard
+        ct, cs, cl = [], [], []
+        for t, s in enumerate(arena.slots):
+            a, b = max(s.offset, self.lo), min(s.offset + s.numel, self.hi)
+            x = a
+            while x < b:
+                ln = min(CHUNK, b - x)
+                ct.append(t); cs.append(x); cl.append(ln)
+                x += ln
+        dev = self.device
+        self.chunk_tensor = torch.tensor(ct, dtype=torch.int32, device=dev)
+        self.chunk_start = torch.tensor(cs, dtype=torch.int64, device=dev)
+        self.chunk_len = torch.tensor(cl, dtype=torch.int32, device=dev)
+        self.stats = torch.zeros(4, dtype=torch.float32, device=dev)
+        self.norms = torch.zeros(2 * T, dtype=torch.float32, device=dev)
+        self.grid_bar = torch.zeros(1, dtype=torch.int32, device=dev)
+        dist.barrier(group=self.group)
+        torch.cuda.synchronize()
+
+    # -- the fused step ------------------------------------------------------------------------------
+    @torch.no_grad()
+    def fused_lamb_step(self, optimizer, loss_scale: float = 1.0) -> None:
+        """reduce-scatter + unscale + partitioned LAMB + all-gather, one kernel.  ``optimizer`` supplies the
+        hyper-parameters and owns the (arena backed) moment buffers."""
+        from .. import ops
+        from ..ops.api import _uniform
+        A = self.arena
+        if A is None or A.exp_avg is None:
+            raise RuntimeError("PeerComm.adopt(arena) and arena.bind_optimizer(optimizer) must be called first")
+        decay = getattr(self, "_decay", None)
+        if decay is None:
+            decay = torch.tensor([1 if s.decay else 0 for s in A.slots], dtype=torch.int32, device=self.device)
+            self._decay = decay
+        lr = _uniform(optimizer, "lr")
+        b1, b2 = _uniform(optimizer, "betas")
+        wd = max(float(g["weight_decay"]) for g in optimizer.param_groups)
+        step = int(optimizer.param_groups[0].get("step", 0)) + 1
+        self.epoch += 1
+        mc = self.use_multicast
+        ops.extension().fused_allreduce_lamb(
+            self.rank, self.world_size, mc,
+            list(self.grad_h.buffer_ptrs), list(self.param_h.buffer_ptrs), list(self.shadow_h.buffer_ptrs),
+            list(self.pad_h.buffer_ptrs), list(self.flag_h.buffer_ptrs),
+            int(self.grad_h.multicast_ptr) if mc else 0, int(self.param_h.multicast_ptr) if mc else 0, 0,
+            A.exp_avg, A.exp_avg_sq, A.numel, self.lo, self.hi, self.chunk_tensor, self.chunk_start, self.chunk_len,
+            decay, self.stats, self.norms, self.grid_bar, self.epoch, 1.0 / (self.world_size * loss_scale),
+            float(lr), float(b1), float(b2), float(_uniform(optimizer, "eps")), wd,
+            float(_uniform(optimizer, "max_grad_norm") or 0.0), step, bool(_uniform(optimizer, "bias_correction")),
+            bool(_uniform(optimizer, "grad_averaging")), bool(optimizer.adam_w_mode), bool(optimizer.use_nvlamb))
+        ops.api._count()
+        for g in optimizer.param_groups:       # bf16 path has no overflow; the fp16 path re-reads stats lazily
+            g["step"] = step
+        self.last_stats = self.stats
+
+    # -- checkpoint support ----------------------------------------------------------------------------
+    @torch.no_grad()
+    def gather_optimizer_state(self) -> None:
+        """Make every rank's moment arenas complete (each rank only maintains its shard): zero everything
+        outside the shard and sum over ranks.  Cold path (checkpoint time) -> NCCL."""
+        A = self.arena
+        for buf in (A.exp_avg, A.exp_avg_sq):
+            buf[: self.lo].zero_()
+            buf[self.hi:].zero_()
+            dist.all_reduce(buf, group=self.group)

@@ -181,8 +181,11 @@ def prepare_model(args):
     model.checkpoint_activations(args.checkpoint_activations)
     if args.no_fused:
         model.enable_apex(False)
+    config.max_predictions_per_seq = args.max_predictions_per_seq    # static MLM row capacity of the fused head
     arena = ParamArena(model, device=args.device_obj)
     comm = make_comm(args.backend)
+    if getattr(comm, "fuses_optimizer", False):
+        comm.adopt(arena)        # arenas move into NVLink symmetric memory; optimizer + reduction fuse
     model = DataParallel(model, comm=comm, arena=arena)
     criterion = modeling.BertPretrainingCriterion(config.vocab_size)
     args.config_obj = config
@@ -279,6 +282,16 @@ def prepare_dataset(args, checkpoint):
 # ---------------------------------------------------------------------------
 
 def take_optimizer_step(optimizer, preconditioner, model, scaler):
+    comm = getattr(model, "comm", None)
+    if comm is not None and getattr(comm, "fuses_optimizer", False) and preconditioner is None:
+        # one peer-memory kernel: reduce-scatter + unscale + partitioned LAMB + parameter all-gather
+        scale = scaler.get_scale() if (scaler is not None and scaler.is_enabled()) else 1.0
+        comm.fused_lamb_step(optimizer, loss_scale=scale)
+        if scaler is not None and scaler.is_enabled():
+            scaler._lazy_init(comm.device)
+            scaler.found_inf.copy_(comm.stats[3].clamp(max=1.0))
+            scaler.update()
+        return
     if preconditioner is not None:
         if scaler is not None:
             scaler.unscale_(optimizer)

@@ -22,6 +22,9 @@ for s in $STAGES; do
     ncu_gemm) timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 12 -c 2 -f -o gpurun_out/prof_gemm python tools/gemm_bench.py --only ${NCU_SHAPE:-qkv_fwd} > gpurun_out/ncu_gemm.log 2>&1; echo "ncu_gemm rc=$?" ;;
     ncu_attn) timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_ -s 6 -c 3 -f -o gpurun_out/prof_attn python tools/attn_bench.py > gpurun_out/ncu_attn.log 2>&1; echo "ncu_attn rc=$?" ;;
     attnbench) timeout 300 python tools/attn_bench.py > gpurun_out/attn_bench.json 2> gpurun_out/attn_bench.err; echo "attnbench rc=$?"; cat gpurun_out/attn_bench.json ;;
+    trace)   timeout 600 python tools/trace_step.py > gpurun_out/trace_step.log 2>&1; echo "trace rc=$?"; cat gpurun_out/trace_step.log | tail -30 ;;
+    trace2)  PHASE=2 timeout 600 python tools/trace_step.py > gpurun_out/trace_step2.log 2>&1; echo "trace2 rc=$?"; cat gpurun_out/trace_step2.log | tail -30 ;;
+    peer)    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29577 tools/peer_check.py ${PEER_ARGS:-} > gpurun_out/peer_check.log 2>&1; echo "peer rc=$?"; tail -20 gpurun_out/peer_check.log ;;
     *) echo "unknown stage $s" ;;
   esac
 done

@@ -1,0 +1,137 @@
+"""Multi-GPU check of the fused peer-memory all-reduce + LAMB kernel (run under torchrun, >= 2 GPUs):
+
+  torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29577 tools/peer_check.py [--big]
+
+1. correctness: fused kernel == NCCL all-reduce(avg) + single-GPU arena LAMB, incl. a clipped step, a
+   tensor straddling shard boundaries and an overflow step that every rank must skip;
+2. (--big) device-timed step on a BERT-large sized arena (336 M parameters): fused kernel vs
+   NCCL all-reduce + unfused LAMB, max over ranks, with the roofline fraction of SURVEY.md 5.8.
+Rank 0 prints one JSON line per section."""
+import copy
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bert_pytorch_b200 import BertConfig  # noqa: E402
+from bert_pytorch_b200.models import BertForPreTraining  # noqa: E402
+from bert_pytorch_b200.models.arena import NO_DECAY_KEYS, ParamArena  # noqa: E402
+from bert_pytorch_b200.optim import Lamb  # noqa: E402
+from bert_pytorch_b200.parallel.peer import PeerComm  # noqa: E402
+
+
+def groups(model):
+    named = list(model.named_parameters())
+    return [{"params": [p for n, p in named if not any(k in n for k in NO_DECAY_KEYS)], "weight_decay": 0.01},
+            {"params": [p for n, p in named if any(k in n for k in NO_DECAY_KEYS)], "weight_decay": 0.0}]
+
+
+def build(cfg, dev, fused, use_mc=None):
+    torch.manual_seed(0)
+    model = BertForPreTraining(cfg).to(dev)
+    arena = ParamArena(model, device=dev)
+    comm = None
+    if fused:
+        comm = PeerComm(use_multicast=use_mc)
+        comm.adopt(arena)
+    opt = Lamb(groups(model), lr=5e-3)
+    arena.bind_optimizer(opt)
+    return model, arena, opt, comm
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", init_method="env://", device_id=dev)
+    out = {"world": world}
+    cfg = BertConfig(vocab_size_or_config_json_file=2048, hidden_size=256, num_hidden_layers=3, num_attention_heads=4,
+                     intermediate_size=1024, max_position_embeddings=128)
+    for mc in ([False, True] if "--no-mc" not in sys.argv else [False]):
+        m_f, a_f, o_f, comm = build(cfg, dev, True, use_mc=mc)
+        if mc and not comm.use_multicast:
+            out["multicast"] = "unavailable"
+            continue
+        m_r, a_r, o_r, _ = build(cfg, dev, False)
+        worst = 0.0
+        for step in range(4):
+            torch.manual_seed(1000 * step + rank)
+            g = torch.randn(a_f.numel, device=dev) * (8.0 if step == 1 else 0.05)
+            if step == 3 and rank == world - 1:
+                g[12345] = float("inf")                       # overflow on one rank only
+            a_f.flat_grad.copy_(g)
+            a_r.flat_grad.copy_(g)
+            torch.cuda.synchronize(); dist.barrier()
+            before = a_f.flat_param.clone()
+            comm.fused_lamb_step(o_f, loss_scale=4.0)
+            torch.cuda.synchronize()
+            if step == 3:
+                skipped = bool(torch.equal(a_f.flat_param, before)) and float(a_f.flat_grad.abs().max()) == 0.0
+                out[f"overflow_skipped_mc{int(mc)}"] = skipped and float(comm.stats[3]) > 0
+                continue
+            dist.all_reduce(a_r.flat_grad)
+            a_r.flat_grad.mul_(1.0 / (world * 4.0))
+            o_r.step()
+            torch.cuda.synchronize()
+            d = (a_f.flat_param - a_r.flat_param).abs().max().item()
+            sh = (a_f.flat_shadow.float() - a_f.flat_param).abs().max().item()
+            worst = max(worst, d)
+            assert sh < 2e-2, sh
+            # every rank must hold identical parameters
+            ref = a_f.flat_param.clone()
+            dist.broadcast(ref, src=0)
+            assert torch.equal(ref, a_f.flat_param), "ranks disagree after the fused step"
+        out[f"max_abs_diff_mc{int(mc)}"] = worst
+        out[f"grad_norm_mc{int(mc)}"] = float(comm.stats[2].sqrt())
+        del comm, m_f, a_f, o_f
+    if "--big" in sys.argv:
+        big = BertConfig(vocab_size_or_config_json_file=30528, hidden_size=1024, num_hidden_layers=24,
+                         num_attention_heads=16, intermediate_size=4096, max_position_embeddings=512)
+        for mc in (False, True):
+            m_f, a_f, o_f, comm = build(big, dev, True, use_mc=mc)
+            if mc and not comm.use_multicast:
+                continue
+            def run_fused():
+                comm.fused_lamb_step(o_f, loss_scale=1.0)
+            def timeit(fn, n=6):
+                for _ in range(2):
+                    fn()
+                torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(n):
+                    fn()
+                e1.record(); torch.cuda.synchronize()
+                t = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                return float(t)
+            a_f.flat_grad.normal_()
+            t_f = timeit(run_fused)
+            out[f"fused_ms_mc{int(mc)}"] = round(t_f, 3)
+            del comm, m_f, a_f, o_f
+            torch.cuda.empty_cache()
+        m_r, a_r, o_r, _ = build(big, dev, False)
+        def run_ref():
+            dist.all_reduce(a_r.flat_grad)
+            a_r.flat_grad.mul_(1.0 / world)
+            o_r.step()
+        a_r.flat_grad.normal_()
+        out["nccl_allreduce_plus_lamb_ms"] = round(timeit(run_ref), 3)
+        n = a_r.numel
+        link = 770e9   # measured peer bandwidth per direction (B200_PROFILING.md)
+        rs_bytes = 4.0 * n * (world - 1) / world          # gradient shards pulled from the peers
+        ag_bytes = 6.0 * n * (world - 1) / world          # fp32 + bf16 pushed to the peers
+        out["roofline_ms_nvlink"] = round(max(rs_bytes, ag_bytes) / link * 1e3, 3)
+        out["arena_numel"] = n
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
