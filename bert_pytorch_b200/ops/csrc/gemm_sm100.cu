@@ -31,7 +31,8 @@ namespace b200 {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;          // 64 bf16 = 128 B = one swizzle atom row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;     // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+constexpr int NUM_THREADS = 320;     // warp0 TMA, warp1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+constexpr int EPI_THREADS = 256;
 constexpr int SMEM_BUDGET = 196608;  // bytes for the operand ring (192 KB)
 
 template <int BLOCK_N>
@@ -64,9 +65,10 @@ struct GemmArgs {
 // Drain one 128 x BLOCK_N fp32 accumulator tile (this warp's 32 TMEM lanes) through the selected epilogue.
 // `taddr` already carries the lane quarter; `row` is this thread's global output row.
 template <int BLOCK_N>
-__device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint32_t taddr, int row, bool row_ok, int n_base) {
+__device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint32_t taddr, int row, bool row_ok, int n_base,
+                                              int c_begin, int c_end) {
   #pragma unroll 1
-  for (int c = 0; c < BLOCK_N / 32; ++c) {
+  for (int c = c_begin; c < c_end; ++c) {
     const int n0 = n_base + c * 32;
     if (n0 >= p.N) break;  // warp uniform
     uint32_t v[32];
@@ -209,7 +211,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 128);
+      mbar_init(&tmem_empty[s], EPI_THREADS);
     }
     fence_barrier_init();
   }
@@ -290,8 +292,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
+    // ------------------------------------------------------------------ epilogue (8 warps: 4 lane quarters x 2 column halves)
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;
+    constexpr int CH = BLOCK_N / 64;   // 32-column chunks per warp
     uint32_t tile_it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
       const int nb = tile % p.n_blocks;
@@ -305,7 +309,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const int row = mb * BLOCK_M + q * 32 + lane;
       const bool row_ok = row < p.M && kb1 > kb0;
       const uint32_t taddr = tmem_base + as * BLOCK_N + (uint32_t(q * 32) << 16);
-      epilogue_tile<BLOCK_N>(p, taddr, row, row_ok, nb * BLOCK_N);
+      epilogue_tile<BLOCK_N>(p, taddr, row, row_ok, nb * BLOCK_N, half * CH, half * CH + CH);
       tc_fence_before();
       mbar_arrive(&tmem_empty[as]);
     }
@@ -356,7 +360,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 256);   // 128 epilogue threads in each CTA of the pair
+      mbar_init(&tmem_empty[s], 2 * EPI_THREADS);   // the epilogue threads of both CTAs of the pair
     }
     fence_barrier_init();
   }
@@ -436,6 +440,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else {                               // ---------------- epilogue (both CTAs, own 128 rows)
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     uint32_t tile_it = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += nclusters, ++tile_it) {
       const int nb = tile % p.n_blocks;
@@ -445,7 +450,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       tc_fence_after();
       const int row = mb * PAIR_M + (int)rank * 128 + q * 32 + lane;
       const uint32_t taddr = tmem_base + as * PAIR_N + (uint32_t(q * 32) << 16);
-      epilogue_tile<PAIR_N>(p, taddr, row, row < p.M, nb * PAIR_N);
+      epilogue_tile<PAIR_N>(p, taddr, row, row < p.M, nb * PAIR_N, half * 4, half * 4 + 4);
       tc_fence_before();
       mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), 0));
     }
