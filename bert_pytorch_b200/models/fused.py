@@ -207,6 +207,7 @@ class FusedEncoderEngine:
         A, H, M = self.arena, self.H, sv.B * sv.S
         ph, pa, seed = sv.p_hidden, sv.p_attn, sv.seed
         d = d_out
+        kfac = getattr(self.bert, "_kfac", None)      # K-FAC taps: the saved activations double as its statistics
         for l in reversed(range(self.L)):
             pre = f"encoder.layer.{l}."
             ls = sv.layers[l]
@@ -216,6 +217,8 @@ class FusedEncoderEngine:
                 dgamma=self.g(pre + "output.LayerNorm.weight"), dbeta=self.g(pre + "output.LayerNorm.bias"),
                 dbias=self.g(pre + "output.dense.bias"), want_dropped=True, p_drop=ph, seed=seed,
                 drop_stream=_stream(l, SITE_FFN_OUT))
+            if kfac is not None:
+                kfac.tap(self.prefix + pre + "output.dense", ls.act, d_y2)
             # ---- FFN-2
             d_y1 = K.gemm(d_y2, self.w(pre + "output.dense.weight"), layout=K.NN, epi=K.EPI_DGELU, res=ls.y1)
             K.wgrad_accumulate(d_y2, ls.act, self.g(pre + "output.dense.weight"))
@@ -230,6 +233,8 @@ class FusedEncoderEngine:
                 dbeta=self.g(pre + "attention.output.LayerNorm.bias"),
                 dbias=self.g(pre + "attention.output.dense.bias"), want_dropped=True, p_drop=ph, seed=seed,
                 drop_stream=_stream(l, SITE_ATTN_OUT))
+            if kfac is not None:
+                kfac.tap(self.prefix + pre + "attention.output.dense", ls.ctx, d_yo)
             # ---- attention output projection
             d_ctx = K.gemm(d_yo, self.w(pre + "attention.output.dense.weight"), layout=K.NN)
             K.wgrad_accumulate(d_yo, ls.ctx, self.g(pre + "attention.output.dense.weight"))
@@ -240,6 +245,9 @@ class FusedEncoderEngine:
                 d_qkv = K.attention_bwd(ls.qkv.view(sv.B, sv.S, 3 * H), sv.seqlens, ls.ctx.view(sv.B, sv.S, H),
                                         d_ctx.view(sv.B, sv.S, H), ls.lse, self.heads, p_drop=pa, seed=seed,
                                         stream=_stream(l, SITE_ATTN_PROB)).view(M, 3 * H)
+            if kfac is not None:
+                for j, nm in enumerate(("query", "key", "value")):
+                    kfac.tap(self.prefix + pre + "attention.self." + nm, ls.x, d_qkv[:, j * H:(j + 1) * H])
             # ---- QKV projection
             K.colsum_accumulate(d_qkv, self._qkv(l, A.flat_grad, "bias"))
             d = K.gemm(d_qkv, self._qkv(l, A.flat_shadow, "weight"), layout=K.NN, epi=K.EPI_ADD, res=d_pre1)
