@@ -49,9 +49,11 @@ with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) a
         micro(i)
     torch.cuda.synchronize()
 agg = collections.defaultdict(lambda: [0, 0.0])
+ordered = []
 for ev in prof.events():
     if ev.device_type == torch.autograd.DeviceType.CUDA:
         name = re.sub(r"\(.*", "", ev.name)[:64]
+        ordered.append((ev.time_range.start, name, ev.device_time if hasattr(ev, "device_time") else ev.cuda_time))
         agg[name][0] += 1
         agg[name][1] += ev.device_time if hasattr(ev, "device_time") else ev.cuda_time
 tot = sum(v[1] for v in agg.values())
@@ -60,6 +62,9 @@ print(f"phase {phase}: kernel time per micro-step {tot / N / 1e3:.2f} ms")
 for n, (c, t) in rows[:24]:
     print(f"{t / N:10.1f} us {100 * t / tot:5.1f}%  x{c // N:4d}  avg {t / c:7.1f}  {n}")
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump({"phase": phase, "ms_per_micro_step_kernels": tot / N / 1e3,
+ordered.sort()
+per_step = len(ordered) // N
+last = ordered[-per_step:]
+json.dump({"phase": phase, "ordered_last_step": [[n, round(t, 1)] for _, n, t in last], "ms_per_micro_step_kernels": tot / N / 1e3,
            "kernels": [{"name": n, "calls": c // N, "us_per_step": t / N} for n, (c, t) in rows]},
           open(f"gpurun_out/trace_step_p{phase}.json", "w"), indent=1)
