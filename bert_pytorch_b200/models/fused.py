@@ -183,9 +183,10 @@ class FusedEncoderEngine:
                           stream=_stream(l, SITE_ATTN_OUT))
             x1, mean1, rstd1 = K.layer_norm_fwd(pre1, self.p(pre + "attention.output.LayerNorm.weight"),
                                                 self.p(pre + "attention.output.LayerNorm.bias"), save_stats=training)
-            y1 = torch.empty(M, self.I, dtype=torch.bfloat16, device=x.device)
-            act = K.gemm(x1, self.w(pre + "intermediate.dense_act.weight"), epi=K.EPI_BIAS_GELU,
-                         bias=self.w(pre + "intermediate.dense_act.bias"), aux_out=y1)
+            # GELU runs as its own bandwidth kernel: with K = 1024 it does not fit under the GEMM main loop
+            y1 = K.gemm(x1, self.w(pre + "intermediate.dense_act.weight"), epi=K.EPI_BIAS,
+                        bias=self.w(pre + "intermediate.dense_act.bias"))
+            act = K.gelu_fwd(y1)
             pre2 = K.gemm(act, self.w(pre + "output.dense.weight"), epi=K.EPI_BIAS_DROP_RES,
                           bias=self.w(pre + "output.dense.bias"), res=x1, p_drop=ph, seed=seed,
                           stream=_stream(l, SITE_FFN_OUT))
@@ -220,10 +221,10 @@ class FusedEncoderEngine:
             if kfac is not None:
                 kfac.tap(self.prefix + pre + "output.dense", ls.act, d_y2)
             # ---- FFN-2
-            d_y1 = K.gemm(d_y2, self.w(pre + "output.dense.weight"), layout=K.NN, epi=K.EPI_DGELU, res=ls.y1)
+            d_act = K.gemm(d_y2, self.w(pre + "output.dense.weight"), layout=K.NN)
             K.wgrad_accumulate(d_y2, ls.act, self.g(pre + "output.dense.weight"))
-            # ---- FFN-1
-            K.colsum_accumulate(d_y1, self.g(pre + "intermediate.dense_act.bias"))
+            # ---- FFN-1 (GELU' and the bias gradient in one bandwidth pass)
+            d_y1 = K.dgelu_bwd(d_act, ls.y1, self.g(pre + "intermediate.dense_act.bias"))
             d_x1 = K.gemm(d_y1, self.w(pre + "intermediate.dense_act.weight"), layout=K.NN, epi=K.EPI_ADD, res=d_pre2)
             K.wgrad_accumulate(d_y1, ls.x1, self.g(pre + "intermediate.dense_act.weight"))
             # ---- LN1
@@ -353,9 +354,9 @@ class FusedPretrainer:
 
         # ---- MLM head forward (masked rows only)
         rows = K.gather_rows(seq, idx)
-        t_pre = torch.empty_like(rows)
-        t_act = K.gemm(rows, A.shadow("cls.predictions.transform.dense_act.weight"), epi=K.EPI_BIAS_GELU,
-                       bias=A.shadow("cls.predictions.transform.dense_act.bias"), aux_out=t_pre)
+        t_pre = K.gemm(rows, A.shadow("cls.predictions.transform.dense_act.weight"), epi=K.EPI_BIAS,
+                       bias=A.shadow("cls.predictions.transform.dense_act.bias"))
+        t_act = K.gelu_fwd(t_pre)
         t_ln, t_mean, t_rstd = K.layer_norm_fwd(t_act, A.view("cls.predictions.transform.LayerNorm.weight"),
                                                 A.view("cls.predictions.transform.LayerNorm.bias"))
         emb_w = eng.w("embeddings.word_embeddings.weight")            # tied decoder weight [V, H]
@@ -369,8 +370,7 @@ class FusedPretrainer:
         d_t_act, _ = K.layer_norm_bwd(d_t_ln, t_act, t_mean, t_rstd, A.view("cls.predictions.transform.LayerNorm.weight"),
                                       dgamma=A.grad("cls.predictions.transform.LayerNorm.weight"),
                                       dbeta=A.grad("cls.predictions.transform.LayerNorm.bias"))
-        d_t_pre = torch.ops.aten.gelu_backward(d_t_act, t_pre)
-        K.colsum_accumulate(d_t_pre, A.grad("cls.predictions.transform.dense_act.bias"))
+        d_t_pre = K.dgelu_bwd(d_t_act, t_pre, A.grad("cls.predictions.transform.dense_act.bias"))
         K.wgrad_accumulate(d_t_pre, rows, A.grad("cls.predictions.transform.dense_act.weight"))
         d_rows = K.gemm(d_t_pre, A.shadow("cls.predictions.transform.dense_act.weight"), layout=K.NN)
         d_seq = torch.zeros(M, H, dtype=torch.bfloat16, device=seq.device)

@@ -136,6 +136,21 @@ def colsum_accumulate(x: torch.Tensor, out: torch.Tensor) -> None:
     _count()
 
 
+def gelu_fwd(x: torch.Tensor) -> torch.Tensor:
+    y = torch.empty_like(x)
+    extension().gelu_fwd(x, y)
+    _count()
+    return y
+
+
+def dgelu_bwd(dy: torch.Tensor, x: torch.Tensor, dbias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dy * gelu'(x); ``dbias`` (fp32 [N]) accumulates the column sums of the result."""
+    dx = torch.empty_like(dy)
+    extension().dgelu_bwd(dy, x, dx, dbias)
+    _count()
+    return dx
+
+
 def embedding_fwd(ids, seg, word, pos, type_emb, gamma, beta, S: int, *, eps=1e-12, p_drop=0.0, seed=0, stream=0):
     M, H = ids.numel(), word.size(1)
     e = torch.empty(M, H, dtype=torch.bfloat16, device=ids.device)

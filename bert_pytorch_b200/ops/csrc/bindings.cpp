@@ -112,6 +112,20 @@ void layer_norm_bwd(Tensor dy, Tensor x, Tensor mean, Tensor rstd, Tensor gamma,
                        (unsigned)in_stream, (float)p_drop, cur_stream());
 }
 
+void gelu_fwd(Tensor x, Tensor y) {
+  check_bf16(x, "x"); check_bf16(y, "y");
+  TORCH_CHECK(x.is_contiguous() && y.is_contiguous() && x.numel() == y.numel() && x.numel() % 8 == 0, "gelu_fwd shapes");
+  c10::cuda::CUDAGuard guard(x.device());
+  b200::gelu_fwd(x.data_ptr(), y.data_ptr(), x.numel(), cur_stream());
+}
+void dgelu_bwd(Tensor dy, Tensor x, Tensor dx, c10::optional<Tensor> dbias) {
+  check_bf16(dy, "dy"); check_bf16(x, "x"); check_bf16(dx, "dx");
+  TORCH_CHECK(dy.dim() == 2 && dy.is_contiguous() && x.is_contiguous() && dx.is_contiguous() && dy.size(1) % 8 == 0,
+              "dgelu_bwd: contiguous [M,N] with N % 8 == 0");
+  c10::cuda::CUDAGuard guard(x.device());
+  b200::dgelu_bwd(dy.data_ptr(), x.data_ptr(), dx.data_ptr(), opt_f32(dbias), (int)dy.size(0), (int)dy.size(1), cur_stream());
+}
+
 void colsum(Tensor x, Tensor out) {
   check_bf16(x, "x");
   TORCH_CHECK(x.dim() == 2 && out.scalar_type() == at::kFloat && out.numel() == x.size(1), "colsum shapes");
@@ -299,6 +313,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("layer_norm_bwd", &layer_norm_bwd);
   m.def("ln_bwd_workspace", &ln_bwd_workspace);
   m.def("colsum", &colsum);
+  m.def("gelu_fwd", &gelu_fwd);
+  m.def("dgelu_bwd", &dgelu_bwd);
   m.def("embedding_fwd", &embedding_fwd);
   m.def("embedding_bwd_scatter", &embedding_bwd_scatter);
   m.def("mlm_compact", &mlm_compact);

@@ -12,6 +12,8 @@ void layer_norm_bwd(const void* dy, const void* x, const float* mean, const floa
                     void* dxd, float* dgamma, float* dbeta, float* dbias, float* workspace, int M, int H,
                     unsigned long long seed, unsigned int drop_stream, unsigned int in_stream, float p_drop,
                     cudaStream_t st);
+void gelu_fwd(const void* x, void* y, long long n, cudaStream_t st);
+void dgelu_bwd(const void* dy, const void* x, void* dx, float* dbias, int M, int N, cudaStream_t st);
 void colsum_bf16(const void* x, int M, int N, int ld, float* out, cudaStream_t st);
 void embedding_fwd(const int* ids, const int* seg, const void* word, const void* pos, const void* type,
                    const float* gamma, const float* beta, void* e_out, void* y, float* mean, float* rstd, int M, int S,

@@ -279,6 +279,64 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
 }
 
 // ------------------------------------------------------------------------------------------------
+// GELU as bandwidth kernels.  With K = 1024 the FFN-1 / FFN-2-dgrad GEMM tiles give the epilogue only
+// ~8k cycles for 32k elements; erf-GELU (~20 instructions per element on 4 issue ports) does not fit under
+// that main loop (measured in situ: 192 us and 202 us per GEMM instead of ~83), so the activation runs here
+// where the instruction budget per byte is 10x larger: one pass at HBM speed forward, and the backward pass
+// also produces the FFN-1 bias gradient (column sums) that used to be a separate kernel.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gelu_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                      long long n8) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 u = reinterpret_cast<const uint4*>(x)[i];
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 f = unpack_bf16(w[t]);
+      o[t] = pack_bf16(gelu_erf(f.x), gelu_erf(f.y));
+    }
+    reinterpret_cast<uint4*>(y)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// dx[m][n] = dy[m][n] * gelu'(x[m][n]);  dbias[n] += sum_m dx[m][n]
+__global__ void __launch_bounds__(256)
+dgelu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ dx,
+                 float* __restrict__ dbias, int M, int N) {
+  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int col = blockIdx.x * 256 + cg * 8;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (col < N) {
+    for (int row = blockIdx.y * 8 + rl; row < M; row += gridDim.y * 8) {
+      const size_t off = (size_t)row * N + col;
+      const uint4 a = *reinterpret_cast<const uint4*>(dy + off), b = *reinterpret_cast<const uint4*>(x + off);
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 g = unpack_bf16(aw[t]), v = unpack_bf16(bw[t]);
+        const float r0 = g.x * dgelu_erf(v.x), r1 = g.y * dgelu_erf(v.y);
+        acc[2 * t] += r0;
+        acc[2 * t + 1] += r1;
+        o[t] = pack_bf16(r0, r1);
+      }
+      *reinterpret_cast<uint4*>(dx + off) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+  if (dbias == nullptr) return;
+  __shared__ float sm[8][256];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) sm[rl][cg * 8 + t] = acc[t];
+  __syncthreads();
+  const int c = threadIdx.x;
+  float sum = 0.f;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) sum += sm[r][c];
+  if (blockIdx.x * 256 + c < N) atomicAdd(dbias + blockIdx.x * 256 + c, sum);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Embedding forward: e = word[id] + pos[s] (+ type[seg]); y = dropout(LN(e)); saves e, mean, rstd
 // ------------------------------------------------------------------------------------------------
 template <int CHUNKS>
@@ -478,6 +536,17 @@ void layer_norm_bwd(const void* dy, const void* x, const float* mean, const floa
 void colsum_bf16(const void* x, int M, int N, int ld, float* out, cudaStream_t st) {
   dim3 grid((N + 255) / 256, M >= 4096 ? 64 : (M >= 512 ? 16 : 1));
   colsum_bf16_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, M, N, ld, out);
+}
+
+void gelu_fwd(const void* x, void* y, long long n, cudaStream_t st) {
+  const long long n8 = n >> 3;
+  long long g = (n8 + 255) / 256;
+  if (g > 148 * 32) g = 148 * 32;
+  if (g > 0) gelu_fwd_kernel<<<(unsigned)g, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, n8);
+}
+void dgelu_bwd(const void* dy, const void* x, void* dx, float* dbias, int M, int N, cudaStream_t st) {
+  dim3 grid((N + 255) / 256, M >= 4096 ? 74 : (M >= 512 ? 16 : 1));
+  dgelu_bwd_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (__nv_bfloat16*)dx, dbias, M, N);
 }
 
 void embedding_fwd(const int* ids, const int* seg, const void* word, const void* pos, const void* type,

@@ -255,3 +255,18 @@ def test_encoder_autograd_bridge_matches_oracle():
     w, wo = model.bert.encoder.layer[0].output.dense.weight, oracle.bert.encoder.layer[0].output.dense.weight
     rel = (w.grad - wo.grad).abs().max() / (wo.grad.abs().max() + 1e-6)
     assert rel < 8e-2, rel
+
+
+def test_gelu_kernels():
+    K = _api()
+    x = (torch.randn(3000, 1024, device="cuda") * 2).to(torch.bfloat16)
+    dy = torch.randn(3000, 1024, device="cuda").to(torch.bfloat16)
+    y = K.gelu_fwd(x)
+    xf = x.float().requires_grad_(True)
+    ref = F.gelu(xf)
+    assert ((y.float() - ref).abs() / (ref.abs() + 1.0)).max() < 1e-2
+    ref.backward(dy.float())
+    db = torch.zeros(1024, device="cuda")
+    dx = K.dgelu_bwd(dy, x, db)
+    assert (dx.float() - xf.grad).abs().max() < 3e-2
+    assert torch.allclose(db, dx.float().sum(0), rtol=1e-3, atol=5e-2)
