@@ -24,7 +24,8 @@
 
 namespace b200 {
 
-constexpr int ATT_THREADS = 160;   // 4 softmax warps + 1 control warp
+constexpr int ATT_THREADS = 160;   // forward: 4 softmax warps + 1 control warp
+constexpr int ATT_BWD_THREADS = 288;   // backward: 8 math warps (2 per TMEM lane quarter) + 1 control warp
 constexpr int TILE = 128;          // query rows / key rows per block
 constexpr int HD = 64;             // head dim
 constexpr float LOG2E = 1.4426950408889634f;
@@ -58,7 +59,7 @@ __device__ __forceinline__ uint32_t p_chunk_offset(int r, int col8) {
 // KV_STAGES = 1: the whole key range is one block (S <= 128): 80 KB of shared memory and 128 TMEM columns
 // (the PV result reuses the S columns) -> two CTAs per SM.  KV_STAGES = 2: K/V blocks stream through a ring.
 template <int KV_STAGES>
-__global__ void __launch_bounds__(ATT_THREADS, 2)
+__global__ void __launch_bounds__(ATT_BWD_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -75,6 +76,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs p) 
   uint64_t* p_ready = bars + 6;
   uint64_t* pv_done = bars + 7;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* xch = reinterpret_cast<float*>(bars + 10);      // [2 buffers][2 halves][128 rows] row-max exchange (+ final sum)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qb = blockIdx.x, bh = blockIdx.y;
@@ -83,23 +85,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs p) 
   const int nkb = max(1, (seqlen + TILE - 1) / TILE);   // key blocks that contain valid keys
   const int row0 = b * p.S;
 
-  if (threadIdx.x == 128) {
+  if (threadIdx.x == 256) {
     tma_prefetch_desc(&tmap_qkv);
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     mbar_init(s_ready, 1);
-    mbar_init(p_ready, 128);
+    mbar_init(p_ready, 256);
     mbar_init(pv_done, 1);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 8) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tS = tmem, tO = KV_STAGES == 1 ? tmem : tmem + 128;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       const int cq = head * HD, ck = p.H + head * HD, cv = 2 * p.H + head * HD;
       mbar_arrive_expect_tx(q_full, 16384);
@@ -141,42 +143,49 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs p) 
       }
     }
   } else {
-    const int r = warp * 32 + lane;            // query row inside the tile == TMEM lane
+    // two threads per query row: thread (r, ch) owns key columns [64 ch, 64 ch + 64) of every key block and
+    // output columns [32 ch, 32 ch + 32); row maxima are exchanged through shared memory
+    const int r = (warp & 3) * 32 + lane;      // query row inside the tile == TMEM lane
+    const int ch = warp >> 2;
     const int q = qb * TILE + r;               // query position in the sequence
-    const uint32_t lane_base = uint32_t(warp * 32) << 16;
+    const uint32_t lane_base = uint32_t((warp & 3) * 32) << 16;
     const float c_scale = p.scale * LOG2E;
     float m = -INFINITY, l = 0.f;
-    float o[HD];
+    float o[32];
 #pragma unroll
-    for (int t = 0; t < HD; ++t) o[t] = 0.f;
+    for (int t = 0; t < 32; ++t) o[t] = 0.f;
     const uint64_t erow = ((uint64_t)bh * p.S + (uint64_t)q) * (uint64_t)p.S;   // dropout element index base
     for (int j = 0; j < nkb; ++j) {
       mbar_wait(s_ready, j & 1);
       tc_fence_after();
-      // pass 1: row max over the valid keys of this block
+      // pass 1: row max over the valid keys of this half block
       float mx = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tS + lane_base + c * 32, v);
+      for (int c = ch * 4; c < ch * 4 + 4; ++c) {        // 16-column sub-chunks keep the register count low
+        uint32_t v[16];
+        tmem_ld_32x16(tS + lane_base + c * 16, v);
         tmem_ld_wait();
-        const int k0 = j * TILE + c * 32;
+        const int k0 = j * TILE + c * 16;
 #pragma unroll
-        for (int t = 0; t < 32; ++t)
+        for (int t = 0; t < 16; ++t)
           if (k0 + t < seqlen) mx = fmaxf(mx, __uint_as_float(v[t]) * c_scale);
       }
+      float* xb = xch + (j & 1) * 256;
+      xb[ch * 128 + r] = mx;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mx = fmaxf(xb[r], xb[128 + r]);
       const float m_new = fmaxf(m, mx);
       const float alpha = (m == -INFINITY) ? 0.f : exp2f(m - m_new);
       float rowsum = 0.f;
       // pass 2: probabilities, dropout, P -> shared memory
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tS + lane_base + c * 32, v);
+      for (int c = ch * 4; c < ch * 4 + 4; ++c) {
+        uint32_t v[16];
+        tmem_ld_32x16(tS + lane_base + c * 16, v);
         tmem_ld_wait();
-        const int k0 = j * TILE + c * 32;
+        const int k0 = j * TILE + c * 16;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < 2; ++g) {
           float pr[8];
 #pragma unroll
           for (int t = 0; t < 8; ++t) {
@@ -192,41 +201,44 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs p) 
           }
           const uint4 pk = make_uint4(pack_bf16(pr[0], pr[1]), pack_bf16(pr[2], pr[3]), pack_bf16(pr[4], pr[5]),
                                       pack_bf16(pr[6], pr[7]));
-          *reinterpret_cast<uint4*>(sP + p_chunk_offset(r, c * 4 + g)) = pk;
+          *reinterpret_cast<uint4*>(sP + p_chunk_offset(r, c * 2 + g)) = pk;
         }
       }
-      l = l * alpha + rowsum;
+      l = l * alpha + rowsum;                  // this half's share of the denominator
       m = m_new;
 #pragma unroll
-      for (int t = 0; t < HD; ++t) o[t] *= alpha;
+      for (int t = 0; t < 32; ++t) o[t] *= alpha;
       fence_proxy_async();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();
       mbar_arrive(p_ready);
       mbar_wait(pv_done, j & 1);
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      {
         uint32_t v[32];
-        tmem_ld_32x32(tO + lane_base + c * 32, v);
+        tmem_ld_32x32(tO + lane_base + ch * 32, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int t = 0; t < 32; ++t) o[c * 32 + t] += __uint_as_float(v[t]);
+        for (int t = 0; t < 32; ++t) o[t] += __uint_as_float(v[t]);
       }
     }
+    float* xs = xch + 512;                     // final exchange of the two partial denominators
+    xs[ch * 128 + r] = l;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    l = xs[r] + xs[128 + r];
     if (q < p.S) {
       const float inv_l = 1.f / l;
-      __nv_bfloat16* dst = p.ctx + (size_t)(row0 + q) * p.H + head * HD;
+      __nv_bfloat16* dst = p.ctx + (size_t)(row0 + q) * p.H + head * HD + ch * 32;
 #pragma unroll
-      for (int g = 0; g < 8; ++g)
+      for (int g = 0; g < 4; ++g)
         *reinterpret_cast<uint4*>(dst + g * 8) =
             make_uint4(pack_bf16(o[g * 8] * inv_l, o[g * 8 + 1] * inv_l), pack_bf16(o[g * 8 + 2] * inv_l, o[g * 8 + 3] * inv_l),
                        pack_bf16(o[g * 8 + 4] * inv_l, o[g * 8 + 5] * inv_l), pack_bf16(o[g * 8 + 6] * inv_l, o[g * 8 + 7] * inv_l));
-      p.lse[(size_t)bh * p.S + q] = (m + log2f(l)) * 0.6931471805599453f;
+      if (ch == 0) p.lse[(size_t)bh * p.S + q] = (m + log2f(l)) * 0.6931471805599453f;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem, TMEM_COLS);
   }
@@ -263,7 +275,7 @@ attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __re
   }
 }
 
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+__global__ void __launch_bounds__(ATT_BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
                 const AttnArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -309,25 +321,25 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     return;
   }
 
-  if (threadIdx.x == 128) {
+  if (threadIdx.x == 256) {
     tma_prefetch_desc(&tmap_qkv);
     tma_prefetch_desc(&tmap_do);
     mbar_init(kv_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
     mbar_init(sdp_ready, 1);
-    mbar_init(ds_ready, 128);
+    mbar_init(ds_ready, 256);
     mbar_init(dq_ready, 1);
     mbar_init(fin, 1);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(tmem_slot, 512);
+  if (warp == 8) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tS = tmem, tDP = tmem + 128, tDV = tmem + 256, tDK = tmem + 320, tDQ = tmem + 384;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       const int cq = head * HD, ck = p.H + head * HD, cv = 2 * p.H + head * HD;
       mbar_arrive_expect_tx(kv_full, 32768);
@@ -387,8 +399,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       umma_commit(fin);
     }
   } else {
-    const int r = warp * 32 + lane;
-    const uint32_t lane_base = uint32_t(warp * 32) << 16;
+    const int r = (warp & 3) * 32 + lane;        // query row inside the tile == TMEM lane
+    const int ch = warp >> 2;                    // which 64-column half this thread handles
+    const uint32_t lane_base = uint32_t((warp & 3) * 32) << 16;
     const float c_scale = p.scale * LOG2E;
     for (int i = 0; i < nqb; ++i) {
       const int q = i * TILE + r;
@@ -399,7 +412,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       mbar_wait(sdp_ready, i & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = ch * 2; c < ch * 2 + 2; ++c) {
         uint32_t sv[32], dv[32];
         tmem_ld_32x32(tS + lane_base + c * 32, sv);
         tmem_ld_32x32(tDP + lane_base + c * 32, dv);
@@ -433,8 +446,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       mbar_arrive(ds_ready);
       mbar_wait(dq_ready, i & 1);
       tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
+      {
+        const int c = ch;                        // each thread writes 32 of the 64 dQ columns of its row
         uint32_t v[32];
         tmem_ld_32x32(tDQ + lane_base + c * 32, v);
         tmem_ld_wait();
@@ -465,8 +478,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     mbar_wait(fin, 0);
     tc_fence_after();
     const int key = kb * TILE + r;
-#pragma unroll 1
-    for (int w = 0; w < 2; ++w) {       // 0: dK, 1: dV
+    {
+      const int w = ch;                   // column half 0 writes dK, half 1 writes dV
       const uint32_t src = w == 0 ? tDK : tDV;
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
@@ -488,7 +501,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
@@ -531,15 +544,15 @@ void attention_fwd(const void* qkv, const int* seqlens, void* ctx, float* lse, i
   CUtensorMap tm = make_tmap_2d_bf16(qkv, 3 * H, (uint64_t)B * S, 3 * H, 64, TILE);
   dim3 grid((S + TILE - 1) / TILE, B * h);
   if (S <= TILE) {
-    constexpr int SMEM = 16384 * 5 + 1024 + 128;
+    constexpr int SMEM = 16384 * 5 + 1024 + 128 + 3200;
     static bool once = false;
     if (!once) { B200_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); once = true; }
-    attn_fwd_kernel<1><<<grid, ATT_THREADS, SMEM, st>>>(tm, a);
+    attn_fwd_kernel<1><<<grid, ATT_BWD_THREADS, SMEM, st>>>(tm, a);
   } else {
-    constexpr int SMEM = 16384 * 7 + 1024 + 128;
+    constexpr int SMEM = 16384 * 7 + 1024 + 128 + 3200;
     static bool once = false;
     if (!once) { B200_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); once = true; }
-    attn_fwd_kernel<2><<<grid, ATT_THREADS, SMEM, st>>>(tm, a);
+    attn_fwd_kernel<2><<<grid, ATT_BWD_THREADS, SMEM, st>>>(tm, a);
   }
 }
 
@@ -564,7 +577,7 @@ void attention_bwd(const void* qkv, const int* seqlens, const void* ctx, const v
   static bool once = false;
   if (!once) { B200_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); once = true; }
   dim3 grid(nkb, B * h);
-  attn_bwd_kernel<<<grid, ATT_THREADS, SMEM, st>>>(tq, td, a);
+  attn_bwd_kernel<<<grid, ATT_BWD_THREADS, SMEM, st>>>(tq, td, a);
   if (nkb > 1) {
     const long long work = (long long)B * S * (H / 8);
     int g = (int)((work + 255) / 256);
