@@ -79,3 +79,18 @@ def init_distributed(backend: Optional[str] = None, device: Optional[torch.devic
         kw["device_id"] = device
     dist.init_process_group(backend=backend, init_method="env://", **kw)
     return backend
+
+
+class WorkerInitObj:
+    """``worker_init_fn`` for torch DataLoaders: gives every worker its own numpy / python RNG stream
+    (src/utils.py:22-27 defines this helper but the reference never uses it, quirk Q5)."""
+
+    def __init__(self, seed: int):
+        self.seed = seed
+
+    def __call__(self, worker_id: int) -> None:
+        import random
+
+        import numpy as np
+        np.random.seed(seed=self.seed + worker_id)
+        random.seed(self.seed + worker_id)
