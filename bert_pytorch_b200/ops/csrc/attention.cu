@@ -29,6 +29,11 @@ constexpr int ATT_BWD_THREADS = 288;   // backward: 8 math warps (2 per TMEM lan
 constexpr int TILE = 128;          // query rows / key rows per block
 constexpr int HD = 64;             // head dim
 constexpr float LOG2E = 1.4426950408889634f;
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 struct AttnArgs {
   int B, S, h, H;
@@ -160,16 +165,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs p) 
       tc_fence_after();
       // pass 1: row max over the valid keys of this half block
       float mx = -INFINITY;
+      const bool full = (j + 1) * TILE <= seqlen;         // every key of this block is valid (CTA uniform)
 #pragma unroll 1
       for (int c = ch * 4; c < ch * 4 + 4; ++c) {        // 16-column sub-chunks keep the register count low
         uint32_t v[16];
         tmem_ld_32x16(tS + lane_base + c * 16, v);
         tmem_ld_wait();
         const int k0 = j * TILE + c * 16;
+        if (full) {
 #pragma unroll
-        for (int t = 0; t < 16; ++t)
-          if (k0 + t < seqlen) mx = fmaxf(mx, __uint_as_float(v[t]) * c_scale);
+          for (int t = 0; t < 16; ++t) mx = fmaxf(mx, __uint_as_float(v[t]));
+        } else {
+#pragma unroll
+          for (int t = 0; t < 16; ++t)
+            if (k0 + t < seqlen) mx = fmaxf(mx, __uint_as_float(v[t]));
+        }
       }
+      mx *= c_scale;                                      // c_scale > 0: max commutes with the scaling
       float* xb = xch + (j & 1) * 256;
       xb[ch * 128 + r] = mx;
       asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -190,7 +202,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs p) 
 #pragma unroll
           for (int t = 0; t < 8; ++t) {
             const int key = k0 + g * 8 + t;
-            const float e = (key < seqlen) ? exp2f(__uint_as_float(v[g * 8 + t]) * c_scale - m_new) : 0.f;
+            float e = ex2_approx(fmaf(__uint_as_float(v[g * 8 + t]), c_scale, -m_new));
+            if (!full && key >= seqlen) e = 0.f;
             rowsum += e;
             pr[t] = e;
           }
@@ -428,7 +441,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
           for (int t = 0; t < 8; ++t) {
             const int key = k0 + g * 8 + t;
             const bool ok = q_ok && key < seqlen;
-            const float pr = ok ? exp2f(__uint_as_float(sv[g * 8 + t]) * c_scale - lse2) : 0.f;
+            const float pr = ok ? ex2_approx(fmaf(__uint_as_float(sv[g * 8 + t]), c_scale, -lse2)) : 0.f;
             const bool kp = (keep >> t) & 1u;
             const float dp = kp ? __uint_as_float(dv[g * 8 + t]) * p.inv_keep : 0.f;
             pd[t] = kp ? pr * p.inv_keep : 0.f;

@@ -67,12 +67,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Blocking wait with a watchdog: a protocol bug must trap (visible error), never hang the box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = globaltimer_ns();
-  while (!mbar_try_wait(bar, parity)) {
-    if (globaltimer_ns() - t0 > B200_WATCHDOG_NS) {
-      printf("[b200] mbarrier watchdog: block (%d,%d) thread %d parity %u\n", blockIdx.x, blockIdx.y,
-             threadIdx.x, parity);
-      __trap();
+  uint64_t t0 = 0;
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {          // try_wait itself suspends the thread for a HW-defined time
+    if ((++spins & 255u) == 0) {                 // look at the clock only now and then (keeps issue slots free)
+      const uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > B200_WATCHDOG_NS) {
+        printf("[b200] mbarrier watchdog: block (%d,%d) thread %d parity %u\n", blockIdx.x, blockIdx.y,
+               threadIdx.x, parity);
+        __trap();
+      }
     }
   }
 }
@@ -268,7 +273,8 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, b
 }
 
 // ------------------------------------------------------------------------------------------------
-// Philox4x32-10 counter RNG (dropout masks are a pure function of (seed, stream, element index) so the
+// Philox4x32-7 counter RNG (7 rounds: the Crush-resistant variant of Random123; 10 buys nothing for dropout)
+// Philox counter RNG (dropout masks are a pure function of (seed, stream, element index) so the
 // backward pass and any recompute regenerate them instead of storing them).
 // ------------------------------------------------------------------------------------------------
 struct Philox {
@@ -288,7 +294,7 @@ struct Philox {
     uint2 k = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
     uint4 c = make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), stream, 0x5EEDu);
 #pragma unroll
-    for (int i = 0; i < 10; ++i) {
+    for (int i = 0; i < 7; ++i) {
       c = round(c, k);
       k.x += kW0;
       k.y += kW1;

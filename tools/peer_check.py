@@ -77,8 +77,19 @@ def main():
             a_r.flat_grad.mul_(1.0 / (world * 4.0))
             o_r.step()
             torch.cuda.synchronize()
-            d = (a_f.flat_param - a_r.flat_param).abs().max().item()
+            diff = (a_f.flat_param - a_r.flat_param).abs()
+            d = diff.max().item()
             sh = (a_f.flat_shadow.float() - a_f.flat_param).abs().max().item()
+            if rank == 0:
+                i = int(diff.argmax())
+                slot = next((sl for sl in a_f.slots if sl.offset <= i < sl.offset + sl.numel), None)
+                lo, hi = comm.lo, comm.hi
+                dm = (a_f.exp_avg[lo:hi] - a_r.exp_avg[lo:hi]).abs().max().item()
+                dv = (a_f.exp_avg_sq[lo:hi] - a_r.exp_avg_sq[lo:hi]).abs().max().item()
+                out.setdefault(f"detail_mc{int(mc)}", []).append(
+                    dict(step=step, max_diff=d, at=i, slot=(slot.name if slot else "gap"), decay=(slot.decay if slot else None),
+                         p_fused=float(a_f.flat_param[i]), p_ref=float(a_r.flat_param[i]), dm=dm, dv=dv,
+                         gnorm_fused=float(comm.stats[2].sqrt()), gnorm_ref=float(o_r.last_grad_norm)))
             worst = max(worst, d)
             assert sh < 2e-2, sh
             # every rank must hold identical parameters
