@@ -160,6 +160,8 @@ def run_ours(args, ph, B, accum, rank, world, dev):
     model = BertForPreTraining(cfg).to(dev)
     arena = ParamArena(model, device=dev)
     comm = make_comm(args.backend if world > 1 else None)
+    if getattr(comm, "fuses_optimizer", False):
+        comm.adopt(arena)            # arenas -> NVLink symmetric memory; reduction + LAMB become one kernel
     ddp = DataParallel(model, comm=comm, arena=arena)
     named = list(model.named_parameters())
     groups = [{"params": [p for n, p in named if not any(k in n for k in NO_DECAY_KEYS)], "weight_decay": 0.01},

@@ -266,6 +266,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_allreduce_lamb_kernel(
       __syncthreads();
     }
   }
+  // The update directions u live in the gradient arena: every block must be done with phase C before anyone
+  // clears it (a missing barrier here silently dropped the update of late chunks).
+  grid_sync(a.grid_bar, gen);
   // zero the whole local gradient arena (all peers finished reading it: they passed barrier 1)
   {
     float4* g4 = reinterpret_cast<float4*>(lgrad);

@@ -327,23 +327,34 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
 }
-// erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, i.e. fp32-exact for our purposes) on one reciprocal,
-// one exp and five FMAs -- erff() costs ~3x more instructions and the GELU epilogues are instruction bound.
-__device__ __forceinline__ float erf_fast(float x) {
-  const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+// erf-GELU through the complementary error function of Abramowitz & Stegun 7.1.26:
+//   erfc(z) = (a1 t + ... + a5 t^5) exp(-z^2),  t = 1/(1 + p z),  z >= 0,  |error| <= 1.5e-7
+// so  Phi(x) = 0.5 erfc(|x|/sqrt2)  for x < 0  and  1 - that  for x >= 0  (no cancellation in the negative tail),
+// gelu(x) = x Phi(x)  and  gelu'(x) = Phi(x) + x phi(x)  with  phi(x) = exp(-x^2/2)/sqrt(2 pi)  sharing the SAME
+// exponential.  One rcp.approx + one ex2.approx + ~10 FMA-class instructions (erff() needs ~3x as many; the
+// GELU kernels and epilogues are instruction bound).
+struct GeluParts { float Phi, e; };   // e = exp(-x^2/2)
+__device__ __forceinline__ GeluParts gelu_parts(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
-  const float e = 1.0f - poly * t * __expf(-ax * ax);
-  return copysignf(e, x);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
+  const float h = 0.5f * poly * t * e;                 // 0.5 erfc(z)
+  GeluParts r;
+  r.Phi = x < 0.f ? h : 1.0f - h;
+  r.e = e;
+  return r;
 }
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float erf_fast(float x) { return 2.0f * gelu_parts(x * 1.4142135623730951f).Phi - 1.0f; }
+__device__ __forceinline__ float gelu_erf(float x) { return x * gelu_parts(x).Phi; }
 __device__ __forceinline__ float dgelu_erf(float x) {
-  const float cdf = 0.5f * (1.0f + erf_fast(x * 0.70710678118654752f));
-  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  const GeluParts g = gelu_parts(x);
+  return fmaf(x * 0.3989422804014327f, g.e, g.Phi);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
