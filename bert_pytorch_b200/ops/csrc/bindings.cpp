@@ -274,7 +274,7 @@ void fused_allreduce_lamb(int64_t rank, int64_t world, bool use_multicast, std::
                           Tensor chunk_len, Tensor decay_flag, Tensor stats, Tensor norms, Tensor grid_bar, int64_t epoch,
                           double grad_mul, double lr, double beta1, double beta2, double eps, double weight_decay,
                           double max_grad_norm, int64_t step, bool bias_correction, bool grad_averaging,
-                          bool adam_w_mode, bool use_nvlamb) {
+                          bool adam_w_mode, bool use_nvlamb, bool push_master) {
   TORCH_CHECK((int64_t)grad_ptrs.size() == world && world <= 16, "peer pointer lists must have `world` (<= 16) entries");
   TORCH_CHECK(lo % 4 == 0 && hi % 4 == 0 && numel % 4 == 0, "shard bounds must be multiples of 4 elements");
   c10::cuda::CUDAGuard guard(m.device());
@@ -300,7 +300,7 @@ void fused_allreduce_lamb(int64_t rank, int64_t world, bool use_multicast, std::
   L.grad_mul = (float)grad_mul; L.lr = (float)lr; L.beta1 = (float)beta1; L.beta2 = (float)beta2; L.eps = (float)eps;
   L.weight_decay = (float)weight_decay; L.max_grad_norm = (float)max_grad_norm; L.step = (int)step;
   L.bias_correction = bias_correction; L.grad_averaging = grad_averaging; L.adam_w_mode = adam_w_mode;
-  L.use_nvlamb = use_nvlamb;
+  L.use_nvlamb = use_nvlamb; L.push_master = push_master ? 1 : 0;
   b200::fused_allreduce_lamb(L, cur_stream());
 }
 

@@ -51,6 +51,7 @@ struct FusedLambArgs {
   float grad_mul;                         // 1 / (world * loss_scale)
   float lr, beta1, beta2, beta3, eps, weight_decay, bc1, bc2, max_grad_norm;
   int adam_w_mode, use_nvlamb;
+  int push_master;                        // 0: fp32 master stays shard-local (peers get only the bf16 shadow)
 };
 
 __device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int& gen) {
@@ -184,23 +185,41 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_allreduce_lamb_kernel(
     const float gnorm = sqrtf(gsumsq);
     const float clip = (a.max_grad_norm > 0.f && gnorm > a.max_grad_norm) ? gnorm / a.max_grad_norm : 1.f;
     const float inv_clip = 1.f / clip;
+    const float rbc1 = 1.f / a.bc1, rbc2 = 1.f / a.bc2;
     for (int c = blockIdx.x; c < a.nchunks; c += gridDim.x) {
       const int t = a.chunk_tensor[c];
       const long long off = a.chunk_start[c];
       const int n = a.chunk_len[c];
       const float wd = a.decay_flag[t] ? a.weight_decay : 0.f;
       float sp = 0.f, su = 0.f;
-      for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        float g = lgrad[off + i] * inv_clip;
-        const float pp = lparam[off + i];
+      auto one = [&](float g, float pp, float& mm, float& vv) -> float {
+        g *= inv_clip;
         if (!a.adam_w_mode) g += wd * pp;
-        const float mm = a.beta1 * a.m[off + i] + a.beta3 * g;
-        const float vv = a.beta2 * a.v[off + i] + (1.f - a.beta2) * g * g;
-        float u = (mm / a.bc1) / (sqrtf(vv / a.bc2) + a.eps);
+        mm = a.beta1 * mm + a.beta3 * g;
+        vv = a.beta2 * vv + (1.f - a.beta2) * g * g;
+        float u = (mm * rbc1) / (sqrtf(vv * rbc2) + a.eps);
         if (a.adam_w_mode) u += wd * pp;
+        sp += pp * pp; su += u * u;
+        return u;
+      };
+      const int nv = (off & 3) ? 0 : (n >> 2);           // 16 B path (chunks start 4-aligned except odd tails)
+      for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+        const long long o = off + 4 * i;
+        float4 g = *reinterpret_cast<const float4*>(lgrad + o);
+        const float4 pp = *reinterpret_cast<const float4*>(lparam + o);
+        float4 mm = *reinterpret_cast<const float4*>(a.m + o);
+        float4 vv = *reinterpret_cast<const float4*>(a.v + o);
+        g.x = one(g.x, pp.x, mm.x, vv.x); g.y = one(g.y, pp.y, mm.y, vv.y);
+        g.z = one(g.z, pp.z, mm.z, vv.z); g.w = one(g.w, pp.w, mm.w, vv.w);
+        *reinterpret_cast<float4*>(a.m + o) = mm;
+        *reinterpret_cast<float4*>(a.v + o) = vv;
+        *reinterpret_cast<float4*>(lgrad + o) = g;
+      }
+      for (int i = 4 * nv + threadIdx.x; i < n; i += blockDim.x) {
+        float mm = a.m[off + i], vv = a.v[off + i];
+        const float u = one(lgrad[off + i], lparam[off + i], mm, vv);
         a.m[off + i] = mm; a.v[off + i] = vv;
         lgrad[off + i] = u;
-        sp += pp * pp; su += u * u;
       }
       sp = block_sum_f(sp, sm);
       su = block_sum_f(su, sm);
@@ -249,19 +268,40 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_allreduce_lamb_kernel(
       }
       __syncthreads();
       const float ratio = s_bcast[0];
-      // chunks start on multiples of 4 elements except at tensor tails: scalar path keeps it simple and the
-      // stores still coalesce (consecutive threads -> consecutive addresses)
-      for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const float np = lparam[off + i] - ratio * lgrad[off + i];
-        const __nv_bfloat16 nb = __float2bfloat16(np);
-        if (a.use_multicast) {
-          asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(a.param_mc + off + i), "f"(np) : "memory");
+      const int nv = (off & 3) ? 0 : (n >> 2);
+      for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+        const long long o = off + 4 * i;
+        const float4 pp = *reinterpret_cast<const float4*>(lparam + o);
+        const float4 u = *reinterpret_cast<const float4*>(lgrad + o);
+        float4 np;
+        np.x = pp.x - ratio * u.x; np.y = pp.y - ratio * u.y; np.z = pp.z - ratio * u.z; np.w = pp.w - ratio * u.w;
+        uint2 nb;
+        nb.x = pack_bf16(np.x, np.y); nb.y = pack_bf16(np.z, np.w);
+        if (a.push_master && a.use_multicast) {
+          asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.param_mc + o), "f"(np.x),
+                       "f"(np.y), "f"(np.z), "f"(np.w) : "memory");
+        } else if (a.push_master) {
+#pragma unroll 1
+          for (int p = 0; p < a.world; ++p) *reinterpret_cast<float4*>(a.param[p] + o) = np;
+        } else {
+          *reinterpret_cast<float4*>(lparam + o) = np;
+        }
+        if (a.shadow_mc) {
+          asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(a.shadow_mc + o),
+                       "f"(__uint_as_float(nb.x)), "f"(__uint_as_float(nb.y)) : "memory");
         } else {
 #pragma unroll 1
-          for (int p = 0; p < a.world; ++p) a.param[p][off + i] = np;
+          for (int p = 0; p < a.world; ++p) *reinterpret_cast<uint2*>(a.shadow[p] + o) = nb;
         }
+      }
+      for (int i = 4 * nv + threadIdx.x; i < n; i += blockDim.x) {
+        const float np = lparam[off + i] - ratio * lgrad[off + i];
+        const __nv_bfloat16 nb = __float2bfloat16(np);
 #pragma unroll 1
-        for (int p = 0; p < a.world; ++p) a.shadow[p][off + i] = nb;
+        for (int p = 0; p < a.world; ++p) {
+          if (a.push_master || p == a.rank) a.param[p][off + i] = np;
+          a.shadow[p][off + i] = nb;
+        }
       }
       __syncthreads();
     }
@@ -298,7 +338,7 @@ void fused_allreduce_lamb(const FusedLambLaunch& L, cudaStream_t st) {
   a.eps = L.eps; a.weight_decay = L.weight_decay;
   a.bc1 = L.bias_correction ? 1.f - powf(L.beta1, (float)L.step) : 1.f;
   a.bc2 = L.bias_correction ? 1.f - powf(L.beta2, (float)L.step) : 1.f;
-  a.max_grad_norm = L.max_grad_norm; a.adam_w_mode = L.adam_w_mode; a.use_nvlamb = L.use_nvlamb;
+  a.max_grad_norm = L.max_grad_norm; a.adam_w_mode = L.adam_w_mode; a.use_nvlamb = L.use_nvlamb; a.push_master = L.push_master;
   B200_CUDA_CHECK(cudaMemsetAsync(L.grid_bar, 0, sizeof(unsigned int), st));
   int dev, sms;
   B200_CUDA_CHECK(cudaGetDevice(&dev));

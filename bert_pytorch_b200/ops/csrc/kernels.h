@@ -67,6 +67,7 @@ struct FusedLambLaunch {
   unsigned int epoch;
   float grad_mul, lr, beta1, beta2, eps, weight_decay, max_grad_norm;
   int step, bias_correction, grad_averaging, adam_w_mode, use_nvlamb;
+  int push_master = 1;   // 0: peers receive only the bf16 shadow; the fp32 master stays with its owner
 };
 void fused_allreduce_lamb(const FusedLambLaunch& L, cudaStream_t st);
 

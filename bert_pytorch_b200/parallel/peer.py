@@ -35,8 +35,16 @@ class PeerComm(TorchComm):
     name = "fused"
     fuses_optimizer = True
 
-    def __init__(self, group=None, use_multicast: Optional[bool] = None):
+    def __init__(self, group=None, use_multicast: Optional[bool] = None, push_master: Optional[bool] = None):
         super().__init__(group)
+        import os
+        # push_master=False keeps the fp32 master weights shard-local (ZeRO-1 style): only the bf16 shadow the
+        # kernels read is all-gathered, 3x less NVLink traffic; ``gather_master()`` restores full fp32 views
+        # before anything reads them (checkpoint, torch-path evaluation).  B200_PEER_MASTER_LOCAL=1 selects it.
+        if push_master is None:
+            push_master = os.environ.get("B200_PEER_MASTER_LOCAL", "0") != "1"
+        self.push_master = bool(push_master)
+        self._master_stale = False
         self.name = "fused"
         self.device = torch.device("cuda", torch.cuda.current_device())
         self.arena = None
@@ -121,16 +129,31 @@ class PeerComm(TorchComm):
             self.rank, self.world_size, mc,
             list(self.grad_h.buffer_ptrs), list(self.param_h.buffer_ptrs), list(self.shadow_h.buffer_ptrs),
             list(self.pad_h.buffer_ptrs), list(self.flag_h.buffer_ptrs),
-            int(self.grad_h.multicast_ptr) if mc else 0, int(self.param_h.multicast_ptr) if mc else 0, 0,
+            int(self.grad_h.multicast_ptr) if mc else 0, int(self.param_h.multicast_ptr) if mc else 0,
+            int(getattr(self.shadow_h, "multicast_ptr", 0) or 0) if mc else 0,
             A.exp_avg, A.exp_avg_sq, A.numel, self.lo, self.hi, self.chunk_tensor, self.chunk_start, self.chunk_len,
             decay, self.stats, self.norms, self.grid_bar, self.epoch, 1.0 / (self.world_size * loss_scale),
             float(lr), float(b1), float(b2), float(_uniform(optimizer, "eps")), wd,
             float(_uniform(optimizer, "max_grad_norm") or 0.0), step, bool(_uniform(optimizer, "bias_correction")),
-            bool(_uniform(optimizer, "grad_averaging")), bool(optimizer.adam_w_mode), bool(optimizer.use_nvlamb))
+            bool(_uniform(optimizer, "grad_averaging")), bool(optimizer.adam_w_mode), bool(optimizer.use_nvlamb),
+            self.push_master)
+        self._master_stale = not self.push_master
         ops.api._count()
         for g in optimizer.param_groups:       # bf16 path has no overflow; the fp16 path re-reads stats lazily
             g["step"] = step
         self.last_stats = self.stats
+
+    @torch.no_grad()
+    def gather_master(self) -> None:
+        """Make every rank's fp32 parameter arena complete again (only needed with ``push_master=False``):
+        zero the foreign shards and sum over the ranks -- cold path (checkpoint / evaluation)."""
+        if not self._master_stale:
+            return
+        flat = self.param_t
+        flat[: self.lo].zero_()
+        flat[self.hi:].zero_()
+        dist.all_reduce(flat, group=self.group)
+        self._master_stale = False
 
     # -- checkpoint support ----------------------------------------------------------------------------
     @torch.no_grad()
