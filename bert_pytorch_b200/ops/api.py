@@ -49,8 +49,10 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, layout: int = NT, epi: int = EPI_N
          out: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
          res: Optional[torch.Tensor] = None, aux_out: Optional[torch.Tensor] = None, k_splits: int = 1,
          block_n: Optional[int] = None, alpha: float = 1.0, p_drop: float = 0.0, seed: int = 0,
-         stream: int = 0) -> torch.Tensor:
-    """tcgen05 GEMM with a fused epilogue (see csrc/gemm_sm100.cu).  ``a``/``b`` are 2-D bf16."""
+         stream: int = 0, scale_a: Optional[torch.Tensor] = None, scale_b: Optional[torch.Tensor] = None,
+         a_e5m2: bool = False, b_e5m2: bool = False) -> torch.Tensor:
+    """tcgen05 GEMM with a fused epilogue (see csrc/gemm_sm100.cu).  ``a``/``b`` are 2-D bf16, or -- with
+    ``scale_a``/``scale_b`` (device inv-scale scalars from an :class:`Fp8Meta`) -- 1-byte fp8 tensors."""
     if layout == NT:
         M, N = a.size(0), b.size(0)
     elif layout == NN:
@@ -60,11 +62,58 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, layout: int = NT, epi: int = EPI_N
     if out is None:
         dt = torch.float32 if epi in (EPI_ACCUM_F32, EPI_F32) else torch.bfloat16
         out = torch.empty(M, N, dtype=dt, device=a.device)
-    if block_n is None:
+    if scale_a is not None:
+        block_n = 512                      # fp8 operands run on the CTA-pair kernel
+    elif block_n is None:
         block_n = _pick_block_n(M, N)
-    extension().gemm(a, b, out, layout, epi, bias, res, aux_out, k_splits, block_n, alpha, p_drop, seed, stream)
+    extension().gemm(a, b, out, layout, epi, bias, res, aux_out, k_splits, block_n, alpha, p_drop, seed, stream,
+                     scale_a, scale_b, a_e5m2, b_e5m2)
     _count()
     return out
+
+
+class Fp8Meta:
+    """Device-resident per-tensor scaling records ``{amax, scale, inv_scale, _}`` for the fp8 GEMM path
+    (delayed scaling: quantise with the scale derived from the previous step's amax; csrc/fp8.cu)."""
+
+    def __init__(self, sites: Sequence[str], e5m2: Sequence[bool], device, margin: float = 1.0):
+        self.index = {name: i for i, name in enumerate(sites)}
+        self.e5m2 = list(bool(x) for x in e5m2)
+        self.table = torch.zeros(len(sites), 4, dtype=torch.float32, device=device)
+        self.table[:, 1:3] = 1.0
+        self.flags = torch.tensor([1 if x else 0 for x in self.e5m2], dtype=torch.int32, device=device)
+        self.margin = float(margin)
+
+    def record(self, site) -> torch.Tensor:
+        return self.table[self.index[site] if isinstance(site, str) else site]
+
+    def inv_scale(self, site) -> torch.Tensor:
+        return self.record(site)[2:3]
+
+    def is_e5m2(self, site) -> bool:
+        return self.e5m2[self.index[site] if isinstance(site, str) else site]
+
+    def quantize(self, x: torch.Tensor, site, out: Optional[torch.Tensor] = None, calibrate: bool = False) -> torch.Tensor:
+        """bf16 -> fp8 bytes with the site's current scale; records amax for the next ``update``.  With
+        ``calibrate`` the scale is first derived from this very tensor (current scaling, one extra pass)."""
+        ext = extension()
+        rec = self.record(site)
+        e5 = self.is_e5m2(site)
+        if calibrate:
+            ext.fp8_amax(x, rec)
+            i = self.index[site] if isinstance(site, str) else site
+            ext.fp8_update(self.table[i:i + 1], self.flags[i:i + 1], self.margin)
+            _count(2)
+        if out is None:
+            out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+        ext.fp8_quantize(x, out, rec, e5)
+        _count()
+        return out
+
+    def update(self) -> None:
+        """new scales from the amaxes seen since the last update (one tiny launch for all sites)"""
+        extension().fp8_update(self.table, self.flags, self.margin)
+        _count()
 
 
 def wgrad_splits(n_out: int, k_out: int, reduce_len: int, block_n: int = 256) -> int:

@@ -27,11 +27,23 @@ inline float* opt_f32(const c10::optional<Tensor>& t) {
 
 // D = epilogue(A op B).  a/b are 2-D bf16 (row stride arbitrary, multiple of 8 elements).
 //   layout 0 (NT): a [M,K], b [N,K]     1 (NN): a [M,K], b [K,N]     2 (TN): a [K,M], b [K,N]
+// fp8 mode (scale_a/scale_b given): a/b are 1-byte e4m3 (or e5m2, per flag) tensors, row strides multiples of 16,
+// scale_* are the device inv_scale floats (views into the fp8 meta table); CTA-pair kernel only.
 void gemm(Tensor a, Tensor b, Tensor out, int64_t layout, int64_t epi, c10::optional<Tensor> bias,
           c10::optional<Tensor> res, c10::optional<Tensor> aux_out, int64_t k_splits, int64_t block_n, double alpha,
-          double p_drop, int64_t seed, int64_t stream_id) {
-  check_bf16(a, "a");
-  check_bf16(b, "b");
+          double p_drop, int64_t seed, int64_t stream_id, c10::optional<Tensor> scale_a, c10::optional<Tensor> scale_b,
+          bool a_e5m2, bool b_e5m2) {
+  const bool fp8 = scale_a.has_value() && scale_a->defined();
+  if (fp8) {
+    TORCH_CHECK(a.is_cuda() && b.is_cuda() && a.element_size() == 1 && b.element_size() == 1 && a.stride(1) == 1 &&
+                b.stride(1) == 1, "fp8 gemm operands must be CUDA 1-byte tensors with unit inner stride");
+    TORCH_CHECK(scale_b.has_value() && scale_b->defined(), "fp8 gemm needs both dequantisation factors");
+    TORCH_CHECK(a.stride(0) % 16 == 0 && b.stride(0) % 16 == 0 && reinterpret_cast<uintptr_t>(a.data_ptr()) % 16 == 0 &&
+                reinterpret_cast<uintptr_t>(b.data_ptr()) % 16 == 0, "fp8 operands must be 16-byte aligned");
+  } else {
+    check_bf16(a, "a");
+    check_bf16(b, "b");
+  }
   TORCH_CHECK(a.dim() == 2 && b.dim() == 2 && out.dim() == 2, "gemm operands must be 2-D");
   c10::cuda::CUDAGuard guard(a.device());
   b200::GemmCall c;
@@ -51,6 +63,10 @@ void gemm(Tensor a, Tensor b, Tensor out, int64_t layout, int64_t epi, c10::opti
   TORCH_CHECK(reinterpret_cast<uintptr_t>(out.data_ptr()) % 16 == 0 && out.stride(0) % (f32_out ? 4 : 8) == 0,
               "out must be 16-byte aligned with an aligned row stride");
   c.M = (int)M; c.N = (int)N; c.K = (int)K;
+  if (fp8) {
+    c.fp8 = true; c.a_e5m2 = a_e5m2; c.b_e5m2 = b_e5m2;
+    c.scale_a = opt_f32(scale_a); c.scale_b = opt_f32(scale_b);
+  }
   c.A = a.data_ptr(); c.lda = (int)a.stride(0);
   c.B = b.data_ptr(); c.ldb = (int)b.stride(0);
   c.out = out.data_ptr(); c.ldo = (int)out.stride(0);
@@ -304,11 +320,38 @@ void fused_allreduce_lamb(int64_t rank, int64_t world, bool use_multicast, std::
   b200::fused_allreduce_lamb(L, cur_stream());
 }
 
+void fp8_quantize(Tensor x, Tensor q, Tensor meta, bool e5m2) {
+  check_bf16(x, "x");
+  TORCH_CHECK(x.is_contiguous() && q.is_contiguous() && q.is_cuda() && q.element_size() == 1 && q.numel() == x.numel(),
+              "fp8_quantize: q must be a contiguous 1-byte tensor of x's size");
+  TORCH_CHECK(x.numel() % 16 == 0, "fp8_quantize: numel must be a multiple of 16");
+  TORCH_CHECK(meta.scalar_type() == at::kFloat && meta.is_cuda() && meta.numel() >= 4, "fp8 meta record");
+  c10::cuda::CUDAGuard guard(x.device());
+  b200::fp8_quantize(x.data_ptr(), q.data_ptr(), x.numel(), meta.data_ptr<float>(), e5m2, cur_stream());
+}
+
+void fp8_amax(Tensor x, Tensor meta) {
+  check_bf16(x, "x");
+  TORCH_CHECK(x.is_contiguous() && x.numel() % 8 == 0, "fp8_amax: contiguous, numel % 8 == 0");
+  c10::cuda::CUDAGuard guard(x.device());
+  b200::fp8_amax(x.data_ptr(), x.numel(), meta.data_ptr<float>(), cur_stream());
+}
+
+void fp8_update(Tensor meta, Tensor is_e5m2, double margin_pow2) {
+  TORCH_CHECK(meta.scalar_type() == at::kFloat && meta.is_cuda() && meta.is_contiguous() && meta.numel() % 4 == 0, "meta");
+  TORCH_CHECK(is_e5m2.scalar_type() == at::kInt && is_e5m2.numel() * 4 == meta.numel(), "is_e5m2 flags");
+  c10::cuda::CUDAGuard guard(meta.device());
+  b200::fp8_update(meta.data_ptr<float>(), (int)(meta.numel() / 4), is_e5m2.data_ptr<int>(), (float)margin_pow2, cur_stream());
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "bert_pytorch_b200 sm_100a kernels";
   m.def("gemm", &gemm);
+  m.def("fp8_quantize", &fp8_quantize);
+  m.def("fp8_amax", &fp8_amax);
+  m.def("fp8_update", &fp8_update);
   m.def("layer_norm_fwd", &layer_norm_fwd);
   m.def("layer_norm_bwd", &layer_norm_bwd);
   m.def("ln_bwd_workspace", &ln_bwd_workspace);

@@ -245,6 +245,15 @@ __device__ __forceinline__ void umma_bf16_ss_2sm(uint32_t tmem_d, uint64_t desc_
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// fp8 operands (e4m3 / e5m2 selected in the instruction descriptor), fp32 accumulation: K = 32 per instruction
+__device__ __forceinline__ void umma_fp8_ss_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive (once the issued MMAs retire) on the barrier at the same offset in every CTA of `cta_mask`
 __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
   asm volatile(
@@ -270,6 +279,13 @@ __host__ __device__ constexpr uint64_t umma_smem_desc_sw128(uint32_t smem_addr, 
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, bool a_mn_major, bool b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
          ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// kind::f8f6f4: same field layout; A/B format 0 = e4m3, 1 = e5m2
+__host__ __device__ constexpr uint32_t umma_idesc_fp8(uint32_t M, uint32_t N, bool a_mn_major, bool b_mn_major,
+                                                      uint32_t a_e5m2, uint32_t b_e5m2) {
+  return (1u << 4) | ((a_e5m2 & 1u) << 7) | ((b_e5m2 & 1u) << 10) | ((a_mn_major ? 1u : 0u) << 15) |
+         ((b_mn_major ? 1u : 0u) << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -60,13 +60,16 @@ struct GemmArgs {
   unsigned int drop_thresh16;
   float drop_scale;
   float alpha;
+  const float* scale_a;      // fp8: device dequantisation factors (nullptr for bf16 operands)
+  const float* scale_b;
+  unsigned int fp8_fmt;      // bit0: A is e5m2 (else e4m3), bit1: B is e5m2
 };
 
 // Drain one 128 x BLOCK_N fp32 accumulator tile (this warp's 32 TMEM lanes) through the selected epilogue.
 // `taddr` already carries the lane quarter; `row` is this thread's global output row.
 template <int BLOCK_N>
 __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint32_t taddr, int row, bool row_ok, int n_base,
-                                              int c_begin, int c_end) {
+                                              int c_begin, int c_end, float alpha) {
   #pragma unroll 1
   for (int c = c_begin; c < c_end; ++c) {
     const int n0 = n_base + c * 32;
@@ -76,7 +79,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint32_t taddr,
     tmem_ld_wait();
     float f[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * alpha;
     const int ncols = min(32, p.N - n0);  // multiple of 8
     const size_t roff = (size_t)row * p.ldr + n0;
     const size_t ooff = (size_t)row * p.ldo + n0;
@@ -309,7 +312,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const int row = mb * BLOCK_M + q * 32 + lane;
       const bool row_ok = row < p.M && kb1 > kb0;
       const uint32_t taddr = tmem_base + as * BLOCK_N + (uint32_t(q * 32) << 16);
-      epilogue_tile<BLOCK_N>(p, taddr, row, row_ok, nb * BLOCK_N, half * CH, half * CH + CH);
+      epilogue_tile<BLOCK_N>(p, taddr, row, row_ok, nb * BLOCK_N, half * CH, half * CH + CH, p.alpha);
       tc_fence_before();
       mbar_arrive(&tmem_empty[as]);
     }
@@ -343,7 +346,7 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 //                                 MODE 2: GELU second pass: staging -> gelu(staging)
 template <int MODE>
 __device__ __forceinline__ void staged_pass(const GemmArgs& p, uint8_t* sC, uint32_t taddr, int r, int row, int n_base,
-                                            int c_begin, bool use_res) {
+                                            int c_begin, bool use_res, float alpha) {
 #pragma unroll 1
   for (int c = c_begin; c < c_begin + 4; ++c) {
     const int col0 = c * 32;
@@ -367,7 +370,7 @@ __device__ __forceinline__ void staged_pass(const GemmArgs& p, uint8_t* sC, uint
       tmem_ld_32x32(taddr + col0, v);
       tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * alpha;
       const int ncols = min(32, p.N - n0);
       if (p.bias != nullptr) {
 #pragma unroll
@@ -439,7 +442,7 @@ constexpr int PAIR_M = 256, PAIR_N = 256, PAIR_STAGE = 32768, PAIR_STAGES = 5;
 constexpr int PAIR_CSTAGE = 128 * PAIR_N * 2;   // bf16 output/residual staging tile of one CTA: 4 x [128 x 64] swizzled boxes
 constexpr int PAIR_SMEM = PAIR_STAGES * PAIR_STAGE + PAIR_CSTAGE + 1024 + 256;
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool FP8>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_aux,
@@ -457,6 +460,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
+  // elements per k-block: one 128-byte swizzle row of the operand type.  The fp8 variant moves the same bytes
+  // per stage as bf16 (16 KB of A + 16 KB of B per CTA) and the same 32 bytes of K per MMA, at twice the FLOPs.
+  constexpr int BK = FP8 ? 128 : BLOCK_K;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -500,23 +506,32 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * PAIR_STAGE);
           const uint32_t fb = mapa_shared(smem_u32(&full_bar[s]), 0);
           if constexpr (!A_MN) {
-            tma_load_2d_2sm(sa, &tmap_a, fb, kb * BLOCK_K, m0);
+            tma_load_2d_2sm(sa, &tmap_a, fb, kb * BK, m0);
+          } else if constexpr (FP8) {
+            tma_load_2d_2sm(sa, &tmap_a, fb, m0, kb * BK);          // 128 MN bytes x 128 K rows: one box
           } else {
-            tma_load_2d_2sm(sa, &tmap_a, fb, m0, kb * BLOCK_K);
-            tma_load_2d_2sm(sa + 8192, &tmap_a, fb, m0 + 64, kb * BLOCK_K);
+            tma_load_2d_2sm(sa, &tmap_a, fb, m0, kb * BK);
+            tma_load_2d_2sm(sa + 8192, &tmap_a, fb, m0 + 64, kb * BK);
           }
           if constexpr (!B_MN) {
-            tma_load_2d_2sm(sb, &tmap_b, fb, kb * BLOCK_K, n0);
+            tma_load_2d_2sm(sb, &tmap_b, fb, kb * BK, n0);
+          } else if constexpr (FP8) {
+            tma_load_2d_2sm(sb, &tmap_b, fb, n0, kb * BK);
           } else {
-            tma_load_2d_2sm(sb, &tmap_b, fb, n0, kb * BLOCK_K);
-            tma_load_2d_2sm(sb + 8192, &tmap_b, fb, n0 + 64, kb * BLOCK_K);
+            tma_load_2d_2sm(sb, &tmap_b, fb, n0, kb * BK);
+            tma_load_2d_2sm(sb + 8192, &tmap_b, fb, n0 + 64, kb * BK);
           }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0 && leader) {           // ---------------- MMA issuer (leader CTA only)
-      constexpr uint32_t idesc = umma_idesc_bf16(PAIR_M, PAIR_N, A_MN, B_MN);
+      const uint32_t idesc = FP8 ? umma_idesc_fp8(PAIR_M, PAIR_N, A_MN, B_MN, p.fp8_fmt & 1u, (p.fp8_fmt >> 1) & 1u)
+                                 : umma_idesc_bf16(PAIR_M, PAIR_N, A_MN, B_MN);
+      // bytes between consecutive MMAs along K inside one stage: K-major 32 B (16 bf16 / 32 fp8); MN-major one
+      // MMA-K worth of rows (16 x 128 B for bf16, 32 x 128 B for fp8)
+      constexpr uint32_t A_KSTEP = A_MN ? (FP8 ? 4096u : 2048u) : 32u;
+      constexpr uint32_t B_KSTEP = B_MN ? (FP8 ? 4096u : 2048u) : 32u;
       uint32_t it = 0, tile_it = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += nclusters, ++tile_it) {
         const int ks = tile / (p.n_blocks * p.m_blocks);
@@ -537,9 +552,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const uint64_t db0 = B_MN ? umma_smem_desc_sw128(sb, 8192, 1024) : umma_smem_desc_sw128(sb, 16, 1024);
 #pragma unroll
           for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
-            const uint64_t da = da0 + (uint64_t)(A_MN ? (kk * 2048) >> 4 : (kk * 32) >> 4);
-            const uint64_t db = db0 + (uint64_t)(B_MN ? (kk * 2048) >> 4 : (kk * 32) >> 4);
-            umma_bf16_ss_2sm(tmem_d, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+            const uint64_t da = da0 + (uint64_t)((kk * A_KSTEP) >> 4);
+            const uint64_t db = db0 + (uint64_t)((kk * B_KSTEP) >> 4);
+            if constexpr (FP8) umma_fp8_ss_2sm(tmem_d, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+            else umma_bf16_ss_2sm(tmem_d, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
           }
           umma_commit_2sm(&empty_bar[s], 3);     // both CTAs may refill this slot
         }
@@ -554,6 +570,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                          (p.epi == EPI_BIAS_DROP_RES || p.epi == EPI_ADD || p.epi == EPI_DGELU);
     const bool issuer = threadIdx.x == 64;   // first epilogue thread drives the staging tile's TMA traffic
     const int r = q * 32 + lane;             // row inside the CTA tile == TMEM lane
+    float alpha = p.alpha;
+    if constexpr (FP8) alpha *= __ldg(p.scale_a) * __ldg(p.scale_b);   // per-tensor dequantisation
     auto load_res = [&](int tile) {
       const int nb = tile % p.n_blocks;
       const int mb = (tile / p.n_blocks) % p.m_blocks;
@@ -574,7 +592,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int row = row0 + r;
       const uint32_t taddr = tmem_base + as * PAIR_N + (uint32_t(q * 32) << 16);
       if (!staged) {
-        epilogue_tile<PAIR_N>(p, taddr, row, row < p.M, nb * PAIR_N, half * 4, half * 4 + 4);
+        epilogue_tile<PAIR_N>(p, taddr, row, row < p.M, nb * PAIR_N, half * 4, half * 4 + 4, alpha);
         tc_fence_before();
         mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), 0));
         continue;
@@ -583,8 +601,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         mbar_wait(c_full, c_phase);
         c_phase ^= 1;
       }
-      if (p.epi == EPI_BIAS_GELU) staged_pass<1>(p, sC, taddr, r, row, nb * PAIR_N, half * 4, false);
-      else staged_pass<0>(p, sC, taddr, r, row, nb * PAIR_N, half * 4, use_res);
+      if (p.epi == EPI_BIAS_GELU) staged_pass<1>(p, sC, taddr, r, row, nb * PAIR_N, half * 4, false, alpha);
+      else staged_pass<0>(p, sC, taddr, r, row, nb * PAIR_N, half * 4, use_res, alpha);
       tc_fence_before();
       mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), 0));   // accumulator drained: MMA may reuse it
       fence_proxy_async();
@@ -598,7 +616,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           tma_store_wait_read<0>();
         }
         epi_bar_sync();
-        staged_pass<2>(p, sC, taddr, r, row, nb * PAIR_N, half * 4, false);
+        staged_pass<2>(p, sC, taddr, r, row, nb * PAIR_N, half * 4, false, alpha);
         fence_proxy_async();
         epi_bar_sync();
       }
@@ -648,31 +666,43 @@ static EncodeTiledFn get_encode_fn() {
 
 // 2D bf16 tensor map: `inner` contiguous elements per row, `outer` rows, row pitch `ld` elements,
 // box = [box_outer][box_inner], 128B swizzle (box_inner must be 64 bf16).
+static CUtensorMap make_tmap_2d(const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                                uint32_t box_outer, uint32_t esize);
+
 CUtensorMap make_tmap_2d_bf16(const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
                               uint32_t box_outer) {
+  return make_tmap_2d(ptr, inner, outer, ld, box_inner, box_outer, 2);
+}
+
+// `esize` 2: bf16 (box_inner 64), 1: fp8 bytes (box_inner 128)
+static CUtensorMap make_tmap_2d(const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                                uint32_t box_outer, uint32_t esize) {
   struct Key {
-    const void* p; uint64_t i, o, l; uint32_t bi, bo;
-    bool operator==(const Key& k) const { return p == k.p && i == k.i && o == k.o && l == k.l && bi == k.bi && bo == k.bo; }
+    const void* p; uint64_t i, o, l; uint32_t bi, bo, es;
+    bool operator==(const Key& k) const {
+      return p == k.p && i == k.i && o == k.o && l == k.l && bi == k.bi && bo == k.bo && es == k.es;
+    }
   };
   struct Hash {
     size_t operator()(const Key& k) const {
       size_t h = reinterpret_cast<size_t>(k.p);
       h = h * 1000003u ^ k.i; h = h * 1000003u ^ k.o; h = h * 1000003u ^ k.l; h = h * 1000003u ^ k.bi;
+      h = h * 1000003u ^ k.es;
       return h * 1000003u ^ k.bo;
     }
   };
   static std::unordered_map<Key, CUtensorMap, Hash> cache;
   static std::mutex mu;
-  Key key{ptr, inner, outer, ld, box_inner, box_outer};
+  Key key{ptr, inner, outer, ld, box_inner, box_outer, esize};
   std::lock_guard<std::mutex> lock(mu);
   auto itf = cache.find(key);
   if (itf != cache.end()) return itf->second;
   CUtensorMap m;
   cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {ld * 2};
+  cuuint64_t strides[1] = {ld * esize};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box,
+  CUresult r = get_encode_fn()(&m, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box,
                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -717,6 +747,7 @@ static void launch(const GemmCall& c, cudaStream_t st) {
   p.drop_thresh16 = pd > 0.f ? (unsigned)(pd * 65536.f + 0.5f) : 0u;
   p.drop_scale = pd > 0.f ? 65536.f / (65536.f - (float)p.drop_thresh16) : 1.f;
   p.alpha = c.alpha;
+  p.scale_a = nullptr; p.scale_b = nullptr; p.fp8_fmt = 0;
   // operand maps
   CUtensorMap ta = A_MN ? make_tmap_2d_bf16(c.A, c.M, c.K, c.lda, 64, BLOCK_K)
                         : make_tmap_2d_bf16(c.A, c.K, c.M, c.lda, BLOCK_K, BLOCK_M);
@@ -734,13 +765,14 @@ static void launch(const GemmCall& c, cudaStream_t st) {
   kern<<<grid, NUM_THREADS, C::SMEM_TOTAL, st>>>(ta, tb, p);
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool FP8>
 static void launch_pair(const GemmCall& c, cudaStream_t st) {
+  constexpr int BK = FP8 ? 128 : BLOCK_K;
   GemmArgs p;
   p.M = c.M; p.N = c.N; p.K = c.K;
   p.m_blocks = (c.M + PAIR_M - 1) / PAIR_M;
   p.n_blocks = (c.N + PAIR_N - 1) / PAIR_N;
-  p.k_blocks = (c.K + BLOCK_K - 1) / BLOCK_K;
+  p.k_blocks = (c.K + BK - 1) / BK;
   p.k_splits = c.k_splits < 1 ? 1 : c.k_splits;
   if (p.k_splits > p.k_blocks) p.k_splits = p.k_blocks;
   p.k_per_split = (p.k_blocks + p.k_splits - 1) / p.k_splits;
@@ -754,17 +786,24 @@ static void launch_pair(const GemmCall& c, cudaStream_t st) {
   p.drop_thresh16 = pd > 0.f ? (unsigned)(pd * 65536.f + 0.5f) : 0u;
   p.drop_scale = pd > 0.f ? 65536.f / (65536.f - (float)p.drop_thresh16) : 1.f;
   p.alpha = c.alpha;
-  // each CTA loads 128-row boxes of A and 128-column boxes of B
-  CUtensorMap ta = A_MN ? make_tmap_2d_bf16(c.A, c.M, c.K, c.lda, 64, BLOCK_K)
-                        : make_tmap_2d_bf16(c.A, c.K, c.M, c.lda, BLOCK_K, 128);
-  CUtensorMap tb = B_MN ? make_tmap_2d_bf16(c.B, c.N, c.K, c.ldb, 64, BLOCK_K)
-                        : make_tmap_2d_bf16(c.B, c.K, c.N, c.ldb, BLOCK_K, 128);
+  p.scale_a = c.scale_a; p.scale_b = c.scale_b;
+  p.fp8_fmt = (c.a_e5m2 ? 1u : 0u) | (c.b_e5m2 ? 2u : 0u);
+  if (FP8 && (c.scale_a == nullptr || c.scale_b == nullptr)) {
+    fprintf(stderr, "[b200] fp8 gemm needs the device dequantisation factors of both operands\n");
+    abort();
+  }
+  // each CTA loads 128-row boxes of A and 128-column boxes of B (one 128-byte swizzle row wide)
+  constexpr uint32_t ES = FP8 ? 1 : 2, BI = FP8 ? 128 : 64;
+  CUtensorMap ta = A_MN ? make_tmap_2d(c.A, c.M, c.K, c.lda, BI, BK, ES)
+                        : make_tmap_2d(c.A, c.K, c.M, c.lda, BK, 128, ES);
+  CUtensorMap tb = B_MN ? make_tmap_2d(c.B, c.N, c.K, c.ldb, BI, BK, ES)
+                        : make_tmap_2d(c.B, c.K, c.N, c.ldb, BK, 128, ES);
   const bool f32_out = c.epi == EPI_ACCUM_F32 || c.epi == EPI_F32;
   // output / pre-activation / residual tiles of one CTA travel as 4 boxes of [128 rows x 64 columns]
   CUtensorMap to = f32_out ? ta : make_tmap_2d_bf16(c.out, c.N, c.M, c.ldo, 64, 128);
   CUtensorMap tx = (c.aux_out != nullptr && !f32_out) ? make_tmap_2d_bf16(c.aux_out, c.N, c.M, c.ldo, 64, 128) : to;
   CUtensorMap tr = (c.res != nullptr && !f32_out) ? make_tmap_2d_bf16(c.res, c.N, c.M, c.ldr, 64, 128) : to;
-  auto kern = gemm_pair_kernel<A_MN, B_MN>;
+  auto kern = gemm_pair_kernel<A_MN, B_MN, FP8>;
   static bool configured = false;
   if (!configured) {
     B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
@@ -778,11 +817,15 @@ static void launch_pair(const GemmCall& c, cudaStream_t st) {
 }
 
 void gemm_bf16(const GemmCall& c, cudaStream_t st) {
+  if (c.fp8 && c.block_n != 512) {
+    fprintf(stderr, "[b200] fp8 operands are implemented on the CTA-pair kernel only (block_n=512)\n");
+    abort();
+  }
   if (c.block_n == 512) {   // CTA-pair 256 x 256 tiles
     switch (c.layout) {
-      case GEMM_NT: launch_pair<false, false>(c, st); return;
-      case GEMM_NN: launch_pair<false, true>(c, st); return;
-      case GEMM_TN: launch_pair<true, true>(c, st); return;
+      case GEMM_NT: c.fp8 ? launch_pair<false, false, true>(c, st) : launch_pair<false, false, false>(c, st); return;
+      case GEMM_NN: c.fp8 ? launch_pair<false, true, true>(c, st) : launch_pair<false, true, false>(c, st); return;
+      case GEMM_TN: c.fp8 ? launch_pair<true, true, true>(c, st) : launch_pair<true, true, false>(c, st); return;
       default: fprintf(stderr, "[b200] bad gemm layout %d\n", c.layout); abort();
     }
   }

@@ -38,6 +38,11 @@ struct GemmCall {
   int k_splits = 1;
   unsigned long long seed = 0; unsigned int stream = 0; float p_drop = 0.f;
   float alpha = 1.f;
+  // fp8 operands (CTA-pair kernel): A/B are e4m3 (default) or e5m2 bytes, lda/ldb in elements (= bytes);
+  // scale_a/scale_b point at the device-resident per-tensor dequantisation factors (x = q * scale)
+  bool fp8 = false, a_e5m2 = false, b_e5m2 = false;
+  const float* scale_a = nullptr;
+  const float* scale_b = nullptr;
 };
 
 void gemm_bf16(const GemmCall& c, cudaStream_t st);

@@ -71,4 +71,9 @@ struct FusedLambLaunch {
 };
 void fused_allreduce_lamb(const FusedLambLaunch& L, cudaStream_t st);
 
+// fp8.cu: per-tensor scaled fp8 operand preparation; meta records are {amax, scale, inv_scale, _}
+void fp8_quantize(const void* x_bf16, void* q, long long n, float* meta, bool e5m2, cudaStream_t st);
+void fp8_amax(const void* x_bf16, long long n, float* meta, cudaStream_t st);
+void fp8_update(float* meta, int nrec, const int* is_e5m2, float margin_pow2, cudaStream_t st);
+
 }  // namespace b200

@@ -226,21 +226,39 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
 // (first version, one warp per row with 32 columns per lane: 38 us for a 100 MB backward pass).
 // Row statistics travel through shared memory + a named barrier per row group.
 // ------------------------------------------------------------------------------------------------
+// two sums at once across the WPR warps of a row group: ONE named barrier per row -- the exchange slots are
+// double buffered by row parity (a warp can only overwrite parity p again after the barrier of the row in
+// between, which the slowest reader of parity p has to reach first).
 template <int WPR>
-__device__ __forceinline__ float group_sum(float v, float* slot, int wi, int group) {
-  v = warp_sum(v);
-  if (WPR == 1) return v;
-  if ((threadIdx.x & 31) == 0) slot[wi] = v;
+__device__ __forceinline__ float2 group_sum2(float a, float b, float2* slot, int wi, int group) {
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if (WPR == 1) return make_float2(a, b);
+  if ((threadIdx.x & 31) == 0) slot[wi] = make_float2(a, b);
   if (group == 0) asm volatile("bar.sync 1, %0;" ::"n"(WPR * 32) : "memory");
   else asm volatile("bar.sync 2, %0;" ::"n"(WPR * 32) : "memory");
-  float t = 0.f;
+  float2 t = make_float2(0.f, 0.f);
 #pragma unroll
-  for (int w = 0; w < WPR; ++w) t += slot[w];
-  if (group == 0) asm volatile("bar.sync 1, %0;" ::"n"(WPR * 32) : "memory");   // slot reusable
-  else asm volatile("bar.sync 2, %0;" ::"n"(WPR * 32) : "memory");
+  for (int w = 0; w < WPR; ++w) { const float2 v = slot[w]; t.x += v.x; t.y += v.y; }
   return t;
 }
 
+// 16-byte streaming load (read once: do not keep it in L1)
+__device__ __forceinline__ uint4 ld_stream16(const __nv_bfloat16* p) {
+  uint4 u;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(p));
+  return u;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float2 f = unpack_bf16(w[t]);
+    v[2 * t] = f.x;
+    v[2 * t + 1] = f.y;
+  }
+}
 __device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
   const uint4 u = *reinterpret_cast<const uint4*>(p);
   const uint32_t w[4] = {u.x, u.y, u.z, u.w};
@@ -261,7 +279,7 @@ __global__ void __launch_bounds__(2 * WPR * 32)
 ln_fwd2_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int H,
                float eps, unsigned long long seed, unsigned int stream, unsigned int thresh16, float drop_scale) {
-  __shared__ float xchg[2][16];
+  __shared__ float2 xchg[2][2][8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int group = warp / WPR, wi = warp % WPR;
   const int col = (wi * 32 + lane) * 8;
@@ -269,23 +287,32 @@ ln_fwd2_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ ga
   float g[8], b[8];
 #pragma unroll
   for (int t = 0; t < 8; ++t) { g[t] = live ? gamma[col + t] : 0.f; b[t] = live ? beta[col + t] : 0.f; }
-  for (int row = blockIdx.x * 2 + group; row < M; row += gridDim.x * 2) {
+  const int stride = gridDim.x * 2;
+  int row = blockIdx.x * 2 + group;
+  uint4 nx = make_uint4(0, 0, 0, 0);
+  float nshift = 0.f;
+  if (row < M) {
+    if (live) nx = ld_stream16(x + (size_t)row * H + col);
+    nshift = __bfloat162float(x[(size_t)row * H]);
+  }
+  for (int it = 0; row < M; row += stride, ++it) {
     float v[8];
-    if (live) load8(x + (size_t)row * H + col, v);
-    else {
-#pragma unroll
-      for (int t = 0; t < 8; ++t) v[t] = 0.f;
+    unpack8(nx, v);
+    const float shift = nshift;           // first element of the row: keeps sum / sum-of-squares well conditioned
+    const int nrow = row + stride;
+    if (nrow < M) {                        // prefetch the next row before this row's barrier
+      if (live) nx = ld_stream16(x + (size_t)nrow * H + col);
+      nshift = __bfloat162float(x[(size_t)nrow * H]);
     }
-    float s = 0.f;
-#pragma unroll
-    for (int t = 0; t < 8; ++t) s += v[t];
-    const float mean = group_sum<WPR>(s, xchg[group], wi, group) / (float)H;
-    float qv = 0.f;
+    float s = 0.f, q = 0.f;
     if (live) {
 #pragma unroll
-      for (int t = 0; t < 8; ++t) { const float d = v[t] - mean; qv += d * d; }
+      for (int t = 0; t < 8; ++t) { const float d = v[t] - shift; s += d; q += d * d; }
     }
-    const float rstd = rsqrtf(group_sum<WPR>(qv, xchg[group], wi, group) / (float)H + eps);
+    const float2 r = group_sum2<WPR>(s, q, xchg[group][it & 1], wi, group);
+    const float ms = r.x / (float)H;
+    const float mean = shift + ms;
+    const float rstd = rsqrtf(fmaxf(r.y / (float)H - ms * ms, 0.f) + eps);
     if (live) {
       uint32_t keep = 0xFFu;
       if (thresh16 != 0) keep = dropout_keep8(seed, stream, ((uint64_t)row * H + col) >> 3, thresh16);
@@ -311,7 +338,7 @@ ln_bwd2_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __rest
                __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dxd, float* __restrict__ partial, int M,
                int H, unsigned long long seed, unsigned int drop_stream, unsigned int in_stream,
                unsigned int thresh16, float drop_scale) {
-  __shared__ float xchg[2][16];
+  __shared__ float2 xchg[2][2][8];
   __shared__ float comb[3][WPR * 256];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int group = warp / WPR, wi = warp % WPR;
@@ -320,16 +347,24 @@ ln_bwd2_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __rest
   float g[8], ag[8], ab[8], ad[8];
 #pragma unroll
   for (int t = 0; t < 8; ++t) { g[t] = live ? gamma[col + t] : 0.f; ag[t] = ab[t] = ad[t] = 0.f; }
-  for (int row = blockIdx.x * 2 + group; row < M; row += gridDim.x * 2) {
+  const int stride = gridDim.x * 2;
+  int row = blockIdx.x * 2 + group;
+  uint4 nd = make_uint4(0, 0, 0, 0), nv = make_uint4(0, 0, 0, 0);
+  float nmu = 0.f, nrs = 0.f;
+  if (row < M) {
+    if (live) { nd = ld_stream16(dy + (size_t)row * H + col); nv = ld_stream16(x + (size_t)row * H + col); }
+    nmu = mean[row]; nrs = rstd[row];
+  }
+  for (int it = 0; row < M; row += stride, ++it) {
     float d[8], v[8];
-    if (live) {
-      load8(dy + (size_t)row * H + col, d);
-      load8(x + (size_t)row * H + col, v);
-    } else {
-#pragma unroll
-      for (int t = 0; t < 8; ++t) d[t] = v[t] = 0.f;
+    unpack8(nd, d);
+    unpack8(nv, v);
+    const float mu = nmu, rs = nrs;
+    const int nrow = row + stride;
+    if (nrow < M) {                        // next row's loads are in flight across this row's barrier
+      if (live) { nd = ld_stream16(dy + (size_t)nrow * H + col); nv = ld_stream16(x + (size_t)nrow * H + col); }
+      nmu = mean[nrow]; nrs = rstd[nrow];
     }
-    const float mu = mean[row], rs = rstd[row];
     if (in_stream != 0xFFFFFFFFu && thresh16 != 0 && live) {
       const uint32_t keep = dropout_keep8(seed, in_stream, ((uint64_t)row * H + col) >> 3, thresh16);
 #pragma unroll
@@ -338,7 +373,7 @@ ln_bwd2_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __rest
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
-      const float xh = (v[t] - mu) * rs;
+      const float xh = live ? (v[t] - mu) * rs : 0.f;
       const float dg = d[t] * g[t];
       ag[t] += d[t] * xh;
       ab[t] += d[t];
@@ -347,8 +382,9 @@ ln_bwd2_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __rest
       s1 += dg;
       s2 += dg * xh;
     }
-    s1 = group_sum<WPR>(s1, xchg[group], wi, group) / (float)H;
-    s2 = group_sum<WPR>(s2, xchg[group], wi, group) / (float)H;
+    const float2 r = group_sum2<WPR>(s1, s2, xchg[group][it & 1], wi, group);
+    s1 = r.x / (float)H;
+    s2 = r.y / (float)H;
     if (live) {
 #pragma unroll
       for (int t = 0; t < 8; ++t) d[t] = rs * (d[t] - s1 - v[t] * s2);
@@ -683,9 +719,9 @@ static inline int ln_grid(int M) {
     else { fprintf(stderr, "[b200] hidden size %d too large for the LN kernels\n", (H)); abort(); } \
   } while (0)
 
-static inline int ln2_grid(int M) {
+static inline int ln2_grid(int M) {     // 2 rows per block at a time; 4 resident blocks per SM
   int g = (M + 1) / 2;
-  return g < 148 * 8 ? g : 148 * 8;
+  return g < 148 * 4 ? g : 148 * 4;
 }
 
 void layer_norm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int M,

@@ -1,0 +1,88 @@
+"""fp8 (e4m3 / e5m2, per-tensor delayed scaling) operands on the tcgen05 CTA-pair GEMM vs fp32 references."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from bert_pytorch_b200 import ops
+    return ops
+
+
+def _deq(q, meta, site):
+    dt = torch.float8_e5m2 if meta.is_e5m2(site) else torch.float8_e4m3fn
+    return q.view(dt).float() * meta.inv_scale(site)
+
+
+@pytest.mark.parametrize("layout", ["NT", "NN", "TN"])
+@pytest.mark.parametrize("shape", [(512, 768, 1024), (256, 256, 128), (1000, 520, 384)])
+def test_fp8_gemm_matches_dequantised_reference(layout, shape):
+    ops = _ops()
+    api = ops.api
+    M, N, K = shape
+    if layout == "TN":
+        M, N = (M + 15) // 16 * 16, (N + 15) // 16 * 16
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cuda").manual_seed(5)
+    if layout == "NT":
+        a = torch.randn(M, K, device=dev, generator=g).bfloat16()
+        b = (torch.randn(N, K, device=dev, generator=g) * 0.05).bfloat16()
+    elif layout == "NN":
+        a = (torch.randn(M, K, device=dev, generator=g) * 1e-3).bfloat16()
+        b = (torch.randn(K, N - N % 16, device=dev, generator=g) * 0.05).bfloat16()
+    else:
+        a = (torch.randn(K, M, device=dev, generator=g) * 1e-3).bfloat16()
+        b = torch.randn(K, N, device=dev, generator=g).bfloat16()
+    a_e5 = layout != "NT"                       # gradients travel as e5m2, activations / weights as e4m3
+    meta = api.Fp8Meta(["a", "b"], [a_e5, False], dev)
+    qa = meta.quantize(a, "a", calibrate=True)
+    qb = meta.quantize(b, "b", calibrate=True)
+    lay = {"NT": api.NT, "NN": api.NN, "TN": api.TN}[layout]
+    epi = api.EPI_F32 if layout == "TN" else api.EPI_NONE
+    out = api.gemm(qa, qb, layout=lay, epi=epi, scale_a=meta.inv_scale("a"), scale_b=meta.inv_scale("b"),
+                   a_e5m2=a_e5, b_e5m2=False)
+    torch.cuda.synchronize()
+    da, db = _deq(qa, meta, "a"), _deq(qb, meta, "b")
+    ref = {"NT": lambda: da @ db.t(), "NN": lambda: da @ db, "TN": lambda: da.t() @ db}[layout]()
+    err = (out.float() - ref).abs().max().item()
+    tol = 1e-2 * ref.abs().max().item() + 1e-6       # bf16 output rounding (fp32 for TN)
+    assert err <= tol, (layout, shape, err, tol)
+    # and the quantisation itself is sane: relative error vs the unquantised product within fp8 expectations
+    full = {"NT": lambda: a.float() @ b.float().t(), "NN": lambda: a.float() @ b.float(),
+            "TN": lambda: a.float().t() @ b.float()}[layout]()
+    rel = (out.float() - full).norm() / full.norm()
+    assert rel < (0.2 if a_e5 else 0.08), rel
+
+
+def test_fp8_quantize_roundtrip_and_delayed_update():
+    ops = _ops()
+    api = ops.api
+    dev = torch.device("cuda")
+    x = (torch.randn(4096, 1024, device=dev) * 3).bfloat16()
+    meta = api.Fp8Meta(["x", "g"], [False, True], dev)
+    q = meta.quantize(x, "x", calibrate=True)
+    rec = meta.record("x").tolist()
+    amax = x.float().abs().max().item()
+    assert rec[0] == pytest.approx(amax)                  # amax re-recorded by the quantise pass
+    assert amax * rec[1] <= 448.0 and amax * rec[1] * 2 > 448.0
+    deq = _deq(q, meta, "x")
+    assert ((deq - x.float()).abs() <= x.float().abs() * 0.0625 + 2e-3 / rec[1]).all()
+    meta.update()                                          # delayed scaling: same scale again, amax cleared
+    rec2 = meta.record("x").tolist()
+    assert rec2[0] == 0.0 and rec2[1] == rec[1]
+    assert meta.record("g").tolist()[1] == 1.0             # untouched site keeps its scale
+
+
+def test_fp8_gemm_bias_epilogue():
+    ops = _ops()
+    api = ops.api
+    dev = torch.device("cuda")
+    a = torch.randn(768, 1024, device=dev).bfloat16()
+    w = (torch.randn(1024, 1024, device=dev) * 0.03).bfloat16()
+    bias = torch.randn(1024, device=dev).bfloat16()
+    meta = api.Fp8Meta(["a", "w"], [False, False], dev)
+    qa, qw = meta.quantize(a, "a", calibrate=True), meta.quantize(w, "w", calibrate=True)
+    out = api.gemm(qa, qw, epi=api.EPI_BIAS, bias=bias, scale_a=meta.inv_scale("a"), scale_b=meta.inv_scale("w"))
+    ref = _deq(qa, meta, "a") @ _deq(qw, meta, "w").t() + bias.float()
+    assert (out.float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()

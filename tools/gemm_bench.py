@@ -60,6 +60,22 @@ def main():
                 o = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
                 t = timeit(lambda: K.gemm(a, b, layout=layout, out=o, block_n=bn))
                 rec[f"ours_bn{bn}_ms"], rec[f"ours_bn{bn}_tflops"] = round(t, 4), round(flops / t / 1e9, 1)
+        if "--fp8" in sys.argv:          # same shape with e4m3 (e5m2 for the gradient operand) bytes on the pair kernel
+            a_e5 = layout != K.NT
+            meta = K.Fp8Meta(["a", "b"], [a_e5, False], "cuda")
+            qa, qb = meta.quantize(a, "a", calibrate=True), meta.quantize(b, "b", calibrate=True)
+            kw = dict(layout=layout, scale_a=meta.inv_scale("a"), scale_b=meta.inv_scale("b"), a_e5m2=a_e5)
+            if layout == K.TN:
+                o = torch.zeros(m, n, device="cuda")
+                for sp in (1, 2, 4):
+                    t = timeit(lambda: K.gemm(qa, qb, epi=K.EPI_ACCUM_F32, out=o, k_splits=sp, **kw))
+                    rec[f"fp8_s{sp}_tflops"] = round(flops / t / 1e9, 1)
+            else:
+                o = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
+                t = timeit(lambda: K.gemm(qa, qb, out=o, **kw))
+                rec["fp8_ms"], rec["fp8_tflops"] = round(t, 4), round(flops / t / 1e9, 1)
+            t = timeit(lambda: meta.quantize(a, "a", out=qa))
+            rec["quantize_a_gbs"] = round(a.numel() * 3 / t / 1e6, 1)
         out.append(rec)
         print(json.dumps(rec), flush=True)
 

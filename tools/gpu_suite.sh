@@ -17,7 +17,8 @@ for s in $STAGES; do
     smoke)   timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" ;;
     bench)   timeout 900 python bench.py --steps ${BENCH_STEPS:-3} --warmup 3 ${BENCH_ARGS:-} > gpurun_out/bench_ours.json 2> gpurun_out/bench_ours.err; echo "bench rc=$?"; tail -c 1500 gpurun_out/bench_ours.json ;;
     ref)     timeout 1200 python bench.py --impl reference --steps ${BENCH_STEPS:-3} --warmup 3 ${BENCH_ARGS:-} > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"; tail -c 1500 gpurun_out/bench_ref.json ;;
-    gemmbench) timeout 600 python tools/gemm_bench.py > gpurun_out/gemm_bench.json 2> gpurun_out/gemm_bench.err; echo "gemmbench rc=$?"; tail -c 3000 gpurun_out/gemm_bench.json ;;
+    fp8)     timeout 600 python -m pytest tests/test_gpu_fp8.py -m gpu -q --timeout 300 > gpurun_out/test_fp8.log 2>&1; echo "fp8 rc=$?"; tail -15 gpurun_out/test_fp8.log ;;
+    gemmbench) timeout 600 python tools/gemm_bench.py ${GEMMBENCH_ARGS:-} > gpurun_out/gemm_bench.json 2> gpurun_out/gemm_bench.err; echo "gemmbench rc=$?"; tail -c 3000 gpurun_out/gemm_bench.json ;;
     launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --accum 1 --no-e2e > gpurun_out/launches.log 2>&1; echo "launches rc=$?" ;;
     ncu_gemm) timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 12 -c 2 -f -o gpurun_out/prof_gemm python tools/gemm_bench.py --only ${NCU_SHAPE:-qkv_fwd} > gpurun_out/ncu_gemm.log 2>&1; echo "ncu_gemm rc=$?" ;;
     ncu_attn) timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_ -s 6 -c 3 -f -o gpurun_out/prof_attn python tools/attn_bench.py > gpurun_out/ncu_attn.log 2>&1; echo "ncu_attn rc=$?" ;;
