@@ -62,6 +62,7 @@ def parse():
     ap.add_argument("--backend", default="nccl", choices=["nccl", "fused"], help="gradient reduction (ours)")
     ap.add_argument("--layers", type=int, default=0, help="debug only: fewer layers (marks the result invalid)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--fp8", action="store_true", help="fp8 GEMM operands (separate config; the headline stays bf16)")
     ap.add_argument("--seed", type=int, default=42)
     return ap.parse_args()
 
@@ -172,6 +173,8 @@ def run_ours(args, ph, B, accum, rank, world, dev):
     scaler = GradScaler(enabled=False)
     crit = BertPretrainingCriterion(cfg.vocab_size)
     model.train()
+    if args.fp8:
+        model.bert.fused_engine().enable_fp8()
     flusher = L2Flusher(dev)
 
     pool = synth_batches(8, B, ph["seq"], MODEL["vocab_size"], ph["max_pred"], args.seed + 17 * rank, torch.int32)
@@ -309,7 +312,8 @@ def main():
         "metric": f"BERT-large phase{args.phase} (seq{ph['seq']}) pretraining sequences/sec, whole job, device-timed max over ranks",
         "value": round(value, 2), "unit": "sequences/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16" if args.impl == "ours" else "fp16 (reference stock AMP)", "data": "synthetic",
+        "dtype": ("fp8 GEMM operands (e4m3 fwd / e5m2 grads, per-tensor delayed scaling) + bf16" if args.fp8 else "bf16")
+        if args.impl == "ours" else "fp16 (reference stock AMP)", "data": "synthetic",
         "impl": args.impl,
         "config": {"model": "bert-large-uncased L24 H1024 A16 I4096 V30528" + (f" [DEBUG layers={args.layers}]" if args.layers else ""),
                    "global_batch": global_batch, "seq_len": ph["seq"], "local_batch": B, "accumulation_steps": accum,

@@ -92,6 +92,7 @@ class ParamArena:
         self.flat_shadow = (torch.zeros(self.numel, dtype=shadow_dtype, device=self.device)
                             if shadow_dtype is not None else None)
         self.by_name: Dict[str, Slot] = {s.name: s for s in self.slots}
+        self.version = 0          # bumped whenever the weights change (consumers cache derived copies, e.g. fp8)
         with torch.no_grad():
             for s, p in zip(self.slots, self.params):
                 view = self.flat_param[s.offset:s.offset + s.numel].view(s.shape)
@@ -126,6 +127,7 @@ class ParamArena:
 
     @torch.no_grad()
     def refresh_shadow(self) -> None:
+        self.version += 1
         if self.flat_shadow is not None:
             self.flat_shadow.copy_(self.flat_param)
 
@@ -212,10 +214,12 @@ class ParamArena:
 
     def fused_lamb_step(self, optimizer, inv_scale=None, found_inf=None) -> None:
         from .. import ops
+        self.version += 1
         ops.arena_lamb_step(self, optimizer, inv_scale, found_inf)
 
     def fused_adam_step(self, optimizer, inv_scale=None, found_inf=None) -> None:
         from .. import ops
+        self.version += 1
         ops.arena_adam_step(self, optimizer, inv_scale, found_inf)
 
     # -- sharding helpers (partitioned optimizer / reduce-scatter) ----------------------

@@ -28,7 +28,7 @@ from __future__ import annotations
 import math
 import os
 from dataclasses import dataclass, field
-from typing import List, Optional
+from typing import Dict, List, Optional
 
 import torch
 import torch.nn.functional as F
@@ -66,6 +66,10 @@ class _LayerSaved:
     mean2: torch.Tensor = None
     rstd2: torch.Tensor = None
     sdpa: tuple = None
+    x_op: torch.Tensor = None      # operands of the four weight-gradient GEMMs (bf16 tensors or their fp8 copies)
+    ctx_op: torch.Tensor = None
+    x1_op: torch.Tensor = None
+    act_op: torch.Tensor = None
 
 
 @dataclass
@@ -112,6 +116,12 @@ class FusedEncoderEngine:
         self._seed_base = int(torch.initial_seed()) & 0x7FFFFFFF
         self._calls = 0
         self._hook = torch.zeros(1, device=arena.device, requires_grad=True)
+        # fp8 GEMM operands (B200_FP8=1 or enable_fp8()): activations / weights as e4m3, gradients as e5m2,
+        # per-tensor delayed scaling; LN / GELU / attention / residual stream / master weights unchanged
+        self.fp8 = False
+        self.meta = None
+        if os.environ.get("B200_FP8", "0") == "1":
+            self.enable_fp8()
 
     # -- parameter lookup --------------------------------------------------------------------
     def _find_prefix(self) -> str:
@@ -135,6 +145,60 @@ class FusedEncoderEngine:
         if kind == "weight":
             return self.arena.span(base + "query.weight", base + "value.weight", flat, (3 * self.H, self.H))
         return self.arena.span(base + "query.bias", base + "value.bias", flat, (3 * self.H,))
+
+    # -- fp8 ------------------------------------------------------------------------------------------
+    _FP8_ACT = ("x", "ctx", "x1", "act")
+    _FP8_W = ("wqkv", "wo", "w1", "w2")
+    _FP8_GRAD = ("d_y2", "d_y1", "d_yo", "d_qkv")
+
+    def enable_fp8(self, margin: float = 1.0) -> None:
+        sites, e5 = [], []
+        for l in range(self.L):
+            for n in self._FP8_ACT + self._FP8_W:
+                sites.append(f"{l}.{n}"); e5.append(False)
+            for n in self._FP8_GRAD:
+                sites.append(f"{l}.{n}"); e5.append(True)
+        self.meta = K.Fp8Meta(sites, e5, self.arena.device, margin=margin)
+        self.fp8 = True
+        self._fp8_calibrated = False
+        self._w8: Dict[str, torch.Tensor] = {}
+        self._w8_version = -1
+
+    def _weight8(self, l: int, which: str, w_bf16: torch.Tensor) -> torch.Tensor:
+        """e4m3 copy of a weight, re-quantised (current scaling) only when the arena's weights changed --
+        once per optimizer step, i.e. amortised over the accumulation steps."""
+        if self._w8_version != self.arena.version:
+            self._w8.clear()
+            self._w8_version = self.arena.version
+        key = f"{l}.{which}"
+        q = self._w8.get(key)
+        if q is None:
+            q = self.meta.quantize(w_bf16.contiguous(), key, calibrate=True)
+            self._w8[key] = q
+        return q
+
+    def _lin(self, l: int, act_site: str, w_site: str, x: torch.Tensor, w: torch.Tensor, **kw):
+        """y = x @ w^T through the bf16 or the fp8 operand path; returns (y, saved operand for wgrad)."""
+        if not self.fp8:
+            return K.gemm(x, w, **kw), x
+        qx = self.meta.quantize(x, f"{l}.{act_site}", calibrate=not self._fp8_calibrated)
+        qw = self._weight8(l, w_site, w)
+        y = K.gemm(qx, qw, scale_a=self.meta.inv_scale(f"{l}.{act_site}"), scale_b=self.meta.inv_scale(f"{l}.{w_site}"), **kw)
+        return y, qx
+
+    def _lin_bwd(self, l: int, g_site: str, act_site: str, w_site: str, dy: torch.Tensor, x_saved: torch.Tensor,
+                 w: torch.Tensor, wgrad: torch.Tensor, **kw) -> torch.Tensor:
+        """dx = dy @ w (with the epilogue in ``kw``) and wgrad += dy^T @ x."""
+        if not self.fp8:
+            dx = K.gemm(dy, w, layout=K.NN, **kw)
+            K.wgrad_accumulate(dy, x_saved, wgrad)
+            return dx
+        m = self.meta
+        qdy = m.quantize(dy, f"{l}.{g_site}", calibrate=not self._fp8_calibrated)
+        sg, sw, sx = m.inv_scale(f"{l}.{g_site}"), m.inv_scale(f"{l}.{w_site}"), m.inv_scale(f"{l}.{act_site}")
+        dx = K.gemm(qdy, self._weight8(l, w_site, w), layout=K.NN, scale_a=sg, scale_b=sw, a_e5m2=True, **kw)
+        K.wgrad_accumulate(qdy, x_saved, wgrad, scale_a=sg, scale_b=sx, a_e5m2=True)
+        return dx
 
     def next_seed(self) -> int:
         self._calls += 1
@@ -168,8 +232,8 @@ class FusedEncoderEngine:
         for l in range(self.L):
             pre = f"encoder.layer.{l}."
             ls = _LayerSaved() if training else None
-            qkv = K.gemm(x, self._qkv(l, A.flat_shadow, "weight"), epi=K.EPI_BIAS,
-                         bias=self._qkv(l, A.flat_shadow, "bias"))
+            qkv, x_op = self._lin(l, "x", "wqkv", x, self._qkv(l, A.flat_shadow, "weight"), epi=K.EPI_BIAS,
+                                  bias=self._qkv(l, A.flat_shadow, "bias"))
             if _use_sdpa():
                 ctx, lse, sd = self._sdpa_fwd(qkv, seqlens, B, S, pa, training)
                 if training:
@@ -178,24 +242,25 @@ class FusedEncoderEngine:
                 ctx, lse = K.attention_fwd(qkv.view(B, S, 3 * H), seqlens, self.heads, p_drop=pa, seed=seed,
                                            stream=_stream(l, SITE_ATTN_PROB))
                 ctx = ctx.view(M, H)
-            pre1 = K.gemm(ctx, self.w(pre + "attention.output.dense.weight"), epi=K.EPI_BIAS_DROP_RES,
-                          bias=self.w(pre + "attention.output.dense.bias"), res=x, p_drop=ph, seed=seed,
-                          stream=_stream(l, SITE_ATTN_OUT))
+            pre1, ctx_op = self._lin(l, "ctx", "wo", ctx, self.w(pre + "attention.output.dense.weight"),
+                                     epi=K.EPI_BIAS_DROP_RES, bias=self.w(pre + "attention.output.dense.bias"), res=x,
+                                     p_drop=ph, seed=seed, stream=_stream(l, SITE_ATTN_OUT))
             x1, mean1, rstd1 = K.layer_norm_fwd(pre1, self.p(pre + "attention.output.LayerNorm.weight"),
                                                 self.p(pre + "attention.output.LayerNorm.bias"), save_stats=training)
             # GELU runs as its own bandwidth kernel: with K = 1024 it does not fit under the GEMM main loop
-            y1 = K.gemm(x1, self.w(pre + "intermediate.dense_act.weight"), epi=K.EPI_BIAS,
-                        bias=self.w(pre + "intermediate.dense_act.bias"))
+            y1, x1_op = self._lin(l, "x1", "w1", x1, self.w(pre + "intermediate.dense_act.weight"), epi=K.EPI_BIAS,
+                                  bias=self.w(pre + "intermediate.dense_act.bias"))
             act = K.gelu_fwd(y1)
-            pre2 = K.gemm(act, self.w(pre + "output.dense.weight"), epi=K.EPI_BIAS_DROP_RES,
-                          bias=self.w(pre + "output.dense.bias"), res=x1, p_drop=ph, seed=seed,
-                          stream=_stream(l, SITE_FFN_OUT))
+            pre2, act_op = self._lin(l, "act", "w2", act, self.w(pre + "output.dense.weight"), epi=K.EPI_BIAS_DROP_RES,
+                                     bias=self.w(pre + "output.dense.bias"), res=x1, p_drop=ph, seed=seed,
+                                     stream=_stream(l, SITE_FFN_OUT))
             x2, mean2, rstd2 = K.layer_norm_fwd(pre2, self.p(pre + "output.LayerNorm.weight"),
                                                 self.p(pre + "output.LayerNorm.bias"), save_stats=training)
             if training:
                 ls.x, ls.qkv, ls.ctx, ls.lse = x, qkv, ctx, lse
                 ls.pre1, ls.mean1, ls.rstd1, ls.x1 = pre1, mean1, rstd1, x1
                 ls.y1, ls.act, ls.pre2, ls.mean2, ls.rstd2 = y1, act, pre2, mean2, rstd2
+                ls.x_op, ls.ctx_op, ls.x1_op, ls.act_op = x_op, ctx_op, x1_op, act_op   # wgrad operands (fp8 or bf16)
                 sv.layers.append(ls)
             x = x2
         return x, sv
@@ -221,12 +286,12 @@ class FusedEncoderEngine:
             if kfac is not None:
                 kfac.tap(self.prefix + pre + "output.dense", ls.act, d_y2)
             # ---- FFN-2
-            d_act = K.gemm(d_y2, self.w(pre + "output.dense.weight"), layout=K.NN)
-            K.wgrad_accumulate(d_y2, ls.act, self.g(pre + "output.dense.weight"))
+            d_act = self._lin_bwd(l, "d_y2", "act", "w2", d_y2, ls.act_op, self.w(pre + "output.dense.weight"),
+                                  self.g(pre + "output.dense.weight"))
             # ---- FFN-1 (GELU' and the bias gradient in one bandwidth pass)
             d_y1 = K.dgelu_bwd(d_act, ls.y1, self.g(pre + "intermediate.dense_act.bias"))
-            d_x1 = K.gemm(d_y1, self.w(pre + "intermediate.dense_act.weight"), layout=K.NN, epi=K.EPI_ADD, res=d_pre2)
-            K.wgrad_accumulate(d_y1, ls.x1, self.g(pre + "intermediate.dense_act.weight"))
+            d_x1 = self._lin_bwd(l, "d_y1", "x1", "w1", d_y1, ls.x1_op, self.w(pre + "intermediate.dense_act.weight"),
+                                 self.g(pre + "intermediate.dense_act.weight"), epi=K.EPI_ADD, res=d_pre2)
             # ---- LN1
             d_pre1, d_yo = K.layer_norm_bwd(
                 d_x1, ls.pre1, ls.mean1, ls.rstd1, self.p(pre + "attention.output.LayerNorm.weight"),
@@ -237,8 +302,8 @@ class FusedEncoderEngine:
             if kfac is not None:
                 kfac.tap(self.prefix + pre + "attention.output.dense", ls.ctx, d_yo)
             # ---- attention output projection
-            d_ctx = K.gemm(d_yo, self.w(pre + "attention.output.dense.weight"), layout=K.NN)
-            K.wgrad_accumulate(d_yo, ls.ctx, self.g(pre + "attention.output.dense.weight"))
+            d_ctx = self._lin_bwd(l, "d_yo", "ctx", "wo", d_yo, ls.ctx_op, self.w(pre + "attention.output.dense.weight"),
+                                  self.g(pre + "attention.output.dense.weight"))
             # ---- attention core
             if ls.sdpa is not None:
                 d_qkv = self._sdpa_bwd(ls.sdpa, d_ctx, sv.B, sv.S)
@@ -251,8 +316,8 @@ class FusedEncoderEngine:
                     kfac.tap(self.prefix + pre + "attention.self." + nm, ls.x, d_qkv[:, j * H:(j + 1) * H])
             # ---- QKV projection
             K.colsum_accumulate(d_qkv, self._qkv(l, A.flat_grad, "bias"))
-            d = K.gemm(d_qkv, self._qkv(l, A.flat_shadow, "weight"), layout=K.NN, epi=K.EPI_ADD, res=d_pre1)
-            K.wgrad_accumulate(d_qkv, ls.x, self._qkv(l, A.flat_grad, "weight"))
+            d = self._lin_bwd(l, "d_qkv", "x", "wqkv", d_qkv, ls.x_op, self._qkv(l, A.flat_shadow, "weight"),
+                              self._qkv(l, A.flat_grad, "weight"), epi=K.EPI_ADD, res=d_pre1)
         # ---- embeddings: output dropout -> LN -> scatter into the three tables
         d_e, _ = K.layer_norm_bwd(
             d, sv.emb_sum, sv.emb_mean, sv.emb_rstd, self.p("embeddings.LayerNorm.weight"),
@@ -261,6 +326,9 @@ class FusedEncoderEngine:
         K.embedding_bwd_scatter(d_e, sv.ids, sv.seg, self.g("embeddings.word_embeddings.weight"),
                                 self.g("embeddings.position_embeddings.weight"),
                                 self.g("embeddings.token_type_embeddings.weight") if self.has_type else None, sv.S)
+        if self.fp8:                       # delayed scaling: next micro-step quantises with this one's amaxes
+            self.meta.update()
+            self._fp8_calibrated = True
 
     # -- library attention (bring-up / bisecting aid: B200_ATTN=sdpa) ---------------------------------
     def _sdpa_fwd(self, qkv, seqlens, B, S, p, training):

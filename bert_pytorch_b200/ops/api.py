@@ -129,14 +129,14 @@ def wgrad_splits(n_out: int, k_out: int, reduce_len: int, block_n: int = 256) ->
     return max(1, min(want, kb // 4 if kb >= 8 else 1, 32))
 
 
-def wgrad_accumulate(dy: torch.Tensor, x: torch.Tensor, grad: torch.Tensor, alpha: float = 1.0) -> None:
-    """grad[N,K] (fp32, arena view) += dy[M,N]^T @ x[M,K]."""
+def wgrad_accumulate(dy: torch.Tensor, x: torch.Tensor, grad: torch.Tensor, alpha: float = 1.0, **fp8) -> None:
+    """grad[N,K] (fp32, arena view) += dy[M,N]^T @ x[M,K]  (``fp8``: scale_a / scale_b / a_e5m2 for 1-byte operands)."""
     n_out, k_out = grad.shape
-    bn = _pick_block_n(n_out, k_out)
+    bn = 512 if fp8 else _pick_block_n(n_out, k_out)
     if bn == 128 and k_out >= 256:
         bn = 256
     gemm(dy, x, layout=TN, epi=EPI_ACCUM_F32, out=grad, block_n=bn, alpha=alpha,
-         k_splits=wgrad_splits(n_out, k_out, dy.size(0), bn))
+         k_splits=wgrad_splits(n_out, k_out, dy.size(0) // (2 if fp8 else 1), bn), **fp8)
 
 
 def layer_norm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, eps: float = 1e-12,

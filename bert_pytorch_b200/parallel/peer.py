@@ -138,6 +138,7 @@ class PeerComm(TorchComm):
             bool(_uniform(optimizer, "grad_averaging")), bool(optimizer.adam_w_mode), bool(optimizer.use_nvlamb),
             self.push_master)
         self._master_stale = not self.push_master
+        A.version += 1
         ops.api._count()
         for g in optimizer.param_groups:       # bf16 path has no overflow; the fp16 path re-reads stats lazily
             g["step"] = step
