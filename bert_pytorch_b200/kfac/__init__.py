@@ -200,13 +200,21 @@ class KFAC:
         comm, rank = self.comm, self.comm.rank
         # ---- factor update: average over micro-batches and ranks, fold into the running average
         if self.steps % g0["factor_update_freq"] == 0:
+            fresh = []
+            for l in self.layers:
+                if l.A_new is None:
+                    continue
+                l.A_new = l.A_new / max(l.n_new, 1)
+                l.G_new = l.G_new / max(l.n_new, 1)
+                fresh += [l.A_new, l.G_new]
+            # all factors of the step travel together: one packed transfer per staging buffer on the peer-memory
+            # backend (ops/csrc/comm.cu: peer_allreduce_kernel), a loop of all-reduces elsewhere
+            comm.all_reduce_many_(fresh, op="avg")
             for l in self.layers:
                 if l.A_new is None:
                     continue
                 for key in ("A", "G"):
-                    new = getattr(l, key + "_new") / max(l.n_new, 1)
-                    comm.all_reduce_(new, op="avg")
-                    cur = getattr(l, key)
+                    new, cur = getattr(l, key + "_new"), getattr(l, key)
                     setattr(l, key, new.clone() if cur is None else cur.mul_(decay).add_(new, alpha=1.0 - decay))
                 l.A_new = l.G_new = None
                 l.n_new = 0

@@ -86,6 +86,8 @@ class _Saved:
     emb_mean: torch.Tensor = None
     emb_rstd: torch.Tensor = None
     layers: List[_LayerSaved] = field(default_factory=list)
+    boundaries: Dict[int, torch.Tensor] = field(default_factory=dict)   # segment inputs under --checkpoint_activations
+    seg_len: int = 0
 
 
 class FusedEncoderEngine:
@@ -229,41 +231,56 @@ class FusedEncoderEngine:
         if training:
             sv.emb_sum, sv.emb_mean, sv.emb_rstd = e, mean, rstd
 
+        ckpt = training and bool(getattr(self.bert.encoder, "_checkpoint_activations", False))
+        seg_len = int(math.ceil(math.sqrt(self.L))) if ckpt else 0
+        if ckpt and _use_sdpa():
+            raise NotImplementedError("B200_ATTN=sdpa (library bring-up path) cannot replay its dropout under --checkpoint_activations")
         for l in range(self.L):
-            pre = f"encoder.layer.{l}."
-            ls = _LayerSaved() if training else None
-            qkv, x_op = self._lin(l, "x", "wqkv", x, self._qkv(l, A.flat_shadow, "weight"), epi=K.EPI_BIAS,
-                                  bias=self._qkv(l, A.flat_shadow, "bias"))
-            if _use_sdpa():
-                ctx, lse, sd = self._sdpa_fwd(qkv, seqlens, B, S, pa, training)
-                if training:
-                    ls.sdpa = sd
-            else:
-                ctx, lse = K.attention_fwd(qkv.view(B, S, 3 * H), seqlens, self.heads, p_drop=pa, seed=seed,
-                                           stream=_stream(l, SITE_ATTN_PROB))
-                ctx = ctx.view(M, H)
-            pre1, ctx_op = self._lin(l, "ctx", "wo", ctx, self.w(pre + "attention.output.dense.weight"),
-                                     epi=K.EPI_BIAS_DROP_RES, bias=self.w(pre + "attention.output.dense.bias"), res=x,
-                                     p_drop=ph, seed=seed, stream=_stream(l, SITE_ATTN_OUT))
-            x1, mean1, rstd1 = K.layer_norm_fwd(pre1, self.p(pre + "attention.output.LayerNorm.weight"),
-                                                self.p(pre + "attention.output.LayerNorm.bias"), save_stats=training)
-            # GELU runs as its own bandwidth kernel: with K = 1024 it does not fit under the GEMM main loop
-            y1, x1_op = self._lin(l, "x1", "w1", x1, self.w(pre + "intermediate.dense_act.weight"), epi=K.EPI_BIAS,
-                                  bias=self.w(pre + "intermediate.dense_act.bias"))
-            act = K.gelu_fwd(y1)
-            pre2, act_op = self._lin(l, "act", "w2", act, self.w(pre + "output.dense.weight"), epi=K.EPI_BIAS_DROP_RES,
-                                     bias=self.w(pre + "output.dense.bias"), res=x1, p_drop=ph, seed=seed,
-                                     stream=_stream(l, SITE_FFN_OUT))
-            x2, mean2, rstd2 = K.layer_norm_fwd(pre2, self.p(pre + "output.LayerNorm.weight"),
-                                                self.p(pre + "output.LayerNorm.bias"), save_stats=training)
-            if training:
-                ls.x, ls.qkv, ls.ctx, ls.lse = x, qkv, ctx, lse
-                ls.pre1, ls.mean1, ls.rstd1, ls.x1 = pre1, mean1, rstd1, x1
-                ls.y1, ls.act, ls.pre2, ls.mean2, ls.rstd2 = y1, act, pre2, mean2, rstd2
-                ls.x_op, ls.ctx_op, ls.x1_op, ls.act_op = x_op, ctx_op, x1_op, act_op   # wgrad operands (fp8 or bf16)
+            if ckpt and l % seg_len == 0:
+                sv.boundaries[l] = x             # --checkpoint_activations: keep segment inputs only (K27)
+            x, ls = self._layer_forward(l, x, seqlens, B, S, ph, pa, seed, save=training and not ckpt)
+            if ls is not None:
                 sv.layers.append(ls)
-            x = x2
+        if ckpt:
+            sv.seg_len = seg_len
         return x, sv
+
+    def _layer_forward(self, l: int, x, seqlens, B: int, S: int, ph: float, pa: float, seed: int, save: bool):
+        """One post-LN transformer layer (reference: src/modeling.py:482-499) as 9 kernel launches."""
+        A, H, M = self.arena, self.H, B * S
+        training = save or pa > 0 or ph > 0
+        pre = f"encoder.layer.{l}."
+        ls = _LayerSaved() if save else None
+        qkv, x_op = self._lin(l, "x", "wqkv", x, self._qkv(l, A.flat_shadow, "weight"), epi=K.EPI_BIAS,
+                              bias=self._qkv(l, A.flat_shadow, "bias"))
+        if _use_sdpa():
+            ctx, lse, sd = self._sdpa_fwd(qkv, seqlens, B, S, pa, training)
+            if save:
+                ls.sdpa = sd
+        else:
+            ctx, lse = K.attention_fwd(qkv.view(B, S, 3 * H), seqlens, self.heads, p_drop=pa, seed=seed,
+                                       stream=_stream(l, SITE_ATTN_PROB))
+            ctx = ctx.view(M, H)
+        pre1, ctx_op = self._lin(l, "ctx", "wo", ctx, self.w(pre + "attention.output.dense.weight"),
+                                 epi=K.EPI_BIAS_DROP_RES, bias=self.w(pre + "attention.output.dense.bias"), res=x,
+                                 p_drop=ph, seed=seed, stream=_stream(l, SITE_ATTN_OUT))
+        x1, mean1, rstd1 = K.layer_norm_fwd(pre1, self.p(pre + "attention.output.LayerNorm.weight"),
+                                            self.p(pre + "attention.output.LayerNorm.bias"), save_stats=save)
+        # GELU runs as its own bandwidth kernel: with K = 1024 it does not fit under the GEMM main loop
+        y1, x1_op = self._lin(l, "x1", "w1", x1, self.w(pre + "intermediate.dense_act.weight"), epi=K.EPI_BIAS,
+                              bias=self.w(pre + "intermediate.dense_act.bias"))
+        act = K.gelu_fwd(y1)
+        pre2, act_op = self._lin(l, "act", "w2", act, self.w(pre + "output.dense.weight"), epi=K.EPI_BIAS_DROP_RES,
+                                 bias=self.w(pre + "output.dense.bias"), res=x1, p_drop=ph, seed=seed,
+                                 stream=_stream(l, SITE_FFN_OUT))
+        x2, mean2, rstd2 = K.layer_norm_fwd(pre2, self.p(pre + "output.LayerNorm.weight"),
+                                            self.p(pre + "output.LayerNorm.bias"), save_stats=save)
+        if save:
+            ls.x, ls.qkv, ls.ctx, ls.lse = x, qkv, ctx, lse
+            ls.pre1, ls.mean1, ls.rstd1, ls.x1 = pre1, mean1, rstd1, x1
+            ls.y1, ls.act, ls.pre2, ls.mean2, ls.rstd2 = y1, act, pre2, mean2, rstd2
+            ls.x_op, ls.ctx_op, ls.x1_op, ls.act_op = x_op, ctx_op, x1_op, act_op   # wgrad operands (fp8 or bf16)
+        return x2, ls
 
     # -- backward -------------------------------------------------------------------------------
     @torch.no_grad()
@@ -274,50 +291,20 @@ class FusedEncoderEngine:
         ph, pa, seed = sv.p_hidden, sv.p_attn, sv.seed
         d = d_out
         kfac = getattr(self.bert, "_kfac", None)      # K-FAC taps: the saved activations double as its statistics
-        for l in reversed(range(self.L)):
-            pre = f"encoder.layer.{l}."
-            ls = sv.layers[l]
-            # ---- LN2 -> (residual grad, dropped grad of the FFN-2 output)
-            d_pre2, d_y2 = K.layer_norm_bwd(
-                d, ls.pre2, ls.mean2, ls.rstd2, self.p(pre + "output.LayerNorm.weight"),
-                dgamma=self.g(pre + "output.LayerNorm.weight"), dbeta=self.g(pre + "output.LayerNorm.bias"),
-                dbias=self.g(pre + "output.dense.bias"), want_dropped=True, p_drop=ph, seed=seed,
-                drop_stream=_stream(l, SITE_FFN_OUT))
-            if kfac is not None:
-                kfac.tap(self.prefix + pre + "output.dense", ls.act, d_y2)
-            # ---- FFN-2
-            d_act = self._lin_bwd(l, "d_y2", "act", "w2", d_y2, ls.act_op, self.w(pre + "output.dense.weight"),
-                                  self.g(pre + "output.dense.weight"))
-            # ---- FFN-1 (GELU' and the bias gradient in one bandwidth pass)
-            d_y1 = K.dgelu_bwd(d_act, ls.y1, self.g(pre + "intermediate.dense_act.bias"))
-            d_x1 = self._lin_bwd(l, "d_y1", "x1", "w1", d_y1, ls.x1_op, self.w(pre + "intermediate.dense_act.weight"),
-                                 self.g(pre + "intermediate.dense_act.weight"), epi=K.EPI_ADD, res=d_pre2)
-            # ---- LN1
-            d_pre1, d_yo = K.layer_norm_bwd(
-                d_x1, ls.pre1, ls.mean1, ls.rstd1, self.p(pre + "attention.output.LayerNorm.weight"),
-                dgamma=self.g(pre + "attention.output.LayerNorm.weight"),
-                dbeta=self.g(pre + "attention.output.LayerNorm.bias"),
-                dbias=self.g(pre + "attention.output.dense.bias"), want_dropped=True, p_drop=ph, seed=seed,
-                drop_stream=_stream(l, SITE_ATTN_OUT))
-            if kfac is not None:
-                kfac.tap(self.prefix + pre + "attention.output.dense", ls.ctx, d_yo)
-            # ---- attention output projection
-            d_ctx = self._lin_bwd(l, "d_yo", "ctx", "wo", d_yo, ls.ctx_op, self.w(pre + "attention.output.dense.weight"),
-                                  self.g(pre + "attention.output.dense.weight"))
-            # ---- attention core
-            if ls.sdpa is not None:
-                d_qkv = self._sdpa_bwd(ls.sdpa, d_ctx, sv.B, sv.S)
-            else:
-                d_qkv = K.attention_bwd(ls.qkv.view(sv.B, sv.S, 3 * H), sv.seqlens, ls.ctx.view(sv.B, sv.S, H),
-                                        d_ctx.view(sv.B, sv.S, H), ls.lse, self.heads, p_drop=pa, seed=seed,
-                                        stream=_stream(l, SITE_ATTN_PROB)).view(M, 3 * H)
-            if kfac is not None:
-                for j, nm in enumerate(("query", "key", "value")):
-                    kfac.tap(self.prefix + pre + "attention.self." + nm, ls.x, d_qkv[:, j * H:(j + 1) * H])
-            # ---- QKV projection
-            K.colsum_accumulate(d_qkv, self._qkv(l, A.flat_grad, "bias"))
-            d = self._lin_bwd(l, "d_qkv", "x", "wqkv", d_qkv, ls.x_op, self._qkv(l, A.flat_shadow, "weight"),
-                              self._qkv(l, A.flat_grad, "weight"), epi=K.EPI_ADD, res=d_pre1)
+        if sv.seg_len:                                    # recompute each segment from its saved input, then walk it back
+            for lo in reversed(range(0, self.L, sv.seg_len)):
+                hi = min(self.L, lo + sv.seg_len)
+                x, saved = sv.boundaries.pop(lo), []
+                for l in range(lo, hi):                   # same seed -> same Philox dropout masks as the first pass
+                    x, ls = self._layer_forward(l, x, sv.seqlens, sv.B, sv.S, ph, pa, seed, save=True)
+                    saved.append(ls)
+                for l in reversed(range(lo, hi)):
+                    d = self._layer_backward(l, saved[l - lo], d, sv, kfac)
+                del saved
+        else:
+            for l in reversed(range(self.L)):
+                d = self._layer_backward(l, sv.layers[l], d, sv, kfac)
+                sv.layers[l] = None                       # activations of finished layers go back to the allocator
         # ---- embeddings: output dropout -> LN -> scatter into the three tables
         d_e, _ = K.layer_norm_bwd(
             d, sv.emb_sum, sv.emb_mean, sv.emb_rstd, self.p("embeddings.LayerNorm.weight"),
@@ -329,6 +316,53 @@ class FusedEncoderEngine:
         if self.fp8:                       # delayed scaling: next micro-step quantises with this one's amaxes
             self.meta.update()
             self._fp8_calibrated = True
+
+    def _layer_backward(self, l: int, ls: _LayerSaved, d: torch.Tensor, sv: _Saved, kfac) -> torch.Tensor:
+        A, H, M = self.arena, self.H, sv.B * sv.S
+        ph, pa, seed = sv.p_hidden, sv.p_attn, sv.seed
+        pre = f"encoder.layer.{l}."
+        # ---- LN2 -> (residual grad, dropped grad of the FFN-2 output)
+        d_pre2, d_y2 = K.layer_norm_bwd(
+            d, ls.pre2, ls.mean2, ls.rstd2, self.p(pre + "output.LayerNorm.weight"),
+            dgamma=self.g(pre + "output.LayerNorm.weight"), dbeta=self.g(pre + "output.LayerNorm.bias"),
+            dbias=self.g(pre + "output.dense.bias"), want_dropped=True, p_drop=ph, seed=seed,
+            drop_stream=_stream(l, SITE_FFN_OUT))
+        if kfac is not None:
+            kfac.tap(self.prefix + pre + "output.dense", ls.act, d_y2)
+        # ---- FFN-2
+        d_act = self._lin_bwd(l, "d_y2", "act", "w2", d_y2, ls.act_op, self.w(pre + "output.dense.weight"),
+                              self.g(pre + "output.dense.weight"))
+        # ---- FFN-1 (GELU' and the bias gradient in one bandwidth pass)
+        d_y1 = K.dgelu_bwd(d_act, ls.y1, self.g(pre + "intermediate.dense_act.bias"))
+        d_x1 = self._lin_bwd(l, "d_y1", "x1", "w1", d_y1, ls.x1_op, self.w(pre + "intermediate.dense_act.weight"),
+                             self.g(pre + "intermediate.dense_act.weight"), epi=K.EPI_ADD, res=d_pre2)
+        # ---- LN1
+        d_pre1, d_yo = K.layer_norm_bwd(
+            d_x1, ls.pre1, ls.mean1, ls.rstd1, self.p(pre + "attention.output.LayerNorm.weight"),
+            dgamma=self.g(pre + "attention.output.LayerNorm.weight"),
+            dbeta=self.g(pre + "attention.output.LayerNorm.bias"),
+            dbias=self.g(pre + "attention.output.dense.bias"), want_dropped=True, p_drop=ph, seed=seed,
+            drop_stream=_stream(l, SITE_ATTN_OUT))
+        if kfac is not None:
+            kfac.tap(self.prefix + pre + "attention.output.dense", ls.ctx, d_yo)
+        # ---- attention output projection
+        d_ctx = self._lin_bwd(l, "d_yo", "ctx", "wo", d_yo, ls.ctx_op, self.w(pre + "attention.output.dense.weight"),
+                              self.g(pre + "attention.output.dense.weight"))
+        # ---- attention core
+        if ls.sdpa is not None:
+            d_qkv = self._sdpa_bwd(ls.sdpa, d_ctx, sv.B, sv.S)
+        else:
+            d_qkv = K.attention_bwd(ls.qkv.view(sv.B, sv.S, 3 * H), sv.seqlens, ls.ctx.view(sv.B, sv.S, H),
+                                    d_ctx.view(sv.B, sv.S, H), ls.lse, self.heads, p_drop=pa, seed=seed,
+                                    stream=_stream(l, SITE_ATTN_PROB)).view(M, 3 * H)
+        if kfac is not None:
+            for j, nm in enumerate(("query", "key", "value")):
+                kfac.tap(self.prefix + pre + "attention.self." + nm, ls.x, d_qkv[:, j * H:(j + 1) * H])
+        # ---- QKV projection
+        K.colsum_accumulate(d_qkv, self._qkv(l, A.flat_grad, "bias"))
+        d = self._lin_bwd(l, "d_qkv", "x", "wqkv", d_qkv, ls.x_op, self._qkv(l, A.flat_shadow, "weight"),
+                          self._qkv(l, A.flat_grad, "weight"), epi=K.EPI_ADD, res=d_pre1)
+        return d
 
     # -- library attention (bring-up / bisecting aid: B200_ATTN=sdpa) ---------------------------------
     def _sdpa_fwd(self, qkv, seqlens, B, S, p, training):

@@ -320,6 +320,23 @@ void fused_allreduce_lamb(int64_t rank, int64_t world, bool use_multicast, std::
   b200::fused_allreduce_lamb(L, cur_stream());
 }
 
+void peer_allreduce(int64_t rank, int64_t world, bool use_multicast, std::vector<int64_t> buf_ptrs,
+                    std::vector<int64_t> flag_ptrs, int64_t buf_mc, Tensor grid_bar, int64_t epoch, int64_t n, double scale) {
+  TORCH_CHECK((int64_t)buf_ptrs.size() == world && (int64_t)flag_ptrs.size() == world && world <= 16, "peer pointer lists");
+  TORCH_CHECK(n % 4 == 0 && n > 0, "peer_allreduce: element count must be a positive multiple of 4");
+  c10::cuda::CUDAGuard guard(grid_bar.device());
+  b200::PeerAllreduceLaunch L;
+  L.rank = (int)rank; L.world = (int)world; L.use_multicast = use_multicast ? 1 : 0;
+  for (int p = 0; p < world; ++p) {
+    L.buf_ptrs[p] = reinterpret_cast<const void*>(buf_ptrs[p]);
+    L.flag_ptrs[p] = reinterpret_cast<const void*>(flag_ptrs[p]);
+  }
+  L.buf_mc = reinterpret_cast<void*>(buf_mc);
+  L.grid_bar = reinterpret_cast<unsigned int*>(grid_bar.data_ptr<int>());
+  L.epoch = (unsigned int)epoch; L.n = n; L.scale = (float)scale;
+  b200::peer_allreduce(L, cur_stream());
+}
+
 void fp8_quantize(Tensor x, Tensor q, Tensor meta, bool e5m2) {
   check_bf16(x, "x");
   TORCH_CHECK(x.is_contiguous() && q.is_contiguous() && q.is_cuda() && q.element_size() == 1 && q.numel() == x.numel(),
@@ -349,6 +366,7 @@ void fp8_update(Tensor meta, Tensor is_e5m2, double margin_pow2) {
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "bert_pytorch_b200 sm_100a kernels";
   m.def("gemm", &gemm);
+  m.def("peer_allreduce", &peer_allreduce);
   m.def("fp8_quantize", &fp8_quantize);
   m.def("fp8_amax", &fp8_amax);
   m.def("fp8_update", &fp8_update);

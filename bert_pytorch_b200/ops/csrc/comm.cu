@@ -348,4 +348,78 @@ void fused_allreduce_lamb(const FusedLambLaunch& L, cudaStream_t st) {
   B200_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)fused_allreduce_lamb_kernel, dim3(sms), dim3(FUSED_THREADS), args, 0, st));
 }
 
+// ------------------------------------------------------------------------------------------------
+// General fp32 all-reduce over a symmetric staging buffer (K-FAC factor statistics; any other
+// small reduction that would otherwise be an ncclAllReduce).  Two-shot inside ONE kernel:
+//   barrier -> rank r reduces slice r of every peer's buffer (P2P loads or one multimem.ld_reduce), scales,
+//   and writes the result into every peer's buffer (P2P stores or multimem.st) -> barrier.
+// In place: slice r is read only by rank r, and rank r overwrites it after reading.
+// ------------------------------------------------------------------------------------------------
+struct PeerAllreduceArgs {
+  int rank, world, use_multicast;
+  float* buf[MAX_WORLD];
+  float* buf_mc;
+  unsigned int* flags[MAX_WORLD];
+  unsigned int* grid_bar;
+  unsigned int epoch;
+  long long n;          // multiple of 4
+  float scale;
+};
+
+__global__ void __launch_bounds__(FUSED_THREADS, 1) peer_allreduce_kernel(const PeerAllreduceArgs a) {
+  unsigned int gen = 0;
+  FusedLambArgs b;                       // the barrier helpers only read rank / world / flags / epoch
+  b.rank = a.rank; b.world = a.world; b.epoch = a.epoch;
+  for (int p = 0; p < a.world; ++p) b.flags[p] = a.flags[p];
+  peer_barrier(b, 0);
+  grid_sync(a.grid_bar, gen);
+  const long long n4 = a.n >> 2;
+  const long long per = (n4 + a.world - 1) / a.world;
+  const long long lo = per * a.rank, hi = min(n4, lo + per);
+  const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long gstride = (long long)gridDim.x * blockDim.x;
+  for (long long i = lo + gtid; i < hi; i += gstride) {
+    float4 acc;
+    if (a.use_multicast) {
+      asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(acc.x), "=f"(acc.y), "=f"(acc.z), "=f"(acc.w) : "l"(a.buf_mc + 4 * i) : "memory");
+    } else {
+      acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+      for (int p = 0; p < a.world; ++p) {
+        float4 g;
+        asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(g.x), "=f"(g.y), "=f"(g.z), "=f"(g.w) : "l"(a.buf[p] + 4 * i) : "memory");
+        acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+      }
+    }
+    acc.x *= a.scale; acc.y *= a.scale; acc.z *= a.scale; acc.w *= a.scale;
+    if (a.use_multicast) {
+      asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.buf_mc + 4 * i), "f"(acc.x),
+                   "f"(acc.y), "f"(acc.z), "f"(acc.w) : "memory");
+    } else {
+#pragma unroll 1
+      for (int p = 0; p < a.world; ++p) *reinterpret_cast<float4*>(a.buf[p] + 4 * i) = acc;
+    }
+  }
+  grid_sync(a.grid_bar, gen);
+  peer_barrier(b, 1);
+}
+
+void peer_allreduce(const PeerAllreduceLaunch& L, cudaStream_t st) {
+  PeerAllreduceArgs a;
+  a.rank = L.rank; a.world = L.world; a.use_multicast = L.use_multicast;
+  if (L.world > MAX_WORLD) { fprintf(stderr, "[b200] peer all-reduce supports <= %d ranks\n", MAX_WORLD); abort(); }
+  for (int p = 0; p < L.world; ++p) { a.buf[p] = (float*)L.buf_ptrs[p]; a.flags[p] = (unsigned int*)L.flag_ptrs[p]; }
+  a.buf_mc = (float*)L.buf_mc; a.grid_bar = L.grid_bar; a.epoch = L.epoch; a.n = L.n; a.scale = L.scale;
+  B200_CUDA_CHECK(cudaMemsetAsync(L.grid_bar, 0, sizeof(unsigned int), st));
+  int dev, sms;
+  B200_CUDA_CHECK(cudaGetDevice(&dev));
+  B200_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const long long work = (L.n / 4 + L.world - 1) / L.world;
+  int grid = (int)std::min<long long>(sms, std::max<long long>(1, (work + FUSED_THREADS - 1) / FUSED_THREADS));
+  void* args[] = {(void*)&a};
+  B200_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)peer_allreduce_kernel, dim3(grid), dim3(FUSED_THREADS), args, 0, st));
+}
+
 }  // namespace b200

@@ -71,6 +71,18 @@ struct FusedLambLaunch {
 };
 void fused_allreduce_lamb(const FusedLambLaunch& L, cudaStream_t st);
 
+// in-place fp32 all-reduce (sum * scale) of a symmetric staging buffer, one kernel, P2P or NVLS multicast
+struct PeerAllreduceLaunch {
+  int rank, world, use_multicast;
+  const void* buf_ptrs[16]; const void* flag_ptrs[16];
+  void* buf_mc;
+  unsigned int* grid_bar;
+  unsigned int epoch;
+  long long n;
+  float scale;
+};
+void peer_allreduce(const PeerAllreduceLaunch& L, cudaStream_t st);
+
 // fp8.cu: per-tensor scaled fp8 operand preparation; meta records are {amax, scale, inv_scale, _}
 void fp8_quantize(const void* x_bf16, void* q, long long n, float* meta, bool e5m2, cudaStream_t st);
 void fp8_amax(const void* x_bf16, long long n, float* meta, cudaStream_t st);

@@ -30,6 +30,11 @@ class Comm:
     def all_reduce_(self, t: torch.Tensor, op: str = "sum") -> torch.Tensor:
         return t
 
+    def all_reduce_many_(self, tensors, op: str = "sum") -> None:
+        """In-place all-reduce of a list of tensors (backends may pack them into one transfer)."""
+        for t in tensors:
+            self.all_reduce_(t, op=op)
+
     def reduce_scatter(self, full: torch.Tensor, out: torch.Tensor, lo: int, hi: int) -> torch.Tensor:
         """out[:hi-lo] = sum over ranks of full[lo:hi] (each rank passes its own bounds)."""
         out[: hi - lo].copy_(full[lo:hi])

@@ -144,6 +144,78 @@ class PeerComm(TorchComm):
             g["step"] = step
         self.last_stats = self.stats
 
+    # -- general all-reduce through our own kernel (K-FAC factors etc.) -------------------------------------
+    STAGE_FLOATS = 64 << 20          # 256 MB symmetric staging buffer, allocated on first use
+
+    def _stage(self):
+        if getattr(self, "_stage_t", None) is None:
+            self._stage_t, self._stage_h = self._symm(self.STAGE_FLOATS, torch.float32)
+            self._ar_flag_t, self._ar_flag_h = self._symm(2 * self.world_size + 64, torch.int32)
+            self._ar_bar = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self._ar_epoch = 0
+            mc = int(getattr(self._stage_h, "multicast_ptr", 0) or 0)
+            self._ar_mc = mc if (self._want_mc is None or self._want_mc) else 0
+            dist.barrier(group=self.group)
+        return self._stage_t
+
+    def _stage_allreduce(self, n: int, scale: float) -> None:
+        from .. import ops
+        n4 = (n + 3) // 4 * 4
+        self._ar_epoch += 1
+        ops.extension().peer_allreduce(self.rank, self.world_size, self._ar_mc != 0, list(self._stage_h.buffer_ptrs),
+                                       list(self._ar_flag_h.buffer_ptrs), self._ar_mc, self._ar_bar, self._ar_epoch,
+                                       n4, scale)
+        ops.api._count()
+
+    @torch.no_grad()
+    def all_reduce_many_(self, tensors, op: str = "sum") -> None:
+        """fp32 CUDA tensors are packed into the symmetric staging buffer and reduced by ONE peer-memory kernel
+        per 256 MB (no NCCL); anything else falls back to the torch.distributed path."""
+        mine = [t for t in tensors if t.is_cuda and t.dtype == torch.float32 and op in ("sum", "avg")]
+        for t in tensors:
+            if not any(t is m for m in mine):
+                super().all_reduce_(t, op=op)
+        if not mine:
+            return
+        stage = self._stage()
+        scale = 1.0 / self.world_size if op == "avg" else 1.0
+        cap = stage.numel()
+        pieces = []                                   # (flat view of the source, offset in it, length)
+        for t in mine:
+            flat = t.reshape(-1) if t.is_contiguous() else None
+            src = flat if flat is not None else t.contiguous().reshape(-1)
+            off = 0
+            while off < src.numel():
+                ln = min(src.numel() - off, cap)
+                pieces.append((t, src, off, ln, flat is None))
+                off += ln
+        i = 0
+        while i < len(pieces):
+            used, batch = 0, []
+            while i < len(pieces) and used + (pieces[i][3] + 3) // 4 * 4 <= cap:
+                batch.append((pieces[i], used))
+                used += (pieces[i][3] + 3) // 4 * 4
+                i += 1
+            if used < cap:
+                stage[used:min(cap, used + 4)].zero_()
+            for (t, src, off, ln, _), pos in batch:
+                stage[pos:pos + ln].copy_(src[off:off + ln])
+                if ln % 4:
+                    stage[pos + ln:pos + (ln + 3) // 4 * 4].zero_()
+            self._stage_allreduce(used, scale)
+            for (t, src, off, ln, copied), pos in batch:
+                src[off:off + ln].copy_(stage[pos:pos + ln])
+        for t, src, off, ln, copied in pieces:
+            if copied and off + ln == src.numel():
+                t.copy_(src.view_as(t))
+
+    @torch.no_grad()
+    def all_reduce_(self, t, op="sum", async_op: bool = False):
+        if async_op or not (t.is_cuda and t.dtype == torch.float32 and op in ("sum", "avg")) or t.numel() < 1024:
+            return super().all_reduce_(t, op=op, async_op=async_op)
+        self.all_reduce_many_([t], op=op)
+        return t
+
     @torch.no_grad()
     def gather_master(self) -> None:
         """Make every rank's fp32 parameter arena complete again (only needed with ``push_master=False``):

@@ -92,7 +92,7 @@ def test_fp8_engine_tracks_bf16_engine():
     """The fused kernel program with fp8 GEMM operands vs the same program in bf16: same loss within fp8 noise,
     weight gradients within the expected quantisation error; second micro-step runs on delayed scales."""
     import copy
-    from tests.test_gpu_kernels import _tiny_model, _batch
+    from test_gpu_kernels import _tiny_model, _batch
     from bert_pytorch_b200.models.arena import ParamArena
     model = _tiny_model(hidden=256, layers=2, heads=4, inter=1024).cuda()
     model8 = copy.deepcopy(model)

@@ -98,7 +98,34 @@ def main():
             assert torch.equal(ref, a_f.flat_param), "ranks disagree after the fused step"
         out[f"max_abs_diff_mc{int(mc)}"] = worst
         out[f"grad_norm_mc{int(mc)}"] = float(comm.stats[2].sqrt())
-        del comm, m_f, a_f, o_f
+        # general all-reduce through our own kernel (K-FAC factor path): odd sizes, packing, avg
+        torch.manual_seed(77 + rank)
+        ts = [torch.randn(1025, 1025, device=dev), torch.randn(7, device=dev), torch.randn(300, 64, device=dev).t()]
+        refs = [t.clone() for t in ts]
+        comm.all_reduce_many_(ts, op="avg")
+        for r in refs:
+            dist.all_reduce(r, op=dist.ReduceOp.AVG)
+        torch.cuda.synchronize()
+        out[f"allreduce_many_err_mc{int(mc)}"] = max(float((t - r).abs().max()) for t, r in zip(ts, refs))
+        big_t = torch.randn(64 << 20, device=dev)
+        def run_ar():
+            comm.all_reduce_many_([big_t], op="sum")
+        def run_nccl():
+            dist.all_reduce(big_t)
+        for name, fn in (("peer", run_ar), ("nccl", run_nccl)):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize(); dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                fn()
+            e1.record(); torch.cuda.synchronize()
+            tt = torch.tensor([e0.elapsed_time(e1) / 5], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            out[f"allreduce_256MB_{name}_ms_mc{int(mc)}"] = round(float(tt), 3)
+            big_t.normal_()
+        del comm, m_f, a_f, o_f, big_t
     if "--big" in sys.argv:
         big = BertConfig(vocab_size_or_config_json_file=30528, hidden_size=1024, num_hidden_layers=24,
                          num_attention_heads=16, intermediate_size=4096, max_position_embeddings=512)
