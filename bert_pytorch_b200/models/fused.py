@@ -163,21 +163,33 @@ class FusedEncoderEngine:
         self.meta = K.Fp8Meta(sites, e5, self.arena.device, margin=margin)
         self.fp8 = True
         self._fp8_calibrated = False
-        self._w8: Dict[str, torch.Tensor] = {}
-        self._w8_version = -1
+        self._w8: Dict[str, tuple] = {}
 
     def _weight8(self, l: int, which: str, w_bf16: torch.Tensor) -> torch.Tensor:
         """e4m3 copy of a weight, re-quantised (current scaling) only when the arena's weights changed --
         once per optimizer step, i.e. amortised over the accumulation steps."""
-        if self._w8_version != self.arena.version:
-            self._w8.clear()
-            self._w8_version = self.arena.version
         key = f"{l}.{which}"
-        q = self._w8.get(key)
-        if q is None:
-            q = self.meta.quantize(w_bf16.contiguous(), key, calibrate=True)
-            self._w8[key] = q
-        return q
+        ent = self._w8.get(key)
+        if ent is None or ent[1] != self.arena.version:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("fp8 weight copies are stale inside a CUDA-graph capture: call prepare_step() first")
+            q = self.meta.quantize(w_bf16.contiguous(), key, out=ent[0] if ent is not None else None, calibrate=True)
+            ent = (q, self.arena.version)          # same storage every time: captured graphs keep reading it
+            self._w8[key] = ent
+        return ent[0]
+
+    def prepare_step(self) -> None:
+        """Host-side work that must not happen inside a captured graph: refresh the fp8 weight copies when the
+        optimizer has changed the weights (once per optimizer step)."""
+        if not self.fp8:
+            return
+        A = self.arena
+        for l in range(self.L):
+            pre = f"encoder.layer.{l}."
+            self._weight8(l, "wqkv", self._qkv(l, A.flat_shadow, "weight"))
+            self._weight8(l, "wo", self.w(pre + "attention.output.dense.weight"))
+            self._weight8(l, "w1", self.w(pre + "intermediate.dense_act.weight"))
+            self._weight8(l, "w2", self.w(pre + "output.dense.weight"))
 
     def _lin(self, l: int, act_site: str, w_site: str, x: torch.Tensor, w: torch.Tensor, **kw):
         """y = x @ w^T through the bf16 or the fp8 operand path; returns (y, saved operand for wgrad)."""
@@ -208,12 +220,15 @@ class FusedEncoderEngine:
 
     # -- forward --------------------------------------------------------------------------------
     @torch.no_grad()
-    def forward(self, input_ids, token_type_ids, attention_mask, training: bool, seed: Optional[int] = None):
-        """Returns (sequence_output [B*S, H] bf16, saved-or-None)."""
+    def forward(self, input_ids, token_type_ids, attention_mask, training: bool, seed: Optional[int] = None,
+                dropout: Optional[bool] = None):
+        """Returns (sequence_output [B*S, H] bf16, saved-or-None).  ``training`` saves activations for
+        ``backward``; ``dropout`` (default: same as ``training``) applies the dropout sites."""
         B, S = input_ids.shape
         M, H, A = B * S, self.H, self.arena
-        ph = self.p_hidden if training else 0.0
-        pa = self.p_attn if training else 0.0
+        dropout = training if dropout is None else dropout
+        ph = self.p_hidden if dropout else 0.0
+        pa = self.p_attn if dropout else 0.0
         seed = self.next_seed() if seed is None else seed
         ids = input_ids.reshape(-1).to(torch.int32).contiguous()
         seg = None
@@ -431,6 +446,12 @@ class FusedPretrainer:
         self.has_nsp = model.cls.has_nsp and model.bert.pooler is not None
         self.max_pred = int(getattr(cfg, "max_predictions_per_seq", 0)) or None
         self._loss = None
+        # CUDA graphs: the micro-step is ~600 launches of static shape; replaying it as one graph removes the
+        # launch gaps (~6 % of the phase-1 step).  B200_GRAPH=0 keeps the eager program.
+        self.use_graphs = os.environ.get("B200_GRAPH", "1") != "0"
+        self.graph_warmup = 2                 # eager calls per input signature before capturing
+        self._graphs: Dict[tuple, dict] = {}
+        self._seed_step: Optional[torch.Tensor] = None
 
     def _max_pred(self, labels: torch.Tensor) -> int:
         # capacity of masked positions per sequence; fixed per run so shapes stay static
@@ -439,16 +460,63 @@ class FusedPretrainer:
             self.max_pred = (self.max_pred + 7) // 8 * 8
         return self.max_pred
 
+    def _graph_ok(self) -> bool:
+        if not self.use_graphs or _use_sdpa() or getattr(self.model.bert, "_kfac", None) is not None:
+            return False                      # K-FAC taps keep Python-side state; the library attention path owns its RNG
+        return self.arena.device.type == "cuda"
+
     @torch.no_grad()
     def forward_backward(self, input_ids, segment_ids, input_mask, masked_lm_labels, next_sentence_labels,
                          grad_scale: float = 1.0) -> torch.Tensor:
+        """One micro-step.  After ``graph_warmup`` eager calls with the same input signature the whole kernel
+        program (forward, loss, backward: ~600 launches) is captured once and replayed as ONE CUDA graph; the
+        dropout seed advances through a device-side step counter inside the graph."""
+        if not self._graph_ok():
+            return self._program(input_ids, segment_ids, input_mask, masked_lm_labels, next_sentence_labels, grad_scale)
+        args = (input_ids, segment_ids, input_mask, masked_lm_labels, next_sentence_labels)
+        key = (tuple(input_ids.shape), self.model.training, next_sentence_labels is not None,
+               segment_ids is not None, tuple(str(t.dtype) for t in args if t is not None),
+               bool(getattr(self.model.bert.encoder, "_checkpoint_activations", False)), self.engine.fp8)
+        ent = self._graphs.setdefault(key, {"calls": 0})
+        ent["calls"] += 1
+        eng = self.engine
+        if "graph" in ent and ent["grad_scale"] != float(grad_scale):
+            # the loss scale is a launch constant: a GradScaler update invalidates the capture (rare); drop it
+            # (and its private memory pool) and capture again right away
+            for k in ("graph", "static", "loss"):
+                ent.pop(k)
+        if "graph" not in ent:
+            if ent["calls"] <= self.graph_warmup or (eng.fp8 and not eng._fp8_calibrated):
+                return self._program(*args, grad_scale)
+            if self._seed_step is None:
+                self._seed_step = torch.zeros(1, dtype=torch.int64, device=self.arena.device)
+                ops.extension().set_seed_step(self._seed_step)
+            self._max_pred(masked_lm_labels.to(torch.int32))
+            static = [None if t is None else t.clone() for t in args]
+            eng.prepare_step()
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            n0 = K.KERNEL_LAUNCHES
+            with torch.cuda.graph(graph):
+                self._seed_step.add_(1)
+                loss = self._program(*static, grad_scale, seed=eng._seed_base)
+            ent.update(graph=graph, static=static, loss=loss, launches=K.KERNEL_LAUNCHES - n0, grad_scale=float(grad_scale))
+            K.KERNEL_LAUNCHES = n0            # the capture itself ran nothing
+        for dst, src in zip(ent["static"], args):
+            if dst is not None:
+                dst.copy_(src, non_blocking=True)
+        eng.prepare_step()
+        ent["graph"].replay()
+        K._count(ent["launches"])
+        return ent["loss"]
+
+    @torch.no_grad()
+    def _program(self, input_ids, segment_ids, input_mask, masked_lm_labels, next_sentence_labels,
+                 grad_scale: float = 1.0, seed: Optional[int] = None) -> torch.Tensor:
         eng, A, H, V = self.engine, self.arena, self.H, self.V
         B, S = input_ids.shape
         M = B * S
-        training = self.model.training
-        seq, sv = eng.forward(input_ids, segment_ids, input_mask, training=True)
-        if not training:          # eval(): same path but dropout disabled upstream via p=0
-            pass
+        seq, sv = eng.forward(input_ids, segment_ids, input_mask, training=True, seed=seed, dropout=self.model.training)
         labels = masked_lm_labels.to(torch.int32).contiguous()
         mp = self._max_pred(labels)
         idx, tgt, count = K.mlm_compact(labels, mp)
@@ -478,18 +546,27 @@ class FusedPretrainer:
         d_seq = torch.zeros(M, H, dtype=torch.bfloat16, device=seq.device)
         K.scatter_rows(d_rows, idx, d_seq)
 
-        # ---- NSP head: [B,H] sized, plain torch (library GEMMs on 96 rows) with autograd into the arena grads
+        # ---- NSP head: [B,H] sized; plain torch ops with the backward written out (no autograd: the whole
+        #      micro-step stays capturable), gradients accumulated straight into the arena views
         if self.has_nsp and next_sentence_labels is not None:
             pool, nsp = self.model.bert.pooler.dense_act, self.model.cls.seq_relationship
-            with torch.enable_grad():
-                cls_tok = seq.view(B, S, H)[:, 0].float().requires_grad_(True)
-                pooled = torch.tanh(F.linear(cls_tok, pool.weight, pool.bias))
-                nsp_loss = F.cross_entropy(F.linear(pooled, nsp.weight, nsp.bias), next_sentence_labels.long().view(-1),
-                                           ignore_index=-1)
-                torch.autograd.backward(nsp_loss * grad_scale,
-                                        inputs=[cls_tok, pool.weight, pool.bias, nsp.weight, nsp.bias])
-            d_seq.view(B, S, H)[:, 0] += cls_tok.grad.to(torch.bfloat16)
-            loss = loss + nsp_loss.detach()
+            cls_tok = seq.view(B, S, H)[:, 0].float()
+            pooled = torch.tanh(torch.addmm(pool.bias, cls_tok, pool.weight.t()))
+            nsp_logits = torch.addmm(nsp.bias, pooled, nsp.weight.t())
+            tgt_n = next_sentence_labels.long().view(-1)
+            valid = (tgt_n >= 0).float()
+            n_valid = valid.sum().clamp_(min=1.0)
+            logp = torch.log_softmax(nsp_logits, dim=-1)
+            onehot = F.one_hot(tgt_n.clamp(min=0), nsp_logits.size(-1)).float()
+            nsp_loss = -((logp * onehot).sum(-1) * valid).sum() / n_valid
+            d_logits = (logp.exp() - onehot) * (valid / n_valid * grad_scale).unsqueeze(1)
+            nsp.weight.grad.addmm_(d_logits.t(), pooled)
+            nsp.bias.grad.add_(d_logits.sum(0))
+            d_z = (d_logits @ nsp.weight) * (1.0 - pooled * pooled)
+            pool.weight.grad.addmm_(d_z.t(), cls_tok)
+            pool.bias.grad.add_(d_z.sum(0))
+            d_seq.view(B, S, H)[:, 0] += (d_z @ pool.weight).to(torch.bfloat16)
+            loss = loss + nsp_loss
 
         eng.backward(sv, d_seq)
         return loss.squeeze(0) if loss.dim() else loss

@@ -23,6 +23,9 @@ _PAIR_ENABLED = os.environ.get("B200_GEMM_PAIR", "1") != "0"
 KERNEL_LAUNCHES = 0     # every wrapper bumps this: bench.py reports it as ``gpu_launches``
 
 
+STREAM_K = os.environ.get("B200_STREAM_K", "1") != "0"
+
+
 def _count(n: int = 1) -> None:
     global KERNEL_LAUNCHES
     KERNEL_LAUNCHES += n
@@ -135,8 +138,14 @@ def wgrad_accumulate(dy: torch.Tensor, x: torch.Tensor, grad: torch.Tensor, alph
     bn = 512 if fp8 else _pick_block_n(n_out, k_out)
     if bn == 128 and k_out >= 256:
         bn = 256
-    gemm(dy, x, layout=TN, epi=EPI_ACCUM_F32, out=grad, block_n=bn, alpha=alpha,
-         k_splits=wgrad_splits(n_out, k_out, dy.size(0) // (2 if fp8 else 1), bn), **fp8)
+    splits = wgrad_splits(n_out, k_out, dy.size(0) // (2 if fp8 else 1), bn)
+    if bn == 512 and STREAM_K:
+        # stream-K: equal (tile, k-block) ranges per CTA pair instead of whole tiles (csrc/gemm_sm100.cu: seg_get)
+        tiles = ((n_out + 255) // 256) * ((k_out + 255) // 256)
+        kb = (dy.size(0) + (127 if fp8 else 63)) // (128 if fp8 else 64)
+        if tiles % (NUM_SMS // 2) != 0 and tiles * kb >= 8 * (NUM_SMS // 2):
+            splits = -1
+    gemm(dy, x, layout=TN, epi=EPI_ACCUM_F32, out=grad, block_n=bn, alpha=alpha, k_splits=splits, **fp8)
 
 
 def layer_norm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, eps: float = 1e-12,

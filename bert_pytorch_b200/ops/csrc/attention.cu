@@ -41,7 +41,7 @@ struct AttnArgs {
   __nv_bfloat16* ctx;      // fwd out [B*S, H]
   float* lse;              // [B, h, S] natural-log LSE of the scaled scores
   float scale;
-  unsigned long long seed;
+  Seed seed;
   unsigned int stream;
   unsigned int thresh16;
   float inv_keep;
@@ -104,6 +104,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs p) 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  const unsigned long long seed = p.thresh16 != 0 ? p.seed.value() : 0ull;
   const uint32_t tS = tmem, tO = KV_STAGES == 1 ? tmem : tmem + 128;
 
   if (warp == 8) {
@@ -208,7 +209,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs p) 
             pr[t] = e;
           }
           if (p.thresh16 != 0) {
-            const uint32_t keep = dropout_keep8(p.seed, p.stream, (erow + (uint64_t)(k0 + g * 8)) >> 3, p.thresh16);
+            const uint32_t keep = dropout_keep8(seed, p.stream, (erow + (uint64_t)(k0 + g * 8)) >> 3, p.thresh16);
 #pragma unroll
             for (int t = 0; t < 8; ++t) pr[t] = ((keep >> t) & 1u) ? pr[t] * p.inv_keep : 0.f;
           }
@@ -350,6 +351,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  const unsigned long long seed = p.thresh16 != 0 ? p.seed.value() : 0ull;
   const uint32_t tS = tmem, tDP = tmem + 128, tDV = tmem + 256, tDK = tmem + 320, tDQ = tmem + 384;
 
   if (warp == 8) {
@@ -435,7 +437,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         for (int g = 0; g < 4; ++g) {
           uint32_t keep = 0xFFu;
           if (p.thresh16 != 0)
-            keep = dropout_keep8(p.seed, p.stream, (erow + (uint64_t)(k0 + g * 8)) >> 3, p.thresh16);
+            keep = dropout_keep8(seed, p.stream, (erow + (uint64_t)(k0 + g * 8)) >> 3, p.thresh16);
           float pd[8], ds[8];
 #pragma unroll
           for (int t = 0; t < 8; ++t) {
@@ -539,7 +541,7 @@ attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict_
 // launchers
 // ------------------------------------------------------------------------------------------------
 static void fill_args(AttnArgs& a, int B, int S, int h, int d, const int* seqlens, float scale,
-                      unsigned long long seed, unsigned int stream, float p_drop) {
+                      Seed seed, unsigned int stream, float p_drop) {
   if (d != HD) { fprintf(stderr, "[b200] attention kernels need head_dim 64 (got %d)\n", d); abort(); }
   if (S > 512 || S % 8 != 0) { fprintf(stderr, "[b200] attention kernels need S <= 512 and S %% 8 == 0 (got %d)\n", S); abort(); }
   a.B = B; a.S = S; a.h = h; a.H = h * d; a.seqlens = seqlens; a.scale = scale; a.seed = seed; a.stream = stream;
@@ -549,7 +551,7 @@ static void fill_args(AttnArgs& a, int B, int S, int h, int d, const int* seqlen
 }
 
 void attention_fwd(const void* qkv, const int* seqlens, void* ctx, float* lse, int B, int S, int h, int d,
-                   float scale, unsigned long long seed, unsigned int stream, float p_drop, cudaStream_t st) {
+                   float scale, Seed seed, unsigned int stream, float p_drop, cudaStream_t st) {
   AttnArgs a;
   fill_args(a, B, S, h, d, seqlens, scale, seed, stream, p_drop);
   a.ctx = (__nv_bfloat16*)ctx; a.lse = lse;
@@ -571,7 +573,7 @@ void attention_fwd(const void* qkv, const int* seqlens, void* ctx, float* lse, i
 
 void attention_bwd(const void* qkv, const int* seqlens, const void* ctx, const void* dctx, const float* lse,
                    void* dqkv, float* delta_ws, float* dq_acc, int B, int S, int h, int d, float scale,
-                   unsigned long long seed, unsigned int stream, float p_drop, cudaStream_t st) {
+                   Seed seed, unsigned int stream, float p_drop, cudaStream_t st) {
   AttnArgs a;
   fill_args(a, B, S, h, d, seqlens, scale, seed, stream, p_drop);
   const int H = h * d;

@@ -18,6 +18,22 @@ inline void check_bf16(const Tensor& t, const char* name) {
   TORCH_CHECK(t.stride(-1) == 1, name, " must have a unit inner stride");
   TORCH_CHECK(reinterpret_cast<uintptr_t>(t.data_ptr()) % 16 == 0, name, " must be 16-byte aligned");
 }
+// Device-resident dropout step counter mixed into every seed (set by the engine when it captures CUDA graphs:
+// the pointer is baked into the captured launches, the counter is advanced inside the graph).
+const unsigned long long* g_seed_step = nullptr;
+Tensor g_seed_step_keepalive;
+void set_seed_step(c10::optional<Tensor> t) {
+  if (t.has_value() && t->defined()) {
+    TORCH_CHECK(t->is_cuda() && t->scalar_type() == at::kLong && t->numel() == 1, "seed step must be a CUDA int64 scalar");
+    g_seed_step_keepalive = *t;
+    g_seed_step = reinterpret_cast<const unsigned long long*>(t->data_ptr<int64_t>());
+  } else {
+    g_seed_step = nullptr;
+    g_seed_step_keepalive = Tensor();
+  }
+}
+inline b200::Seed mk_seed(int64_t seed) { return b200::Seed{static_cast<unsigned long long>(seed), g_seed_step}; }
+
 inline const void* opt_ptr(const c10::optional<Tensor>& t) { return t.has_value() && t->defined() ? t->data_ptr() : nullptr; }
 inline float* opt_f32(const c10::optional<Tensor>& t) {
   if (!t.has_value() || !t->defined()) return nullptr;
@@ -95,6 +111,7 @@ void gemm(Tensor a, Tensor b, Tensor out, int64_t layout, int64_t epi, c10::opti
   c.alpha = (float)alpha;
   c.p_drop = (float)p_drop;
   c.seed = (unsigned long long)seed;
+  c.seed_step = g_seed_step;
   c.stream = (unsigned int)stream_id;
   b200::gemm_bf16(c, cur_stream());
 }
@@ -107,7 +124,7 @@ void layer_norm_fwd(Tensor x, Tensor gamma, Tensor beta, Tensor y, c10::optional
   TORCH_CHECK(H % 8 == 0, "hidden size must be a multiple of 8");
   c10::cuda::CUDAGuard guard(x.device());
   b200::layer_norm_fwd(x.data_ptr(), gamma.data_ptr<float>(), beta.data_ptr<float>(), y.data_ptr(), opt_f32(mean),
-                       opt_f32(rstd), M, H, (float)eps, (unsigned long long)seed, (unsigned)stream_id, (float)p_drop,
+                       opt_f32(rstd), M, H, (float)eps, mk_seed(seed), (unsigned)stream_id, (float)p_drop,
                        cur_stream());
 }
 
@@ -124,7 +141,7 @@ void layer_norm_bwd(Tensor dy, Tensor x, Tensor mean, Tensor rstd, Tensor gamma,
   if (dxd.has_value() && dxd->defined()) { check_bf16(*dxd, "dxd"); dxd_p = dxd->data_ptr(); }
   b200::layer_norm_bwd(dy.data_ptr(), x.data_ptr(), mean.data_ptr<float>(), rstd.data_ptr<float>(),
                        gamma.data_ptr<float>(), dx.data_ptr(), dxd_p, opt_f32(dgamma), opt_f32(dbeta), opt_f32(dbias),
-                       workspace.data_ptr<float>(), M, H, (unsigned long long)seed, (unsigned)drop_stream,
+                       workspace.data_ptr<float>(), M, H, mk_seed(seed), (unsigned)drop_stream,
                        (unsigned)in_stream, (float)p_drop, cur_stream());
 }
 
@@ -165,7 +182,7 @@ void embedding_fwd(Tensor ids, c10::optional<Tensor> seg, Tensor word, Tensor po
   }
   b200::embedding_fwd(ids.data_ptr<int>(), seg_p, word.data_ptr(), pos.data_ptr(), type_p, gamma.data_ptr<float>(),
                       beta.data_ptr<float>(), e_out.data_ptr(), y.data_ptr(), mean.data_ptr<float>(),
-                      rstd.data_ptr<float>(), M, (int)S, H, (float)eps, (unsigned long long)seed, (unsigned)stream_id,
+                      rstd.data_ptr<float>(), M, (int)S, H, (float)eps, mk_seed(seed), (unsigned)stream_id,
                       (float)p_drop, cur_stream());
 }
 
@@ -270,7 +287,7 @@ void attention_fwd(Tensor qkv, Tensor seqlens, Tensor ctx, Tensor lse, int64_t h
   const int B = (int)qkv.size(0), S = (int)qkv.size(1), H = (int)qkv.size(2) / 3;
   c10::cuda::CUDAGuard guard(qkv.device());
   b200::attention_fwd(qkv.data_ptr(), seqlens.data_ptr<int>(), ctx.data_ptr(), lse.data_ptr<float>(), B, S, (int)heads,
-                      H / (int)heads, (float)scale, (unsigned long long)seed, (unsigned)stream_id, (float)p_drop, cur_stream());
+                      H / (int)heads, (float)scale, mk_seed(seed), (unsigned)stream_id, (float)p_drop, cur_stream());
 }
 void attention_bwd(Tensor qkv, Tensor seqlens, Tensor ctx, Tensor dctx, Tensor lse, Tensor dqkv, Tensor delta_ws,
                    c10::optional<Tensor> dq_acc, int64_t heads, double scale, double p_drop, int64_t seed, int64_t stream_id) {
@@ -280,7 +297,7 @@ void attention_bwd(Tensor qkv, Tensor seqlens, Tensor ctx, Tensor dctx, Tensor l
   c10::cuda::CUDAGuard guard(qkv.device());
   b200::attention_bwd(qkv.data_ptr(), seqlens.data_ptr<int>(), ctx.data_ptr(), dctx.data_ptr(), lse.data_ptr<float>(),
                       dqkv.data_ptr(), delta_ws.data_ptr<float>(), opt_f32(dq_acc), B, S, (int)heads, H / (int)heads, (float)scale,
-                      (unsigned long long)seed, (unsigned)stream_id, (float)p_drop, cur_stream());
+                      mk_seed(seed), (unsigned)stream_id, (float)p_drop, cur_stream());
 }
 
 void fused_allreduce_lamb(int64_t rank, int64_t world, bool use_multicast, std::vector<int64_t> grad_ptrs,
@@ -366,6 +383,7 @@ void fp8_update(Tensor meta, Tensor is_e5m2, double margin_pow2) {
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "bert_pytorch_b200 sm_100a kernels";
   m.def("gemm", &gemm);
+  m.def("set_seed_step", &set_seed_step);
   m.def("peer_allreduce", &peer_allreduce);
   m.def("fp8_quantize", &fp8_quantize);
   m.def("fp8_amax", &fp8_amax);

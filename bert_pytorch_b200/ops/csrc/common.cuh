@@ -9,6 +9,8 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include "seed.h"
+
 #ifndef B200_WATCHDOG_NS
 #define B200_WATCHDOG_NS 4000000000ull  // a barrier wait longer than 4 s traps instead of hanging the GPU
 #endif

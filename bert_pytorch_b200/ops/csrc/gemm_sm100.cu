@@ -55,7 +55,7 @@ struct GemmArgs {
   const __nv_bfloat16* bias;
   const __nv_bfloat16* res;
   int ldr;
-  unsigned long long seed;
+  Seed seed;
   unsigned int stream;
   unsigned int drop_thresh16;
   float drop_scale;
@@ -63,13 +63,14 @@ struct GemmArgs {
   const float* scale_a;      // fp8: device dequantisation factors (nullptr for bf16 operands)
   const float* scale_b;
   unsigned int fp8_fmt;      // bit0: A is e5m2 (else e4m3), bit1: B is e5m2
+  int stream_k;              // pair kernel: contiguous (tile, k-block) ranges per cluster instead of whole tiles
 };
 
 // Drain one 128 x BLOCK_N fp32 accumulator tile (this warp's 32 TMEM lanes) through the selected epilogue.
 // `taddr` already carries the lane quarter; `row` is this thread's global output row.
 template <int BLOCK_N>
 __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint32_t taddr, int row, bool row_ok, int n_base,
-                                              int c_begin, int c_end, float alpha) {
+                                              int c_begin, int c_end, float alpha, unsigned long long seed) {
   #pragma unroll 1
   for (int c = c_begin; c < c_end; ++c) {
     const int n0 = n_base + c * 32;
@@ -150,7 +151,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint32_t taddr,
         for (int g = 0; g < 4; ++g) {
           if (g * 8 < ncols) {
             const uint64_t e8 = ((uint64_t)row * (uint64_t)p.N + (uint64_t)(n0 + g * 8)) >> 3;
-            const uint32_t keep = dropout_keep8(p.seed, p.stream, e8, p.drop_thresh16);
+            const uint32_t keep = dropout_keep8(seed, p.stream, e8, p.drop_thresh16);
 #pragma unroll
             for (int t = 0; t < 8; ++t) f[g * 8 + t] = ((keep >> t) & 1u) ? f[g * 8 + t] * p.drop_scale : 0.f;
           }
@@ -297,6 +298,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   } else {
     // ------------------------------------------------------------------ epilogue (8 warps: 4 lane quarters x 2 column halves)
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const unsigned long long seed = p.drop_thresh16 != 0 ? p.seed.value() : 0ull;
     const int half = (warp - 2) >> 2;
     constexpr int CH = BLOCK_N / 64;   // 32-column chunks per warp
     uint32_t tile_it = 0;
@@ -312,7 +314,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const int row = mb * BLOCK_M + q * 32 + lane;
       const bool row_ok = row < p.M && kb1 > kb0;
       const uint32_t taddr = tmem_base + as * BLOCK_N + (uint32_t(q * 32) << 16);
-      epilogue_tile<BLOCK_N>(p, taddr, row, row_ok, nb * BLOCK_N, half * CH, half * CH + CH, p.alpha);
+      epilogue_tile<BLOCK_N>(p, taddr, row, row_ok, nb * BLOCK_N, half * CH, half * CH + CH, p.alpha, seed);
       tc_fence_before();
       mbar_arrive(&tmem_empty[as]);
     }
@@ -346,7 +348,7 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 //                                 MODE 2: GELU second pass: staging -> gelu(staging)
 template <int MODE>
 __device__ __forceinline__ void staged_pass(const GemmArgs& p, uint8_t* sC, uint32_t taddr, int r, int row, int n_base,
-                                            int c_begin, bool use_res, float alpha) {
+                                            int c_begin, bool use_res, float alpha, unsigned long long seed) {
 #pragma unroll 1
   for (int c = c_begin; c < c_begin + 4; ++c) {
     const int col0 = c * 32;
@@ -396,7 +398,7 @@ __device__ __forceinline__ void staged_pass(const GemmArgs& p, uint8_t* sC, uint
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const uint64_t e8 = ((uint64_t)row * (uint64_t)p.N + (uint64_t)(n0 + g * 8)) >> 3;
-            const uint32_t keep = dropout_keep8(p.seed, p.stream, e8, p.drop_thresh16);
+            const uint32_t keep = dropout_keep8(seed, p.stream, e8, p.drop_thresh16);
 #pragma unroll
             for (int t = 0; t < 8; ++t) f[g * 8 + t] = ((keep >> t) & 1u) ? f[g * 8 + t] * p.drop_scale : 0.f;
           }
@@ -442,6 +444,41 @@ constexpr int PAIR_M = 256, PAIR_N = 256, PAIR_STAGE = 32768, PAIR_STAGES = 5;
 constexpr int PAIR_CSTAGE = 128 * PAIR_N * 2;   // bf16 output/residual staging tile of one CTA: 4 x [128 x 64] swizzled boxes
 constexpr int PAIR_SMEM = PAIR_STAGES * PAIR_STAGE + PAIR_CSTAGE + 1024 + 256;
 
+// Work decomposition of the pair kernel.  Classic: cluster c owns the (split, tile) units c, c + C, c + 2C, ...
+// Stream-K (accumulating fp32 epilogue only): the m_blocks * n_blocks * k_blocks iteration space is cut into C
+// equal contiguous ranges, so every cluster does the same number of MMAs regardless of how the tile count
+// divides the machine (64 weight-gradient tiles on 74 CTA pairs would otherwise idle 14 % of the tensor cores);
+// a range spans at most a few tiles and each piece is added with red.global.add.
+struct WorkSeg { int mn, kb0, kb1; };
+__device__ __forceinline__ int seg_count(const GemmArgs& p, int c, int C) {
+  if (!p.stream_k) {
+    const int total = p.m_blocks * p.n_blocks * p.k_splits;
+    return c < total ? (total - c + C - 1) / C : 0;
+  }
+  const long long total = (long long)p.m_blocks * p.n_blocks * p.k_blocks;
+  const long long it0 = total * c / C, it1 = total * (c + 1) / C;
+  return it1 > it0 ? (int)((it1 - 1) / p.k_blocks - it0 / p.k_blocks + 1) : 0;
+}
+__device__ __forceinline__ WorkSeg seg_get(const GemmArgs& p, int c, int C, int idx) {
+  WorkSeg w;
+  if (!p.stream_k) {
+    const int tile = c + idx * C;
+    const int mnt = p.m_blocks * p.n_blocks;
+    const int ks = tile / mnt;
+    w.mn = tile % mnt;
+    w.kb0 = ks * p.k_per_split;
+    w.kb1 = min(p.k_blocks, w.kb0 + p.k_per_split);
+    return w;
+  }
+  const long long total = (long long)p.m_blocks * p.n_blocks * p.k_blocks;
+  const long long it0 = total * c / C, it1 = total * (c + 1) / C;
+  const long long start = idx == 0 ? it0 : (it0 / p.k_blocks + idx) * p.k_blocks;
+  w.mn = (int)(start / p.k_blocks);
+  w.kb0 = (int)(start % p.k_blocks);
+  w.kb1 = (int)min((long long)p.k_blocks, w.kb0 + (it1 - start));
+  return w;
+}
+
 template <bool A_MN, bool B_MN, bool FP8>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -485,17 +522,15 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const uint32_t tmem_base = *tmem_base_slot;
 
   const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
-  const int total_tiles = p.m_blocks * p.n_blocks * p.k_splits;
+  const int nseg = seg_count(p, cluster_id, nclusters);
 
   if (warp == 0) {
     if (lane == 0) {                     // ---------------- TMA producer (both CTAs)
       uint32_t it = 0;
-      for (int tile = cluster_id; tile < total_tiles; tile += nclusters) {
-        const int nb = tile % p.n_blocks;
-        const int mb = (tile / p.n_blocks) % p.m_blocks;
-        const int ks = tile / (p.n_blocks * p.m_blocks);
-        const int kb0 = ks * p.k_per_split;
-        const int kb1 = min(p.k_blocks, kb0 + p.k_per_split);
+      for (int si = 0; si < nseg; ++si) {
+        const WorkSeg w = seg_get(p, cluster_id, nclusters, si);
+        const int nb = w.mn % p.n_blocks, mb = w.mn / p.n_blocks;
+        const int kb0 = w.kb0, kb1 = w.kb1;
         const int m0 = mb * PAIR_M + (int)rank * 128, n0 = nb * PAIR_N + (int)rank * 128;
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % PAIR_STAGES;
@@ -533,10 +568,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       constexpr uint32_t A_KSTEP = A_MN ? (FP8 ? 4096u : 2048u) : 32u;
       constexpr uint32_t B_KSTEP = B_MN ? (FP8 ? 4096u : 2048u) : 32u;
       uint32_t it = 0, tile_it = 0;
-      for (int tile = cluster_id; tile < total_tiles; tile += nclusters, ++tile_it) {
-        const int ks = tile / (p.n_blocks * p.m_blocks);
-        const int kb0 = ks * p.k_per_split;
-        const int kb1 = min(p.k_blocks, kb0 + p.k_per_split);
+      for (int si = 0; si < nseg; ++si, ++tile_it) {
+        const WorkSeg w = seg_get(p, cluster_id, nclusters, si);
+        const int kb0 = w.kb0, kb1 = w.kb1;
         const uint32_t as = tile_it & 1, aph = (tile_it >> 1) & 1;
         mbar_wait(&tmem_empty[as], aph ^ 1);
         tc_fence_after();
@@ -570,6 +604,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                          (p.epi == EPI_BIAS_DROP_RES || p.epi == EPI_ADD || p.epi == EPI_DGELU);
     const bool issuer = threadIdx.x == 64;   // first epilogue thread drives the staging tile's TMA traffic
     const int r = q * 32 + lane;             // row inside the CTA tile == TMEM lane
+    const unsigned long long seed = p.drop_thresh16 != 0 ? p.seed.value() : 0ull;
     float alpha = p.alpha;
     if constexpr (FP8) alpha *= __ldg(p.scale_a) * __ldg(p.scale_b);   // per-tensor dequantisation
     auto load_res = [&](int tile) {
@@ -580,11 +615,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       for (int j = 0; j < 4; ++j)
         tma_load_2d(sC + j * 16384, &tmap_res, c_full, nb * PAIR_N + j * 64, mb * PAIR_M + (int)rank * 128);
     };
-    if (use_res && issuer && cluster_id < total_tiles) load_res(cluster_id);
+    if (use_res && issuer && nseg > 0) load_res(seg_get(p, cluster_id, nclusters, 0).mn);
     uint32_t tile_it = 0, c_phase = 0;
-    for (int tile = cluster_id; tile < total_tiles; tile += nclusters, ++tile_it) {
-      const int nb = tile % p.n_blocks;
-      const int mb = (tile / p.n_blocks) % p.m_blocks;
+    for (int si = 0; si < nseg; ++si, ++tile_it) {
+      const int mn = seg_get(p, cluster_id, nclusters, si).mn;
+      const int nb = mn % p.n_blocks, mb = mn / p.n_blocks;
       const uint32_t as = tile_it & 1, aph = (tile_it >> 1) & 1;
       mbar_wait(&tmem_full[as], aph);
       tc_fence_after();
@@ -592,7 +627,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int row = row0 + r;
       const uint32_t taddr = tmem_base + as * PAIR_N + (uint32_t(q * 32) << 16);
       if (!staged) {
-        epilogue_tile<PAIR_N>(p, taddr, row, row < p.M, nb * PAIR_N, half * 4, half * 4 + 4, alpha);
+        epilogue_tile<PAIR_N>(p, taddr, row, row < p.M, nb * PAIR_N, half * 4, half * 4 + 4, alpha, seed);
         tc_fence_before();
         mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), 0));
         continue;
@@ -601,8 +636,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         mbar_wait(c_full, c_phase);
         c_phase ^= 1;
       }
-      if (p.epi == EPI_BIAS_GELU) staged_pass<1>(p, sC, taddr, r, row, nb * PAIR_N, half * 4, false, alpha);
-      else staged_pass<0>(p, sC, taddr, r, row, nb * PAIR_N, half * 4, use_res, alpha);
+      if (p.epi == EPI_BIAS_GELU) staged_pass<1>(p, sC, taddr, r, row, nb * PAIR_N, half * 4, false, alpha, seed);
+      else staged_pass<0>(p, sC, taddr, r, row, nb * PAIR_N, half * 4, use_res, alpha, seed);
       tc_fence_before();
       mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), 0));   // accumulator drained: MMA may reuse it
       fence_proxy_async();
@@ -616,7 +651,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           tma_store_wait_read<0>();
         }
         epi_bar_sync();
-        staged_pass<2>(p, sC, taddr, r, row, nb * PAIR_N, half * 4, false, alpha);
+        staged_pass<2>(p, sC, taddr, r, row, nb * PAIR_N, half * 4, false, alpha, seed);
         fence_proxy_async();
         epi_bar_sync();
       }
@@ -626,7 +661,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (nb * PAIR_N + j * 64 < p.N) tma_store_2d(&tmap_out, sC + j * 16384, nb * PAIR_N + j * 64, row0);
         tma_store_commit();
         tma_store_wait_read<0>();                         // staging tile free again
-        if (use_res && tile + nclusters < total_tiles) load_res(tile + nclusters);
+        if (use_res && si + 1 < nseg) load_res(seg_get(p, cluster_id, nclusters, si + 1).mn);
       }
       epi_bar_sync();                                     // nobody touches the staging tile before that
     }
@@ -742,12 +777,12 @@ static void launch(const GemmCall& c, cudaStream_t st) {
   p.out = c.out; p.ldo = c.ldo; p.aux_out = reinterpret_cast<__nv_bfloat16*>(c.aux_out);
   p.bias = reinterpret_cast<const __nv_bfloat16*>(c.bias);
   p.res = reinterpret_cast<const __nv_bfloat16*>(c.res); p.ldr = c.ldr;
-  p.seed = c.seed; p.stream = c.stream;
+  p.seed = Seed{c.seed, c.seed_step}; p.stream = c.stream;
   float pd = c.p_drop;
   p.drop_thresh16 = pd > 0.f ? (unsigned)(pd * 65536.f + 0.5f) : 0u;
   p.drop_scale = pd > 0.f ? 65536.f / (65536.f - (float)p.drop_thresh16) : 1.f;
   p.alpha = c.alpha;
-  p.scale_a = nullptr; p.scale_b = nullptr; p.fp8_fmt = 0;
+  p.scale_a = nullptr; p.scale_b = nullptr; p.fp8_fmt = 0; p.stream_k = 0;
   // operand maps
   CUtensorMap ta = A_MN ? make_tmap_2d_bf16(c.A, c.M, c.K, c.lda, 64, BLOCK_K)
                         : make_tmap_2d_bf16(c.A, c.K, c.M, c.lda, BLOCK_K, BLOCK_M);
@@ -781,11 +816,22 @@ static void launch_pair(const GemmCall& c, cudaStream_t st) {
   p.out = c.out; p.ldo = c.ldo; p.aux_out = reinterpret_cast<__nv_bfloat16*>(c.aux_out);
   p.bias = reinterpret_cast<const __nv_bfloat16*>(c.bias);
   p.res = reinterpret_cast<const __nv_bfloat16*>(c.res); p.ldr = c.ldr;
-  p.seed = c.seed; p.stream = c.stream;
+  p.seed = Seed{c.seed, c.seed_step}; p.stream = c.stream;
   float pd = c.p_drop;
   p.drop_thresh16 = pd > 0.f ? (unsigned)(pd * 65536.f + 0.5f) : 0u;
   p.drop_scale = pd > 0.f ? 65536.f / (65536.f - (float)p.drop_thresh16) : 1.f;
   p.alpha = c.alpha;
+  // k_splits < 0 asks for stream-K (fp32 accumulate epilogue only): equal MMA work per cluster, pieces merged by
+  // red.global.add.  Needs enough k-blocks per cluster to amortise the extra partial tiles.
+  p.stream_k = 0;
+  if (c.k_splits < 0 && c.epi == EPI_ACCUM_F32) {
+    const long long iters = (long long)p.m_blocks * p.n_blocks * p.k_blocks;
+    const int pairs_ = num_sms() / 2;
+    if (iters >= 8ll * pairs_ && (p.m_blocks * p.n_blocks) % pairs_ != 0) {
+      p.stream_k = 1;
+      p.k_splits = 2;               // "more than one contributor per tile": the epilogue uses red.global.add
+    }
+  }
   p.scale_a = c.scale_a; p.scale_b = c.scale_b;
   p.fp8_fmt = (c.a_e5m2 ? 1u : 0u) | (c.b_e5m2 ? 2u : 0u);
   if (FP8 && (c.scale_a == nullptr || c.scale_b == nullptr)) {
@@ -811,7 +857,7 @@ static void launch_pair(const GemmCall& c, cudaStream_t st) {
   }
   const int tiles = p.m_blocks * p.n_blocks * p.k_splits;
   const int pairs = num_sms() / 2;
-  const int grid = 2 * (tiles < pairs ? tiles : pairs);
+  const int grid = p.stream_k ? 2 * pairs : 2 * (tiles < pairs ? tiles : pairs);
   if (grid <= 0) return;
   kern<<<grid, NUM_THREADS, PAIR_SMEM, st>>>(ta, tb, to, tx, tr, p);
 }

@@ -37,6 +37,7 @@ struct GemmCall {
   const void* res = nullptr; int ldr = 0;
   int k_splits = 1;
   unsigned long long seed = 0; unsigned int stream = 0; float p_drop = 0.f;
+  const unsigned long long* seed_step = nullptr;   // device step counter mixed into the seed (CUDA-graph replays)
   float alpha = 1.f;
   // fp8 operands (CTA-pair kernel): A/B are e4m3 (default) or e5m2 bytes, lda/ldb in elements (= bytes);
   // scale_a/scale_b point at the device-resident per-tensor dequantisation factors (x = q * scale)

@@ -2,22 +2,24 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "seed.h"
+
 namespace b200 {
 
 // norm_embed.cu
 void layer_norm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int M,
-                    int H, float eps, unsigned long long seed, unsigned int stream, float p_drop, cudaStream_t st);
+                    int H, float eps, Seed seed, unsigned int stream, float p_drop, cudaStream_t st);
 int ln_bwd_workspace_floats(int M, int H);
 void layer_norm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
                     void* dxd, float* dgamma, float* dbeta, float* dbias, float* workspace, int M, int H,
-                    unsigned long long seed, unsigned int drop_stream, unsigned int in_stream, float p_drop,
+                    Seed seed, unsigned int drop_stream, unsigned int in_stream, float p_drop,
                     cudaStream_t st);
 void gelu_fwd(const void* x, void* y, long long n, cudaStream_t st);
 void dgelu_bwd(const void* dy, const void* x, void* dx, float* dbias, int M, int N, cudaStream_t st);
 void colsum_bf16(const void* x, int M, int N, int ld, float* out, cudaStream_t st);
 void embedding_fwd(const int* ids, const int* seg, const void* word, const void* pos, const void* type,
                    const float* gamma, const float* beta, void* e_out, void* y, float* mean, float* rstd, int M, int S,
-                   int H, float eps, unsigned long long seed, unsigned int stream, float p_drop, cudaStream_t st);
+                   int H, float eps, Seed seed, unsigned int stream, float p_drop, cudaStream_t st);
 void embedding_bwd_scatter(const void* de, const int* ids, const int* seg, float* gword, float* gpos, float* gtype,
                            int M, int S, int H, cudaStream_t st);
 void mlm_compact(const int* labels, int B, int S, int max_pred, int* idx, int* tgt, int* count, cudaStream_t st);
@@ -48,10 +50,10 @@ void arena_adam(float* g, float* p, float* m, float* v, void* shadow, const int*
 
 // attention.cu
 void attention_fwd(const void* qkv, const int* seqlens, void* ctx, float* lse, int B, int S, int h, int d,
-                   float scale, unsigned long long seed, unsigned int stream, float p_drop, cudaStream_t st);
+                   float scale, Seed seed, unsigned int stream, float p_drop, cudaStream_t st);
 void attention_bwd(const void* qkv, const int* seqlens, const void* ctx, const void* dctx, const float* lse,
                    void* dqkv, float* delta_ws, float* dq_acc, int B, int S, int h, int d, float scale,
-                   unsigned long long seed, unsigned int stream, float p_drop, cudaStream_t st);
+                   Seed seed, unsigned int stream, float p_drop, cudaStream_t st);
 
 // comm.cu -- fused peer-memory all-reduce + partitioned LAMB (one cooperative kernel per step)
 struct FusedLambLaunch {

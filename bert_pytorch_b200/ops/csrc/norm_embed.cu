@@ -85,141 +85,6 @@ __device__ __forceinline__ void row_stats(const float (&x)[CHUNKS][8], int H, in
 }
 
 // ------------------------------------------------------------------------------------------------
-// LayerNorm forward:  y = (x - mean) * rstd * gamma + beta     (optionally followed by dropout)
-// ------------------------------------------------------------------------------------------------
-template <int CHUNKS>
-__global__ void __launch_bounds__(LN_WARPS * 32)
-ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-              __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int H,
-              float eps, unsigned long long seed, unsigned int stream, unsigned int thresh16, float drop_scale) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float g[CHUNKS][8], b[CHUNKS][8];
-  load_vec_f32<CHUNKS>(gamma, H, lane, g);
-  load_vec_f32<CHUNKS>(beta, H, lane, b);
-  for (int row = blockIdx.x * LN_WARPS + warp; row < M; row += gridDim.x * LN_WARPS) {
-    float v[CHUNKS][8];
-    load_row<CHUNKS>(x + (size_t)row * H, H, lane, v);
-    float mean, rstd;
-    row_stats<CHUNKS>(v, H, lane, eps, mean, rstd);
-#pragma unroll
-    for (int c = 0; c < CHUNKS; ++c) {
-      const int col = c * 256 + lane * 8;
-      uint32_t keep = 0xFFu;
-      if (thresh16 != 0 && col < H)
-        keep = dropout_keep8(seed, stream, ((uint64_t)row * H + col) >> 3, thresh16);
-#pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        float o = (v[c][t] - mean) * rstd * g[c][t] + b[c][t];
-        if (thresh16 != 0) o = ((keep >> t) & 1u) ? o * drop_scale : 0.f;
-        v[c][t] = o;
-      }
-    }
-    store_row<CHUNKS>(y + (size_t)row * H, H, lane, v);
-    if (lane == 0) {
-      if (mean_out) mean_out[row] = mean;
-      if (rstd_out) rstd_out[row] = rstd;
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// LayerNorm backward.
-//   in : dy [M,H] (grad wrt LN output; if out_drop_* given, dy is first multiplied by the *output* dropout
-//        mask of stream `in_stream` -- used by the embedding LN whose output was dropped out)
-//        x  [M,H] pre-LN input, mean/rstd [M], gamma [H]
-//   out: dx [M,H]          grad wrt the pre-LN input (this is also the residual-branch gradient)
-//        dxd [M,H] optional: dx * dropout_mask(stream `drop_stream`) * scale  -> gradient of the GEMM output
-//                            that was dropped out before the residual add (K14/K18)
-//        partial [grid, 3, H]: per-block column sums of (dy*xhat, dy, dxd) -> dgamma, dbeta, dbias
-// ------------------------------------------------------------------------------------------------
-template <int CHUNKS>
-__global__ void __launch_bounds__(LN_WARPS * 32)
-ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
-              const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
-              __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dxd, float* __restrict__ partial, int M,
-              int H, unsigned long long seed, unsigned int drop_stream, unsigned int in_stream,
-              unsigned int thresh16, float drop_scale) {
-  __shared__ float red[LN_WARPS][3][8 * 32];  // per warp: 3 quantities x (one chunk of 256 columns)
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float g[CHUNKS][8];
-  load_vec_f32<CHUNKS>(gamma, H, lane, g);
-  float acc_g[CHUNKS][8], acc_b[CHUNKS][8], acc_d[CHUNKS][8];
-#pragma unroll
-  for (int c = 0; c < CHUNKS; ++c)
-#pragma unroll
-    for (int t = 0; t < 8; ++t) acc_g[c][t] = acc_b[c][t] = acc_d[c][t] = 0.f;
-
-  for (int row = blockIdx.x * LN_WARPS + warp; row < M; row += gridDim.x * LN_WARPS) {
-    float d[CHUNKS][8], v[CHUNKS][8];
-    load_row<CHUNKS>(dy + (size_t)row * H, H, lane, d);
-    load_row<CHUNKS>(x + (size_t)row * H, H, lane, v);
-    const float mu = mean[row], rs = rstd[row];
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int c = 0; c < CHUNKS; ++c) {
-      const int col = c * 256 + lane * 8;
-      if (in_stream != 0xFFFFFFFFu && thresh16 != 0 && col < H) {
-        const uint32_t keep = dropout_keep8(seed, in_stream, ((uint64_t)row * H + col) >> 3, thresh16);
-#pragma unroll
-        for (int t = 0; t < 8; ++t) d[c][t] = ((keep >> t) & 1u) ? d[c][t] * drop_scale : 0.f;
-      }
-#pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const float xh = (v[c][t] - mu) * rs;
-        const float dg = d[c][t] * g[c][t];
-        acc_g[c][t] += d[c][t] * xh;
-        acc_b[c][t] += d[c][t];
-        v[c][t] = xh;
-        d[c][t] = dg;
-        s1 += dg;
-        s2 += dg * xh;
-      }
-    }
-    s1 = warp_sum(s1) / (float)H;
-    s2 = warp_sum(s2) / (float)H;
-#pragma unroll
-    for (int c = 0; c < CHUNKS; ++c)
-#pragma unroll
-      for (int t = 0; t < 8; ++t) d[c][t] = rs * (d[c][t] - s1 - v[c][t] * s2);
-    store_row<CHUNKS>(dx + (size_t)row * H, H, lane, d);
-    if (dxd != nullptr) {
-#pragma unroll
-      for (int c = 0; c < CHUNKS; ++c) {
-        const int col = c * 256 + lane * 8;
-        if (thresh16 != 0 && col < H) {
-          const uint32_t keep = dropout_keep8(seed, drop_stream, ((uint64_t)row * H + col) >> 3, thresh16);
-#pragma unroll
-          for (int t = 0; t < 8; ++t) d[c][t] = ((keep >> t) & 1u) ? d[c][t] * drop_scale : 0.f;
-        }
-#pragma unroll
-        for (int t = 0; t < 8; ++t) acc_d[c][t] += d[c][t];
-      }
-      store_row<CHUNKS>(dxd + (size_t)row * H, H, lane, d);
-    }
-  }
-  // block reduce the three column sums, one 256-column chunk at a time
-#pragma unroll
-  for (int c = 0; c < CHUNKS; ++c) {
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      red[warp][0][lane * 8 + t] = acc_g[c][t];
-      red[warp][1][lane * 8 + t] = acc_b[c][t];
-      red[warp][2][lane * 8 + t] = acc_d[c][t];
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 3 * 256; i += LN_WARPS * 32) {
-      const int qn = i / 256, cc = i % 256;
-      float s = 0.f;
-#pragma unroll
-      for (int w = 0; w < LN_WARPS; ++w) s += red[w][qn][cc];
-      const int col = c * 256 + cc;
-      if (col < H) partial[((size_t)blockIdx.x * 3 + qn) * H + col] = s;
-    }
-    __syncthreads();
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // LayerNorm forward / backward, occupancy-friendly layout: WPR warps share one row, every lane owns ONE
 // 16-byte chunk (8 columns), a block holds two such row groups.  ~70-90 registers per thread instead of
 // 255 -> 4-6x more warps in flight, which is what a pure streaming kernel needs to reach HBM speed
@@ -278,7 +143,8 @@ template <int WPR>
 __global__ void __launch_bounds__(2 * WPR * 32)
 ln_fwd2_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int H,
-               float eps, unsigned long long seed, unsigned int stream, unsigned int thresh16, float drop_scale) {
+               float eps, Seed seed_in, unsigned int stream, unsigned int thresh16, float drop_scale) {
+  const unsigned long long seed = seed_in.value();
   __shared__ float2 xchg[2][2][8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int group = warp / WPR, wi = warp % WPR;
@@ -331,13 +197,22 @@ ln_fwd2_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ ga
   }
 }
 
+// LayerNorm backward.
+//   in : dy [M,H] (grad wrt LN output; with `in_stream` given, dy is first multiplied by the *output* dropout
+//        mask of that stream -- used by the embedding LN whose output was dropped out)
+//        x  [M,H] pre-LN input, mean/rstd [M], gamma [H]
+//   out: dx [M,H]          grad wrt the pre-LN input (this is also the residual-branch gradient)
+//        dxd [M,H] optional: dx * dropout_mask(stream `drop_stream`) * scale  -> gradient of the GEMM output
+//                            that was dropped out before the residual add (K14/K18)
+//        partial [grid, 3, H]: per-block column sums of (dy*xhat, dy, dxd) -> dgamma, dbeta, dbias
 template <int WPR>
 __global__ void __launch_bounds__(2 * WPR * 32)
 ln_bwd2_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
                __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dxd, float* __restrict__ partial, int M,
-               int H, unsigned long long seed, unsigned int drop_stream, unsigned int in_stream,
+               int H, Seed seed_in, unsigned int drop_stream, unsigned int in_stream,
                unsigned int thresh16, float drop_scale) {
+  const unsigned long long seed = seed_in.value();
   __shared__ float2 xchg[2][2][8];
   __shared__ float comb[3][WPR * 256];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -545,8 +420,9 @@ embed_fwd_kernel(const int* __restrict__ ids, const int* __restrict__ seg, const
                  const __nv_bfloat16* __restrict__ pos, const __nv_bfloat16* __restrict__ type,
                  const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ e_out,
                  __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int M,
-                 int S, int H, float eps, unsigned long long seed, unsigned int stream, unsigned int thresh16,
+                 int S, int H, float eps, Seed seed_in, unsigned int stream, unsigned int thresh16,
                  float drop_scale) {
+  const unsigned long long seed = seed_in.value();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float g[CHUNKS][8], b[CHUNKS][8];
   load_vec_f32<CHUNKS>(gamma, H, lane, g);
@@ -725,7 +601,7 @@ static inline int ln2_grid(int M) {     // 2 rows per block at a time; 4 residen
 }
 
 void layer_norm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int M,
-                    int H, float eps, unsigned long long seed, unsigned int stream, float p_drop, cudaStream_t st) {
+                    int H, float eps, Seed seed, unsigned int stream, float p_drop, cudaStream_t st) {
   unsigned int th; float sc;
   drop_params(p_drop, th, sc);
   DISPATCH_WPR(H, (ln_fwd2_kernel<WPR><<<ln2_grid(M), 2 * WPR * 32, 0, st>>>(
@@ -736,7 +612,7 @@ int ln_bwd_workspace_floats(int M, int H) { return ln2_grid(M) * 3 * H; }
 
 void layer_norm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
                     void* dxd, float* dgamma, float* dbeta, float* dbias, float* workspace, int M, int H,
-                    unsigned long long seed, unsigned int drop_stream, unsigned int in_stream, float p_drop,
+                    Seed seed, unsigned int drop_stream, unsigned int in_stream, float p_drop,
                     cudaStream_t st) {
   unsigned int th; float sc;
   drop_params(p_drop, th, sc);
@@ -766,7 +642,7 @@ void dgelu_bwd(const void* dy, const void* x, void* dx, float* dbias, int M, int
 
 void embedding_fwd(const int* ids, const int* seg, const void* word, const void* pos, const void* type,
                    const float* gamma, const float* beta, void* e_out, void* y, float* mean, float* rstd, int M, int S,
-                   int H, float eps, unsigned long long seed, unsigned int stream, float p_drop, cudaStream_t st) {
+                   int H, float eps, Seed seed, unsigned int stream, float p_drop, cudaStream_t st) {
   unsigned int th; float sc;
   drop_params(p_drop, th, sc);
   DISPATCH_CHUNKS(H, (embed_fwd_kernel<CH><<<ln_grid(M), LN_WARPS * 32, 0, st>>>(

@@ -55,6 +55,20 @@ def test_gemm_tn_accumulate(M, N, K, block_n, splits):
     _check(out, base + a.float().t() @ b.float(), tol=1e-2)
 
 
+@pytest.mark.parametrize("M,N,K", [(1024, 4096, 12288), (1024, 1024, 4096), (520, 1000, 3000), (3072, 1024, 2048)])
+def test_gemm_tn_stream_k(M, N, K):
+    """k_splits=-1: stream-K decomposition (contiguous (tile, k-block) ranges per CTA pair, merged by red.add)."""
+    K_ = _ops()
+    a, b = _rand(K, M), _rand(K, N)
+    base = torch.randn(M, N, device="cuda")
+    out = base.clone()
+    K_.gemm(a, b, layout=K_.TN, epi=K_.EPI_ACCUM_F32, out=out, block_n=512, k_splits=-1)
+    _check(out, base + a.float().t() @ b.float(), tol=1e-2)
+    grad = torch.zeros(M, N, device="cuda")
+    K_.wgrad_accumulate(a, b, grad)                      # the engine's entry point picks stream-K by itself
+    _check(grad, a.float().t() @ b.float(), tol=1e-2)
+
+
 @pytest.mark.parametrize("bn", [256, 512])
 def test_gemm_epilogues(bn):
     import functools

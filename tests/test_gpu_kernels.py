@@ -291,3 +291,39 @@ def test_checkpoint_activations_replays_dropout_exactly():
     for (n, p), q in zip(m1.named_parameters(), m2.parameters()):
         scale = p.grad.abs().max().item() + 1e-12
         assert (p.grad - q.grad).abs().max().item() <= 1e-4 * scale, n      # split-K atomics reorder fp32 adds
+
+
+def test_cuda_graph_replay_matches_eager_program():
+    """forward_backward switches to a captured CUDA graph after two eager calls per input signature: the
+    replays must produce the eager program's loss and gradients on fresh inputs (dropout off), and advance
+    the dropout stream on every replay (dropout on)."""
+    from bert_pytorch_b200.models.arena import ParamArena
+    m_g = _tiny_model().cuda()
+    m_e = copy.deepcopy(m_g)
+    a_g, a_e = ParamArena(m_g), ParamArena(m_e)
+    e_g, e_e = m_g.pretrain_engine(), m_e.pretrain_engine()
+    e_e.use_graphs = False
+    assert e_g.use_graphs
+    base = _batch()
+    for it in range(5):
+        ids = torch.roll(base[0], it, dims=1)
+        labels = torch.roll(base[3], it, dims=1)
+        batch = (ids, base[1], base[2], labels, base[4])
+        a_g.zero_grad(); a_e.zero_grad()
+        lg = e_g.forward_backward(*batch).clone()
+        le = e_e.forward_backward(*batch)
+        assert abs(lg.item() - le.item()) <= 1e-5 * abs(le.item()), (it, lg.item(), le.item())
+        for (n, p), q in zip(m_g.named_parameters(), m_e.parameters()):
+            scale = q.grad.abs().max().item() + 1e-12
+            assert (p.grad - q.grad).abs().max().item() <= 1e-4 * scale, (it, n)
+    assert any("graph" in ent for ent in e_g._graphs.values())
+    # dropout: two replays on identical inputs must draw different masks
+    m_d = _tiny_model(drop=0.1).cuda()
+    a_d = ParamArena(m_d)
+    e_d = m_d.pretrain_engine()
+    losses = []
+    for it in range(6):
+        a_d.zero_grad()
+        losses.append(e_d.forward_backward(*base).item())
+    assert any("graph" in ent for ent in e_d._graphs.values())
+    assert len({round(x, 6) for x in losses[3:]}) == 3, losses
