@@ -101,7 +101,7 @@ def main():
         # general all-reduce through our own kernel (K-FAC factor path): odd sizes, packing, avg
         torch.manual_seed(77 + rank)
         ts = [torch.randn(1025, 1025, device=dev), torch.randn(7, device=dev), torch.randn(300, 64, device=dev).t()]
-        refs = [t.clone() for t in ts]
+        refs = [t.detach().clone(memory_format=torch.contiguous_format) for t in ts]
         comm.all_reduce_many_(ts, op="avg")
         for r in refs:
             dist.all_reduce(r, op=dist.ReduceOp.AVG)
