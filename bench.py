@@ -59,7 +59,8 @@ def parse():
     ap.add_argument("--accum", type=int, default=32, help="micro-batches per optimizer step (ignored with --global-batch)")
     ap.add_argument("--global-batch", type=int, default=0, help="use the shipped ceil arithmetic for this global batch")
     ap.add_argument("--local-batch", type=int, default=0)
-    ap.add_argument("--backend", default="nccl", choices=["nccl", "fused"], help="gradient reduction (ours)")
+    ap.add_argument("--backend", default="fused", choices=["nccl", "fused"],
+                    help="gradient reduction (ours): fused = one peer-memory kernel for reduce-scatter + LAMB + all-gather")
     ap.add_argument("--layers", type=int, default=0, help="debug only: fewer layers (marks the result invalid)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--fp8", action="store_true", help="fp8 GEMM operands (separate config; the headline stays bf16)")
@@ -162,7 +163,12 @@ def run_ours(args, ph, B, accum, rank, world, dev):
     arena = ParamArena(model, device=dev)
     comm = make_comm(args.backend if world > 1 else None)
     if getattr(comm, "fuses_optimizer", False):
-        comm.adopt(arena)            # arenas -> NVLink symmetric memory; reduction + LAMB become one kernel
+        try:
+            comm.adopt(arena)        # arenas -> NVLink symmetric memory; reduction + LAMB become one kernel
+        except Exception as e:       # no P2P fabric / symmetric memory on this box: the NCCL backend still works
+            if rank == 0:
+                print(f"[bench] fused backend unavailable ({type(e).__name__}: {e}); falling back to nccl", file=sys.stderr)
+            comm = make_comm("nccl")
     ddp = DataParallel(model, comm=comm, arena=arena)
     named = list(model.named_parameters())
     groups = [{"params": [p for n, p in named if not any(k in n for k in NO_DECAY_KEYS)], "weight_decay": 0.01},

@@ -550,9 +550,13 @@ class FusedPretrainer:
         #      micro-step stays capturable), gradients accumulated straight into the arena views
         if self.has_nsp and next_sentence_labels is not None:
             pool, nsp = self.model.bert.pooler.dense_act, self.model.cls.seq_relationship
+            # weights from the bf16 shadow (what every other GEMM multiplies with; also the only copy that is
+            # complete on every rank when the fp32 master is kept shard-local), biases from the master copy
+            w_pool = A.shadow(eng.prefix + "pooler.dense_act.weight").float()
+            w_nsp = A.shadow("cls.seq_relationship.weight").float()
             cls_tok = seq.view(B, S, H)[:, 0].float()
-            pooled = torch.tanh(torch.addmm(pool.bias, cls_tok, pool.weight.t()))
-            nsp_logits = torch.addmm(nsp.bias, pooled, nsp.weight.t())
+            pooled = torch.tanh(torch.addmm(pool.bias, cls_tok, w_pool.t()))
+            nsp_logits = torch.addmm(nsp.bias, pooled, w_nsp.t())
             tgt_n = next_sentence_labels.long().view(-1)
             valid = (tgt_n >= 0).float()
             n_valid = valid.sum().clamp_(min=1.0)
@@ -562,10 +566,10 @@ class FusedPretrainer:
             d_logits = (logp.exp() - onehot) * (valid / n_valid * grad_scale).unsqueeze(1)
             nsp.weight.grad.addmm_(d_logits.t(), pooled)
             nsp.bias.grad.add_(d_logits.sum(0))
-            d_z = (d_logits @ nsp.weight) * (1.0 - pooled * pooled)
+            d_z = (d_logits @ w_nsp) * (1.0 - pooled * pooled)
             pool.weight.grad.addmm_(d_z.t(), cls_tok)
             pool.bias.grad.add_(d_z.sum(0))
-            d_seq.view(B, S, H)[:, 0] += (d_z @ pool.weight).to(torch.bfloat16)
+            d_seq.view(B, S, H)[:, 0] += (d_z @ w_pool).to(torch.bfloat16)
             loss = loss + nsp_loss
 
         eng.backward(sv, d_seq)

@@ -137,13 +137,21 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_allreduce_lamb_kernel(
         asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
                      : "=f"(acc.x), "=f"(acc.y), "=f"(acc.z), "=f"(acc.w) : "l"(a.grad_mc + off) : "memory");
       } else {
+        // four peers' loads in flight per thread before the first add (NVLink latency is ~2 us: a dependent
+        // load-add chain leaves the links idle); fixed rank order keeps the sum bitwise identical on every rank
         acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
-        for (int p = 0; p < a.world; ++p) {           // fixed rank order: bitwise identical on every rank
-          float4 g;
-          asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];"
-                       : "=f"(g.x), "=f"(g.y), "=f"(g.z), "=f"(g.w) : "l"(a.grad[p] + off) : "memory");
-          acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+        for (int p0 = 0; p0 < a.world; p0 += 4) {
+          float4 g[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            g[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p0 + j < a.world)
+              asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(g[j].x), "=f"(g[j].y), "=f"(g[j].z), "=f"(g[j].w) : "l"(a.grad[p0 + j] + off) : "memory");
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { acc.x += g[j].x; acc.y += g[j].y; acc.z += g[j].z; acc.w += g[j].w; }
         }
       }
       acc.x *= a.grad_mul; acc.y *= a.grad_mul; acc.z *= a.grad_mul; acc.w *= a.grad_mul;
@@ -268,6 +276,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_allreduce_lamb_kernel(
       }
       __syncthreads();
       const float ratio = s_bcast[0];
+      // 1-D tensors (biases, LayerNorm) always travel in fp32: the engine reads LayerNorm parameters from the master copy
+      const bool push_f32 = a.push_master || !a.decay_flag[t];
       const int nv = (off & 3) ? 0 : (n >> 2);
       for (int i = threadIdx.x; i < nv; i += blockDim.x) {
         const long long o = off + 4 * i;
@@ -277,10 +287,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_allreduce_lamb_kernel(
         np.x = pp.x - ratio * u.x; np.y = pp.y - ratio * u.y; np.z = pp.z - ratio * u.z; np.w = pp.w - ratio * u.w;
         uint2 nb;
         nb.x = pack_bf16(np.x, np.y); nb.y = pack_bf16(np.z, np.w);
-        if (a.push_master && a.use_multicast) {
+        if (push_f32 && a.use_multicast) {
           asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.param_mc + o), "f"(np.x),
                        "f"(np.y), "f"(np.z), "f"(np.w) : "memory");
-        } else if (a.push_master) {
+        } else if (push_f32) {
 #pragma unroll 1
           for (int p = 0; p < a.world; ++p) *reinterpret_cast<float4*>(a.param[p] + o) = np;
         } else {
@@ -299,7 +309,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_allreduce_lamb_kernel(
         const __nv_bfloat16 nb = __float2bfloat16(np);
 #pragma unroll 1
         for (int p = 0; p < a.world; ++p) {
-          if (a.push_master || p == a.rank) a.param[p][off + i] = np;
+          if (push_f32 || p == a.rank) a.param[p][off + i] = np;
           a.shadow[p][off + i] = nb;
         }
       }
