@@ -23,7 +23,9 @@ _PAIR_ENABLED = os.environ.get("B200_GEMM_PAIR", "1") != "0"
 KERNEL_LAUNCHES = 0     # every wrapper bumps this: bench.py reports it as ``gpu_launches``
 
 
-STREAM_K = os.environ.get("B200_STREAM_K", "1") != "0"
+# stream-K weight gradients: measured slower than 2-4 way split-K on the BERT-large shapes (operands of
+# neighbouring clusters stop sharing L2 lines: profiles/gemm_bench_r1_v3_streamk.jsonl), so opt-in
+STREAM_K = os.environ.get("B200_STREAM_K", "0") == "1"
 
 
 def _count(n: int = 1) -> None:

@@ -106,8 +106,9 @@ def test_fp8_engine_tracks_bf16_engine():
         l8 = e8.forward_backward(ids, seg, mask, labels, nsl)
         assert abs(l16.item() - l8.item()) < 0.05 * abs(l16.item()), (step, l16.item(), l8.item())
         worst = 0.0
+        gmax = max(p.grad.float().abs().max().item() for p in model.parameters())
         for (n, p), q in zip(model.named_parameters(), model8.parameters()):
-            if p.grad.float().norm() < 1e-6:
+            if p.grad.float().abs().max().item() < 1e-3 * gmax:     # e.g. key.bias: exactly-zero true gradient
                 continue
             rel = ((p.grad - q.grad).float().norm() / p.grad.float().norm()).item()
             worst = max(worst, rel)

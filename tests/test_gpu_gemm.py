@@ -65,7 +65,7 @@ def test_gemm_tn_stream_k(M, N, K):
     K_.gemm(a, b, layout=K_.TN, epi=K_.EPI_ACCUM_F32, out=out, block_n=512, k_splits=-1)
     _check(out, base + a.float().t() @ b.float(), tol=1e-2)
     grad = torch.zeros(M, N, device="cuda")
-    K_.wgrad_accumulate(a, b, grad)                      # the engine's entry point picks stream-K by itself
+    K_.wgrad_accumulate(a, b, grad)                      # the engine's entry point (split-K heuristics)
     _check(grad, a.float().t() @ b.float(), tol=1e-2)
 
 
