@@ -175,6 +175,7 @@ def run_ours(args, ph, B, accum, rank, world, dev):
               {"params": [p for n, p in named if any(k in n for k in NO_DECAY_KEYS)], "weight_decay": 0.0}]
     opt = Lamb(groups, lr=ph["lr"])
     arena.bind_optimizer(opt)
+    pretrain.configure_fused_reduction(ddp)
     sched = PolyWarmUpScheduler(opt, warmup=ph["warmup"], total_steps=ph["max_steps"])
     scaler = GradScaler(enabled=False)
     crit = BertPretrainingCriterion(cfg.vocab_size)

@@ -178,6 +178,17 @@ class FusedEncoderEngine:
             self._w8[key] = ent
         return ent[0]
 
+    def gemm_reduced_parameters(self) -> List[str]:
+        """Arena names of the parameters whose whole gradient comes out of fp32-accumulate GEMMs of this engine
+        (candidates for the GEMM -> reduce-scatter fusion of the peer-memory backend)."""
+        out = []
+        for l in range(self.L):
+            pre = f"{self.prefix}encoder.layer.{l}."
+            out += [pre + "attention.self.query.weight", pre + "attention.self.key.weight",
+                    pre + "attention.self.value.weight", pre + "attention.output.dense.weight",
+                    pre + "intermediate.dense_act.weight", pre + "output.dense.weight"]
+        return out
+
     def prepare_step(self) -> None:
         """Host-side work that must not happen inside a captured graph: refresh the fp8 weight copies when the
         optimizer has changed the weights (once per optimizer step)."""
@@ -452,6 +463,7 @@ class FusedPretrainer:
         self.graph_warmup = 2                 # eager calls per input signature before capturing
         self._graphs: Dict[tuple, dict] = {}
         self._seed_step: Optional[torch.Tensor] = None
+        self.grad_push = False                # set by the runtime around the last micro-step (PeerComm.begin_push)
 
     def _max_pred(self, labels: torch.Tensor) -> int:
         # capacity of masked positions per sequence; fixed per run so shapes stay static
@@ -476,7 +488,8 @@ class FusedPretrainer:
         args = (input_ids, segment_ids, input_mask, masked_lm_labels, next_sentence_labels)
         key = (tuple(input_ids.shape), self.model.training, next_sentence_labels is not None,
                segment_ids is not None, tuple(str(t.dtype) for t in args if t is not None),
-               bool(getattr(self.model.bert.encoder, "_checkpoint_activations", False)), self.engine.fp8)
+               bool(getattr(self.model.bert.encoder, "_checkpoint_activations", False)), self.engine.fp8,
+               bool(self.grad_push))
         ent = self._graphs.setdefault(key, {"calls": 0})
         ent["calls"] += 1
         eng = self.engine
@@ -497,7 +510,8 @@ class FusedPretrainer:
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             n0 = K.KERNEL_LAUNCHES
-            with torch.cuda.graph(graph):
+            pool = next((e["graph"].pool() for e in self._graphs.values() if "graph" in e), None)
+            with torch.cuda.graph(graph, pool=pool):      # replays never overlap: all captures share one memory pool
                 self._seed_step.add_(1)
                 loss = self._program(*static, grad_scale, seed=eng._seed_base)
             ent.update(graph=graph, static=static, loss=loss, launches=K.KERNEL_LAUNCHES - n0, grad_scale=float(grad_scale))

@@ -34,6 +34,22 @@ void set_seed_step(c10::optional<Tensor> t) {
 }
 inline b200::Seed mk_seed(int64_t seed) { return b200::Seed{static_cast<unsigned long long>(seed), g_seed_step}; }
 
+// Gradient arenas in NVLink symmetric memory: once registered, every fp32-accumulate GEMM whose output lies inside
+// the local arena adds atomically (peers may be adding into it), and with `push` on the tile goes straight to
+// the owner rank's arena (GEMM -> reduce-scatter in one kernel).
+struct GradPeers {
+  int world = 0, rank = 0, push = 0;
+  int64_t numel = 0, per = 0;
+  float* base[16] = {};
+} g_grad_peers;
+void set_grad_peers(int64_t world, int64_t rank, std::vector<int64_t> ptrs, int64_t numel, int64_t per) {
+  TORCH_CHECK(world <= 16 && (int64_t)ptrs.size() == world, "set_grad_peers: <= 16 ranks, one pointer each");
+  g_grad_peers = GradPeers();
+  g_grad_peers.world = (int)world; g_grad_peers.rank = (int)rank; g_grad_peers.numel = numel; g_grad_peers.per = per;
+  for (int i = 0; i < world; ++i) g_grad_peers.base[i] = reinterpret_cast<float*>(ptrs[i]);
+}
+void set_grad_push(bool on) { g_grad_peers.push = on ? 1 : 0; }
+
 inline const void* opt_ptr(const c10::optional<Tensor>& t) { return t.has_value() && t->defined() ? t->data_ptr() : nullptr; }
 inline float* opt_f32(const c10::optional<Tensor>& t) {
   if (!t.has_value() || !t->defined()) return nullptr;
@@ -112,6 +128,15 @@ void gemm(Tensor a, Tensor b, Tensor out, int64_t layout, int64_t epi, c10::opti
   c.p_drop = (float)p_drop;
   c.seed = (unsigned long long)seed;
   c.seed_step = g_seed_step;
+  if (epi == b200::EPI_ACCUM_F32 && g_grad_peers.world > 1) {
+    const float* lo = g_grad_peers.base[g_grad_peers.rank];
+    const float* o = reinterpret_cast<const float*>(out.data_ptr());
+    if (o >= lo && o < lo + g_grad_peers.numel) {
+      c.peer_world = g_grad_peers.world; c.peer_rank = g_grad_peers.rank; c.peer_push = g_grad_peers.push;
+      c.peer_off = (long long)(o - lo); c.peer_per = g_grad_peers.per;
+      for (int i = 0; i < g_grad_peers.world; ++i) c.peer_base[i] = g_grad_peers.base[i];
+    }
+  }
   c.stream = (unsigned int)stream_id;
   b200::gemm_bf16(c, cur_stream());
 }
@@ -307,7 +332,7 @@ void fused_allreduce_lamb(int64_t rank, int64_t world, bool use_multicast, std::
                           Tensor chunk_len, Tensor decay_flag, Tensor stats, Tensor norms, Tensor grid_bar, int64_t epoch,
                           double grad_mul, double lr, double beta1, double beta2, double eps, double weight_decay,
                           double max_grad_norm, int64_t step, bool bias_correction, bool grad_averaging,
-                          bool adam_w_mode, bool use_nvlamb, bool push_master) {
+                          bool adam_w_mode, bool use_nvlamb, bool push_master, c10::optional<Tensor> prereduced) {
   TORCH_CHECK((int64_t)grad_ptrs.size() == world && world <= 16, "peer pointer lists must have `world` (<= 16) entries");
   TORCH_CHECK(lo % 4 == 0 && hi % 4 == 0 && numel % 4 == 0, "shard bounds must be multiples of 4 elements");
   c10::cuda::CUDAGuard guard(m.device());
@@ -334,6 +359,10 @@ void fused_allreduce_lamb(int64_t rank, int64_t world, bool use_multicast, std::
   L.weight_decay = (float)weight_decay; L.max_grad_norm = (float)max_grad_norm; L.step = (int)step;
   L.bias_correction = bias_correction; L.grad_averaging = grad_averaging; L.adam_w_mode = adam_w_mode;
   L.use_nvlamb = use_nvlamb; L.push_master = push_master ? 1 : 0;
+  if (prereduced.has_value() && prereduced->defined()) {
+    TORCH_CHECK(prereduced->scalar_type() == at::kInt && prereduced->numel() == decay_flag.numel(), "prereduced flags");
+    L.prereduced = prereduced->data_ptr<int>();
+  }
   b200::fused_allreduce_lamb(L, cur_stream());
 }
 
@@ -384,6 +413,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "bert_pytorch_b200 sm_100a kernels";
   m.def("gemm", &gemm);
   m.def("set_seed_step", &set_seed_step);
+  m.def("set_grad_peers", &set_grad_peers);
+  m.def("set_grad_push", &set_grad_push);
   m.def("peer_allreduce", &peer_allreduce);
   m.def("fp8_quantize", &fp8_quantize);
   m.def("fp8_amax", &fp8_amax);

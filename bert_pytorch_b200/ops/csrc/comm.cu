@@ -44,6 +44,7 @@ struct FusedLambArgs {
   const int* chunk_len;
   int nchunks, ntensors;
   const int* decay_flag;
+  const int* prereduced;                  // per tensor: gradient already summed into the owner's arena (or null)
   float* stats;                           // local [4]: sumsq, found_inf, global sumsq, global inf
   float* norms;                           // local [2T] partial norms
   unsigned int* grid_bar;                 // local grid barrier counter (zeroed before launch)
@@ -126,14 +127,17 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_allreduce_lamb_kernel(
   grid_sync(a.grid_bar, gen);
 
   // ---- phase A: reduce-scatter the own shard
+  // Tensors flagged `prereduced` already hold the sum over the ranks in the owner's arena: their weight-gradient
+  // GEMMs of the last micro-step added every tile (plus the locally accumulated value) straight into the owner's
+  // arena over NVLink (gemm_sm100.cu, peer_push) -- the reduce-scatter happened inside the backward pass.
   {
-    const long long n4 = (a.hi - a.lo) >> 2;
     float sq = 0.f;
     bool bad = false;
-    for (long long i = gtid; i < n4; i += gstride) {
-      const long long off = a.lo + (i << 2);
+    auto reduce4 = [&](long long off, bool local_only) -> float4 {
       float4 acc;
-      if (a.use_multicast) {
+      if (local_only) {
+        acc = *reinterpret_cast<const float4*>(lgrad + off);
+      } else if (a.use_multicast) {
         asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
                      : "=f"(acc.x), "=f"(acc.y), "=f"(acc.z), "=f"(acc.w) : "l"(a.grad_mc + off) : "memory");
       } else {
@@ -159,6 +163,33 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_allreduce_lamb_kernel(
       bad |= !isfinite(q);
       sq += q;
       *reinterpret_cast<float4*>(lgrad + off) = acc;   // own shard: no peer reads this region
+      return acc;
+    };
+    if (a.prereduced == nullptr) {
+      const long long n4 = (a.hi - a.lo) >> 2;
+      for (long long i = gtid; i < n4; i += gstride) reduce4(a.lo + (i << 2), false);
+    } else {
+      for (int c = blockIdx.x; c < a.nchunks; c += gridDim.x) {
+        const long long off = a.chunk_start[c];
+        const int n = a.chunk_len[c];
+        const bool local_only = a.prereduced[a.chunk_tensor[c]] != 0;
+        const int nv = (off & 3) ? 0 : (n >> 2);
+        for (int i = threadIdx.x; i < nv; i += blockDim.x) reduce4(off + 4 * i, local_only);
+        for (int i = 4 * nv + threadIdx.x; i < n; i += blockDim.x) {      // odd tails (e.g. the 2-element NSP bias)
+          float acc = 0.f;
+          if (local_only) acc = lgrad[off + i];
+          else
+            for (int p = 0; p < a.world; ++p) {
+              float g;
+              asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(g) : "l"(a.grad[p] + off + i) : "memory");
+              acc += g;
+            }
+          acc *= a.grad_mul;
+          bad |= !isfinite(acc);
+          sq += acc * acc;
+          lgrad[off + i] = acc;
+        }
+      }
     }
     sq = block_sum_f(sq, sm);
     if (threadIdx.x == 0) atomicAdd(a.stats, sq);
@@ -341,7 +372,7 @@ void fused_allreduce_lamb(const FusedLambLaunch& L, cudaStream_t st) {
   a.grad_mc = (float*)L.grad_mc; a.param_mc = (float*)L.param_mc; a.shadow_mc = (__nv_bfloat16*)L.shadow_mc;
   a.m = L.m; a.v = L.v; a.numel = L.numel; a.lo = L.lo; a.hi = L.hi;
   a.chunk_tensor = L.chunk_tensor; a.chunk_start = L.chunk_start; a.chunk_len = L.chunk_len;
-  a.nchunks = L.nchunks; a.ntensors = L.ntensors; a.decay_flag = L.decay_flag;
+  a.nchunks = L.nchunks; a.ntensors = L.ntensors; a.decay_flag = L.decay_flag; a.prereduced = L.prereduced;
   a.stats = L.stats; a.norms = L.norms; a.grid_bar = L.grid_bar; a.epoch = L.epoch;
   a.grad_mul = L.grad_mul;
   a.lr = L.lr; a.beta1 = L.beta1; a.beta2 = L.beta2; a.beta3 = L.grad_averaging ? 1.f - L.beta1 : 1.f;

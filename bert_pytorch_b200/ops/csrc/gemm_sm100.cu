@@ -64,13 +64,21 @@ struct GemmArgs {
   const float* scale_b;
   unsigned int fp8_fmt;      // bit0: A is e5m2 (else e4m3), bit1: B is e5m2
   int stream_k;              // pair kernel: contiguous (tile, k-block) ranges per cluster instead of whole tiles
+  // GEMM -> reduce-scatter fusion (EPI_ACCUM_F32 into a gradient arena that lives in NVLink symmetric memory):
+  // peer_world > 1 makes every accumulation atomic (peers add into this arena concurrently); peer_push adds the
+  // tile -- plus, once per tile, the locally accumulated value -- straight into the arena of the rank that owns
+  // that shard, so the gradient is reduced tile by tile while the backward pass is still running.
+  int peer_world, peer_rank, peer_push;
+  long long peer_off;        // element offset of `out` inside the arena
+  long long peer_per;        // shard size in elements: owner(e) = min(e / peer_per, world - 1)
+  float* peer_base[16];      // gradient arena of every rank (symmetric-memory mapping)
 };
 
 // Drain one 128 x BLOCK_N fp32 accumulator tile (this warp's 32 TMEM lanes) through the selected epilogue.
 // `taddr` already carries the lane quarter; `row` is this thread's global output row.
 template <int BLOCK_N>
 __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint32_t taddr, int row, bool row_ok, int n_base,
-                                              int c_begin, int c_end, float alpha, unsigned long long seed) {
+                                              int c_begin, int c_end, float alpha, unsigned long long seed, bool add_local = true) {
   #pragma unroll 1
   for (int c = c_begin; c < c_end; ++c) {
     const int n0 = n_base + c * 32;
@@ -88,6 +96,32 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint32_t taddr,
     if (p.epi == EPI_ACCUM_F32) {
       if (row_ok) {
         float* o = reinterpret_cast<float*>(p.out) + ooff;
+        if (p.peer_world > 1) {
+          // a 32-column chunk crosses at most one shard boundary (shards are multiples of 2048 elements)
+          const long long e0 = p.peer_off + (long long)ooff;
+          const int own0 = (int)min((long long)(p.peer_world - 1), e0 / p.peer_per);
+          const long long bound = own0 + 1 < p.peer_world ? (long long)(own0 + 1) * p.peer_per : (1ll << 62);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (j < ncols) {
+              const int owner = (e0 + j >= bound) ? own0 + 1 : own0;
+              if (!p.peer_push || owner == p.peer_rank) {
+                asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j), "f"(f[j]),
+                             "f"(f[j + 1]), "f"(f[j + 2]), "f"(f[j + 3]) : "memory");
+              } else {
+                float4 v = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                if (add_local) {                       // what the earlier micro-steps accumulated here
+                  const float4 cur = *reinterpret_cast<const float4*>(o + j);
+                  v.x += cur.x; v.y += cur.y; v.z += cur.z; v.w += cur.w;
+                }
+                float* dst = p.peer_base[owner] + (e0 + j);
+                asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y),
+                             "f"(v.z), "f"(v.w) : "memory");
+              }
+            }
+          }
+          continue;
+        }
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           if (j < ncols) {
@@ -314,7 +348,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const int row = mb * BLOCK_M + q * 32 + lane;
       const bool row_ok = row < p.M && kb1 > kb0;
       const uint32_t taddr = tmem_base + as * BLOCK_N + (uint32_t(q * 32) << 16);
-      epilogue_tile<BLOCK_N>(p, taddr, row, row_ok, nb * BLOCK_N, half * CH, half * CH + CH, p.alpha, seed);
+      epilogue_tile<BLOCK_N>(p, taddr, row, row_ok, nb * BLOCK_N, half * CH, half * CH + CH, p.alpha, seed, ks == 0);
       tc_fence_before();
       mbar_arrive(&tmem_empty[as]);
     }
@@ -618,7 +652,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (use_res && issuer && nseg > 0) load_res(seg_get(p, cluster_id, nclusters, 0).mn);
     uint32_t tile_it = 0, c_phase = 0;
     for (int si = 0; si < nseg; ++si, ++tile_it) {
-      const int mn = seg_get(p, cluster_id, nclusters, si).mn;
+      const WorkSeg wseg = seg_get(p, cluster_id, nclusters, si);
+      const int mn = wseg.mn;
       const int nb = mn % p.n_blocks, mb = mn / p.n_blocks;
       const uint32_t as = tile_it & 1, aph = (tile_it >> 1) & 1;
       mbar_wait(&tmem_full[as], aph);
@@ -627,7 +662,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int row = row0 + r;
       const uint32_t taddr = tmem_base + as * PAIR_N + (uint32_t(q * 32) << 16);
       if (!staged) {
-        epilogue_tile<PAIR_N>(p, taddr, row, row < p.M, nb * PAIR_N, half * 4, half * 4 + 4, alpha, seed);
+        epilogue_tile<PAIR_N>(p, taddr, row, row < p.M, nb * PAIR_N, half * 4, half * 4 + 4, alpha, seed, wseg.kb0 == 0);
         tc_fence_before();
         mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), 0));
         continue;
@@ -761,6 +796,12 @@ static int num_sms() {
   return n;
 }
 
+static void fill_peer(GemmArgs& p, const GemmCall& c) {
+  p.peer_world = c.peer_world; p.peer_rank = c.peer_rank; p.peer_push = c.peer_push;
+  p.peer_off = c.peer_off; p.peer_per = c.peer_per;
+  for (int i = 0; i < 16; ++i) p.peer_base[i] = i < c.peer_world ? c.peer_base[i] : nullptr;
+}
+
 template <bool A_MN, bool B_MN, int BLOCK_N>
 static void launch(const GemmCall& c, cudaStream_t st) {
   using C = Cfg<BLOCK_N>;
@@ -782,6 +823,7 @@ static void launch(const GemmCall& c, cudaStream_t st) {
   p.drop_thresh16 = pd > 0.f ? (unsigned)(pd * 65536.f + 0.5f) : 0u;
   p.drop_scale = pd > 0.f ? 65536.f / (65536.f - (float)p.drop_thresh16) : 1.f;
   p.alpha = c.alpha;
+  fill_peer(p, c);
   p.scale_a = nullptr; p.scale_b = nullptr; p.fp8_fmt = 0; p.stream_k = 0;
   // operand maps
   CUtensorMap ta = A_MN ? make_tmap_2d_bf16(c.A, c.M, c.K, c.lda, 64, BLOCK_K)
@@ -821,6 +863,7 @@ static void launch_pair(const GemmCall& c, cudaStream_t st) {
   p.drop_thresh16 = pd > 0.f ? (unsigned)(pd * 65536.f + 0.5f) : 0u;
   p.drop_scale = pd > 0.f ? 65536.f / (65536.f - (float)p.drop_thresh16) : 1.f;
   p.alpha = c.alpha;
+  fill_peer(p, c);
   // k_splits < 0 asks for stream-K (fp32 accumulate epilogue only): equal MMA work per cluster, pieces merged by
   // red.global.add.  Needs enough k-blocks per cluster to amortise the extra partial tiles.
   p.stream_k = 0;

@@ -44,6 +44,10 @@ struct GemmCall {
   bool fp8 = false, a_e5m2 = false, b_e5m2 = false;
   const float* scale_a = nullptr;
   const float* scale_b = nullptr;
+  // EPI_ACCUM_F32 into a gradient arena shared over NVLink (see GemmArgs::peer_*)
+  int peer_world = 0, peer_rank = 0, peer_push = 0;
+  long long peer_off = 0, peer_per = 0;
+  float* peer_base[16] = {};
 };
 
 void gemm_bf16(const GemmCall& c, cudaStream_t st);

@@ -65,6 +65,7 @@ struct FusedLambLaunch {
   long long numel, lo, hi;
   const int* chunk_tensor; const long long* chunk_start; const int* chunk_len; int nchunks, ntensors;
   const int* decay_flag;
+  const int* prereduced = nullptr;   // per tensor flags: already reduced into the owner's arena by the wgrad GEMMs
   float* stats; float* norms; unsigned int* grid_bar;
   unsigned int epoch;
   float grad_mul, lr, beta1, beta2, eps, weight_decay, max_grad_norm;

@@ -78,8 +78,8 @@ class DataParallel(nn.Module):
         ``backward``)."""
         if self.comm.world_size == 1 or not self.require_sync:
             return
-        if getattr(self.comm, "fuses_optimizer", False):
-            return  # the fused step reduces inside the optimizer kernels
+        if getattr(self.comm, "fuses_optimizer", False) and getattr(self, "defer_reduction", False):
+            return  # the runtime reduces inside the fused optimizer kernel (PeerComm.fused_lamb_step)
         if self.arena is not None:
             flat = self.arena.flat_grad
             n = flat.numel()

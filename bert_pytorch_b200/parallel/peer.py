@@ -99,11 +99,42 @@ class PeerComm(TorchComm):
         self.chunk_tensor = torch.tensor(ct, dtype=torch.int32, device=dev)
         self.chunk_start = torch.tensor(cs, dtype=torch.int64, device=dev)
         self.chunk_len = torch.tensor(cl, dtype=torch.int32, device=dev)
+        # GEMM -> reduce-scatter fusion: register the gradient arenas with the GEMM launcher.  From now on every
+        # fp32-accumulate GEMM into the local arena adds atomically, and between begin_push()/end_push() its tiles
+        # go straight into the owner rank's arena (ops/csrc/gemm_sm100.cu, peer_push).
+        per = (arena.numel + self.world_size - 1) // self.world_size
+        per = (per + GRANULE - 1) // GRANULE * GRANULE
+        from .. import ops
+        ops.extension().set_grad_peers(self.world_size, self.rank, list(self.grad_h.buffer_ptrs), arena.numel, per)
+        self._prereduced = None               # int32 [T]: tensors whose reduction happens inside the backward
+        self._pushed = False
         self.stats = torch.zeros(4, dtype=torch.float32, device=dev)
         self.norms = torch.zeros(2 * T, dtype=torch.float32, device=dev)
         self.grid_bar = torch.zeros(1, dtype=torch.int32, device=dev)
         dist.barrier(group=self.group)
         torch.cuda.synchronize()
+
+    # -- GEMM -> reduce-scatter fusion -------------------------------------------------------------------
+    def set_prereduced(self, names) -> None:
+        """Names of the tensors whose ENTIRE gradient is produced by fp32-accumulate GEMMs (the engine's
+        weight-gradient launches): with push mode on in the last micro-step they arrive fully reduced at
+        their owner and the fused step skips their peer reads."""
+        names = set(names)
+        flags = [1 if s.name in names else 0 for s in self.arena.slots]
+        self._prereduced = torch.tensor(flags, dtype=torch.int32, device=self.device) if any(flags) else None
+
+    def begin_push(self) -> bool:
+        """Call before the forward/backward of the LAST micro-step of an optimizer step."""
+        if self._prereduced is None:
+            return False
+        from .. import ops
+        ops.extension().set_grad_push(True)
+        self._pushed = True
+        return True
+
+    def end_push(self) -> None:
+        from .. import ops
+        ops.extension().set_grad_push(False)
 
     # -- the fused step ------------------------------------------------------------------------------
     @torch.no_grad()
@@ -136,7 +167,8 @@ class PeerComm(TorchComm):
             float(lr), float(b1), float(b2), float(_uniform(optimizer, "eps")), wd,
             float(_uniform(optimizer, "max_grad_norm") or 0.0), step, bool(_uniform(optimizer, "bias_correction")),
             bool(_uniform(optimizer, "grad_averaging")), bool(optimizer.adam_w_mode), bool(optimizer.use_nvlamb),
-            self.push_master)
+            self.push_master, self._prereduced if self._pushed else None)
+        self._pushed = False
         self._master_stale = not self.push_master
         A.version += 1
         ops.api._count()

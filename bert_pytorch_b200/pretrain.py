@@ -236,7 +236,23 @@ def prepare_optimizers(args, model, checkpoint, global_steps):
             preconditioner.load_state_dict(checkpoint["preconditioner"])
         if is_main_process():
             logger.info(preconditioner)
+    configure_fused_reduction(model, preconditioner)
     return optimizer, preconditioner, lr_schedulers, scaler
+
+
+def configure_fused_reduction(model, preconditioner=None) -> None:
+    """Peer-memory backend: the gradient reduction is deferred into the fused LAMB kernel, and the engine's
+    weight-gradient GEMMs of the last micro-step reduce-scatter straight into the owner ranks' arenas
+    (``B200_PEER_PUSH=0`` keeps the reduction entirely inside the optimizer kernel).  With a preconditioner
+    (K-FAC needs the averaged gradients before the optimizer) the reduction stays a separate all-reduce."""
+    comm = getattr(model, "comm", None)
+    if comm is None or not getattr(comm, "fuses_optimizer", False):
+        return
+    model.defer_reduction = preconditioner is None
+    base = unwrap(model)
+    eng = base.pretrain_engine() if hasattr(base, "pretrain_engine") else None
+    if model.defer_reduction and eng is not None and os.environ.get("B200_PEER_PUSH", "1") != "0":
+        comm.set_prereduced(eng.engine.gemm_reduced_parameters())
 
 
 def find_input_files(input_dir: str) -> List[str]:
@@ -312,8 +328,17 @@ def forward_backward_pass(model, criterion, scaler, batch, divisor, sync_grads=T
     loss_scale = scaler.get_scale() if (scaler is not None and scaler.is_enabled()) else 1.0
     if engine is not None:
         # fused sm_100a path: forward + backward in one call, grads accumulate into the arena
-        loss = engine.forward_backward(input_ids, segment_ids, input_mask, masked_lm_labels,
-                                       next_sentence_labels, grad_scale=loss_scale / divisor)
+        comm = getattr(model, "comm", None)
+        push = (sync_grads and comm is not None and getattr(model, "defer_reduction", False)
+                and hasattr(comm, "begin_push") and comm.begin_push())
+        engine.grad_push = bool(push)       # last micro-step: weight-gradient GEMMs reduce-scatter over NVLink
+        try:
+            loss = engine.forward_backward(input_ids, segment_ids, input_mask, masked_lm_labels,
+                                           next_sentence_labels, grad_scale=loss_scale / divisor)
+        finally:
+            if push:
+                comm.end_push()
+                engine.grad_push = False
         loss = loss / divisor
     else:
         dev_type = input_ids.device.type

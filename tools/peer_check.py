@@ -98,6 +98,51 @@ def main():
             assert torch.equal(ref, a_f.flat_param), "ranks disagree after the fused step"
         out[f"max_abs_diff_mc{int(mc)}"] = worst
         out[f"grad_norm_mc{int(mc)}"] = float(comm.stats[2].sqrt())
+        # GEMM -> reduce-scatter fusion: two micro-steps of the real engine per optimizer step, the second one with
+        # its weight-gradient tiles pushed into the owners' arenas, against local accumulation + NCCL + LAMB
+        from bert_pytorch_b200.ops import api as K
+        ext = K.extension()
+        pcfg = BertConfig(vocab_size_or_config_json_file=2048, hidden_size=256, num_hidden_layers=2, num_attention_heads=4,
+                          intermediate_size=1024, max_position_embeddings=128, hidden_dropout_prob=0.0,
+                          attention_probs_dropout_prob=0.0)
+        pcfg.max_predictions_per_seq = 16
+        m_p, a_p, o_p, comm_p = build(pcfg, dev, True, use_mc=mc)
+        m_q, a_q, o_q, _ = build(pcfg, dev, False)
+        m_p.train(); m_q.train()
+        e_p, e_q = m_p.pretrain_engine(), m_q.pretrain_engine()
+        e_p.use_graphs = e_q.use_graphs = False
+        comm_p.set_prereduced(e_p.engine.gemm_reduced_parameters())
+        gen = torch.Generator(device=dev).manual_seed(4321 + rank)
+        push_worst = 0.0
+        for step in range(3):
+            for micro in range(2):
+                ids = torch.randint(5, 2048, (4, 64), device=dev, generator=gen)
+                seg = torch.zeros_like(ids); seg[:, 32:] = 1
+                mask = torch.ones_like(ids)
+                labels = torch.full_like(ids, -1)
+                pos = torch.randint(0, 64, (4, 10), device=dev, generator=gen)
+                labels.scatter_(1, pos, ids.gather(1, pos))
+                nsl = torch.randint(0, 2, (4,), device=dev, generator=gen)
+                e_q.forward_backward(ids, seg, mask, labels, nsl, grad_scale=0.5)
+                if micro == 1:
+                    assert comm_p.begin_push()
+                e_p.forward_backward(ids, seg, mask, labels, nsl, grad_scale=0.5)
+                if micro == 1:
+                    comm_p.end_push()
+            torch.cuda.synchronize(); dist.barrier()
+            comm_p.fused_lamb_step(o_p, loss_scale=1.0)
+            dist.all_reduce(a_q.flat_grad)
+            a_q.flat_grad.mul_(1.0 / world)
+            o_q.step()
+            a_q.zero_grad()
+            torch.cuda.synchronize()
+            push_worst = max(push_worst, (a_p.flat_param - a_q.flat_param).abs().max().item())
+            ref = a_p.flat_param.clone()
+            dist.broadcast(ref, src=0)
+            assert torch.equal(ref, a_p.flat_param), "ranks disagree after the pushed step"
+        out[f"push_max_abs_diff_mc{int(mc)}"] = push_worst
+        del comm_p, m_p, a_p, o_p, m_q, a_q, o_q, e_p, e_q
+        ext.set_grad_peers(0, 0, [], 0, 1)
         # general all-reduce through our own kernel (K-FAC factor path): odd sizes, packing, avg
         torch.manual_seed(77 + rank)
         ts = [torch.randn(1025, 1025, device=dev), torch.randn(7, device=dev), torch.randn(300, 64, device=dev).t()]
