@@ -202,27 +202,33 @@ class FusedEncoderEngine:
             self._weight8(l, "w1", self.w(pre + "intermediate.dense_act.weight"))
             self._weight8(l, "w2", self.w(pre + "output.dense.weight"))
 
-    def _lin(self, l: int, act_site: str, w_site: str, x: torch.Tensor, w: torch.Tensor, **kw):
-        """y = x @ w^T through the bf16 or the fp8 operand path; returns (y, saved operand for wgrad)."""
+    def _side(self, site: str):
+        """(meta, site) for a producer kernel's fused fp8 copy -- only once the scales are calibrated (delayed
+        scaling needs last step's amax; the first micro-step quantises in a separate pass)."""
+        return (self.meta, site) if (self.fp8 and self._fp8_calibrated) else None
+
+    def _lin(self, l: int, act_site: str, w_site: str, x: torch.Tensor, w: torch.Tensor, xq=None, **kw):
+        """y = x @ w^T through the bf16 or the fp8 operand path; returns (y, saved operand for wgrad).
+        ``xq``: fp8 copy of x already emitted by the kernel that produced x."""
         if not self.fp8:
             return K.gemm(x, w, **kw), x
-        qx = self.meta.quantize(x, f"{l}.{act_site}", calibrate=not self._fp8_calibrated)
+        qx = xq if xq is not None else self.meta.quantize(x, f"{l}.{act_site}", calibrate=not self._fp8_calibrated)
         qw = self._weight8(l, w_site, w)
         y = K.gemm(qx, qw, scale_a=self.meta.inv_scale(f"{l}.{act_site}"), scale_b=self.meta.inv_scale(f"{l}.{w_site}"), **kw)
         return y, qx
 
     def _lin_bwd(self, l: int, g_site: str, act_site: str, w_site: str, dy: torch.Tensor, x_saved: torch.Tensor,
-                 w: torch.Tensor, wgrad: torch.Tensor, **kw) -> torch.Tensor:
+                 w: torch.Tensor, wgrad: torch.Tensor, dyq=None, **kw) -> torch.Tensor:
         """dx = dy @ w (with the epilogue in ``kw``) and wgrad += dy^T @ x."""
         if not self.fp8:
             dx = K.gemm(dy, w, layout=K.NN, **kw)
-            K.wgrad_accumulate(dy, x_saved, wgrad)
+            K.wgrad_accumulate(dy, x_saved, wgrad, push=True)
             return dx
         m = self.meta
-        qdy = m.quantize(dy, f"{l}.{g_site}", calibrate=not self._fp8_calibrated)
+        qdy = dyq if dyq is not None else m.quantize(dy, f"{l}.{g_site}", calibrate=not self._fp8_calibrated)
         sg, sw, sx = m.inv_scale(f"{l}.{g_site}"), m.inv_scale(f"{l}.{w_site}"), m.inv_scale(f"{l}.{act_site}")
         dx = K.gemm(qdy, self._weight8(l, w_site, w), layout=K.NN, scale_a=sg, scale_b=sw, a_e5m2=True, **kw)
-        K.wgrad_accumulate(qdy, x_saved, wgrad, scale_a=sg, scale_b=sx, a_e5m2=True)
+        K.wgrad_accumulate(qdy, x_saved, wgrad, push=True, scale_a=sg, scale_b=sx, a_e5m2=True)
         return dx
 
     def next_seed(self) -> int:
@@ -264,20 +270,21 @@ class FusedEncoderEngine:
         for l in range(self.L):
             if ckpt and l % seg_len == 0:
                 sv.boundaries[l] = x             # --checkpoint_activations: keep segment inputs only (K27)
-            x, ls = self._layer_forward(l, x, seqlens, B, S, ph, pa, seed, save=training and not ckpt)
+            x, ls, xq = self._layer_forward(l, x, seqlens, B, S, ph, pa, seed, save=training and not ckpt,
+                                            xq=None if (l == 0 or (ckpt and l % seg_len == 0)) else xq)
             if ls is not None:
                 sv.layers.append(ls)
         if ckpt:
             sv.seg_len = seg_len
         return x, sv
 
-    def _layer_forward(self, l: int, x, seqlens, B: int, S: int, ph: float, pa: float, seed: int, save: bool):
+    def _layer_forward(self, l: int, x, seqlens, B: int, S: int, ph: float, pa: float, seed: int, save: bool, xq=None):
         """One post-LN transformer layer (reference: src/modeling.py:482-499) as 9 kernel launches."""
         A, H, M = self.arena, self.H, B * S
         training = save or pa > 0 or ph > 0
         pre = f"encoder.layer.{l}."
         ls = _LayerSaved() if save else None
-        qkv, x_op = self._lin(l, "x", "wqkv", x, self._qkv(l, A.flat_shadow, "weight"), epi=K.EPI_BIAS,
+        qkv, x_op = self._lin(l, "x", "wqkv", x, self._qkv(l, A.flat_shadow, "weight"), xq=xq, epi=K.EPI_BIAS,
                               bias=self._qkv(l, A.flat_shadow, "bias"))
         if _use_sdpa():
             ctx, lse, sd = self._sdpa_fwd(qkv, seqlens, B, S, pa, training)
@@ -290,23 +297,28 @@ class FusedEncoderEngine:
         pre1, ctx_op = self._lin(l, "ctx", "wo", ctx, self.w(pre + "attention.output.dense.weight"),
                                  epi=K.EPI_BIAS_DROP_RES, bias=self.w(pre + "attention.output.dense.bias"), res=x,
                                  p_drop=ph, seed=seed, stream=_stream(l, SITE_ATTN_OUT))
-        x1, mean1, rstd1 = K.layer_norm_fwd(pre1, self.p(pre + "attention.output.LayerNorm.weight"),
-                                            self.p(pre + "attention.output.LayerNorm.bias"), save_stats=save)
+        # producers emit the fp8 copy of their output for the next GEMM (no separate quantise pass)
+        x1, mean1, rstd1, *q = K.layer_norm_fwd(pre1, self.p(pre + "attention.output.LayerNorm.weight"),
+                                                self.p(pre + "attention.output.LayerNorm.bias"), save_stats=save,
+                                                fp8=self._side(f"{l}.x1"))
         # GELU runs as its own bandwidth kernel: with K = 1024 it does not fit under the GEMM main loop
-        y1, x1_op = self._lin(l, "x1", "w1", x1, self.w(pre + "intermediate.dense_act.weight"), epi=K.EPI_BIAS,
-                              bias=self.w(pre + "intermediate.dense_act.bias"))
-        act = K.gelu_fwd(y1)
-        pre2, act_op = self._lin(l, "act", "w2", act, self.w(pre + "output.dense.weight"), epi=K.EPI_BIAS_DROP_RES,
-                                 bias=self.w(pre + "output.dense.bias"), res=x1, p_drop=ph, seed=seed,
-                                 stream=_stream(l, SITE_FFN_OUT))
-        x2, mean2, rstd2 = K.layer_norm_fwd(pre2, self.p(pre + "output.LayerNorm.weight"),
-                                            self.p(pre + "output.LayerNorm.bias"), save_stats=save)
+        y1, x1_op = self._lin(l, "x1", "w1", x1, self.w(pre + "intermediate.dense_act.weight"), xq=q[0] if q else None,
+                              epi=K.EPI_BIAS, bias=self.w(pre + "intermediate.dense_act.bias"))
+        side = self._side(f"{l}.act")
+        act, *q = K.gelu_fwd(y1, fp8=side) if side else (K.gelu_fwd(y1),)
+        pre2, act_op = self._lin(l, "act", "w2", act, self.w(pre + "output.dense.weight"), xq=q[0] if q else None,
+                                 epi=K.EPI_BIAS_DROP_RES, bias=self.w(pre + "output.dense.bias"), res=x1, p_drop=ph,
+                                 seed=seed, stream=_stream(l, SITE_FFN_OUT))
+        x2, mean2, rstd2, *q = K.layer_norm_fwd(pre2, self.p(pre + "output.LayerNorm.weight"),
+                                                self.p(pre + "output.LayerNorm.bias"), save_stats=save,
+                                                fp8=self._side(f"{l + 1}.x") if l + 1 < self.L else None)
+        x2q = q[0] if q else None
         if save:
             ls.x, ls.qkv, ls.ctx, ls.lse = x, qkv, ctx, lse
             ls.pre1, ls.mean1, ls.rstd1, ls.x1 = pre1, mean1, rstd1, x1
             ls.y1, ls.act, ls.pre2, ls.mean2, ls.rstd2 = y1, act, pre2, mean2, rstd2
             ls.x_op, ls.ctx_op, ls.x1_op, ls.act_op = x_op, ctx_op, x1_op, act_op   # wgrad operands (fp8 or bf16)
-        return x2, ls
+        return x2, ls, x2q
 
     # -- backward -------------------------------------------------------------------------------
     @torch.no_grad()
@@ -320,9 +332,9 @@ class FusedEncoderEngine:
         if sv.seg_len:                                    # recompute each segment from its saved input, then walk it back
             for lo in reversed(range(0, self.L, sv.seg_len)):
                 hi = min(self.L, lo + sv.seg_len)
-                x, saved = sv.boundaries.pop(lo), []
+                x, saved, xq = sv.boundaries.pop(lo), [], None
                 for l in range(lo, hi):                   # same seed -> same Philox dropout masks as the first pass
-                    x, ls = self._layer_forward(l, x, sv.seqlens, sv.B, sv.S, ph, pa, seed, save=True)
+                    x, ls, xq = self._layer_forward(l, x, sv.seqlens, sv.B, sv.S, ph, pa, seed, save=True, xq=xq)
                     saved.append(ls)
                 for l in reversed(range(lo, hi)):
                     d = self._layer_backward(l, saved[l - lo], d, sv, kfac)
@@ -348,32 +360,35 @@ class FusedEncoderEngine:
         ph, pa, seed = sv.p_hidden, sv.p_attn, sv.seed
         pre = f"encoder.layer.{l}."
         # ---- LN2 -> (residual grad, dropped grad of the FFN-2 output)
-        d_pre2, d_y2 = K.layer_norm_bwd(
+        d_pre2, d_y2, *q = K.layer_norm_bwd(
             d, ls.pre2, ls.mean2, ls.rstd2, self.p(pre + "output.LayerNorm.weight"),
             dgamma=self.g(pre + "output.LayerNorm.weight"), dbeta=self.g(pre + "output.LayerNorm.bias"),
             dbias=self.g(pre + "output.dense.bias"), want_dropped=True, p_drop=ph, seed=seed,
-            drop_stream=_stream(l, SITE_FFN_OUT))
+            drop_stream=_stream(l, SITE_FFN_OUT), fp8=self._side(f"{l}.d_y2"))
         if kfac is not None:
             kfac.tap(self.prefix + pre + "output.dense", ls.act, d_y2)
         # ---- FFN-2
         d_act = self._lin_bwd(l, "d_y2", "act", "w2", d_y2, ls.act_op, self.w(pre + "output.dense.weight"),
-                              self.g(pre + "output.dense.weight"))
+                              self.g(pre + "output.dense.weight"), dyq=q[0] if q else None)
         # ---- FFN-1 (GELU' and the bias gradient in one bandwidth pass)
-        d_y1 = K.dgelu_bwd(d_act, ls.y1, self.g(pre + "intermediate.dense_act.bias"))
+        side = self._side(f"{l}.d_y1")
+        d_y1, *q = (K.dgelu_bwd(d_act, ls.y1, self.g(pre + "intermediate.dense_act.bias"), fp8=side) if side
+                    else (K.dgelu_bwd(d_act, ls.y1, self.g(pre + "intermediate.dense_act.bias")),))
         d_x1 = self._lin_bwd(l, "d_y1", "x1", "w1", d_y1, ls.x1_op, self.w(pre + "intermediate.dense_act.weight"),
-                             self.g(pre + "intermediate.dense_act.weight"), epi=K.EPI_ADD, res=d_pre2)
+                             self.g(pre + "intermediate.dense_act.weight"), dyq=q[0] if q else None,
+                             epi=K.EPI_ADD, res=d_pre2)
         # ---- LN1
-        d_pre1, d_yo = K.layer_norm_bwd(
+        d_pre1, d_yo, *q = K.layer_norm_bwd(
             d_x1, ls.pre1, ls.mean1, ls.rstd1, self.p(pre + "attention.output.LayerNorm.weight"),
             dgamma=self.g(pre + "attention.output.LayerNorm.weight"),
             dbeta=self.g(pre + "attention.output.LayerNorm.bias"),
             dbias=self.g(pre + "attention.output.dense.bias"), want_dropped=True, p_drop=ph, seed=seed,
-            drop_stream=_stream(l, SITE_ATTN_OUT))
+            drop_stream=_stream(l, SITE_ATTN_OUT), fp8=self._side(f"{l}.d_yo"))
         if kfac is not None:
             kfac.tap(self.prefix + pre + "attention.output.dense", ls.ctx, d_yo)
         # ---- attention output projection
         d_ctx = self._lin_bwd(l, "d_yo", "ctx", "wo", d_yo, ls.ctx_op, self.w(pre + "attention.output.dense.weight"),
-                              self.g(pre + "attention.output.dense.weight"))
+                              self.g(pre + "attention.output.dense.weight"), dyq=q[0] if q else None)
         # ---- attention core
         if ls.sdpa is not None:
             d_qkv = self._sdpa_bwd(ls.sdpa, d_ctx, sv.B, sv.S)

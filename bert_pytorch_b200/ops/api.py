@@ -55,7 +55,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, layout: int = NT, epi: int = EPI_N
          res: Optional[torch.Tensor] = None, aux_out: Optional[torch.Tensor] = None, k_splits: int = 1,
          block_n: Optional[int] = None, alpha: float = 1.0, p_drop: float = 0.0, seed: int = 0,
          stream: int = 0, scale_a: Optional[torch.Tensor] = None, scale_b: Optional[torch.Tensor] = None,
-         a_e5m2: bool = False, b_e5m2: bool = False) -> torch.Tensor:
+         a_e5m2: bool = False, b_e5m2: bool = False, push: bool = False) -> torch.Tensor:
     """tcgen05 GEMM with a fused epilogue (see csrc/gemm_sm100.cu).  ``a``/``b`` are 2-D bf16, or -- with
     ``scale_a``/``scale_b`` (device inv-scale scalars from an :class:`Fp8Meta`) -- 1-byte fp8 tensors."""
     if layout == NT:
@@ -72,7 +72,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, layout: int = NT, epi: int = EPI_N
     elif block_n is None:
         block_n = _pick_block_n(M, N)
     extension().gemm(a, b, out, layout, epi, bias, res, aux_out, k_splits, block_n, alpha, p_drop, seed, stream,
-                     scale_a, scale_b, a_e5m2, b_e5m2)
+                     scale_a, scale_b, a_e5m2, b_e5m2, push)
     _count()
     return out
 
@@ -134,7 +134,8 @@ def wgrad_splits(n_out: int, k_out: int, reduce_len: int, block_n: int = 256) ->
     return max(1, min(want, kb // 4 if kb >= 8 else 1, 32))
 
 
-def wgrad_accumulate(dy: torch.Tensor, x: torch.Tensor, grad: torch.Tensor, alpha: float = 1.0, **fp8) -> None:
+def wgrad_accumulate(dy: torch.Tensor, x: torch.Tensor, grad: torch.Tensor, alpha: float = 1.0, push: bool = False,
+                     **fp8) -> None:
     """grad[N,K] (fp32, arena view) += dy[M,N]^T @ x[M,K]  (``fp8``: scale_a / scale_b / a_e5m2 for 1-byte operands)."""
     n_out, k_out = grad.shape
     bn = 512 if fp8 else _pick_block_n(n_out, k_out)
@@ -147,18 +148,29 @@ def wgrad_accumulate(dy: torch.Tensor, x: torch.Tensor, grad: torch.Tensor, alph
         kb = (dy.size(0) + (127 if fp8 else 63)) // (128 if fp8 else 64)
         if tiles % (NUM_SMS // 2) != 0 and tiles * kb >= 8 * (NUM_SMS // 2):
             splits = -1
-    gemm(dy, x, layout=TN, epi=EPI_ACCUM_F32, out=grad, block_n=bn, alpha=alpha, k_splits=splits, **fp8)
+    # ``push``: with the peer-memory backend in push mode the tiles go to the owner rank's arena (GEMM -> reduce-scatter)
+    gemm(dy, x, layout=TN, epi=EPI_ACCUM_F32, out=grad, block_n=bn, alpha=alpha, k_splits=splits, push=push, **fp8)
+
+
+def _fp8_side(fp8, like: torch.Tensor):
+    """``fp8`` = (Fp8Meta, site) -> (q tensor, meta record, e5m2) for a kernel's fused fp8 copy of its output."""
+    if fp8 is None:
+        return None, None, False
+    meta, site = fp8
+    return torch.empty(like.shape, dtype=torch.uint8, device=like.device), meta.record(site), meta.is_e5m2(site)
 
 
 def layer_norm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, eps: float = 1e-12,
-                   save_stats: bool = True, p_drop: float = 0.0, seed: int = 0, stream: int = 0):
+                   save_stats: bool = True, p_drop: float = 0.0, seed: int = 0, stream: int = 0, fp8=None):
+    """``fp8=(meta, site)``: also emit the fp8 copy of y (delayed scaling) -> returns (y, mean, rstd, q)."""
     y = torch.empty_like(x)
     M = x.numel() // x.size(-1)
     mean = torch.empty(M, dtype=torch.float32, device=x.device) if save_stats else None
     rstd = torch.empty(M, dtype=torch.float32, device=x.device) if save_stats else None
-    extension().layer_norm_fwd(x, gamma, beta, y, mean, rstd, eps, p_drop, seed, stream)
+    q, rec, e5 = _fp8_side(fp8, x)
+    extension().layer_norm_fwd(x, gamma, beta, y, mean, rstd, eps, p_drop, seed, stream, q, rec, e5)
     _count()
-    return y, mean, rstd
+    return (y, mean, rstd) if fp8 is None else (y, mean, rstd, q)
 
 
 _LN_WS: Dict[Tuple[int, int, int], torch.Tensor] = {}
@@ -179,15 +191,17 @@ NO_STREAM = 0xFFFFFFFF
 def layer_norm_bwd(dy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor, gamma: torch.Tensor, *,
                    dgamma: Optional[torch.Tensor], dbeta: Optional[torch.Tensor], dbias: Optional[torch.Tensor] = None,
                    want_dropped: bool = False, p_drop: float = 0.0, seed: int = 0, drop_stream: int = 0,
-                   in_stream: int = NO_STREAM):
-    """Returns (dx, dx_dropped or None).  ``dgamma``/``dbeta``/``dbias`` are *accumulated into*."""
+                   in_stream: int = NO_STREAM, fp8=None):
+    """Returns (dx, dx_dropped or None).  ``dgamma``/``dbeta``/``dbias`` are *accumulated into*.
+    ``fp8=(meta, site)`` (with ``want_dropped``): also the fp8 copy of dx_dropped -> (dx, dxd, q)."""
     dx = torch.empty_like(x)
     dxd = torch.empty_like(x) if want_dropped else None
     M, H = x.numel() // x.size(-1), x.size(-1)
+    q, rec, e5 = _fp8_side(fp8 if want_dropped else None, x)
     extension().layer_norm_bwd(dy, x, mean, rstd, gamma, dx, dxd, dgamma, dbeta, dbias, _ln_workspace(M, H, x.device),
-                               p_drop, seed, drop_stream, in_stream)
+                               p_drop, seed, drop_stream, in_stream, q, rec, e5)
     _count(2)
-    return dx, dxd
+    return (dx, dxd) if fp8 is None else (dx, dxd, q)
 
 
 def colsum_accumulate(x: torch.Tensor, out: torch.Tensor) -> None:
@@ -196,19 +210,21 @@ def colsum_accumulate(x: torch.Tensor, out: torch.Tensor) -> None:
     _count()
 
 
-def gelu_fwd(x: torch.Tensor) -> torch.Tensor:
+def gelu_fwd(x: torch.Tensor, fp8=None):
     y = torch.empty_like(x)
-    extension().gelu_fwd(x, y)
+    q, rec, e5 = _fp8_side(fp8, x)
+    extension().gelu_fwd(x, y, q, rec, e5)
     _count()
-    return y
+    return y if fp8 is None else (y, q)
 
 
-def dgelu_bwd(dy: torch.Tensor, x: torch.Tensor, dbias: Optional[torch.Tensor] = None) -> torch.Tensor:
+def dgelu_bwd(dy: torch.Tensor, x: torch.Tensor, dbias: Optional[torch.Tensor] = None, fp8=None):
     """dy * gelu'(x); ``dbias`` (fp32 [N]) accumulates the column sums of the result."""
     dx = torch.empty_like(dy)
-    extension().dgelu_bwd(dy, x, dx, dbias)
+    q, rec, e5 = _fp8_side(fp8, dy)
+    extension().dgelu_bwd(dy, x, dx, dbias, q, rec, e5)
     _count()
-    return dx
+    return dx if fp8 is None else (dx, q)
 
 
 def embedding_fwd(ids, seg, word, pos, type_emb, gamma, beta, S: int, *, eps=1e-12, p_drop=0.0, seed=0, stream=0):

@@ -50,6 +50,19 @@ void set_grad_peers(int64_t world, int64_t rank, std::vector<int64_t> ptrs, int6
 }
 void set_grad_push(bool on) { g_grad_peers.push = on ? 1 : 0; }
 
+// optional fp8 side output: (q bytes, meta record, e5m2)
+inline b200::Fp8Out mk_fp8(const c10::optional<Tensor>& q, const c10::optional<Tensor>& meta, bool e5m2, int64_t numel) {
+  b200::Fp8Out f;
+  if (q.has_value() && q->defined()) {
+    TORCH_CHECK(meta.has_value() && meta->defined() && meta->scalar_type() == at::kFloat && meta->numel() >= 4, "fp8 meta");
+    TORCH_CHECK(q->is_cuda() && q->is_contiguous() && q->element_size() == 1 && q->numel() == numel, "fp8 side output shape");
+    f.q = reinterpret_cast<unsigned char*>(q->data_ptr());
+    f.meta = meta->data_ptr<float>();
+    f.e5m2 = e5m2 ? 1 : 0;
+  }
+  return f;
+}
+
 inline const void* opt_ptr(const c10::optional<Tensor>& t) { return t.has_value() && t->defined() ? t->data_ptr() : nullptr; }
 inline float* opt_f32(const c10::optional<Tensor>& t) {
   if (!t.has_value() || !t->defined()) return nullptr;
@@ -64,7 +77,7 @@ inline float* opt_f32(const c10::optional<Tensor>& t) {
 void gemm(Tensor a, Tensor b, Tensor out, int64_t layout, int64_t epi, c10::optional<Tensor> bias,
           c10::optional<Tensor> res, c10::optional<Tensor> aux_out, int64_t k_splits, int64_t block_n, double alpha,
           double p_drop, int64_t seed, int64_t stream_id, c10::optional<Tensor> scale_a, c10::optional<Tensor> scale_b,
-          bool a_e5m2, bool b_e5m2) {
+          bool a_e5m2, bool b_e5m2, bool allow_push) {
   const bool fp8 = scale_a.has_value() && scale_a->defined();
   if (fp8) {
     TORCH_CHECK(a.is_cuda() && b.is_cuda() && a.element_size() == 1 && b.element_size() == 1 && a.stride(1) == 1 &&
@@ -132,7 +145,8 @@ void gemm(Tensor a, Tensor b, Tensor out, int64_t layout, int64_t epi, c10::opti
     const float* lo = g_grad_peers.base[g_grad_peers.rank];
     const float* o = reinterpret_cast<const float*>(out.data_ptr());
     if (o >= lo && o < lo + g_grad_peers.numel) {
-      c.peer_world = g_grad_peers.world; c.peer_rank = g_grad_peers.rank; c.peer_push = g_grad_peers.push;
+      c.peer_world = g_grad_peers.world; c.peer_rank = g_grad_peers.rank;
+      c.peer_push = (g_grad_peers.push && allow_push) ? 1 : 0;   // only tensors the fused step knows to be pre-reduced
       c.peer_off = (long long)(o - lo); c.peer_per = g_grad_peers.per;
       for (int i = 0; i < g_grad_peers.world; ++i) c.peer_base[i] = g_grad_peers.base[i];
     }
@@ -142,7 +156,8 @@ void gemm(Tensor a, Tensor b, Tensor out, int64_t layout, int64_t epi, c10::opti
 }
 
 void layer_norm_fwd(Tensor x, Tensor gamma, Tensor beta, Tensor y, c10::optional<Tensor> mean,
-                    c10::optional<Tensor> rstd, double eps, double p_drop, int64_t seed, int64_t stream_id) {
+                    c10::optional<Tensor> rstd, double eps, double p_drop, int64_t seed, int64_t stream_id,
+                    c10::optional<Tensor> q8, c10::optional<Tensor> meta8, bool e5m2) {
   check_bf16(x, "x"); check_bf16(y, "y");
   TORCH_CHECK(x.is_contiguous() && y.is_contiguous(), "x/y must be contiguous");
   const int H = (int)x.size(-1), M = (int)(x.numel() / H);
@@ -150,14 +165,15 @@ void layer_norm_fwd(Tensor x, Tensor gamma, Tensor beta, Tensor y, c10::optional
   c10::cuda::CUDAGuard guard(x.device());
   b200::layer_norm_fwd(x.data_ptr(), gamma.data_ptr<float>(), beta.data_ptr<float>(), y.data_ptr(), opt_f32(mean),
                        opt_f32(rstd), M, H, (float)eps, mk_seed(seed), (unsigned)stream_id, (float)p_drop,
-                       cur_stream());
+                       mk_fp8(q8, meta8, e5m2, x.numel()), cur_stream());
 }
 
 int64_t ln_bwd_workspace(int64_t M, int64_t H) { return b200::ln_bwd_workspace_floats((int)M, (int)H); }
 
 void layer_norm_bwd(Tensor dy, Tensor x, Tensor mean, Tensor rstd, Tensor gamma, Tensor dx, c10::optional<Tensor> dxd,
                     c10::optional<Tensor> dgamma, c10::optional<Tensor> dbeta, c10::optional<Tensor> dbias,
-                    Tensor workspace, double p_drop, int64_t seed, int64_t drop_stream, int64_t in_stream) {
+                    Tensor workspace, double p_drop, int64_t seed, int64_t drop_stream, int64_t in_stream,
+                    c10::optional<Tensor> q8, c10::optional<Tensor> meta8, bool e5m2) {
   check_bf16(dy, "dy"); check_bf16(x, "x"); check_bf16(dx, "dx");
   const int H = (int)x.size(-1), M = (int)(x.numel() / H);
   TORCH_CHECK(workspace.numel() >= b200::ln_bwd_workspace_floats(M, H), "LN workspace too small");
@@ -167,21 +183,23 @@ void layer_norm_bwd(Tensor dy, Tensor x, Tensor mean, Tensor rstd, Tensor gamma,
   b200::layer_norm_bwd(dy.data_ptr(), x.data_ptr(), mean.data_ptr<float>(), rstd.data_ptr<float>(),
                        gamma.data_ptr<float>(), dx.data_ptr(), dxd_p, opt_f32(dgamma), opt_f32(dbeta), opt_f32(dbias),
                        workspace.data_ptr<float>(), M, H, mk_seed(seed), (unsigned)drop_stream,
-                       (unsigned)in_stream, (float)p_drop, cur_stream());
+                       (unsigned)in_stream, (float)p_drop, mk_fp8(q8, meta8, e5m2, x.numel()), cur_stream());
 }
 
-void gelu_fwd(Tensor x, Tensor y) {
+void gelu_fwd(Tensor x, Tensor y, c10::optional<Tensor> q8, c10::optional<Tensor> meta8, bool e5m2) {
   check_bf16(x, "x"); check_bf16(y, "y");
   TORCH_CHECK(x.is_contiguous() && y.is_contiguous() && x.numel() == y.numel() && x.numel() % 8 == 0, "gelu_fwd shapes");
   c10::cuda::CUDAGuard guard(x.device());
-  b200::gelu_fwd(x.data_ptr(), y.data_ptr(), x.numel(), cur_stream());
+  b200::gelu_fwd(x.data_ptr(), y.data_ptr(), x.numel(), mk_fp8(q8, meta8, e5m2, x.numel()), cur_stream());
 }
-void dgelu_bwd(Tensor dy, Tensor x, Tensor dx, c10::optional<Tensor> dbias) {
+void dgelu_bwd(Tensor dy, Tensor x, Tensor dx, c10::optional<Tensor> dbias, c10::optional<Tensor> q8,
+               c10::optional<Tensor> meta8, bool e5m2) {
   check_bf16(dy, "dy"); check_bf16(x, "x"); check_bf16(dx, "dx");
   TORCH_CHECK(dy.dim() == 2 && dy.is_contiguous() && x.is_contiguous() && dx.is_contiguous() && dy.size(1) % 8 == 0,
               "dgelu_bwd: contiguous [M,N] with N % 8 == 0");
   c10::cuda::CUDAGuard guard(x.device());
-  b200::dgelu_bwd(dy.data_ptr(), x.data_ptr(), dx.data_ptr(), opt_f32(dbias), (int)dy.size(0), (int)dy.size(1), cur_stream());
+  b200::dgelu_bwd(dy.data_ptr(), x.data_ptr(), dx.data_ptr(), opt_f32(dbias), (int)dy.size(0), (int)dy.size(1),
+                  mk_fp8(q8, meta8, e5m2, dy.numel()), cur_stream());
 }
 
 void colsum(Tensor x, Tensor out) {

@@ -9,6 +9,8 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include <cuda_fp8.h>
+
 #include "seed.h"
 
 #ifndef B200_WATCHDOG_NS
@@ -384,6 +386,34 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp8 side outputs (see Fp8Out in seed.h)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t fp8_cvt4(float a, float b, float c, float d, bool e5m2) {
+  uint32_t lo, hi;
+  if (e5m2) {
+    lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E5M2);
+    hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E5M2);
+  } else {
+    lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
+    hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E4M3);
+  }
+  return lo | (hi << 16);
+}
+// 8 consecutive elements starting at element offset `off` (multiple of 8)
+__device__ __forceinline__ void fp8_emit8(const Fp8Out& f, size_t off, const float (&v)[8], float scale, float& amax) {
+#pragma unroll
+  for (int t = 0; t < 8; ++t) amax = fmaxf(amax, fabsf(v[t]));
+  const uint2 o = make_uint2(fp8_cvt4(v[0] * scale, v[1] * scale, v[2] * scale, v[3] * scale, f.e5m2 != 0),
+                             fp8_cvt4(v[4] * scale, v[5] * scale, v[6] * scale, v[7] * scale, f.e5m2 != 0));
+  *reinterpret_cast<uint2*>(f.q + off) = o;
+}
+__device__ __forceinline__ void fp8_amax_commit(const Fp8Out& f, float amax) {
+  amax = warp_max(amax);
+  if ((threadIdx.x & 31) == 0 && amax > 0.f)
+    atomicMax(reinterpret_cast<int*>(f.meta), __float_as_int(isfinite(amax) ? amax : 3.0e38f));
 }
 
 }  // namespace b200

@@ -8,14 +8,14 @@ namespace b200 {
 
 // norm_embed.cu
 void layer_norm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int M,
-                    int H, float eps, Seed seed, unsigned int stream, float p_drop, cudaStream_t st);
+                    int H, float eps, Seed seed, unsigned int stream, float p_drop, Fp8Out f8, cudaStream_t st);
 int ln_bwd_workspace_floats(int M, int H);
 void layer_norm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
                     void* dxd, float* dgamma, float* dbeta, float* dbias, float* workspace, int M, int H,
-                    Seed seed, unsigned int drop_stream, unsigned int in_stream, float p_drop,
+                    Seed seed, unsigned int drop_stream, unsigned int in_stream, float p_drop, Fp8Out f8,
                     cudaStream_t st);
-void gelu_fwd(const void* x, void* y, long long n, cudaStream_t st);
-void dgelu_bwd(const void* dy, const void* x, void* dx, float* dbias, int M, int N, cudaStream_t st);
+void gelu_fwd(const void* x, void* y, long long n, Fp8Out f8, cudaStream_t st);
+void dgelu_bwd(const void* dy, const void* x, void* dx, float* dbias, int M, int N, Fp8Out f8, cudaStream_t st);
 void colsum_bf16(const void* x, int M, int N, int ld, float* out, cudaStream_t st);
 void embedding_fwd(const int* ids, const int* seg, const void* word, const void* pos, const void* type,
                    const float* gamma, const float* beta, void* e_out, void* y, float* mean, float* rstd, int M, int S,

@@ -143,8 +143,10 @@ template <int WPR>
 __global__ void __launch_bounds__(2 * WPR * 32)
 ln_fwd2_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int H,
-               float eps, Seed seed_in, unsigned int stream, unsigned int thresh16, float drop_scale) {
+               float eps, Seed seed_in, unsigned int stream, unsigned int thresh16, float drop_scale, const Fp8Out f8) {
   const unsigned long long seed = seed_in.value();
+  const float qscale = f8.q ? f8.meta[1] : 0.f;
+  float amax = 0.f;
   __shared__ float2 xchg[2][2][8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int group = warp / WPR, wi = warp % WPR;
@@ -189,12 +191,14 @@ ln_fwd2_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ ga
         v[t] = o;
       }
       store8(y + (size_t)row * H + col, v);
+      if (f8.q) fp8_emit8(f8, (size_t)row * H + col, v, qscale, amax);
     }
     if (wi == 0 && lane == 0) {
       if (mean_out) mean_out[row] = mean;
       if (rstd_out) rstd_out[row] = rstd;
     }
   }
+  if (f8.q) fp8_amax_commit(f8, amax);
 }
 
 // LayerNorm backward.
@@ -211,8 +215,10 @@ ln_bwd2_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __rest
                const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
                __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dxd, float* __restrict__ partial, int M,
                int H, Seed seed_in, unsigned int drop_stream, unsigned int in_stream,
-               unsigned int thresh16, float drop_scale) {
+               unsigned int thresh16, float drop_scale, const Fp8Out f8) {
   const unsigned long long seed = seed_in.value();
+  const float qscale = f8.q ? f8.meta[1] : 0.f;
+  float amax = 0.f;
   __shared__ float2 xchg[2][2][8];
   __shared__ float comb[3][WPR * 256];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -273,9 +279,11 @@ ln_bwd2_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __rest
 #pragma unroll
         for (int t = 0; t < 8; ++t) ad[t] += d[t];
         store8(dxd + (size_t)row * H + col, d);
+        if (f8.q) fp8_emit8(f8, (size_t)row * H + col, d, qscale, amax);
       }
     }
   }
+  if (f8.q) fp8_amax_commit(f8, amax);
   // combine the two row groups of the block and write the per-block partial column sums
   const int cbase = (wi * 32 + lane) * 8;
   if (group == 1) {
@@ -361,26 +369,35 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
 // also produces the FFN-1 bias gradient (column sums) that used to be a separate kernel.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) gelu_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
-                                                      long long n8) {
+                                                      long long n8, const Fp8Out f8) {
+  const float qscale = f8.q ? f8.meta[1] : 0.f;
+  float amax = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     const uint4 u = reinterpret_cast<const uint4*>(x)[i];
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
     uint32_t o[4];
+    float r[8];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       const float2 f = unpack_bf16(w[t]);
-      o[t] = pack_bf16(gelu_erf(f.x), gelu_erf(f.y));
+      r[2 * t] = gelu_erf(f.x);
+      r[2 * t + 1] = gelu_erf(f.y);
+      o[t] = pack_bf16(r[2 * t], r[2 * t + 1]);
     }
     reinterpret_cast<uint4*>(y)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    if (f8.q) fp8_emit8(f8, (size_t)i * 8, r, qscale, amax);
   }
+  if (f8.q) fp8_amax_commit(f8, amax);
 }
 
 // dx[m][n] = dy[m][n] * gelu'(x[m][n]);  dbias[n] += sum_m dx[m][n]
 __global__ void __launch_bounds__(256)
 dgelu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ dx,
-                 float* __restrict__ dbias, int M, int N) {
+                 float* __restrict__ dbias, int M, int N, const Fp8Out f8) {
   const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + cg * 8;
+  const float qscale = f8.q ? f8.meta[1] : 0.f;
+  float amax = 0.f;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (col < N) {
     for (int row = blockIdx.y * 8 + rl; row < M; row += gridDim.y * 8) {
@@ -388,17 +405,21 @@ dgelu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __re
       const uint4 a = *reinterpret_cast<const uint4*>(dy + off), b = *reinterpret_cast<const uint4*>(x + off);
       const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
       uint32_t o[4];
+      float r[8];
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const float2 g = unpack_bf16(aw[t]), v = unpack_bf16(bw[t]);
         const float r0 = g.x * dgelu_erf(v.x), r1 = g.y * dgelu_erf(v.y);
         acc[2 * t] += r0;
         acc[2 * t + 1] += r1;
+        r[2 * t] = r0; r[2 * t + 1] = r1;
         o[t] = pack_bf16(r0, r1);
       }
       *reinterpret_cast<uint4*>(dx + off) = make_uint4(o[0], o[1], o[2], o[3]);
+      if (f8.q) fp8_emit8(f8, off, r, qscale, amax);
     }
   }
+  if (f8.q) fp8_amax_commit(f8, amax);
   if (dbias == nullptr) return;
   __shared__ float sm[8][256];
 #pragma unroll
@@ -601,25 +622,25 @@ static inline int ln2_grid(int M) {     // 2 rows per block at a time; 4 residen
 }
 
 void layer_norm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int M,
-                    int H, float eps, Seed seed, unsigned int stream, float p_drop, cudaStream_t st) {
+                    int H, float eps, Seed seed, unsigned int stream, float p_drop, Fp8Out f8, cudaStream_t st) {
   unsigned int th; float sc;
   drop_params(p_drop, th, sc);
   DISPATCH_WPR(H, (ln_fwd2_kernel<WPR><<<ln2_grid(M), 2 * WPR * 32, 0, st>>>(
-      (const __nv_bfloat16*)x, gamma, beta, (__nv_bfloat16*)y, mean, rstd, M, H, eps, seed, stream, th, sc)));
+      (const __nv_bfloat16*)x, gamma, beta, (__nv_bfloat16*)y, mean, rstd, M, H, eps, seed, stream, th, sc, f8)));
 }
 
 int ln_bwd_workspace_floats(int M, int H) { return ln2_grid(M) * 3 * H; }
 
 void layer_norm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
                     void* dxd, float* dgamma, float* dbeta, float* dbias, float* workspace, int M, int H,
-                    Seed seed, unsigned int drop_stream, unsigned int in_stream, float p_drop,
+                    Seed seed, unsigned int drop_stream, unsigned int in_stream, float p_drop, Fp8Out f8,
                     cudaStream_t st) {
   unsigned int th; float sc;
   drop_params(p_drop, th, sc);
   const int grid = ln2_grid(M);
   DISPATCH_WPR(H, (ln_bwd2_kernel<WPR><<<grid, 2 * WPR * 32, 0, st>>>(
       (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, gamma, (__nv_bfloat16*)dx, (__nv_bfloat16*)dxd,
-      workspace, M, H, seed, drop_stream, in_stream, th, sc)));
+      workspace, M, H, seed, drop_stream, in_stream, th, sc, f8)));
   dim3 g2((H + 31) / 32, 3);
   colsum_finalize_kernel<<<g2, 256, 0, st>>>(workspace, grid, H, dgamma, dbeta, dxd ? dbias : nullptr);
 }
@@ -629,15 +650,15 @@ void colsum_bf16(const void* x, int M, int N, int ld, float* out, cudaStream_t s
   colsum_bf16_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, M, N, ld, out);
 }
 
-void gelu_fwd(const void* x, void* y, long long n, cudaStream_t st) {
+void gelu_fwd(const void* x, void* y, long long n, Fp8Out f8, cudaStream_t st) {
   const long long n8 = n >> 3;
   long long g = (n8 + 255) / 256;
   if (g > 148 * 32) g = 148 * 32;
-  if (g > 0) gelu_fwd_kernel<<<(unsigned)g, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, n8);
+  if (g > 0) gelu_fwd_kernel<<<(unsigned)g, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, n8, f8);
 }
-void dgelu_bwd(const void* dy, const void* x, void* dx, float* dbias, int M, int N, cudaStream_t st) {
+void dgelu_bwd(const void* dy, const void* x, void* dx, float* dbias, int M, int N, Fp8Out f8, cudaStream_t st) {
   dim3 grid((N + 255) / 256, M >= 4096 ? 74 : (M >= 512 ? 16 : 1));
-  dgelu_bwd_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (__nv_bfloat16*)dx, dbias, M, N);
+  dgelu_bwd_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (__nv_bfloat16*)dx, dbias, M, N, f8);
 }
 
 void embedding_fwd(const int* ids, const int* seg, const void* word, const void* pos, const void* type,

@@ -14,4 +14,12 @@ struct Seed {
 #endif
 };
 
+// Optional fp8 copy of a kernel's bf16 output (delayed scaling: quantise with meta[1], record |x| max in meta[0]),
+// so that the tensor does not have to be read again by a separate quantise pass.
+struct Fp8Out {
+  unsigned char* q = nullptr;         // nullptr: disabled
+  float* meta = nullptr;              // {amax, scale, inv_scale, _}
+  int e5m2 = 0;
+};
+
 }  // namespace b200

@@ -20,7 +20,9 @@ for s in $STAGES; do
     fp8)     timeout 600 python -m pytest tests/test_gpu_fp8.py -m gpu -q --timeout 300 > gpurun_out/test_fp8.log 2>&1; echo "fp8 rc=$?"; tail -15 gpurun_out/test_fp8.log ;;
     gemmbench) timeout 600 python tools/gemm_bench.py ${GEMMBENCH_ARGS:-} > gpurun_out/gemm_bench.json 2> gpurun_out/gemm_bench.err; echo "gemmbench rc=$?"; tail -c 3000 gpurun_out/gemm_bench.json ;;
     launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --accum 1 --no-e2e > gpurun_out/launches.log 2>&1; echo "launches rc=$?" ;;
-    ncu_gemm) timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 12 -c 2 -f -o gpurun_out/prof_gemm python tools/gemm_bench.py --only ${NCU_SHAPE:-qkv_fwd} > gpurun_out/ncu_gemm.log 2>&1; echo "ncu_gemm rc=$?" ;;
+    ncu_gemm) timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_pair_kernel -s 12 -c 2 -f -o gpurun_out/prof_gemm python tools/gemm_bench.py --only ${NCU_SHAPE:-ffn1_fwd} > gpurun_out/ncu_gemm.log 2>&1; echo "ncu_gemm rc=$?" ;;
+    ncu_elt)  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"ln_fwd2|ln_bwd2|gelu_fwd|dgelu_bwd" -s 20 -c 4 -f -o gpurun_out/prof_elt python tools/elt_bench.py > gpurun_out/ncu_elt.log 2>&1; echo "ncu_elt rc=$?" ;;
+    eltbench) timeout 300 python tools/elt_bench.py > gpurun_out/elt_bench.json 2> gpurun_out/elt_bench.err; echo "eltbench rc=$?"; cat gpurun_out/elt_bench.json ;;
     ncu_attn) timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_ -s 6 -c 3 -f -o gpurun_out/prof_attn python tools/attn_bench.py > gpurun_out/ncu_attn.log 2>&1; echo "ncu_attn rc=$?" ;;
     attnbench) timeout 300 python tools/attn_bench.py > gpurun_out/attn_bench.json 2> gpurun_out/attn_bench.err; echo "attnbench rc=$?"; cat gpurun_out/attn_bench.json ;;
     trace)   timeout 600 python tools/trace_step.py > gpurun_out/trace_step.log 2>&1; echo "trace rc=$?"; cat gpurun_out/trace_step.log | tail -30 ;;
