@@ -629,6 +629,13 @@ void layer_norm_fwd(const void* x, const float* gamma, const float* beta, void* 
       (const __nv_bfloat16*)x, gamma, beta, (__nv_bfloat16*)y, mean, rstd, M, H, eps, seed, stream, th, sc, f8)));
 }
 
+// backward: ~80 registers x 256 threads -> 3 blocks per SM are co-resident; one exact wave (a grid of 4 per SM
+// ran a 1/3-full second wave)
+static inline int ln2_bwd_grid(int M) {
+  int g = (M + 1) / 2;
+  return g < 148 * 3 ? g : 148 * 3;
+}
+
 int ln_bwd_workspace_floats(int M, int H) { return ln2_grid(M) * 3 * H; }
 
 void layer_norm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
@@ -637,7 +644,7 @@ void layer_norm_bwd(const void* dy, const void* x, const float* mean, const floa
                     cudaStream_t st) {
   unsigned int th; float sc;
   drop_params(p_drop, th, sc);
-  const int grid = ln2_grid(M);
+  const int grid = ln2_bwd_grid(M);
   DISPATCH_WPR(H, (ln_bwd2_kernel<WPR><<<grid, 2 * WPR * 32, 0, st>>>(
       (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, gamma, (__nv_bfloat16*)dx, (__nv_bfloat16*)dxd,
       workspace, M, H, seed, drop_stream, in_stream, th, sc, f8)));

@@ -22,11 +22,13 @@ for s in $STAGES; do
     launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --accum 1 --no-e2e > gpurun_out/launches.log 2>&1; echo "launches rc=$?" ;;
     ncu_gemm) timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_pair_kernel -s 12 -c 2 -f -o gpurun_out/prof_gemm python tools/gemm_bench.py --only ${NCU_SHAPE:-ffn1_fwd} > gpurun_out/ncu_gemm.log 2>&1; echo "ncu_gemm rc=$?" ;;
     ncu_elt)  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"ln_fwd2|ln_bwd2|gelu_fwd|dgelu_bwd" -s 20 -c 4 -f -o gpurun_out/prof_elt python tools/elt_bench.py > gpurun_out/ncu_elt.log 2>&1; echo "ncu_elt rc=$?" ;;
+    ncu_all)  timeout 900 ncu --set full --profile-from-start off --clock-control none --import-source on -f -o gpurun_out/prof_all python tools/ncu_targets.py > gpurun_out/ncu_all.log 2>&1; echo "ncu_all rc=$?"; tail -3 gpurun_out/ncu_all.log ;;
     eltbench) timeout 300 python tools/elt_bench.py > gpurun_out/elt_bench.json 2> gpurun_out/elt_bench.err; echo "eltbench rc=$?"; cat gpurun_out/elt_bench.json ;;
     ncu_attn) timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_ -s 6 -c 3 -f -o gpurun_out/prof_attn python tools/attn_bench.py > gpurun_out/ncu_attn.log 2>&1; echo "ncu_attn rc=$?" ;;
     attnbench) timeout 300 python tools/attn_bench.py > gpurun_out/attn_bench.json 2> gpurun_out/attn_bench.err; echo "attnbench rc=$?"; cat gpurun_out/attn_bench.json ;;
     trace)   timeout 600 python tools/trace_step.py > gpurun_out/trace_step.log 2>&1; echo "trace rc=$?"; cat gpurun_out/trace_step.log | tail -30 ;;
     trace2)  PHASE=2 timeout 600 python tools/trace_step.py > gpurun_out/trace_step2.log 2>&1; echo "trace2 rc=$?"; cat gpurun_out/trace_step2.log | tail -30 ;;
+    push)    timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29578 tools/push_check.py > gpurun_out/push_check.log 2>&1; echo "push rc=$?"; grep "^{" gpurun_out/push_check.log | tail -1 | cut -c1-3000; tail -5 gpurun_out/push_check.log | cut -c1-500 ;;
     peer)    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29577 tools/peer_check.py ${PEER_ARGS:-} > gpurun_out/peer_check.log 2>&1; echo "peer rc=$?"; tail -20 gpurun_out/peer_check.log ;;
     *) echo "unknown stage $s" ;;
   esac
