@@ -116,3 +116,39 @@ def test_fp8_engine_tracks_bf16_engine():
         assert worst > 0.0                 # the fp8 path really ran (not bitwise the bf16 program)
     rec = e8.engine.meta.table
     assert torch.isfinite(rec).all() and (rec[:, 1] > 0).all()
+
+
+def test_producer_kernels_emit_fp8_copies():
+    """LayerNorm fwd/bwd, GELU and dGELU write the fp8 copy of their output in the same pass (delayed scaling):
+    the copy must dequantise to the bf16 output and the amax record must see the tensor."""
+    ops = _ops()
+    api = ops.api
+    dev = torch.device("cuda")
+    M, H = 512, 1024
+    x = torch.randn(M, H, device=dev).bfloat16()
+    g, b = torch.rand(H, device=dev) + 0.5, torch.randn(H, device=dev) * 0.1
+    meta = api.Fp8Meta(["ln", "gelu", "dxd", "dgelu"], [False, False, True, True], dev)
+    # scales as the previous step would have left them
+    for site, t in (("ln", 6.0), ("gelu", 6.0), ("dxd", 0.05), ("dgelu", 0.05)):
+        rec = meta.record(site)
+        rec[0] = t
+    meta.update()
+
+    def close(q, ref, site, rel):
+        deq = _deq(q, meta, site)
+        err = (deq - ref.float()).abs()
+        assert (err <= rel * ref.float().abs() + 2.0 / meta.record(site)[1].item() * (2e-3 if not meta.is_e5m2(site) else 2e-5)).all(), site
+        assert meta.record(site)[0].item() == pytest.approx(ref.float().abs().max().item(), rel=2e-2)
+
+    y, mean, rstd, q = api.layer_norm_fwd(x, g, b, fp8=(meta, "ln"))
+    close(q, y, "ln", 0.07)
+    act, q = api.gelu_fwd(x, fp8=(meta, "gelu"))
+    close(q, act, "gelu", 0.07)
+    dy = (torch.randn(M, H, device=dev) * 0.01).bfloat16()
+    dg, db, dbias = (torch.zeros(H, device=dev) for _ in range(3))
+    dx, dxd, q = api.layer_norm_bwd(dy, x, mean, rstd, g, dgamma=dg, dbeta=db, dbias=dbias, want_dropped=True, p_drop=0.1,
+                                    seed=11, drop_stream=3, fp8=(meta, "dxd"))
+    close(q, dxd, "dxd", 0.14)
+    dbi = torch.zeros(H, device=dev)
+    d1, q = api.dgelu_bwd(dy, x, dbi, fp8=(meta, "dgelu"))
+    close(q, d1, "dgelu", 0.14)

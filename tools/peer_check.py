@@ -113,7 +113,7 @@ def main():
         e_p.use_graphs = e_q.use_graphs = False
         comm_p.set_prereduced(e_p.engine.gemm_reduced_parameters())
         gen = torch.Generator(device=dev).manual_seed(4321 + rank)
-        push_worst = 0.0
+        push_worst, push_steps = 0.0, []
         for step in range(3):
             for micro in range(2):
                 ids = torch.randint(5, 2048, (4, 64), device=dev, generator=gen)
@@ -136,11 +136,13 @@ def main():
             o_q.step()
             a_q.zero_grad()
             torch.cuda.synchronize()
-            push_worst = max(push_worst, (a_p.flat_param - a_q.flat_param).abs().max().item())
+            push_steps.append((a_p.flat_param - a_q.flat_param).abs().max().item())
+            push_worst = max(push_worst, push_steps[-1])
             ref = a_p.flat_param.clone()
             dist.broadcast(ref, src=0)
             assert torch.equal(ref, a_p.flat_param), "ranks disagree after the pushed step"
         out[f"push_max_abs_diff_mc{int(mc)}"] = push_worst
+        out[f"push_diff_per_step_mc{int(mc)}"] = push_steps     # the two arms train independently: only step 0 is a bitwise-level comparison
         del comm_p, m_p, a_p, o_p, m_q, a_q, o_q, e_p, e_q
         ext.set_grad_peers(0, 0, [], 0, 1)
         # general all-reduce through our own kernel (K-FAC factor path): odd sizes, packing, avg
