@@ -522,6 +522,200 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// backward, S <= 128 (phase 1): ONE key block and ONE query block per (batch, head), so nothing accumulates across
+// iterations and the kernel can be made small enough for TWO CTAs per SM (the generic kernel is latency bound at
+// one CTA per SM: ~11 us per head, almost all of it dependent waits):
+//   * TMEM 256 columns: S | dP; dV then overwrites S[0,64), dK S[64,128) and dQ dP[0,64) -- by then every thread
+//     has consumed S and dP
+//   * ONE 32 KB operand buffer for P~ (dropped probabilities) and dS: P~ goes out first and feeds dV = P~^T dO while
+//     the threads keep dS packed in 32 registers; once that MMA has retired the same buffer receives dS for
+//     dK = dS^T Q and dQ = dS K
+//   * 96 KB of shared memory, <= 112 registers
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ATT_BWD_THREADS, 2)
+attn_bwd_single_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
+                       const AttnArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;                      // 16 KB each
+  uint8_t* sV = smem + 16384;
+  uint8_t* sQ = smem + 16384 * 2;
+  uint8_t* sDO = smem + 16384 * 3;
+  uint8_t* sP = smem + 16384 * 4;          // 32 KB: P~, later dS
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 16384 * 6);
+  uint64_t* in_full = bars;                // Q, K, V, dO landed
+  uint64_t* sdp_ready = bars + 1;          // S and dP accumulators complete
+  uint64_t* pd_ready = bars + 2;           // 256 threads: P~ is in shared memory
+  uint64_t* dv_done = bars + 3;            // dV MMA retired: the buffer may be overwritten with dS
+  uint64_t* ds_ready = bars + 4;           // 256 threads: dS is in shared memory
+  uint64_t* fin = bars + 5;                // dK, dQ complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.y;
+  const int b = bh / p.h, head = bh % p.h;
+  const int seqlen = min(p.seqlens[b], p.S);
+  const int row0 = b * p.S;
+
+  if (threadIdx.x == 256) {
+    tma_prefetch_desc(&tmap_qkv);
+    tma_prefetch_desc(&tmap_do);
+    mbar_init(in_full, 1);
+    mbar_init(sdp_ready, 1);
+    mbar_init(pd_ready, 256);
+    mbar_init(dv_done, 1);
+    mbar_init(ds_ready, 256);
+    mbar_init(fin, 1);
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const unsigned long long seed = p.thresh16 != 0 ? p.seed.value() : 0ull;
+  const uint32_t tS = tmem, tDP = tmem + 128, tDV = tmem, tDK = tmem + 64, tDQ = tmem + 128;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      const int cq = head * HD, ck = p.H + head * HD, cv = 2 * p.H + head * HD;
+      mbar_arrive_expect_tx(in_full, 65536);
+      tma_load_2d(sK, &tmap_qkv, in_full, ck, row0);
+      tma_load_2d(sV, &tmap_qkv, in_full, cv, row0);
+      tma_load_2d(sQ, &tmap_qkv, in_full, cq, row0);
+      tma_load_2d(sDO, &tmap_do, in_full, head * HD, row0);
+      constexpr uint32_t id_kk = umma_idesc_bf16(128, 128, false, false);  // [q x keys], both K-major
+      constexpr uint32_t id_tt = umma_idesc_bf16(128, 64, true, true);     // [keys x d] = X^T Y, both MN-major
+      constexpr uint32_t id_kt = umma_idesc_bf16(128, 64, false, true);    // [q x d] = dS K, A K-major, B MN-major
+      const uint32_t aq = smem_u32(sQ), ado = smem_u32(sDO), ak = smem_u32(sK), av = smem_u32(sV), ap = smem_u32(sP);
+      mbar_wait(in_full, 0);
+      tc_fence_after();
+#pragma unroll
+      for (int kk = 0; kk < HD / 16; ++kk)   // S = Q K^T
+        umma_bf16_ss(tS, umma_smem_desc_sw128(aq + kk * 32, 16, 1024), umma_smem_desc_sw128(ak + kk * 32, 16, 1024), id_kk,
+                     kk > 0);
+#pragma unroll
+      for (int kk = 0; kk < HD / 16; ++kk)   // dP = dO V^T
+        umma_bf16_ss(tDP, umma_smem_desc_sw128(ado + kk * 32, 16, 1024), umma_smem_desc_sw128(av + kk * 32, 16, 1024), id_kk,
+                     kk > 0);
+      umma_commit(sdp_ready);
+      mbar_wait(pd_ready, 0);
+      tc_fence_after();
+#pragma unroll
+      for (int kk = 0; kk < TILE / 16; ++kk)   // dV = P~^T dO   (reduction over the query rows) -> overwrites S[0,64)
+        umma_bf16_ss(tDV, umma_smem_desc_sw128(ap + kk * 2048, 16384, 1024), umma_smem_desc_sw128(ado + kk * 2048, 8192, 1024),
+                     id_tt, kk > 0);
+      umma_commit(dv_done);
+      mbar_wait(ds_ready, 0);
+      tc_fence_after();
+#pragma unroll
+      for (int kk = 0; kk < TILE / 16; ++kk)   // dK = dS^T Q -> S[64,128)
+        umma_bf16_ss(tDK, umma_smem_desc_sw128(ap + kk * 2048, 16384, 1024), umma_smem_desc_sw128(aq + kk * 2048, 8192, 1024),
+                     id_tt, kk > 0);
+#pragma unroll
+      for (int kk = 0; kk < TILE / 16; ++kk)   // dQ = dS K (reduction over the keys) -> dP[0,64)
+        umma_bf16_ss(tDQ, umma_smem_desc_sw128(ap + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                     umma_smem_desc_sw128(ak + kk * 2048, 8192, 1024), id_kt, kk > 0);
+      umma_commit(fin);
+    }
+  } else {
+    const int r = (warp & 3) * 32 + lane;        // query row inside the tile == TMEM lane
+    const int ch = warp >> 2;                    // which 64-column half this thread handles
+    const uint32_t lane_base = uint32_t((warp & 3) * 32) << 16;
+    const float c_scale = p.scale * LOG2E;
+    const int q = r;
+    const bool q_ok = q < p.S;
+    const float lse2 = q_ok ? p.lse[(size_t)bh * p.S + q] * LOG2E : 0.f;
+    const float dlt = q_ok ? p.delta[(size_t)bh * p.S + q] : 0.f;
+    const uint64_t erow = ((uint64_t)bh * p.S + (uint64_t)q) * (uint64_t)p.S;
+    uint32_t dsp[32];                            // this thread's 64 dS values, packed bf16
+    mbar_wait(sdp_ready, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int sc = 0; sc < 4; ++sc) {             // 16-column sub-chunks of this thread's key half
+      const int c16 = ch * 4 + sc;
+      uint32_t sv[16], dv[16];
+      tmem_ld_32x16(tS + lane_base + c16 * 16, sv);
+      tmem_ld_32x16(tDP + lane_base + c16 * 16, dv);
+      tmem_ld_wait();
+      const int k0 = c16 * 16;
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        uint32_t keep = 0xFFu;
+        if (p.thresh16 != 0) keep = dropout_keep8(seed, p.stream, (erow + (uint64_t)(k0 + g * 8)) >> 3, p.thresh16);
+        float pd[8], ds[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const int key = k0 + g * 8 + t;
+          const bool ok = q_ok && key < seqlen;
+          const float pr = ok ? ex2_approx(fmaf(__uint_as_float(sv[g * 8 + t]), c_scale, -lse2)) : 0.f;
+          const bool kp = (keep >> t) & 1u;
+          const float dp = kp ? __uint_as_float(dv[g * 8 + t]) * p.inv_keep : 0.f;
+          pd[t] = kp ? pr * p.inv_keep : 0.f;
+          ds[t] = pr * (dp - dlt) * p.scale;
+        }
+        *reinterpret_cast<uint4*>(sP + p_chunk_offset(r, c16 * 2 + g)) =
+            make_uint4(pack_bf16(pd[0], pd[1]), pack_bf16(pd[2], pd[3]), pack_bf16(pd[4], pd[5]), pack_bf16(pd[6], pd[7]));
+#pragma unroll
+        for (int t = 0; t < 4; ++t) dsp[(sc * 2 + g) * 4 + t] = pack_bf16(ds[2 * t], ds[2 * t + 1]);
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();                           // S / dP reads retired before dV may overwrite S
+    mbar_arrive(pd_ready);
+    mbar_wait(dv_done, 0);                       // the tensor core no longer reads P~
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      *reinterpret_cast<uint4*>(sP + p_chunk_offset(r, ch * 8 + i)) =
+          make_uint4(dsp[i * 4], dsp[i * 4 + 1], dsp[i * 4 + 2], dsp[i * 4 + 3]);
+    fence_proxy_async();
+    mbar_arrive(ds_ready);
+    mbar_wait(fin, 0);
+    tc_fence_after();
+    // epilogue: column half 0 writes dQ[:, 0:32], dK; half 1 writes dQ[:, 32:64], dV
+    {
+      uint32_t v[32];
+      tmem_ld_32x32(tDQ + lane_base + ch * 32, v);
+      tmem_ld_wait();
+      if (q_ok) {
+        __nv_bfloat16* dq = p.dqkv + (size_t)(row0 + q) * 3 * p.H + head * HD + ch * 32;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          *reinterpret_cast<uint4*>(dq + g * 8) = make_uint4(
+              pack_bf16(__uint_as_float(v[g * 8]), __uint_as_float(v[g * 8 + 1])),
+              pack_bf16(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3])),
+              pack_bf16(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5])),
+              pack_bf16(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7])));
+      }
+    }
+    const int key = r;
+    const uint32_t src = ch == 0 ? tDK : tDV;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(src + lane_base + c * 32, v);
+      tmem_ld_wait();
+      if (key < p.S) {
+        __nv_bfloat16* dst = p.dqkv + (size_t)(row0 + key) * 3 * p.H + (ch + 1) * p.H + head * HD + c * 32;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          *reinterpret_cast<uint4*>(dst + g * 8) = make_uint4(
+              pack_bf16(__uint_as_float(v[g * 8]), __uint_as_float(v[g * 8 + 1])),
+              pack_bf16(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3])),
+              pack_bf16(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5])),
+              pack_bf16(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7])));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
 // dq_acc (fp32 [B*S, H]) -> q slots of dqkv (bf16 [B*S, 3H])
 __global__ void __launch_bounds__(256)
 attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, long long rows, int H) {
@@ -592,6 +786,17 @@ void attention_bwd(const void* qkv, const int* seqlens, const void* ctx, const v
   static bool once = false;
   if (!once) { B200_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); once = true; }
   dim3 grid(nkb, B * h);
+  static const bool single_ok = []() { const char* e = getenv("B200_ATTN_BWD_SINGLE"); return !(e && e[0] == '0'); }();
+  if (nkb == 1 && single_ok) {                 // S <= 128: the two-CTAs-per-SM variant
+    constexpr int SMEM1 = 16384 * 6 + 1024 + 128;
+    static bool once1 = false;
+    if (!once1) {
+      B200_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM1));
+      once1 = true;
+    }
+    attn_bwd_single_kernel<<<grid, ATT_BWD_THREADS, SMEM1, st>>>(tq, td, a);
+    return;
+  }
   attn_bwd_kernel<<<grid, ATT_BWD_THREADS, SMEM, st>>>(tq, td, a);
   if (nkb > 1) {
     const long long work = (long long)B * S * (H / 8);
