@@ -259,6 +259,161 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs p) 
 }
 
 // ------------------------------------------------------------------------------------------------
+// forward, S <= 128 (phase 1): one query block and one key block per (batch, head).  No online-softmax state, the
+// probabilities overwrite the Q|K operand buffers once S = Q K^T has retired (48 KB of shared memory), the PV
+// result overwrites the S columns (128 TMEM columns) and the softmax needs < 75 registers: three CTAs per SM
+// instead of two, which is what this latency-bound kernel (one dependent chain per head) is short of.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ATT_BWD_THREADS, 3)
+attn_fwd_single_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                  // 16 KB  } P (32 KB) lands here after the S MMA
+  uint8_t* sK = smem + 16384;                          // 16 KB  }
+  uint8_t* sV = smem + 32768;                          // 16 KB
+  uint8_t* sP = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 49152);
+  uint64_t* in_full = bars;
+  uint64_t* s_ready = bars + 1;
+  uint64_t* p_ready = bars + 2;
+  uint64_t* pv_done = bars + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  float* xch = reinterpret_cast<float*>(bars + 6);     // [2 exchanges][2 halves][128 rows]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.y;
+  const int b = bh / p.h, head = bh % p.h;
+  const int seqlen = min(p.seqlens[b], p.S);
+  const int row0 = b * p.S;
+
+  if (threadIdx.x == 256) {
+    tma_prefetch_desc(&tmap_qkv);
+    mbar_init(in_full, 1);
+    mbar_init(s_ready, 1);
+    mbar_init(p_ready, 256);
+    mbar_init(pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tS = *tmem_slot;
+  const unsigned long long seed = p.thresh16 != 0 ? p.seed.value() : 0ull;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(in_full, 49152);
+      tma_load_2d(sQ, &tmap_qkv, in_full, head * HD, row0);
+      tma_load_2d(sK, &tmap_qkv, in_full, p.H + head * HD, row0);
+      tma_load_2d(sV, &tmap_qkv, in_full, 2 * p.H + head * HD, row0);
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);  // Q K^T : both K-major
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, false, true);    // P V   : V is MN-major
+      mbar_wait(in_full, 0);
+      tc_fence_after();
+      const uint64_t dq = umma_smem_desc_sw128(smem_u32(sQ), 16, 1024);
+      const uint64_t dk = umma_smem_desc_sw128(smem_u32(sK), 16, 1024);
+#pragma unroll
+      for (int kk = 0; kk < HD / 16; ++kk) umma_bf16_ss(tS, dq + 2 * kk, dk + 2 * kk, idesc_s, kk > 0);
+      umma_commit(s_ready);                    // also: Q and K are no longer read -> P may overwrite them
+      mbar_wait(p_ready, 0);
+      tc_fence_after();
+      const uint32_t ap = smem_u32(sP), av = smem_u32(sV);
+#pragma unroll
+      for (int kk = 0; kk < TILE / 16; ++kk) {
+        const uint64_t da = umma_smem_desc_sw128(ap + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024);
+        const uint64_t db = umma_smem_desc_sw128(av + kk * 2048, 8192, 1024);
+        umma_bf16_ss(tS, da, db, idesc_o, kk > 0);   // O -> columns [0, 64) of the (consumed) S accumulator
+      }
+      umma_commit(pv_done);
+    }
+  } else {
+    // two threads per query row: thread (r, ch) owns key columns [64 ch, 64 ch + 64) and output columns [32 ch, 32 ch + 32)
+    const int r = (warp & 3) * 32 + lane;
+    const int ch = warp >> 2;
+    const uint32_t lane_base = uint32_t((warp & 3) * 32) << 16;
+    const float c_scale = p.scale * LOG2E;
+    const uint64_t erow = ((uint64_t)bh * p.S + (uint64_t)r) * (uint64_t)p.S;
+    const bool full = TILE <= seqlen;
+    mbar_wait(s_ready, 0);
+    tc_fence_after();
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int c = ch * 4; c < ch * 4 + 4; ++c) {
+      uint32_t v[16];
+      tmem_ld_32x16(tS + lane_base + c * 16, v);
+      tmem_ld_wait();
+      if (full) {
+#pragma unroll
+        for (int t = 0; t < 16; ++t) mx = fmaxf(mx, __uint_as_float(v[t]));
+      } else {
+#pragma unroll
+        for (int t = 0; t < 16; ++t)
+          if (c * 16 + t < seqlen) mx = fmaxf(mx, __uint_as_float(v[t]));
+      }
+    }
+    mx *= c_scale;
+    xch[ch * 128 + r] = mx;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float m = fmaxf(fmaxf(xch[r], xch[128 + r]), -1e30f);   // an all-padding row stays finite
+    float rowsum = 0.f;
+#pragma unroll 1
+    for (int c = ch * 4; c < ch * 4 + 4; ++c) {
+      uint32_t v[16];
+      tmem_ld_32x16(tS + lane_base + c * 16, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        float pr[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          float e = ex2_approx(fmaf(__uint_as_float(v[g * 8 + t]), c_scale, -m));
+          if (!full && c * 16 + g * 8 + t >= seqlen) e = 0.f;
+          rowsum += e;
+          pr[t] = e;
+        }
+        if (p.thresh16 != 0) {
+          const uint32_t keep = dropout_keep8(seed, p.stream, (erow + (uint64_t)(c * 16 + g * 8)) >> 3, p.thresh16);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) pr[t] = ((keep >> t) & 1u) ? pr[t] * p.inv_keep : 0.f;
+        }
+        *reinterpret_cast<uint4*>(sP + p_chunk_offset(r, c * 2 + g)) =
+            make_uint4(pack_bf16(pr[0], pr[1]), pack_bf16(pr[2], pr[3]), pack_bf16(pr[4], pr[5]), pack_bf16(pr[6], pr[7]));
+      }
+    }
+    xch[256 + ch * 128 + r] = rowsum;
+    fence_proxy_async();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    tc_fence_before();         // S reads retired before the PV MMA overwrites those columns
+    mbar_arrive(p_ready);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float l = xch[256 + r] + xch[256 + 128 + r];
+    mbar_wait(pv_done, 0);
+    tc_fence_after();
+    uint32_t o[32];
+    tmem_ld_32x32(tS + lane_base + ch * 32, o);
+    tmem_ld_wait();
+    if (r < p.S) {
+      const float inv_l = 1.f / l;
+      __nv_bfloat16* dst = p.ctx + (size_t)(row0 + r) * p.H + head * HD + ch * 32;
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        *reinterpret_cast<uint4*>(dst + g * 8) = make_uint4(
+            pack_bf16(__uint_as_float(o[g * 8]) * inv_l, __uint_as_float(o[g * 8 + 1]) * inv_l),
+            pack_bf16(__uint_as_float(o[g * 8 + 2]) * inv_l, __uint_as_float(o[g * 8 + 3]) * inv_l),
+            pack_bf16(__uint_as_float(o[g * 8 + 4]) * inv_l, __uint_as_float(o[g * 8 + 5]) * inv_l),
+            pack_bf16(__uint_as_float(o[g * 8 + 6]) * inv_l, __uint_as_float(o[g * 8 + 7]) * inv_l));
+      if (ch == 0) p.lse[(size_t)bh * p.S + r] = (m + log2f(l)) * 0.6931471805599453f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tS, 128);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -752,7 +907,13 @@ void attention_fwd(const void* qkv, const int* seqlens, void* ctx, float* lse, i
   const int H = h * d;
   CUtensorMap tm = make_tmap_2d_bf16(qkv, 3 * H, (uint64_t)B * S, 3 * H, 64, TILE);
   dim3 grid((S + TILE - 1) / TILE, B * h);
-  if (S <= TILE) {
+  static const bool single_ok = []() { const char* e = getenv("B200_ATTN_FWD_SINGLE"); return !(e && e[0] == '0'); }();
+  if (S <= TILE && single_ok) {
+    constexpr int SMEM1 = 16384 * 3 + 1024 + 64 + 2048;
+    static bool once1 = false;
+    if (!once1) { B200_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM1)); once1 = true; }
+    attn_fwd_single_kernel<<<grid, ATT_BWD_THREADS, SMEM1, st>>>(tm, a);
+  } else if (S <= TILE) {
     constexpr int SMEM = 16384 * 5 + 1024 + 128 + 3200;
     static bool once = false;
     if (!once) { B200_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); once = true; }
