@@ -706,6 +706,7 @@ attn_bwd_single_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gri
   uint64_t* ds_ready = bars + 4;           // 256 threads: dS is in shared memory
   uint64_t* fin = bars + 5;                // dK, dQ complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  float* xch = reinterpret_cast<float*>(bars + 8);   // [2 halves][128 rows]: partial delta = <dO, O> of a row
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.y;
@@ -782,7 +783,28 @@ attn_bwd_single_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gri
     const int q = r;
     const bool q_ok = q < p.S;
     const float lse2 = q_ok ? p.lse[(size_t)bh * p.S + q] * LOG2E : 0.f;
-    const float dlt = q_ok ? p.delta[(size_t)bh * p.S + q] : 0.f;
+    // delta = <dO, O> of the row, computed here instead of in a separate pass: this thread's 32 columns of O come
+    // from global memory (issued before any wait), dO from the tile TMA already brought in
+    uint4 ov[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      ov[g] = q_ok ? __ldg(reinterpret_cast<const uint4*>(p.ctx + (size_t)(row0 + q) * p.H + head * HD + ch * 32 + g * 8))
+                   : make_uint4(0, 0, 0, 0);
+    mbar_wait(in_full, 0);
+    float part = 0.f;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const uint4 dv = *reinterpret_cast<const uint4*>(sDO + r * 128 + (((ch * 4 + g) ^ (r & 7)) << 4));
+      const uint32_t a[4] = {ov[g].x, ov[g].y, ov[g].z, ov[g].w}, d[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 x = unpack_bf16(a[t]), y = unpack_bf16(d[t]);
+        part += x.x * y.x + x.y * y.y;
+      }
+    }
+    xch[ch * 128 + r] = part;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float dlt = q_ok ? xch[r] + xch[128 + r] : 0.f;
     const uint64_t erow = ((uint64_t)bh * p.S + (uint64_t)q) * (uint64_t)p.S;
     uint32_t dsp[32];                            // this thread's 64 dS values, packed bf16
     mbar_wait(sdp_ready, 0);
@@ -933,10 +955,14 @@ void attention_bwd(const void* qkv, const int* seqlens, const void* ctx, const v
   fill_args(a, B, S, h, d, seqlens, scale, seed, stream, p_drop);
   const int H = h * d;
   a.lse = const_cast<float*>(lse); a.delta = delta_ws; a.dqkv = (__nv_bfloat16*)dqkv; a.dq_acc = dq_acc;
-  const long long groups = (long long)B * S * h;
-  attn_delta_kernel<<<(unsigned)((groups * 8 + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)ctx,
-                                                                       (const __nv_bfloat16*)dctx, delta_ws, B, S, h, H);
+  a.ctx = (__nv_bfloat16*)const_cast<void*>(ctx);
   const int nkb = (S + TILE - 1) / TILE;
+  static const bool single_ok = []() { const char* e = getenv("B200_ATTN_BWD_SINGLE"); return !(e && e[0] == '0'); }();
+  if (!(nkb == 1 && single_ok)) {               // the single-block kernel computes delta itself
+    const long long groups = (long long)B * S * h;
+    attn_delta_kernel<<<(unsigned)((groups * 8 + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)ctx,
+                                                                         (const __nv_bfloat16*)dctx, delta_ws, B, S, h, H);
+  }
   if (nkb > 1) {
     if (dq_acc == nullptr) { fprintf(stderr, "[b200] attention_bwd needs a dq accumulation buffer when S > 128\n"); abort(); }
     B200_CUDA_CHECK(cudaMemsetAsync(dq_acc, 0, sizeof(float) * (size_t)B * S * H, st));
@@ -947,9 +973,8 @@ void attention_bwd(const void* qkv, const int* seqlens, const void* ctx, const v
   static bool once = false;
   if (!once) { B200_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); once = true; }
   dim3 grid(nkb, B * h);
-  static const bool single_ok = []() { const char* e = getenv("B200_ATTN_BWD_SINGLE"); return !(e && e[0] == '0'); }();
   if (nkb == 1 && single_ok) {                 // S <= 128: the two-CTAs-per-SM variant
-    constexpr int SMEM1 = 16384 * 6 + 1024 + 128;
+    constexpr int SMEM1 = 16384 * 6 + 1024 + 128 + 1024;
     static bool once1 = false;
     if (!once1) {
       B200_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM1));
