@@ -287,7 +287,7 @@ def test_checkpoint_activations_replays_dropout_exactly():
     a1.zero_grad(); a2.zero_grad()
     l1 = e1.forward_backward(*batch)
     l2 = e2.forward_backward(*batch)
-    assert l1.item() == l2.item()
+    assert abs(l1.item() - l2.item()) <= 1e-5 * abs(l1.item())      # the loss sum itself is reduced with atomics
     for (n, p), q in zip(m1.named_parameters(), m2.parameters()):
         scale = p.grad.abs().max().item() + 1e-12
         assert (p.grad - q.grad).abs().max().item() <= 1e-4 * scale, n      # split-K atomics reorder fp32 adds
