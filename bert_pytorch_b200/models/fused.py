@@ -526,7 +526,9 @@ class FusedPretrainer:
             graph = torch.cuda.CUDAGraph()
             n0 = K.KERNEL_LAUNCHES
             pool = next((e["graph"].pool() for e in self._graphs.values() if "graph" in e), None)
-            with torch.cuda.graph(graph, pool=pool):      # replays never overlap: all captures share one memory pool
+            # replays never overlap: all captures share one memory pool; thread_local: a data-loader thread that pins
+            # or allocates memory while we capture must not abort the capture
+            with torch.cuda.graph(graph, pool=pool, capture_error_mode="thread_local"):
                 self._seed_step.add_(1)
                 loss = self._program(*static, grad_scale, seed=eng._seed_base)
             ent.update(graph=graph, static=static, loss=loss, launches=K.KERNEL_LAUNCHES - n0, grad_scale=float(grad_scale))

@@ -70,8 +70,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs p) 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                  // 16 KB
   uint8_t* sK = smem + 16384;                          // KV_STAGES x 16 KB
-  uint8_t* sV = sK + 16384 * KV_STAGES;                // KV_STAGES x 16 KB
-  uint8_t* sP = sV + 16384 * KV_STAGES;                // 32 KB
+  uint8_t* sV = sK + 16384 * KV_STAGES;                // 16 KB: ONE V buffer (it is needed late, after the softmax of
+                                                       // its block, so the next V streams in behind the PV MMA) -- keeps
+                                                       // the streaming variant at 96 KB: two CTAs per SM
+  uint8_t* sP = sV + 16384;                            // 32 KB
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 32768);
   constexpr uint32_t TMEM_COLS = KV_STAGES == 1 ? 128 : 256;
   uint64_t* q_full = bars;               // 1
@@ -80,8 +82,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs p) 
   uint64_t* s_ready = bars + 5;
   uint64_t* p_ready = bars + 6;
   uint64_t* pv_done = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-  float* xch = reinterpret_cast<float*>(bars + 10);      // [2 buffers][2 halves][128 rows] row-max exchange (+ final sum)
+  uint64_t* v_full = bars + 8;
+  uint64_t* v_empty = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  float* xch = reinterpret_cast<float*>(bars + 12);      // [2 buffers][2 halves][128 rows] row-max exchange (+ final sum)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qb = blockIdx.x, bh = blockIdx.y;
@@ -94,6 +98,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs p) 
     tma_prefetch_desc(&tmap_qkv);
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    mbar_init(v_full, 1);
+    mbar_init(v_empty, 1);
     mbar_init(s_ready, 1);
     mbar_init(p_ready, 256);
     mbar_init(pv_done, 1);
@@ -112,26 +118,39 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs p) 
       const int cq = head * HD, ck = p.H + head * HD, cv = 2 * p.H + head * HD;
       mbar_arrive_expect_tx(q_full, 16384);
       tma_load_2d(sQ, &tmap_qkv, q_full, cq, row0 + qb * TILE);
+      // K blocks ride a KV_STAGES-deep ring (kv_full / kv_empty), V has one buffer (v_full / v_empty)
       for (int j = 0; j < min(KV_STAGES, nkb); ++j) {
-        mbar_arrive_expect_tx(&kv_full[j], 32768);
+        mbar_arrive_expect_tx(&kv_full[j], 16384);
         tma_load_2d(sK + j * 16384, &tmap_qkv, &kv_full[j], ck, row0 + j * TILE);
-        tma_load_2d(sV + j * 16384, &tmap_qkv, &kv_full[j], cv, row0 + j * TILE);
       }
+      mbar_arrive_expect_tx(v_full, 16384);
+      tma_load_2d(sV, &tmap_qkv, v_full, cv, row0);
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);  // Q K^T : both K-major
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, false, true);    // P V   : V is MN-major
       mbar_wait(q_full, 0);
-      for (int j = 0; j < nkb; ++j) {
+      const uint64_t dq = umma_smem_desc_sw128(smem_u32(sQ), 16, 1024);
+      auto issue_s = [&](int j) {              // S_j = Q K_j^T, then the K slot is free for block j + KV_STAGES
         const int st = KV_STAGES == 1 ? 0 : (j & 1);
-        mbar_wait(&kv_full[st], (j >> 1) & 1);
+        mbar_wait(&kv_full[st], (j / KV_STAGES) & 1);
         tc_fence_after();
-        const uint64_t dq = umma_smem_desc_sw128(smem_u32(sQ), 16, 1024);
         const uint64_t dk = umma_smem_desc_sw128(smem_u32(sK + st * 16384), 16, 1024);
 #pragma unroll
         for (int kk = 0; kk < HD / 16; ++kk) umma_bf16_ss(tS, dq + 2 * kk, dk + 2 * kk, idesc_s, kk > 0);
         umma_commit(s_ready);
-        mbar_wait(p_ready, j & 1);
+        umma_commit(&kv_empty[st]);
+      };
+      issue_s(0);
+      for (int j = 0; j < nkb; ++j) {
+        const int st = KV_STAGES == 1 ? 0 : (j & 1);
+        if (j + KV_STAGES < nkb) {             // refill the K slot S_j just released
+          mbar_wait(&kv_empty[st], (j / KV_STAGES) & 1);
+          mbar_arrive_expect_tx(&kv_full[st], 16384);
+          tma_load_2d(sK + st * 16384, &tmap_qkv, &kv_full[st], ck, row0 + (j + KV_STAGES) * TILE);
+        }
+        mbar_wait(p_ready, j & 1);             // P_j is in shared memory (and S_j has been consumed)
+        mbar_wait(v_full, j & 1);
         tc_fence_after();
-        const uint32_t ap = smem_u32(sP), av = smem_u32(sV + st * 16384);
+        const uint32_t ap = smem_u32(sP), av = smem_u32(sV);
 #pragma unroll
         for (int kk = 0; kk < TILE / 16; ++kk) {
           const uint64_t da = umma_smem_desc_sw128(ap + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024);
@@ -139,12 +158,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs p) 
           umma_bf16_ss(tO, da, db, idesc_o, kk > 0);
         }
         umma_commit(pv_done);
-        umma_commit(&kv_empty[st]);
-        if (KV_STAGES == 2 && j + 2 < nkb) {
-          mbar_wait(&kv_empty[st], (j >> 1) & 1);
-          mbar_arrive_expect_tx(&kv_full[st], 32768);
-          tma_load_2d(sK + st * 16384, &tmap_qkv, &kv_full[st], ck, row0 + (j + 2) * TILE);
-          tma_load_2d(sV + st * 16384, &tmap_qkv, &kv_full[st], cv, row0 + (j + 2) * TILE);
+        umma_commit(v_empty);
+        if (j + 1 < nkb) {
+          if (KV_STAGES > 1) issue_s(j + 1);   // the S accumulator is free: overlap Q K^T with the PV MMA's drain
+          mbar_wait(v_empty, j & 1);
+          mbar_arrive_expect_tx(v_full, 16384);
+          tma_load_2d(sV, &tmap_qkv, v_full, cv, row0 + (j + 1) * TILE);
+          if (KV_STAGES == 1) issue_s(j + 1);
         }
       }
     }
@@ -941,7 +961,7 @@ void attention_fwd(const void* qkv, const int* seqlens, void* ctx, float* lse, i
     if (!once) { B200_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); once = true; }
     attn_fwd_kernel<1><<<grid, ATT_BWD_THREADS, SMEM, st>>>(tm, a);
   } else {
-    constexpr int SMEM = 16384 * 7 + 1024 + 128 + 3200;
+    constexpr int SMEM = 16384 * 6 + 1024 + 128 + 3200;
     static bool once = false;
     if (!once) { B200_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); once = true; }
     attn_fwd_kernel<2><<<grid, ATT_BWD_THREADS, SMEM, st>>>(tm, a);
