@@ -87,8 +87,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint32_t taddr,
     tmem_ld_32x32(taddr + c * 32, v);
     tmem_ld_wait();
     float f[32];
+    if (alpha != 1.f) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * alpha;
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * alpha;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+    }
     const int ncols = min(32, p.N - n0);  // multiple of 8
     const size_t roff = (size_t)row * p.ldr + n0;
     const size_t ooff = (size_t)row * p.ldo + n0;
@@ -402,26 +407,35 @@ __device__ __forceinline__ void staged_pass(const GemmArgs& p, uint8_t* sC, uint
         }
       }
     } else {
+      // the bias loads are issued before the TMEM read so both latencies overlap; acc * alpha + bias is one FFMA
+      // per element, and nothing at all when there is no bias and alpha == 1 (the epilogue is instruction bound)
+      const int ncols = min(32, p.N - n0);
+      uint4 bq[4];
+      if (p.bias != nullptr) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          bq[g] = g * 8 < ncols ? __ldg(reinterpret_cast<const uint4*>(p.bias + n0 + g * 8)) : make_uint4(0, 0, 0, 0);
+      }
       uint32_t v[32];
       tmem_ld_32x32(taddr + col0, v);
       tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * alpha;
-      const int ncols = min(32, p.N - n0);
       if (p.bias != nullptr) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          if (g * 8 < ncols) {
-            const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.bias + n0 + g * 8));
-            const uint32_t w[4] = {b.x, b.y, b.z, b.w};
+          const uint32_t w[4] = {bq[g].x, bq[g].y, bq[g].z, bq[g].w};
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const float2 bb = unpack_bf16(w[t]);
-              f[g * 8 + 2 * t] += bb.x;
-              f[g * 8 + 2 * t + 1] += bb.y;
-            }
+          for (int t = 0; t < 4; ++t) {
+            const float2 bb = unpack_bf16(w[t]);
+            f[g * 8 + 2 * t] = fmaf(__uint_as_float(v[g * 8 + 2 * t]), alpha, bb.x);
+            f[g * 8 + 2 * t + 1] = fmaf(__uint_as_float(v[g * 8 + 2 * t + 1]), alpha, bb.y);
           }
         }
+      } else if (alpha != 1.f) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * alpha;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
       }
       if (MODE == 0) {
         if (p.epi == EPI_BIAS_TANH) {
