@@ -43,7 +43,7 @@ from .parallel import DataParallel, make_comm, unwrap
 from .utils import checkpoint as ckpt_utils
 from .utils import logging as logger
 from .utils.dist import get_rank, get_world_size, init_distributed, is_main_process
-from .utils.timing import DeviceTimer, max_over_ranks
+from .utils.timing import DeviceTimer, max_over_ranks, nvtx_range
 
 
 # ---------------------------------------------------------------------------
@@ -384,6 +384,12 @@ def main(args) -> Tuple[int, float]:
     def save(step_no: int) -> None:
         if args.skip_checkpoint:
             return
+        comm = getattr(model, "comm", None)
+        if comm is not None and getattr(model, "defer_reduction", False) and hasattr(comm, "gather_optimizer_state"):
+            # peer-memory backend: the LAMB moments (and, with a shard-local master, the fp32 weights) are partitioned;
+            # every rank joins the gather so that rank 0 writes the full per-parameter layout
+            comm.gather_optimizer_state()
+            comm.gather_master()
         payload: Dict[str, Any] = {
             "model": unwrap(model).state_dict(),
             "optimizer": optimizer.state_dict(),
@@ -399,6 +405,14 @@ def main(args) -> Tuple[int, float]:
             logger.info(f"Saved checkpoint {path}")
 
     done = global_step >= args.max_steps
+    # B200_PROFILE_DIR=<dir>: torch.profiler (CUPTI) trace of optimizer steps 2-3 of this session, one file per rank
+    profiler = None
+    if os.environ.get("B200_PROFILE_DIR") and device.type == "cuda":
+        from torch.profiler import ProfilerActivity, profile, schedule, tensorboard_trace_handler
+        profiler = profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA],
+                           schedule=schedule(wait=1, warmup=1, active=2, repeat=1),
+                           on_trace_ready=tensorboard_trace_handler(os.environ["B200_PROFILE_DIR"]))
+        profiler.start()
     timer.start()
     while not done:
         sampler.set_epoch(epoch)
@@ -406,8 +420,9 @@ def main(args) -> Tuple[int, float]:
             batch = [t.to(device, non_blocking=True) for t in batch]
             micro += 1
             sync = micro == acc
-            loss = forward_backward_pass(model, criterion, scaler, batch, acc, sync_grads=sync,
-                                         compute_dtype=args.compute_dtype)
+            with nvtx_range("micro_step_sync" if sync else "micro_step"):
+                loss = forward_backward_pass(model, criterion, scaler, batch, acc, sync_grads=sync,
+                                             compute_dtype=args.compute_dtype)
             window_loss += loss
             last_loss = loss
             session_seqs += batch[0].size(0)
@@ -415,7 +430,10 @@ def main(args) -> Tuple[int, float]:
                 continue
             for lrs in lr_schedulers:
                 lrs.step()
-            take_optimizer_step(optimizer, preconditioner, model, scaler)
+            with nvtx_range("optimizer_step"):
+                take_optimizer_step(optimizer, preconditioner, model, scaler)
+            if profiler is not None:
+                profiler.step()
             global_step += 1
             optimization_steps += 1
             micro = 0
@@ -440,6 +458,8 @@ def main(args) -> Tuple[int, float]:
             continue
         break
     train_ms = timer.stop()
+    if profiler is not None:
+        profiler.stop()
     loader.close()
     if pbar is not None:
         pbar.close()
