@@ -23,6 +23,7 @@ for s in $STAGES; do
     ncu_gemm) timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_pair_kernel -s 12 -c 2 -f -o gpurun_out/prof_gemm python tools/gemm_bench.py --only ${NCU_SHAPE:-ffn1_fwd} > gpurun_out/ncu_gemm.log 2>&1; echo "ncu_gemm rc=$?" ;;
     ncu_elt)  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"ln_fwd2|ln_bwd2|gelu_fwd|dgelu_bwd" -s 20 -c 4 -f -o gpurun_out/prof_elt python tools/elt_bench.py > gpurun_out/ncu_elt.log 2>&1; echo "ncu_elt rc=$?" ;;
     ncu_all)  timeout 900 ncu --set full --profile-from-start off --clock-control none --import-source on -f -o gpurun_out/prof_all python tools/ncu_targets.py > gpurun_out/ncu_all.log 2>&1; echo "ncu_all rc=$?"; tail -3 gpurun_out/ncu_all.log ;;
+    sanitize) timeout 420 compute-sanitizer --tool ${SAN_TOOL:-memcheck} --error-exitcode 9 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_gemm.py -q -x --timeout 400 -k "layer_norm_fwd_bwd or gelu_kernels or colsum or embedding_fwd_bwd or mlm_compact or (gemm_nt and 256-256-128)" > gpurun_out/sanitize_${SAN_TOOL:-memcheck}.log 2>&1; echo "sanitize rc=$?"; tail -6 gpurun_out/sanitize_${SAN_TOOL:-memcheck}.log ;;
     eltbench) timeout 300 python tools/elt_bench.py > gpurun_out/elt_bench.json 2> gpurun_out/elt_bench.err; echo "eltbench rc=$?"; cat gpurun_out/elt_bench.json ;;
     ncu_attn) timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_ -s 6 -c 3 -f -o gpurun_out/prof_attn python tools/attn_bench.py > gpurun_out/ncu_attn.log 2>&1; echo "ncu_attn rc=$?" ;;
     attnbench) timeout 300 python tools/attn_bench.py > gpurun_out/attn_bench.json 2> gpurun_out/attn_bench.err; echo "attnbench rc=$?"; cat gpurun_out/attn_bench.json ;;
