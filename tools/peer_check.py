@@ -197,6 +197,19 @@ def main():
             a_f.flat_grad.normal_()
             t_f = timeit(run_fused)
             out[f"fused_ms_mc{int(mc)}"] = round(t_f, 3)
+            comm.push_master = False                         # ZeRO-1 style: only bf16 weights + fp32 1-D tensors travel
+            out[f"fused_ms_mc{int(mc)}_master_local"] = round(timeit(run_fused), 3)
+            comm.push_master = True
+            # with the weight-gradient tiles already reduced by the GEMM epilogues (push mode), phase A is local for 90 %
+            eng_names = [s_.name for s_ in a_f.slots if s_.name.endswith(".weight") and ".encoder.layer." in s_.name
+                         and "LayerNorm" not in s_.name]
+            comm.set_prereduced(eng_names)
+            def run_fused_pre():
+                comm._pushed = True
+                comm.fused_lamb_step(o_f, loss_scale=1.0)
+            out[f"fused_ms_mc{int(mc)}_prereduced"] = round(timeit(run_fused_pre), 3)
+            comm.push_master = False
+            out[f"fused_ms_mc{int(mc)}_prereduced_master_local"] = round(timeit(run_fused_pre), 3)
             del comm, m_f, a_f, o_f
             torch.cuda.empty_cache()
         m_r, a_r, o_r, _ = build(big, dev, False)
@@ -211,6 +224,12 @@ def main():
         rs_bytes = 4.0 * n * (world - 1) / world          # gradient shards pulled from the peers
         ag_bytes = 6.0 * n * (world - 1) / world          # fp32 + bf16 pushed to the peers
         out["roofline_ms_nvlink"] = round(max(rs_bytes, ag_bytes) / link * 1e3, 3)
+        hbm = 6.5e12                                      # measured copy bandwidth (MEASURED_PEAKS.json)
+        lamb_bytes = (28.0 + 18.0) * n / world            # phase B (g,p,m,v in; m,v,u out) + phase C local traffic + zeroing share
+        # the three phases depend on each other (global norm, trust ratios): their times add up
+        out["roofline_ms_serial"] = round((rs_bytes / link + lamb_bytes / hbm + 4.0 * n / hbm + ag_bytes / link) * 1e3, 3)
+        out["roofline_ms_serial_bf16_allgather"] = round((rs_bytes / link + lamb_bytes / hbm + 4.0 * n / hbm
+                                                          + 2.0 * n * (world - 1) / world / link) * 1e3, 3)
         out["arena_numel"] = n
     if rank == 0:
         print(json.dumps(out), flush=True)
