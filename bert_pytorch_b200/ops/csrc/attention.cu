@@ -229,9 +229,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs p) 
             pr[t] = e;
           }
           if (p.thresh16 != 0) {
-            const uint32_t keep = dropout_keep8(seed, p.stream, (erow + (uint64_t)(k0 + g * 8)) >> 3, p.thresh16);
+            const Keep8 keep = dropout_keep8(seed, p.stream, (erow + (uint64_t)(k0 + g * 8)) >> 3, p.thresh16);
 #pragma unroll
-            for (int t = 0; t < 8; ++t) pr[t] = ((keep >> t) & 1u) ? pr[t] * p.inv_keep : 0.f;
+            for (int t = 0; t < 8; ++t) pr[t] = keep[t] ? pr[t] * p.inv_keep : 0.f;
           }
           const uint4 pk = make_uint4(pack_bf16(pr[0], pr[1]), pack_bf16(pr[2], pr[3]), pack_bf16(pr[4], pr[5]),
                                       pack_bf16(pr[6], pr[7]));
@@ -393,9 +393,9 @@ attn_fwd_single_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnA
           pr[t] = e;
         }
         if (p.thresh16 != 0) {
-          const uint32_t keep = dropout_keep8(seed, p.stream, (erow + (uint64_t)(c * 16 + g * 8)) >> 3, p.thresh16);
+          const Keep8 keep = dropout_keep8(seed, p.stream, (erow + (uint64_t)(c * 16 + g * 8)) >> 3, p.thresh16);
 #pragma unroll
-          for (int t = 0; t < 8; ++t) pr[t] = ((keep >> t) & 1u) ? pr[t] * p.inv_keep : 0.f;
+          for (int t = 0; t < 8; ++t) pr[t] = keep[t] ? pr[t] * p.inv_keep : 0.f;
         }
         *reinterpret_cast<uint4*>(sP + p_chunk_offset(r, c * 2 + g)) =
             make_uint4(pack_bf16(pr[0], pr[1]), pack_bf16(pr[2], pr[3]), pack_bf16(pr[4], pr[5]), pack_bf16(pr[6], pr[7]));
@@ -610,7 +610,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         const int k0 = kb * TILE + c * 32;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          uint32_t keep = 0xFFu;
+          Keep8 keep = Keep8::all();
           if (p.thresh16 != 0)
             keep = dropout_keep8(seed, p.stream, (erow + (uint64_t)(k0 + g * 8)) >> 3, p.thresh16);
           float pd[8], ds[8];
@@ -619,7 +619,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
             const int key = k0 + g * 8 + t;
             const bool ok = q_ok && key < seqlen;
             const float pr = ok ? ex2_approx(fmaf(__uint_as_float(sv[g * 8 + t]), c_scale, -lse2)) : 0.f;
-            const bool kp = (keep >> t) & 1u;
+            const bool kp = keep[t];
             const float dp = kp ? __uint_as_float(dv[g * 8 + t]) * p.inv_keep : 0.f;
             pd[t] = kp ? pr * p.inv_keep : 0.f;
             ds[t] = pr * (dp - dlt) * p.scale;
@@ -839,7 +839,7 @@ attn_bwd_single_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gri
       const int k0 = c16 * 16;
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
-        uint32_t keep = 0xFFu;
+        Keep8 keep = Keep8::all();
         if (p.thresh16 != 0) keep = dropout_keep8(seed, p.stream, (erow + (uint64_t)(k0 + g * 8)) >> 3, p.thresh16);
         float pd[8], ds[8];
 #pragma unroll
@@ -847,7 +847,7 @@ attn_bwd_single_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gri
           const int key = k0 + g * 8 + t;
           const bool ok = q_ok && key < seqlen;
           const float pr = ok ? ex2_approx(fmaf(__uint_as_float(sv[g * 8 + t]), c_scale, -lse2)) : 0.f;
-          const bool kp = (keep >> t) & 1u;
+          const bool kp = keep[t];
           const float dp = kp ? __uint_as_float(dv[g * 8 + t]) * p.inv_keep : 0.f;
           pd[t] = kp ? pr * p.inv_keep : 0.f;
           ds[t] = pr * (dp - dlt) * p.scale;

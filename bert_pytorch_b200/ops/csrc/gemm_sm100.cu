@@ -190,9 +190,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint32_t taddr,
         for (int g = 0; g < 4; ++g) {
           if (g * 8 < ncols) {
             const uint64_t e8 = ((uint64_t)row * (uint64_t)p.N + (uint64_t)(n0 + g * 8)) >> 3;
-            const uint32_t keep = dropout_keep8(seed, p.stream, e8, p.drop_thresh16);
+            const Keep8 keep = dropout_keep8(seed, p.stream, e8, p.drop_thresh16);
 #pragma unroll
-            for (int t = 0; t < 8; ++t) f[g * 8 + t] = ((keep >> t) & 1u) ? f[g * 8 + t] * p.drop_scale : 0.f;
+            for (int t = 0; t < 8; ++t) f[g * 8 + t] = keep[t] ? f[g * 8 + t] * p.drop_scale : 0.f;
           }
         }
       }
@@ -446,9 +446,9 @@ __device__ __forceinline__ void staged_pass(const GemmArgs& p, uint8_t* sC, uint
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const uint64_t e8 = ((uint64_t)row * (uint64_t)p.N + (uint64_t)(n0 + g * 8)) >> 3;
-            const uint32_t keep = dropout_keep8(seed, p.stream, e8, p.drop_thresh16);
+            const Keep8 keep = dropout_keep8(seed, p.stream, e8, p.drop_thresh16);
 #pragma unroll
-            for (int t = 0; t < 8; ++t) f[g * 8 + t] = ((keep >> t) & 1u) ? f[g * 8 + t] * p.drop_scale : 0.f;
+            for (int t = 0; t < 8; ++t) f[g * 8 + t] = keep[t] ? f[g * 8 + t] * p.drop_scale : 0.f;
           }
         }
         if (use_res) {

@@ -182,12 +182,12 @@ ln_fwd2_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ ga
     const float mean = shift + ms;
     const float rstd = rsqrtf(fmaxf(r.y / (float)H - ms * ms, 0.f) + eps);
     if (live) {
-      uint32_t keep = 0xFFu;
+      Keep8 keep = Keep8::all();
       if (thresh16 != 0) keep = dropout_keep8(seed, stream, ((uint64_t)row * H + col) >> 3, thresh16);
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
         float o = (v[t] - mean) * rstd * g[t] + b[t];
-        if (thresh16 != 0) o = ((keep >> t) & 1u) ? o * drop_scale : 0.f;
+        if (thresh16 != 0) o = keep[t] ? o * drop_scale : 0.f;
         v[t] = o;
       }
       store8(y + (size_t)row * H + col, v);
@@ -247,9 +247,9 @@ ln_bwd2_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __rest
       nmu = mean[nrow]; nrs = rstd[nrow];
     }
     if (in_stream != 0xFFFFFFFFu && thresh16 != 0 && live) {
-      const uint32_t keep = dropout_keep8(seed, in_stream, ((uint64_t)row * H + col) >> 3, thresh16);
+      const Keep8 keep = dropout_keep8(seed, in_stream, ((uint64_t)row * H + col) >> 3, thresh16);
 #pragma unroll
-      for (int t = 0; t < 8; ++t) d[t] = ((keep >> t) & 1u) ? d[t] * drop_scale : 0.f;
+      for (int t = 0; t < 8; ++t) d[t] = keep[t] ? d[t] * drop_scale : 0.f;
     }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -272,9 +272,9 @@ ln_bwd2_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __rest
       store8(dx + (size_t)row * H + col, d);
       if (dxd != nullptr) {
         if (thresh16 != 0) {
-          const uint32_t keep = dropout_keep8(seed, drop_stream, ((uint64_t)row * H + col) >> 3, thresh16);
+          const Keep8 keep = dropout_keep8(seed, drop_stream, ((uint64_t)row * H + col) >> 3, thresh16);
 #pragma unroll
-          for (int t = 0; t < 8; ++t) d[t] = ((keep >> t) & 1u) ? d[t] * drop_scale : 0.f;
+          for (int t = 0; t < 8; ++t) d[t] = keep[t] ? d[t] * drop_scale : 0.f;
         }
 #pragma unroll
         for (int t = 0; t < 8; ++t) ad[t] += d[t];
@@ -486,12 +486,12 @@ embed_fwd_kernel(const int* __restrict__ ids, const int* __restrict__ seg, const
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) {
       const int col = c * 256 + lane * 8;
-      uint32_t keep = 0xFFu;
+      Keep8 keep = Keep8::all();
       if (thresh16 != 0 && col < H) keep = dropout_keep8(seed, stream, ((uint64_t)row * H + col) >> 3, thresh16);
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
         float o = (v[c][t] - mean) * rstd * g[c][t] + b[c][t];
-        if (thresh16 != 0) o = ((keep >> t) & 1u) ? o * drop_scale : 0.f;
+        if (thresh16 != 0) o = keep[t] ? o * drop_scale : 0.f;
         v[c][t] = o;
       }
     }
