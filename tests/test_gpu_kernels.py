@@ -327,3 +327,38 @@ def test_cuda_graph_replay_matches_eager_program():
         losses.append(e_d.forward_backward(*base).item())
     assert any("graph" in ent for ent in e_d._graphs.values())
     assert len({round(x, 6) for x in losses[3:]}) == 3, losses
+
+
+def test_kfac_taps_of_the_fused_engine_match_module_hooks():
+    """K-FAC statistics collected from the engine's saved activations (no module hooks fire on the fused path)
+    equal the ones the hooks collect on the autograd path; the preconditioned step keeps gradients finite."""
+    from bert_pytorch_b200 import kfac
+    from bert_pytorch_b200.models import BertPretrainingCriterion
+    from bert_pytorch_b200.models.arena import ParamArena
+    m_f = _tiny_model().cuda()
+    m_t = copy.deepcopy(m_f)
+    for p in m_t.parameters():
+        p.data = p.data.to(torch.bfloat16).float()
+    m_t.bert.use_fused = False
+    a_f = ParamArena(m_f)
+    skip = ["BertLMPredictionHead", "embedding"]
+    k_f = kfac.KFAC(m_f, factor_update_freq=1, inv_update_freq=1, skip_layers=skip, damping=0.003)
+    k_t = kfac.KFAC(m_t, factor_update_freq=1, inv_update_freq=1, skip_layers=skip, damping=0.003)
+    m_f.train(); m_t.train()
+    ids, seg, mask, labels, nsl = _batch()
+    a_f.zero_grad()
+    eng = m_f.pretrain_engine()
+    eng.forward_backward(ids, seg, mask, labels, nsl)
+    crit = BertPretrainingCriterion(m_t.config.vocab_size)
+    scores, nsp = m_t(ids, seg, mask)
+    crit(scores, labels, nsp, nsl).backward()
+    name = "bert.encoder.layer.1.output.dense"
+    lf, lt = k_f.layer(name), k_t.layer(name)
+    assert lf is not None and lf.A_new is not None and lt.A_new is not None
+    for key in ("A_new", "G_new"):
+        a, b = getattr(lf, key).float(), getattr(lt, key).float()
+        rel = (a - b).norm() / b.norm()
+        assert rel < 5e-2, (key, rel.item())
+    k_f.step()
+    assert all(torch.isfinite(p.grad).all() for p in m_f.parameters() if p.grad is not None)
+    assert not any("graph" in e for e in eng._graphs.values())      # Python-side taps: no graph capture with K-FAC
