@@ -595,6 +595,9 @@ class FusedPretrainer:
             onehot = F.one_hot(tgt_n.clamp(min=0), nsp_logits.size(-1)).float()
             nsp_loss = -((logp * onehot).sum(-1) * valid).sum() / n_valid
             d_logits = (logp.exp() - onehot) * (valid / n_valid * grad_scale).unsqueeze(1)
+            kf = getattr(self.model.bert, "_kfac", None)
+            if kf is not None:                     # the NSP classifier is an nn.Linear: K-FAC preconditions it too
+                kf.tap("cls.seq_relationship", pooled, d_logits)
             nsp.weight.grad.addmm_(d_logits.t(), pooled)
             nsp.bias.grad.add_(d_logits.sum(0))
             d_z = (d_logits @ w_nsp) * (1.0 - pooled * pooled)
