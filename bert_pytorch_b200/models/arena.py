@@ -127,6 +127,9 @@ class ParamArena:
 
     @torch.no_grad()
     def refresh_shadow(self) -> None:
+        sync = getattr(self, "_master_sync", None)
+        if sync is not None:          # peer-memory backend with a shard-local fp32 master: complete it first
+            sync()
         self.version += 1
         if self.flat_shadow is not None:
             self.flat_shadow.copy_(self.flat_param)

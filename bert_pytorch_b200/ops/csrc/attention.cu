@@ -25,7 +25,8 @@
 namespace b200 {
 
 constexpr int ATT_THREADS = 160;   // forward: 4 softmax warps + 1 control warp
-constexpr int ATT_BWD_THREADS = 288;   // backward: 8 math warps (2 per TMEM lane quarter) + 1 control warp
+constexpr int ATT_BWD_THREADS = 288;   // 8 math warps (2 per TMEM lane quarter) + 1 control warp
+constexpr int ATT_BWD16_THREADS = 544; // streaming backward: 16 math warps (4 per TMEM lane quarter) + 1 control warp
 constexpr int TILE = 128;          // query rows / key rows per block
 constexpr int HD = 64;             // head dim
 constexpr float LOG2E = 1.4426950408889634f;
@@ -464,7 +465,10 @@ attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __re
   }
 }
 
-__global__ void __launch_bounds__(ATT_BWD_THREADS, 1)
+// 16 math warps: four threads per query row (TMEM lane quarter = warp & 3, 32-key column quarter = warp >> 2).  With
+// one CTA per SM (512 TMEM columns, 160 KB) the kernel is bound by the latency of the per-thread softmax-gradient
+// chain; twice the warps halve it.  16-column TMEM loads keep the kernel under the 120 registers 544 threads allow.
+__global__ void __launch_bounds__(ATT_BWD16_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
                 const AttnArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -510,18 +514,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     return;
   }
 
-  if (threadIdx.x == 256) {
+  if (threadIdx.x == 512) {
     tma_prefetch_desc(&tmap_qkv);
     tma_prefetch_desc(&tmap_do);
     mbar_init(kv_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
     mbar_init(sdp_ready, 1);
-    mbar_init(ds_ready, 256);
+    mbar_init(ds_ready, 512);
     mbar_init(dq_ready, 1);
     mbar_init(fin, 1);
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(tmem_slot, 512);
+  if (warp == 16) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -529,7 +533,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   const unsigned long long seed = p.thresh16 != 0 ? p.seed.value() : 0ull;
   const uint32_t tS = tmem, tDP = tmem + 128, tDV = tmem + 256, tDK = tmem + 320, tDQ = tmem + 384;
 
-  if (warp == 8) {
+  if (warp == 16) {
     if (lane == 0) {
       const int cq = head * HD, ck = p.H + head * HD, cv = 2 * p.H + head * HD;
       mbar_arrive_expect_tx(kv_full, 32768);
@@ -590,7 +594,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     }
   } else {
     const int r = (warp & 3) * 32 + lane;        // query row inside the tile == TMEM lane
-    const int ch = warp >> 2;                    // which 64-column half this thread handles
+    const int ch = warp >> 2;                    // which 32-key column quarter this thread handles
     const uint32_t lane_base = uint32_t((warp & 3) * 32) << 16;
     const float c_scale = p.scale * LOG2E;
     for (int i = 0; i < nqb; ++i) {
@@ -601,15 +605,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       const uint64_t erow = ((uint64_t)bh * p.S + (uint64_t)q) * (uint64_t)p.S;
       mbar_wait(sdp_ready, i & 1);
       tc_fence_after();
-#pragma unroll 1
-      for (int c = ch * 2; c < ch * 2 + 2; ++c) {
-        uint32_t sv[32], dv[32];
-        tmem_ld_32x32(tS + lane_base + c * 32, sv);
-        tmem_ld_32x32(tDP + lane_base + c * 32, dv);
-        tmem_ld_wait();
-        const int k0 = kb * TILE + c * 32;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+      for (int sc = 0; sc < 2; ++sc) {           // two 16-column sub-chunks
+        const int c16 = ch * 2 + sc;
+        uint32_t sv[16], dv[16];
+        tmem_ld_32x16(tS + lane_base + c16 * 16, sv);
+        tmem_ld_32x16(tDP + lane_base + c16 * 16, dv);
+        tmem_ld_wait();
+        const int k0 = kb * TILE + c16 * 16;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
           Keep8 keep = Keep8::all();
           if (p.thresh16 != 0)
             keep = dropout_keep8(seed, p.stream, (erow + (uint64_t)(k0 + g * 8)) >> 3, p.thresh16);
@@ -624,7 +629,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
             pd[t] = kp ? pr * p.inv_keep : 0.f;
             ds[t] = pr * (dp - dlt) * p.scale;
           }
-          const uint32_t off = p_chunk_offset(r, c * 4 + g);
+          const uint32_t off = p_chunk_offset(r, c16 * 2 + g);
           *reinterpret_cast<uint4*>(sPd + off) = make_uint4(pack_bf16(pd[0], pd[1]), pack_bf16(pd[2], pd[3]),
                                                             pack_bf16(pd[4], pd[5]), pack_bf16(pd[6], pd[7]));
           *reinterpret_cast<uint4*>(sDS + off) = make_uint4(pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]),
@@ -637,24 +642,23 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       mbar_wait(dq_ready, i & 1);
       tc_fence_after();
       {
-        const int c = ch;                        // each thread writes 32 of the 64 dQ columns of its row
-        uint32_t v[32];
-        tmem_ld_32x32(tDQ + lane_base + c * 32, v);
+        uint32_t v[16];                          // each thread writes 16 of the 64 dQ columns of its row
+        tmem_ld_32x16(tDQ + lane_base + ch * 16, v);
         tmem_ld_wait();
         if (q_ok) {
           if (nkb_total == 1) {
-            __nv_bfloat16* dq = p.dqkv + (size_t)(row0 + q) * 3 * p.H + head * HD + c * 32;
+            __nv_bfloat16* dq = p.dqkv + (size_t)(row0 + q) * 3 * p.H + head * HD + ch * 16;
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
+            for (int g = 0; g < 2; ++g)
               *reinterpret_cast<uint4*>(dq + g * 8) = make_uint4(
                   pack_bf16(__uint_as_float(v[g * 8]), __uint_as_float(v[g * 8 + 1])),
                   pack_bf16(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3])),
                   pack_bf16(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5])),
                   pack_bf16(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7])));
           } else {
-            float* dq = p.dq_acc + (size_t)(row0 + q) * p.H + head * HD + c * 32;
+            float* dq = p.dq_acc + (size_t)(row0 + q) * p.H + head * HD + ch * 16;
 #pragma unroll
-            for (int g = 0; g < 8; ++g)
+            for (int g = 0; g < 4; ++g)
               asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dq + g * 4),
                            "f"(__uint_as_float(v[g * 4])), "f"(__uint_as_float(v[g * 4 + 1])),
                            "f"(__uint_as_float(v[g * 4 + 2])), "f"(__uint_as_float(v[g * 4 + 3]))
@@ -664,34 +668,31 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       }
       tc_fence_before();   // dQ TMEM reads done before the next block's MMA may overwrite it
     }
-    // dK / dV of this key block
+    // dK / dV of this key block: column quarters 0,1 write the two halves of dK, quarters 2,3 those of dV
     mbar_wait(fin, 0);
     tc_fence_after();
     const int key = kb * TILE + r;
     {
-      const int w = ch;                   // column half 0 writes dK, half 1 writes dV
+      const int w = ch >> 1, c = ch & 1;
       const uint32_t src = w == 0 ? tDK : tDV;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(src + lane_base + c * 32, v);
-        tmem_ld_wait();
-        if (key < p.S) {
-          __nv_bfloat16* dst = p.dqkv + (size_t)(row0 + key) * 3 * p.H + (w + 1) * p.H + head * HD + c * 32;
+      uint32_t v[32];
+      tmem_ld_32x32(src + lane_base + c * 32, v);
+      tmem_ld_wait();
+      if (key < p.S) {
+        __nv_bfloat16* dst = p.dqkv + (size_t)(row0 + key) * 3 * p.H + (w + 1) * p.H + head * HD + c * 32;
 #pragma unroll
-          for (int g = 0; g < 4; ++g)
-            *reinterpret_cast<uint4*>(dst + g * 8) = make_uint4(
-                pack_bf16(__uint_as_float(v[g * 8]), __uint_as_float(v[g * 8 + 1])),
-                pack_bf16(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3])),
-                pack_bf16(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5])),
-                pack_bf16(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7])));
-        }
+        for (int g = 0; g < 4; ++g)
+          *reinterpret_cast<uint4*>(dst + g * 8) = make_uint4(
+              pack_bf16(__uint_as_float(v[g * 8]), __uint_as_float(v[g * 8 + 1])),
+              pack_bf16(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3])),
+              pack_bf16(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5])),
+              pack_bf16(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7])));
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 16) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
@@ -1003,7 +1004,7 @@ void attention_bwd(const void* qkv, const int* seqlens, const void* ctx, const v
     attn_bwd_single_kernel<<<grid, ATT_BWD_THREADS, SMEM1, st>>>(tq, td, a);
     return;
   }
-  attn_bwd_kernel<<<grid, ATT_BWD_THREADS, SMEM, st>>>(tq, td, a);
+  attn_bwd_kernel<<<grid, ATT_BWD16_THREADS, SMEM, st>>>(tq, td, a);
   if (nkb > 1) {
     const long long work = (long long)B * S * (H / 8);
     int g = (int)((work + 255) / 256);

@@ -38,9 +38,11 @@ class PeerComm(TorchComm):
     def __init__(self, group=None, use_multicast: Optional[bool] = None, push_master: Optional[bool] = None):
         super().__init__(group)
         import os
-        # push_master=False keeps the fp32 master weights shard-local (ZeRO-1 style): only the bf16 shadow the
-        # kernels read is all-gathered, 3x less NVLink traffic; ``gather_master()`` restores full fp32 views
-        # before anything reads them (checkpoint, torch-path evaluation).  B200_PEER_MASTER_LOCAL=1 selects it.
+        # push_master=False keeps the fp32 master weights shard-local (ZeRO-1 style): only the bf16 weights the
+        # kernels read (and the fp32 1-D tensors) are all-gathered, 3x less NVLink traffic: 3.2 vs 5.0 ms per step
+        # at 8 GPUs (profiles/peer_check_r1_8gpu.log).  ``gather_master()`` completes the fp32 views before
+        # anything reads them (checkpoint, ``arena.refresh_shadow``, torch-path evaluation).  The pre-training
+        # runtime selects it (pretrain.configure_fused_reduction); B200_PEER_MASTER_LOCAL=0/1 overrides.
         if push_master is None:
             push_master = os.environ.get("B200_PEER_MASTER_LOCAL", "0") != "1"
         self.push_master = bool(push_master)
@@ -83,8 +85,11 @@ class PeerComm(TorchComm):
             p.grad = self.grad_t[s.offset:s.offset + s.numel].view(s.shape)
         arena._opt_tables = None
         self.arena = arena
+        arena._master_sync = self.gather_master
         mc_ok = all(int(getattr(h, "multicast_ptr", 0) or 0) != 0 for h in (self.grad_h, self.param_h))
-        self.use_multicast = mc_ok if self._want_mc is None else (bool(self._want_mc) and mc_ok)
+        # NVLS multimem wins from 4 ranks up (in-switch reduction / replication); at 2 ranks plain P2P is faster
+        # (measured: profiles/peer_check_r1_2gpu_v3.log, peer_check_r1_8gpu.log)
+        self.use_multicast = (mc_ok and self.world_size > 2) if self._want_mc is None else (bool(self._want_mc) and mc_ok)
         self.lo, self.hi = arena.shard_bounds(self.world_size, self.rank, GRANULE)
         # chunk table of the arena restricted to the shard
         ct, cs, cl = [], [], []

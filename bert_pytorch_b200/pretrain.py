@@ -249,6 +249,8 @@ def configure_fused_reduction(model, preconditioner=None) -> None:
     if comm is None or not getattr(comm, "fuses_optimizer", False):
         return
     model.defer_reduction = preconditioner is None
+    if model.defer_reduction and "B200_PEER_MASTER_LOCAL" not in os.environ and hasattr(comm, "push_master"):
+        comm.push_master = False      # fp32 master stays with its owner; checkpoints gather it (save())
     base = unwrap(model)
     eng = base.pretrain_engine() if hasattr(base, "pretrain_engine") else None
     if model.defer_reduction and eng is not None and os.environ.get("B200_PEER_PUSH", "1") != "0":
