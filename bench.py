@@ -249,6 +249,9 @@ def run_reference(args, ph, B, accum, rank, world, dev):
         kfac_damping=0.003, kfac_kl_clip=0.001, kfac_skip_layers=["BertLMPredictionHead", "embedding"],
         local_rank=int(os.environ.get("LOCAL_RANK", 0)))
     os.makedirs(ns.output_dir, exist_ok=True)
+    # the reference creates its output tree on the main process only but every rank lists it (run_pretraining.py:246);
+    # with per-rank scratch directories each rank makes its own
+    os.makedirs(os.path.join(ns.output_dir, "pretrain_ckpts"), exist_ok=True)
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     os.environ.setdefault("MASTER_PORT", "29534")
     os.environ.setdefault("RANK", "0")
