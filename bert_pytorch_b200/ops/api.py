@@ -77,6 +77,37 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, layout: int = NT, epi: int = EPI_N
     return out
 
 
+def mx_quantize(x: torch.Tensor):
+    """bf16 [R, K] -> (e4m3 bytes [R, K], ue8m0 block scales in the tensor-core layout): OCP MXFP8, one scale per
+    32 elements along K (csrc/gemm_mx.cu)."""
+    R, Kd = x.shape
+    q = torch.empty(R, Kd, dtype=torch.uint8, device=x.device)
+    sf = torch.empty(((R + 127) // 128) * (Kd // 128) * 512, dtype=torch.uint8, device=x.device)
+    extension().mx_quantize(x, q, sf)
+    _count()
+    return q, sf
+
+
+def mx_dequantize(q: torch.Tensor, sf: torch.Tensor) -> torch.Tensor:
+    """fp32 view of an MXFP8 tensor (test / debugging aid; plain torch)."""
+    R, Kd = q.shape
+    rows = torch.arange(R, device=q.device)
+    groups = torch.arange(Kd // 32, device=q.device)
+    idx = ((rows[:, None] // 128) * (Kd // 128) + groups[None, :] // 4) * 512 + (rows[:, None] % 32) * 16 \
+        + ((rows[:, None] // 32) % 4) * 4 + groups[None, :] % 4
+    scale = torch.exp2(sf.long()[idx].float() - 127.0)                    # [R, K/32]
+    return q.view(torch.float8_e4m3fn).float() * scale.repeat_interleave(32, dim=1)
+
+
+def gemm_mx(a_q: torch.Tensor, a_sf: torch.Tensor, b_q: torch.Tensor, b_sf: torch.Tensor, *,
+            bias: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """D = A . B^T on block-scaled fp8 operands (tcgen05.mma.kind::mxf8f6f4.block_scale, scales staged in TMEM)."""
+    out = torch.empty(a_q.size(0), b_q.size(0), dtype=out_dtype, device=a_q.device)
+    extension().gemm_mxfp8(a_q, a_sf, b_q, b_sf, out, bias)
+    _count()
+    return out
+
+
 class Fp8Meta:
     """Device-resident per-tensor scaling records ``{amax, scale, inv_scale, _}`` for the fp8 GEMM path
     (delayed scaling: quantise with the scale derived from the previous step's amax; csrc/fp8.cu)."""

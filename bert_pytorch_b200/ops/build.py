@@ -23,11 +23,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
 
-CUDA_SOURCES = ["gemm_sm100.cu", "norm_embed.cu", "optim.cu", "loss.cu", "attention.cu", "comm.cu", "fp8.cu"]
+CUDA_SOURCES = ["gemm_sm100.cu", "norm_embed.cu", "optim.cu", "loss.cu", "attention.cu", "comm.cu", "fp8.cu", "gemm_mx.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--use_fast_math", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 # erff/expf accuracy matters for GELU and softmax statistics -> no fast-math there
-PRECISE = {"gemm_sm100.cu", "norm_embed.cu", "optim.cu", "loss.cu", "attention.cu", "comm.cu", "fp8.cu"}
+PRECISE = {"gemm_sm100.cu", "norm_embed.cu", "optim.cu", "loss.cu", "attention.cu", "comm.cu", "fp8.cu", "gemm_mx.cu"}
 
 
 def _cuda_home() -> str:

@@ -401,6 +401,37 @@ void peer_allreduce(int64_t rank, int64_t world, bool use_multicast, std::vector
   b200::peer_allreduce(L, cur_stream());
 }
 
+// MXFP8: bf16 [R, K] -> e4m3 bytes [R, K] + ue8m0 block scales (one per 32 elements of K) in the tensor core's
+// scale-factor layout [ceil(R/128)][K/128][512]
+void mx_quantize(Tensor x, Tensor q, Tensor sf) {
+  check_bf16(x, "x");
+  TORCH_CHECK(x.dim() == 2 && x.is_contiguous() && x.size(1) % 128 == 0, "mx_quantize: contiguous [R, K] with K % 128 == 0");
+  const int64_t R = x.size(0), K = x.size(1);
+  TORCH_CHECK(q.is_cuda() && q.is_contiguous() && q.element_size() == 1 && q.numel() == R * K, "mx_quantize: q shape");
+  TORCH_CHECK(sf.is_cuda() && sf.is_contiguous() && sf.element_size() == 1 &&
+              sf.numel() == ((R + 127) / 128) * (K / 128) * 512, "mx_quantize: sf shape");
+  c10::cuda::CUDAGuard guard(x.device());
+  b200::mx_quantize(x.data_ptr(), q.data_ptr(), sf.data_ptr(), (int)R, (int)K, cur_stream());
+}
+
+// D[M,N] = A[M,K] . B[N,K]^T with block-scaled fp8 operands (tcgen05 kind::mxf8f6f4.block_scale)
+void gemm_mxfp8(Tensor a, Tensor sfa, Tensor b, Tensor sfb, Tensor out, c10::optional<Tensor> bias) {
+  TORCH_CHECK(a.dim() == 2 && b.dim() == 2 && a.is_contiguous() && b.is_contiguous() && a.element_size() == 1 &&
+              b.element_size() == 1 && a.size(1) == b.size(1) && a.size(1) % 128 == 0, "gemm_mxfp8 operands");
+  const int64_t M = a.size(0), N = b.size(0), K = a.size(1);
+  TORCH_CHECK(sfa.numel() == ((M + 127) / 128) * (K / 128) * 512 && sfb.numel() == ((N + 127) / 128) * (K / 128) * 512,
+              "gemm_mxfp8: scale-factor sizes");
+  TORCH_CHECK(out.is_cuda() && out.dim() == 2 && out.size(0) == M && out.size(1) == N && out.stride(1) == 1 && N % 8 == 0,
+              "gemm_mxfp8: out");
+  const bool f32 = out.scalar_type() == at::kFloat;
+  TORCH_CHECK(f32 || out.scalar_type() == at::kBFloat16, "gemm_mxfp8: out must be fp32 or bf16");
+  const void* bp = nullptr;
+  if (bias.has_value() && bias->defined()) { check_bf16(*bias, "bias"); TORCH_CHECK(bias->numel() == N, "bias"); bp = bias->data_ptr(); }
+  c10::cuda::CUDAGuard guard(a.device());
+  b200::gemm_mxfp8(a.data_ptr(), sfa.data_ptr(), b.data_ptr(), sfb.data_ptr(), out.data_ptr(), (int)out.stride(0), f32, bp,
+                   (int)M, (int)N, (int)K, cur_stream());
+}
+
 void fp8_quantize(Tensor x, Tensor q, Tensor meta, bool e5m2) {
   check_bf16(x, "x");
   TORCH_CHECK(x.is_contiguous() && q.is_contiguous() && q.is_cuda() && q.element_size() == 1 && q.numel() == x.numel(),
@@ -434,6 +465,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("set_grad_peers", &set_grad_peers);
   m.def("set_grad_push", &set_grad_push);
   m.def("peer_allreduce", &peer_allreduce);
+  m.def("mx_quantize", &mx_quantize);
+  m.def("gemm_mxfp8", &gemm_mxfp8);
   m.def("fp8_quantize", &fp8_quantize);
   m.def("fp8_amax", &fp8_amax);
   m.def("fp8_update", &fp8_update);

@@ -800,6 +800,11 @@ static CUtensorMap make_tmap_2d(const void* ptr, uint64_t inner, uint64_t outer,
   return m;
 }
 
+CUtensorMap make_tmap_2d_u8(const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                            uint32_t box_outer) {
+  return make_tmap_2d(ptr, inner, outer, ld, box_inner, box_outer, 1);
+}
+
 static int num_sms() {
   static int n = 0;
   if (n == 0) {

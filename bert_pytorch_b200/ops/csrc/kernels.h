@@ -86,6 +86,11 @@ struct PeerAllreduceLaunch {
 };
 void peer_allreduce(const PeerAllreduceLaunch& L, cudaStream_t st);
 
+// gemm_mx.cu: block-scaled MXFP8 (e4m3 + one ue8m0 scale per 32 elements along K), NT layout
+void mx_quantize(const void* x_bf16, void* q, void* sf, int R, int K, cudaStream_t st);
+void gemm_mxfp8(const void* a, const void* sfa, const void* b, const void* sfb, void* out, int ldo, bool out_f32,
+                const void* bias, int M, int N, int K, cudaStream_t st);
+
 // fp8.cu: per-tensor scaled fp8 operand preparation; meta records are {amax, scale, inv_scale, _}
 void fp8_quantize(const void* x_bf16, void* q, long long n, float* meta, bool e5m2, cudaStream_t st);
 void fp8_amax(const void* x_bf16, long long n, float* meta, cudaStream_t st);

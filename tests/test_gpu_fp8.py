@@ -153,3 +153,31 @@ def test_producer_kernels_emit_fp8_copies():
     dbi = torch.zeros(H, device=dev)
     d1, q = api.dgelu_bwd(dy, x, dbi, fp8=(meta, "dgelu"))
     close(q, d1, "dgelu", 0.14)
+
+
+@pytest.mark.parametrize("shape", [(256, 256, 256), (512, 1024, 1024), (1000, 520, 384), (128, 128, 128)])
+def test_mxfp8_block_scaled_gemm(shape):
+    """OCP MXFP8 (e4m3 + one ue8m0 scale per 32 K elements, scales applied by the tensor core from TMEM) vs the
+    dequantised operands multiplied in fp32, and vs the unquantised product."""
+    ops = _ops()
+    api = ops.api
+    M, N, K = shape
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cuda").manual_seed(9)
+    # block scaling must absorb a wide dynamic range along K: scale every 32-column group differently
+    col_scale = torch.exp2(torch.randint(-6, 7, (1, K // 32), device=dev, generator=g).float()).repeat_interleave(32, dim=1)
+    a = (torch.randn(M, K, device=dev, generator=g) * col_scale).bfloat16()
+    b = (torch.randn(N, K, device=dev, generator=g) * 0.05 / col_scale).bfloat16()
+    bias = torch.randn(N, device=dev, generator=g).bfloat16()
+    qa, sfa = api.mx_quantize(a)
+    qb, sfb = api.mx_quantize(b)
+    da, db = api.mx_dequantize(qa, sfa), api.mx_dequantize(qb, sfb)
+    blk_amax = a.float().abs().view(M, K // 32, 32).amax(-1).repeat_interleave(32, dim=1)
+    assert ((da - a.float()).abs() <= a.float().abs() * 0.0625 + blk_amax * 0.0025).all()   # 3 mantissa bits / subnormals
+    out = api.gemm_mx(qa, sfa, qb, sfb, out_dtype=torch.float32)
+    ref = da @ db.t()
+    assert (out - ref).abs().max().item() <= 1e-3 * ref.abs().max().item() + 1e-6
+    out_b = api.gemm_mx(qa, sfa, qb, sfb, bias=bias)
+    assert (out_b.float() - (ref + bias.float())).abs().max().item() <= 1e-2 * (ref.abs().max().item() + 1.0)
+    full = a.float() @ b.float().t()
+    assert ((out - full).norm() / full.norm()).item() < 0.06
