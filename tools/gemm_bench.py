@@ -76,6 +76,11 @@ def main():
                 rec["fp8_ms"], rec["fp8_tflops"] = round(t, 4), round(flops / t / 1e9, 1)
             t = timeit(lambda: meta.quantize(a, "a", out=qa))
             rec["quantize_a_gbs"] = round(a.numel() * 3 / t / 1e6, 1)
+            if layout == K.NT and k % 128 == 0:        # block-scaled MXFP8 (1-CTA 128x128 tiles, scale factors in TMEM)
+                ma, msa = K.mx_quantize(a)
+                mb_, msb = K.mx_quantize(b)
+                t = timeit(lambda: K.gemm_mx(ma, msa, mb_, msb))
+                rec["mxfp8_ms"], rec["mxfp8_tflops"] = round(t, 4), round(flops / t / 1e9, 1)
         out.append(rec)
         print(json.dumps(rec), flush=True)
 
