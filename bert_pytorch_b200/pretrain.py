@@ -93,6 +93,9 @@ def build_parser() -> argparse.ArgumentParser:
                    help="gradient-reduction backend (default: nccl on CUDA, gloo on CPU)")
     p.add_argument("--device", default=None, choices=[None, "cuda", "cpu"])
     p.add_argument("--no_fused", default=False, action="store_true", help="run the plain-PyTorch oracle path")
+    p.add_argument("--fp8", default=False, action="store_true",
+                   help="B200 extension: fp8 GEMM operands in the fused engine (e4m3 activations/weights, e5m2 gradients, "
+                        "per-tensor delayed scaling); LayerNorm, attention, master weights unchanged")
     p.add_argument("--loader_depth", type=int, default=4)
     return p
 
@@ -181,6 +184,8 @@ def prepare_model(args):
     model.checkpoint_activations(args.checkpoint_activations)
     if args.no_fused:
         model.enable_apex(False)
+    if getattr(args, "fp8", False) and not args.no_fused and args.device_obj.type == "cuda":
+        os.environ["B200_FP8"] = "1"          # picked up by the fused engine when it is built (models/fused.py)
     config.max_predictions_per_seq = args.max_predictions_per_seq    # static MLM row capacity of the fused head
     arena = ParamArena(model, device=args.device_obj)
     comm = make_comm(args.backend)
