@@ -88,7 +88,6 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--local_rank", type=int, default=0)
     # new in this code base
     p.add_argument("--bf16", default=False, action="store_true", help="bf16 compute (default on CUDA unless --fp16)")
-    p.add_argument("--fp8", default=False, action="store_true", help="block-scaled fp8 GEMMs where supported")
     p.add_argument("--backend", default=None, choices=[None, "nccl", "gloo", "fused"],
                    help="gradient-reduction backend (default: nccl on CUDA, gloo on CPU)")
     p.add_argument("--device", default=None, choices=[None, "cuda", "cpu"])
