@@ -27,7 +27,7 @@ def _run(tmp_path, extra=()):
     return out, model_json
 
 
-@pytest.mark.parametrize("extra", [(), ("--checkpoint_activations",)])
+@pytest.mark.parametrize("extra", [(), ("--checkpoint_activations",), ("--fp8",)])
 def test_pretraining_runtime_on_gpu(tmp_path, extra):
     from bert_pytorch_b200 import BertConfig
     from bert_pytorch_b200.models import BertForPreTraining
