@@ -7,24 +7,31 @@
 // tiles of one head are plain 2-D TMA boxes of that matrix -- no permute/contiguous copies (K6 is gone);
 // the context is written as [B*S, H], ready for the output projection.
 //
-// Forward, one CTA per (batch, head, 128-query block):
-//   warp 4 lane 0 : TMA loads (Q once, K/V blocks through a 2-stage ring) and all tcgen05.mma issue
-//   warps 0-3     : one thread per query row: S row from TMEM -> online softmax (fp32, exp2) ->
-//                   dropout (Philox counter RNG, regenerated in backward) -> P (bf16) into shared memory in
-//                   the 128B-swizzled K-major layout the second MMA reads -> O += P V accumulated in
-//                   registers from the TMEM result of each key block.
-// Backward, one CTA per (batch, head, 128-key block), looping over query blocks:
-//   S = Q K^T and dPd = dO V^T into TMEM; threads form P, dS (and the dropped P) -> shared memory;
-//   dV += Pd^T dO, dK += dS^T Q (accumulated in TMEM over the query loop; the transposes are free: the
-//   same shared-memory tile is read through an MN-major descriptor), dQ = dS K per query block
-//   (direct store when S == 128, fp32 atomics + a conversion pass otherwise).
+// Every kernel: 8 (or 16) math warps + 1 control warp.  The control warp's elected lane issues all TMA loads and
+// all tcgen05.mma; a query row (= TMEM lane) is shared by two (four) threads that own 64 (32) key columns each and
+// exchange row statistics through shared memory.
+//
+// Forward
+//   attn_fwd_single_kernel  S <= 128: one CTA per (batch, head); P overwrites the Q|K buffers, O overwrites the S
+//                           accumulator; 48 KB / 128 TMEM columns / 70 registers -> three CTAs per SM
+//   attn_fwd_kernel<2>      S > 128: one CTA per (batch, head, 128-query block); K blocks double buffered, one V
+//                           buffer, online softmax (fp32, exp2), O accumulated in registers from the TMEM result of
+//                           each key block; 96 KB / 256 columns -> two CTAs per SM
+//   dropout: Philox counter RNG on the probabilities, regenerated in the backward; P (bf16) goes to shared memory in
+//   the 128B-swizzled K-major layout the PV MMA reads.
+// Backward
+//   attn_bwd_single_kernel  S <= 128: one CTA per (batch, head); S = Q K^T, dP = dO V^T -> threads form P~, dS ->
+//                           dV = P~^T dO, dK = dS^T Q, dQ = dS K (transposes are free: MN-major descriptors on the
+//                           same tile); dV/dK/dQ overwrite the consumed S/dP accumulators, P~ and dS share one
+//                           buffer, delta = <dO, O> computed in-kernel; 96 KB / 256 columns -> two CTAs per SM
+//   attn_bwd_kernel         S > 128: one CTA per (batch, head, 128-key block) looping over the query blocks; dV, dK
+//                           accumulate in TMEM, dQ goes out per query block through fp32 atomics + a conversion pass
 #include "common.cuh"
 #include "gemm_sm100.h"
 #include "kernels.h"
 
 namespace b200 {
 
-constexpr int ATT_THREADS = 160;   // forward: 4 softmax warps + 1 control warp
 constexpr int ATT_BWD_THREADS = 288;   // 8 math warps (2 per TMEM lane quarter) + 1 control warp
 constexpr int ATT_BWD16_THREADS = 544; // streaming backward: 16 math warps (4 per TMEM lane quarter) + 1 control warp
 constexpr int TILE = 128;          // query rows / key rows per block
