@@ -9,19 +9,24 @@ The ``nn.Module`` tree in :mod:`.modeling` only *holds* the parameters (as views
                flash attention (scale, key-padding, softmax, dropout, PV)   tcgen05    (K7-K12)
                out-proj GEMM + bias + dropout + residual                    tcgen05    (K13-K14)
                LayerNorm                                                     1 kernel   (K15)
-               FFN-1 GEMM + bias + GELU (saves pre-activation)               tcgen05    (K16)
+               FFN-1 GEMM + bias, GELU as its own bandwidth kernel           tcgen05    (K16; a fused erf epilogue is
+                                                                                       instruction bound at K = 1024)
                FFN-2 GEMM + bias + dropout + residual                        tcgen05    (K17-K18)
                LayerNorm                                                     1 kernel
   MLM head     compact masked positions -> gather -> transform GEMM+GELU -> LN -> decoder GEMM + bias
                -> softmax-CE fwd+bwd in place (only max_pred rows/sequence, K21-K24; fixes Q15)
   backward     the mirror image: LN-bwd kernels emit the residual gradient *and* the dropout-masked
                gradient plus all dgamma/dbeta/dbias column sums; dgrad GEMMs fuse the residual-gradient
-               add or GELU'; wgrad GEMMs (both operands MN-major, split-K) accumulate in fp32 straight
-               into the gradient arena.
+               add, GELU' (+ bias gradient) is one bandwidth pass; wgrad GEMMs (both operands MN-major,
+               split-K) accumulate in fp32 straight into the gradient arena -- or, on the last micro-step
+               with the peer-memory backend, straight into the OWNER rank's arena over NVLink.
 
 Dropout masks are a counter-based function of (seed, stream id, element index) so backward regenerates
 them (nothing stored, and recompute is deterministic -- SURVEY.md K27).
-Activations are saved rather than recomputed: a B200 has 180 GB (phase-1 micro-batch 96x128 needs ~10 GB).
+Activations are saved rather than recomputed by default: a B200 has 180 GB (phase-1 micro-batch 96x128 needs
+~10 GB); ``--checkpoint_activations`` replays ceil(sqrt(L))-layer segments instead.
+Options: fp8 GEMM operands (``enable_fp8`` / ``B200_FP8=1`` / ``--fp8``), whole-micro-step CUDA-graph replay
+(``FusedPretrainer``, on by default, ``B200_GRAPH=0`` disables), K-FAC taps.
 """
 from __future__ import annotations
 
