@@ -12,7 +12,8 @@ bridge; ``--fp16``/``--amp`` select 16-bit compute (bf16 by default on CUDA -- n
 ``--loss_scale`` is honoured for fp16) with the fused multi-tensor Adam kernel (apex FusedAdam contract,
 ``bias_correction=False``) on the flat arena and device-side gradient clipping (no ``.item()`` per
 micro-step); without them the fp32 ``BertAdam`` path of the reference is kept.  Data
-parallelism is this repo's engine (NCCL / gloo / fused), replacing apex DDP and nn.DataParallel.
+parallelism is this repo's engine (NCCL / gloo / fused), replacing apex DDP; the reference's single-process
+nn.DataParallel fallback (local_rank == -1 and several GPUs) is kept as a legacy mode on the plain PyTorch forward.
 Fixed reference quirks: Q19 (BPE casing flag inverted), Q20 (v2 null scores keyed by the wrong id),
 Q21 (amp.master_params on the non-amp path), Q22 (max_steps off by one).
 """
@@ -192,6 +193,16 @@ def main(argv=None) -> dict:
     arena = ParamArena(model, device=device)
     comm = make_comm(args.backend)
     ddp = DataParallel(model, comm=comm, arena=arena)
+    # Single-process multi-GPU fallback (reference: run_squad.py:1012-1013, nn.DataParallel when local_rank == -1 and
+    # n_gpu > 1).  The fused engine is a one-device kernel program, so this legacy mode runs the plain PyTorch
+    # forward replicated by torch.nn.DataParallel; gradients land in the arena views on device 0.  One process per
+    # GPU (torchrun) is the supported way to scale; B200_DATAPARALLEL=0 turns the fallback off.
+    forward_model = ddp
+    if (use_cuda and not distributed and args.local_rank == -1 and torch.cuda.device_count() > 1
+            and os.environ.get("B200_DATAPARALLEL", "1") != "0"):
+        model.bert.use_fused = False
+        forward_model = torch.nn.DataParallel(model)
+        dll.log(step="PARAMETER", data={"single_process_data_parallel_gpus": torch.cuda.device_count()})
 
     optimizer = scheduler = scaler = None
     if args.do_train:
@@ -248,7 +259,7 @@ def main(argv=None) -> dict:
                 ids, mask, seg, sp, ep = (t.to(device, non_blocking=True) for t in batch)
                 with torch.autocast(device_type=device.type, dtype=compute_dtype,
                                     enabled=compute_dtype != torch.float32):
-                    start_logits, end_logits = ddp(ids, seg, mask)
+                    start_logits, end_logits = forward_model(ids, seg, mask)
                     loss = squad_loss(start_logits, end_logits, sp, ep)
                 if acc > 1:
                     loss = loss / acc
