@@ -49,3 +49,53 @@ def test_pretraining_runtime_on_gpu(tmp_path, extra):
     missing, unexpected = ref.load_state_dict(payload["model"], strict=False)
     assert not unexpected and all("position_ids" in m for m in missing)
     assert payload["optimizer"]["param_groups"][0]["step"] == 12
+
+
+def _squad_fixture(tmp_path):
+    from test_kfac_squad_ner import VOCAB
+    vf = tmp_path / "vocab.txt"
+    vf.write_text("\n".join(VOCAB) + "\n")
+    data = {"version": "1.1", "data": [{"title": "t", "paragraphs": [
+        {"context": "The capital of France is Paris. The river Seine flows through Paris.",
+         "qas": [{"id": "q1", "question": "What is the capital of France?", "answers": [{"text": "Paris", "answer_start": 25}]},
+                 {"id": "q2", "question": "What river flows through Paris?", "answers": [{"text": "Seine", "answer_start": 42}]}]},
+        {"context": "Hamlet is a play. The play was written by William Shakespeare.",
+         "qas": [{"id": "q3", "question": "Who wrote Hamlet?", "answers": [{"text": "William Shakespeare", "answer_start": 42}]}]}]}]}
+    f = tmp_path / "train.json"
+    f.write_text(json.dumps(data))
+    return str(f), str(vf), VOCAB
+
+
+def test_squad_and_ner_runners_on_gpu(tmp_path, monkeypatch):
+    """Fine-tuning CLIs on the GPU: the encoder runs through the fused engine behind the autograd bridge
+    (head_dim 64), 16-bit compute, fused arena Adam."""
+    from bert_pytorch_b200 import BertConfig, finetune_ner, finetune_squad
+    from bert_pytorch_b200.models import modeling as M
+    from bert_pytorch_b200.ops import api as K
+    monkeypatch.setenv("B200_DATAPARALLEL", "0")            # single-device run even on a multi-GPU box
+    f, vf, VOCAB = _squad_fixture(tmp_path)
+    cfg = {"vocab_size": len(VOCAB), "hidden_size": 128, "num_hidden_layers": 2, "num_attention_heads": 2,
+           "intermediate_size": 256, "max_position_embeddings": 64, "vocab_file": vf, "tokenizer": "wordpiece",
+           "next_sentence": True}
+    cj = tmp_path / "model.json"; cj.write_text(json.dumps(cfg))
+    m = M.BertForPreTraining(BertConfig.from_dict(dict(cfg)).pad_vocab(8))
+    ck = tmp_path / "ckpt_1.pt"; torch.save({"model": m.state_dict()}, ck)
+    out = tmp_path / "out"
+    n0 = K.KERNEL_LAUNCHES
+    summary = finetune_squad.main(["--bert_model", "tiny", "--output_dir", str(out), "--init_checkpoint", str(ck),
+                                   "--config_file", str(cj), "--train_file", f, "--predict_file", f, "--do_train",
+                                   "--do_predict", "--do_eval", "--do_lower_case", "--train_batch_size", "2",
+                                   "--num_train_epochs", "2", "--max_seq_length", "48", "--doc_stride", "16",
+                                   "--max_query_length", "12", "--fp16", "--disable-progress-bar", "--skip_cache",
+                                   "--eval_script", "/nonexistent"])
+    assert K.KERNEL_LAUNCHES > n0                              # sm_100a kernels ran (encoder + Adam)
+    assert set(json.load(open(out / "predictions.json"))) == {"q1", "q2", "q3"}
+    assert summary["final_loss"] == summary["final_loss"]       # finite
+    conll = tmp_path / "train.txt"
+    conll.write_text("-DOCSTART- -X- -X- O\n\nWilliam NNP B-NP B-PER\nShakespeare NNP I-NP I-PER\nwrote VBD B-VP O\n"
+                     "Hamlet NNP B-NP B-MISC\n. . O O\n\nParis NNP B-NP B-LOC\nis VBZ B-VP O\nbig JJ B-ADJP O\n. . O O\n")
+    res = finetune_ner.main(["--train_file", str(conll), "--val_file", str(conll), "--test_file", str(conll), "--labels",
+                             "O", "B-PER", "I-PER", "B-LOC", "B-MISC", "--model_config_file", str(cj),
+                             "--model_checkpoint", str(ck), "--epochs", "2", "--lr", "0.01", "--batch_size", "2",
+                             "--max_seq_len", "12"])
+    assert res is None or res == res
