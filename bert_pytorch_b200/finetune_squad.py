@@ -279,7 +279,7 @@ def main(argv=None) -> dict:
                     optimizer.zero_grad()
                     global_step += 1
                 if step % args.log_freq == 0:
-                    final_loss = float(loss)
+                    final_loss = float(loss.detach())
                     dll.log(step=(epoch, global_step), data={"step_loss": final_loss,
                                                              "learning_rate": optimizer.param_groups[0]["lr"]})
             if done:

@@ -26,6 +26,7 @@ KERNEL_LAUNCHES = 0     # every wrapper bumps this: bench.py reports it as ``gpu
 # stream-K weight gradients: measured slower than 2-4 way split-K on the BERT-large shapes (operands of
 # neighbouring clusters stop sharing L2 lines: profiles/gemm_bench_r1_v3_streamk.jsonl), so opt-in
 STREAM_K = os.environ.get("B200_STREAM_K", "0") == "1"
+TAIL_SPLIT = os.environ.get("B200_TAIL_SPLIT", "1") != "0"
 
 
 def _count(n: int = 1) -> None:
@@ -173,6 +174,17 @@ def wgrad_accumulate(dy: torch.Tensor, x: torch.Tensor, grad: torch.Tensor, alph
     if bn == 128 and k_out >= 256:
         bn = 256
     splits = wgrad_splits(n_out, k_out, dy.size(0) // (2 if fp8 else 1), bn)
+    if bn == 512 and TAIL_SPLIT:
+        # fewer tiles than CTA pairs and a split-K grid that leaves > 7 % of the machine idle in its last wave:
+        # tail split (cluster t runs the head of tile t's K range, the idle clusters share the tails; gemm_sm100.cu)
+        tiles = ((n_out + 255) // 256) * ((k_out + 255) // 256)
+        pairs = NUM_SMS // 2
+        kb = (dy.size(0) + (127 if fp8 else 63)) // (128 if fp8 else 64)
+        if tiles < pairs:
+            units = tiles * max(splits, 1)
+            eff = units / (((units + pairs - 1) // pairs) * pairs)
+            if eff < 0.93 and kb * tiles // pairs >= 4:
+                splits = -2
     if bn == 512 and STREAM_K:
         # stream-K: equal (tile, k-block) ranges per CTA pair instead of whole tiles (csrc/gemm_sm100.cu: seg_get)
         tiles = ((n_out + 255) // 256) * ((k_out + 255) // 256)

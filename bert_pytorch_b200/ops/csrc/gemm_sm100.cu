@@ -63,7 +63,8 @@ struct GemmArgs {
   const float* scale_a;      // fp8: device dequantisation factors (nullptr for bf16 operands)
   const float* scale_b;
   unsigned int fp8_fmt;      // bit0: A is e5m2 (else e4m3), bit1: B is e5m2
-  int stream_k;              // pair kernel: contiguous (tile, k-block) ranges per cluster instead of whole tiles
+  int stream_k;              // pair kernel: 1 = contiguous (tile, k-block) ranges per cluster; 2 = tail split (below)
+  int k_main;                // tail split: k-blocks [0, k_main) of tile t go to cluster t, the rest to the helper clusters
   // GEMM -> reduce-scatter fusion (EPI_ACCUM_F32 into a gradient arena that lives in NVLink symmetric memory):
   // peer_world > 1 makes every accumulation atomic (peers add into this arena concurrently); peer_push adds the
   // tile -- plus, once per tile, the locally accumulated value -- straight into the arena of the rank that owns
@@ -497,8 +498,20 @@ constexpr int PAIR_SMEM = PAIR_STAGES * PAIR_STAGE + PAIR_CSTAGE + 1024 + 256;
 // equal contiguous ranges, so every cluster does the same number of MMAs regardless of how the tile count
 // divides the machine (64 weight-gradient tiles on 74 CTA pairs would otherwise idle 14 % of the tensor cores);
 // a range spans at most a few tiles and each piece is added with red.global.add.
+// Tail split (stream_k == 2, fewer tiles T than clusters C, accumulating epilogue): cluster t < T runs k-blocks
+// [0, k_main) of tile t -- all of them in lock step from k = 0, so clusters that share an operand panel still hit the
+// same L2 lines at the same time (what plain stream-K loses) -- and the C - T otherwise idle clusters split the
+// remaining k-blocks [k_main, K) of all tiles evenly among themselves.  64 weight-gradient tiles on 74 CTA pairs:
+// 86 % -> ~99 % of the machine busy.
 struct WorkSeg { int mn, kb0, kb1; };
 __device__ __forceinline__ int seg_count(const GemmArgs& p, int c, int C) {
+  if (p.stream_k == 2) {
+    const int T = p.m_blocks * p.n_blocks, rt = p.k_blocks - p.k_main;
+    if (c < T) return 1;
+    const long long R = (long long)T * rt, H = C - T, h = c - T;
+    const long long r0 = R * h / H, r1 = R * (h + 1) / H;
+    return r1 > r0 ? (int)((r1 - 1) / rt - r0 / rt + 1) : 0;
+  }
   if (!p.stream_k) {
     const int total = p.m_blocks * p.n_blocks * p.k_splits;
     return c < total ? (total - c + C - 1) / C : 0;
@@ -509,6 +522,18 @@ __device__ __forceinline__ int seg_count(const GemmArgs& p, int c, int C) {
 }
 __device__ __forceinline__ WorkSeg seg_get(const GemmArgs& p, int c, int C, int idx) {
   WorkSeg w;
+  if (p.stream_k == 2) {
+    const int T = p.m_blocks * p.n_blocks, rt = p.k_blocks - p.k_main;
+    if (c < T) { w.mn = c; w.kb0 = 0; w.kb1 = p.k_main; return w; }
+    const long long R = (long long)T * rt, H = C - T, h = c - T;
+    const long long r0 = R * h / H, r1 = R * (h + 1) / H;
+    const long long start = idx == 0 ? r0 : (r0 / rt + idx) * rt;
+    const int inside = (int)(start % rt);
+    w.mn = (int)(start / rt);
+    w.kb0 = p.k_main + inside;
+    w.kb1 = p.k_main + (int)min((long long)rt, inside + (r1 - start));
+    return w;
+  }
   if (!p.stream_k) {
     const int tile = c + idx * C;
     const int mnt = p.m_blocks * p.n_blocks;
@@ -843,7 +868,7 @@ static void launch(const GemmCall& c, cudaStream_t st) {
   p.drop_scale = pd > 0.f ? 65536.f / (65536.f - (float)p.drop_thresh16) : 1.f;
   p.alpha = c.alpha;
   fill_peer(p, c);
-  p.scale_a = nullptr; p.scale_b = nullptr; p.fp8_fmt = 0; p.stream_k = 0;
+  p.scale_a = nullptr; p.scale_b = nullptr; p.fp8_fmt = 0; p.stream_k = 0; p.k_main = 0;
   // operand maps
   CUtensorMap ta = A_MN ? make_tmap_2d_bf16(c.A, c.M, c.K, c.lda, 64, BLOCK_K)
                         : make_tmap_2d_bf16(c.A, c.K, c.M, c.lda, BLOCK_K, BLOCK_M);
@@ -885,8 +910,16 @@ static void launch_pair(const GemmCall& c, cudaStream_t st) {
   fill_peer(p, c);
   // k_splits < 0 asks for stream-K (fp32 accumulate epilogue only): equal MMA work per cluster, pieces merged by
   // red.global.add.  Needs enough k-blocks per cluster to amortise the extra partial tiles.
-  p.stream_k = 0;
-  if (c.k_splits < 0 && c.epi == EPI_ACCUM_F32) {
+  p.stream_k = 0; p.k_main = 0;
+  if (c.k_splits == -2 && c.epi == EPI_ACCUM_F32) {       // tail split: see seg_count
+    const int T = p.m_blocks * p.n_blocks, pairs_ = num_sms() / 2;
+    const int kmain = (int)((long long)p.k_blocks * T / pairs_);
+    if (T < pairs_ && kmain >= 4 && p.k_blocks - kmain >= 1) {
+      p.stream_k = 2; p.k_main = kmain; p.k_splits = 2;     // k_splits > 1: the epilogue adds with red.global.add
+    } else {
+      p.k_splits = 1; p.k_per_split = p.k_blocks;
+    }
+  } else if (c.k_splits < 0 && c.epi == EPI_ACCUM_F32) {
     const long long iters = (long long)p.m_blocks * p.n_blocks * p.k_blocks;
     const int pairs_ = num_sms() / 2;
     if (iters >= 8ll * pairs_ && (p.m_blocks * p.n_blocks) % pairs_ != 0) {

@@ -69,6 +69,18 @@ def test_gemm_tn_stream_k(M, N, K):
     _check(grad, a.float().t() @ b.float(), tol=1e-2)
 
 
+@pytest.mark.parametrize("M,N,K", [(4096, 1024, 12288), (1024, 1024, 4096), (3072, 1024, 2048), (520, 1000, 3000),
+                                   (256, 256, 64)])
+def test_gemm_tn_tail_split(M, N, K):
+    """k_splits=-2: tail split (cluster t runs the head of tile t's K range, the otherwise idle clusters the tails)."""
+    K_ = _ops()
+    a, b = _rand(K, M), _rand(K, N)
+    base = torch.randn(M, N, device="cuda")
+    out = base.clone()
+    K_.gemm(a, b, layout=K_.TN, epi=K_.EPI_ACCUM_F32, out=out, block_n=512, k_splits=-2)
+    _check(out, base + a.float().t() @ b.float(), tol=1e-2)
+
+
 @pytest.mark.parametrize("bn", [256, 512])
 def test_gemm_epilogues(bn):
     import functools

@@ -53,9 +53,9 @@ def main():
         for bn in (256, 512):
             if layout == K.TN:
                 o = torch.zeros(m, n, device="cuda")
-                for sp in (1, 2, 4, 8) + ((-1,) if bn == 512 else ()):
+                for sp in (1, 2, 4, 8) + ((-1, -2) if bn == 512 else ()):
                     t = timeit(lambda: K.gemm(a, b, layout=layout, epi=K.EPI_ACCUM_F32, out=o, block_n=bn, k_splits=sp))
-                    rec[f"ours_bn{bn}_s{'treamk' if sp < 0 else sp}_tflops"] = round(flops / t / 1e9, 1)
+                    rec[f"ours_bn{bn}_s{({-1: 'treamk', -2: '_tailsplit'}.get(sp, sp))}_tflops"] = round(flops / t / 1e9, 1)
             else:
                 o = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
                 t = timeit(lambda: K.gemm(a, b, layout=layout, out=o, block_n=bn))
