@@ -26,7 +26,9 @@ KERNEL_LAUNCHES = 0     # every wrapper bumps this: bench.py reports it as ``gpu
 # stream-K weight gradients: measured slower than 2-4 way split-K on the BERT-large shapes (operands of
 # neighbouring clusters stop sharing L2 lines: profiles/gemm_bench_r1_v3_streamk.jsonl), so opt-in
 STREAM_K = os.environ.get("B200_STREAM_K", "0") == "1"
-TAIL_SPLIT = os.environ.get("B200_TAIL_SPLIT", "1") != "0"
+# tail split (idle CTA pairs take the K tails): +3 % on the 48-tile QKV weight gradient, -8 % on the 64-tile FFN
+# ones (each helper pays one fp32 red epilogue per tail piece) -> opt-in as well
+TAIL_SPLIT = os.environ.get("B200_TAIL_SPLIT", "0") == "1"
 
 
 def _count(n: int = 1) -> None:
