@@ -188,6 +188,8 @@ def run_ours(args, ph, B, accum, rank, world, dev):
     dev_pool = [[t.to(dev) for t in b] for b in pool]
     loss_acc = torch.zeros((), device=dev)
 
+    opt_events = []
+
     def step_device(i):
         for m in range(accum):
             batch = dev_pool[(i * accum + m) % len(dev_pool)]
@@ -195,7 +197,11 @@ def run_ours(args, ph, B, accum, rank, world, dev):
                                                   compute_dtype=torch.bfloat16)
             loss_acc.add_(loss)
         sched.step()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         pretrain.take_optimizer_step(opt, None, ddp, scaler)
+        e1.record()
+        opt_events.append((e0, e1))
 
     host_losses = []
 
@@ -220,7 +226,14 @@ def run_ours(args, ph, B, accum, rank, world, dev):
         h2d = sum(t.numel() * t.element_size() for t in pool[0]) * accum
         e2e = dict(ms=ms_e2e, h2d=h2d, d2h=4)
     final_loss = float(loss_acc) / max(1, (args.steps + args.warmup))
-    return ms, clocks, launches, e2e, dict(loss_mean=final_loss, backend=getattr(comm, "name", "single"))
+    torch.cuda.synchronize()
+    opt_ms = [a.elapsed_time(b) for a, b in opt_events[args.warmup:args.warmup + args.steps]]
+    opt_mean = max_over_ranks(sum(opt_ms) / max(1, len(opt_ms)), dev) if opt_ms else None
+    what = ("fused reduce-scatter + LAMB + all-gather kernel" if getattr(comm, "fuses_optimizer", False) and world > 1
+            else "LAMB kernels (all-reduce happens in the last micro-step)" if world > 1 else "LAMB kernels")
+    return ms, clocks, launches, e2e, dict(loss_mean=final_loss, backend=getattr(comm, "name", "single"),
+                                           optimizer_step_ms=None if opt_mean is None else round(opt_mean, 3),
+                                           optimizer_step_is=what)
 
 
 # ------------------------------------------------------------------------------------------------
