@@ -35,7 +35,6 @@ import math
 import os
 import sys
 import tempfile
-import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:

@@ -14,7 +14,7 @@ import copy
 import json
 import math
 import os
-from typing import Any, Dict, Iterable, Optional, Sequence
+from typing import Any, Dict, Optional, Sequence
 
 
 class BertConfig:

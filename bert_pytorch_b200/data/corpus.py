@@ -20,7 +20,7 @@ import subprocess
 import time
 import urllib.request
 from pathlib import Path
-from typing import Dict, Iterable, Iterator, List, Optional, Sequence
+from typing import Iterable, Iterator, List, Optional, Sequence
 
 # ---------------------------------------------------------------------------
 # helpers

@@ -16,11 +16,10 @@ and written through this repo's native HDF5 writer (no h5py).
 """
 from __future__ import annotations
 
-import os
 import random
 import time
-from dataclasses import dataclass, field
-from typing import Iterator, List, Optional, Sequence, Tuple
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 

@@ -25,7 +25,6 @@ the oracle for its tests.
 """
 from __future__ import annotations
 
-import io
 import os
 import struct
 import zlib

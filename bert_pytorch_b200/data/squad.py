@@ -18,8 +18,8 @@ import json
 import math
 import re
 import string
-from dataclasses import dataclass, field
-from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
 
 from .tokenization import BasicTokenizer, whitespace_tokenize
 

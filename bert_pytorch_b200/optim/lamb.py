@@ -18,7 +18,7 @@ Two execution paths share this class:
 from __future__ import annotations
 
 import math
-from typing import Iterable, List, Optional
+from typing import List, Optional
 
 import torch
 from torch.optim import Optimizer

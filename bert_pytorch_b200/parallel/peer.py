@@ -20,7 +20,7 @@ The algorithm is specified and unit-tested on CPU in :mod:`bert_pytorch_b200.par
 """
 from __future__ import annotations
 
-from typing import List, Optional
+from typing import Optional
 
 import torch
 import torch.distributed as dist

@@ -22,13 +22,12 @@ from __future__ import annotations
 
 import argparse
 import json
-import math
 import os
 import random
 import warnings
 from pathlib import Path
 from time import perf_counter
-from typing import Any, Dict, List, Optional, Tuple
+from typing import Any, Dict, List, Tuple
 
 import numpy as np
 import torch

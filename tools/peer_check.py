@@ -7,7 +7,6 @@
 2. (--big) device-timed step on a BERT-large sized arena (336 M parameters): fused kernel vs
    NCCL all-reduce + unfused LAMB, max over ranks, with the roofline fraction of SURVEY.md 5.8.
 Rank 0 prints one JSON line per section."""
-import copy
 import json
 import os
 import sys
