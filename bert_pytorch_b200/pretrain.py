@@ -182,10 +182,10 @@ def prepare_model(args):
     model.checkpoint_activations(args.checkpoint_activations)
     if args.no_fused:
         model.enable_apex(False)
-    if getattr(args, "fp8", False) and not args.no_fused and args.device_obj.type == "cuda":
-        os.environ["B200_FP8"] = "1"          # picked up by the fused engine when it is built (models/fused.py)
     config.max_predictions_per_seq = args.max_predictions_per_seq    # static MLM row capacity of the fused head
     arena = ParamArena(model, device=args.device_obj)
+    if getattr(args, "fp8", False) and not args.no_fused and args.device_obj.type == "cuda":
+        model.bert.fused_engine().enable_fp8()      # this model's engine only (no process-wide switch)
     comm = make_comm(args.backend)
     if getattr(comm, "fuses_optimizer", False):
         comm.adopt(arena)        # arenas move into NVLink symmetric memory; optimizer + reduction fuse
