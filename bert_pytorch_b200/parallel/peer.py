@@ -12,6 +12,13 @@ with cross-rank norm exchange through peer stores, and the parameter all-gather 
 stores of the updated fp32 + bf16 values.  No NCCL call on this path.  The bootstrap (rendezvous, handle
 exchange) uses torch.distributed / ``torch.distributed._symmetric_memory``; the kernels are ours.
 
+GEMM -> reduce-scatter fusion: with the gradient arenas registered at the GEMM launcher (``set_grad_peers``) the
+weight-gradient GEMMs of the LAST micro-step of an optimizer step (``begin_push`` / ``end_push``) add their
+tiles -- plus the locally accumulated value -- straight into the arena of the rank that owns the shard, so most
+of the reduce-scatter happens tile by tile under the remaining backward pass and the fused kernel reads those
+tensors locally (``set_prereduced``).  ``all_reduce_many_`` is a general packed all-reduce through our own
+kernel (K-FAC factor statistics).
+
 The optimizer state (moments) is *partitioned*: each rank only ever touches its own contiguous shard, so
 ``state_dict`` gathers the shards (cold path, NCCL all-reduce of the zero-padded shards) into the full
 per-parameter layout the checkpoint format expects.
