@@ -228,7 +228,8 @@ def run_ours(args, ph, B, accum, rank, world, dev):
     torch.cuda.synchronize()
     opt_ms = [a.elapsed_time(b) for a, b in opt_events[args.warmup:args.warmup + args.steps]]
     opt_mean = max_over_ranks(sum(opt_ms) / max(1, len(opt_ms)), dev) if opt_ms else None
-    what = ("fused reduce-scatter + LAMB + all-gather kernel" if getattr(comm, "fuses_optimizer", False) and world > 1
+    what = ("fused reduce-scatter + LAMB + all-gather kernel, INCLUDING its wait for the slowest rank's backward "
+            "(the kernel alone: tools/peer_check.py --big)" if getattr(comm, "fuses_optimizer", False) and world > 1
             else "LAMB kernels (all-reduce happens in the last micro-step)" if world > 1 else "LAMB kernels")
     return ms, clocks, launches, e2e, dict(loss_mean=final_loss, backend=getattr(comm, "name", "single"),
                                            optimizer_step_ms=None if opt_mean is None else round(opt_mean, 3),
