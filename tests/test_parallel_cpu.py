@@ -141,3 +141,37 @@ def test_gloo_data_parallel_broadcast_nosync_and_average():
     assert torch.equal(w0a, w0b)                                   # broadcast at construction
     assert not torch.equal(ga, gb)                                 # no_sync kept gradients local
     assert torch.allclose(sa, (ga + gb) / 2, atol=1e-7) and torch.equal(sa, sb)
+
+
+def test_all_reduce_many_default_and_fused_reduction_config():
+    """Comm.all_reduce_many_ (packed by the peer backend, a loop elsewhere) and the runtime's choice of where the
+    gradient reduction happens (deferred into the fused optimizer kernel unless a preconditioner needs averaged grads)."""
+    import torch
+    from bert_pytorch_b200 import pretrain
+    from bert_pytorch_b200.parallel.comm import FakeComm
+
+    def run(c):
+        ts = [torch.full((3, 2), float(c.rank + 1)), torch.arange(5, dtype=torch.float32) * (c.rank + 1)]
+        c.all_reduce_many_(ts, op="avg")
+        return ts
+    outs = FakeComm.spawn(3, run)
+    for ts in outs:
+        assert torch.allclose(ts[0], torch.full((3, 2), 2.0)) and torch.allclose(ts[1], torch.arange(5.0) * 2.0)
+
+    class _Peer:                                   # the interface pretrain.configure_fused_reduction relies on
+        fuses_optimizer = True
+        push_master = True
+        def __init__(self): self.names = None
+        def set_prereduced(self, names): self.names = list(names)
+
+    class _Wrapped(torch.nn.Module):
+        def __init__(self, comm):
+            super().__init__()
+            self.module = torch.nn.Linear(2, 2)
+            self.comm = comm
+    w = _Wrapped(_Peer())
+    pretrain.configure_fused_reduction(w, preconditioner=None)
+    assert w.defer_reduction is True and w.comm.push_master is False and w.comm.names is None   # no fused engine on CPU
+    w2 = _Wrapped(_Peer())
+    pretrain.configure_fused_reduction(w2, preconditioner=object())
+    assert w2.defer_reduction is False and w2.comm.push_master is True          # K-FAC: classic all-reduce first
