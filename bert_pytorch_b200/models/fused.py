@@ -51,6 +51,10 @@ def _stream(layer: int, site: int) -> int:
     return layer * 8 + site
 
 
+def _as_tuple(x):
+    return x if isinstance(x, tuple) else (x,)
+
+
 def _use_sdpa() -> bool:
     return os.environ.get("B200_ATTN", "native") == "sdpa"
 
@@ -293,13 +297,15 @@ class FusedEncoderEngine:
                               bias=self._qkv(l, A.flat_shadow, "bias"))
         if _use_sdpa():
             ctx, lse, sd = self._sdpa_fwd(qkv, seqlens, B, S, pa, training)
+            ctx_q = None
             if save:
                 ls.sdpa = sd
         else:
-            ctx, lse = K.attention_fwd(qkv.view(B, S, 3 * H), seqlens, self.heads, p_drop=pa, seed=seed,
-                                       stream=_stream(l, SITE_ATTN_PROB))
+            ctx, lse, *q = K.attention_fwd(qkv.view(B, S, 3 * H), seqlens, self.heads, p_drop=pa, seed=seed,
+                                           stream=_stream(l, SITE_ATTN_PROB), fp8=self._side(f"{l}.ctx"))
             ctx = ctx.view(M, H)
-        pre1, ctx_op = self._lin(l, "ctx", "wo", ctx, self.w(pre + "attention.output.dense.weight"),
+            ctx_q = q[0].view(M, H) if q else None
+        pre1, ctx_op = self._lin(l, "ctx", "wo", ctx, self.w(pre + "attention.output.dense.weight"), xq=ctx_q,
                                  epi=K.EPI_BIAS_DROP_RES, bias=self.w(pre + "attention.output.dense.bias"), res=x,
                                  p_drop=ph, seed=seed, stream=_stream(l, SITE_ATTN_OUT))
         # producers emit the fp8 copy of their output for the next GEMM (no separate quantise pass)
@@ -395,19 +401,22 @@ class FusedEncoderEngine:
         d_ctx = self._lin_bwd(l, "d_yo", "ctx", "wo", d_yo, ls.ctx_op, self.w(pre + "attention.output.dense.weight"),
                               self.g(pre + "attention.output.dense.weight"), dyq=q[0] if q else None)
         # ---- attention core
+        dqkv_q = None
         if ls.sdpa is not None:
             d_qkv = self._sdpa_bwd(ls.sdpa, d_ctx, sv.B, sv.S)
         else:
-            d_qkv = K.attention_bwd(ls.qkv.view(sv.B, sv.S, 3 * H), sv.seqlens, ls.ctx.view(sv.B, sv.S, H),
-                                    d_ctx.view(sv.B, sv.S, H), ls.lse, self.heads, p_drop=pa, seed=seed,
-                                    stream=_stream(l, SITE_ATTN_PROB)).view(M, 3 * H)
+            d_qkv, *q = _as_tuple(K.attention_bwd(ls.qkv.view(sv.B, sv.S, 3 * H), sv.seqlens, ls.ctx.view(sv.B, sv.S, H),
+                                                  d_ctx.view(sv.B, sv.S, H), ls.lse, self.heads, p_drop=pa, seed=seed,
+                                                  stream=_stream(l, SITE_ATTN_PROB), fp8=self._side(f"{l}.d_qkv")))
+            d_qkv = d_qkv.view(M, 3 * H)
+            dqkv_q = q[0].view(M, 3 * H) if q else None
         if kfac is not None:
             for j, nm in enumerate(("query", "key", "value")):
                 kfac.tap(self.prefix + pre + "attention.self." + nm, ls.x, d_qkv[:, j * H:(j + 1) * H])
         # ---- QKV projection
         K.colsum_accumulate(d_qkv, self._qkv(l, A.flat_grad, "bias"))
         d = self._lin_bwd(l, "d_qkv", "x", "wqkv", d_qkv, ls.x_op, self._qkv(l, A.flat_shadow, "weight"),
-                          self._qkv(l, A.flat_grad, "weight"), epi=K.EPI_ADD, res=d_pre1)
+                          self._qkv(l, A.flat_grad, "weight"), dyq=dqkv_q, epi=K.EPI_ADD, res=d_pre1)
         return d
 
     # -- library attention (bring-up / bisecting aid: B200_ATTN=sdpa) ---------------------------------

@@ -317,26 +317,30 @@ def softmax_ce_(logits: torch.Tensor, targets: torch.Tensor, count: torch.Tensor
     _count()
 
 
-def attention_fwd(qkv: torch.Tensor, seqlens: torch.Tensor, heads: int, *, p_drop=0.0, seed=0, stream=0):
+def attention_fwd(qkv: torch.Tensor, seqlens: torch.Tensor, heads: int, *, p_drop=0.0, seed=0, stream=0, fp8=None):
+    """``fp8=(meta, site)``: the kernel also writes the fp8 copy of the context -> (ctx, lse, q)."""
     B, S, H3 = qkv.shape
     H = H3 // 3
     ctx = torch.empty(B, S, H, dtype=torch.bfloat16, device=qkv.device)
     lse = torch.empty(B, heads, S, dtype=torch.float32, device=qkv.device)
-    extension().attention_fwd(qkv, seqlens, ctx, lse, heads, 1.0 / math.sqrt(H // heads), p_drop, seed, stream)
+    q, rec, e5 = _fp8_side(fp8, ctx)
+    extension().attention_fwd(qkv, seqlens, ctx, lse, heads, 1.0 / math.sqrt(H // heads), p_drop, seed, stream, q, rec, e5)
     _count()
-    return ctx, lse
+    return (ctx, lse) if fp8 is None else (ctx, lse, q)
 
 
-def attention_bwd(qkv, seqlens, ctx, dctx, lse, heads: int, *, p_drop=0.0, seed=0, stream=0):
+def attention_bwd(qkv, seqlens, ctx, dctx, lse, heads: int, *, p_drop=0.0, seed=0, stream=0, fp8=None):
+    """``fp8=(meta, site)``: the kernels also write the fp8 copy of dqkv -> (dqkv, q)."""
     B, S, H3 = qkv.shape
     H = H3 // 3
     dqkv = torch.empty_like(qkv)
     delta = torch.empty(B, heads, S, dtype=torch.float32, device=qkv.device)
     dq_acc = torch.empty(B * S, H, dtype=torch.float32, device=qkv.device) if S > 128 else None
+    q, rec, e5 = _fp8_side(fp8, dqkv)
     extension().attention_bwd(qkv, seqlens, ctx, dctx, lse, dqkv, delta, dq_acc, heads, 1.0 / math.sqrt(H // heads), p_drop,
-                              seed, stream)
+                              seed, stream, q, rec, e5)
     _count(2)
-    return dqkv
+    return dqkv if fp8 is None else (dqkv, q)
 
 
 # ---------------------------------------------------------------------------

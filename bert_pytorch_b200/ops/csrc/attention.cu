@@ -57,6 +57,7 @@ struct AttnArgs {
   const float* delta;      // [B, h, S]
   __nv_bfloat16* dqkv;     // [B*S, 3H]
   float* dq_acc;           // [B*S, H] fp32 (only when more than one key block)
+  Fp8Out f8;               // optional fp8 copy of the output (ctx in the forward, dqkv in the backward)
 };
 
 // address of the 16-byte chunk holding columns [col8*8, col8*8+8) of row r inside a [128 x 128] bf16 tile
@@ -64,6 +65,19 @@ struct AttnArgs {
 __device__ __forceinline__ uint32_t p_chunk_offset(int r, int col8) {
   const int sub = col8 >> 3, ck = col8 & 7;
   return (uint32_t)(sub * 16384 + r * 128 + ((ck ^ (r & 7)) << 4));
+}
+
+// fp8 copy of NG*8 consecutive output elements held as raw fp32 bits in v[] (scaled by `mul`)
+template <int NG>
+__device__ __forceinline__ void emit_fp8_row(const Fp8Out& f8, size_t off, const uint32_t* v, float mul, float qscale,
+                                             float& amax) {
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    float t8[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) t8[t] = __uint_as_float(v[g * 8 + t]) * mul;
+    fp8_emit8(f8, off + g * 8, t8, qscale, amax);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -275,6 +289,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs p) 
         *reinterpret_cast<uint4*>(dst + g * 8) =
             make_uint4(pack_bf16(o[g * 8] * inv_l, o[g * 8 + 1] * inv_l), pack_bf16(o[g * 8 + 2] * inv_l, o[g * 8 + 3] * inv_l),
                        pack_bf16(o[g * 8 + 4] * inv_l, o[g * 8 + 5] * inv_l), pack_bf16(o[g * 8 + 6] * inv_l, o[g * 8 + 7] * inv_l));
+      if (p.f8.q) {
+        float amax = 0.f;
+        const float qscale = p.f8.meta[1];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float t8[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) t8[t] = o[g * 8 + t] * inv_l;
+          fp8_emit8(p.f8, (size_t)(row0 + q) * p.H + head * HD + ch * 32 + g * 8, t8, qscale, amax);
+        }
+        if (amax > 0.f) atomicMax(reinterpret_cast<int*>(p.f8.meta), __float_as_int(isfinite(amax) ? amax : 3.0e38f));
+      }
       if (ch == 0) p.lse[(size_t)bh * p.S + q] = (m + log2f(l)) * 0.6931471805599453f;
     }
   }
@@ -430,6 +456,11 @@ attn_fwd_single_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnA
             pack_bf16(__uint_as_float(o[g * 8 + 2]) * inv_l, __uint_as_float(o[g * 8 + 3]) * inv_l),
             pack_bf16(__uint_as_float(o[g * 8 + 4]) * inv_l, __uint_as_float(o[g * 8 + 5]) * inv_l),
             pack_bf16(__uint_as_float(o[g * 8 + 6]) * inv_l, __uint_as_float(o[g * 8 + 7]) * inv_l));
+      if (p.f8.q) {
+        float amax = 0.f;
+        emit_fp8_row<4>(p.f8, (size_t)(row0 + r) * p.H + head * HD + ch * 32, o, inv_l, p.f8.meta[1], amax);
+        if (amax > 0.f) atomicMax(reinterpret_cast<int*>(p.f8.meta), __float_as_int(isfinite(amax) ? amax : 3.0e38f));
+      }
       if (ch == 0) p.lse[(size_t)bh * p.S + r] = (m + log2f(l)) * 0.6931471805599453f;
     }
   }
@@ -515,6 +546,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         for (int g = 0; g < 8; ++g) {
           *reinterpret_cast<uint4*>(dk + g * 8) = make_uint4(0, 0, 0, 0);
           *reinterpret_cast<uint4*>(dv + g * 8) = make_uint4(0, 0, 0, 0);
+        }
+        if (p.f8.q) {
+          unsigned char* qk = p.f8.q + (size_t)(row0 + key) * 3 * p.H + p.H + head * HD;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            *reinterpret_cast<uint4*>(qk + g * 16) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(qk + p.H + g * 16) = make_uint4(0, 0, 0, 0);
+          }
         }
       }
     }
@@ -604,6 +643,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     const int ch = warp >> 2;                    // which 32-key column quarter this thread handles
     const uint32_t lane_base = uint32_t((warp & 3) * 32) << 16;
     const float c_scale = p.scale * LOG2E;
+    const float qscale8 = p.f8.q ? p.f8.meta[1] : 0.f;
+    float amax8 = 0.f;
     for (int i = 0; i < nqb; ++i) {
       const int q = i * TILE + r;
       const bool q_ok = q < p.S;
@@ -662,6 +703,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
                   pack_bf16(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3])),
                   pack_bf16(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5])),
                   pack_bf16(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7])));
+            if (p.f8.q) emit_fp8_row<2>(p.f8, (size_t)(row0 + q) * 3 * p.H + head * HD + ch * 16, v, 1.f, qscale8, amax8);
           } else {
             float* dq = p.dq_acc + (size_t)(row0 + q) * p.H + head * HD + ch * 16;
 #pragma unroll
@@ -694,8 +736,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
               pack_bf16(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3])),
               pack_bf16(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5])),
               pack_bf16(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7])));
+        if (p.f8.q)
+          emit_fp8_row<4>(p.f8, (size_t)(row0 + key) * 3 * p.H + (w + 1) * p.H + head * HD + c * 32, v, 1.f, qscale8, amax8);
       }
     }
+    if (p.f8.q) fp8_amax_commit(p.f8, amax8);
   }
   tc_fence_before();
   __syncthreads();
@@ -835,6 +880,8 @@ attn_bwd_single_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gri
     const float dlt = q_ok ? xch[r] + xch[128 + r] : 0.f;
     const uint64_t erow = ((uint64_t)bh * p.S + (uint64_t)q) * (uint64_t)p.S;
     uint32_t dsp[32];                            // this thread's 64 dS values, packed bf16
+    const float qscale8 = p.f8.q ? p.f8.meta[1] : 0.f;
+    float amax8 = 0.f;
     mbar_wait(sdp_ready, 0);
     tc_fence_after();
 #pragma unroll
@@ -892,6 +939,7 @@ attn_bwd_single_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gri
               pack_bf16(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3])),
               pack_bf16(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5])),
               pack_bf16(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7])));
+        if (p.f8.q) emit_fp8_row<4>(p.f8, (size_t)(row0 + q) * 3 * p.H + head * HD + ch * 32, v, 1.f, qscale8, amax8);
       }
     }
     const int key = r;
@@ -910,8 +958,11 @@ attn_bwd_single_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gri
               pack_bf16(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3])),
               pack_bf16(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5])),
               pack_bf16(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7])));
+        if (p.f8.q)
+          emit_fp8_row<4>(p.f8, (size_t)(row0 + key) * 3 * p.H + (ch + 1) * p.H + head * HD + c * 32, v, 1.f, qscale8, amax8);
       }
     }
+    if (p.f8.q) fp8_amax_commit(p.f8, amax8);
   }
   tc_fence_before();
   __syncthreads();
@@ -923,8 +974,10 @@ attn_bwd_single_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gri
 
 // dq_acc (fp32 [B*S, H]) -> q slots of dqkv (bf16 [B*S, 3H])
 __global__ void __launch_bounds__(256)
-attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, long long rows, int H) {
+attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, long long rows, int H, const Fp8Out f8) {
   const int per_row = H / 8;
+  const float qscale = f8.q ? f8.meta[1] : 0.f;
+  float amax = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows * per_row;
        i += (long long)gridDim.x * blockDim.x) {
     const long long row = i / per_row;
@@ -933,7 +986,12 @@ attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict_
     const float4 c = *reinterpret_cast<const float4*>(acc + row * H + col + 4);
     *reinterpret_cast<uint4*>(dqkv + row * 3 * H + col) =
         make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(c.x, c.y), pack_bf16(c.z, c.w));
+    if (f8.q) {
+      const float t8[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+      fp8_emit8(f8, (size_t)(row * 3 * H + col), t8, qscale, amax);
+    }
   }
+  if (f8.q) fp8_amax_commit(f8, amax);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -950,10 +1008,10 @@ static void fill_args(AttnArgs& a, int B, int S, int h, int d, const int* seqlen
 }
 
 void attention_fwd(const void* qkv, const int* seqlens, void* ctx, float* lse, int B, int S, int h, int d,
-                   float scale, Seed seed, unsigned int stream, float p_drop, cudaStream_t st) {
+                   float scale, Seed seed, unsigned int stream, float p_drop, Fp8Out f8, cudaStream_t st) {
   AttnArgs a;
   fill_args(a, B, S, h, d, seqlens, scale, seed, stream, p_drop);
-  a.ctx = (__nv_bfloat16*)ctx; a.lse = lse;
+  a.ctx = (__nv_bfloat16*)ctx; a.lse = lse; a.f8 = f8;
   const int H = h * d;
   CUtensorMap tm = make_tmap_2d_bf16(qkv, 3 * H, (uint64_t)B * S, 3 * H, 64, TILE);
   dim3 grid((S + TILE - 1) / TILE, B * h);
@@ -978,9 +1036,10 @@ void attention_fwd(const void* qkv, const int* seqlens, void* ctx, float* lse, i
 
 void attention_bwd(const void* qkv, const int* seqlens, const void* ctx, const void* dctx, const float* lse,
                    void* dqkv, float* delta_ws, float* dq_acc, int B, int S, int h, int d, float scale,
-                   Seed seed, unsigned int stream, float p_drop, cudaStream_t st) {
+                   Seed seed, unsigned int stream, float p_drop, Fp8Out f8, cudaStream_t st) {
   AttnArgs a;
   fill_args(a, B, S, h, d, seqlens, scale, seed, stream, p_drop);
+  a.f8 = f8;
   const int H = h * d;
   a.lse = const_cast<float*>(lse); a.delta = delta_ws; a.dqkv = (__nv_bfloat16*)dqkv; a.dq_acc = dq_acc;
   a.ctx = (__nv_bfloat16*)const_cast<void*>(ctx);
@@ -1016,7 +1075,7 @@ void attention_bwd(const void* qkv, const int* seqlens, const void* ctx, const v
     const long long work = (long long)B * S * (H / 8);
     int g = (int)((work + 255) / 256);
     if (g > 148 * 16) g = 148 * 16;
-    attn_dq_convert_kernel<<<g, 256, 0, st>>>(dq_acc, (__nv_bfloat16*)dqkv, (long long)B * S, H);
+    attn_dq_convert_kernel<<<g, 256, 0, st>>>(dq_acc, (__nv_bfloat16*)dqkv, (long long)B * S, H, a.f8);
   }
 }
 

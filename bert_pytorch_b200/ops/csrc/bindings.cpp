@@ -324,23 +324,25 @@ void arena_adam(Tensor g, Tensor p, Tensor m, Tensor v, c10::optional<Tensor> sh
 }
 
 void attention_fwd(Tensor qkv, Tensor seqlens, Tensor ctx, Tensor lse, int64_t heads, double scale, double p_drop,
-                   int64_t seed, int64_t stream_id) {
+                   int64_t seed, int64_t stream_id, c10::optional<Tensor> q8, c10::optional<Tensor> meta8, bool e5m2) {
   check_bf16(qkv, "qkv"); check_bf16(ctx, "ctx");
   TORCH_CHECK(qkv.dim() == 3 && qkv.is_contiguous(), "qkv: contiguous [B,S,3H]");
   const int B = (int)qkv.size(0), S = (int)qkv.size(1), H = (int)qkv.size(2) / 3;
   c10::cuda::CUDAGuard guard(qkv.device());
   b200::attention_fwd(qkv.data_ptr(), seqlens.data_ptr<int>(), ctx.data_ptr(), lse.data_ptr<float>(), B, S, (int)heads,
-                      H / (int)heads, (float)scale, mk_seed(seed), (unsigned)stream_id, (float)p_drop, cur_stream());
+                      H / (int)heads, (float)scale, mk_seed(seed), (unsigned)stream_id, (float)p_drop,
+                      mk_fp8(q8, meta8, e5m2, ctx.numel()), cur_stream());
 }
 void attention_bwd(Tensor qkv, Tensor seqlens, Tensor ctx, Tensor dctx, Tensor lse, Tensor dqkv, Tensor delta_ws,
-                   c10::optional<Tensor> dq_acc, int64_t heads, double scale, double p_drop, int64_t seed, int64_t stream_id) {
+                   c10::optional<Tensor> dq_acc, int64_t heads, double scale, double p_drop, int64_t seed, int64_t stream_id,
+                   c10::optional<Tensor> q8, c10::optional<Tensor> meta8, bool e5m2) {
   check_bf16(qkv, "qkv"); check_bf16(ctx, "ctx"); check_bf16(dctx, "dctx"); check_bf16(dqkv, "dqkv");
   TORCH_CHECK(qkv.is_contiguous() && ctx.is_contiguous() && dctx.is_contiguous() && dqkv.is_contiguous(), "attention_bwd needs contiguous tensors");
   const int B = (int)qkv.size(0), S = (int)qkv.size(1), H = (int)qkv.size(2) / 3;
   c10::cuda::CUDAGuard guard(qkv.device());
   b200::attention_bwd(qkv.data_ptr(), seqlens.data_ptr<int>(), ctx.data_ptr(), dctx.data_ptr(), lse.data_ptr<float>(),
                       dqkv.data_ptr(), delta_ws.data_ptr<float>(), opt_f32(dq_acc), B, S, (int)heads, H / (int)heads, (float)scale,
-                      mk_seed(seed), (unsigned)stream_id, (float)p_drop, cur_stream());
+                      mk_seed(seed), (unsigned)stream_id, (float)p_drop, mk_fp8(q8, meta8, e5m2, dqkv.numel()), cur_stream());
 }
 
 void fused_allreduce_lamb(int64_t rank, int64_t world, bool use_multicast, std::vector<int64_t> grad_ptrs,

@@ -50,10 +50,10 @@ void arena_adam(float* g, float* p, float* m, float* v, void* shadow, const int*
 
 // attention.cu
 void attention_fwd(const void* qkv, const int* seqlens, void* ctx, float* lse, int B, int S, int h, int d,
-                   float scale, Seed seed, unsigned int stream, float p_drop, cudaStream_t st);
+                   float scale, Seed seed, unsigned int stream, float p_drop, Fp8Out f8, cudaStream_t st);
 void attention_bwd(const void* qkv, const int* seqlens, const void* ctx, const void* dctx, const float* lse,
                    void* dqkv, float* delta_ws, float* dq_acc, int B, int S, int h, int d, float scale,
-                   Seed seed, unsigned int stream, float p_drop, cudaStream_t st);
+                   Seed seed, unsigned int stream, float p_drop, Fp8Out f8, cudaStream_t st);
 
 // comm.cu -- fused peer-memory all-reduce + partitioned LAMB (one cooperative kernel per step)
 struct FusedLambLaunch {

@@ -181,3 +181,29 @@ def test_mxfp8_block_scaled_gemm(shape):
     assert (out_b.float() - (ref + bias.float())).abs().max().item() <= 1e-2 * (ref.abs().max().item() + 1.0)
     full = a.float() @ b.float().t()
     assert ((out - full).norm() / full.norm()).item() < 0.06
+
+
+def test_attention_kernels_emit_fp8_copies():
+    """Attention forward / backward write the fp8 copy of ctx / dqkv in the same kernels (S = 128 single-block and
+    S = 256 streaming variants)."""
+    ops = _ops()
+    api = ops.api
+    dev = torch.device("cuda")
+    for S in (128, 256):
+        B, heads = 2, 2
+        H = heads * 64
+        qkv = (torch.randn(B, S, 3 * H, device=dev) * 0.5).bfloat16()
+        lens = torch.tensor([S, S - 40], device=dev, dtype=torch.int32)
+        meta = api.Fp8Meta(["ctx", "dqkv"], [False, True], dev)
+        meta.record("ctx")[0] = 8.0
+        meta.record("dqkv")[0] = 16.0
+        meta.update()
+        ctx, lse, q = api.attention_fwd(qkv, lens, heads, fp8=(meta, "ctx"))
+        deq = _deq(q, meta, "ctx")
+        assert ((deq - ctx.float()).abs() <= ctx.float().abs() * 0.07 + 2e-3 / meta.record("ctx")[1].item()).all()
+        assert meta.record("ctx")[0].item() == pytest.approx(ctx.float().abs().max().item(), rel=2e-2)
+        dctx = torch.randn(B, S, H, device=dev).bfloat16()
+        dqkv, q2 = api.attention_bwd(qkv, lens, ctx, dctx, lse, heads, fp8=(meta, "dqkv"))
+        deq2 = _deq(q2, meta, "dqkv")
+        assert ((deq2 - dqkv.float()).abs() <= dqkv.float().abs() * 0.14 + 2e-5 / meta.record("dqkv")[1].item() + 1e-6).all()
+        assert meta.record("dqkv")[0].item() == pytest.approx(dqkv.float().abs().max().item(), rel=2e-2)
