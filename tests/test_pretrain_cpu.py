@@ -81,3 +81,29 @@ def test_phase2_style_step_surgery(tmp_path):
 def test_required_arguments():
     with pytest.raises(ValueError):
         pretrain.check_required(pretrain.parse_arguments(["--output_dir", "x"]))
+
+
+def test_kfac_flag_and_multi_rank_gloo(tmp_path):
+    """--kfac on the CLI path (preconditioner built, stepped, checkpointed) and a 2-rank gloo launch of the same
+    runtime through torchrun (sampler chunking, gradient all-reduce, rank-0-only outputs)."""
+    import subprocess
+    import sys
+    data, model_json, _ = _workspace(tmp_path)
+    out = str(tmp_path / "k" / "out"); os.makedirs(os.path.dirname(out))
+    pretrain.cli(_argv(data, model_json, out, steps=3, max_steps=3, extra=["--kfac", "--kfac_inv_interval", "1",
+                                                                           "--kfac_factor_interval", "1"]))
+    payload = torch.load(ck.find_latest(os.path.join(out, "pretrain_ckpts"))[1], map_location="cpu", weights_only=False)
+    assert "preconditioner" in payload and payload["preconditioner"]["steps"] == 3
+    assert payload["preconditioner"]["layers"]                  # factors were collected through the module hooks
+
+    out2 = str(tmp_path / "g" / "out"); os.makedirs(os.path.dirname(out2))
+    argv = _argv(data, model_json, out2, steps=2, max_steps=2)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29733", os.path.join(root, "run_pretraining.py"), *argv]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root,
+                         env=dict(os.environ, OMP_NUM_THREADS="1"))
+    assert res.returncode == 0, res.stderr[-3000:]
+    assert ck.find_latest(os.path.join(out2, "pretrain_ckpts"))[0] == 2
+    rows = list(csv.DictReader(open(os.path.join(out2, "pretraining_phase1_log_metrics.csv"))))
+    assert [int(r["step"]) for r in rows] == [1, 2]
