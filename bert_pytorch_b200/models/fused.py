@@ -493,6 +493,8 @@ class FusedPretrainer:
         self._graphs: Dict[tuple, dict] = {}
         self._seed_step: Optional[torch.Tensor] = None
         self.grad_push = False                # set by the runtime around the last micro-step (PeerComm.begin_push)
+        self._cls_idx = None                  # row indices of the [CLS] tokens (NSP head)
+        self._cls_S = 0
 
     def _max_pred(self, labels: torch.Tensor) -> int:
         # capacity of masked positions per sequence; fixed per run so shapes stay static
@@ -591,34 +593,32 @@ class FusedPretrainer:
         d_seq = torch.zeros(M, H, dtype=torch.bfloat16, device=seq.device)
         K.scatter_rows(d_rows, idx, d_seq)
 
-        # ---- NSP head: [B,H] sized; plain torch ops with the backward written out (no autograd: the whole
-        #      micro-step stays capturable), gradients accumulated straight into the arena views
+        # ---- NSP head on our own kernels as well (K19 / K20 / K25): pooler = tcgen05 GEMM with the bias+tanh epilogue
+        #      on the [CLS] rows, classifier + CE + their backward = one small kernel, pooler backward = the usual
+        #      dgrad / wgrad GEMMs (M = B rows)
         if self.has_nsp and next_sentence_labels is not None:
             pool, nsp = self.model.bert.pooler.dense_act, self.model.cls.seq_relationship
-            # weights from the bf16 shadow (what every other GEMM multiplies with; also the only copy that is
-            # complete on every rank when the fp32 master is kept shard-local), biases from the master copy
-            w_pool = A.shadow(eng.prefix + "pooler.dense_act.weight").float()
-            w_nsp = A.shadow("cls.seq_relationship.weight").float()
-            cls_tok = seq.view(B, S, H)[:, 0].float()
-            pooled = torch.tanh(torch.addmm(pool.bias, cls_tok, w_pool.t()))
-            nsp_logits = torch.addmm(nsp.bias, pooled, w_nsp.t())
-            tgt_n = next_sentence_labels.long().view(-1)
-            valid = (tgt_n >= 0).float()
-            n_valid = valid.sum().clamp_(min=1.0)
-            logp = torch.log_softmax(nsp_logits, dim=-1)
-            onehot = F.one_hot(tgt_n.clamp(min=0), nsp_logits.size(-1)).float()
-            nsp_loss = -((logp * onehot).sum(-1) * valid).sum() / n_valid
-            d_logits = (logp.exp() - onehot) * (valid / n_valid * grad_scale).unsqueeze(1)
+            pw = A.shadow(eng.prefix + "pooler.dense_act.weight")
+            if self._cls_idx is None or self._cls_idx.numel() != B or self._cls_S != S:
+                self._cls_idx = (torch.arange(B, device=seq.device, dtype=torch.int32) * S).contiguous()
+                self._cls_S = S
+            cls_tok = K.gather_rows(seq, self._cls_idx)                                        # [B, H] bf16
+            pooled = K.gemm(cls_tok, pw, epi=K.EPI_BIAS_TANH, bias=A.shadow(eng.prefix + "pooler.dense_act.bias"))
+            d_z = K.nsp_head_(pooled, A.shadow("cls.seq_relationship.weight"), nsp.bias, next_sentence_labels.long().view(-1),
+                              grad_scale, loss, nsp.weight.grad, nsp.bias.grad)
             kf = getattr(self.model.bert, "_kfac", None)
-            if kf is not None:                     # the NSP classifier is an nn.Linear: K-FAC preconditions it too
-                kf.tap("cls.seq_relationship", pooled, d_logits)
-            nsp.weight.grad.addmm_(d_logits.t(), pooled)
-            nsp.bias.grad.add_(d_logits.sum(0))
-            d_z = (d_logits @ w_nsp) * (1.0 - pooled * pooled)
-            pool.weight.grad.addmm_(d_z.t(), cls_tok)
-            pool.bias.grad.add_(d_z.sum(0))
-            d_seq.view(B, S, H)[:, 0] += (d_z @ w_pool).to(torch.bfloat16)
-            loss = loss + nsp_loss
+            if kf is not None:                     # the NSP classifier is an nn.Linear: K-FAC preconditions it; its output
+                with torch.no_grad():              # gradient is rebuilt here (K-FAC mode only, plain torch on [B, 2])
+                    lg = pooled.float() @ A.shadow("cls.seq_relationship.weight").float().t() + nsp.bias
+                    y = next_sentence_labels.long().view(-1)
+                    valid = (y >= 0).float()
+                    d_lg = (torch.softmax(lg, -1) - F.one_hot(y.clamp(min=0), 2).float()) \
+                        * (valid / valid.sum().clamp_(min=1.0) * grad_scale).unsqueeze(1)
+                kf.tap("cls.seq_relationship", pooled, d_lg)
+            K.wgrad_accumulate(d_z, cls_tok, pool.weight.grad)
+            K.colsum_accumulate(d_z, pool.bias.grad)
+            d_cls = K.gemm(d_z, pw, layout=K.NN)
+            d_seq.view(B, S, H)[:, 0] += d_cls
 
         eng.backward(sv, d_seq)
         return loss.squeeze(0) if loss.dim() else loss

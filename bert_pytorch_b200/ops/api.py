@@ -310,6 +310,17 @@ def scatter_rows(src: torch.Tensor, idx: torch.Tensor, dst: torch.Tensor) -> Non
     _count()
 
 
+def nsp_head_(pooled: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, labels: torch.Tensor, grad_scale: float,
+              loss_out: torch.Tensor, dw: torch.Tensor, db: torch.Tensor) -> torch.Tensor:
+    """NSP classifier [B,H] x [H,2] + cross-entropy (ignore_index -1) + backward in one launch: ``loss_out`` += mean CE,
+    ``dw`` / ``db`` (fp32) accumulate the classifier gradients, returns dz = d loss / d (pooler pre-activation) [B,H]
+    bf16 (tanh' of the pooler folded in)."""
+    dz = torch.empty_like(pooled)
+    extension().nsp_head(pooled, w, bias, labels, grad_scale, loss_out, dz, dw, db)
+    _count()
+    return dz
+
+
 def softmax_ce_(logits: torch.Tensor, targets: torch.Tensor, count: torch.Tensor, grad_scale: float,
                 loss_out: torch.Tensor) -> None:
     """In place: logits <- d loss / d logits (scaled); loss_out += mean CE over valid targets."""

@@ -386,6 +386,22 @@ void fused_allreduce_lamb(int64_t rank, int64_t world, bool use_multicast, std::
   b200::fused_allreduce_lamb(L, cur_stream());
 }
 
+void nsp_head(Tensor pooled, Tensor w, Tensor bias, Tensor labels, double grad_scale, Tensor loss_out, Tensor dz, Tensor dw,
+              Tensor db) {
+  check_bf16(pooled, "pooled"); check_bf16(w, "w"); check_bf16(dz, "dz");
+  TORCH_CHECK(pooled.dim() == 2 && pooled.is_contiguous() && dz.is_contiguous() && dz.sizes() == pooled.sizes(), "nsp_head: pooled/dz");
+  const int64_t B = pooled.size(0), H = pooled.size(1);
+  TORCH_CHECK(w.is_contiguous() && w.size(0) == 2 && w.size(1) == H, "nsp_head: w must be [2, H]");
+  TORCH_CHECK(bias.scalar_type() == at::kFloat && bias.numel() == 2 && labels.scalar_type() == at::kLong && labels.numel() == B,
+              "nsp_head: bias fp32 [2], labels int64 [B]");
+  TORCH_CHECK(dw.scalar_type() == at::kFloat && dw.is_contiguous() && dw.numel() == 2 * H && db.scalar_type() == at::kFloat &&
+              db.numel() == 2 && loss_out.scalar_type() == at::kFloat, "nsp_head: fp32 gradient / loss buffers");
+  c10::cuda::CUDAGuard guard(pooled.device());
+  b200::nsp_head(pooled.data_ptr(), w.data_ptr(), bias.data_ptr<float>(), reinterpret_cast<const long long*>(labels.data_ptr<int64_t>()), (int)B, (int)H,
+                 (float)grad_scale, loss_out.data_ptr<float>(), dz.data_ptr(), dw.data_ptr<float>(), db.data_ptr<float>(),
+                 cur_stream());
+}
+
 void peer_allreduce(int64_t rank, int64_t world, bool use_multicast, std::vector<int64_t> buf_ptrs,
                     std::vector<int64_t> flag_ptrs, int64_t buf_mc, Tensor grid_bar, int64_t epoch, int64_t n, double scale) {
   TORCH_CHECK((int64_t)buf_ptrs.size() == world && (int64_t)flag_ptrs.size() == world && world <= 16, "peer pointer lists");
@@ -484,6 +500,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gather_rows", &gather_rows);
   m.def("scatter_rows", &scatter_rows);
   m.def("softmax_ce", &softmax_ce);
+  m.def("nsp_head", &nsp_head);
   m.def("mt_l2norm", &mt_l2norm);
   m.def("mt_scale", &mt_scale);
   m.def("flat_sumsq", &flat_sumsq);

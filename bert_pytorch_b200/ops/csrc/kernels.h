@@ -86,6 +86,10 @@ struct PeerAllreduceLaunch {
 };
 void peer_allreduce(const PeerAllreduceLaunch& L, cudaStream_t st);
 
+// loss.cu: NSP classifier + CE + backward in one launch
+void nsp_head(const void* pooled_bf16, const void* w_bf16, const float* bias, const long long* labels, int B, int H,
+              float grad_scale, float* loss_out, void* dz_bf16, float* dw, float* db, cudaStream_t st);
+
 // gemm_mx.cu: block-scaled MXFP8 (e4m3 + one ue8m0 scale per 32 elements along K), NT layout
 void mx_quantize(const void* x_bf16, void* q, void* sf, int R, int K, cudaStream_t st);
 void gemm_mxfp8(const void* a, const void* sfa, const void* b, const void* sfb, void* out, int ldo, bool out_f32,
