@@ -16,6 +16,7 @@ and written through this repo's native HDF5 writer (no h5py).
 """
 from __future__ import annotations
 
+import os
 import random
 import time
 from dataclasses import dataclass
@@ -48,18 +49,37 @@ class TrainingSample:
         return ids, special
 
 
-def read_documents(path: str, tokenizer) -> List[Document]:
+def read_documents(path: str, tokenizer, fast=None, batch_lines: int = 8192) -> List[Document]:
+    """Documents = blank-line separated groups of lines; every line becomes a list of token ids.  With ``fast``
+    (:class:`~.tokenization.FastWordPiece`) the ASCII lines are tokenised in bulk by the native C++ WordPiece
+    (identical ids to the ``tokenizers`` package on ASCII text, tests/test_dataset.py), the rest by ``tokenizer``."""
     docs: List[Document] = [[]]
-    with open(path, "r", encoding="utf-8", errors="ignore") as f:
-        for line in f:
-            line = line.strip()
-            if not line:
+    pending: List[str] = []          # lines of the current batch; None marks a document boundary
+
+    def flush():
+        lines = [l for l in pending if l is not None]
+        if fast is not None:
+            enc = fast.encode_batch(lines, fallback=lambda t: tokenizer.encode(t, add_special_tokens=False).ids)
+        else:
+            enc = [tokenizer.encode(l, add_special_tokens=False).ids for l in lines]
+        it = iter(enc)
+        for l in pending:
+            if l is None:
                 if docs[-1]:
                     docs.append([])
                 continue
-            ids = tokenizer.encode(line, add_special_tokens=False).ids
-            if ids:
+            ids = next(it)
+            if len(ids):
                 docs[-1].append(list(ids))
+        pending.clear()
+
+    with open(path, "r", encoding="utf-8", errors="ignore") as f:
+        for line in f:
+            line = line.strip()
+            pending.append(line if line else None)
+            if len(pending) >= batch_lines:
+                flush()
+    flush()
     return [d for d in docs if d]
 
 
@@ -164,7 +184,13 @@ def encode_file(input_file: str, output_file: str, vocab_file: str, tokenizer_ki
     if cls_id is None or sep_id is None:
         raise ValueError("the vocabulary must contain [CLS] and [SEP]")
     print(f"[encoder] Creating instances from {input_file}", flush=True)
-    docs = read_documents(input_file, tok)
+    fast = None
+    if tokenizer_kind == "wordpiece" and os.environ.get("B200_NATIVE_TOKENIZER", "1") != "0":
+        from .tokenization import FastWordPiece
+        fast = FastWordPiece(vocab_file, do_lower_case=not uppercase)
+        if fast.native is None:
+            fast = None
+    docs = read_documents(input_file, tok, fast=fast)
     packer = SamplePacker(max_seq_len, next_seq_prob, short_seq_prob, random.Random(seed))
     samples = packer.pack_file(docs)
     write_samples_to_hdf5(output_file, samples, max_seq_len, cls_id, sep_id)

@@ -174,3 +174,40 @@ class BertTokenizer:
 
     def token_to_id(self, token: str) -> Optional[int]:
         return self.vocab.get(token)
+
+
+class FastWordPiece:
+    """WordPiece ids for bulk encoding (dataset building): ASCII lines go through the native C++ tokenizer
+    (``ops/csrc/host.cpp``), everything else -- and every line when the helper is not built -- through the pure
+    Python ``BasicTokenizer`` + ``WordpieceTokenizer`` above.  Both paths implement the same rules."""
+
+    def __init__(self, vocab_file: str, do_lower_case: bool = True):
+        self.py = BertTokenizer(vocab_file, do_lower_case=do_lower_case)
+        self.native = None
+        try:
+            from ..ops import native_host
+            host = native_host.load_or_none()
+            tokens = list(self.py.vocab.keys())
+            # the native table is positional: only usable when ids are exactly 0..n-1 in file order
+            if host is not None and all(self.py.vocab[t] == i for i, t in enumerate(tokens)) and \
+                    all("\n" not in t for t in tokens):
+                self.native = native_host.WordPieceEncoder(host, tokens, lowercase=do_lower_case)
+        except Exception:
+            self.native = None
+
+    def encode_batch(self, texts: List[str], fallback=None) -> List[List[int]]:
+        """``fallback(text) -> ids`` handles the lines the native path does not take (non-ASCII); default: the
+        pure-Python tokenizer of this module."""
+        out: List[Optional[List[int]]] = [None] * len(texts)
+        if self.native is not None:
+            idx = [i for i, t in enumerate(texts) if t.isascii()]
+            if idx:
+                for i, ids in zip(idx, self.native.encode_batch([texts[i] for i in idx])):
+                    out[i] = ids.tolist()
+        for i, t in enumerate(texts):
+            if out[i] is None:
+                out[i] = list(fallback(t)) if fallback is not None else self.py.convert_tokens_to_ids(self.py.tokenize(t))
+        return out  # type: ignore[return-value]
+
+    def encode(self, text: str) -> List[int]:
+        return self.encode_batch([text])[0]

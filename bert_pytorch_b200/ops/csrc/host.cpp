@@ -4,12 +4,17 @@
 //   * mask_batch_i32  -- dynamic MLM masking of a whole micro-batch (semantics of the reference's
 //     per-sample Python loop, src/dataset.py:277-296, see data/dataset.py::mask_batch), threaded over rows
 //     with a counter-based RNG so results do not depend on the thread count.
+//   * wp_*            -- WordPiece tokenisation of ASCII text (BasicTokenizer + greedy longest-match sub-words,
+//     the semantics of data/tokenization.py, i.e. of the reference's src/tokenization.py:60-229; the reference gets
+//     its speed from the Rust `tokenizers` package), batched and threaded; non-ASCII text stays on the Python path.
 // zlib is linked as libz.so.1 with hand-declared prototypes (the image ships no zlib.h).
 #include <algorithm>
 #include <atomic>
 #include <cstdint>
 #include <cstring>
+#include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 extern "C" {
@@ -120,3 +125,122 @@ void mask_batch_i32(const int32_t* ids, const int32_t* sp, int32_t* out_ids, int
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// WordPiece (ASCII fast path)
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct WordPiece {
+  std::unordered_map<std::string, int32_t> vocab;
+  int32_t unk = 0;
+  bool lower = true;
+  int max_chars = 100;
+};
+
+inline bool ascii_punct(unsigned char c) {
+  return (c >= 33 && c <= 47) || (c >= 58 && c <= 64) || (c >= 91 && c <= 96) || (c >= 123 && c <= 126);
+}
+
+// greedy longest-match-first split of one word (already lower-cased / punctuation-free or a single punctuation mark)
+void wordpiece_word(const WordPiece& wp, const std::string& word, std::vector<int32_t>& out) {
+  if ((int)word.size() > wp.max_chars) { out.push_back(wp.unk); return; }
+  const size_t mark = out.size();
+  size_t start = 0;
+  std::string sub;
+  while (start < word.size()) {
+    size_t end = word.size();
+    int32_t id = -1;
+    while (start < end) {
+      sub.assign(start > 0 ? "##" : "");
+      sub.append(word, start, end - start);
+      auto it = wp.vocab.find(sub);
+      if (it != wp.vocab.end()) { id = it->second; break; }
+      --end;
+    }
+    if (id < 0) { out.resize(mark); out.push_back(wp.unk); return; }
+    out.push_back(id);
+    start = end;
+  }
+}
+
+void encode_ascii(const WordPiece& wp, const char* s, int64_t n, std::vector<int32_t>& out) {
+  static const char* kNever[] = {"[UNK]", "[SEP]", "[PAD]", "[CLS]", "[MASK]"};
+  std::string tok, piece;
+  int64_t i = 0;
+  while (i < n) {
+    // clean + whitespace split: control characters vanish, \t \n \r and space separate tokens
+    tok.clear();
+    for (; i < n; ++i) {
+      const unsigned char c = (unsigned char)s[i];
+      if (c == ' ' || c == '\t' || c == '\n' || c == '\r') { if (!tok.empty()) break; else continue; }
+      if (c < 0x20 || c == 0x7F) continue;
+      tok.push_back((char)c);
+    }
+    if (tok.empty()) continue;
+    bool never = false;
+    for (const char* k : kNever) never |= tok == k;
+    if (never) {
+      auto it = wp.vocab.find(tok);
+      out.push_back(it != wp.vocab.end() ? it->second : wp.unk);
+      continue;
+    }
+    if (wp.lower)
+      for (auto& c : tok) if (c >= 'A' && c <= 'Z') c = (char)(c - 'A' + 'a');
+    // punctuation marks are their own words
+    piece.clear();
+    for (char c : tok) {
+      if (ascii_punct((unsigned char)c)) {
+        if (!piece.empty()) { wordpiece_word(wp, piece, out); piece.clear(); }
+        wordpiece_word(wp, std::string(1, c), out);
+      } else {
+        piece.push_back(c);
+      }
+    }
+    if (!piece.empty()) wordpiece_word(wp, piece, out);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+// vocab: tokens separated by '\n', id = line number
+void* wp_create(const char* blob, int64_t len, int lowercase) {
+  auto* wp = new WordPiece();
+  wp->lower = lowercase != 0;
+  int32_t id = 0;
+  int64_t a = 0;
+  for (int64_t i = 0; i <= len; ++i) {
+    if (i == len || blob[i] == '\n') {
+      int64_t b = i;
+      if (b > a && blob[b - 1] == '\r') --b;
+      if (i < len || b > a) wp->vocab.emplace(std::string(blob + a, (size_t)(b - a)), id++);
+      a = i + 1;
+    }
+  }
+  auto it = wp->vocab.find("[UNK]");
+  wp->unk = it != wp->vocab.end() ? it->second : 0;
+  return wp;
+}
+
+void wp_destroy(void* h) { delete static_cast<WordPiece*>(h); }
+
+// texts: buf[offs[i] .. offs[i+1]) (ASCII).  Writes the ids of text i to out[out_offs[i] .. out_offs[i+1]).
+// Returns the total number of ids; if that exceeds `cap` nothing is copied and the caller retries with a larger buffer.
+int64_t wp_encode_batch(void* h, const char* buf, const int64_t* offs, int64_t n, int32_t* out, int64_t cap,
+                        int64_t* out_offs, int threads) {
+  const WordPiece& wp = *static_cast<const WordPiece*>(h);
+  std::vector<std::vector<int32_t>> res((size_t)n);
+  parallel_for(n, threads, [&](int64_t i) { encode_ascii(wp, buf + offs[i], offs[i + 1] - offs[i], res[(size_t)i]); });
+  int64_t total = 0;
+  for (int64_t i = 0; i < n; ++i) { out_offs[i] = total; total += (int64_t)res[(size_t)i].size(); }
+  out_offs[n] = total;
+  if (total > cap) return total;
+  for (int64_t i = 0; i < n; ++i)
+    if (!res[(size_t)i].empty()) std::memcpy(out + out_offs[i], res[(size_t)i].data(), res[(size_t)i].size() * sizeof(int32_t));
+  return total;
+}
+
+}  // extern "C"
+

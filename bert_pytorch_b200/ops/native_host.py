@@ -33,6 +33,14 @@ class _Host:
                                        ctypes.c_int32, ctypes.c_double, ctypes.c_int32, ctypes.c_double,
                                        ctypes.c_double, ctypes.c_uint64, ctypes.c_int]
 
+        lib.wp_create.restype = ctypes.c_void_p
+        lib.wp_create.argtypes = [ctypes.c_char_p, ctypes.c_int64, ctypes.c_int]
+        lib.wp_destroy.restype = None
+        lib.wp_destroy.argtypes = [ctypes.c_void_p]
+        lib.wp_encode_batch.restype = ctypes.c_int64
+        lib.wp_encode_batch.argtypes = [ctypes.c_void_p, ctypes.c_char_p, i64p, ctypes.c_int64, ctypes.c_void_p,
+                                        ctypes.c_int64, i64p, ctypes.c_int]
+
     def inflate_rows(self, raw: bytes, offs: np.ndarray, sizes: np.ndarray, rows0: np.ndarray,
                      chunk_rows: int, total_rows: int, row_bytes: int, out: np.ndarray,
                      threads: int = 0) -> None:
@@ -81,3 +89,44 @@ def mask_batch(host: _Host, ids: np.ndarray, sp: np.ndarray, *, seed: int, mask_
                             B, S, sp.shape[1], mask_token_index, max_pred_per_seq, masked_lm_prob,
                             vocab_size, original_token_prob, random_token_prob, seed, threads)
     return out_ids, labels
+
+
+class WordPieceEncoder:
+    """Native WordPiece for ASCII text (ops/csrc/host.cpp: wp_*): BasicTokenizer + greedy longest-match sub-words,
+    batched and threaded.  ``vocab`` maps token -> id with ids 0..n-1 in file order."""
+
+    def __init__(self, host: _Host, vocab_tokens, lowercase: bool = True):
+        self._host = host
+        blob = "\n".join(vocab_tokens).encode("utf-8")
+        self._h = host.lib.wp_create(blob, len(blob), 1 if lowercase else 0)
+        if not self._h:
+            raise RuntimeError("wp_create failed")
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                self._host.lib.wp_destroy(h)
+            except Exception:
+                pass
+
+    def encode_batch(self, texts, threads: int = 0):
+        """``texts``: ASCII strings -> list of int32 arrays of token ids (no special tokens added)."""
+        n = len(texts)
+        if n == 0:
+            return []
+        enc = [t.encode("ascii") for t in texts]
+        offs = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum([len(e) for e in enc], out=offs[1:])
+        buf = b"".join(enc)
+        out_offs = np.empty(n + 1, dtype=np.int64)
+        cap = max(16, len(buf))                      # a token has at least one character: ids <= characters
+        out = np.empty(cap, dtype=np.int32)
+        i64p = ctypes.POINTER(ctypes.c_int64)
+        total = self._host.lib.wp_encode_batch(self._h, buf, offs.ctypes.data_as(i64p), n, out.ctypes.data, cap,
+                                               out_offs.ctypes.data_as(i64p), threads)
+        if total > cap:                              # cannot happen with the bound above; kept as a safety net
+            out = np.empty(total, dtype=np.int32)
+            total = self._host.lib.wp_encode_batch(self._h, buf, offs.ctypes.data_as(i64p), n, out.ctypes.data, total,
+                                                   out_offs.ctypes.data_as(i64p), threads)
+        return [out[out_offs[i]:out_offs[i + 1]] for i in range(n)]

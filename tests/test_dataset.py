@@ -178,3 +178,41 @@ def test_batched_loader_covers_epoch_and_resumes(shards):
     sam3.load_state_dict(state)
     rest = list(BatchedPretrainingLoader(ds3, sam3, batch_size=8, pin_memory=False))
     assert sum(b[0].size(0) for b in rest) == 60
+
+
+def test_native_wordpiece_matches_python_and_hf(tmp_path):
+    """ops/csrc/host.cpp wp_*: the C++ WordPiece gives the ids of the pure-Python BasicTokenizer + WordpieceTokenizer and
+    of the `tokenizers` package on ASCII text; non-ASCII lines take the fallback; read_documents keeps document
+    boundaries when it tokenises in bulk."""
+    import random
+    from bert_pytorch_b200.data import encode
+    from bert_pytorch_b200.data.tokenization import FastWordPiece, get_wordpiece_tokenizer
+    words = ["the", "quick", "brown", "fox", "jump", "##s", "##ed", "over", "lazy", "dog", ".", ",", "!", "?", "'", "-", "a", "b",
+             "c", "##a", "##b", "##c", "un", "##able", "##ing", "run", "##n", "1", "2", "##3", "(", ")", "hello", "world", "##ld",
+             "wor", "caf", "##e"]
+    vocab = ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]"] + words
+    vf = tmp_path / "vocab.txt"
+    vf.write_text("\n".join(vocab) + "\n")
+    fw = FastWordPiece(str(vf), True)
+    if fw.native is None:
+        pytest.skip("native host helper not built")
+    hf = get_wordpiece_tokenizer(str(vf))
+    rng = random.Random(3)
+    alphabet = "abcABC thequickbrownfoxjumpsedoverlazydogworldhello .,!?'-()123\t"
+    texts = ["".join(rng.choice(alphabet) for _ in range(rng.randint(0, 70))) for _ in range(1500)]
+    texts += ["[MASK] hello [CLS] WORLD worlds unable running", "", "   ", "a" * 150, "ctrl\x01char\x7f here"]
+    nat = fw.encode_batch(texts)
+    for t, ids in zip(texts, nat):
+        assert ids == fw.py.convert_tokens_to_ids(fw.py.tokenize(t)), t
+        if t.strip() and "[" not in t and "\x01" not in t:
+            assert ids == hf.encode(t, add_special_tokens=False).ids, t
+    # non-ASCII goes to the fallback
+    seen = []
+    out = fw.encode_batch(["hello", "café"], fallback=lambda t: (seen.append(t), [1])[1])
+    assert seen == ["café"] and out[1] == [1] and out[0] == [vocab.index("hello")]
+    # bulk tokenisation inside read_documents: same documents as the line-by-line path
+    src = tmp_path / "corpus.txt"
+    src.write_text("the quick brown fox.\njumps over\n\n\nhello world!\ncafé hello\n\nthe dog\n")
+    a = encode.read_documents(str(src), hf)
+    b = encode.read_documents(str(src), hf, fast=fw, batch_lines=3)
+    assert a == b and len(a) == 3
