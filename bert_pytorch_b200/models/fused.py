@@ -544,9 +544,18 @@ class FusedPretrainer:
             pool = next((e["graph"].pool() for e in self._graphs.values() if "graph" in e), None)
             # replays never overlap: all captures share one memory pool; thread_local: a data-loader thread that pins
             # or allocates memory while we capture must not abort the capture
-            with torch.cuda.graph(graph, pool=pool, capture_error_mode="thread_local"):
-                self._seed_step.add_(1)
-                loss = self._program(*static, grad_scale, seed=eng._seed_base)
+            try:
+                with torch.cuda.graph(graph, pool=pool, capture_error_mode="thread_local"):
+                    self._seed_step.add_(1)
+                    loss = self._program(*static, grad_scale, seed=eng._seed_base)
+            except Exception as e:            # e.g. an allocator / stream condition this build of torch cannot capture
+                import warnings
+                warnings.warn(f"CUDA-graph capture of the micro-step failed ({type(e).__name__}: {e}); "
+                              "continuing with the eager kernel program")
+                K.KERNEL_LAUNCHES = n0
+                self.use_graphs = False
+                torch.cuda.synchronize()      # nothing of the captured program ran: the accumulated gradients are intact
+                return self._program(*args, grad_scale)
             ent.update(graph=graph, static=static, loss=loss, launches=K.KERNEL_LAUNCHES - n0, grad_scale=float(grad_scale))
             K.KERNEL_LAUNCHES = n0            # the capture itself ran nothing
         for dst, src in zip(ent["static"], args):
