@@ -51,8 +51,8 @@ class TrainingSample:
 
 def read_documents(path: str, tokenizer, fast=None, batch_lines: int = 8192) -> List[Document]:
     """Documents = blank-line separated groups of lines; every line becomes a list of token ids.  With ``fast``
-    (:class:`~.tokenization.FastWordPiece`) the ASCII lines are tokenised in bulk by the native C++ WordPiece
-    (identical ids to the ``tokenizers`` package on ASCII text, tests/test_dataset.py), the rest by ``tokenizer``."""
+    (:class:`~.tokenization.FastWordPiece`) the lines covered by its character table (Latin scripts, punctuation) are tokenised in bulk by the native C++
+    WordPiece (identical ids to the ``tokenizers`` package, tests/test_dataset.py), the rest by ``tokenizer``."""
     docs: List[Document] = [[]]
     pending: List[str] = []          # lines of the current batch; None marks a document boundary
 

@@ -176,10 +176,50 @@ class BertTokenizer:
         return self.vocab.get(token)
 
 
+def _char_table(do_lower_case: bool, limit: int = 0x2100):
+    """This module's character rules for code points < ``limit`` in the form the native tokenizer consumes:
+    class per code point (0 normal, 1 whitespace, 2 dropped, 255 not covered) and, for normal characters, the
+    replacement characters (lower-cased + accents stripped when ``do_lower_case``) each flagged punctuation or not."""
+    import numpy as np
+    cls = np.zeros(limit, dtype=np.uint8)
+    off = np.zeros(limit + 1, dtype=np.int32)
+    blob = bytearray()
+    for cp in range(limit):
+        ch = chr(cp)
+        off[cp] = len(blob)
+        if 0xD800 <= cp <= 0xDFFF or _is_cjk(cp):
+            cls[cp] = 255
+        elif cp == 0 or cp == 0xFFFD or _is_control(ch):
+            cls[cp] = 2
+        elif _is_whitespace(ch):
+            cls[cp] = 1
+        else:
+            rep = ch
+            if do_lower_case:
+                rep = "".join(c for c in unicodedata.normalize("NFD", ch.lower()) if unicodedata.category(c) != "Mn")
+            rec = bytearray()
+            for c in rep:
+                b = c.encode("utf-8")
+                # a replacement that is itself whitespace / control / outside the table cannot be expressed
+                if ord(c) >= limit or _is_whitespace(c) or _is_control(c) or len(b) > 3:
+                    rec = None
+                    break
+                rec.append((0x80 if _is_punctuation(c) else 0) | len(b))
+                rec += b
+            if rec is None:
+                cls[cp] = 255
+            else:
+                blob += rec
+    off[limit] = len(blob)
+    return cls, off, np.frombuffer(bytes(blob), dtype=np.uint8)
+
+
 class FastWordPiece:
-    """WordPiece ids for bulk encoding (dataset building): ASCII lines go through the native C++ tokenizer
-    (``ops/csrc/host.cpp``), everything else -- and every line when the helper is not built -- through the pure
-    Python ``BasicTokenizer`` + ``WordpieceTokenizer`` above.  Both paths implement the same rules."""
+    """WordPiece ids for bulk encoding (dataset building): lines whose characters are covered by the character table
+    (Latin scripts, general punctuation, ...: everything below U+2100 that this module's rules can express) go through
+    the native C++ tokenizer (``ops/csrc/host.cpp``), everything else -- and every line when the helper is not
+    built -- through the fallback.  The native path is driven by THIS module's character rules, so it returns exactly
+    what ``BasicTokenizer`` + ``WordpieceTokenizer`` return."""
 
     def __init__(self, vocab_file: str, do_lower_case: bool = True):
         self.py = BertTokenizer(vocab_file, do_lower_case=do_lower_case)
@@ -191,18 +231,17 @@ class FastWordPiece:
             # the native table is positional: only usable when ids are exactly 0..n-1 in file order
             if host is not None and all(self.py.vocab[t] == i for i, t in enumerate(tokens)) and \
                     all("\n" not in t for t in tokens):
-                self.native = native_host.WordPieceEncoder(host, tokens, lowercase=do_lower_case)
+                self.native = native_host.WordPieceEncoder(host, tokens, _char_table(do_lower_case))
         except Exception:
             self.native = None
 
     def encode_batch(self, texts: List[str], fallback=None) -> List[List[int]]:
-        """``fallback(text) -> ids`` handles the lines the native path does not take (non-ASCII); default: the
-        pure-Python tokenizer of this module."""
+        """``fallback(text) -> ids`` handles the lines the native path does not take; default: the pure-Python
+        tokenizer of this module."""
         out: List[Optional[List[int]]] = [None] * len(texts)
-        if self.native is not None:
-            idx = [i for i, t in enumerate(texts) if t.isascii()]
-            if idx:
-                for i, ids in zip(idx, self.native.encode_batch([texts[i] for i in idx])):
+        if self.native is not None and texts:
+            for i, ids in enumerate(self.native.encode_batch(texts)):
+                if ids is not None:
                     out[i] = ids.tolist()
         for i, t in enumerate(texts):
             if out[i] is None:

@@ -4,9 +4,10 @@
 //   * mask_batch_i32  -- dynamic MLM masking of a whole micro-batch (semantics of the reference's
 //     per-sample Python loop, src/dataset.py:277-296, see data/dataset.py::mask_batch), threaded over rows
 //     with a counter-based RNG so results do not depend on the thread count.
-//   * wp_*            -- WordPiece tokenisation of ASCII text (BasicTokenizer + greedy longest-match sub-words,
-//     the semantics of data/tokenization.py, i.e. of the reference's src/tokenization.py:60-229; the reference gets
-//     its speed from the Rust `tokenizers` package), batched and threaded; non-ASCII text stays on the Python path.
+//   * wp_*            -- WordPiece tokenisation (BasicTokenizer + greedy longest-match sub-words, the semantics of
+//     data/tokenization.py, i.e. of the reference's src/tokenization.py:60-229; the reference gets its speed from
+//     the Rust `tokenizers` package), batched and threaded; character classes / case folding come from a table the
+//     Python side builds from its own rules, text outside the table stays on the fallback path.
 // zlib is linked as libz.so.1 with hand-declared prototypes (the image ships no zlib.h).
 #include <algorithm>
 #include <atomic>
@@ -127,33 +128,40 @@ void mask_batch_i32(const int32_t* ids, const int32_t* sp, int32_t* out_ids, int
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------------------
-// WordPiece (ASCII fast path)
+// WordPiece.  Character handling is table driven: the Python side (data/tokenization.py) evaluates ITS OWN
+// character rules (whitespace / control / punctuation classes, lower-casing + accent stripping) for every code point
+// below `ncp` and hands the result over, so both implementations agree by construction; a text containing a code
+// point outside the table is reported back and tokenised by the fallback.
 // ------------------------------------------------------------------------------------------------
 namespace {
+
+enum : uint8_t { CP_NORMAL = 0, CP_SPACE = 1, CP_DROP = 2, CP_UNSUPPORTED = 255 };
 
 struct WordPiece {
   std::unordered_map<std::string, int32_t> vocab;
   int32_t unk = 0;
-  bool lower = true;
   int max_chars = 100;
+  // per code point: class, and for CP_NORMAL the replacement characters as records {flags | nbytes, bytes...}
+  // (flags bit 7: the replacement character is punctuation)
+  std::vector<uint8_t> cls;
+  std::vector<int32_t> map_off;
+  std::vector<uint8_t> map_blob;
 };
 
-inline bool ascii_punct(unsigned char c) {
-  return (c >= 33 && c <= 47) || (c >= 58 && c <= 64) || (c >= 91 && c <= 96) || (c >= 123 && c <= 126);
-}
-
-// greedy longest-match-first split of one word (already lower-cased / punctuation-free or a single punctuation mark)
-void wordpiece_word(const WordPiece& wp, const std::string& word, std::vector<int32_t>& out) {
-  if ((int)word.size() > wp.max_chars) { out.push_back(wp.unk); return; }
+// greedy longest-match-first split of one word given as UTF-8 bytes + the byte offsets of its characters
+void wordpiece_word(const WordPiece& wp, const std::string& word, const std::vector<uint32_t>& bounds,
+                    std::vector<int32_t>& out) {
+  const size_t nchar = bounds.size() - 1;
+  if ((int)nchar > wp.max_chars) { out.push_back(wp.unk); return; }
   const size_t mark = out.size();
   size_t start = 0;
   std::string sub;
-  while (start < word.size()) {
-    size_t end = word.size();
+  while (start < nchar) {
+    size_t end = nchar;
     int32_t id = -1;
     while (start < end) {
       sub.assign(start > 0 ? "##" : "");
-      sub.append(word, start, end - start);
+      sub.append(word, bounds[start], bounds[end] - bounds[start]);
       auto it = wp.vocab.find(sub);
       if (it != wp.vocab.end()) { id = it->second; break; }
       --end;
@@ -164,75 +172,111 @@ void wordpiece_word(const WordPiece& wp, const std::string& word, std::vector<in
   }
 }
 
-void encode_ascii(const WordPiece& wp, const char* s, int64_t n, std::vector<int32_t>& out) {
+// returns false when the text contains something the tables do not cover (caller falls back)
+bool encode_text(const WordPiece& wp, const unsigned char* s, int64_t n, std::vector<int32_t>& out) {
   static const char* kNever[] = {"[UNK]", "[SEP]", "[PAD]", "[CLS]", "[MASK]"};
-  std::string tok, piece;
+  const int64_t ncp = (int64_t)wp.cls.size();
+  std::string raw, piece;
+  std::vector<uint32_t> raw_cp, bounds;
   int64_t i = 0;
   while (i < n) {
-    // clean + whitespace split: control characters vanish, \t \n \r and space separate tokens
-    tok.clear();
-    for (; i < n; ++i) {
-      const unsigned char c = (unsigned char)s[i];
-      if (c == ' ' || c == '\t' || c == '\n' || c == '\r') { if (!tok.empty()) break; else continue; }
-      if (c < 0x20 || c == 0x7F) continue;
-      tok.push_back((char)c);
+    // ---- next whitespace-delimited token: raw bytes + its code points (control characters vanish)
+    raw.clear();
+    raw_cp.clear();
+    while (i < n) {
+      uint32_t cp;
+      int len;
+      const unsigned char c = s[i];
+      if (c < 0x80) { cp = c; len = 1; }
+      else if ((c >> 5) == 6 && i + 1 < n) { cp = ((c & 31u) << 6) | (s[i + 1] & 63u); len = 2; }
+      else if ((c >> 4) == 14 && i + 2 < n) { cp = ((c & 15u) << 12) | ((s[i + 1] & 63u) << 6) | (s[i + 2] & 63u); len = 3; }
+      else return false;                                   // 4-byte sequences / malformed input: not covered
+      if ((int64_t)cp >= ncp) return false;
+      const uint8_t k = wp.cls[cp];
+      if (k == CP_UNSUPPORTED) return false;
+      if (k == CP_SPACE) { i += len; if (!raw.empty()) break; else continue; }
+      if (k == CP_DROP) { i += len; continue; }
+      raw.append(reinterpret_cast<const char*>(s + i), (size_t)len);
+      raw_cp.push_back(cp);
+      i += len;
     }
-    if (tok.empty()) continue;
+    if (raw.empty()) continue;
     bool never = false;
-    for (const char* k : kNever) never |= tok == k;
+    for (const char* k : kNever) never |= raw == k;
     if (never) {
-      auto it = wp.vocab.find(tok);
+      auto it = wp.vocab.find(raw);
       out.push_back(it != wp.vocab.end() ? it->second : wp.unk);
       continue;
     }
-    if (wp.lower)
-      for (auto& c : tok) if (c >= 'A' && c <= 'Z') c = (char)(c - 'A' + 'a');
-    // punctuation marks are their own words
+    // ---- replacement characters (lower-cased, accents stripped) with punctuation marks as their own words
     piece.clear();
-    for (char c : tok) {
-      if (ascii_punct((unsigned char)c)) {
-        if (!piece.empty()) { wordpiece_word(wp, piece, out); piece.clear(); }
-        wordpiece_word(wp, std::string(1, c), out);
-      } else {
-        piece.push_back(c);
+    bounds.assign(1, 0u);
+    auto flush = [&]() {
+      if (!piece.empty()) { wordpiece_word(wp, piece, bounds, out); piece.clear(); bounds.assign(1, 0u); }
+    };
+    for (uint32_t cp : raw_cp) {
+      const uint8_t* r = wp.map_blob.data() + wp.map_off[cp];
+      const uint8_t* e = wp.map_blob.data() + wp.map_off[cp + 1];
+      while (r < e) {
+        const int nb = *r & 0x7F;
+        const bool punct = (*r & 0x80) != 0;
+        ++r;
+        if (punct) {
+          flush();
+          piece.assign(reinterpret_cast<const char*>(r), (size_t)nb);
+          bounds.assign({0u, (uint32_t)nb});
+          flush();
+        } else {
+          piece.append(reinterpret_cast<const char*>(r), (size_t)nb);
+          bounds.push_back((uint32_t)piece.size());
+        }
+        r += nb;
       }
     }
-    if (!piece.empty()) wordpiece_word(wp, piece, out);
+    flush();
   }
+  return true;
 }
 
 }  // namespace
 
 extern "C" {
 
-// vocab: tokens separated by '\n', id = line number
-void* wp_create(const char* blob, int64_t len, int lowercase) {
+// vocab: tokens separated by '\n', id = line number.  cls[ncp], map_off[ncp + 1], map_blob: see WordPiece.
+void* wp_create(const char* blob, int64_t len, const uint8_t* cls, const int32_t* map_off, int64_t ncp,
+                const uint8_t* map_blob, int64_t map_len) {
   auto* wp = new WordPiece();
-  wp->lower = lowercase != 0;
   int32_t id = 0;
   int64_t a = 0;
   for (int64_t i = 0; i <= len; ++i) {
     if (i == len || blob[i] == '\n') {
       int64_t b = i;
-      if (b > a && blob[b - 1] == '\r') --b;
       if (i < len || b > a) wp->vocab.emplace(std::string(blob + a, (size_t)(b - a)), id++);
       a = i + 1;
     }
   }
   auto it = wp->vocab.find("[UNK]");
   wp->unk = it != wp->vocab.end() ? it->second : 0;
+  wp->cls.assign(cls, cls + ncp);
+  wp->map_off.assign(map_off, map_off + ncp + 1);
+  wp->map_blob.assign(map_blob, map_blob + map_len);
   return wp;
 }
 
 void wp_destroy(void* h) { delete static_cast<WordPiece*>(h); }
 
-// texts: buf[offs[i] .. offs[i+1]) (ASCII).  Writes the ids of text i to out[out_offs[i] .. out_offs[i+1]).
-// Returns the total number of ids; if that exceeds `cap` nothing is copied and the caller retries with a larger buffer.
+// texts: buf[offs[i] .. offs[i+1]) (UTF-8).  Writes the ids of text i to out[out_offs[i] .. out_offs[i+1]) and
+// ok[i] = 1, or ok[i] = 0 (no ids) when the text is not covered by the tables.  Returns the total number of ids; if
+// that exceeds `cap` nothing is copied and the caller retries with a larger buffer.
 int64_t wp_encode_batch(void* h, const char* buf, const int64_t* offs, int64_t n, int32_t* out, int64_t cap,
-                        int64_t* out_offs, int threads) {
+                        int64_t* out_offs, uint8_t* ok, int threads) {
   const WordPiece& wp = *static_cast<const WordPiece*>(h);
   std::vector<std::vector<int32_t>> res((size_t)n);
-  parallel_for(n, threads, [&](int64_t i) { encode_ascii(wp, buf + offs[i], offs[i + 1] - offs[i], res[(size_t)i]); });
+  parallel_for(n, threads, [&](int64_t i) {
+    auto& r = res[(size_t)i];
+    ok[i] = encode_text(wp, reinterpret_cast<const unsigned char*>(buf) + offs[i], offs[i + 1] - offs[i], r) ? 1 : 0;
+    if (!ok[i]) r.clear();
+  });
   int64_t total = 0;
   for (int64_t i = 0; i < n; ++i) { out_offs[i] = total; total += (int64_t)res[(size_t)i].size(); }
   out_offs[n] = total;
@@ -243,4 +287,3 @@ int64_t wp_encode_batch(void* h, const char* buf, const int64_t* offs, int64_t n
 }
 
 }  // extern "C"
-

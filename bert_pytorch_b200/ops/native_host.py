@@ -34,12 +34,13 @@ class _Host:
                                        ctypes.c_double, ctypes.c_uint64, ctypes.c_int]
 
         lib.wp_create.restype = ctypes.c_void_p
-        lib.wp_create.argtypes = [ctypes.c_char_p, ctypes.c_int64, ctypes.c_int]
+        lib.wp_create.argtypes = [ctypes.c_char_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                  ctypes.c_void_p, ctypes.c_int64]
         lib.wp_destroy.restype = None
         lib.wp_destroy.argtypes = [ctypes.c_void_p]
         lib.wp_encode_batch.restype = ctypes.c_int64
         lib.wp_encode_batch.argtypes = [ctypes.c_void_p, ctypes.c_char_p, i64p, ctypes.c_int64, ctypes.c_void_p,
-                                        ctypes.c_int64, i64p, ctypes.c_int]
+                                        ctypes.c_int64, i64p, ctypes.c_void_p, ctypes.c_int]
 
     def inflate_rows(self, raw: bytes, offs: np.ndarray, sizes: np.ndarray, rows0: np.ndarray,
                      chunk_rows: int, total_rows: int, row_bytes: int, out: np.ndarray,
@@ -92,13 +93,19 @@ def mask_batch(host: _Host, ids: np.ndarray, sp: np.ndarray, *, seed: int, mask_
 
 
 class WordPieceEncoder:
-    """Native WordPiece for ASCII text (ops/csrc/host.cpp: wp_*): BasicTokenizer + greedy longest-match sub-words,
-    batched and threaded.  ``vocab`` maps token -> id with ids 0..n-1 in file order."""
+    """Native WordPiece (ops/csrc/host.cpp: wp_*): clean-up + whitespace / punctuation splitting + greedy
+    longest-match sub-words, batched and threaded.  ``vocab_tokens``: tokens in id order.  ``char_table``:
+    ``(cls uint8[N], map_off int32[N+1], map_blob uint8[...])`` -- the caller's character rules for code points
+    below N (see ``data/tokenization.py: FastWordPiece``)."""
 
-    def __init__(self, host: _Host, vocab_tokens, lowercase: bool = True):
+    def __init__(self, host: _Host, vocab_tokens, char_table):
         self._host = host
         blob = "\n".join(vocab_tokens).encode("utf-8")
-        self._h = host.lib.wp_create(blob, len(blob), 1 if lowercase else 0)
+        cls, off, mp = (np.ascontiguousarray(char_table[0], dtype=np.uint8),
+                        np.ascontiguousarray(char_table[1], dtype=np.int32),
+                        np.ascontiguousarray(char_table[2], dtype=np.uint8))
+        assert off.size == cls.size + 1
+        self._h = host.lib.wp_create(blob, len(blob), cls.ctypes.data, off.ctypes.data, cls.size, mp.ctypes.data, mp.size)
         if not self._h:
             raise RuntimeError("wp_create failed")
 
@@ -111,22 +118,23 @@ class WordPieceEncoder:
                 pass
 
     def encode_batch(self, texts, threads: int = 0):
-        """``texts``: ASCII strings -> list of int32 arrays of token ids (no special tokens added)."""
+        """-> list with an int32 id array per text, or ``None`` where the text is outside the character table."""
         n = len(texts)
         if n == 0:
             return []
-        enc = [t.encode("ascii") for t in texts]
+        enc = [t.encode("utf-8", errors="surrogatepass") for t in texts]
         offs = np.zeros(n + 1, dtype=np.int64)
         np.cumsum([len(e) for e in enc], out=offs[1:])
         buf = b"".join(enc)
         out_offs = np.empty(n + 1, dtype=np.int64)
-        cap = max(16, len(buf))                      # a token has at least one character: ids <= characters
-        out = np.empty(cap, dtype=np.int32)
+        ok = np.empty(n, dtype=np.uint8)
+        cap = max(16, 2 * len(buf))
         i64p = ctypes.POINTER(ctypes.c_int64)
-        total = self._host.lib.wp_encode_batch(self._h, buf, offs.ctypes.data_as(i64p), n, out.ctypes.data, cap,
-                                               out_offs.ctypes.data_as(i64p), threads)
-        if total > cap:                              # cannot happen with the bound above; kept as a safety net
-            out = np.empty(total, dtype=np.int32)
-            total = self._host.lib.wp_encode_batch(self._h, buf, offs.ctypes.data_as(i64p), n, out.ctypes.data, total,
-                                                   out_offs.ctypes.data_as(i64p), threads)
-        return [out[out_offs[i]:out_offs[i + 1]] for i in range(n)]
+        for _ in range(2):
+            out = np.empty(cap, dtype=np.int32)
+            total = self._host.lib.wp_encode_batch(self._h, buf, offs.ctypes.data_as(i64p), n, out.ctypes.data, cap,
+                                                   out_offs.ctypes.data_as(i64p), ok.ctypes.data, threads)
+            if total <= cap:
+                break
+            cap = int(total)
+        return [out[out_offs[i]:out_offs[i + 1]] if ok[i] else None for i in range(n)]

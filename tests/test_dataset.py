@@ -206,13 +206,20 @@ def test_native_wordpiece_matches_python_and_hf(tmp_path):
         assert ids == fw.py.convert_tokens_to_ids(fw.py.tokenize(t)), t
         if t.strip() and "[" not in t and "\x01" not in t:
             assert ids == hf.encode(t, add_special_tokens=False).ids, t
-    # non-ASCII goes to the fallback
+    # Latin text with accents / typographic punctuation is native too (table driven by the Python rules) ...
+    uni = ["Café hello “world” – naïve…", "ÜBER Straße", "ǅ İ x", "\u0301combining", "tab\tsep\u00a0nbsp"]
+    uni += ["".join(rng.choice(alphabet + "éèüÜßçñœæ“”–…«»") for _ in range(rng.randint(0, 50))) for _ in range(1500)]
+    res = fw.native.encode_batch(uni)
+    assert all(r is not None for r in res)
+    for t, r in zip(uni, res):
+        assert r.tolist() == fw.py.convert_tokens_to_ids(fw.py.tokenize(t)), t
+    # ... while characters outside the table (CJK, astral planes) send the line to the fallback
     seen = []
-    out = fw.encode_batch(["hello", "café"], fallback=lambda t: (seen.append(t), [1])[1])
-    assert seen == ["café"] and out[1] == [1] and out[0] == [vocab.index("hello")]
+    out = fw.encode_batch(["hello", "hello 中文", "smile \U0001F600"], fallback=lambda t: (seen.append(t), [1])[1])
+    assert seen == ["hello 中文", "smile \U0001F600"] and out[1] == [1] and out[0] == [vocab.index("hello")]
     # bulk tokenisation inside read_documents: same documents as the line-by-line path
     src = tmp_path / "corpus.txt"
-    src.write_text("the quick brown fox.\njumps over\n\n\nhello world!\ncafé hello\n\nthe dog\n")
+    src.write_text("the quick brown fox.\njumps over\n\n\nhello world!\ncafé hello\n中文 hello\n\nthe dog\n", encoding="utf-8")
     a = encode.read_documents(str(src), hf)
     b = encode.read_documents(str(src), hf, fast=fw, batch_lines=3)
     assert a == b and len(a) == 3
