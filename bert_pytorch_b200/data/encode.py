@@ -171,6 +171,30 @@ def write_samples_to_hdf5(path: str, samples: Sequence[TrainingSample], max_seq_
         f.create_dataset("next_sentence_labels", data=labels, dtype="i1", compression="gzip")
 
 
+# -- function-style entry points with the reference's names (utils/encode_data.py:38-181) ----------------------
+def convert_to_unicode(text) -> str:
+    from .tokenization import convert_to_unicode as _c
+    return _c(text)
+
+
+def get_documents_from_file(input_file: str, tokenizer) -> List[Document]:
+    """Blank-line separated documents of tokenised sentences (token *ids*, see the module docstring)."""
+    return read_documents(input_file, tokenizer)
+
+
+def create_samples_from_document(document_idx: int, documents: Sequence[Document], max_seq_len: int,
+                                 next_seq_prob: float, short_seq_prob: float,
+                                 rng: Optional[random.Random] = None) -> List[TrainingSample]:
+    return SamplePacker(max_seq_len, next_seq_prob, short_seq_prob, rng).pack_document(documents, document_idx)
+
+
+def create_samples(input_file: str, tokenizer, max_seq_len: int, next_seq_prob: float, short_seq_prob: float,
+                   rng: Optional[random.Random] = None) -> List[TrainingSample]:
+    """All samples of one text file, shuffled."""
+    return SamplePacker(max_seq_len, next_seq_prob, short_seq_prob, rng).pack_file(
+        get_documents_from_file(input_file, tokenizer))
+
+
 def output_dir_name(uppercase: bool, max_seq_len: int, nsp: bool) -> str:
     return f"sequences_{'uppercase' if uppercase else 'lowercase'}_max_seq_len_{max_seq_len}_next_seq_task_{str(nsp).lower()}"
 

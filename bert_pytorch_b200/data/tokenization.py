@@ -40,6 +40,15 @@ def load_vocab(vocab_file: str) -> "collections.OrderedDict[str, int]":
     return vocab
 
 
+def convert_to_unicode(text) -> str:
+    """``str`` passes through, ``bytes`` are decoded as UTF-8 ignoring errors (src/tokenization.py helper)."""
+    if isinstance(text, str):
+        return text
+    if isinstance(text, (bytes, bytearray)):
+        return bytes(text).decode("utf-8", "ignore")
+    raise ValueError(f"Unsupported string type: {type(text)}")
+
+
 def whitespace_tokenize(text: str) -> List[str]:
     text = text.strip()
     return text.split() if text else []

@@ -37,6 +37,9 @@ from torch.utils.data.distributed import DistributedSampler as TorchDistributedS
 from . import models as modeling
 from .config import BertConfig
 from .data import squad as SQ
+from .data.squad import (  # noqa: F401  (public helpers of run_squad.py, implemented in data/squad.py)
+    InputFeatures, SquadExample, convert_examples_to_features, get_answer_text, get_answers, get_final_text,
+    get_valid_prelim_predictions, match_results, read_squad_examples)
 from .data.tokenization import get_bpe_tokenizer, get_wordpiece_tokenizer
 from .models.arena import ParamArena
 from .optim import Adam, BertAdam, GradScaler, GradientClipper, LinearWarmUpScheduler

@@ -1,6 +1,6 @@
 from ..config import BertConfig  # noqa: F401
 from .modeling import (  # noqa: F401
-    ACT2FN, BertLayerNorm, LinearActivation, BertEmbeddings, BertEncoder, BertLayer, BertPooler,
+    ACT2FN, BertLayerNorm, BertNonFusedLayerNorm, LinearActivation, BertEmbeddings, BertEncoder, BertLayer, BertPooler,
     BertModel, BertForPreTraining, BertForMaskedLM, BertForNextSentencePrediction,
     BertForSequenceClassification, BertForMultipleChoice, BertForTokenClassification,
     BertForQuestionAnswering, BertPreTrainedModel, BertPretrainingCriterion,

@@ -113,6 +113,17 @@ class BertLayerNorm(nn.Module):
         return (y * self.weight.float() + self.bias.float()).to(x.dtype)
 
 
+class BertNonFusedLayerNorm(BertLayerNorm):
+    """Name kept for users of the reference's eager LayerNorm (src/modeling.py:282-297).  There is a single
+    LayerNorm module here: the kernels live in the fused engine, this module is the parameter holder and the
+    eager oracle, so the "non fused" variant is the same class (``variance_epsilon`` is the reference's name
+    for ``eps``)."""
+
+    @property
+    def variance_epsilon(self) -> float:
+        return self.eps
+
+
 # ---------------------------------------------------------------------------
 # encoder
 # ---------------------------------------------------------------------------

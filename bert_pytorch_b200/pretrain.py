@@ -36,6 +36,7 @@ from . import models as modeling
 from .config import BertConfig, batch_arithmetic, overlay_json_config
 from .data import BatchedPretrainingLoader, DistributedSampler, ShardedPretrainingDataset
 from .data.tokenization import get_bpe_tokenizer, get_wordpiece_tokenizer
+from .models import BertPretrainingCriterion  # noqa: F401  (public name of run_pretraining.py:96)
 from .models.arena import NO_DECAY_KEYS, ParamArena
 from .optim import GradScaler, Lamb, LinearWarmUpScheduler, PolyWarmUpScheduler
 from .parallel import DataParallel, make_comm, unwrap

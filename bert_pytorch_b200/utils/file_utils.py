@@ -94,3 +94,56 @@ def cached_path(url_or_filename, cache_dir=None) -> str:
     if scheme == "":
         raise FileNotFoundError(f"file {s} not found")
     raise ValueError(f"unable to parse {s} as a URL or as a local path")
+
+
+# -- remaining public helpers of the reference module (src/file_utils.py:127-263) ------------------------------
+def split_s3_path(url: str) -> Tuple[str, str]:
+    """``s3://bucket/key`` -> ``(bucket, key)``."""
+    return _s3_split(url)
+
+
+def s3_request(func):
+    """Decorator turning botocore's 404 ``ClientError`` into ``FileNotFoundError`` (src/file_utils.py:140-157)."""
+    import functools
+
+    @functools.wraps(func)
+    def wrapper(url, *args, **kwargs):
+        try:
+            return func(url, *args, **kwargs)
+        except Exception as e:                      # botocore may be absent: match on the response payload only
+            code = getattr(e, "response", {}).get("Error", {}).get("Code") if hasattr(e, "response") else None
+            if code is not None and int(code) == 404:
+                raise FileNotFoundError(f"file {url} not found") from e
+            raise
+    return wrapper
+
+
+@s3_request
+def s3_etag(url: str) -> Optional[str]:
+    import boto3  # type: ignore
+    bucket, key = split_s3_path(url)
+    return boto3.resource("s3").Object(bucket, key).e_tag
+
+
+@s3_request
+def s3_get(url: str, temp_file) -> None:
+    import boto3  # type: ignore
+    bucket, key = split_s3_path(url)
+    boto3.resource("s3").Bucket(bucket).download_fileobj(key, temp_file)
+
+
+def http_get(url: str, temp_file) -> None:
+    """Stream ``url`` into the open binary file ``temp_file``."""
+    _http_get(url, temp_file)
+
+
+def read_set_from_file(filename: str) -> set:
+    """One item per line -> set of the stripped lines."""
+    with open(filename, "r", encoding="utf-8") as f:
+        return {line.rstrip() for line in f}
+
+
+def get_file_extension(path: str, dot: bool = True, lower: bool = True) -> str:
+    ext = os.path.splitext(path)[1]
+    ext = ext if dot else ext[1:]
+    return ext.lower() if lower else ext
