@@ -63,3 +63,20 @@ def test_small_helpers(tmp_path):
     for s in samples:
         ids, special = s.layout(101, 102)
         assert len(ids) <= 16 and ids[0] == 101 and ids[-1] == 102 and len(special) == 3
+
+
+def test_reference_import_paths():
+    """``src.*`` (the reference's package name) resolves to the same objects as the real package."""
+    import bert_pytorch_b200 as B
+    from bert_pytorch_b200.data.dataset import ShardedPretrainingDataset
+    from src.dataset import DistributedSampler, ShardedPretrainingDataset as S2
+    from src.modeling import BertConfig, BertForPreTraining
+    from src.ner_dataset import NERDataset
+    from src.optimization import BertAdam, warmup_linear
+    from src.schedulers import PolyWarmUpScheduler
+    from src.tokenization import get_wordpiece_tokenizer
+    from src.utils import format_step, is_main_process
+
+    assert S2 is ShardedPretrainingDataset and BertForPreTraining is B.models.BertForPreTraining
+    assert is_main_process() and callable(format_step) and callable(get_wordpiece_tokenizer)
+    assert all(map(callable, (DistributedSampler, BertConfig, NERDataset, BertAdam, warmup_linear, PolyWarmUpScheduler)))
