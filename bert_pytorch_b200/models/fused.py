@@ -133,6 +133,13 @@ class FusedEncoderEngine:
         self.meta = None
         if os.environ.get("B200_FP8", "0") == "1":
             self.enable_fp8()
+        # weight-gradient GEMMs on a second (lower priority) stream: they are off the critical path of the
+        # backward pass, so the bandwidth-bound kernels of the chain (LN / dGELU / attention backward) can share
+        # the machine with them (+2.5 % on the phase-1 step at 1 and 2 GPUs).  B200_WGRAD_STREAM=0 / ``wgrad_side =
+        # False`` keeps everything on one stream.
+        self.wgrad_side = os.environ.get("B200_WGRAD_STREAM", "1") != "0"
+        self._wstream = None
+        self._wkeep: list = []
 
     # -- parameter lookup --------------------------------------------------------------------
     def _find_prefix(self) -> str:
@@ -226,16 +233,55 @@ class FusedEncoderEngine:
         y = K.gemm(qx, qw, scale_a=self.meta.inv_scale(f"{l}.{act_site}"), scale_b=self.meta.inv_scale(f"{l}.{w_site}"), **kw)
         return y, qx
 
+    def _wgrad(self, dy: torch.Tensor, x: torch.Tensor, wgrad: torch.Tensor, **kw) -> None:
+        """wgrad += dy^T @ x, on the side stream when enabled: fork after the producer of ``dy`` (the caller launches
+        the dgrad GEMM afterwards).  The operands stay referenced until the main stream has waited for the side
+        stream again (two layers later, or the join at the end of :meth:`backward`), so the caching allocator cannot
+        hand their memory to a main-stream kernel while the side stream still reads it."""
+        if not (self.wgrad_side and dy.is_cuda):
+            K.wgrad_accumulate(dy, x, wgrad, push=True, **kw)
+            return
+        if self._wstream is None:
+            self._wstream = torch.cuda.Stream(device=dy.device)
+        self._wstream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._wstream):
+            K.wgrad_accumulate(dy, x, wgrad, push=True, **kw)
+        if not self._wkeep or self._wkeep[-1][0] is not None:
+            self._wkeep.append([None, []])
+        self._wkeep[-1][1].append((dy, x))
+
+    def _wgrad_layer_done(self) -> None:
+        """End of one layer's backward: mark the layer's group of side-stream GEMMs with an event and retire the
+        groups that are two layers old (their GEMMs finished long ago: the wait is free, the operands can go)."""
+        if not self._wkeep or self._wkeep[-1][0] is not None:
+            return
+        ev = torch.cuda.Event()
+        ev.record(self._wstream)
+        self._wkeep[-1][0] = ev
+        while len(self._wkeep) > 2:
+            torch.cuda.current_stream().wait_event(self._wkeep.pop(0)[0])
+
+    def _join_wgrads(self) -> None:
+        if self._wkeep:
+            torch.cuda.current_stream().wait_stream(self._wstream)
+            self._wkeep.clear()
+
     def _lin_bwd(self, l: int, g_site: str, act_site: str, w_site: str, dy: torch.Tensor, x_saved: torch.Tensor,
                  w: torch.Tensor, wgrad: torch.Tensor, dyq=None, **kw) -> torch.Tensor:
         """dx = dy @ w (with the epilogue in ``kw``) and wgrad += dy^T @ x."""
         if not self.fp8:
+            if self.wgrad_side:
+                self._wgrad(dy, x_saved, wgrad)
+                return K.gemm(dy, w, layout=K.NN, **kw)
             dx = K.gemm(dy, w, layout=K.NN, **kw)
             K.wgrad_accumulate(dy, x_saved, wgrad, push=True)
             return dx
         m = self.meta
         qdy = dyq if dyq is not None else m.quantize(dy, f"{l}.{g_site}", calibrate=not self._fp8_calibrated)
         sg, sw, sx = m.inv_scale(f"{l}.{g_site}"), m.inv_scale(f"{l}.{w_site}"), m.inv_scale(f"{l}.{act_site}")
+        if self.wgrad_side:
+            self._wgrad(qdy, x_saved, wgrad, scale_a=sg, scale_b=sx, a_e5m2=True)
+            return K.gemm(qdy, self._weight8(l, w_site, w), layout=K.NN, scale_a=sg, scale_b=sw, a_e5m2=True, **kw)
         dx = K.gemm(qdy, self._weight8(l, w_site, w), layout=K.NN, scale_a=sg, scale_b=sw, a_e5m2=True, **kw)
         K.wgrad_accumulate(qdy, x_saved, wgrad, push=True, scale_a=sg, scale_b=sx, a_e5m2=True)
         return dx
@@ -362,6 +408,7 @@ class FusedEncoderEngine:
         K.embedding_bwd_scatter(d_e, sv.ids, sv.seg, self.g("embeddings.word_embeddings.weight"),
                                 self.g("embeddings.position_embeddings.weight"),
                                 self.g("embeddings.token_type_embeddings.weight") if self.has_type else None, sv.S)
+        self._join_wgrads()
         if self.fp8:                       # delayed scaling: next micro-step quantises with this one's amaxes
             self.meta.update()
             self._fp8_calibrated = True
@@ -417,6 +464,7 @@ class FusedEncoderEngine:
         K.colsum_accumulate(d_qkv, self._qkv(l, A.flat_grad, "bias"))
         d = self._lin_bwd(l, "d_qkv", "x", "wqkv", d_qkv, ls.x_op, self._qkv(l, A.flat_shadow, "weight"),
                           self._qkv(l, A.flat_grad, "weight"), dyq=dqkv_q, epi=K.EPI_ADD, res=d_pre1)
+        self._wgrad_layer_done()
         return d
 
     # -- library attention (bring-up / bisecting aid: B200_ATTN=sdpa) ---------------------------------
@@ -494,6 +542,7 @@ class FusedPretrainer:
         self._seed_step: Optional[torch.Tensor] = None
         self.grad_push = False                # set by the runtime around the last micro-step (PeerComm.begin_push)
         self._cls_idx = None                  # row indices of the [CLS] tokens (NSP head)
+        self._cap_stream = None               # high-priority capture stream (wgrad side-stream mode)
         self._cls_S = 0
 
     def _max_pred(self, labels: torch.Tensor) -> int:
@@ -520,7 +569,7 @@ class FusedPretrainer:
         key = (tuple(input_ids.shape), self.model.training, next_sentence_labels is not None,
                segment_ids is not None, tuple(str(t.dtype) for t in args if t is not None),
                bool(getattr(self.model.bert.encoder, "_checkpoint_activations", False)), self.engine.fp8,
-               bool(self.grad_push))
+               bool(self.grad_push), bool(self.engine.wgrad_side))
         ent = self._graphs.setdefault(key, {"calls": 0})
         ent["calls"] += 1
         eng = self.engine
@@ -544,8 +593,13 @@ class FusedPretrainer:
             pool = next((e["graph"].pool() for e in self._graphs.values() if "graph" in e), None)
             # replays never overlap: all captures share one memory pool; thread_local: a data-loader thread that pins
             # or allocates memory while we capture must not abort the capture
+            extra = {}
+            if eng.wgrad_side:                # capture on a high-priority stream: the dgrad chain wins SMs over the wgrads
+                if self._cap_stream is None:
+                    self._cap_stream = torch.cuda.Stream(device=self.arena.device, priority=-1)
+                extra["stream"] = self._cap_stream
             try:
-                with torch.cuda.graph(graph, pool=pool, capture_error_mode="thread_local"):
+                with torch.cuda.graph(graph, pool=pool, capture_error_mode="thread_local", **extra):
                     self._seed_step.add_(1)
                     loss = self._program(*static, grad_scale, seed=eng._seed_base)
             except Exception as e:            # e.g. an allocator / stream condition this build of torch cannot capture

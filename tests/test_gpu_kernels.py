@@ -329,6 +329,34 @@ def test_cuda_graph_replay_matches_eager_program():
     assert len({round(x, 6) for x in losses[3:]}) == 3, losses
 
 
+def test_wgrad_side_stream_matches_single_stream():
+    """Weight-gradient GEMMs forked onto a second stream (eager calls, then the captured graph with the fork/join
+    inside) give the single-stream program's loss and gradients."""
+    from bert_pytorch_b200.models.arena import ParamArena
+    m_s = _tiny_model().cuda()
+    m_e = copy.deepcopy(m_s)
+    a_s, a_e = ParamArena(m_s), ParamArena(m_e)
+    e_s, e_e = m_s.pretrain_engine(), m_e.pretrain_engine()
+    e_s.engine.wgrad_side = True
+    e_e.engine.wgrad_side = False
+    e_e.use_graphs = False
+    base = _batch()
+    for it in range(5):
+        ids = torch.roll(base[0], it, dims=1)
+        labels = torch.roll(base[3], it, dims=1)
+        batch = (ids, base[1], base[2], labels, base[4])
+        a_s.zero_grad(); a_e.zero_grad()
+        ls = e_s.forward_backward(*batch).clone()
+        le = e_e.forward_backward(*batch)
+        torch.cuda.synchronize()
+        assert abs(ls.item() - le.item()) <= 1e-5 * abs(le.item()), (it, ls.item(), le.item())
+        for (n, p), q in zip(m_s.named_parameters(), m_e.parameters()):
+            scale = q.grad.abs().max().item() + 1e-12
+            assert (p.grad - q.grad).abs().max().item() <= 1e-4 * scale, (it, n)
+    assert e_s.engine._wstream is not None and not e_s.engine._wkeep
+    assert any("graph" in ent for ent in e_s._graphs.values())
+
+
 def test_kfac_taps_of_the_fused_engine_match_module_hooks():
     """K-FAC statistics collected from the engine's saved activations (no module hooks fire on the fused path)
     equal the ones the hooks collect on the autograd path; the preconditioned step keeps gradients finite."""
