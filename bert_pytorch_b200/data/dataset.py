@@ -461,3 +461,55 @@ class BatchedPretrainingLoader:
         sd = self.sampler.state_dict()
         sd["index"] = self._consumed
         return sd
+
+
+def _smoke(argv=None) -> int:
+    """Loader smoke loop (reference: src/dataset.py:431-505): run under torchrun (gloo) or stand-alone, walk
+    ``--epochs`` epochs of this rank's share and report sizes + samples/s.
+    ``python -m bert_pytorch_b200.data.dataset --input_dir DIR [--batch_size 8] [--epochs 2]``"""
+    import argparse
+    import time
+    from pathlib import Path
+
+    p = argparse.ArgumentParser(description="Dataloader test")
+    p.add_argument("--input_dir", required=True, help="an .hdf5 shard or a directory of shards")
+    p.add_argument("--max_predictions_per_seq", default=80, type=int)
+    p.add_argument("--masked_lm_prob", type=float, default=0.15)
+    p.add_argument("--batch_size", type=int, default=8)
+    p.add_argument("--epochs", type=int, default=2)
+    p.add_argument("--mask_token_index", type=int, default=103)
+    p.add_argument("--vocab_size", type=int, default=30000)
+    p.add_argument("--local_rank", type=int, default=0)
+    a = p.parse_args(argv)
+
+    import torch.distributed as dist
+    if "RANK" in os.environ and not dist.is_initialized():
+        dist.init_process_group(backend="gloo", init_method="env://")
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    files = [a.input_dir] if os.path.isfile(a.input_dir) else sorted(
+        str(x) for x in Path(a.input_dir).rglob("*.hdf5") if x.is_file())
+    dataset = ShardedPretrainingDataset(files, a.mask_token_index, a.max_predictions_per_seq, a.masked_lm_prob,
+                                        vocab_size=a.vocab_size)
+    sampler = DistributedSampler(dataset, world, rank=rank)
+    loader = BatchedPretrainingLoader(dataset, sampler, a.batch_size, pin_memory=False)
+    if rank == 0:
+        print(f"[rank {rank}] Found {len(files)} input files")
+        print(f"[rank {rank}] Dataset size = {len(dataset)}")
+        print(f"[rank {rank}] Dataloader size = {len(loader)}")
+        print(f"[rank {rank}] Sampler num_samples = {len(sampler)}")
+        print(f"[rank {rank}] Sampler total_size = {sampler.total_size}")
+    for epoch in range(a.epochs):
+        sampler.set_epoch(epoch)
+        t0, n = time.time(), 0
+        for batch in loader:
+            n += batch[0].size(0)
+        print(f"[rank {rank}] epoch {epoch}: {n} samples, {n / max(time.time() - t0, 1e-9):.0f} samples/s", flush=True)
+    loader.close()
+    if dist.is_initialized():
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(_smoke())

@@ -471,6 +471,7 @@ def main(args) -> Tuple[int, float]:
         pbar.close()
     train_s = max_over_ranks(train_ms / 1e3)
     seqs = session_seqs * get_world_size()
+    args.train_time_s = train_s
     return global_step, (seqs / train_s if train_s > 0 else 0.0)
 
 
@@ -494,7 +495,8 @@ def cli(argv=None) -> None:
         logger.info("MODEL CONFIG: " + json.dumps(json.load(f)))
     global_steps, seq_per_sec = main(args)
     runtime = perf_counter() - t0
-    logger.info(f"runtime: {runtime:.2f}s  training_seq_per_sec: {seq_per_sec:.2f}  global_steps: {global_steps}")
+    logger.info(f"runtime: {runtime:.2f}s  train_time: {getattr(args, 'train_time_s', 0.0):.2f}s  "
+                f"training_seq_per_sec: {seq_per_sec:.2f}  global_steps: {global_steps}")
     logger.flush()
     if torch.distributed.is_initialized():
         torch.distributed.destroy_process_group()

@@ -223,3 +223,14 @@ def test_native_wordpiece_matches_python_and_hf(tmp_path):
     a = encode.read_documents(str(src), hf)
     b = encode.read_documents(str(src), hf, fast=fw, batch_lines=3)
     assert a == b and len(a) == 3
+
+
+def test_loader_smoke_main(tmp_path, capsys):
+    """``python -m bert_pytorch_b200.data.dataset`` (the reference's loader smoke loop, src/dataset.py:431-505)."""
+    import numpy as np
+    from bert_pytorch_b200.data import dataset as D, synthetic
+    synthetic.write_shards(str(tmp_path), 2, 24, 32, 1000, True, seed=0)
+    assert D._smoke(["--input_dir", str(tmp_path), "--batch_size", "8", "--epochs", "2", "--max_predictions_per_seq", "8",
+                     "--vocab_size", "1000"]) == 0
+    out = capsys.readouterr().out
+    assert "Dataset size = 48" in out and "epoch 1: 48 samples" in out
