@@ -369,7 +369,8 @@ class BatchedPretrainingLoader:
     kernel and fills a ring of staging buffers ``depth`` deep.
 
     ``state_dict()['index']`` is the number of samples *handed to the training loop*, so a
-    resume neither repeats nor skips samples (fixes reference quirk Q6).
+    resume neither repeats nor skips samples (fixes reference quirk Q6), and the mask RNG is keyed by
+    (seed, rank, epoch, batch position): 5 + 5 steps reproduce 10 steps exactly (tests/test_pretrain_cpu.py).
     """
 
     def __init__(self, dataset: ShardedPretrainingDataset, sampler: DistributedSampler, batch_size: int,
@@ -399,8 +400,7 @@ class BatchedPretrainingLoader:
             yield fi, g - f_lo, g - f_lo + run
             i += run
 
-    def _produce(self, start: int, seed: int) -> None:
-        rng = np.random.default_rng(seed)
+    def _produce(self, start: int, seed: Sequence[int]) -> None:
         n = len(self.sampler)
         i = start
         try:
@@ -408,6 +408,9 @@ class BatchedPretrainingLoader:
                 j = min(i + self.batch_size, n)
                 if self.drop_last and j - i < self.batch_size:
                     break
+                # masks are a function of (seed, rank, epoch, first sample of the batch): a run resumed from a
+                # checkpoint draws exactly the masks the uninterrupted run would have drawn
+                rng = np.random.default_rng([*seed, i])
                 parts = [self.dataset.build_batch(fi, lo, hi, rng) for fi, lo, hi in self._pieces(i, j)]
                 cols = [np.concatenate([p[c] for p in parts], axis=0) if len(parts) > 1 else parts[0][c]
                         for c in range(5)]
@@ -430,7 +433,7 @@ class BatchedPretrainingLoader:
         self._q = queue.Queue(maxsize=self.depth)
         start = self.sampler.index
         self._consumed = start
-        seed = (self.dataset.seed or 0) * 1000003 + self.sampler.rank * 7919 + self.sampler.epoch * 104729 + start
+        seed = (int(self.dataset.seed or 0) & 0x7FFFFFFF, int(self.sampler.rank), int(self.sampler.epoch))
         self._thread = threading.Thread(target=self._produce, args=(start, seed), daemon=True)
         self._thread.start()
         while True:

@@ -59,8 +59,9 @@ def test_phase1_cpu_gloo_10_steps_layout_and_resume(tmp_path):
     pb = torch.load(ck.find_latest(os.path.join(out_b, "pretrain_ckpts"))[1], map_location="cpu", weights_only=False)
     assert pa["sampler"]["index"] == pb["sampler"]["index"]
     worst = max((pa["model"][k].float() - pb["model"][k].float()).abs().max().item() for k in pa["model"])
-    # identical data order; masks are re-drawn after the resume point so allow a small drift
-    assert worst < 0.15, worst
+    # identical data order and identical masks (the mask RNG is keyed by the batch position): only the optimizer
+    # state round trip through the checkpoint separates the two runs
+    assert worst < 1e-5, worst
 
 
 def test_phase2_style_step_surgery(tmp_path):
