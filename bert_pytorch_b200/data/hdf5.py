@@ -19,7 +19,7 @@ readable by stock HDF5 tools.
 The API mirrors the h5py subset the reference touches: ``File(path, 'r'|'w')`` as a
 context manager, ``f.keys()``, ``f[name][:]``, ``f[name].shape/.dtype/len()``,
 ``f.create_dataset(name, data=, dtype=, compression='gzip')``.
-The bulk chunk decode runs in the native helper ``ops/csrc/h5chunks.cpp`` when built
+The bulk chunk decode runs in the native helper ``ops/csrc/host.cpp`` when built
 (multi-threaded inflate + scatter); the pure-Python path below is the fallback and
 the oracle for its tests.
 """
