@@ -108,3 +108,63 @@ def test_kfac_flag_and_multi_rank_gloo(tmp_path):
     assert ck.find_latest(os.path.join(out2, "pretrain_ckpts"))[0] == 2
     rows = list(csv.DictReader(open(os.path.join(out2, "pretraining_phase1_log_metrics.csv"))))
     assert [int(r["step"]) for r in rows] == [1, 2]
+
+
+def test_offline_pipeline_feeds_pretraining(tmp_path):
+    """scripts/create_datasets.sh in miniature, through the CLIs: wikiextractor-style + books text -> utils/format.py
+    -> utils/build_vocab.py -> utils/encode_data.py (NSP shards) -> run_pretraining.py on the result."""
+    import random
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rnd = random.Random(0)
+    words = ("the quick brown fox jumps over lazy dog while rain keeps falling on quiet city streets and people walk "
+             "home with umbrellas under grey clouds thinking about dinner plans music science history").split()
+
+    def sent():
+        return " ".join(rnd.choice(words) for _ in range(rnd.randint(5, 14))).capitalize() + "."
+
+    wiki = tmp_path / "dl" / "wikicorpus" / "AA"; wiki.mkdir(parents=True)
+    with open(wiki / "wiki_00", "w") as f:
+        for d in range(24):
+            f.write(f'<doc id="{d}" url="u" title="T{d}">\nT{d}\n\n')
+            for _ in range(3):
+                f.write(" ".join(sent() for _ in range(5)) + "\n")
+            f.write("</doc>\n")
+    books = tmp_path / "dl" / "books"; books.mkdir(parents=True)
+    for b in range(4):                  # two books per shard: NSP needs >= 2 documents in a file
+        with open(books / f"book{b}.txt", "w", encoding="ISO-8859-1") as f:
+            for _ in range(16):
+                f.write(" ".join(sent() for _ in range(4)) + "\n")
+
+    def run(*cmd):
+        r = subprocess.run([sys.executable, *cmd], cwd=root, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        return r.stdout
+
+    fmt, vocab, enc = str(tmp_path / "fmt"), str(tmp_path / "vocab" / "wp.txt"), str(tmp_path / "enc")
+    run("utils/format.py", "--dataset", "wikicorpus", "--input_dir", str(wiki.parent), "--output_dir", fmt + "/wiki",
+        "--processes", "1", "--shards", "1")
+    run("utils/format.py", "--dataset", "bookscorpus", "--input_dir", str(books), "--output_dir", fmt + "/books",
+        "--processes", "1", "--shards", "2")
+    run("utils/build_vocab.py", "-i", fmt, "-o", vocab, "-s", "200")
+    tokens = open(vocab).read().splitlines()
+    assert tokens[0] == "[PAD]" and {"[MASK]", "[SEP]", "[CLS]", "[UNK]"} <= set(tokens[:5])
+    out = run("utils/encode_data.py", "--input_dir", fmt, "--output_dir", enc, "--vocab_file", vocab, "--max_seq_len", "64",
+              "--next_seq_prob", "0.5", "--short_seq_prob", "0.1", "--processes", "1", "--seed", "1")
+    shard_dir = os.path.join(enc, "sequences_lowercase_max_seq_len_64_next_seq_task_true")
+    assert len([f for f in os.listdir(shard_dir) if f.endswith(".hdf5")]) == 3, out
+
+    model_json = str(tmp_path / "model.json")
+    json.dump({"attention_probs_dropout_prob": 0.1, "hidden_act": "gelu", "hidden_dropout_prob": 0.1, "hidden_size": 32,
+               "initializer_range": 0.02, "intermediate_size": 64, "max_position_embeddings": 64,
+               "num_attention_heads": 2, "num_hidden_layers": 2, "type_vocab_size": 2, "vocab_size": len(tokens),
+               "next_sentence": True, "vocab_file": vocab, "tokenizer": "wordpiece", "lowercase": True},
+              open(model_json, "w"))
+    train_json = str(tmp_path / "train.json")
+    json.dump({"model_config_file": model_json, "max_predictions_per_seq": 10, "masked_token_fraction": 0.15,
+               "learning_rate": 1e-3, "global_batch_size": 16, "local_batch_size": 8, "max_steps": 3,
+               "disable_progress_bar": True}, open(train_json, "w"))
+    outdir = str(tmp_path / "out")
+    pretrain.cli(["--config_file", train_json, "--input_dir", shard_dir, "--output_dir", outdir, "--device", "cpu"])
+    assert ck.find_latest(os.path.join(outdir, "pretrain_ckpts"))[0] == 3
