@@ -354,6 +354,11 @@ def attention_bwd(qkv, seqlens, ctx, dctx, lse, heads: int, *, p_drop=0.0, seed=
     return dqkv if fp8 is None else (dqkv, q)
 
 
+def set_attention_options(bwd_pipe: Optional[bool] = None) -> None:
+    """``bwd_pipe``: force the software-pipelined S > 128 backward kernel on / off (None: follow B200_ATTN_BWD_PIPE)."""
+    extension().set_attention_options(-1 if bwd_pipe is None else int(bool(bwd_pipe)))
+
+
 # ---------------------------------------------------------------------------
 # multi-tensor ops over arbitrary tensor lists
 # ---------------------------------------------------------------------------

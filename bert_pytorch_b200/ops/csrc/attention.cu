@@ -751,6 +751,279 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------
+// backward, S > 128, software-pipelined variant (opt-in: B200_ATTN_BWD_PIPE=1 / set_attention_options).
+// The kernel above runs its per-query-block stages strictly one after the other (S/dP MMAs -> softmax-gradient
+// math -> dV/dK/dQ MMAs -> dQ reduction): ~6 us per block of which < 1 us is tensor work.  Here
+//   * the math warps release S/dP as soon as they have pulled them out of TMEM (`sdp_free`), so the S/dP MMAs of
+//     block i+1 run while block i's math is still in registers;
+//   * block i's dQ is read back one iteration later (after block i+1's S/dP were loaded), so the dV/dK/dQ MMAs of
+//     block i overlap the math of block i+1;
+//   * Q/dO live in a 3-stage ring (blocks i, i+1 in use, i+2 landing); the reload of a stage is issued one iteration
+//     after its last reader, when the wait is free.
+// TMEM / P~ / dS buffers are unchanged (the hazards are covered by dq_ready(i-1) -> stores of block i, and
+// ds_ready(i) -> dQ MMA of block i).  192 KB shared memory, one CTA per SM.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ATT_BWD16_THREADS, 1)
+attn_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
+                     const AttnArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;                      // 16 KB
+  uint8_t* sV = smem + 16384;              // 16 KB
+  uint8_t* sQ = smem + 16384 * 2;          // 3 x 16 KB
+  uint8_t* sDO = smem + 16384 * 5;         // 3 x 16 KB
+  uint8_t* sPd = smem + 16384 * 8;         // 32 KB
+  uint8_t* sDS = smem + 16384 * 10;        // 32 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 16384 * 12);
+  uint64_t* kv_full = bars;
+  uint64_t* qdo_full = bars + 1;           // 3
+  uint64_t* qdo_empty = bars + 4;          // 3
+  uint64_t* sdp_ready = bars + 7;
+  uint64_t* sdp_free = bars + 8;
+  uint64_t* ds_ready = bars + 9;
+  uint64_t* dq_ready = bars + 10;
+  uint64_t* fin = bars + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kb = blockIdx.x, bh = blockIdx.y;
+  const int b = bh / p.h, head = bh % p.h;
+  const int seqlen = min(p.seqlens[b], p.S);
+  const int nqb = (p.S + TILE - 1) / TILE;
+  const int row0 = b * p.S;
+  const bool dead = kb * TILE >= seqlen;     // every key of this block is padding: dK = dV = 0
+
+  if (dead) {
+    if (warp < 4) {
+      const int key = kb * TILE + warp * 32 + lane;
+      if (key < p.S) {
+        __nv_bfloat16* dk = p.dqkv + (size_t)(row0 + key) * 3 * p.H + p.H + head * HD;
+        __nv_bfloat16* dv = dk + p.H;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          *reinterpret_cast<uint4*>(dk + g * 8) = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(dv + g * 8) = make_uint4(0, 0, 0, 0);
+        }
+        if (p.f8.q) {
+          unsigned char* qk = p.f8.q + (size_t)(row0 + key) * 3 * p.H + p.H + head * HD;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            *reinterpret_cast<uint4*>(qk + g * 16) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(qk + p.H + g * 16) = make_uint4(0, 0, 0, 0);
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  if (threadIdx.x == 512) {
+    tma_prefetch_desc(&tmap_qkv);
+    tma_prefetch_desc(&tmap_do);
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < 3; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
+    mbar_init(sdp_ready, 1);
+    mbar_init(sdp_free, 512);
+    mbar_init(ds_ready, 512);
+    mbar_init(dq_ready, 1);
+    mbar_init(fin, 1);
+    fence_barrier_init();
+  }
+  if (warp == 16) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const unsigned long long seed = p.thresh16 != 0 ? p.seed.value() : 0ull;
+  const uint32_t tS = tmem, tDP = tmem + 128, tDV = tmem + 256, tDK = tmem + 320, tDQ = tmem + 384;
+
+  if (warp == 16) {
+    if (lane == 0) {
+      const int cq = head * HD, ck = p.H + head * HD, cv = 2 * p.H + head * HD;
+      mbar_arrive_expect_tx(kv_full, 32768);
+      tma_load_2d(sK, &tmap_qkv, kv_full, ck, row0 + kb * TILE);
+      tma_load_2d(sV, &tmap_qkv, kv_full, cv, row0 + kb * TILE);
+      for (int i = 0; i < min(3, nqb); ++i) {
+        mbar_arrive_expect_tx(&qdo_full[i], 32768);
+        tma_load_2d(sQ + i * 16384, &tmap_qkv, &qdo_full[i], cq, row0 + i * TILE);
+        tma_load_2d(sDO + i * 16384, &tmap_do, &qdo_full[i], head * HD, row0 + i * TILE);
+      }
+      constexpr uint32_t id_kk = umma_idesc_bf16(128, 128, false, false);  // [q x keys], both K-major
+      constexpr uint32_t id_tt = umma_idesc_bf16(128, 64, true, true);     // [keys x d] = X^T Y, both MN-major
+      constexpr uint32_t id_kt = umma_idesc_bf16(128, 64, false, true);    // [q x d] = dS K, A K-major, B MN-major
+      const uint32_t ak = smem_u32(sK), av = smem_u32(sV), apd = smem_u32(sPd), ads = smem_u32(sDS);
+      // S = Q K^T and dPd = dO V^T of query block j (its Q / dO tiles sit in ring slot j % 3)
+      auto issue_sdp = [&](int j) {
+        const int sj = j % 3;
+        mbar_wait(&qdo_full[sj], (j / 3) & 1);
+        tc_fence_after();
+        const uint32_t aq = smem_u32(sQ + sj * 16384), ado = smem_u32(sDO + sj * 16384);
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk)
+          umma_bf16_ss(tS, umma_smem_desc_sw128(aq + kk * 32, 16, 1024), umma_smem_desc_sw128(ak + kk * 32, 16, 1024),
+                       id_kk, kk > 0);
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk)
+          umma_bf16_ss(tDP, umma_smem_desc_sw128(ado + kk * 32, 16, 1024), umma_smem_desc_sw128(av + kk * 32, 16, 1024),
+                       id_kk, kk > 0);
+        umma_commit(sdp_ready);
+      };
+      mbar_wait(kv_full, 0);
+      issue_sdp(0);
+      for (int i = 0; i < nqb; ++i) {
+        const int st = i % 3;
+        if (i + 1 < nqb) {                     // S/dP of the next block as soon as this block's left TMEM
+          mbar_wait(sdp_free, i & 1);
+          tc_fence_after();
+          issue_sdp(i + 1);
+        }
+        mbar_wait(ds_ready, i & 1);
+        tc_fence_after();
+        const uint32_t aq = smem_u32(sQ + st * 16384), ado = smem_u32(sDO + st * 16384);
+#pragma unroll
+        for (int kk = 0; kk < TILE / 16; ++kk) {   // reduction over the 128 query rows of this block
+          const uint64_t a_pd = umma_smem_desc_sw128(apd + kk * 2048, 16384, 1024);
+          const uint64_t a_ds = umma_smem_desc_sw128(ads + kk * 2048, 16384, 1024);
+          const uint64_t b_do = umma_smem_desc_sw128(ado + kk * 2048, 8192, 1024);
+          const uint64_t b_q = umma_smem_desc_sw128(aq + kk * 2048, 8192, 1024);
+          umma_bf16_ss(tDV, a_pd, b_do, id_tt, (i > 0 || kk > 0));   // dV += Pd^T dO
+          umma_bf16_ss(tDK, a_ds, b_q, id_tt, (i > 0 || kk > 0));    // dK += dS^T Q
+        }
+#pragma unroll
+        for (int kk = 0; kk < TILE / 16; ++kk) {   // dQ = dS K   (reduction over the 128 keys)
+          const uint64_t a_ds = umma_smem_desc_sw128(ads + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024);
+          const uint64_t b_k = umma_smem_desc_sw128(ak + kk * 2048, 8192, 1024);
+          umma_bf16_ss(tDQ, a_ds, b_k, id_kt, kk > 0);
+        }
+        umma_commit(dq_ready);
+        umma_commit(&qdo_empty[st]);
+        if (i >= 1 && i + 2 < nqb) {           // slot of block i-1 (its MMAs finished before ds_ready(i) could fire)
+          const int sp = (i - 1) % 3;
+          mbar_wait(&qdo_empty[sp], ((i - 1) / 3) & 1);
+          mbar_arrive_expect_tx(&qdo_full[sp], 32768);
+          tma_load_2d(sQ + sp * 16384, &tmap_qkv, &qdo_full[sp], cq, row0 + (i + 2) * TILE);
+          tma_load_2d(sDO + sp * 16384, &tmap_do, &qdo_full[sp], head * HD, row0 + (i + 2) * TILE);
+        }
+      }
+      umma_commit(fin);
+    }
+  } else {
+    const int r = (warp & 3) * 32 + lane;        // query row inside the tile == TMEM lane
+    const int ch = warp >> 2;                    // which 32-key column quarter this thread handles
+    const uint32_t lane_base = uint32_t((warp & 3) * 32) << 16;
+    const float c_scale = p.scale * LOG2E;
+    const float qscale8 = p.f8.q ? p.f8.meta[1] : 0.f;
+    float amax8 = 0.f;
+    // dQ rows of query block j: read back from TMEM, reduce into the fp32 accumulator (several key blocks)
+    auto drain_dq = [&](int j) {
+      mbar_wait(dq_ready, j & 1);
+      tc_fence_after();
+      uint32_t v[16];                            // each thread owns 16 of the 64 dQ columns of its row
+      tmem_ld_32x16(tDQ + lane_base + ch * 16, v);
+      tmem_ld_wait();
+      const int q = j * TILE + r;
+      if (q < p.S) {
+        float* dq = p.dq_acc + (size_t)(row0 + q) * p.H + head * HD + ch * 16;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dq + g * 4),
+                       "f"(__uint_as_float(v[g * 4])), "f"(__uint_as_float(v[g * 4 + 1])),
+                       "f"(__uint_as_float(v[g * 4 + 2])), "f"(__uint_as_float(v[g * 4 + 3]))
+                       : "memory");
+      }
+      tc_fence_before();                         // dQ reads done before ds_ready lets the next dQ MMA overwrite it
+    };
+    for (int i = 0; i < nqb; ++i) {
+      const int q = i * TILE + r;
+      const bool q_ok = q < p.S;
+      const float lse2 = q_ok ? p.lse[(size_t)bh * p.S + q] * LOG2E : 0.f;
+      const float dlt = q_ok ? p.delta[(size_t)bh * p.S + q] : 0.f;
+      const uint64_t erow = ((uint64_t)bh * p.S + (uint64_t)q) * (uint64_t)p.S;
+      uint4 ppd[4], pds[4];                      // this thread's 32 P~ / dS values, packed bf16
+      mbar_wait(sdp_ready, i & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int sc = 0; sc < 2; ++sc) {           // two 16-column sub-chunks
+        const int c16 = ch * 2 + sc;
+        uint32_t sv[16], dv[16];
+        tmem_ld_32x16(tS + lane_base + c16 * 16, sv);
+        tmem_ld_32x16(tDP + lane_base + c16 * 16, dv);
+        tmem_ld_wait();
+        if (sc == 1) {                           // S / dP of this block are in registers: the next block's may land
+          tc_fence_before();
+          mbar_arrive(sdp_free);
+        }
+        const int k0 = kb * TILE + c16 * 16;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          Keep8 keep = Keep8::all();
+          if (p.thresh16 != 0)
+            keep = dropout_keep8(seed, p.stream, (erow + (uint64_t)(k0 + g * 8)) >> 3, p.thresh16);
+          float pd[8], ds[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const int key = k0 + g * 8 + t;
+            const bool ok = q_ok && key < seqlen;
+            const float pr = ok ? ex2_approx(fmaf(__uint_as_float(sv[g * 8 + t]), c_scale, -lse2)) : 0.f;
+            const bool kp = keep[t];
+            const float dp = kp ? __uint_as_float(dv[g * 8 + t]) * p.inv_keep : 0.f;
+            pd[t] = kp ? pr * p.inv_keep : 0.f;
+            ds[t] = pr * (dp - dlt) * p.scale;
+          }
+          ppd[sc * 2 + g] = make_uint4(pack_bf16(pd[0], pd[1]), pack_bf16(pd[2], pd[3]), pack_bf16(pd[4], pd[5]),
+                                       pack_bf16(pd[6], pd[7]));
+          pds[sc * 2 + g] = make_uint4(pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]), pack_bf16(ds[4], ds[5]),
+                                       pack_bf16(ds[6], ds[7]));
+        }
+      }
+      // block i-1: its dV/dK/dQ MMAs ran while the values above were computed; once dq_ready(i-1) has fired they no
+      // longer read the P~ / dS buffers either
+      if (i > 0) drain_dq(i - 1);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t off = p_chunk_offset(r, (ch * 2 + (c >> 1)) * 2 + (c & 1));
+        *reinterpret_cast<uint4*>(sPd + off) = ppd[c];
+        *reinterpret_cast<uint4*>(sDS + off) = pds[c];
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(ds_ready);
+    }
+    drain_dq(nqb - 1);
+    // dK / dV of this key block: column quarters 0,1 write the two halves of dK, quarters 2,3 those of dV
+    mbar_wait(fin, 0);
+    tc_fence_after();
+    const int key = kb * TILE + r;
+    {
+      const int w = ch >> 1, c = ch & 1;
+      const uint32_t src = w == 0 ? tDK : tDV;
+      uint32_t v[32];
+      tmem_ld_32x32(src + lane_base + c * 32, v);
+      tmem_ld_wait();
+      if (key < p.S) {
+        __nv_bfloat16* dst = p.dqkv + (size_t)(row0 + key) * 3 * p.H + (w + 1) * p.H + head * HD + c * 32;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          *reinterpret_cast<uint4*>(dst + g * 8) = make_uint4(
+              pack_bf16(__uint_as_float(v[g * 8]), __uint_as_float(v[g * 8 + 1])),
+              pack_bf16(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3])),
+              pack_bf16(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5])),
+              pack_bf16(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7])));
+        if (p.f8.q)
+          emit_fp8_row<4>(p.f8, (size_t)(row0 + key) * 3 * p.H + (w + 1) * p.H + head * HD + c * 32, v, 1.f, qscale8, amax8);
+      }
+    }
+    if (p.f8.q) fp8_amax_commit(p.f8, amax8);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 16) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // backward, S <= 128 (phase 1): ONE key block and ONE query block per (batch, head), so nothing accumulates across
 // iterations and the kernel can be made small enough for TWO CTAs per SM (the generic kernel is latency bound at
 // one CTA per SM: ~11 us per head, almost all of it dependent waits):
@@ -1034,6 +1307,15 @@ void attention_fwd(const void* qkv, const int* seqlens, void* ctx, float* lse, i
   }
 }
 
+// -1: follow B200_ATTN_BWD_PIPE (default off until the variant has been measured), 0 / 1: forced by the caller
+static int g_bwd_pipe = -1;
+void attention_set_options(int bwd_pipe) { g_bwd_pipe = bwd_pipe; }
+static bool attn_bwd_pipe_enabled() {
+  if (g_bwd_pipe >= 0) return g_bwd_pipe != 0;
+  static const bool env_on = []() { const char* e = getenv("B200_ATTN_BWD_PIPE"); return e && e[0] == '1'; }();
+  return env_on;
+}
+
 void attention_bwd(const void* qkv, const int* seqlens, const void* ctx, const void* dctx, const float* lse,
                    void* dqkv, float* delta_ws, float* dq_acc, int B, int S, int h, int d, float scale,
                    Seed seed, unsigned int stream, float p_drop, Fp8Out f8, cudaStream_t st) {
@@ -1070,7 +1352,17 @@ void attention_bwd(const void* qkv, const int* seqlens, const void* ctx, const v
     attn_bwd_single_kernel<<<grid, ATT_BWD_THREADS, SMEM1, st>>>(tq, td, a);
     return;
   }
-  attn_bwd_kernel<<<grid, ATT_BWD16_THREADS, SMEM, st>>>(tq, td, a);
+  if (nkb > 1 && attn_bwd_pipe_enabled()) {      // software-pipelined variant (opt-in)
+    constexpr int SMEMP = 16384 * 12 + 1024 + 128;
+    static bool oncep = false;
+    if (!oncep) {
+      B200_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEMP));
+      oncep = true;
+    }
+    attn_bwd_pipe_kernel<<<grid, ATT_BWD16_THREADS, SMEMP, st>>>(tq, td, a);
+  } else {
+    attn_bwd_kernel<<<grid, ATT_BWD16_THREADS, SMEM, st>>>(tq, td, a);
+  }
   if (nkb > 1) {
     const long long work = (long long)B * S * (H / 8);
     int g = (int)((work + 255) / 256);

@@ -32,5 +32,11 @@ for B, S in ((96, 128), (16, 512)):
     tf = timeit(lambda: K.attention_fwd(qkv, lens, h, p_drop=0.1, seed=1, stream=1))
     tb = timeit(lambda: K.attention_bwd(qkv, lens, ctx, d, lse, h, p_drop=0.1, seed=1, stream=1))
     flops = 4.0 * B * h * S * S * 64
-    print(json.dumps({"B": B, "S": S, "fwd_ms": round(tf, 4), "bwd_ms": round(tb, 4),
-                      "fwd_tflops": round(flops / tf / 1e9, 1), "bwd_tflops": round(2.5 * flops / tb / 1e9, 1)}), flush=True)
+    row = {"B": B, "S": S, "fwd_ms": round(tf, 4), "bwd_ms": round(tb, 4),
+           "fwd_tflops": round(flops / tf / 1e9, 1), "bwd_tflops": round(2.5 * flops / tb / 1e9, 1)}
+    if S > 128 and "--pipe" in sys.argv:       # the software-pipelined streaming backward (opt-in kernel)
+        K.set_attention_options(bwd_pipe=True)
+        tp = timeit(lambda: K.attention_bwd(qkv, lens, ctx, d, lse, h, p_drop=0.1, seed=1, stream=1))
+        K.set_attention_options(None)
+        row.update(bwd_pipe_ms=round(tp, 4), bwd_pipe_tflops=round(2.5 * flops / tp / 1e9, 1))
+    print(json.dumps(row), flush=True)
