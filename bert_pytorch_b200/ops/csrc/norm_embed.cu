@@ -303,8 +303,10 @@ ln_bwd2_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __rest
 }
 
 // dst[k][col] += sum over blocks of partial[block][k][col]   (k = 0..2, any dst may be null)
-// grid (ceil(H/32), 3), 256 threads: warp w sums rows w, w+8, ... of a 32-column strip (coalesced 128 B
-// per row), then the 8 warps are combined through shared memory.
+// grid (ceil(H/32), 3, Z), 256 threads: warp w sums rows w, w+8, ... of a 32-column strip (coalesced 128 B
+// per row), then the 8 warps are combined through shared memory.  Z > 1 (B200_LN_FINALIZE_SPLIT, opt-in) cuts the
+// partial rows into Z slices that finish with an atomic add: the kernel is a chain of ~55 dependent loads per warp
+// at Z = 1 (8 us for 444 partial rows), i.e. latency bound.
 __global__ void __launch_bounds__(256)
 colsum_finalize_kernel(const float* __restrict__ partial, int nblocks, int H, float* dgamma, float* dbeta,
                        float* dbias) {
@@ -315,8 +317,10 @@ colsum_finalize_kernel(const float* __restrict__ partial, int nblocks, int H, fl
   const int col = blockIdx.x * 32 + lane;
   float s = 0.f;
   if (col < H) {
+    const int per = (nblocks + gridDim.z - 1) / gridDim.z;
+    const int b_lo = blockIdx.z * per, b_hi = min(nblocks, b_lo + per);
 #pragma unroll 4
-    for (int b = warp; b < nblocks; b += 8) s += partial[((size_t)b * 3 + qn) * H + col];
+    for (int b = b_lo + warp; b < b_hi; b += 8) s += partial[((size_t)b * 3 + qn) * H + col];
   }
   __shared__ float sm[8][32];
   sm[warp][lane] = s;
@@ -325,7 +329,8 @@ colsum_finalize_kernel(const float* __restrict__ partial, int nblocks, int H, fl
     float t = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) t += sm[w][lane];
-    dst[col] += t;
+    if (gridDim.z == 1) dst[col] += t;
+    else atomicAdd(dst + col, t);
   }
 }
 
@@ -660,7 +665,12 @@ void layer_norm_bwd(const void* dy, const void* x, const float* mean, const floa
   DISPATCH_WPR(H, (ln_bwd2_kernel<WPR><<<grid, 2 * WPR * 32, 0, st>>>(
       (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, gamma, (__nv_bfloat16*)dx, (__nv_bfloat16*)dxd,
       workspace, M, H, seed, drop_stream, in_stream, th, sc, f8)));
-  dim3 g2((H + 31) / 32, 3);
+  static const int split = []() {
+    const char* e = getenv("B200_LN_FINALIZE_SPLIT");
+    const int z = e ? atoi(e) : 1;
+    return z < 1 ? 1 : (z > 32 ? 32 : z);
+  }();
+  dim3 g2((H + 31) / 32, 3, split);
   colsum_finalize_kernel<<<g2, 256, 0, st>>>(workspace, grid, H, dgamma, dbeta, dxd ? dbias : nullptr);
 }
 
