@@ -255,6 +255,41 @@ WEIGHT_URLS = {
     "bert_large_cased": "https://storage.googleapis.com/bert_models/2018_10_18/cased_L-24_H-1024_A-16.zip",
 }
 GLUE_TASKS = {"sst-2": "SST", "mrpc": "MRPC"}
+# SHA-256 of the files inside Google's 2018_10_18 archives, in the order (bert_config.json, ckpt.data, ckpt.index,
+# ckpt.meta, vocab.txt): integrity check of the download and a tripwire for upstream changes
+# (reference: utils/download.py:136-175)
+_WEIGHT_FILES = ("bert_config.json", "bert_model.ckpt.data-00000-of-00001", "bert_model.ckpt.index",
+                 "bert_model.ckpt.meta", "vocab.txt")
+_UNCASED_VOCAB = "07eced375cec144d27c900241f3e339478dec958f92fddbc551f295c992038a3"
+_CASED_VOCAB = "eeaa9875b23b04b4c54ef759d03db9d1ba1554838f8fb26c5d96fa551df93d02"
+WEIGHT_SHA256 = {
+    "bert_base_uncased": ("7b4e5f53efbd058c67cda0aacfafb340113ea1b5797d9ce6ee411704ba21fcbc",
+                          "58580dc5e0bf0ae0d2efd51d0e8272b2f808857f0a43a88aaf7549da6d7a8a84",
+                          "04c1323086e2f1c5b7c0759d8d3e484afbb0ab45f51793daab9f647113a0117b",
+                          "dd5682170a10c3ea0280c2e9b9a45fee894eb62da649bbdea37b38b0ded5f60e", _UNCASED_VOCAB),
+    "bert_large_uncased": ("bfa42236d269e2aeb3a6d30412a33d15dbe8ea597e2b01dc9518c63cc6efafcb",
+                           "bc6b3363e3be458c99ecf64b7f472d2b7c67534fd8f564c0556a678f90f4eea1",
+                           "68b52f2205ffc64dc627d1120cf399c1ef1cbc35ea5021d1afc889ffe2ce2093",
+                           "6fcce8ff7628f229a885a593625e3d5ff9687542d5ef128d9beb1b0c05edc4a1", _UNCASED_VOCAB),
+    "bert_base_cased": ("f11dfb757bea16339a33e1bf327b0aade6e57fd9c29dc6b84f7ddb20682f48bc",
+                        "734d5a1b68bf98d4e9cb6b6692725d00842a1937af73902e51776905d8f760ea",
+                        "517d6ef5c41fc2ca1f595276d6fccf5521810d57f5a74e32616151557790f7b1",
+                        "5f8a9771ff25dadd61582abb4e3a748215a10a6b55947cbb66d0f0ba1694be98", _CASED_VOCAB),
+    "bert_large_cased": ("7adb2125c8225da495656c982fd1c5f64ba8f20ad020838571a3f8a954c2df57",
+                         "6ff33640f40d472f7a16af0c17b1179ca9dcc0373155fb05335b6a4dd1657ef0",
+                         "ef42a53f577fbe07381f4161b13c7cab4f4fc3b167cec6a9ae382c53d18049cf",
+                         "d2ddff3ed33b80091eac95171e94149736ea74eb645e575d942ec4a5e01a40a1", _CASED_VOCAB),
+}
+
+
+def verify_weights(name: str, model_dir: str) -> List[str]:
+    """Names of the files under ``model_dir`` whose SHA-256 differs from the recorded one (missing files count)."""
+    bad = []
+    for fname, want in zip(_WEIGHT_FILES, WEIGHT_SHA256[name]):
+        path = os.path.join(model_dir, fname)
+        if not os.path.isfile(path) or sha256sum(path) != want:
+            bad.append(fname)
+    return bad
 
 
 def sha256sum(path: str) -> str:
@@ -316,6 +351,10 @@ def download(dataset: str, root: str) -> None:
             z = fetch(url, os.path.join(base, os.path.basename(url)))
             with zipfile.ZipFile(z) as zf:
                 zf.extractall(base)
-            print(f"[weights] {name}: sha256 {sha256sum(z)}")
+            bad = verify_weights(name, z[:-4])
+            for fname in bad:
+                print(f"[weights] SHA256sum does not match on file: {fname} from download url: {url}")
+            if not bad:
+                print(f"[weights] {name}: {len(_WEIGHT_FILES)} files verified")
     else:
         raise ValueError(f"unknown dataset {dataset}")

@@ -81,3 +81,30 @@ def test_tokenizers(tmp_path):
     hf = T.get_wordpiece_tokenizer(str(vf))
     assert hf.token_to_id("[MASK]") == 4
     assert hf.encode("hello world").tokens == ["[CLS]", "hello", "world", "[SEP]"]
+
+
+def test_downloaders_with_local_urls(tmp_path, monkeypatch, capsys):
+    """utils/download.py back end against file:// URLs: SQuAD files land under v1.1 / v2.0, the weights archive is
+    extracted and its files are checked against the recorded SHA-256 digests (a doctored archive is reported)."""
+    import zipfile
+    from bert_pytorch_b200.data import corpus
+    src = tmp_path / "src"; src.mkdir()
+    (src / "train.json").write_text('{"data": []}')
+    monkeypatch.setattr(corpus, "SQUAD_URLS", {(src / "train.json").as_uri(): "v1.1/train-v1.1.json"})
+    corpus.download("squad", str(tmp_path / "dl"))
+    assert (tmp_path / "dl" / "squad" / "v1.1" / "train-v1.1.json").read_text() == '{"data": []}'
+    corpus.download("squad", str(tmp_path / "dl"))                    # second call: already there
+    assert "already exists" in capsys.readouterr().out
+
+    zpath = src / "uncased_L-24_H-1024_A-16.zip"
+    with zipfile.ZipFile(zpath, "w") as z:
+        z.writestr("uncased_L-24_H-1024_A-16/vocab.txt", "[PAD]\n")
+        z.writestr("uncased_L-24_H-1024_A-16/bert_config.json", "{}")
+    monkeypatch.setattr(corpus, "WEIGHT_URLS", {"bert_large_uncased": zpath.as_uri()})
+    corpus.download("weights", str(tmp_path / "dl"))
+    out = capsys.readouterr().out
+    assert "SHA256sum does not match on file: vocab.txt" in out and "bert_model.ckpt.index" in out
+    assert (tmp_path / "dl" / "weights" / "uncased_L-24_H-1024_A-16" / "vocab.txt").is_file()
+    assert set(corpus.WEIGHT_SHA256) == set(corpus.WEIGHT_URLS) | {"bert_base_uncased", "bert_base_cased", "bert_large_cased"}
+    with pytest.raises(ValueError):
+        corpus.download("imagenet", str(tmp_path / "dl"))
