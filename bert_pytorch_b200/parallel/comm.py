@@ -205,6 +205,24 @@ def make_comm(kind: Optional[str] = None) -> Comm:
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
         return SingleComm()
     if kind == "fused":
+        if spans_nodes():
+            # the peer-memory kernels address the other ranks' arenas through NVLink mappings, which end at the
+            # node boundary; a multi-node job keeps the bucket-free NCCL all-reduce of the flat gradient arena
+            import warnings
+            warnings.warn("--backend fused needs all ranks on one NVLink domain; this job spans several nodes "
+                          "-> using the NCCL backend")
+            return TorchComm()
         from .peer import PeerComm
         return PeerComm()
     return TorchComm()
+
+
+def spans_nodes() -> bool:
+    """True when torchrun reports fewer local ranks than the world size (LOCAL_WORLD_SIZE < WORLD_SIZE)."""
+    import os
+    try:
+        local = int(os.environ.get("LOCAL_WORLD_SIZE", "0"))
+    except ValueError:
+        local = 0
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    return 0 < local < world

@@ -175,3 +175,31 @@ def test_all_reduce_many_default_and_fused_reduction_config():
     w2 = _Wrapped(_Peer())
     pretrain.configure_fused_reduction(w2, preconditioner=object())
     assert w2.defer_reduction is False and w2.comm.push_master is True          # K-FAC: classic all-reduce first
+
+
+def test_fused_backend_falls_back_across_nodes(monkeypatch):
+    """`--backend fused` on a job that spans several nodes (LOCAL_WORLD_SIZE < WORLD_SIZE) keeps the torch backend:
+    NVLink peer mappings end at the node boundary."""
+    import warnings
+    from bert_pytorch_b200.parallel import comm as C
+
+    class _Dist:
+        @staticmethod
+        def is_available(): return True
+        @staticmethod
+        def is_initialized(): return True
+        @staticmethod
+        def get_world_size(*a): return 16
+        @staticmethod
+        def get_rank(*a): return 0
+    monkeypatch.setattr(C, "dist", _Dist)
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "8")
+    assert C.spans_nodes()
+    made = []
+    monkeypatch.setattr(C, "TorchComm", lambda *a, **k: made.append("torch") or "torch-comm")
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        assert C.make_comm("fused") == "torch-comm"
+    assert any("spans several nodes" in str(x.message) for x in w)
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "16")
+    assert not C.spans_nodes()
