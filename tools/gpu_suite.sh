@@ -31,6 +31,11 @@ for s in $STAGES; do
     trace2)  PHASE=2 timeout 600 python tools/trace_step.py > gpurun_out/trace_step2.log 2>&1; echo "trace2 rc=$?"; cat gpurun_out/trace_step2.log | tail -30 ;;
     push)    timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29578 tools/push_check.py > gpurun_out/push_check.log 2>&1; echo "push rc=$?"; grep "^{" gpurun_out/push_check.log | tail -1 | cut -c1-3000; tail -5 gpurun_out/push_check.log | cut -c1-500 ;;
     peer)    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29577 tools/peer_check.py ${PEER_ARGS:-} > gpurun_out/peer_check.log 2>&1; echo "peer rc=$?"; tail -20 gpurun_out/peer_check.log ;;
+    experimental)  # opt-in kernels written without GPU access (NOTES.md): correctness under a short timeout, then timing
+             B200_TEST_EXPERIMENTAL=1 timeout 180 python -m pytest tests/test_gpu_attention.py -m gpu -q -x --timeout 120 -k pipelined > gpurun_out/test_experimental.log 2>&1; echo "pipe test rc=$?"; tail -5 gpurun_out/test_experimental.log
+             timeout 200 python tools/attn_bench.py --pipe > gpurun_out/attn_bench_pipe.json 2> gpurun_out/attn_bench_pipe.err; echo "pipe bench rc=$?"; cat gpurun_out/attn_bench_pipe.json
+             B200_LN_FINALIZE_SPLIT=8 timeout 200 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x --timeout 120 -k "layer_norm or pretrainer_matches" > gpurun_out/test_lnsplit.log 2>&1; echo "ln split test rc=$?"; tail -3 gpurun_out/test_lnsplit.log
+             for z in 1 8; do B200_LN_FINALIZE_SPLIT=$z timeout 200 python tools/elt_bench.py 2>/dev/null | grep -i "ln_bwd\|layer_norm_bwd" | sed "s/^/split=$z /"; done | tee gpurun_out/elt_bench_lnsplit.txt ;;
     *) echo "unknown stage $s" ;;
   esac
 done
