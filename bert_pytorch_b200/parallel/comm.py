@@ -208,21 +208,36 @@ def make_comm(kind: Optional[str] = None) -> Comm:
         if spans_nodes():
             # the peer-memory kernels address the other ranks' arenas through NVLink mappings, which end at the
             # node boundary; a multi-node job keeps the bucket-free NCCL all-reduce of the flat gradient arena
+            # unless the two-level variant is requested (B200_HIER_FUSED=1: node-local fused step + rail all-reduce)
+            import os
             import warnings
+            if os.environ.get("B200_HIER_FUSED") == "1":
+                from .peer import HierarchicalPeerComm
+                return HierarchicalPeerComm(local_world_size())
             warnings.warn("--backend fused needs all ranks on one NVLink domain; this job spans several nodes "
-                          "-> using the NCCL backend")
+                          "-> using the NCCL backend (B200_HIER_FUSED=1 selects the two-level fused variant)")
             return TorchComm()
         from .peer import PeerComm
         return PeerComm()
     return TorchComm()
 
 
-def spans_nodes() -> bool:
-    """True when torchrun reports fewer local ranks than the world size (LOCAL_WORLD_SIZE < WORLD_SIZE)."""
+def local_world_size() -> int:
+    """Ranks per NVLink domain: torchrun's LOCAL_WORLD_SIZE (B200_FAKE_LOCAL_WORLD overrides it so that one box can
+    stand in for several nodes when testing the two-level paths); 0 = unknown."""
     import os
-    try:
-        local = int(os.environ.get("LOCAL_WORLD_SIZE", "0"))
-    except ValueError:
-        local = 0
+    for key in ("B200_FAKE_LOCAL_WORLD", "LOCAL_WORLD_SIZE"):
+        try:
+            v = int(os.environ.get(key, "0"))
+        except ValueError:
+            v = 0
+        if v > 0:
+            return v
+    return 0
+
+
+def spans_nodes() -> bool:
+    """True when there are fewer local ranks than the world size (LOCAL_WORLD_SIZE < WORLD_SIZE)."""
+    local = local_world_size()
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
     return 0 < local < world

@@ -282,3 +282,75 @@ class PeerComm(TorchComm):
             buf[: self.lo].zero_()
             buf[self.hi:].zero_()
             dist.all_reduce(buf, group=self.group)
+
+
+class HierarchicalPeerComm(TorchComm):
+    """The fused backend on a job that spans several NVLink domains (nodes): opt-in (``B200_HIER_FUSED=1``), not yet
+    exercised on hardware (one box can emulate it with ``B200_FAKE_LOCAL_WORLD=k``: ranks [0,k), [k,2k), ... act as nodes).
+
+    Ranks are ``node * local_world + local_rank``.  Inside a node the gradient arena lives in symmetric memory and
+    the unmodified single-node machinery runs (:class:`PeerComm` over the node's process group: GEMM -> reduce-scatter
+    push, reduce-scatter + LAMB + all-gather kernel).  Across nodes every rank first all-reduces its gradient arena
+    with the ranks of the same local index ("rail" groups: NCCL over the NICs, one rail per GPU), so each node then
+    holds the job-wide sums partitioned over its local ranks and the node-local kernel finishes the step; the
+    averaging factor 1 / (nodes * local_world) is folded into the kernel's unscale constant.  Every node ends up with
+    the same parameters and (partitioned) LAMB state, so checkpoints gather inside node 0 only.
+    Generic collectives (broadcast at start-up, K-FAC factors, barriers) use the world NCCL group.
+    The rail all-reduce moves the whole arena; shard-only traffic needs the reduction kernel split at the phase
+    boundary (NOTES.md)."""
+    fuses_optimizer = True
+
+    def __init__(self, local_world: int, **peer_kw):
+        super().__init__(None)                                   # world group: rank / world_size stay global
+        world, rank = self.world_size, self.rank
+        if local_world <= 0 or world % local_world != 0:
+            raise ValueError(f"world size {world} is not a multiple of the node size {local_world}")
+        self.nodes, self.local_world = world // local_world, local_world
+        node, lrank = divmod(rank, local_world)
+        # every rank creates every group, in the same order (torch.distributed requirement)
+        local_groups = [dist.new_group(list(range(n * local_world, (n + 1) * local_world))) for n in range(self.nodes)]
+        rail_groups = [dist.new_group(list(range(l, world, local_world))) for l in range(local_world)]
+        self.rail = rail_groups[lrank]
+        self.inner = PeerComm(group=local_groups[node], **peer_kw)
+        self.name = "fused-hier"
+        self.device = self.inner.device
+
+    # -- what the runtime touches on a fused backend -------------------------------------------------------------
+    @property
+    def push_master(self) -> bool:
+        return self.inner.push_master
+
+    @push_master.setter
+    def push_master(self, v: bool) -> None:
+        self.inner.push_master = bool(v)
+
+    @property
+    def stats(self):
+        return self.inner.stats
+
+    @property
+    def arena(self):
+        return self.inner.arena
+
+    def adopt(self, arena) -> None:
+        self.inner.adopt(arena)
+
+    def set_prereduced(self, names) -> None:
+        self.inner.set_prereduced(names)
+
+    def begin_push(self) -> bool:
+        return self.inner.begin_push()
+
+    def end_push(self) -> None:
+        self.inner.end_push()
+
+    @torch.no_grad()
+    def fused_lamb_step(self, optimizer, loss_scale: float = 1.0) -> None:
+        dist.all_reduce(self.inner.grad_t, group=self.rail)      # sums over nodes, rail by rail
+        self.inner.fused_lamb_step(optimizer, loss_scale=loss_scale * self.nodes)
+
+    def gather_master(self) -> None:
+        self.inner.gather_master()
+
+    def gather_optimizer_state(self) -> None:
+        self.inner.gather_optimizer_state()

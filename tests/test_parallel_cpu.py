@@ -203,3 +203,53 @@ def test_fused_backend_falls_back_across_nodes(monkeypatch):
     assert any("spans several nodes" in str(x.message) for x in w)
     monkeypatch.setenv("LOCAL_WORLD_SIZE", "16")
     assert not C.spans_nodes()
+
+
+class _StubPeer:
+    """Stands in for PeerComm on CPU: 'symmetric' gradient arena = a plain tensor, the fused step = node-local sum
+    times the kernel's unscale constant 1 / (local_world * loss_scale)."""
+    def __init__(self, group=None, **kw):
+        import torch.distributed as dist
+        self.group, self.rank, self.world_size = group, dist.get_rank(group), dist.get_world_size(group)
+        self.device, self.push_master, self.stats, self.arena = torch.device("cpu"), True, torch.zeros(4), None
+        self.grad_t = torch.full((8,), float(dist.get_rank() + 1))
+        self.result = None
+
+    def fused_lamb_step(self, optimizer, loss_scale=1.0):
+        import torch.distributed as dist
+        t = self.grad_t.clone()
+        dist.all_reduce(t, group=self.group)
+        self.result = t / (self.world_size * loss_scale)
+
+
+def _hier_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      B200_FAKE_LOCAL_WORLD="2", B200_HIER_FUSED="1")
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method="env://")
+    from bert_pytorch_b200.parallel import comm as C, peer as P
+    P.PeerComm = _StubPeer
+    c = C.make_comm("fused")
+    assert isinstance(c, P.HierarchicalPeerComm) and (c.rank, c.world_size, c.nodes, c.local_world) == (rank, world, 2, 2)
+    assert c.inner.rank == rank % 2 and c.inner.world_size == 2
+    c.push_master = False
+    c.fused_lamb_step(optimizer=None, loss_scale=4.0)
+    q.put((rank, c.inner.result.clone(), c.inner.push_master))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_level_fused_backend_composition_gloo():
+    """4 gloo ranks as 2 'nodes' x 2: rail all-reduce + node-local step = job-wide mean / loss_scale on every rank."""
+    world, port = 4, 29657
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_hier_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+    for _, out, pm in res:
+        assert pm is False
+        assert torch.allclose(out, torch.full((8,), (1 + 2 + 3 + 4) / 4 / 4.0))
