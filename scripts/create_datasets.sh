@@ -1,14 +1,15 @@
 #!/bin/bash
 # Build the pre-training datasets end to end:  download -> wikiextractor -> format -> (vocab) -> encode to HDF5.
-#   scripts/create_datasets.sh --output data [--nproc 16] [--download] [--format] [--encode] [--encode-type bert|roberta]
+#   scripts/create_datasets.sh --output data [--nproc 16] [--no-books] [--download] [--format] [--encode] [--encode-type bert|roberta]
 # (The reference's version calls a script/flag that does not exist any more, quirk Q25; this one calls
 #  utils/encode_data.py --vocab_file.)  Encoding 100 MB of text takes a few minutes per process.
 set -e
-OUTPUT_DIR=data; NPROC=8; DOWNLOAD=0; FORMAT=0; ENCODE=0; TYPE=bert; VOCAB=""
+OUTPUT_DIR=data; NPROC=8; DOWNLOAD=0; FORMAT=0; ENCODE=0; TYPE=bert; VOCAB=""; BOOKS=1
 while [[ $# -gt 0 ]]; do
     case $1 in
         -o|--output) OUTPUT_DIR=$2; shift 2 ;;
-        -n|--nproc) NPROC=$2; shift 2 ;;
+        -n|-p|--nproc) NPROC=$2; shift 2 ;;
+        --no-books) BOOKS=0; shift ;;
         --download) DOWNLOAD=1; shift ;;
         --format) FORMAT=1; shift ;;
         --encode) ENCODE=1; shift ;;
@@ -20,12 +21,15 @@ while [[ $# -gt 0 ]]; do
 done
 DL=$OUTPUT_DIR/download; FMT=$OUTPUT_DIR/formatted; ENC=$OUTPUT_DIR/encoded
 if [[ $DOWNLOAD -eq 1 ]]; then
-    python utils/download.py --dir "$DL" --datasets wikicorpus bookscorpus squad weights
+    python utils/download.py --dir "$DL" --datasets wikicorpus squad weights
+    if [[ $BOOKS -eq 1 ]]; then python utils/download.py --dir "$DL" --datasets bookscorpus; fi
 fi
 if [[ $FORMAT -eq 1 ]]; then
     python -m wikiextractor.WikiExtractor "$DL/wikicorpus/wikicorpus_en.xml" -b 25M --processes "$NPROC" -o "$DL/wikicorpus/data"
     python utils/format.py --dataset wikicorpus --input_dir "$DL/wikicorpus/data" --output_dir "$FMT/wikicorpus" --processes "$NPROC" --shards 256
-    python utils/format.py --dataset bookscorpus --input_dir "$DL/bookscorpus/download" --output_dir "$FMT/bookscorpus" --processes "$NPROC" --shards 256
+    if [[ $BOOKS -eq 1 ]]; then
+        python utils/format.py --dataset bookscorpus --input_dir "$DL/bookscorpus/download" --output_dir "$FMT/bookscorpus" --processes "$NPROC" --shards 256
+    fi
 fi
 if [[ $ENCODE -eq 1 ]]; then
     VOCAB=${VOCAB:-$DL/weights/uncased_L-24_H-1024_A-16/vocab.txt}
