@@ -1,10 +1,12 @@
 #!/bin/bash
 # SQuAD fine-tuning + evaluation with the reference's recipe (scripts/run_squad.sh: lr 3e-5, 2 epochs, seq 384,
 # stride 128, batch 4, 16-bit compute, 1 GPU).
-CHECKPOINT=${CHECKPOINT:-results/bert_pretraining/pretrain_ckpts/ckpt_8601.pt}
-CONFIG=${CONFIG:-config/bert_large_uncased_config.json}
+#   scripts/run_squad.sh [CHECKPOINT [OUT_DIR [CONFIG]]]      (positional, as in the reference; or the variables below)
+CHECKPOINT=${1:-${CHECKPOINT:-results/bert_pretraining/pretrain_ckpts/ckpt_8601.pt}}
+OUT_DIR=${2:-${OUT_DIR:-results/squad}}
+CONFIG=${3:-${CONFIG:-config/bert_large_uncased_config.json}}
+shift $(( $# < 3 ? $# : 3 ))
 SQUAD_DIR=${SQUAD_DIR:-data/download/squad/v1.1}
-OUT_DIR=${OUT_DIR:-results/squad}
 EPOCHS=${EPOCHS:-2.0}
 LR=${LR:-3e-5}
 BATCH=${BATCH:-4}
