@@ -25,7 +25,9 @@ if [[ "$NNODES" -eq 1 ]]; then
     LAUNCHER+="--standalone --local-addr 127.0.0.1 "
 else
     LAUNCHER+="--rdzv_backend=c10d --rdzv_endpoint=$MASTER_RANK "
-    BACKEND=nccl      # the peer-memory path is a single NVSwitch domain; across nodes gradients go through NCCL
+    # the peer-memory path is a single NVSwitch domain; across nodes gradients go through NCCL unless the two-level
+    # variant is requested (B200_HIER_FUSED=1: node-local fused step + rail-wise NCCL all-reduce)
+    if [[ "${B200_HIER_FUSED:-0}" == 1 ]]; then PRELOAD+="export B200_HIER_FUSED=1 ; "; else BACKEND=nccl; fi
 fi
 CMD="run_pretraining.py --input_dir $DATA --output_dir $OUTPUT_DIR --config_file $CONFIG --backend $BACKEND "
 FULL_CMD=" $PRELOAD $LAUNCHER $CMD $* "
