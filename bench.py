@@ -303,6 +303,29 @@ def run_reference(args, ph, B, accum, rank, world, dev):
     return ms, clocks, 0, e2e, dict(backend="nccl-ddp", scaler=float(scaler.get_scale()))
 
 
+def roofline(args, ph, seq_per_s_per_gpu: float) -> dict:
+    """Model FLOPs per sequence as executed (GEMMs + attention, forward + backward = 3x forward; the MLM head on the
+    masked rows only for this repo, on every position for the reference) against the MEASURED sustained cuBLAS bf16
+    throughput of this pool (MEASURED_PEAKS.json; the profiling recipe's fallback when the file is absent)."""
+    try:
+        H, I, L, V, S = 1024, 4096, args.layers or 24, 30528, ph["seq"]
+        head_rows = ph["max_pred"] if args.impl == "ours" else S
+        fwd = S * L * (2 * (4 * H * H + 2 * H * I) + 4 * S * H) + head_rows * (2 * H * H + 2 * H * V)
+        gflop = 3 * fwd / 1e9
+        peak, src = 1590.0, "fallback"
+        path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(path):
+            with open(path) as f:
+                mp = json.load(f)
+            peak = float(mp.get("bf16_tflops_sustained") or mp.get("bf16_tflops") or peak)
+            src = "MEASURED_PEAKS.json bf16_tflops_sustained"
+        tflops = seq_per_s_per_gpu * gflop / 1e3
+        return {"gflop_per_seq": round(gflop, 1), "tflops_per_gpu": round(tflops, 1), "peak_tflops": peak,
+                "peak_source": src, "fraction_of_peak": round(tflops / peak, 3)}
+    except Exception as e:  # noqa: BLE001 - diagnostics only, never fail the benchmark line
+        return {"error": repr(e)}
+
+
 def main():
     args = parse()
     if args.impl == "reference" and not os.path.exists(os.path.join(ROOT, "baseline", "_ref", "run_pretraining.py")):
@@ -331,6 +354,8 @@ def main():
     ms_local, clocks, launches, e2e, extra = res
     ms = max_over_ranks(ms_local, dev)
     value = global_batch / (ms / 1e3)
+    extra = dict(extra)
+    extra["roofline"] = roofline(args, ph, value / world)
     out = {
         "metric": f"BERT-large phase{args.phase} (seq{ph['seq']}) pretraining sequences/sec, whole job, device-timed max over ranks",
         "value": round(value, 2), "unit": "sequences/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
