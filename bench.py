@@ -44,6 +44,10 @@ PHASES = {
     1: dict(seq=128, local_batch=96, max_pred=20, lr=6e-3, warmup=0.2843, max_steps=7038, global_batch=65536),
     2: dict(seq=512, local_batch=16, max_pred=80, lr=4e-3, warmup=0.128, max_steps=1563, global_batch=32768),
 }
+# config #4 of BASELINE.json: RoBERTa-style recipe (config/roberta_pretraining_config.json + roberta_large_cased_config.json):
+# no next-sentence task, cased 28996-token vocabulary, 15 % dynamic masking, linear decay
+ROBERTA = dict(seq=512, local_batch=16, max_pred=80, lr=4e-4, warmup=0.06, max_steps=100000, global_batch=8192,
+               vocab_size=28996, next_sentence=False, mask_prob=0.15, lr_decay="linear")
 MODEL = dict(vocab_size=30522, hidden_size=1024, num_hidden_layers=24, num_attention_heads=16,
              intermediate_size=4096, max_position_embeddings=512, type_vocab_size=2)
 
@@ -63,6 +67,9 @@ def parse():
     ap.add_argument("--layers", type=int, default=0, help="debug only: fewer layers (marks the result invalid)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--fp8", action="store_true", help="fp8 GEMM operands (separate config; the headline stays bf16)")
+    ap.add_argument("--roberta", action="store_true",
+                    help="RoBERTa-style recipe (seq 512, no NSP, cased vocabulary, linear decay) instead of --phase; ours only")
+    ap.add_argument("--kfac", action="store_true", help="K-FAC preconditioner on (BASELINE config #5); ours only")
     ap.add_argument("--seed", type=int, default=42)
     return ap.parse_args()
 
@@ -82,7 +89,7 @@ def dist_setup(args):
     return rank, world, local, dev
 
 
-def synth_batches(n, B, S, vocab, max_pred, seed, dtype, pin=True):
+def synth_batches(n, B, S, vocab, max_pred, seed, dtype, pin=True, next_sentence=True, mask_prob=0.2):
     """n pre-masked micro-batches on the host: [ids, seg, mask, labels, nsp]."""
     import numpy as np
     import torch
@@ -91,9 +98,9 @@ def synth_batches(n, B, S, vocab, max_pred, seed, dtype, pin=True):
     rng = np.random.default_rng(seed)
     out = []
     for _ in range(n):
-        ids, sp, nsl = synthetic.make_samples(B, S, vocab, True, rng)
+        ids, sp, nsl = synthetic.make_samples(B, S, vocab, next_sentence, rng)
         seg, im = segment_ids_and_input_mask(ids, sp)
-        masked, labels = mask_batch(ids, sp, mask_token_index=4, max_pred_per_seq=max_pred, masked_lm_prob=0.2,
+        masked, labels = mask_batch(ids, sp, mask_token_index=4, max_pred_per_seq=max_pred, masked_lm_prob=mask_prob,
                                     vocab_size=vocab, rng=rng)
         ts = [torch.from_numpy(np.ascontiguousarray(a)).to(dtype) for a in (masked, seg, im, labels, nsl.astype(np.int32))]
         out.append([t.pin_memory() if pin else t for t in ts])
@@ -147,13 +154,14 @@ def run_ours(args, ph, B, accum, rank, world, dev):
     from bert_pytorch_b200.models import BertForPreTraining, BertPretrainingCriterion
     from bert_pytorch_b200.models.arena import NO_DECAY_KEYS, ParamArena
     from bert_pytorch_b200.ops import api as K
-    from bert_pytorch_b200.optim import GradScaler, Lamb, PolyWarmUpScheduler
+    from bert_pytorch_b200.optim import GradScaler, Lamb, LinearWarmUpScheduler, PolyWarmUpScheduler
     from bert_pytorch_b200.parallel import DataParallel, make_comm
     from bert_pytorch_b200.utils.timing import L2Flusher
     assert ops.available(), "sm_100a extension not loaded"
     torch.manual_seed(args.seed + rank)
-    cfg = BertConfig.from_dict(dict(MODEL, next_sentence=True, hidden_act="gelu", hidden_dropout_prob=0.1,
-                                    attention_probs_dropout_prob=0.1, initializer_range=0.02))
+    vocab = ph.get("vocab_size", MODEL["vocab_size"])
+    cfg = BertConfig.from_dict(dict(MODEL, vocab_size=vocab, next_sentence=ph.get("next_sentence", True), hidden_act="gelu",
+                                    hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1, initializer_range=0.02))
     if args.layers:
         cfg.num_hidden_layers = args.layers
     cfg.pad_vocab(8)
@@ -174,16 +182,28 @@ def run_ours(args, ph, B, accum, rank, world, dev):
               {"params": [p for n, p in named if any(k in n for k in NO_DECAY_KEYS)], "weight_decay": 0.0}]
     opt = Lamb(groups, lr=ph["lr"])
     arena.bind_optimizer(opt)
-    pretrain.configure_fused_reduction(ddp)
-    sched = PolyWarmUpScheduler(opt, warmup=ph["warmup"], total_steps=ph["max_steps"])
     scaler = GradScaler(enabled=False)
+    precond = None
+    if args.kfac:                      # the runtime's K-FAC set-up (pretrain.prepare_optimizers, reference defaults)
+        from bert_pytorch_b200 import kfac
+        precond = kfac.KFAC(model, lr=ph["lr"], factor_decay=0.95, damping=0.003, kl_clip=0.001, factor_update_freq=1,
+                            inv_update_freq=10, skip_layers=["BertLMPredictionHead", "embedding"],
+                            comm_method=kfac.CommMethod.HYBRID_OPT, grad_worker_fraction=0.5, inv_dtype=torch.float16,
+                            accumulate_data=False, compute_factor_in_hook=True, distribute_layer_factors=False,
+                            grad_scaler=scaler, comm=ddp.comm)
+    pretrain.configure_fused_reduction(ddp, precond)
+    Sched = LinearWarmUpScheduler if ph.get("lr_decay") == "linear" else PolyWarmUpScheduler
+    scheds = [Sched(opt, warmup=ph["warmup"], total_steps=ph["max_steps"])]
+    if precond is not None:
+        scheds.append(Sched(precond, warmup=ph["warmup"], total_steps=ph["max_steps"]))
     crit = BertPretrainingCriterion(cfg.vocab_size)
     model.train()
     if args.fp8:
         model.bert.fused_engine().enable_fp8()
     flusher = L2Flusher(dev)
 
-    pool = synth_batches(8, B, ph["seq"], MODEL["vocab_size"], ph["max_pred"], args.seed + 17 * rank, torch.int32)
+    pool = synth_batches(8, B, ph["seq"], vocab, ph["max_pred"], args.seed + 17 * rank, torch.int32,
+                         next_sentence=ph.get("next_sentence", True), mask_prob=ph.get("mask_prob", 0.2))
     dev_pool = [[t.to(dev) for t in b] for b in pool]
     loss_acc = torch.zeros((), device=dev)
 
@@ -195,10 +215,11 @@ def run_ours(args, ph, B, accum, rank, world, dev):
             loss = pretrain.forward_backward_pass(ddp, crit, scaler, batch, accum, sync_grads=(m == accum - 1),
                                                   compute_dtype=torch.bfloat16)
             loss_acc.add_(loss)
-        sched.step()
+        for sc in scheds:
+            sc.step()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        pretrain.take_optimizer_step(opt, None, ddp, scaler)
+        pretrain.take_optimizer_step(opt, precond, ddp, scaler)
         e1.record()
         opt_events.append((e0, e1))
 
@@ -212,8 +233,9 @@ def run_ours(args, ph, B, accum, rank, world, dev):
             batch = [t.to(dev, non_blocking=True) for t in hb]
             window += pretrain.forward_backward_pass(ddp, crit, scaler, batch, accum, sync_grads=(m == accum - 1),
                                                      compute_dtype=torch.bfloat16)
-        sched.step()
-        pretrain.take_optimizer_step(opt, None, ddp, scaler)
+        for sc in scheds:
+            sc.step()
+        pretrain.take_optimizer_step(opt, precond, ddp, scaler)
         host_losses.append(float(window))
 
     l0 = K.KERNEL_LAUNCHES
@@ -228,7 +250,8 @@ def run_ours(args, ph, B, accum, rank, world, dev):
     torch.cuda.synchronize()
     opt_ms = [a.elapsed_time(b) for a, b in opt_events[args.warmup:args.warmup + args.steps]]
     opt_mean = max_over_ranks(sum(opt_ms) / max(1, len(opt_ms)), dev) if opt_ms else None
-    what = ("fused reduce-scatter + LAMB + all-gather kernel, INCLUDING its wait for the slowest rank's backward "
+    what = ("K-FAC preconditioner step + gradient all-reduce + LAMB kernels" if args.kfac else
+            "fused reduce-scatter + LAMB + all-gather kernel, INCLUDING its wait for the slowest rank's backward "
             "(the kernel alone: tools/peer_check.py --big)" if getattr(comm, "fuses_optimizer", False) and world > 1
             else "LAMB kernels (all-reduce happens in the last micro-step)" if world > 1 else "LAMB kernels")
     return ms, clocks, launches, e2e, dict(loss_mean=final_loss, backend=getattr(comm, "name", "single"),
@@ -308,7 +331,8 @@ def roofline(args, ph, seq_per_s_per_gpu: float) -> dict:
     masked rows only for this repo, on every position for the reference) against the MEASURED sustained cuBLAS bf16
     throughput of this pool (MEASURED_PEAKS.json; the profiling recipe's fallback when the file is absent)."""
     try:
-        H, I, L, V, S = 1024, 4096, args.layers or 24, 30528, ph["seq"]
+        H, I, L, S = 1024, 4096, args.layers or 24, ph["seq"]
+        V = (ph.get("vocab_size", 30522) + 7) // 8 * 8
         head_rows = ph["max_pred"] if args.impl == "ours" else S
         fwd = S * L * (2 * (4 * H * H + 2 * H * I) + 4 * S * H) + head_rows * (2 * H * H + 2 * H * V)
         gflop = 3 * fwd / 1e9
@@ -336,7 +360,11 @@ def main():
     if not torch.cuda.is_available():
         print(json.dumps({"impl": args.impl, "unavailable": "no CUDA device"}))
         return
-    ph = dict(PHASES[args.phase])
+    ph = dict(ROBERTA) if args.roberta else dict(PHASES[args.phase])
+    if (args.roberta or args.kfac) and args.impl != "ours":
+        print(json.dumps({"impl": args.impl, "unavailable": "--roberta / --kfac are measured for this repository only "
+                          "(the reference arm runs the two headline configs)"}))
+        return
     rank, world, local, dev = dist_setup(args)
     assert world == max(1, args.gpus) or world == 1, f"WORLD_SIZE={world} but --gpus {args.gpus}"
     B = args.local_batch or ph["local_batch"]
@@ -357,13 +385,16 @@ def main():
     extra = dict(extra)
     extra["roofline"] = roofline(args, ph, value / world)
     out = {
-        "metric": f"BERT-large phase{args.phase} (seq{ph['seq']}) pretraining sequences/sec, whole job, device-timed max over ranks",
+        "metric": (f"RoBERTa-large recipe (seq{ph['seq']}, no NSP)" if args.roberta else f"BERT-large phase{args.phase} (seq{ph['seq']})")
+        + (" + K-FAC" if args.kfac else "") + " pretraining sequences/sec, whole job, device-timed max over ranks",
         "value": round(value, 2), "unit": "sequences/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": ("fp8 GEMM operands (e4m3 fwd / e5m2 grads, per-tensor delayed scaling) + bf16" if args.fp8 else "bf16")
         if args.impl == "ours" else "fp16 (reference stock AMP)", "data": "synthetic",
         "impl": args.impl,
-        "config": {"model": "bert-large-uncased L24 H1024 A16 I4096 V30528" + (f" [DEBUG layers={args.layers}]" if args.layers else ""),
+        "config": {"model": ("roberta-large-cased (BERT-large, no NSP) L24 H1024 A16 I4096 V29000" if args.roberta
+                             else "bert-large-uncased L24 H1024 A16 I4096 V30528")
+                   + (f" [DEBUG layers={args.layers}]" if args.layers else ""), "kfac": bool(args.kfac),
                    "global_batch": global_batch, "seq_len": ph["seq"], "local_batch": B, "accumulation_steps": accum,
                    "max_predictions_per_seq": ph["max_pred"], "optimizer": "LAMB", "dropout": 0.1,
                    "parallelism": f"dp{world}", "grad_reduction": extra.get("backend"),
