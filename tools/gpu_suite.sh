@@ -32,6 +32,7 @@ for s in $STAGES; do
     push)    timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29578 tools/push_check.py > gpurun_out/push_check.log 2>&1; echo "push rc=$?"; grep "^{" gpurun_out/push_check.log | tail -1 | cut -c1-3000; tail -5 gpurun_out/push_check.log | cut -c1-500 ;;
     peer)    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29577 tools/peer_check.py ${PEER_ARGS:-} > gpurun_out/peer_check.log 2>&1; echo "peer rc=$?"; tail -20 gpurun_out/peer_check.log ;;
     experimental)  # opt-in kernels written without GPU access (NOTES.md): correctness under a short timeout, then timing
+             B200_TEST_EXPERIMENTAL=1 timeout 180 python -m pytest tests/test_gpu_zz_variants.py -m gpu -q --timeout 120 > gpurun_out/test_variants.log 2>&1; echo "variants rc=$?"; tail -5 gpurun_out/test_variants.log
              B200_TEST_EXPERIMENTAL=1 timeout 180 python -m pytest tests/test_gpu_attention.py -m gpu -q -x --timeout 120 -k pipelined > gpurun_out/test_experimental.log 2>&1; echo "pipe test rc=$?"; tail -5 gpurun_out/test_experimental.log
              timeout 200 python tools/attn_bench.py --pipe > gpurun_out/attn_bench_pipe.json 2> gpurun_out/attn_bench_pipe.err; echo "pipe bench rc=$?"; cat gpurun_out/attn_bench_pipe.json
              B200_LN_FINALIZE_SPLIT=8 timeout 200 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x --timeout 120 -k "layer_norm or pretrainer_matches" > gpurun_out/test_lnsplit.log 2>&1; echo "ln split test rc=$?"; tail -3 gpurun_out/test_lnsplit.log
