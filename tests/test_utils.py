@@ -108,3 +108,25 @@ def test_downloaders_with_local_urls(tmp_path, monkeypatch, capsys):
     assert set(corpus.WEIGHT_SHA256) == set(corpus.WEIGHT_URLS) | {"bert_base_uncased", "bert_base_cased", "bert_large_cased"}
     with pytest.raises(ValueError):
         corpus.download("imagenet", str(tmp_path / "dl"))
+
+
+def test_attention_backward_pipeline_protocol_model():
+    """tools/sim_attn_bwd_pipe.py: the barrier protocol of attn_bwd_pipe_kernel survives random schedules, and the
+    model does flag the three classic ways of breaking it."""
+    import importlib.util
+    import random
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("sim_attn", os.path.join(root, "tools", "sim_attn_bwd_pipe.py"))
+    sim = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sim)
+    for nqb in (1, 2, 3, 4, 5):
+        for t in range(60):
+            sim.Sim(nqb, 4, random.Random(1000 * nqb + t)).run()
+    for mutate in (1, 2, 3):
+        caught = 0
+        for t in range(40):
+            try:
+                sim.Sim(4, 4, random.Random(t), mutate).run()
+            except AssertionError:
+                caught += 1
+        assert caught >= 20, (mutate, caught)
