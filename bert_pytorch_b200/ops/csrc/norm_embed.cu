@@ -201,6 +201,96 @@ ln_fwd2_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ ga
   if (f8.q) fp8_amax_commit(f8, amax);
 }
 
+// Opt-in variant (B200_LN_ROWS=2): every group of WPR warps works on TWO rows per iteration -- twice the bytes in
+// flight per thread (the kernel above is latency bound: 16 B per thread and one barrier per row) and one barrier per
+// two rows.  Same arithmetic per row, so the results are bit-identical to ln_fwd2_kernel.
+template <int WPR>
+__device__ __forceinline__ float4 group_sum4(float a, float b, float c, float d, float4* slot, int wi, int group) {
+  a = warp_sum(a); b = warp_sum(b); c = warp_sum(c); d = warp_sum(d);
+  if (WPR == 1) return make_float4(a, b, c, d);
+  if ((threadIdx.x & 31) == 0) slot[wi] = make_float4(a, b, c, d);
+  if (group == 0) asm volatile("bar.sync 1, %0;" ::"n"(WPR * 32) : "memory");
+  else asm volatile("bar.sync 2, %0;" ::"n"(WPR * 32) : "memory");
+  float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int w = 0; w < WPR; ++w) { const float4 v = slot[w]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
+  return t;
+}
+
+template <int WPR>
+__global__ void __launch_bounds__(2 * WPR * 32)
+ln_fwd2x2_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int H,
+                 float eps, Seed seed_in, unsigned int stream, unsigned int thresh16, float drop_scale, const Fp8Out f8) {
+  const unsigned long long seed = seed_in.value();
+  const float qscale = f8.q ? f8.meta[1] : 0.f;
+  float amax = 0.f;
+  __shared__ float4 xchg[2][2][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int group = warp / WPR, wi = warp % WPR;
+  const int col = (wi * 32 + lane) * 8;
+  const bool live = col < H;
+  float g[8], b[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) { g[t] = live ? gamma[col + t] : 0.f; b[t] = live ? beta[col + t] : 0.f; }
+  const int stride = gridDim.x * 4;                 // 2 groups x 2 rows per block and iteration
+  int row = (blockIdx.x * 2 + group) * 2;           // this group's rows: row, row + 1
+  uint4 nx[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+  float nshift[2] = {0.f, 0.f};
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+    if (row + r < M) {
+      if (live) nx[r] = ld_stream16(x + (size_t)(row + r) * H + col);
+      nshift[r] = __bfloat162float(x[(size_t)(row + r) * H]);
+    }
+  for (int it = 0; row < M; row += stride, ++it) {
+    float v[2][8], shift[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) { unpack8(nx[r], v[r]); shift[r] = nshift[r]; }
+    const int nrow = row + stride;
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+      if (nrow + r < M) {                  // prefetch the next pair before this pair's barrier
+        if (live) nx[r] = ld_stream16(x + (size_t)(nrow + r) * H + col);
+        nshift[r] = __bfloat162float(x[(size_t)(nrow + r) * H]);
+      }
+    float s[2] = {0.f, 0.f}, q[2] = {0.f, 0.f};
+    if (live) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int t = 0; t < 8; ++t) { const float d = v[r][t] - shift[r]; s[r] += d; q[r] += d * d; }
+    }
+    const float4 red = group_sum4<WPR>(s[0], q[0], s[1], q[1], xchg[group][it & 1], wi, group);
+    const float rs[2] = {red.x, red.z}, rq[2] = {red.y, red.w};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int rr = row + r;
+      if (rr >= M) continue;
+      const float ms = rs[r] / (float)H;
+      const float mean = shift[r] + ms;
+      const float rstd = rsqrtf(fmaxf(rq[r] / (float)H - ms * ms, 0.f) + eps);
+      if (live) {
+        Keep8 keep = Keep8::all();
+        if (thresh16 != 0) keep = dropout_keep8(seed, stream, ((uint64_t)rr * H + col) >> 3, thresh16);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          float o = (v[r][t] - mean) * rstd * g[t] + b[t];
+          if (thresh16 != 0) o = keep[t] ? o * drop_scale : 0.f;
+          v[r][t] = o;
+        }
+        store8(y + (size_t)rr * H + col, v[r]);
+        if (f8.q) fp8_emit8(f8, (size_t)rr * H + col, v[r], qscale, amax);
+      }
+      if (wi == 0 && lane == 0) {
+        if (mean_out) mean_out[rr] = mean;
+        if (rstd_out) rstd_out[rr] = rstd;
+      }
+    }
+  }
+  if (f8.q) fp8_amax_commit(f8, amax);
+}
+
 // LayerNorm backward.
 //   in : dy [M,H] (grad wrt LN output; with `in_stream` given, dy is first multiplied by the *output* dropout
 //        mask of that stream -- used by the embedding LN whose output was dropped out)
@@ -642,6 +732,14 @@ void layer_norm_fwd(const void* x, const float* gamma, const float* beta, void* 
                     int H, float eps, Seed seed, unsigned int stream, float p_drop, Fp8Out f8, cudaStream_t st) {
   unsigned int th; float sc;
   drop_params(p_drop, th, sc);
+  static const bool two_rows = []() { const char* e = getenv("B200_LN_ROWS"); return e && e[0] == '2'; }();
+  if (two_rows) {                        // opt-in: two rows per warp group and iteration (not yet measured)
+    int g4 = (M + 3) / 4;                // 76 registers x 256 threads -> 3 resident blocks per SM: one exact wave
+    if (g4 > 148 * 3) g4 = 148 * 3;
+    DISPATCH_WPR(H, (ln_fwd2x2_kernel<WPR><<<g4, 2 * WPR * 32, 0, st>>>(
+        (const __nv_bfloat16*)x, gamma, beta, (__nv_bfloat16*)y, mean, rstd, M, H, eps, seed, stream, th, sc, f8)));
+    return;
+  }
   DISPATCH_WPR(H, (ln_fwd2_kernel<WPR><<<ln2_grid(M), 2 * WPR * 32, 0, st>>>(
       (const __nv_bfloat16*)x, gamma, beta, (__nv_bfloat16*)y, mean, rstd, M, H, eps, seed, stream, th, sc, f8)));
 }

@@ -36,6 +36,8 @@ for s in $STAGES; do
              B200_TEST_EXPERIMENTAL=1 timeout 180 python -m pytest tests/test_gpu_attention.py -m gpu -q -x --timeout 120 -k pipelined > gpurun_out/test_experimental.log 2>&1; echo "pipe test rc=$?"; tail -5 gpurun_out/test_experimental.log
              timeout 200 python tools/attn_bench.py --pipe > gpurun_out/attn_bench_pipe.json 2> gpurun_out/attn_bench_pipe.err; echo "pipe bench rc=$?"; cat gpurun_out/attn_bench_pipe.json
              B200_LN_FINALIZE_SPLIT=8 timeout 200 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x --timeout 120 -k "layer_norm or pretrainer_matches" > gpurun_out/test_lnsplit.log 2>&1; echo "ln split test rc=$?"; tail -3 gpurun_out/test_lnsplit.log
+             B200_LN_ROWS=2 timeout 200 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_fp8.py -m gpu -q -x --timeout 120 -k "layer_norm or pretrainer_matches or producer" > gpurun_out/test_lnrows.log 2>&1; echo "ln rows test rc=$?"; tail -3 gpurun_out/test_lnrows.log
+             for r in 1 2; do B200_LN_ROWS=$r timeout 200 python tools/elt_bench.py 2>/dev/null | grep -i "layer_norm_fwd" | sed "s/^/rows=$r /"; done | tee gpurun_out/elt_bench_lnrows.txt
              for z in 1 8; do B200_LN_FINALIZE_SPLIT=$z timeout 200 python tools/elt_bench.py 2>/dev/null | grep -i "ln_bwd\|layer_norm_bwd" | sed "s/^/split=$z /"; done | tee gpurun_out/elt_bench_lnsplit.txt ;;
     *) echo "unknown stage $s" ;;
   esac
