@@ -43,7 +43,7 @@ from .parallel import DataParallel, make_comm, unwrap
 from .utils import checkpoint as ckpt_utils
 from .utils import logging as logger
 from .utils.dist import get_rank, get_world_size, init_distributed, is_main_process
-from .utils.timing import DeviceTimer, max_over_ranks, nvtx_range
+from .utils.timing import DeviceTimer, StepClock, max_over_ranks, nvtx_range
 
 
 # ---------------------------------------------------------------------------
@@ -420,6 +420,8 @@ def main(args) -> Tuple[int, float]:
                            on_trace_ready=tensorboard_trace_handler(os.environ["B200_PROFILE_DIR"]))
         profiler.start()
     timer.start()
+    clock = StepClock(device)           # device-side split of every optimizer step: micro-steps | reduction + optimizer
+    clock.mark()
     while not done:
         sampler.set_epoch(epoch)
         for batch in loader:
@@ -436,8 +438,10 @@ def main(args) -> Tuple[int, float]:
                 continue
             for lrs in lr_schedulers:
                 lrs.step()
+            clock.mark()
             with nvtx_range("optimizer_step"):
                 take_optimizer_step(optimizer, preconditioner, model, scaler)
+            clock.mark()
             if profiler is not None:
                 profiler.step()
             global_step += 1
@@ -446,10 +450,15 @@ def main(args) -> Tuple[int, float]:
             now = perf_counter()
             step_time = now - step_t0
             step_t0 = now
+            average_loss = float(window_loss)          # the one host synchronisation of the step
+            micro_ms, opt_ms = clock.intervals()[-2:]      # complete: the read-back above waited for the stream
+            clock.reset()
+            clock.mark()
             logger.log(tag="train", step=global_step, epoch=epoch,
-                       average_loss=float(window_loss), step_loss=float(last_loss) * acc,
+                       average_loss=average_loss, step_loss=float(last_loss) * acc,
                        learning_rate=optimizer.param_groups[0]["lr"],
-                       samples_per_second=(acc * args.local_batch_size * get_world_size()) / max(step_time, 1e-9))
+                       samples_per_second=(acc * args.local_batch_size * get_world_size()) / max(step_time, 1e-9),
+                       device_step_ms=micro_ms + opt_ms, optimizer_ms=opt_ms)
             window_loss.zero_()
             if pbar is not None:
                 pbar.update(1)

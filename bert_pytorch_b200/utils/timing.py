@@ -42,6 +42,33 @@ class DeviceTimer:
         return (time.perf_counter() - self._t0) * 1e3
 
 
+class StepClock:
+    """Device-side split of one optimizer step without adding a synchronisation: ``mark()`` records an event on the
+    current stream (or the host clock on CPU); ``intervals()`` -- call it after something else has synchronised,
+    e.g. the loss read-back -- returns the milliseconds between consecutive marks."""
+
+    def __init__(self, device: Optional[torch.device] = None):
+        self.cuda = torch.cuda.is_available() and (device is None or device.type == "cuda")
+        self._marks: List = []
+
+    def reset(self) -> None:
+        self._marks = []
+
+    def mark(self) -> None:
+        if self.cuda:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self._marks.append(e)
+        else:
+            self._marks.append(time.perf_counter())
+
+    def intervals(self) -> List[float]:
+        m = self._marks
+        if self.cuda:
+            return [a.elapsed_time(b) for a, b in zip(m[:-1], m[1:])]
+        return [(b - a) * 1e3 for a, b in zip(m[:-1], m[1:])]
+
+
 def max_over_ranks(value: float, device: Optional[torch.device] = None) -> float:
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return float(value)

@@ -38,8 +38,10 @@ def test_phase1_cpu_gloo_10_steps_layout_and_resume(tmp_path):
     assert os.path.isfile(os.path.join(out_a, "pretraining_phase1_log.txt"))
     rows = list(csv.DictReader(open(os.path.join(out_a, "pretraining_phase1_log_metrics.csv"))))
     assert [int(r["step"]) for r in rows] == list(range(1, 11))
-    for k in ("tag", "epoch", "average_loss", "step_loss", "learning_rate", "samples_per_second"):
+    for k in ("tag", "epoch", "average_loss", "step_loss", "learning_rate", "samples_per_second",
+              "device_step_ms", "optimizer_ms"):
         assert k in rows[0]
+    assert all(0.0 < float(r["optimizer_ms"]) < float(r["device_step_ms"]) for r in rows)
     assert float(rows[-1]["average_loss"]) < float(rows[0]["average_loss"]) + 1.0
     ckpts = ck.list_checkpoints(os.path.join(out_a, "pretrain_ckpts"))
     assert [s for s, _ in ckpts] == [6, 8, 10]                       # rolling window of 3
