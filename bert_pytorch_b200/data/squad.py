@@ -164,7 +164,16 @@ _DocSpan = collections.namedtuple("DocSpan", ["start", "length"])
 
 
 def convert_examples_to_features(examples: Sequence[SquadExample], tokenizer, max_seq_length: int, doc_stride: int,
-                                 max_query_length: int, is_training: bool) -> List[InputFeatures]:
+                                 max_query_length: int, is_training: bool,
+                                 improve_answer_span: bool = True) -> List[InputFeatures]:
+    """Sliding-window featurisation (run_squad.py:209-346).
+
+    ``improve_answer_span``: tighten the training span to the word pieces that spell the annotated answer
+    ("paris" instead of "paris ." when the document word is "Paris.").  The reference intends this
+    (``_improve_answer_span``, run_squad.py:349-383) but compares against ``tokenizer.encode(answer).tokens``, which
+    carries [CLS] / [SEP] and therefore never matches: its spans stay at whole whitespace words.  The default here is
+    the intended behaviour; ``False`` reproduces the reference's targets bit for bit
+    (tests/test_reference_parity.py)."""
     tok = _adapt(tokenizer)
     unique_id = 1000000000
     features: List[InputFeatures] = []
@@ -184,7 +193,8 @@ def convert_examples_to_features(examples: Sequence[SquadExample], tokenizer, ma
         if is_training and not ex.is_impossible:
             t_start = orig_to_tok[ex.start_position]
             t_end = orig_to_tok[ex.end_position + 1] - 1 if ex.end_position < len(ex.doc_tokens) - 1 else len(all_doc) - 1
-            t_start, t_end = _improve_answer_span(all_doc, t_start, t_end, tok, ex.orig_answer_text)
+            if improve_answer_span:
+                t_start, t_end = _improve_answer_span(all_doc, t_start, t_end, tok, ex.orig_answer_text)
         max_doc = max_seq_length - len(query) - 3          # [CLS] q [SEP] doc [SEP]
         spans = []
         off = 0

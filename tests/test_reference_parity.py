@@ -1,0 +1,257 @@
+"""Differential tests against the LIVE reference code (CPU): the unmodified reference modules (baseline/_ref or
+/root/reference, with the torch-native shims of baseline/shims standing in for apex / dllogger / ...) run in a
+subprocess on fixed inputs, this repository runs on the same inputs, and the results are compared:
+
+* model zoo: the reference's state dict loads strictly into our models; logits agree to float precision
+* tokenizers (BasicTokenizer / WordpieceTokenizer), SQuAD featurisation and n-best post-processing
+* LR schedulers coupled to the optimizer step, BertAdam updates, distributed sampler chunking
+
+Skipped when no copy of the reference is reachable."""
+import json
+import os
+import pickle
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = next((p for p in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference")
+            if os.path.isfile(os.path.join(p, "src", "modeling.py"))), None)
+pytestmark = pytest.mark.skipif(REF is None, reason="no copy of the reference tree available")
+
+MODEL_CFG = dict(vocab_size=120, hidden_size=32, num_hidden_layers=2, num_attention_heads=4, intermediate_size=64,
+                 hidden_act="gelu", hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1, max_position_embeddings=64,
+                 type_vocab_size=2, initializer_range=0.02, next_sentence=True)
+VOCAB = ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]", "the", "capital", "of", "france", "is", "paris", ".", "river",
+         "seine", "flows", "through", "what", "?", "who", "wrote", "hamlet", "a", "play", "was", "written", "by",
+         "william", "shakespeare", "##s", "##ing", "un", "##aff", "##able", ",", "-", "'", "1603", "in", "and", "it"]
+TEXTS = ["The capital of France is Paris.", "  Hello,\tWORLD!! unaffable-playing  ", "naïve café — 東京 is big",
+         "Who wrote Hamlet? William Shakespeare's play, in 1603.", "", "x" * 120]
+SQUAD = {"version": "1.1", "data": [{"title": "t", "paragraphs": [
+    {"context": "The capital of France is Paris. The river Seine flows through Paris and it is a river.",
+     "qas": [{"id": "q1", "question": "What is the capital of France?", "answers": [{"text": "Paris", "answer_start": 25}]},
+             {"id": "q2", "question": "What river flows through Paris?", "answers": [{"text": "Seine", "answer_start": 42}]}]},
+    {"context": "Hamlet is a play. The play was written by William Shakespeare in 1603.",
+     "qas": [{"id": "q3", "question": "Who wrote Hamlet?", "answers": [{"text": "William Shakespeare", "answer_start": 42}]}]}]}]}
+
+REF_SCRIPT = r'''
+import collections, json, pickle, sys, types
+import numpy as np, torch
+sys.path.insert(0, ".")
+work, = sys.argv[1:]
+spec = pickle.load(open(work + "/spec.pkl", "rb"))
+out = {}
+import src.modeling as M, src.tokenization as T, src.schedulers as S, src.optimization as O, src.dataset as D
+import run_squad as RS
+
+# ---- models
+torch.manual_seed(0)
+cfg = M.BertConfig.from_dict(spec["cfg"])
+ids, seg, mask = (torch.tensor(a) for a in spec["inputs"])
+models = {}
+for name, ctor in (("pretraining", lambda: M.BertForPreTraining(cfg)), ("qa", lambda: M.BertForQuestionAnswering(cfg)),
+                   ("token", lambda: M.BertForTokenClassification(cfg, 5)), ("seq", lambda: M.BertForSequenceClassification(cfg, 3)),
+                   ("mlm", lambda: M.BertForMaskedLM(cfg))):
+    m = ctor().eval()
+    with torch.no_grad():
+        y = m(ids, seg, mask)
+    y = [t.numpy() for t in (y if isinstance(y, (tuple, list)) else [y])]
+    models[name] = ({k: v.numpy() for k, v in m.state_dict().items()}, y)
+out["models"] = models
+
+# ---- tokenizers
+vocab = T.load_vocab(work + "/vocab.txt")
+basic = T.BasicTokenizer(do_lower_case=True)
+wp = T.WordpieceTokenizer(vocab=vocab)
+out["basic"] = [basic.tokenize(t) for t in spec["texts"]]
+out["wordpiece"] = [[p for w in basic.tokenize(t) for p in wp.tokenize(w)] for t in spec["texts"]]
+out["basic_cased"] = [T.BasicTokenizer(do_lower_case=False).tokenize(t) for t in spec["texts"]]
+
+# ---- SQuAD featurisation + post-processing
+tok = T.get_wordpiece_tokenizer(work + "/vocab.txt", uppercase=False)
+ex = RS.read_squad_examples(work + "/squad.json", True, False)
+feats = RS.convert_examples_to_features(ex, tok, 48, 16, 12, True)
+out["features"] = [dict(unique_id=f.unique_id, example_index=f.example_index, doc_span_index=f.doc_span_index,
+                        tokens=list(f.tokens), token_to_orig_map=dict(f.token_to_orig_map),
+                        token_is_max_context=dict(f.token_is_max_context), input_ids=list(f.input_ids),
+                        input_mask=list(f.input_mask), segment_ids=list(f.segment_ids),
+                        start_position=f.start_position, end_position=f.end_position) for f in feats]
+ex_eval = RS.read_squad_examples(work + "/squad.json", False, False)
+feats_eval = RS.convert_examples_to_features(ex_eval, tok, 48, 16, 12, False)
+rng = np.random.default_rng(0)
+results = []
+logits = {}
+for f in feats_eval:
+    s, e = rng.normal(size=48).tolist(), rng.normal(size=48).tolist()
+    logits[f.unique_id] = (s, e)
+    results.append(RS.RawResult(f.unique_id, s, e))
+args = types.SimpleNamespace(version_2_with_negative=False, n_best_size=5, max_answer_length=10, do_lower_case=True,
+                             null_score_diff_threshold=0.0, verbose_logging=False)
+answers, nbest = RS.get_answers(ex_eval, feats_eval, results, args)
+out["logits"] = logits
+out["answers"] = dict(answers)
+out["nbest"] = {k: [dict(d) for d in v] for k, v in nbest.items()}
+
+# ---- schedulers coupled to the optimizer's step counter (src/schedulers.py:97-105,126-134)
+def lr_curve(cls, **kw):
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.SGD([p], lr=1.0)
+    sch = cls(opt, **kw)
+    lrs = []
+    for step in range(1, 41):
+        opt.param_groups[0]["step"] = step
+        sch.step()
+        lrs.append(opt.param_groups[0]["lr"])
+    return lrs
+out["poly"] = lr_curve(S.PolyWarmUpScheduler, warmup=0.25, total_steps=40)
+out["linear"] = lr_curve(S.LinearWarmUpScheduler, warmup=0.25, total_steps=40)
+
+# ---- BertAdam (src/optimization.py:64-174)
+torch.manual_seed(3)
+w = torch.nn.Parameter(torch.randn(7, 5))
+opt = O.BertAdam([w], lr=1e-2, warmup=0.1, t_total=20, weight_decay=0.01, max_grad_norm=1.0)
+traj = []
+for i in range(6):
+    w.grad = torch.randn(7, 5, generator=torch.Generator().manual_seed(10 + i)) * (3.0 if i == 2 else 1.0)
+    opt.step()
+    traj.append(w.detach().clone().numpy())
+out["bertadam"] = traj
+
+# ---- sampler chunking (src/dataset.py:341-428)
+class _DS(torch.utils.data.Dataset):
+    def __len__(self): return 23
+    def __getitem__(self, i): return i
+    def set_epoch(self, epoch): pass
+chunks = {}
+for world in (1, 2, 4):
+    for rank in range(world):
+        sm = D.DistributedSampler(_DS(), num_replicas=world, rank=rank)
+        sm.set_epoch(1)
+        chunks[(world, rank)] = list(iter(sm))
+out["sampler"] = chunks
+pickle.dump(out, open(work + "/ref.pkl", "wb"))
+'''
+
+
+@pytest.fixture(scope="module")
+def ref(tmp_path_factory):
+    work = tmp_path_factory.mktemp("refparity")
+    rng = np.random.default_rng(1)
+    ids = rng.integers(5, MODEL_CFG["vocab_size"], size=(3, 24))
+    seg = np.zeros_like(ids); seg[:, 12:] = 1
+    mask = np.ones_like(ids); mask[1, 18:] = 0; mask[2, 9:] = 0
+    spec = dict(cfg=MODEL_CFG, inputs=[ids.tolist(), seg.tolist(), mask.tolist()], texts=TEXTS)
+    pickle.dump(spec, open(work / "spec.pkl", "wb"))
+    (work / "vocab.txt").write_text("\n".join(VOCAB) + "\n")
+    (work / "squad.json").write_text(json.dumps(SQUAD))
+    (work / "ref_script.py").write_text(REF_SCRIPT)
+    env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "baseline", "shims"), CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, str(work / "ref_script.py"), str(work)], cwd=REF, env=env, capture_output=True,
+                       text=True, timeout=600)
+    if r.returncode != 0:
+        pytest.skip("the reference code does not run here: " + (r.stderr or r.stdout)[-400:])
+    out = pickle.load(open(work / "ref.pkl", "rb"))
+    out["work"], out["spec"] = str(work), spec
+    return out
+
+
+def test_reference_state_dicts_load_and_logits_agree(ref):
+    from bert_pytorch_b200 import BertConfig, models as M
+    cfg = BertConfig.from_dict(MODEL_CFG)
+    ids, seg, mask = (torch.tensor(a) for a in ref["spec"]["inputs"])
+    ctors = {"pretraining": lambda: M.BertForPreTraining(cfg), "qa": lambda: M.BertForQuestionAnswering(cfg),
+             "token": lambda: M.BertForTokenClassification(cfg, 5), "seq": lambda: M.BertForSequenceClassification(cfg, 3),
+             "mlm": lambda: M.BertForMaskedLM(cfg)}
+    for name, (sd, outs) in ref["models"].items():
+        m = ctors[name]().eval()
+        ours = set(m.state_dict())
+        assert ours == set(sd), (name, sorted(ours ^ set(sd))[:6])          # the checkpoint contract, both directions
+        m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+        with torch.no_grad():
+            y = m(ids, seg, mask)
+        y = list(y) if isinstance(y, (tuple, list)) else [y]
+        assert len(y) == len(outs), name
+        for a, b in zip(y, outs):
+            assert a.shape == b.shape and np.allclose(a.numpy(), b, atol=2e-5, rtol=1e-4), (name, np.abs(a.numpy() - b).max())
+
+
+def test_tokenizers_agree(ref):
+    from bert_pytorch_b200.data import tokenization as T
+    vocab = T.load_vocab(os.path.join(ref["work"], "vocab.txt"))
+    basic, wp = T.BasicTokenizer(do_lower_case=True), T.WordpieceTokenizer(vocab=vocab)
+    assert [basic.tokenize(t) for t in TEXTS] == ref["basic"]
+    assert [[p for w in basic.tokenize(t) for p in wp.tokenize(w)] for t in TEXTS] == ref["wordpiece"]
+    assert [T.BasicTokenizer(do_lower_case=False).tokenize(t) for t in TEXTS] == ref["basic_cased"]
+
+
+def test_squad_features_and_answers_agree(ref):
+    from bert_pytorch_b200.data import squad as SQ
+    from bert_pytorch_b200.data.tokenization import get_wordpiece_tokenizer
+    work = ref["work"]
+    tok = get_wordpiece_tokenizer(os.path.join(work, "vocab.txt"), uppercase=False)
+    ex = SQ.read_squad_examples(os.path.join(work, "squad.json"), True, False)
+    # the reference's answer-span refinement never fires (it compares against a string with [CLS] / [SEP]):
+    # improve_answer_span=False reproduces its targets exactly, the default tightens "paris ." to "paris"
+    feats = SQ.convert_examples_to_features(ex, tok, 48, 16, 12, True, improve_answer_span=False)
+    tight = SQ.convert_examples_to_features(ex, tok, 48, 16, 12, True)
+    assert tight[0].tokens[tight[0].start_position:tight[0].end_position + 1] == ["paris"]
+    assert feats[0].tokens[feats[0].start_position:feats[0].end_position + 1] == ["paris", "."]
+    assert len(feats) == len(ref["features"])
+    for f, r in zip(feats, ref["features"]):
+        for k, v in r.items():
+            mine = getattr(f, k)
+            mine = dict(mine) if isinstance(v, dict) else (list(mine) if isinstance(v, list) else mine)
+            assert mine == v, (r["unique_id"], k)
+    ex_eval = SQ.read_squad_examples(os.path.join(work, "squad.json"), False, False)
+    feats_eval = SQ.convert_examples_to_features(ex_eval, tok, 48, 16, 12, False)
+    results = [SQ.RawResult(f.unique_id, *ref["logits"][f.unique_id]) for f in feats_eval]
+    answers, nbest = SQ.get_answers(ex_eval, feats_eval, results, n_best_size=5, max_answer_length=10, do_lower_case=True)
+    assert dict(answers) == ref["answers"]
+    for qid, lst in ref["nbest"].items():
+        mine = nbest[qid]
+        assert [d["text"] for d in mine] == [d["text"] for d in lst], qid
+        for a, b in zip(mine, lst):
+            assert abs(a["probability"] - b["probability"]) < 1e-9 and abs(a["start_logit"] - b["start_logit"]) < 1e-12
+
+
+def test_schedulers_bertadam_and_sampler_agree(ref):
+    from bert_pytorch_b200.data.dataset import DistributedSampler
+    from bert_pytorch_b200.optim import BertAdam, LinearWarmUpScheduler, PolyWarmUpScheduler
+
+    def lr_curve(cls, **kw):
+        p = torch.nn.Parameter(torch.zeros(1))
+        opt = torch.optim.SGD([p], lr=1.0)
+        sch = cls(opt, **kw)
+        lrs = []
+        for step in range(1, 41):
+            opt.param_groups[0]["step"] = step
+            sch.step()
+            lrs.append(opt.param_groups[0]["lr"])
+        return lrs
+    poly = lr_curve(PolyWarmUpScheduler, warmup=0.25, total_steps=40)
+    # identical while progress <= 1; one step past the end the reference returns a complex number
+    # ((1 - 41/40) ** 0.5), this repo clamps the decay at zero
+    assert np.allclose(poly[:39], np.real(ref["poly"][:39]), rtol=1e-12, atol=1e-15)
+    assert isinstance(ref["poly"][39], complex) and poly[39] == 0.0
+    assert np.allclose(lr_curve(LinearWarmUpScheduler, warmup=0.25, total_steps=40), ref["linear"], rtol=1e-12, atol=1e-15)
+
+    torch.manual_seed(3)
+    w = torch.nn.Parameter(torch.randn(7, 5))
+    opt = BertAdam([w], lr=1e-2, warmup=0.1, t_total=20, weight_decay=0.01, max_grad_norm=1.0)
+    for i, want in enumerate(ref["bertadam"]):
+        w.grad = torch.randn(7, 5, generator=torch.Generator().manual_seed(10 + i)) * (3.0 if i == 2 else 1.0)
+        opt.step()
+        assert np.allclose(w.detach().numpy(), want, atol=1e-6, rtol=1e-5), i
+
+    class _DS(torch.utils.data.Dataset):
+        files = ["x"]
+        def __len__(self): return 23
+        def __getitem__(self, i): return i
+        def set_epoch(self, epoch): pass
+    for (world, rank), want in ref["sampler"].items():
+        sm = DistributedSampler(_DS(), world, rank=rank)
+        sm.set_epoch(1)
+        assert list(iter(sm)) == want, (world, rank)
