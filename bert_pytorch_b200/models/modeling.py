@@ -541,7 +541,7 @@ class BertModel(BertPreTrainedModel):
             layers = self.encoder(x, self.additive_mask(attention_mask, dtype))
         pooled = self.pooler(layers[-1]) if self.pooler is not None else None
         if not self.output_all_encoded_layers:
-            return layers[-1], pooled
+            layers = layers[-1:]            # a LIST, as in the reference (src/modeling.py:880-883): callers index [-1]
         return layers, pooled
 
 
@@ -557,7 +557,8 @@ class BertForPreTraining(BertPreTrainedModel):
         self.apply(self.init_bert_weights)
 
     def forward(self, input_ids, token_type_ids=None, attention_mask=None):
-        seq, pooled = self.bert(input_ids, token_type_ids, attention_mask)
+        layers, pooled = self.bert(input_ids, token_type_ids, attention_mask)
+        seq = layers[-1]
         return self.cls(seq, pooled)
 
     def pretrain_engine(self):
@@ -584,7 +585,8 @@ class BertForMaskedLM(BertPreTrainedModel):
         self.apply(self.init_bert_weights)
 
     def forward(self, input_ids, token_type_ids=None, attention_mask=None, masked_lm_labels=None):
-        seq, _ = self.bert(input_ids, token_type_ids, attention_mask)
+        layers, _ = self.bert(input_ids, token_type_ids, attention_mask)
+        seq = layers[-1]
         scores = self.cls(seq)
         if masked_lm_labels is not None:
             return F.cross_entropy(scores.view(-1, scores.size(-1)).float(), masked_lm_labels.view(-1),
@@ -662,7 +664,8 @@ class BertForTokenClassification(BertPreTrainedModel):
         self.apply(self.init_bert_weights)
 
     def forward(self, input_ids, token_type_ids=None, attention_mask=None, labels=None):
-        seq, _ = self.bert(input_ids, token_type_ids, attention_mask)
+        layers, _ = self.bert(input_ids, token_type_ids, attention_mask)
+        seq = layers[-1]
         logits = self.classifier(self.dropout(seq))
         if labels is not None:
             flat_logits = logits.view(-1, self.num_labels).float()
@@ -682,7 +685,8 @@ class BertForQuestionAnswering(BertPreTrainedModel):
         self.apply(self.init_bert_weights)
 
     def forward(self, input_ids, token_type_ids=None, attention_mask=None):
-        seq, _ = self.bert(input_ids, token_type_ids, attention_mask)
+        layers, _ = self.bert(input_ids, token_type_ids, attention_mask)
+        seq = layers[-1]
         logits = self.qa_outputs(seq)
         start, end = logits.split(1, dim=-1)
         return start.squeeze(-1), end.squeeze(-1)

@@ -71,14 +71,14 @@ def test_padding_does_not_change_valid_positions_and_checkpointing():
     cfg = _cfg(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
     m = M.BertModel(cfg).eval()
     ids = torch.randint(0, 512, (1, 16))
-    full, _ = m(ids[:, :10], None, torch.ones(1, 10, dtype=torch.long))
+    (full,), _ = m(ids[:, :10], None, torch.ones(1, 10, dtype=torch.long))     # a list of layers, as in the reference
     mask = torch.zeros(1, 16, dtype=torch.long); mask[:, :10] = 1
-    padded, _ = m(ids, None, mask)
+    (padded,), _ = m(ids, None, mask)
     assert torch.allclose(full, padded[:, :10], atol=1e-5)
     m.train()
-    ref, _ = m(ids, None, mask)
+    (ref,), _ = m(ids, None, mask)
     m.checkpoint_activations(True)
-    ck, _ = m(ids, None, mask)
+    (ck,), _ = m(ids, None, mask)
     assert torch.allclose(ref, ck, atol=1e-6)
 
 

@@ -37,6 +37,11 @@ SQUAD = {"version": "1.1", "data": [{"title": "t", "paragraphs": [
     {"context": "Hamlet is a play. The play was written by William Shakespeare in 1603.",
      "qas": [{"id": "q3", "question": "Who wrote Hamlet?", "answers": [{"text": "William Shakespeare", "answer_start": 42}]}]}]}]}
 
+NER_LABELS = ["O", "B-PER", "I-PER", "B-LOC"]
+NER_TEXT = ("-DOCSTART- -X- -X- O\n\nWilliam NNP B-NP B-PER\nShakespeare NNP I-NP I-PER\nwrote VBD B-VP O\nHamlet NNP B-NP O\n"
+            "in IN B-PP O\nParis NNP B-NP B-LOC\n.\t.\tO\tO\n\nThe DT B-NP O\nriver NN I-NP O\nSeine NNP I-NP B-LOC\nflows VBZ B-VP O\n"
+            "through IN B-PP O\nParis NNP B-NP B-LOC\nand CC O O\nit PRP B-NP O\nis VBZ B-VP O\na DT B-NP O\nriver NN I-NP O\n. . O O\n")
+
 REF_SCRIPT = r'''
 import collections, json, pickle, sys, types
 import numpy as np, torch
@@ -132,6 +137,62 @@ for world in (1, 2, 4):
         sm.set_epoch(1)
         chunks[(world, rank)] = list(iter(sm))
 out["sampler"] = chunks
+sm = D.DistributedSampler(_DS(), num_replicas=2, rank=1)
+sm.set_epoch(3)
+it = iter(sm); first = [next(it) for _ in range(4)]
+out["sampler_state"] = (first, sm.state_dict())
+
+# ---- more task models
+extra = {}
+ids4 = torch.stack([ids, ids.flip(1)], dim=1)            # [B, 2 choices, S]
+seg4, mask4 = torch.stack([seg, seg], dim=1), torch.stack([mask, mask], dim=1)
+for name, ctor, inp in (("nsp", lambda: M.BertForNextSentencePrediction(cfg), (ids, seg, mask)),
+                        ("choice", lambda: M.BertForMultipleChoice(cfg, 2), (ids4, seg4, mask4)),
+                        ("encoder", lambda: M.BertModel(cfg), (ids, seg, mask))):
+    torch.manual_seed(5)
+    m = ctor().eval()
+    with torch.no_grad():
+        y = m(*inp)
+    flat = []
+    for t in (y if isinstance(y, (tuple, list)) else [y]):
+        flat += [u.numpy() for u in (t if isinstance(t, (tuple, list)) else [t]) if torch.is_tensor(u)]
+    extra[name] = ({k: v.numpy() for k, v in m.state_dict().items()}, flat, type(y[0]).__name__ if isinstance(y, tuple) else "")
+out["models2"] = extra
+
+# ---- pre-training criterion (run_pretraining.py:58-72) incl. ignored labels and the no-NSP form
+import run_pretraining as RP
+g = torch.Generator().manual_seed(11)
+scores = torch.randn(3, 24, cfg.vocab_size, generator=g)
+labels = torch.full((3, 24), -1, dtype=torch.long); labels[:, 3] = 7; labels[1, 9] = 50
+nsp_s, nsp_l = torch.randn(3, 2, generator=g), torch.tensor([0, 1, 1])
+crit = RP.BertPretrainingCriterion(cfg.vocab_size)
+out["criterion"] = (scores.numpy(), labels.numpy(), nsp_s.numpy(), nsp_l.numpy(),
+                    float(crit(scores, labels, nsp_s, nsp_l)), float(crit(scores, labels)))
+
+# ---- dataset helpers (src/dataset.py:224-275): deterministic parts
+ds = D.ShardedPretrainingDataset.__new__(D.ShardedPretrainingDataset)
+row = np.zeros(16, dtype=np.int64); row[:11] = np.arange(20, 31)
+out["segments"] = [(ds._get_segment_ids(row, np.array(sp)).tolist(), ds._get_input_mask(row, np.array(sp)).tolist())
+                   for sp in ([0, 10], [0, 4, 10], [0, 1, 2])]
+pos = np.array([2, 5, 9, 0, 0]); lab = np.array([21, 22, 23, 0, 0])
+out["premasked"] = ds._get_masked_labels(row, pos, lab).tolist()
+
+# ---- NER: CoNLL parsing, word-piece label replication, truncation, macro-F1
+from src.ner_dataset import NERDataset
+import run_ner as RN
+nds = NERDataset(work + "/ner.txt", tok, spec["ner_labels"], 12)
+out["ner"] = [[t.tolist() for t in nds[i]] for i in range(len(nds))]
+rngm = np.random.default_rng(4)
+preds = rngm.normal(size=(3, 12, len(spec["ner_labels"]) + 1))
+lbl = rngm.integers(-1, len(spec["ner_labels"]) + 1, size=(3, 12)); lbl[lbl < 0] = -100
+idx_to_label = {i: l for i, l in enumerate(spec["ner_labels"], start=1)}
+idx_to_label[0] = "O"
+out["ner_f1"] = (preds, lbl, float(RN.compute_metrics(preds, lbl, idx_to_label)))
+
+# ---- small helpers
+import src.utils as U, src.file_utils as F
+out["format_step"] = [U.format_step(x) for x in ("PARAMETER", (1,), (1, 20), (2, 30, 4), ())]
+out["url_to_filename"] = [F.url_to_filename("https://example.org/a/b.bin"), F.url_to_filename("s3://bucket/key", etag='"abc"')]
 pickle.dump(out, open(work + "/ref.pkl", "wb"))
 '''
 
@@ -143,7 +204,8 @@ def ref(tmp_path_factory):
     ids = rng.integers(5, MODEL_CFG["vocab_size"], size=(3, 24))
     seg = np.zeros_like(ids); seg[:, 12:] = 1
     mask = np.ones_like(ids); mask[1, 18:] = 0; mask[2, 9:] = 0
-    spec = dict(cfg=MODEL_CFG, inputs=[ids.tolist(), seg.tolist(), mask.tolist()], texts=TEXTS)
+    spec = dict(cfg=MODEL_CFG, inputs=[ids.tolist(), seg.tolist(), mask.tolist()], texts=TEXTS, ner_labels=NER_LABELS)
+    (work / "ner.txt").write_text(NER_TEXT)
     pickle.dump(spec, open(work / "spec.pkl", "wb"))
     (work / "vocab.txt").write_text("\n".join(VOCAB) + "\n")
     (work / "squad.json").write_text(json.dumps(SQUAD))
@@ -255,3 +317,78 @@ def test_schedulers_bertadam_and_sampler_agree(ref):
         sm = DistributedSampler(_DS(), world, rank=rank)
         sm.set_epoch(1)
         assert list(iter(sm)) == want, (world, rank)
+
+
+def test_more_models_criterion_dataset_helpers_ner_and_small_helpers_agree(ref):
+    from bert_pytorch_b200 import BertConfig, models as M
+    from bert_pytorch_b200.data import dataset as D
+    from bert_pytorch_b200.data.ner import NERDataset
+    from bert_pytorch_b200.data.tokenization import get_wordpiece_tokenizer
+    from bert_pytorch_b200.finetune_ner import compute_metrics
+    from bert_pytorch_b200.utils.dist import format_step
+    from bert_pytorch_b200.utils.file_utils import url_to_filename
+    cfg = BertConfig.from_dict(MODEL_CFG)
+    ids, seg, mask = (torch.tensor(a) for a in ref["spec"]["inputs"])
+    ids4 = torch.stack([ids, ids.flip(1)], dim=1)
+    seg4, mask4 = torch.stack([seg, seg], dim=1), torch.stack([mask, mask], dim=1)
+    ctors = {"nsp": (lambda: M.BertForNextSentencePrediction(cfg), (ids, seg, mask)),
+             "choice": (lambda: M.BertForMultipleChoice(cfg, 2), (ids4, seg4, mask4)),
+             "encoder": (lambda: M.BertModel(cfg), (ids, seg, mask))}
+    for name, (sd, outs, first_type) in ref["models2"].items():
+        ctor, inp = ctors[name]
+        m = ctor().eval()
+        assert set(m.state_dict()) == set(sd), (name, sorted(set(m.state_dict()) ^ set(sd))[:6])
+        m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+        with torch.no_grad():
+            y = m(*inp)
+        if isinstance(y, tuple):
+            assert type(y[0]).__name__ == first_type, (name, type(y[0]).__name__, first_type)   # e.g. BertModel -> (list, tensor)
+        flat = []
+        for t in (y if isinstance(y, (tuple, list)) else [y]):
+            flat += [u for u in (t if isinstance(t, (tuple, list)) else [t]) if torch.is_tensor(u)]
+        assert len(flat) == len(outs), name
+        for a, b in zip(flat, outs):
+            assert a.shape == b.shape and np.allclose(a.numpy(), b, atol=2e-5, rtol=1e-4), (name, np.abs(a.numpy() - b).max())
+
+    scores, labels, nsp_s, nsp_l, with_nsp, without = ref["criterion"]
+    crit = M.BertPretrainingCriterion(cfg.vocab_size)
+    t = torch.from_numpy
+    assert abs(float(crit(t(scores), t(labels), t(nsp_s), t(nsp_l))) - with_nsp) < 1e-5
+    assert abs(float(crit(t(scores), t(labels))) - without) < 1e-5
+
+    row = np.zeros((1, 16), dtype=np.int32); row[0, :11] = np.arange(20, 31)
+    for sp, (want_seg, want_mask) in zip(([0, 10], [0, 4, 10], [0, 1, 2]), ref["segments"]):
+        sg, im = D.segment_ids_and_input_mask(row, np.array([sp], dtype=np.int32))
+        assert sg[0].tolist() == want_seg and im[0].tolist() == want_mask, sp
+    lab = D.labels_from_premasked(row, np.array([[2, 5, 9, 0, 0]]), np.array([[21, 22, 23, 0, 0]]))
+    assert lab[0].tolist() == ref["premasked"]
+
+    tok = get_wordpiece_tokenizer(os.path.join(ref["work"], "vocab.txt"), uppercase=False)
+    nds = NERDataset(os.path.join(ref["work"], "ner.txt"), tok, NER_LABELS, 12)
+    assert len(nds) == len(ref["ner"])
+    for i, want in enumerate(ref["ner"]):
+        assert [x.tolist() for x in nds[i]] == want, i
+    preds, lbl, f1 = ref["ner_f1"]
+    idx_to_label = {i: l for i, l in enumerate(NER_LABELS, start=1)}
+    idx_to_label[0] = "O"
+    assert abs(compute_metrics(preds, lbl, idx_to_label) - f1) < 1e-9
+
+    assert [format_step(x) for x in ("PARAMETER", (1,), (1, 20), (2, 30, 4), ())] == ref["format_step"]
+    assert [url_to_filename("https://example.org/a/b.bin"), url_to_filename("s3://bucket/key", etag='"abc"')] == ref["url_to_filename"]
+
+    first, state = ref["sampler_state"]
+    class _DS(torch.utils.data.Dataset):
+        files = ["x"]
+        def __len__(self): return 23
+        def __getitem__(self, i): return i
+        def set_epoch(self, epoch): pass
+    sm = D.DistributedSampler(_DS(), 2, rank=1)
+    sm.set_epoch(3)
+    it = iter(sm)
+    assert [next(it) for _ in range(4)] == first
+    # the reference's set_epoch() only forwards to the dataset, so its state dict always says epoch 0; this
+    # sampler records the epoch it was given -- everything else is identical
+    assert state["epoch"] == 0 and sm.state_dict() == dict(state, epoch=3)
+    sm2 = D.DistributedSampler(_DS(), 2, rank=1)
+    sm2.load_state_dict(state)
+    assert sm2.index == state["index"] and sm2.epoch == state["epoch"]
