@@ -43,7 +43,7 @@ NER_TEXT = ("-DOCSTART- -X- -X- O\n\nWilliam NNP B-NP B-PER\nShakespeare NNP I-N
             "through IN B-PP O\nParis NNP B-NP B-LOC\nand CC O O\nit PRP B-NP O\nis VBZ B-VP O\na DT B-NP O\nriver NN I-NP O\n. . O O\n")
 
 REF_SCRIPT = r'''
-import collections, json, pickle, sys, types
+import collections, json, os, pickle, sys, types
 import numpy as np, torch
 sys.path.insert(0, ".")
 work, = sys.argv[1:]
@@ -193,6 +193,36 @@ out["ner_f1"] = (preds, lbl, float(RN.compute_metrics(preds, lbl, idx_to_label))
 import src.utils as U, src.file_utils as F
 out["format_step"] = [U.format_step(x) for x in ("PARAMETER", (1,), (1, 20), (2, 30, 4), ())]
 out["url_to_filename"] = [F.url_to_filename("https://example.org/a/b.bin"), F.url_to_filename("s3://bucket/key", etag='"abc"')]
+
+# ---- CLI: defaults, JSON overlay and CLI precedence of run_pretraining.py / run_ner.py
+import sys as _sys
+def parse(mod, argv):
+    old = _sys.argv
+    _sys.argv = ["prog"] + argv
+    try:
+        return {k: v for k, v in vars(mod.parse_arguments()).items()}
+    finally:
+        _sys.argv = old
+out["cli_pretrain"] = [parse(RP, a) for a in spec["pretrain_argvs"]]
+out["cli_ner"] = parse(RN, spec["ner_argv"])
+
+# ---- fresh initialisation under a fixed seed (structure + init rules), config JSON round trip
+torch.manual_seed(123)
+fresh = M.BertForPreTraining(cfg)
+out["fresh"] = {k: (tuple(v.shape), float(v.float().mean()), float(v.float().std()) if v.numel() > 1 else 0.0)
+                for k, v in fresh.state_dict().items()}
+out["fresh_exact"] = {k: v.numpy() for k, v in fresh.state_dict().items()}
+out["config_json"] = json.loads(cfg.to_json_string())
+
+# ---- encoder sample layout (utils/encode_data.py:12-35)
+try:
+    import importlib.util
+    sp_ = importlib.util.spec_from_file_location("ref_encode_data", spec["ref_utils"] + "/encode_data.py")
+    E = importlib.util.module_from_spec(sp_); sp_.loader.exec_module(E)
+    ts = [E.TrainingSample(["a", "b", "c"]), E.TrainingSample(["a", "b"], ["c", "d", "e"], True), E.TrainingSample([], [])]
+    out["samples"] = [(t.sequence, t.special_token_positions, t.is_random_next) for t in ts]
+except Exception as e:
+    out["samples"] = repr(e)
 pickle.dump(out, open(work + "/ref.pkl", "wb"))
 '''
 
@@ -204,7 +234,16 @@ def ref(tmp_path_factory):
     ids = rng.integers(5, MODEL_CFG["vocab_size"], size=(3, 24))
     seg = np.zeros_like(ids); seg[:, 12:] = 1
     mask = np.ones_like(ids); mask[1, 18:] = 0; mask[2, 9:] = 0
-    spec = dict(cfg=MODEL_CFG, inputs=[ids.tolist(), seg.tolist(), mask.tolist()], texts=TEXTS, ner_labels=NER_LABELS)
+    (work / "train.json").write_text(json.dumps({"learning_rate": 1e-3, "max_steps": 77, "kfac_damping": 0.5, "lr_decay": "linear",
+                                                  "unknown_key": 1, "global_batch_size": 1024}))
+    argvs = [[], ["--config_file", str(work / "train.json")],
+             # (no store_true flag here: the reference's auxiliary parser registers every option as taking a value, so
+             #  `--fp16` on its command line is an argparse error -- booleans can only come from the JSON file there)
+             ["--config_file", str(work / "train.json"), "--learning_rate", "0.5", "--steps", "12", "--input_dir", "/x"]]
+    ref_utils = next((p for p in (os.path.join(REF, "utils"), "/root/reference/utils") if os.path.isfile(os.path.join(p, "encode_data.py"))), "")
+    spec = dict(cfg=MODEL_CFG, inputs=[ids.tolist(), seg.tolist(), mask.tolist()], texts=TEXTS, ner_labels=NER_LABELS,
+                pretrain_argvs=argvs, ner_argv=["--train_file", "t.txt", "--labels", "O", "B-X", "--model_config_file", "m.json", "--model_checkpoint", "c.pt"],
+                ref_utils=ref_utils)
     (work / "ner.txt").write_text(NER_TEXT)
     pickle.dump(spec, open(work / "spec.pkl", "wb"))
     (work / "vocab.txt").write_text("\n".join(VOCAB) + "\n")
@@ -392,3 +431,43 @@ def test_more_models_criterion_dataset_helpers_ner_and_small_helpers_agree(ref):
     sm2 = D.DistributedSampler(_DS(), 2, rank=1)
     sm2.load_state_dict(state)
     assert sm2.index == state["index"] and sm2.epoch == state["epoch"]
+
+
+def test_cli_defaults_overlay_and_initialisation_agree(ref, monkeypatch):
+    from bert_pytorch_b200 import BertConfig, finetune_ner, models as M, pretrain
+    from bert_pytorch_b200.data.encode import TrainingSample
+    monkeypatch.delenv("LOCAL_RANK", raising=False)
+    for argv, want in zip(ref["spec"]["pretrain_argvs"], ref["cli_pretrain"]):
+        mine = vars(pretrain.parse_arguments(argv))
+        for k, v in want.items():                                   # every reference flag: same name, same resolved value
+            assert k in mine, k
+            assert mine[k] == v, (argv, k, mine[k], v)
+    mine = vars(finetune_ner.parse_arguments(ref["spec"]["ner_argv"]))
+    for k, v in ref["cli_ner"].items():
+        assert k in mine and mine[k] == v, (k, mine.get(k), v)
+
+    # same seed -> the same freshly initialised weights, tensor by tensor (module order, init rules, kaiming vs normal)
+    cfg = BertConfig.from_dict(MODEL_CFG)
+    torch.manual_seed(123)
+    fresh = M.BertForPreTraining(cfg).state_dict()
+    assert list(fresh) == list(ref["fresh"])                          # same registration order
+    exact = 0
+    for k, (shape, mean, std) in ref["fresh"].items():
+        v = fresh[k]
+        assert tuple(v.shape) == shape, k
+        if np.array_equal(v.numpy(), ref["fresh_exact"][k]):
+            exact += 1
+            continue
+        assert abs(float(v.float().mean()) - mean) < 0.02 and abs((float(v.float().std()) if v.numel() > 1 else 0.0) - std) < 0.02 + 0.25 * std, k
+    assert exact >= len(fresh) // 2, (exact, len(fresh))              # LayerNorm / bias tensors at least are bit-identical
+
+    mine_json = json.loads(cfg.to_json_string())
+    for k, v in ref["config_json"].items():
+        assert mine_json.get(k) == v, k
+
+    if isinstance(ref["samples"], list):
+        ts = [TrainingSample([1, 2, 3]), TrainingSample([1, 2], [3, 4, 5], True), TrainingSample([], [])]
+        for t, (seq, special, rnd) in zip(ts, ref["samples"]):
+            ids, sp = t.layout(101, 102)
+            assert sp == special and len(ids) == len(seq) and t.is_random_next == rnd
+            assert [i for i, tok in enumerate(seq) if tok in ("[CLS]", "[SEP]")] == sp
