@@ -255,6 +255,25 @@ for i in range(len(dsr)):
                  int((lab_ >= 0).sum()), ids_.shape[0]))
 out["dataset_rows"] = rows
 out["dataset_len"] = len(dsr)
+
+# ---- a few optimisation steps end to end (model backward through autograd + criterion + BertAdam), dropout off
+cfg0 = M.BertConfig.from_dict(dict(spec["cfg"], hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0))
+torch.manual_seed(77)
+net = M.BertForPreTraining(cfg0).train()
+out["train_init"] = {k: v.numpy().copy() for k, v in net.state_dict().items()}
+opt2 = O.BertAdam([p for p in net.parameters()], lr=5e-3, warmup=0.2, t_total=10, weight_decay=0.01, max_grad_norm=1.0)
+crit2 = RP.BertPretrainingCriterion(cfg0.vocab_size)
+lab2 = torch.full_like(ids, -1); lab2[:, 2] = 9; lab2[:, 7] = 30; lab2[0, 11] = 5
+nsl2 = torch.tensor([1, 0, 1])
+losses = []
+for step in range(4):
+    sc, rel = net(torch.roll(ids, step, 1), seg, mask)
+    loss = crit2(sc, lab2, rel, nsl2)
+    loss.backward()
+    opt2.step(); opt2.zero_grad()
+    losses.append(float(loss))
+out["train_losses"] = losses
+out["train_final"] = {k: v.numpy().copy() for k, v in net.state_dict().items()}
 pickle.dump(out, open(work + "/ref.pkl", "wb"))
 '''
 
@@ -549,3 +568,26 @@ def test_squad_v2_helpers_and_sharded_dataset_agree(ref):
         assert np.asarray(seg_).tolist() == seg and np.asarray(msk_).tolist() == msk and int(np.asarray(nsl_)) == nsl, i
         assert np.asarray(ids_).shape[0] == width
         assert 1 <= int((np.asarray(lab_) >= 0).sum()) <= 5 and 1 <= n_masked <= 5     # masking itself is random on both sides
+
+
+def test_training_steps_agree(ref):
+    """Four optimisation steps of BertForPreTraining + criterion + BertAdam from the reference's initial weights:
+    the same loss trajectory and the same final weights (autograd backward of every module, tied decoder, optimizer)."""
+    from bert_pytorch_b200 import BertConfig, models as M
+    from bert_pytorch_b200.optim import BertAdam
+    cfg0 = BertConfig.from_dict(dict(MODEL_CFG, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0))
+    ids, seg, mask = (torch.tensor(a) for a in ref["spec"]["inputs"])
+    net = M.BertForPreTraining(cfg0).train()
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in ref["train_init"].items()}, strict=True)
+    opt = BertAdam([p for p in net.parameters()], lr=5e-3, warmup=0.2, t_total=10, weight_decay=0.01, max_grad_norm=1.0)
+    crit = M.BertPretrainingCriterion(cfg0.vocab_size)
+    lab = torch.full_like(ids, -1); lab[:, 2] = 9; lab[:, 7] = 30; lab[0, 11] = 5
+    nsl = torch.tensor([1, 0, 1])
+    for step, want in enumerate(ref["train_losses"]):
+        sc, rel = net(torch.roll(ids, step, 1), seg, mask)
+        loss = crit(sc, lab, rel, nsl)
+        loss.backward()
+        opt.step(); opt.zero_grad()
+        assert abs(float(loss) - want) < 2e-5 * max(1.0, abs(want)), (step, float(loss), want)
+    worst = max(float(np.abs(v.numpy() - ref["train_final"][k]).max()) for k, v in net.state_dict().items())
+    assert worst < 5e-5, worst
