@@ -591,3 +591,35 @@ def test_training_steps_agree(ref):
         assert abs(float(loss) - want) < 2e-5 * max(1.0, abs(want)), (step, float(loss), want)
     worst = max(float(np.abs(v.numpy() - ref["train_final"][k]).max()) for k, v in net.state_dict().items())
     assert worst < 5e-5, worst
+
+
+def test_run_squad_predict_cli_end_to_end(ref, tmp_path):
+    """Both run_squad.py command lines (the reference's and this repo's), same checkpoint, prediction only on the CPU:
+    identical predictions.json and n-best lists (CLI -> checkpoint load -> features -> forward -> post-processing)."""
+    from bert_pytorch_b200 import BertConfig, finetune_squad, models as M
+    work = ref["work"]
+    cfg = dict(MODEL_CFG, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0,
+               vocab_file=os.path.join(work, "vocab.txt"), tokenizer="wordpiece", lowercase=True)
+    model_json = str(tmp_path / "model.json")
+    json.dump(cfg, open(model_json, "w"))
+    torch.manual_seed(5)
+    ckpt = str(tmp_path / "ckpt_10.pt")
+    torch.save({"model": M.BertForPreTraining(BertConfig.from_dict(cfg)).state_dict()}, ckpt)
+    common = ["--no_cuda", "--bert_model", "bert-large-uncased", "--init_checkpoint", ckpt, "--config_file", model_json,
+              "--vocab_file", cfg["vocab_file"], "--do_predict", "--predict_file", os.path.join(work, "squad.json"),
+              "--predict_batch_size", "4", "--max_seq_length", "48", "--doc_stride", "16", "--max_query_length", "12",
+              "--do_lower_case", "--seed", "42"]
+    env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "baseline", "shims"), CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, "run_squad.py", *common, "--output_dir", str(tmp_path / "ref_out")], cwd=REF, env=env,
+                       capture_output=True, text=True, timeout=600)
+    if r.returncode != 0:
+        pytest.skip("the reference runner does not run here: " + (r.stderr or r.stdout)[-300:])
+    finetune_squad.main([*common, "--output_dir", str(tmp_path / "my_out")])
+    a = json.load(open(tmp_path / "ref_out" / "predictions.json"))
+    b = json.load(open(tmp_path / "my_out" / "predictions.json"))
+    assert a == b and set(a) == {"q1", "q2", "q3"}
+    na = json.load(open(tmp_path / "ref_out" / "nbest_predictions.json"))
+    nb = json.load(open(tmp_path / "my_out" / "nbest_predictions.json"))
+    for k in na:
+        assert [x["text"] for x in na[k]] == [x["text"] for x in nb[k]], k
+        assert max(abs(x["probability"] - y["probability"]) for x, y in zip(na[k], nb[k])) < 1e-6
