@@ -190,7 +190,7 @@ def sample_and_shard(input_files: Sequence[str], output_format: str, shard_size:
         order = list(range(len(arts)))
         rng.shuffle(order)
         count = 0
-        for a in order:
+        for a in reversed(order):          # the reference pops from the end of the shuffled list
             if count >= per_input:
                 break
             if written > shard_size:

@@ -623,3 +623,53 @@ def test_run_squad_predict_cli_end_to_end(ref, tmp_path):
     for k in na:
         assert [x["text"] for x in na[k]] == [x["text"] for x in nb[k]], k
         assert max(abs(x["probability"] - y["probability"]) for x, y in zip(na[k], nb[k])) < 1e-6
+
+
+def test_text_sharder_agrees(tmp_path):
+    """utils/shard.py: same shard files for the same input (split at the first article boundary past the byte budget,
+    1-based names, optional shard limit) and the same size parser."""
+    import importlib.util
+    ref_utils = next((p for p in (os.path.join(REF, "utils"), "/root/reference/utils") if os.path.isfile(os.path.join(p, "shard.py"))), None)
+    if ref_utils is None:
+        pytest.skip("the reference's utils/ directory is not available")
+    spec = importlib.util.spec_from_file_location("ref_shard", os.path.join(ref_utils, "shard.py"))
+    RSH = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(RSH)
+    from bert_pytorch_b200.data import corpus
+    text = "".join(f"Article {i} sentence one.\nArticle {i} sentence two is a little longer than one.\n\n" for i in range(40))
+    src = tmp_path / "in.txt"
+    src.write_text(text)
+    for limit in (None, 3):
+        a, b = tmp_path / f"ref_{limit}", tmp_path / f"mine_{limit}"
+        a.mkdir(); b.mkdir()
+        RSH.shard(str(src), str(a / "shard_{index}.txt"), 700, limit)
+        corpus.shard_text(str(src), str(b / "shard_{index}.txt"), 700, limit)
+        fa, fb = sorted(os.listdir(a)), sorted(os.listdir(b))
+        assert fa == fb and len(fa) >= 3, (fa, fb)
+        for f in fa:
+            assert (a / f).read_text() == (b / f).read_text(), (limit, f)
+    for v in (5, "123", "2K", "1.5M", "3b"):
+        assert corpus.parse_value_as_int(v) == RSH.parse_value_as_int(v), v
+
+
+def test_sample_and_shard_agrees(tmp_path):
+    """utils/sample_and_shard.py under the same `random` seed: the same articles in the same shard files."""
+    import random
+    ref_utils = next((p for p in (os.path.join(REF, "utils"), "/root/reference/utils")
+                      if os.path.isfile(os.path.join(p, "sample_and_shard.py"))), None)
+    if ref_utils is None:
+        pytest.skip("the reference's utils/ directory is not available")
+    from bert_pytorch_b200.data import corpus
+    src = tmp_path / "in.txt"
+    src.write_text("".join("".join(f"Article {i} sentence {j}.\n" for j in range(1 + i % 4)) + "\n" for i in range(60)))
+    a, b = tmp_path / "ref", tmp_path / "mine"
+    code = ("import random, runpy, sys; random.seed(11); sys.argv = ['sample_and_shard.py', '-i', sys.argv[1], '-o', sys.argv[2], "
+            "'-b', '400', '-n', '50']; runpy.run_path(sys.argv[0] if False else %r, run_name='__main__')"
+            % os.path.join(ref_utils, "sample_and_shard.py"))
+    r = subprocess.run([sys.executable, "-c", code, str(src), str(a)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    corpus.sample_and_shard([str(src)], str(b / "shard_{index}.txt"), 400, 50, random.Random(11))
+    fa, fb = sorted(os.listdir(a)), sorted(os.listdir(b))
+    assert fa == fb and len(fa) >= 2, (fa, fb)
+    for f in fa:
+        assert (a / f).read_text() == (b / f).read_text(), f
