@@ -673,3 +673,41 @@ def test_sample_and_shard_agrees(tmp_path):
     assert fa == fb and len(fa) >= 2, (fa, fb)
     for f in fa:
         assert (a / f).read_text() == (b / f).read_text(), f
+
+
+@pytest.mark.parametrize("next_seq_prob", [0.5, 0.0])
+def test_sample_packing_agrees_draw_for_draw(next_seq_prob):
+    """utils/encode_data.py:create_samples_from_document under the same `random` seed: the packer makes the same random
+    decisions in the same order (target lengths, A/B cut, random-next documents, re-use of displaced sentences, final
+    shuffle), so the samples are identical."""
+    import importlib.util
+    import random
+    ref_utils = next((p for p in (os.path.join(REF, "utils"), "/root/reference/utils")
+                      if os.path.isfile(os.path.join(p, "encode_data.py"))), None)
+    if ref_utils is None:
+        pytest.skip("the reference's utils/ directory is not available")
+    sys.path.insert(0, os.path.join(ROOT, "baseline", "shims"))          # h5py stand-in for the import
+    try:
+        spec = importlib.util.spec_from_file_location("ref_encode_data2", os.path.join(ref_utils, "encode_data.py"))
+        E = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(E)
+    finally:
+        sys.path.pop(0)
+    from bert_pytorch_b200.data.encode import SamplePacker
+    gen = random.Random(5)
+    docs = [[[gen.randrange(10, 500) for _ in range(gen.randint(1, 30))] for _ in range(gen.randint(1, 12))] for _ in range(9)]
+    docs_ref = [[[f"t{t}" for t in sent] for sent in d] for d in docs]
+    for seed in range(6):
+        random.seed(seed)
+        want = []
+        for i in range(len(docs_ref)):
+            want.extend(E.create_samples_from_document(i, docs_ref, 48, next_seq_prob, 0.3))
+        random.shuffle(want)
+        got = SamplePacker(48, next_seq_prob, 0.3, random.Random(seed)).pack_file(docs)
+        assert len(got) == len(want), seed
+        for g, w in zip(got, want):
+            assert [f"t{t}" for t in g.seq_ids] == w.seq_tokens, seed
+            assert (None if g.next_seq_ids is None else [f"t{t}" for t in g.next_seq_ids]) == w.next_seq_tokens, seed
+            assert g.is_random_next == w.is_random_next
+            ids, special = g.layout(1, 2)
+            assert special == w.special_token_positions and len(ids) == len(w.sequence) <= 48
