@@ -274,6 +274,21 @@ for step in range(4):
     losses.append(float(loss))
 out["train_losses"] = losses
 out["train_final"] = {k: v.numpy().copy() for k, v in net.state_dict().items()}
+
+# ---- dynamic masking statistics (src/dataset.py:277-296)
+dm = D.ShardedPretrainingDataset.__new__(D.ShardedPretrainingDataset)
+dm.max_pred_per_seq, dm.masked_lm_prob, dm.original_token_prob, dm.random_token_prob = 20, 0.2, 0.1, 0.1
+dm.vocab_size, dm.mask_token_index = 1000, 4
+np.random.seed(123)
+base = np.zeros(64, dtype=np.int64); base[:50] = np.arange(100, 150); spx = np.array([0, 20, 49])
+n_lab = n_mask = n_keep = n_rand = bad = 0
+for _ in range(3000):
+    ids_m, lab_m = dm._mask_input(base.copy(), spx)
+    sel = lab_m >= 0
+    n_lab += int(sel.sum()); bad += int(sel[[0, 20, 49]].sum()) + int(sel[50:].sum())
+    n_mask += int((ids_m[sel] == 4).sum()); n_keep += int((ids_m[sel] == base[sel]).sum())
+    n_rand += int(((ids_m[sel] != 4) & (ids_m[sel] != base[sel])).sum())
+out["mask_stats"] = (n_lab / 3000.0, n_mask / n_lab, n_keep / n_lab, n_rand / n_lab, bad)
 pickle.dump(out, open(work + "/ref.pkl", "wb"))
 '''
 
@@ -711,3 +726,25 @@ def test_sample_packing_agrees_draw_for_draw(next_seq_prob):
             assert g.is_random_next == w.is_random_next
             ids, special = g.layout(1, 2)
             assert special == w.special_token_positions and len(ids) == len(w.sequence) <= 48
+
+
+def test_dynamic_masking_statistics_agree(ref):
+    """Same sampling law as src/dataset.py:_mask_input (draws WITH replacement, 80/10/10 applied in draw order): labelled
+    positions per sample and the [MASK] / kept / random split agree with the reference within sampling noise."""
+    from bert_pytorch_b200.data.dataset import mask_batch
+    base = np.zeros((1, 64), dtype=np.int32); base[0, :50] = np.arange(100, 150)
+    sp = np.array([[0, 20, 49]], dtype=np.int32)
+    rng = np.random.default_rng(9)
+    rows = np.repeat(base, 3000, axis=0)
+    ids_m, lab = mask_batch(rows, np.repeat(sp, 3000, axis=0), mask_token_index=4, max_pred_per_seq=20, masked_lm_prob=0.2,
+                            vocab_size=1000, rng=rng)
+    sel = lab >= 0
+    assert not sel[:, [0, 20, 49]].any() and not sel[:, 50:].any()
+    n_lab = sel.sum()
+    mine = (n_lab / 3000.0, (ids_m[sel] == 4).sum() / n_lab, (ids_m[sel] == rows[sel]).sum() / n_lab,
+            ((ids_m[sel] != 4) & (ids_m[sel] != rows[sel])).sum() / n_lab)
+    per_sample, p_mask, p_keep, p_rand, bad = ref["mask_stats"]
+    assert bad == 0
+    assert abs(mine[0] - per_sample) < 0.15, (mine[0], per_sample)          # ~8.3 unique positions out of 9 draws
+    for a, b in zip(mine[1:], (p_mask, p_keep, p_rand)):
+        assert abs(a - b) < 0.012, (mine, ref["mask_stats"])
