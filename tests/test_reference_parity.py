@@ -289,6 +289,22 @@ for _ in range(3000):
     n_mask += int((ids_m[sel] == 4).sum()); n_keep += int((ids_m[sel] == base[sel]).sum())
     n_rand += int(((ids_m[sel] != 4) & (ids_m[sel] != base[sel])).sum())
 out["mask_stats"] = (n_lab / 3000.0, n_mask / n_lab, n_keep / n_lab, n_rand / n_lab, bad)
+
+# ---- task models called WITH labels return their loss (src/modeling.py:998-1271)
+lab_tok = torch.randint(0, 5, ids.shape, generator=torch.Generator().manual_seed(2))
+mlm_lab = torch.full_like(ids, -1); mlm_lab[:, 4] = 17; mlm_lab[2, 1] = 8
+with_labels = {}
+for name, ctor, kwargs in (("mlm", lambda: M.BertForMaskedLM(cfg), dict(masked_lm_labels=mlm_lab)),
+                           ("nsp", lambda: M.BertForNextSentencePrediction(cfg), dict(next_sentence_label=torch.tensor([0, 1, 0]))),
+                           ("token", lambda: M.BertForTokenClassification(cfg, 5), dict(labels=lab_tok)),
+                           ("choice", lambda: M.BertForMultipleChoice(cfg, 2), dict(labels=torch.tensor([1, 0, 1])))):
+    torch.manual_seed(9)
+    m = ctor().eval()
+    inp = (ids4, seg4, mask4) if name == "choice" else (ids, seg, mask)
+    with torch.no_grad():
+        y = m(*inp, **kwargs)
+    with_labels[name] = ({k: v.numpy() for k, v in m.state_dict().items()}, float(y if torch.is_tensor(y) else y[0]))
+out["with_labels"] = with_labels
 pickle.dump(out, open(work + "/ref.pkl", "wb"))
 '''
 
@@ -748,3 +764,26 @@ def test_dynamic_masking_statistics_agree(ref):
     assert abs(mine[0] - per_sample) < 0.15, (mine[0], per_sample)          # ~8.3 unique positions out of 9 draws
     for a, b in zip(mine[1:], (p_mask, p_keep, p_rand)):
         assert abs(a - b) < 0.012, (mine, ref["mask_stats"])
+
+
+def test_task_models_with_labels_return_the_same_loss(ref):
+    from bert_pytorch_b200 import BertConfig, models as M
+    cfg = BertConfig.from_dict(MODEL_CFG)
+    ids, seg, mask = (torch.tensor(a) for a in ref["spec"]["inputs"])
+    ids4 = torch.stack([ids, ids.flip(1)], dim=1)
+    seg4, mask4 = torch.stack([seg, seg], dim=1), torch.stack([mask, mask], dim=1)
+    lab_tok = torch.randint(0, 5, ids.shape, generator=torch.Generator().manual_seed(2))
+    mlm_lab = torch.full_like(ids, -1); mlm_lab[:, 4] = 17; mlm_lab[2, 1] = 8
+    cases = {"mlm": (lambda: M.BertForMaskedLM(cfg), dict(masked_lm_labels=mlm_lab)),
+             "nsp": (lambda: M.BertForNextSentencePrediction(cfg), dict(next_sentence_label=torch.tensor([0, 1, 0]))),
+             "token": (lambda: M.BertForTokenClassification(cfg, 5), dict(labels=lab_tok)),
+             "choice": (lambda: M.BertForMultipleChoice(cfg, 2), dict(labels=torch.tensor([1, 0, 1])))}
+    for name, (sd, want) in ref["with_labels"].items():
+        ctor, kwargs = cases[name]
+        m = ctor().eval()
+        m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+        inp = (ids4, seg4, mask4) if name == "choice" else (ids, seg, mask)
+        with torch.no_grad():
+            y = m(*inp, **kwargs)
+        got = float(y if torch.is_tensor(y) else y[0])
+        assert abs(got - want) < 2e-5 * max(1.0, abs(want)), (name, got, want)
