@@ -305,6 +305,31 @@ for name, ctor, kwargs in (("mlm", lambda: M.BertForMaskedLM(cfg), dict(masked_l
         y = m(*inp, **kwargs)
     with_labels[name] = ({k: v.numpy() for k, v in m.state_dict().items()}, float(y if torch.is_tensor(y) else y[0]))
 out["with_labels"] = with_labels
+
+# ---- from_pretrained: directory with bert_config.json + pytorch_model.bin in the OLD naming (gamma / beta), loaded
+#      (a) into the full pre-training model, (b) into a bare encoder (bert. prefix stripped), (c) a task model with extra args
+import os as _os
+pt_dir = work + "/pretrained"
+_os.makedirs(pt_dir, exist_ok=True)
+torch.manual_seed(21)
+src_model = M.BertForPreTraining(cfg)
+old_sd = collections.OrderedDict((k.replace("LayerNorm.weight", "LayerNorm.gamma").replace("LayerNorm.bias", "LayerNorm.beta"), v)
+                                 for k, v in src_model.state_dict().items())
+torch.save(old_sd, pt_dir + "/pytorch_model.bin")
+open(pt_dir + "/bert_config.json", "w").write(cfg.to_json_string())
+fp = {}
+for name, loader in (("pretraining", lambda: M.BertForPreTraining.from_pretrained(pt_dir)),
+                     ("encoder", lambda: M.BertModel.from_pretrained(pt_dir)),
+                     ("token", lambda: M.BertForTokenClassification.from_pretrained(pt_dir, num_labels=5))):
+    torch.manual_seed(33)                           # the heads that are not in the archive are freshly initialised
+    m = loader().eval()
+    with torch.no_grad():
+        y = m(ids, seg, mask)
+    flat = []
+    for t in (y if isinstance(y, (tuple, list)) else [y]):
+        flat += [u.numpy() for u in (t if isinstance(t, (tuple, list)) else [t]) if torch.is_tensor(u)]
+    fp[name] = flat
+out["from_pretrained"] = fp
 pickle.dump(out, open(work + "/ref.pkl", "wb"))
 '''
 
@@ -787,3 +812,28 @@ def test_task_models_with_labels_return_the_same_loss(ref):
             y = m(*inp, **kwargs)
         got = float(y if torch.is_tensor(y) else y[0])
         assert abs(got - want) < 2e-5 * max(1.0, abs(want)), (name, got, want)
+
+
+def test_from_pretrained_agrees(ref):
+    """A reference-written archive directory in the old gamma / beta naming loads through ``from_pretrained`` into the full
+    model, a bare encoder (``bert.`` prefix) and a task model with constructor arguments -- same outputs."""
+    from bert_pytorch_b200 import models as M
+    pt_dir = os.path.join(ref["work"], "pretrained")
+    ids, seg, mask = (torch.tensor(a) for a in ref["spec"]["inputs"])
+    loaders = {"pretraining": lambda: M.BertForPreTraining.from_pretrained(pt_dir),
+               "encoder": lambda: M.BertModel.from_pretrained(pt_dir),
+               "token": lambda: M.BertForTokenClassification.from_pretrained(pt_dir, num_labels=5)}
+    for name, want in ref["from_pretrained"].items():
+        torch.manual_seed(33)
+        m = loaders[name]().eval()
+        with torch.no_grad():
+            y = m(ids, seg, mask)
+        flat = []
+        for t in (y if isinstance(y, (tuple, list)) else [y]):
+            flat += [u for u in (t if isinstance(t, (tuple, list)) else [t]) if torch.is_tensor(u)]
+        assert len(flat) == len(want), name
+        for a, b in zip(flat, want):
+            if name == "token":                     # the classifier is freshly initialised on both sides: shapes only
+                assert a.shape == b.shape
+            else:
+                assert np.allclose(a.numpy(), b, atol=2e-5, rtol=1e-4), (name, np.abs(a.numpy() - b).max())
