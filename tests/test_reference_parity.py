@@ -837,3 +837,39 @@ def test_from_pretrained_agrees(ref):
                 assert a.shape == b.shape
             else:
                 assert np.allclose(a.numpy(), b, atol=2e-5, rtol=1e-4), (name, np.abs(a.numpy() - b).max())
+
+
+def test_shard_writer_agrees(tmp_path):
+    """utils/encode_data.py:write_samples_to_hdf5 (the reference, writing through the h5py stand-in = this repo's HDF5
+    writer) and data/encode.py write the same three datasets for the same samples (the reference pops from the end of the
+    list, so its rows come out reversed)."""
+    import importlib.util
+    ref_utils = next((p for p in (os.path.join(REF, "utils"), "/root/reference/utils")
+                      if os.path.isfile(os.path.join(p, "encode_data.py"))), None)
+    if ref_utils is None:
+        pytest.skip("the reference's utils/ directory is not available")
+    sys.path.insert(0, os.path.join(ROOT, "baseline", "shims"))
+    try:
+        spec = importlib.util.spec_from_file_location("ref_encode_data3", os.path.join(ref_utils, "encode_data.py"))
+        E = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(E)
+    finally:
+        sys.path.pop(0)
+    from bert_pytorch_b200.data import encode, hdf5
+
+    class Tok:                                            # "t17" -> 17, specials like a real vocabulary
+        def token_to_id(self, t):
+            return {"[CLS]": 101, "[SEP]": 102}.get(t) or int(t[1:])
+    raw = [([5, 6, 7], [8, 9], True), ([10], [11, 12, 13, 14], False), ([20, 21, 22, 23, 24], [25], False)]
+    for nsp in (True, False):
+        ref_samples = [E.TrainingSample([f"t{x}" for x in a], [f"t{x}" for x in b] if nsp else None, r and nsp) for a, b, r in raw]
+        mine = [encode.TrainingSample(list(a), list(b) if nsp else None, r and nsp) for a, b, r in raw]
+        fa, fb = str(tmp_path / f"ref_{nsp}.hdf5"), str(tmp_path / f"mine_{nsp}.hdf5")
+        E.write_samples_to_hdf5(fa, list(ref_samples), Tok(), 16)
+        encode.write_samples_to_hdf5(fb, mine, 16, 101, 102)
+        with hdf5.File(fa, "r") as A, hdf5.File(fb, "r") as B:
+            assert sorted(A.keys()) == sorted(B.keys()) == ["input_ids", "next_sentence_labels", "special_token_positions"]
+            for k in A.keys():
+                a, b = A[k][:], B[k][:]
+                assert a.dtype == b.dtype and a.shape == b.shape, (k, a.dtype, b.dtype, a.shape, b.shape)
+                assert np.array_equal(a[::-1], b), k
