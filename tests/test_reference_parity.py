@@ -330,6 +330,18 @@ for name, loader in (("pretraining", lambda: M.BertForPreTraining.from_pretraine
         flat += [u.numpy() for u in (t if isinstance(t, (tuple, list)) else [t]) if torch.is_tensor(u)]
     fp[name] = flat
 out["from_pretrained"] = fp
+
+# ---- the runtime's micro-step (run_pretraining.py:420-460) with accumulation: loss / divisor, gradients add up
+torch.manual_seed(77)
+net3 = M.BertForPreTraining(cfg0).train()
+net3.load_state_dict({k: torch.from_numpy(v) for k, v in out["train_init"].items()})
+crit3 = RP.BertPretrainingCriterion(cfg0.vocab_size)
+micro_losses = []
+for mstep in range(3):
+    batch = (torch.roll(ids, mstep, 1), seg, mask, lab2, nsl2)
+    micro_losses.append(float(RP.forward_backward_pass(net3, crit3, None, batch, 3, sync_grads=True)))
+out["micro_losses"] = micro_losses
+out["micro_grads"] = {k: p.grad.numpy().copy() for k, p in net3.named_parameters() if p.grad is not None}
 pickle.dump(out, open(work + "/ref.pkl", "wb"))
 '''
 
@@ -873,3 +885,29 @@ def test_shard_writer_agrees(tmp_path):
                 a, b = A[k][:], B[k][:]
                 assert a.dtype == b.dtype and a.shape == b.shape, (k, a.dtype, b.dtype, a.shape, b.shape)
                 assert np.array_equal(a[::-1], b), k
+
+
+def test_runtime_micro_step_accumulation_agrees(ref):
+    """pretrain.forward_backward_pass vs run_pretraining.forward_backward_pass: three accumulated micro-steps with
+    divisor 3 return the same (already divided) losses and leave the same summed gradients."""
+    from bert_pytorch_b200 import BertConfig, models as M, pretrain
+    from bert_pytorch_b200.models.arena import ParamArena
+    from bert_pytorch_b200.parallel import DataParallel
+    from bert_pytorch_b200.parallel.comm import SingleComm
+    cfg0 = BertConfig.from_dict(dict(MODEL_CFG, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0))
+    ids, seg, mask = (torch.tensor(a) for a in ref["spec"]["inputs"])
+    net = M.BertForPreTraining(cfg0).train()
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in ref["train_init"].items()}, strict=True)
+    arena = ParamArena(net)
+    ddp = DataParallel(net, comm=SingleComm(), arena=arena)
+    crit = M.BertPretrainingCriterion(cfg0.vocab_size)
+    lab = torch.full_like(ids, -1); lab[:, 2] = 9; lab[:, 7] = 30; lab[0, 11] = 5
+    nsl = torch.tensor([1, 0, 1])
+    for mstep, want in enumerate(ref["micro_losses"]):
+        batch = (torch.roll(ids, mstep, 1), seg, mask, lab, nsl)
+        loss = pretrain.forward_backward_pass(ddp, crit, None, batch, 3, sync_grads=(mstep == 2), compute_dtype=torch.float32)
+        assert abs(float(loss) - want) < 2e-5 * max(1.0, abs(want)), (mstep, float(loss), want)
+    for k, p in net.named_parameters():
+        if k in ref["micro_grads"]:
+            g = ref["micro_grads"][k]
+            assert np.allclose(p.grad.numpy(), g, atol=2e-6 + 1e-4 * np.abs(g).max()), k
