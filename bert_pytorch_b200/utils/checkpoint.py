@@ -58,6 +58,9 @@ def override_optimizer_hparams(ckpt: Dict[str, Any], *, global_steps: int, max_s
         g["t_total"] = max_steps
         g["warmup"] = warmup
         g["lr"] = lr
+        # the reference leaves the scheduler's ``initial_lr`` of the old phase in place, so its new schedule keeps
+        # decaying from the OLD base LR although ``lr`` was just overwritten (tests/test_reference_parity.py);
+        # dropping it makes the new phase start from the configured learning rate
         g.pop("initial_lr", None)
 
 

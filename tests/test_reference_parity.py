@@ -342,6 +342,25 @@ for mstep in range(3):
     micro_losses.append(float(RP.forward_backward_pass(net3, crit3, None, batch, 3, sync_grads=True)))
 out["micro_losses"] = micro_losses
 out["micro_grads"] = {k: p.grad.numpy().copy() for k, p in net3.named_parameters() if p.grad is not None}
+
+# ---- optimizer set-up and the resume surgery of run_pretraining.prepare_optimizers (phase 1 -> phase 2)
+import copy as _copy
+net4 = M.BertForPreTraining(cfg0)
+a1 = types.SimpleNamespace(lr_decay="poly", learning_rate=6e-3, warmup_proportion=0.25, max_steps=8, fp16=False, kfac=False,
+                           resume_step=0, previous_phase_end_step=0)
+opt4, _, sch4, _ = RP.prepare_optimizers(a1, net4, None, 0)
+names = dict((id(p), n) for n, p in net4.named_parameters())
+out["opt_groups"] = [(g["weight_decay"], sorted(names[id(p)] for p in g["params"])) for g in opt4.param_groups]
+for _ in range(4):
+    for p_ in net4.parameters(): p_.grad = torch.ones_like(p_) * 0.01
+    sch4[0].step(); opt4.step()
+ck4 = {"optimizer": _copy.deepcopy(opt4.state_dict())}
+a2 = types.SimpleNamespace(lr_decay="poly", learning_rate=4e-3, warmup_proportion=0.5, max_steps=10, fp16=False, kfac=False,
+                           resume_step=4, previous_phase_end_step=4)
+opt5, _, sch5, _ = RP.prepare_optimizers(a2, net4, ck4, 0)
+out["resumed_group"] = {k: v for k, v in opt5.param_groups[0].items() if k != "params"}
+out["resumed_base_lrs"] = list(sch5[0].base_lrs)
+out["resumed_state_steps"] = sorted({int(st["step"]) for st in opt5.state_dict()["state"].values()})
 pickle.dump(out, open(work + "/ref.pkl", "wb"))
 '''
 
@@ -911,3 +930,40 @@ def test_runtime_micro_step_accumulation_agrees(ref):
         if k in ref["micro_grads"]:
             g = ref["micro_grads"][k]
             assert np.allclose(p.grad.numpy(), g, atol=2e-6 + 1e-4 * np.abs(g).max()), k
+
+
+def test_optimizer_groups_and_resume_surgery(ref):
+    """pretrain.prepare_optimizers vs run_pretraining.prepare_optimizers: the same decay / no-decay parameter groups, and
+    on a phase-1 -> phase-2 resume the same surgery (step counters reset, t_total / warmup / lr overwritten).  One
+    deliberate difference: the reference leaves the scheduler's ``initial_lr`` of the checkpoint in place, so its
+    phase 2 decays from the PHASE-1 learning rate although ``lr`` was overwritten; here phase 2 starts from its own."""
+    import copy
+    import types
+    from bert_pytorch_b200 import BertConfig, models as M, pretrain
+    from bert_pytorch_b200.models.arena import ParamArena
+    from bert_pytorch_b200.parallel import DataParallel
+    from bert_pytorch_b200.parallel.comm import SingleComm
+    cfg0 = BertConfig.from_dict(dict(MODEL_CFG, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0))
+    net = M.BertForPreTraining(cfg0)
+    ddp = DataParallel(net, comm=SingleComm(), arena=ParamArena(net))
+    base = dict(lr_decay="poly", fp16=False, kfac=False, device_obj=torch.device("cpu"))
+    a1 = types.SimpleNamespace(learning_rate=6e-3, warmup_proportion=0.25, max_steps=8, resume_step=0, previous_phase_end_step=0, **base)
+    opt, _, sch, _ = pretrain.prepare_optimizers(a1, ddp, None, 0)
+    names = dict((id(p), n) for n, p in net.named_parameters())
+    mine = [(g["weight_decay"], sorted(names[id(p)] for p in g["params"])) for g in opt.param_groups]
+    assert mine == ref["opt_groups"]
+    for _ in range(4):
+        for p in net.parameters():
+            p.grad.fill_(0.01) if p.grad is not None else None
+        sch[0].step(); opt.step()
+    ck = {"optimizer": copy.deepcopy(opt.state_dict())}
+    a2 = types.SimpleNamespace(learning_rate=4e-3, warmup_proportion=0.5, max_steps=10, resume_step=4, previous_phase_end_step=4, **base)
+    net2 = M.BertForPreTraining(cfg0)
+    ddp2 = DataParallel(net2, comm=SingleComm(), arena=ParamArena(net2))
+    opt2, _, sch2, _ = pretrain.prepare_optimizers(a2, ddp2, ck, 0)
+    g, want = opt2.param_groups[0], ref["resumed_group"]
+    for k in ("step", "t_total", "warmup", "weight_decay", "betas", "eps", "bias_correction", "grad_averaging", "max_grad_norm"):
+        assert g[k] == want[k] or tuple(g[k]) == tuple(want[k]), (k, g[k], want[k])
+    assert sorted({int(st["step"]) for st in opt2.state_dict()["state"].values()}) == ref["resumed_state_steps"] == [0]
+    assert ref["resumed_base_lrs"] == [6e-3, 6e-3] and want["initial_lr"] == 6e-3      # the reference keeps phase 1's base LR
+    assert list(sch2[0].base_lrs) == [4e-3, 4e-3]                                       # this repo uses the configured one
