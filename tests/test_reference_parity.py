@@ -30,6 +30,24 @@ VOCAB = ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]", "the", "capital", "of", "
          "william", "shakespeare", "##s", "##ing", "un", "##aff", "##able", ",", "-", "'", "1603", "in", "and", "it"]
 TEXTS = ["The capital of France is Paris.", "  Hello,\tWORLD!! unaffable-playing  ", "naïve café — 東京 is big",
          "Who wrote Hamlet? William Shakespeare's play, in 1603.", "", "x" * 120]
+
+
+def _fuzz_texts(n=250, seed=13):
+    """Random strings over Latin / accented / CJK / punctuation / control / whitespace code points."""
+    import random
+    rnd = random.Random(seed)
+    pools = ["abcdefghijklmnopqrstuvwxyz", "ABCDEFGHIJKLMNOPQRSTUVWXYZ", "0123456789", " \t\n\r\u00a0\u2003", ".,;:!?'\"()[]{}-_/\\@#$%^&*+=<>|~`",
+             "\u00e9\u00e8\u00fc\u00f1\u00e7\u00df\u00f8\u0142\u0159\u015f", "\u4e2d\u6587\u6f22\u5b57\u6771\u4eac", "\u3042\u3044\u30a2\u30a4", "\uac00\ub098",
+             "\u0430\u0431\u0432\u0433\u0414\u0416", "\u03b1\u03b2\u03b3\u0394", "\u0627\u0644\u0639", "\u0000\u0007\ufffd\u200b\u200d\u00ad", "\u2014\u2013\u2018\u2019\u201c\u201d\u2026\u20ac",
+             "\u0301\u0308\u0327", "\U0001f600\U0001f680"]
+    out = []
+    for _ in range(n):
+        k = rnd.randint(1, 40)
+        out.append("".join(rnd.choice(rnd.choice(pools)) for _ in range(k)))
+    return out
+
+
+TEXTS = TEXTS + _fuzz_texts()
 SQUAD = {"version": "1.1", "data": [{"title": "t", "paragraphs": [
     {"context": "The capital of France is Paris. The river Seine flows through Paris and it is a river.",
      "qas": [{"id": "q1", "question": "What is the capital of France?", "answers": [{"text": "Paris", "answer_start": 25}]},
@@ -387,7 +405,16 @@ def ref(tmp_path_factory):
     (work / "squad2.json").write_text(json.dumps(v2))
     from bert_pytorch_b200.data import synthetic
     shards = synthetic.write_shards(str(work / "shards"), 3, 7, 16, 100, True, seed=3)
-    pairs = [("paris", "Paris."), ("william shakespeare", "William   Shakespeare's"), ("1603", "(1603)."), ("seine", "the Seine,"),
+    import random as _r
+    rr = _r.Random(3)
+    fuzz_pairs = []
+    for t in _fuzz_texts(120, seed=29):
+        words = t.split()
+        if not words:
+            continue
+        i = rr.randrange(len(words)); j = rr.randrange(i, min(len(words), i + 3))
+        fuzz_pairs.append((" ".join(w.lower().strip(".,!?") for w in words[i:j + 1]), " ".join(words[max(0, i - 1):j + 2])))
+    pairs = fuzz_pairs + [("paris", "Paris."), ("william shakespeare", "William   Shakespeare's"), ("1603", "(1603)."), ("seine", "the Seine,"),
              ("x y", "completely different")]
     spec = dict(shards=shards, final_text_pairs=pairs, cfg=MODEL_CFG, inputs=[ids.tolist(), seg.tolist(), mask.tolist()], texts=TEXTS, ner_labels=NER_LABELS,
                 pretrain_argvs=argvs, ner_argv=["--train_file", "t.txt", "--labels", "O", "B-X", "--model_config_file", "m.json", "--model_checkpoint", "c.pt"],
