@@ -60,6 +60,31 @@ NER_TEXT = ("-DOCSTART- -X- -X- O\n\nWilliam NNP B-NP B-PER\nShakespeare NNP I-N
             "in IN B-PP O\nParis NNP B-NP B-LOC\n.\t.\tO\tO\n\nThe DT B-NP O\nriver NN I-NP O\nSeine NNP I-NP B-LOC\nflows VBZ B-VP O\n"
             "through IN B-PP O\nParis NNP B-NP B-LOC\nand CC O O\nit PRP B-NP O\nis VBZ B-VP O\na DT B-NP O\nriver NN I-NP O\n. . O O\n")
 
+
+
+def _random_squad(n_par=12, seed=17):
+    """Long random paragraphs over the toy vocabulary (several sliding windows each) with exact answer offsets."""
+    import random
+    rnd = random.Random(seed)
+    words = [w for w in VOCAB if w.isalpha()] + ["Paris,", "(1603)", "river-bank", "Seine's", "unaffable."]
+    pars = []
+    for p_i in range(n_par):
+        ctx_words = [rnd.choice(words) for _ in range(rnd.randint(30, 90))]
+        ctx = " ".join(ctx_words)
+        qas = []
+        for q_i in range(rnd.randint(1, 3)):
+            i = rnd.randrange(len(ctx_words)); j = min(len(ctx_words) - 1, i + rnd.randint(0, 3))
+            start = len(" ".join(ctx_words[:i])) + (1 if i else 0)
+            text = " ".join(ctx_words[i:j + 1])
+            assert ctx[start:start + len(text)] == text
+            qas.append({"id": f"r{p_i}_{q_i}", "question": " ".join(rnd.choice(words) for _ in range(rnd.randint(3, 15))) + "?",
+                        "answers": [{"text": text, "answer_start": start}]})
+        pars.append({"context": ctx, "qas": qas})
+    return pars
+
+
+SQUAD["data"][0]["paragraphs"] += _random_squad()
+
 REF_SCRIPT = r'''
 import collections, json, os, pickle, sys, types
 import numpy as np, torch
@@ -731,7 +756,7 @@ def test_run_squad_predict_cli_end_to_end(ref, tmp_path):
     finetune_squad.main([*common, "--output_dir", str(tmp_path / "my_out")])
     a = json.load(open(tmp_path / "ref_out" / "predictions.json"))
     b = json.load(open(tmp_path / "my_out" / "predictions.json"))
-    assert a == b and set(a) == {"q1", "q2", "q3"}
+    assert a == b and {"q1", "q2", "q3"} <= set(a) and len(a) >= 15
     na = json.load(open(tmp_path / "ref_out" / "nbest_predictions.json"))
     nb = json.load(open(tmp_path / "my_out" / "nbest_predictions.json"))
     for k in na:
