@@ -404,6 +404,16 @@ opt5, _, sch5, _ = RP.prepare_optimizers(a2, net4, ck4, 0)
 out["resumed_group"] = {k: v for k, v in opt5.param_groups[0].items() if k != "params"}
 out["resumed_base_lrs"] = list(sch5[0].base_lrs)
 out["resumed_state_steps"] = sorted({int(st["step"]) for st in opt5.state_dict()["state"].values()})
+
+# ---- legacy pre-masked shards (NVIDIA format, src/dataset.py:183-192): no randomness -> every field is comparable;
+#      plus a missing and a corrupt file in the list (skipped with a warning)
+import warnings as _w
+with _w.catch_warnings():
+    _w.simplefilter("ignore")
+    dleg = D.ShardedPretrainingDataset(sorted(spec["legacy_shards"]) + [work + "/does_not_exist.hdf5", work + "/vocab.txt"],
+                                       4, 5, 0.2, vocab_size=100)
+out["legacy_len"] = len(dleg)
+out["legacy_rows"] = [[np.asarray(a).tolist() for a in dleg[i]] for i in range(len(dleg))]
 pickle.dump(out, open(work + "/ref.pkl", "wb"))
 '''
 
@@ -439,9 +449,30 @@ def ref(tmp_path_factory):
             continue
         i = rr.randrange(len(words)); j = rr.randrange(i, min(len(words), i + 3))
         fuzz_pairs.append((" ".join(w.lower().strip(".,!?") for w in words[i:j + 1]), " ".join(words[max(0, i - 1):j + 2])))
+    from bert_pytorch_b200.data import hdf5 as _h5
+    legacy = []
+    lr_ = np.random.default_rng(21)
+    for k in range(2):
+        n = 5 + k
+        lids = lr_.integers(5, 100, size=(n, 16)).astype(np.int32)
+        lens = lr_.integers(6, 16, size=n)
+        lmask = (np.arange(16)[None, :] < lens[:, None]).astype(np.int32)
+        lids *= lmask
+        lseg = ((np.arange(16)[None, :] >= (lens // 2)[:, None]) & (lmask == 1)).astype(np.int32)
+        lpos = np.zeros((n, 4), dtype=np.int32); lmid = np.zeros((n, 4), dtype=np.int32)
+        for r_ in range(n):
+            cnt = int(lr_.integers(1, 4))
+            lpos[r_, :cnt] = np.sort(lr_.choice(np.arange(1, lens[r_]), size=cnt, replace=False))
+            lmid[r_, :cnt] = lr_.integers(5, 100, size=cnt)
+        path = str(work / f"legacy_{k}.hdf5")
+        with _h5.File(path, "w") as f:
+            for name, arr in (("input_ids", lids), ("segment_ids", lseg), ("input_mask", lmask), ("masked_lm_positions", lpos),
+                              ("masked_lm_ids", lmid), ("next_sentence_labels", lr_.integers(0, 2, size=n).astype(np.int8))):
+                f.create_dataset(name, data=arr, dtype=arr.dtype.str[1:], compression="gzip")
+        legacy.append(path)
     pairs = fuzz_pairs + [("paris", "Paris."), ("william shakespeare", "William   Shakespeare's"), ("1603", "(1603)."), ("seine", "the Seine,"),
              ("x y", "completely different")]
-    spec = dict(shards=shards, final_text_pairs=pairs, cfg=MODEL_CFG, inputs=[ids.tolist(), seg.tolist(), mask.tolist()], texts=TEXTS, ner_labels=NER_LABELS,
+    spec = dict(shards=shards, legacy_shards=legacy, final_text_pairs=pairs, cfg=MODEL_CFG, inputs=[ids.tolist(), seg.tolist(), mask.tolist()], texts=TEXTS, ner_labels=NER_LABELS,
                 pretrain_argvs=argvs, ner_argv=["--train_file", "t.txt", "--labels", "O", "B-X", "--model_config_file", "m.json", "--model_checkpoint", "c.pt"],
                 ref_utils=ref_utils)
     (work / "ner.txt").write_text(NER_TEXT)
@@ -1023,3 +1054,20 @@ def test_optimizer_groups_and_resume_surgery(ref):
     assert sorted({int(st["step"]) for st in opt2.state_dict()["state"].values()}) == ref["resumed_state_steps"] == [0]
     assert ref["resumed_base_lrs"] == [6e-3, 6e-3] and want["initial_lr"] == 6e-3      # the reference keeps phase 1's base LR
     assert list(sch2[0].base_lrs) == [4e-3, 4e-3]                                       # this repo uses the configured one
+
+
+def test_legacy_premasked_shards_agree(ref):
+    """Shards in the NVIDIA pre-masked layout (no dynamic masking, nothing random): all five outputs of every sample are
+    identical, and a missing / unreadable file in the list is skipped by both."""
+    import warnings
+    from bert_pytorch_b200.data.dataset import ShardedPretrainingDataset
+    work = ref["work"]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ds = ShardedPretrainingDataset(sorted(ref["spec"]["legacy_shards"]) + [os.path.join(work, "does_not_exist.hdf5"),
+                                                                                os.path.join(work, "vocab.txt")],
+                                       4, 5, 0.2, vocab_size=100)
+    assert len(ds) == ref["legacy_len"] == 11
+    for i, want in enumerate(ref["legacy_rows"]):
+        got = [np.asarray(a).tolist() for a in ds[i]]
+        assert got == want, i
