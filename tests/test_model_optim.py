@@ -207,3 +207,26 @@ def test_gradient_clipper():
     total = GradientClipper(1.0).step(ps)
     assert math.isclose(float(total), 6.0, rel_tol=1e-5)
     assert math.isclose(math.sqrt(sum(float(p.grad.pow(2).sum()) for p in ps)), 1.0, rel_tol=1e-4)
+
+
+def test_grad_scaler_matches_torch_amp_grad_scaler():
+    """Step by step against torch.amp.GradScaler (what the reference uses, run_pretraining.py:316): the same scale
+    trajectory, the same skipped updates on overflow, the same state dict."""
+    from bert_pytorch_b200.optim import GradScaler
+    if not hasattr(torch.amp, "GradScaler"):
+        pytest.skip("torch.amp.GradScaler is not available in this torch build")
+    ts = torch.amp.GradScaler("cpu", init_scale=1024.0, growth_interval=3)
+    ms = GradScaler(init_scale=1024.0, growth_interval=3, device=torch.device("cpu"))
+    p1, p2 = torch.nn.Parameter(torch.ones(3)), torch.nn.Parameter(torch.ones(3))
+    o1, o2 = torch.optim.SGD([p1], lr=0.1), torch.optim.SGD([p2], lr=0.1)
+    for i, bad in enumerate([0, 0, 0, 1, 0, 0, 0, 0, 1, 1, 0, 0, 0, 0, 0, 0]):
+        for s, o, p in ((ts, o1, p1), (ms, o2, p2)):
+            o.zero_grad()
+            s.scale((p * 2).sum()).backward()
+            if bad:
+                p.grad[0] = float("inf")
+            s.step(o)
+            s.update()
+        assert ts.get_scale() == ms.get_scale(), i
+        assert torch.equal(p1.data, p2.data), i
+    assert ts.state_dict() == ms.state_dict()
