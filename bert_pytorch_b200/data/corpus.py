@@ -233,6 +233,10 @@ def build_vocab(input_files: Sequence[str], output: str, size: int = 30000, toke
     with open(output, "w", encoding="utf-8") as f:
         for w in vocab:
             f.write(w + "\n")
+    if tokenizer == "bpe":
+        # a byte-level BPE model is vocab.json + merges.txt (the word list alone cannot tokenise): written next to the
+        # list; pass .../vocab.json as ``vocab_file`` to the encoder / runners
+        tok.save_model(os.path.dirname(os.path.abspath(output)))
     return vocab
 
 

@@ -209,9 +209,10 @@ def encode_file(input_file: str, output_file: str, vocab_file: str, tokenizer_ki
         raise ValueError("the vocabulary must contain [CLS] and [SEP]")
     print(f"[encoder] Creating instances from {input_file}", flush=True)
     fast = None
-    if tokenizer_kind == "wordpiece" and os.environ.get("B200_NATIVE_TOKENIZER", "1") != "0":
-        from .tokenization import FastWordPiece
-        fast = FastWordPiece(vocab_file, do_lower_case=not uppercase)
+    if os.environ.get("B200_NATIVE_TOKENIZER", "1") != "0":      # native C++ encoders (identical ids, tests/test_dataset.py)
+        from .tokenization import FastBPE, FastWordPiece
+        fast = (FastWordPiece(vocab_file, do_lower_case=not uppercase) if tokenizer_kind == "wordpiece"
+                else FastBPE(vocab_file, lowercase=not uppercase))
         if fast.native is None:
             fast = None
     docs = read_documents(input_file, tok, fast=fast)

@@ -10,6 +10,7 @@
 from __future__ import annotations
 
 import collections
+import os
 import unicodedata
 from typing import Dict, Iterable, List, Optional
 
@@ -22,11 +23,15 @@ def get_wordpiece_tokenizer(vocab_file: str, uppercase: bool = False):
 
 def get_bpe_tokenizer(vocab_file: str, uppercase: bool = False):
     import tokenizers
+    # the reference passes only ``vocab`` (src/tokenization.py:51-57), which current `tokenizers` releases turn into an
+    # EMPTY model; here the merges file written next to vocab.json by utils/build_vocab.py is loaded as well.  Same
+    # options as the reference: add_prefix_space=True, trim_offsets=True.
     merges = vocab_file.replace("vocab.json", "merges.txt") if vocab_file.endswith("vocab.json") else None
     try:
-        return tokenizers.ByteLevelBPETokenizer(vocab_file, merges, lowercase=not uppercase)
+        return tokenizers.ByteLevelBPETokenizer(vocab_file, merges, add_prefix_space=True, lowercase=not uppercase,
+                                                trim_offsets=True)
     except TypeError:
-        return tokenizers.ByteLevelBPETokenizer(vocab_file, lowercase=not uppercase)
+        return tokenizers.ByteLevelBPETokenizer(vocab_file, add_prefix_space=True, lowercase=not uppercase, trim_offsets=True)
 
 
 def load_vocab(vocab_file: str) -> "collections.OrderedDict[str, int]":
@@ -259,3 +264,63 @@ class FastWordPiece:
 
     def encode(self, text: str) -> List[int]:
         return self.encode_batch([text])[0]
+
+
+def _bpe_categories() -> "np.ndarray":
+    """Category per BMP code point for the GPT-2 pre-tokenisation pattern: 1 = \\p{L}, 2 = \\p{N}, 3 = \\s, 0 = rest."""
+    import numpy as np
+    cat = np.zeros(0x10000, dtype=np.uint8)
+    for cp in range(0x10000):
+        ch = chr(cp)
+        c = unicodedata.category(ch)
+        if c[0] == "L":
+            cat[cp] = 1
+        elif c[0] == "N":
+            cat[cp] = 2
+        elif ch.isspace() and cp not in (0x1C, 0x1D, 0x1E, 0x1F):
+            cat[cp] = 3
+    return cat
+
+
+class FastBPE:
+    """Byte-level BPE ids for bulk encoding (``--tokenizer bpe`` shards): lines made of BMP characters go through the
+    native C++ encoder (``ops/csrc/host.cpp: bpe_*``), the rest -- and everything when the helper is not built --
+    through ``fallback`` (the ``tokenizers`` package).  ``vocab_file`` is the ``vocab.json`` written by the vocabulary
+    builder, with ``merges.txt`` next to it."""
+
+    def __init__(self, vocab_file: str, lowercase: bool = True, add_prefix_space: bool = True):
+        import json
+        self.lowercase, self.add_prefix_space = lowercase, add_prefix_space
+        self.native = None
+        try:
+            merges_file = os.path.join(os.path.dirname(vocab_file), "merges.txt")
+            with open(vocab_file, "r", encoding="utf-8") as f:
+                vocab = json.load(f)
+            tokens = sorted(vocab, key=vocab.get)
+            if [vocab[t] for t in tokens] != list(range(len(tokens))) or any("\n" in t for t in tokens):
+                return
+            with open(merges_file, "r", encoding="utf-8") as f:
+                merges = [l.rstrip("\n") for l in f if l.strip() and not l.startswith("#version")]
+            from ..ops import native_host
+            host = native_host.load_or_none()
+            if host is not None:
+                self.native = native_host.BpeEncoder(host, tokens, merges, _bpe_categories())
+        except Exception:
+            self.native = None
+
+    def encode_batch(self, texts: List[str], fallback) -> List[List[int]]:
+        out: List[Optional[List[int]]] = [None] * len(texts)
+        if self.native is not None and texts:
+            # lower-casing happens here (str.lower == the normaliser of the `tokenizers` package except for the
+            # context dependent capital sigma / dotted capital I: such lines take the fallback)
+            take = [i for i, t in enumerate(texts) if not (self.lowercase and ("\u03a3" in t or "\u0130" in t))]
+            prepared = [texts[i].lower() if self.lowercase else texts[i] for i in take]
+            if self.add_prefix_space:          # ByteLevel(add_prefix_space=True): a space in front unless there is one
+                prepared = [t if (not t or t.startswith(" ")) else " " + t for t in prepared]
+            for i, ids in zip(take, self.native.encode_batch(prepared)):
+                if ids is not None:
+                    out[i] = ids.tolist()
+        for i, t in enumerate(texts):
+            if out[i] is None:
+                out[i] = list(fallback(t))
+        return out  # type: ignore[return-value]

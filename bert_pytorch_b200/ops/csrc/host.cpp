@@ -11,6 +11,7 @@
 // zlib is linked as libz.so.1 with hand-declared prototypes (the image ships no zlib.h).
 #include <algorithm>
 #include <atomic>
+#include <climits>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -238,6 +239,116 @@ bool encode_text(const WordPiece& wp, const unsigned char* s, int64_t n, std::ve
   return true;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// byte-level BPE (GPT-2 / RoBERTa style, the `tokenizers.ByteLevelBPETokenizer` the reference offers with
+// --tokenizer bpe): pre-tokenisation by the GPT-2 pattern
+//   's|'t|'re|'ve|'m|'ll|'d| ?\p{L}+| ?\p{N}+| ?[^\s\p{L}\p{N}]+|\s+(?!\S)|\s+
+// over a caller-supplied category table (BMP), bytes -> printable code points, then rank-ordered merges.
+// ------------------------------------------------------------------------------------------------
+enum : uint8_t { CAT_OTHER = 0, CAT_LETTER = 1, CAT_NUMBER = 2, CAT_SPACE = 3 };
+
+struct Bpe {
+  std::unordered_map<std::string, int32_t> vocab;   // token (in the byte-level alphabet, UTF-8) -> id
+  std::unordered_map<std::string, int32_t> ranks;   // left + '\x01' + right -> merge rank
+  std::vector<uint8_t> cat;                         // category per BMP code point
+  std::string byte_str[256];                        // byte -> UTF-8 of its printable stand-in
+};
+
+static void append_utf8(std::string& s, uint32_t cp) {
+  if (cp < 0x80) s.push_back((char)cp);
+  else if (cp < 0x800) { s.push_back((char)(0xC0 | (cp >> 6))); s.push_back((char)(0x80 | (cp & 63))); }
+  else { s.push_back((char)(0xE0 | (cp >> 12))); s.push_back((char)(0x80 | ((cp >> 6) & 63))); s.push_back((char)(0x80 | (cp & 63))); }
+}
+
+// merges of one pre-token given as its byte-level symbols
+static bool bpe_word(const Bpe& bpe, std::vector<std::string>& sym, std::vector<int32_t>& out) {
+  std::string key;
+  while (sym.size() > 1) {
+    int32_t best = INT32_MAX;
+    for (size_t i = 0; i + 1 < sym.size(); ++i) {
+      key.assign(sym[i]); key.push_back('\x01'); key.append(sym[i + 1]);
+      auto it = bpe.ranks.find(key);
+      if (it != bpe.ranks.end() && it->second < best) best = it->second;
+    }
+    if (best == INT32_MAX) break;
+    std::vector<std::string> next;
+    next.reserve(sym.size());
+    for (size_t i = 0; i < sym.size();) {                    // merge every occurrence of the best pair, left to right
+      if (i + 1 < sym.size()) {
+        key.assign(sym[i]); key.push_back('\x01'); key.append(sym[i + 1]);
+        auto it = bpe.ranks.find(key);
+        if (it != bpe.ranks.end() && it->second == best) { next.push_back(sym[i] + sym[i + 1]); i += 2; continue; }
+      }
+      next.push_back(sym[i]);
+      ++i;
+    }
+    sym.swap(next);
+  }
+  for (const auto& t : sym) {
+    auto it = bpe.vocab.find(t);
+    if (it == bpe.vocab.end()) return false;
+    out.push_back(it->second);
+  }
+  return true;
+}
+
+static bool bpe_encode_text(const Bpe& bpe, const unsigned char* s, int64_t n, std::vector<int32_t>& out) {
+  // decode to (code point, byte offset) so that the pattern can be applied on characters
+  std::vector<uint32_t> cp;
+  std::vector<int64_t> off;
+  for (int64_t i = 0; i < n;) {
+    const unsigned char c = s[i];
+    uint32_t v; int len;
+    if (c < 0x80) { v = c; len = 1; }
+    else if ((c >> 5) == 6 && i + 1 < n) { v = ((c & 31u) << 6) | (s[i + 1] & 63u); len = 2; }
+    else if ((c >> 4) == 14 && i + 2 < n) { v = ((c & 15u) << 12) | ((s[i + 1] & 63u) << 6) | (s[i + 2] & 63u); len = 3; }
+    else return false;                                       // outside the BMP / malformed: caller falls back
+    if (v >= bpe.cat.size()) return false;
+    cp.push_back(v); off.push_back(i); i += len;
+  }
+  off.push_back(n);
+  const size_t m = cp.size();
+  auto cat = [&](size_t k) { return bpe.cat[cp[k]]; };
+  std::vector<std::string> sym;
+  auto emit = [&](size_t a, size_t b) -> bool {             // characters [a, b) form one pre-token
+    sym.clear();
+    for (int64_t k = off[a]; k < off[b]; ++k) sym.push_back(bpe.byte_str[s[k]]);
+    return bpe_word(bpe, sym, out);
+  };
+  size_t i = 0;
+  while (i < m) {
+    // 's|'t|'re|'ve|'m|'ll|'d
+    if (cp[i] == '\'' && i + 1 < m) {
+      const uint32_t a = cp[i + 1], b = i + 2 < m ? cp[i + 2] : 0;
+      size_t len = 0;
+      if (a == 's' || a == 't' || a == 'm' || a == 'd') len = 2;
+      else if ((a == 'r' && b == 'e') || (a == 'v' && b == 'e') || (a == 'l' && b == 'l')) len = 3;
+      if (len) { if (!emit(i, i + len)) return false; i += len; continue; }
+    }
+    //  ?\p{L}+ |  ?\p{N}+ |  ?[^\s\p{L}\p{N}]+
+    {
+      const size_t j = (cp[i] == ' ' && i + 1 < m) ? i + 1 : i;
+      if (j < m && cat(j) != CAT_SPACE) {
+        const uint8_t kind = cat(j);
+        size_t e = j;
+        while (e < m && cat(e) == kind) ++e;
+        if (!emit(i, e)) return false;
+        i = e;
+        continue;
+      }
+    }
+    // \s+(?!\S) | \s+      (here cp[i] is white space)
+    {
+      size_t e = i;
+      while (e < m && cat(e) == CAT_SPACE) ++e;
+      if (e < m && e - i > 1) --e;                           // leave the last one for the next token's optional space
+      if (!emit(i, e)) return false;
+      i = e;
+    }
+  }
+  return true;
+}
 }  // namespace
 
 extern "C" {
@@ -275,6 +386,64 @@ int64_t wp_encode_batch(void* h, const char* buf, const int64_t* offs, int64_t n
   parallel_for(n, threads, [&](int64_t i) {
     auto& r = res[(size_t)i];
     ok[i] = encode_text(wp, reinterpret_cast<const unsigned char*>(buf) + offs[i], offs[i + 1] - offs[i], r) ? 1 : 0;
+    if (!ok[i]) r.clear();
+  });
+  int64_t total = 0;
+  for (int64_t i = 0; i < n; ++i) { out_offs[i] = total; total += (int64_t)res[(size_t)i].size(); }
+  out_offs[n] = total;
+  if (total > cap) return total;
+  for (int64_t i = 0; i < n; ++i)
+    if (!res[(size_t)i].empty()) std::memcpy(out + out_offs[i], res[(size_t)i].data(), res[(size_t)i].size() * sizeof(int32_t));
+  return total;
+}
+
+
+// vocab_blob: tokens in id order separated by '\n' (byte-level alphabet, UTF-8); merges_blob: "left right" lines in rank
+// order; cat[ncp]: CAT_* per code point.
+void* bpe_create(const char* vocab_blob, int64_t vocab_len, const char* merges_blob, int64_t merges_len, const uint8_t* cat,
+                 int64_t ncp) {
+  auto* bpe = new Bpe();
+  int32_t id = 0;
+  int64_t a = 0;
+  for (int64_t i = 0; i <= vocab_len; ++i)
+    if (i == vocab_len || vocab_blob[i] == '\n') {
+      if (i < vocab_len || i > a) bpe->vocab.emplace(std::string(vocab_blob + a, (size_t)(i - a)), id++);
+      a = i + 1;
+    }
+  int32_t rank = 0;
+  a = 0;
+  for (int64_t i = 0; i <= merges_len; ++i)
+    if (i == merges_len || merges_blob[i] == '\n') {
+      if (i > a) {
+        std::string line(merges_blob + a, (size_t)(i - a));
+        const size_t sp = line.find(' ');
+        if (sp != std::string::npos) {
+          line[sp] = '\x01';
+          bpe->ranks.emplace(line, rank++);
+        }
+      }
+      a = i + 1;
+    }
+  bpe->cat.assign(cat, cat + ncp);
+  // GPT-2's bytes_to_unicode: printable Latin-1 bytes map to themselves, the rest to U+0100, U+0101, ...
+  uint32_t extra = 0;
+  for (int b = 0; b < 256; ++b) {
+    const bool keep = (b >= 0x21 && b <= 0x7E) || (b >= 0xA1 && b <= 0xAC) || (b >= 0xAE && b <= 0xFF);
+    append_utf8(bpe->byte_str[b], keep ? (uint32_t)b : 256u + extra++);
+  }
+  return bpe;
+}
+
+void bpe_destroy(void* h) { delete static_cast<Bpe*>(h); }
+
+// same calling convention as wp_encode_batch
+int64_t bpe_encode_batch(void* h, const char* buf, const int64_t* offs, int64_t n, int32_t* out, int64_t cap,
+                         int64_t* out_offs, uint8_t* ok, int threads) {
+  const Bpe& bpe = *static_cast<const Bpe*>(h);
+  std::vector<std::vector<int32_t>> res((size_t)n);
+  parallel_for(n, threads, [&](int64_t i) {
+    auto& r = res[(size_t)i];
+    ok[i] = bpe_encode_text(bpe, reinterpret_cast<const unsigned char*>(buf) + offs[i], offs[i + 1] - offs[i], r) ? 1 : 0;
     if (!ok[i]) r.clear();
   });
   int64_t total = 0;

@@ -138,3 +138,60 @@ class WordPieceEncoder:
                 break
             cap = int(total)
         return [out[out_offs[i]:out_offs[i + 1]] if ok[i] else None for i in range(n)]
+
+
+class BpeEncoder:
+    """Native byte-level BPE (ops/csrc/host.cpp: bpe_*): GPT-2 pre-tokenisation over a category table for the BMP,
+    byte -> printable alphabet, rank-ordered merges; batched and threaded.  ``vocab_tokens`` in id order, ``merges`` as
+    ``"left right"`` lines in rank order, ``categories`` uint8[65536] (0 other, 1 letter, 2 number, 3 white space)."""
+
+    def __init__(self, host: _Host, vocab_tokens, merges, categories):
+        self._host = host
+        vb = "\n".join(vocab_tokens).encode("utf-8")
+        mb = "\n".join(merges).encode("utf-8")
+        cat = np.ascontiguousarray(categories, dtype=np.uint8)
+        lib = host.lib
+        lib.bpe_create.restype = ctypes.c_void_p
+        lib.bpe_create.argtypes = [ctypes.c_char_p, ctypes.c_int64, ctypes.c_char_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64]
+        lib.bpe_destroy.argtypes = [ctypes.c_void_p]
+        lib.bpe_encode_batch.restype = ctypes.c_int64
+        lib.bpe_encode_batch.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int64), ctypes.c_int64,
+                                         ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64), ctypes.c_void_p,
+                                         ctypes.c_int]
+        self._h = lib.bpe_create(vb, len(vb), mb, len(mb), cat.ctypes.data, cat.size)
+        if not self._h:
+            raise RuntimeError("bpe_create failed")
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                self._host.lib.bpe_destroy(h)
+            except Exception:
+                pass
+
+    def encode_batch(self, texts, threads: int = 0):
+        """-> list with an int32 id array per text, or ``None`` where the text is not covered (non-BMP characters,
+        a symbol missing from the vocabulary)."""
+        n = len(texts)
+        if n == 0:
+            return []
+        try:
+            enc = [t.encode("utf-8") for t in texts]
+        except UnicodeEncodeError:
+            enc = [t.encode("utf-8", errors="replace") for t in texts]
+        offs = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum([len(e) for e in enc], out=offs[1:])
+        buf = b"".join(enc)
+        out_offs = np.empty(n + 1, dtype=np.int64)
+        ok = np.empty(n, dtype=np.uint8)
+        cap = max(16, len(buf) + 16)
+        i64p = ctypes.POINTER(ctypes.c_int64)
+        for _ in range(2):
+            out = np.empty(cap, dtype=np.int32)
+            total = self._host.lib.bpe_encode_batch(self._h, buf, offs.ctypes.data_as(i64p), n, out.ctypes.data, cap,
+                                                    out_offs.ctypes.data_as(i64p), ok.ctypes.data, threads)
+            if total <= cap:
+                break
+            cap = int(total)
+        return [out[out_offs[i]:out_offs[i + 1]] if ok[i] else None for i in range(n)]

@@ -234,3 +234,39 @@ def test_loader_smoke_main(tmp_path, capsys):
                      "--vocab_size", "1000"]) == 0
     out = capsys.readouterr().out
     assert "Dataset size = 48" in out and "epoch 1: 48 samples" in out
+
+
+def test_native_bpe_matches_tokenizers_package(tmp_path):
+    """The C++ byte-level BPE (GPT-2 pre-tokenisation pattern, byte alphabet, rank-ordered merges) returns the ids of
+    ``tokenizers.ByteLevelBPETokenizer`` on mixed-script BMP text, cased and lower-cased; characters outside the BMP and the
+    context-dependent lower-casing cases take the fallback."""
+    import random
+    tokenizers = pytest.importorskip("tokenizers")
+    from bert_pytorch_b200.data.tokenization import FastBPE, get_bpe_tokenizer
+    rnd = random.Random(0)
+    words = ("the quick brown fox jumps over lazy dog while rain keeps falling don't it's we'll they've I'm he'd 1234 56.7 "
+             "café naïve über straße").split()
+    corpus = tmp_path / "c.txt"
+    corpus.write_text("\n".join(" ".join(rnd.choice(words) for _ in range(rnd.randint(3, 14))) for _ in range(300)), encoding="utf-8")
+    tok = tokenizers.ByteLevelBPETokenizer(add_prefix_space=False, lowercase=True)
+    tok.train([str(corpus)], vocab_size=380, show_progress=False, special_tokens=["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]"])
+    tok.save_model(str(tmp_path))
+    vocab = str(tmp_path / "vocab.json")
+    C = lambda *cps: "".join(chr(c) for c in cps)
+    pools = ["abcdefghijklmnopqrstuvwxyz", "ABCDEFGHIJKLMNOPQRSTUVWXYZ", "0123456789", C(0x20, 0x09, 0x0A, 0x0D, 0xA0, 0x2003, 0x3000, 0x85, 0x2028),
+             ".,;:!?'\"()[]{}-_/\\@#$%^&*+=<>|~`", C(0xE9, 0xFC, 0xF1, 0xDF, 0x142, 0x15F, 0x131), C(0x4E2D, 0x6587, 0x6771, 0x4EAC),
+             C(0x3042, 0x30A2), C(0xAC00), C(0x430, 0x414), C(0x3B1, 0x394), C(0x627, 0x644), C(0x00, 0x07, 0xFFFD, 0x200B, 0xAD, 0xFEFF, 0x1C),
+             C(0x2014, 0x2018, 0x201D, 0x2026, 0x20AC), C(0x301, 0x308), C(0xB2, 0xBC, 0x663, 0x2167), "'s 't 're 've 'm 'll 'd 'S 'LL",
+             C(0x3A3, 0x130, 0x1F600)]
+    texts = ["".join(rnd.choice(rnd.choice(pools)) for _ in range(rnd.randint(1, 40))) for _ in range(800)]
+    texts += ["Don't stop, it's 12:30pm!!  ok\n\n next\tline ", "  leading", "trailing   ", "a  b   c", ""]
+    for lower in (True, False):
+        hf = get_bpe_tokenizer(vocab, uppercase=not lower)
+        fast = FastBPE(vocab, lowercase=lower)
+        if fast.native is None:
+            pytest.skip("native host helper not built")
+        fell_back = []
+        got = fast.encode_batch(texts, fallback=lambda t: fell_back.append(t) or hf.encode(t).ids)
+        assert 0 < len(fell_back) < 0.8 * len(texts)                  # both paths are exercised (the last pool forces fallbacks)
+        for t, ids in zip(texts, got):
+            assert list(ids) == hf.encode(t).ids, (lower, ascii(t))
