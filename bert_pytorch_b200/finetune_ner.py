@@ -57,6 +57,7 @@ def get_data(args) -> Tuple[DataLoader, Optional[DataLoader], Optional[DataLoade
     kind = args.tokenizer or cfg.get("tokenizer", "wordpiece")
     if vocab_file is None:
         raise ValueError("vocab_file must be provided on the command line or in the model config")
+    args.vocab_file, args.tokenizer = vocab_file, kind       # resolved values are visible to the caller (run_ner.py:67-81)
     tok = (get_wordpiece_tokenizer if kind == "wordpiece" else get_bpe_tokenizer)(vocab_file, uppercase=args.uppercase)
     def make(path, shuffle):
         if path is None:

@@ -414,6 +414,15 @@ with _w.catch_warnings():
                                        4, 5, 0.2, vocab_size=100)
 out["legacy_len"] = len(dleg)
 out["legacy_rows"] = [[np.asarray(a).tolist() for a in dleg[i]] for i in range(len(dleg))]
+
+# ---- run_ner.get_data: vocabulary / tokenizer resolved from the model config, loaders over the CoNLL files
+json.dump(dict(spec["cfg"], vocab_file=work + "/vocab.txt", tokenizer="wordpiece"), open(work + "/ner_model.json", "w"))
+nargs = types.SimpleNamespace(cuda=False, batch_size=2, vocab_file=None, tokenizer=None, model_config_file=work + "/ner_model.json",
+                              uppercase=False, train_file=work + "/ner.txt", val_file=work + "/ner.txt", test_file=None,
+                              labels=spec["ner_labels"], max_seq_len=12)
+tl, vl, tel = RN.get_data(nargs)
+out["ner_get_data"] = (len(tl), len(vl), tel is None, nargs.vocab_file, nargs.tokenizer,
+                       [[t.tolist() for t in b] for b in vl])
 pickle.dump(out, open(work + "/ref.pkl", "wb"))
 '''
 
@@ -1071,3 +1080,18 @@ def test_legacy_premasked_shards_agree(ref):
     for i, want in enumerate(ref["legacy_rows"]):
         got = [np.asarray(a).tolist() for a in ds[i]]
         assert got == want, i
+
+
+def test_ner_get_data_agrees(ref):
+    import types
+    from bert_pytorch_b200 import finetune_ner
+    work = ref["work"]
+    args = types.SimpleNamespace(cuda=False, batch_size=2, vocab_file=None, tokenizer=None,
+                                 model_config_file=os.path.join(work, "ner_model.json"), uppercase=False,
+                                 train_file=os.path.join(work, "ner.txt"), val_file=os.path.join(work, "ner.txt"), test_file=None,
+                                 labels=NER_LABELS, max_seq_len=12)
+    tl, vl, tel = finetune_ner.get_data(args)
+    n_train, n_val, no_test, vocab_file, tok_kind, val_batches = ref["ner_get_data"]
+    assert (len(tl), len(vl), tel is None) == (n_train, n_val, no_test)
+    assert args.vocab_file == vocab_file and args.tokenizer == tok_kind
+    assert [[t.tolist() for t in b] for b in vl] == val_batches
