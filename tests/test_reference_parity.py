@@ -423,6 +423,14 @@ nargs = types.SimpleNamespace(cuda=False, batch_size=2, vocab_file=None, tokeniz
 tl, vl, tel = RN.get_data(nargs)
 out["ner_get_data"] = (len(tl), len(vl), tel is None, nargs.vocab_file, nargs.tokenizer,
                        [[t.tolist() for t in b] for b in vl])
+
+# ---- run_pretraining.prepare_dataset: recursive shard discovery, tokenizer from the model config, sampler resume
+json.dump(dict(spec["cfg"], vocab_size=100, vocab_file=work + "/vocab.txt", tokenizer="wordpiece", lowercase=True),
+          open(work + "/pt_model.json", "w"))
+pargs = types.SimpleNamespace(input_dir=os.path.dirname(spec["shards"][0]), model_config_file=work + "/pt_model.json",
+                              max_predictions_per_seq=5, masked_token_fraction=0.2, local_batch_size=4, seed=42)
+ld, sm_ = RP.prepare_dataset(pargs, {"sampler": {"epoch": 0, "seed": 0, "num_replicas": 1, "total_size": 21, "index": 9}})
+out["prepare_dataset"] = (len(ld.dataset), len(sm_), sm_.index, len(ld), ld.dataset.mask_token_index)
 pickle.dump(out, open(work + "/ref.pkl", "wb"))
 '''
 
@@ -1095,3 +1103,19 @@ def test_ner_get_data_agrees(ref):
     assert (len(tl), len(vl), tel is None) == (n_train, n_val, no_test)
     assert args.vocab_file == vocab_file and args.tokenizer == tok_kind
     assert [[t.tolist() for t in b] for b in vl] == val_batches
+
+
+def test_prepare_dataset_agrees(ref):
+    import types
+    from bert_pytorch_b200 import pretrain
+    work = ref["work"]
+    args = types.SimpleNamespace(input_dir=os.path.dirname(ref["spec"]["shards"][0]), model_config_file=os.path.join(work, "pt_model.json"),
+                                 max_predictions_per_seq=5, masked_token_fraction=0.2, local_batch_size=4, seed=42, loader_depth=2,
+                                 device_obj=torch.device("cpu"))
+    loader, sampler = pretrain.prepare_dataset(args, {"sampler": {"epoch": 0, "seed": 0, "num_replicas": 1, "total_size": 21, "index": 9}})
+    n_data, n_sampler, index, n_batches, mask_id = ref["prepare_dataset"]
+    assert (len(loader.dataset), len(sampler), sampler.index) == (n_data, n_sampler, index)
+    assert loader.dataset.mask_token_index == mask_id
+    # the reference's DataLoader reports the batches of a full epoch; this loader reports what is left after the resume point
+    assert n_batches == -(-n_data // 4) and len(loader) == -(-(n_data - index) // 4)
+    loader.close()
