@@ -117,6 +117,9 @@ wp = T.WordpieceTokenizer(vocab=vocab)
 out["basic"] = [basic.tokenize(t) for t in spec["texts"]]
 out["wordpiece"] = [[p for w in basic.tokenize(t) for p in wp.tokenize(w)] for t in spec["texts"]]
 out["basic_cased"] = [T.BasicTokenizer(do_lower_case=False).tokenize(t) for t in spec["texts"]]
+bt = T.BertTokenizer(work + "/vocab.txt", do_lower_case=True)
+out["bert_tokenizer"] = [(bt.tokenize(t), bt.convert_tokens_to_ids(bt.tokenize(t))) for t in spec["texts"][:40]]
+out["ids_to_tokens"] = bt.convert_ids_to_tokens([0, 5, 10, 28, 3])
 
 # ---- SQuAD featurisation + post-processing
 tok = T.get_wordpiece_tokenizer(work + "/vocab.txt", uppercase=False)
@@ -534,6 +537,9 @@ def test_tokenizers_agree(ref):
     assert [basic.tokenize(t) for t in TEXTS] == ref["basic"]
     assert [[p for w in basic.tokenize(t) for p in wp.tokenize(w)] for t in TEXTS] == ref["wordpiece"]
     assert [T.BasicTokenizer(do_lower_case=False).tokenize(t) for t in TEXTS] == ref["basic_cased"]
+    bt = T.BertTokenizer(os.path.join(ref["work"], "vocab.txt"), do_lower_case=True)
+    assert [(bt.tokenize(t), bt.convert_tokens_to_ids(bt.tokenize(t))) for t in TEXTS[:40]] == ref["bert_tokenizer"]
+    assert bt.convert_ids_to_tokens([0, 5, 10, 28, 3]) == ref["ids_to_tokens"]
 
 
 def test_squad_features_and_answers_agree(ref):
