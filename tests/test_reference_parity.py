@@ -434,6 +434,22 @@ pargs = types.SimpleNamespace(input_dir=os.path.dirname(spec["shards"][0]), mode
                               max_predictions_per_seq=5, masked_token_fraction=0.2, local_batch_size=4, seed=42)
 ld, sm_ = RP.prepare_dataset(pargs, {"sampler": {"epoch": 0, "seed": 0, "num_replicas": 1, "total_size": 21, "index": 9}})
 out["prepare_dataset"] = (len(ld.dataset), len(sm_), sm_.index, len(ld), ld.dataset.mask_token_index)
+
+# ---- activation table and the Linear+activation module (src/modeling.py:118-185)
+xa = torch.randn(5, 7, generator=torch.Generator().manual_seed(1)) * 3
+ba = torch.randn(7, generator=torch.Generator().manual_seed(2))
+acts = {}
+for name, fn in M.ACT2FN.items():
+    try:
+        acts[name] = (fn(ba, xa) if name.startswith("bias_") else fn(xa)).numpy()
+    except Exception as e:
+        acts[name] = repr(e)
+out["acts"] = (xa.numpy(), ba.numpy(), acts)
+torch.manual_seed(4)
+la = M.LinearActivation(7, 6, act="gelu")
+lt = M.LinearActivation(7, 6, act="tanh")
+out["linear_act"] = ({k: v.numpy() for k, v in la.state_dict().items()}, la(xa).detach().numpy(),
+                     {k: v.numpy() for k, v in lt.state_dict().items()}, lt(xa).detach().numpy())
 pickle.dump(out, open(work + "/ref.pkl", "wb"))
 '''
 
@@ -1125,3 +1141,20 @@ def test_prepare_dataset_agrees(ref):
     # the reference's DataLoader reports the batches of a full epoch; this loader reports what is left after the resume point
     assert n_batches == -(-n_data // 4) and len(loader) == -(-(n_data - index) // 4)
     loader.close()
+
+
+def test_activation_table_and_linear_activation_agree(ref):
+    from bert_pytorch_b200 import models as M
+    xa, ba, acts = ref["acts"]
+    x, b = torch.from_numpy(xa), torch.from_numpy(ba)
+    assert set(acts) <= set(M.ACT2FN), sorted(set(acts) - set(M.ACT2FN))
+    for name, want in acts.items():
+        if isinstance(want, str):
+            continue
+        got = (M.ACT2FN[name](b, x) if name.startswith("bias_") else M.ACT2FN[name](x)).numpy()
+        assert np.allclose(got, want, atol=1e-6, rtol=1e-5), name
+    sd_g, y_g, sd_t, y_t = ref["linear_act"]
+    for act, sd, want in (("gelu", sd_g, y_g), ("tanh", sd_t, y_t)):
+        m = M.LinearActivation(7, 6, act=act)
+        m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+        assert np.allclose(m(x).detach().numpy(), want, atol=1e-6, rtol=1e-5), act
