@@ -230,3 +230,18 @@ def test_grad_scaler_matches_torch_amp_grad_scaler():
         assert ts.get_scale() == ms.get_scale(), i
         assert torch.equal(p1.data, p2.data), i
     assert ts.state_dict() == ms.state_dict()
+
+
+def test_adam_matches_torch_adamw_with_bias_correction():
+    """Adam (apex FusedAdam semantics: decoupled weight decay) with bias correction on is torch.optim.AdamW."""
+    from bert_pytorch_b200.optim import Adam
+    torch.manual_seed(0)
+    w1 = torch.nn.Parameter(torch.randn(6, 5))
+    w2 = torch.nn.Parameter(w1.detach().clone())
+    o1 = torch.optim.AdamW([w1], lr=1e-2, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
+    o2 = Adam([w2], lr=1e-2, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, bias_correction=True)
+    for i in range(8):
+        g = torch.randn(6, 5, generator=torch.Generator().manual_seed(i))
+        w1.grad, w2.grad = g.clone(), g.clone()
+        o1.step(); o2.step()
+        assert (w1 - w2).abs().max().item() < 2e-6, i
