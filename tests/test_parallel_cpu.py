@@ -253,3 +253,50 @@ def test_two_level_fused_backend_composition_gloo():
     for _, out, pm in res:
         assert pm is False
         assert torch.allclose(out, torch.full((8,), (1 + 2 + 3 + 4) / 4 / 4.0))
+
+
+def _ddp_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method="env://")
+    from torch.nn.parallel import DistributedDataParallel as TorchDDP
+    from bert_pytorch_b200.parallel import TorchComm
+    m_ref = _model()
+    m_mine = copy.deepcopy(m_ref)
+    ddp_ref = TorchDDP(m_ref)                       # what the reference wraps its model in (run_pretraining.py:270)
+    arena = ParamArena(m_mine)
+    ddp_mine = DataParallel(m_mine, comm=TorchComm(), arena=arena)
+    torch.manual_seed(7)
+    ids = torch.randint(0, 256, (2 * world, 16))
+    mine = ids[rank * 2:(rank + 1) * 2]
+    worst = 0.0
+    for step in range(2):                           # second step: accumulate one local micro-step first (no_sync)
+        for w in (ddp_ref, ddp_mine):
+            if step == 1:
+                with w.no_sync():
+                    s, n = w(torch.roll(mine, 3, 1))
+                    (s.float().mean() + n.float().mean()).backward()
+            s, n = w(mine)
+            (s.float().mean() + n.float().mean()).backward()
+        ddp_mine.sync_gradients()
+        for (k, p), p2 in zip(m_ref.named_parameters(), m_mine.parameters()):
+            worst = max(worst, float((p.grad - p2.grad).abs().max()))
+        m_ref.zero_grad(); arena.zero_grad()
+    q.put((rank, worst))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_matches_torch_ddp_gloo():
+    """Same model and batches under torch DistributedDataParallel and under this repo's DataParallel (one flat
+    all-reduce of the gradient arena): identical averaged gradients, also after a ``no_sync`` accumulation step."""
+    world, port = 2, 29661
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ddp_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(w < 1e-6 for _, w in res), res
