@@ -1158,3 +1158,38 @@ def test_activation_table_and_linear_activation_agree(ref):
         m = M.LinearActivation(7, 6, act=act)
         m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
         assert np.allclose(m(x).detach().numpy(), want, atol=1e-6, rtol=1e-5), act
+
+
+def test_run_squad_flags_and_defaults_agree():
+    """run_squad.py builds its parser inside main(); its add_argument calls are read from the source (AST) and compared
+    with this repo's parser: every flag exists with the same default, type and store_true behaviour."""
+    import ast
+    from bert_pytorch_b200 import finetune_squad
+    tree = ast.parse(open(os.path.join(REF, "run_squad.py")).read())
+    ref = {}
+    for node in ast.walk(tree):
+        if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and node.func.attr == "add_argument":
+            names = [a.value for a in node.args if isinstance(a, ast.Constant) and isinstance(a.value, str)]
+            if not names:
+                continue
+            kw = {}
+            for k in node.keywords:
+                if k.arg in ("default", "action"):
+                    try:
+                        kw[k.arg] = ast.literal_eval(k.value)
+                    except ValueError:
+                        kw[k.arg] = None                         # computed default (LOCAL_RANK from the environment)
+                elif k.arg == "type" and isinstance(k.value, ast.Name):
+                    kw["type"] = k.value.id
+            ref[names[-1].lstrip("-").replace("-", "_")] = kw
+    assert len(ref) >= 40
+    mine = {a.dest: a for a in finetune_squad.build_parser()._actions}
+    assert not [k for k in ref if k not in mine]
+    for k, kw in ref.items():
+        a = mine[k]
+        if kw.get("default", None) is not None:
+            assert a.default == kw["default"], (k, a.default, kw["default"])
+        if kw.get("action") == "store_true":
+            assert a.nargs == 0 and a.const is True and a.default is False, k
+        if kw.get("type") in ("int", "float", "str") and a.type is not None:
+            assert a.type.__name__ == kw["type"], k
