@@ -1193,3 +1193,43 @@ def test_run_squad_flags_and_defaults_agree():
             assert a.nargs == 0 and a.const is True and a.default is False, k
         if kw.get("type") in ("int", "float", "str") and a.type is not None:
             assert a.type.__name__ == kw["type"], k
+
+
+def _argparse_table(path):
+    """flag -> (default, type name, action) of every add_argument call in a source file (AST, nothing is executed)."""
+    import ast
+    table = {}
+    for node in ast.walk(ast.parse(open(path).read())):
+        if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and node.func.attr == "add_argument":
+            names = [a.value for a in node.args if isinstance(a, ast.Constant) and isinstance(a.value, str)]
+            if not names:
+                continue
+            kw = {"default": None, "type": None, "action": None}
+            for k in node.keywords:
+                if k.arg in ("default", "action"):
+                    try:
+                        kw[k.arg] = ast.literal_eval(k.value)
+                    except ValueError:
+                        kw[k.arg] = "<computed>"
+                elif k.arg == "type" and isinstance(k.value, ast.Name):
+                    kw["type"] = k.value.id
+            table[names[-1].lstrip("-").replace("-", "_")] = kw
+    return table
+
+
+@pytest.mark.parametrize("script", ["encode_data.py", "format.py", "download.py", "build_vocab.py", "shard.py", "sample_and_shard.py"])
+def test_data_tool_flags_and_defaults_agree(script):
+    ref_utils = next((p for p in (os.path.join(REF, "utils"), "/root/reference/utils") if os.path.isfile(os.path.join(p, script))), None)
+    if ref_utils is None:
+        pytest.skip("the reference's utils/ directory is not available")
+    ref, mine = _argparse_table(os.path.join(ref_utils, script)), _argparse_table(os.path.join(ROOT, "utils", script))
+    assert ref, script
+    for flag, kw in ref.items():
+        assert flag in mine, (script, flag)
+        m = mine[flag]
+        if kw["default"] not in (None, "<computed>"):
+            assert m["default"] == kw["default"], (script, flag, m["default"], kw["default"])
+        if kw["action"] == "store_true":
+            assert m["action"] == "store_true", (script, flag)
+        if kw["type"] in ("int", "float", "str") and m["type"] is not None:
+            assert m["type"] == kw["type"], (script, flag)
