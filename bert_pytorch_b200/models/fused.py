@@ -9,15 +9,14 @@ The ``nn.Module`` tree in :mod:`.modeling` only *holds* the parameters (as views
                flash attention (scale, key-padding, softmax, dropout, PV)   tcgen05    (K7-K12)
                out-proj GEMM + bias + dropout + residual                    tcgen05    (K13-K14)
                LayerNorm                                                     1 kernel   (K15)
-               FFN-1 GEMM + bias, GELU as its own bandwidth kernel           tcgen05    (K16; a fused erf epilogue is
-                                                                                       instruction bound at K = 1024)
+               FFN-1 GEMM + bias + GELU (and GELU' for the backward) epilogue  tcgen05    (K16)
                FFN-2 GEMM + bias + dropout + residual                        tcgen05    (K17-K18)
                LayerNorm                                                     1 kernel
   MLM head     compact masked positions -> gather -> transform GEMM+GELU -> LN -> decoder GEMM + bias
                -> softmax-CE fwd+bwd in place (only max_pred rows/sequence, K21-K24; fixes Q15)
   backward     the mirror image: LN-bwd kernels emit the residual gradient *and* the dropout-masked
                gradient plus all dgamma/dbeta/dbias column sums; dgrad GEMMs fuse the residual-gradient
-               add, GELU' (+ bias gradient) is one bandwidth pass; wgrad GEMMs (both operands MN-major,
+               add or the multiplication by GELU' (+ the FFN-1 bias gradient); wgrad GEMMs (both operands MN-major,
                split-K) accumulate in fp32 straight into the gradient arena -- or, on the last micro-step
                with the peer-memory backend, straight into the OWNER rank's arena over NVLink.
 
@@ -138,6 +137,9 @@ class FusedEncoderEngine:
         # the machine with them (+2.5 % on the phase-1 step at 1 and 2 GPUs).  B200_WGRAD_STREAM=0 / ``wgrad_side =
         # False`` keeps everything on one stream.
         self.wgrad_side = os.environ.get("B200_WGRAD_STREAM", "1") != "0"
+        # GELU / GELU' inside the FFN GEMM epilogues (bf16 operand path); B200_FUSED_GELU=0 restores the two
+        # bandwidth kernels
+        self.fused_gelu = os.environ.get("B200_FUSED_GELU", "1") != "0"
         self._wstream = None
         self._wkeep: list = []
 
@@ -358,11 +360,19 @@ class FusedEncoderEngine:
         x1, mean1, rstd1, *q = K.layer_norm_fwd(pre1, self.p(pre + "attention.output.LayerNorm.weight"),
                                                 self.p(pre + "attention.output.LayerNorm.bias"), save_stats=save,
                                                 fp8=self._side(f"{l}.x1"))
-        # GELU runs as its own bandwidth kernel: with K = 1024 it does not fit under the GEMM main loop
-        y1, x1_op = self._lin(l, "x1", "w1", x1, self.w(pre + "intermediate.dense_act.weight"), xq=q[0] if q else None,
-                              epi=K.EPI_BIAS, bias=self.w(pre + "intermediate.dense_act.bias"))
-        side = self._side(f"{l}.act")
-        act, *q = K.gelu_fwd(y1, fp8=side) if side else (K.gelu_fwd(y1),)
+        if self.fused_gelu and not self.fp8:
+            # K16: GELU *and* GELU' leave the FFN-1 GEMM through its epilogue (y1 holds gelu'(x), which is all the
+            # backward pass needs: the FFN-2 dgrad epilogue multiplies by it) -- no activation pass over HBM at all
+            y1 = torch.empty(M, self.I, dtype=torch.bfloat16, device=x1.device)
+            act, x1_op = self._lin(l, "x1", "w1", x1, self.w(pre + "intermediate.dense_act.weight"),
+                                   epi=K.EPI_BIAS_GELU_DG, bias=self.w(pre + "intermediate.dense_act.bias"), aux_out=y1)
+            q = []
+        else:
+            # fp8 operands: GELU stays a bandwidth kernel that also emits the e4m3 copy of the activation
+            y1, x1_op = self._lin(l, "x1", "w1", x1, self.w(pre + "intermediate.dense_act.weight"), xq=q[0] if q else None,
+                                  epi=K.EPI_BIAS, bias=self.w(pre + "intermediate.dense_act.bias"))
+            side = self._side(f"{l}.act")
+            act, *q = K.gelu_fwd(y1, fp8=side) if side else (K.gelu_fwd(y1),)
         pre2, act_op = self._lin(l, "act", "w2", act, self.w(pre + "output.dense.weight"), xq=q[0] if q else None,
                                  epi=K.EPI_BIAS_DROP_RES, bias=self.w(pre + "output.dense.bias"), res=x1, p_drop=ph,
                                  seed=seed, stream=_stream(l, SITE_FFN_OUT))
@@ -425,13 +435,20 @@ class FusedEncoderEngine:
             drop_stream=_stream(l, SITE_FFN_OUT), fp8=self._side(f"{l}.d_y2"))
         if kfac is not None:
             kfac.tap(self.prefix + pre + "output.dense", ls.act, d_y2)
-        # ---- FFN-2
-        d_act = self._lin_bwd(l, "d_y2", "act", "w2", d_y2, ls.act_op, self.w(pre + "output.dense.weight"),
-                              self.g(pre + "output.dense.weight"), dyq=q[0] if q else None)
-        # ---- FFN-1 (GELU' and the bias gradient in one bandwidth pass)
-        side = self._side(f"{l}.d_y1")
-        d_y1, *q = (K.dgelu_bwd(d_act, ls.y1, self.g(pre + "intermediate.dense_act.bias"), fp8=side) if side
-                    else (K.dgelu_bwd(d_act, ls.y1, self.g(pre + "intermediate.dense_act.bias")),))
+        # ---- FFN-2 / GELU'
+        if self.fused_gelu and not self.fp8:
+            # dgrad epilogue: d_y1 = (d_y2 W2) * gelu'(x) with the FFN-1 bias gradient (column sums) reduced from the
+            # staged tile -- the dGELU pass and its bias-gradient pass are gone
+            d_y1 = self._lin_bwd(l, "d_y2", "act", "w2", d_y2, ls.act_op, self.w(pre + "output.dense.weight"),
+                                 self.g(pre + "output.dense.weight"), epi=K.EPI_MUL, res=ls.y1,
+                                 colsum=self.g(pre + "intermediate.dense_act.bias"))
+            q = []
+        else:
+            d_act = self._lin_bwd(l, "d_y2", "act", "w2", d_y2, ls.act_op, self.w(pre + "output.dense.weight"),
+                                  self.g(pre + "output.dense.weight"), dyq=q[0] if q else None)
+            side = self._side(f"{l}.d_y1")
+            d_y1, *q = (K.dgelu_bwd(d_act, ls.y1, self.g(pre + "intermediate.dense_act.bias"), fp8=side) if side
+                        else (K.dgelu_bwd(d_act, ls.y1, self.g(pre + "intermediate.dense_act.bias")),))
         d_x1 = self._lin_bwd(l, "d_y1", "x1", "w1", d_y1, ls.x1_op, self.w(pre + "intermediate.dense_act.weight"),
                              self.g(pre + "intermediate.dense_act.weight"), dyq=q[0] if q else None,
                              epi=K.EPI_ADD, res=d_pre2)

@@ -16,7 +16,8 @@ from . import extension
 
 # GEMM enums (csrc/gemm_sm100.h)
 NT, NN, TN = 0, 1, 2
-EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_DROP_RES, EPI_ADD, EPI_DGELU, EPI_ACCUM_F32, EPI_BIAS_TANH, EPI_F32 = range(9)
+(EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_DROP_RES, EPI_ADD, EPI_DGELU, EPI_ACCUM_F32, EPI_BIAS_TANH, EPI_F32,
+ EPI_BIAS_GELU_DG, EPI_MUL) = range(11)
 
 NUM_SMS = 148
 _PAIR_ENABLED = os.environ.get("B200_GEMM_PAIR", "1") != "0"
@@ -58,9 +59,12 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, layout: int = NT, epi: int = EPI_N
          res: Optional[torch.Tensor] = None, aux_out: Optional[torch.Tensor] = None, k_splits: int = 1,
          block_n: Optional[int] = None, alpha: float = 1.0, p_drop: float = 0.0, seed: int = 0,
          stream: int = 0, scale_a: Optional[torch.Tensor] = None, scale_b: Optional[torch.Tensor] = None,
-         a_e5m2: bool = False, b_e5m2: bool = False, push: bool = False) -> torch.Tensor:
+         a_e5m2: bool = False, b_e5m2: bool = False, push: bool = False,
+         colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
     """tcgen05 GEMM with a fused epilogue (see csrc/gemm_sm100.cu).  ``a``/``b`` are 2-D bf16, or -- with
-    ``scale_a``/``scale_b`` (device inv-scale scalars from an :class:`Fp8Meta`) -- 1-byte fp8 tensors."""
+    ``scale_a``/``scale_b`` (device inv-scale scalars from an :class:`Fp8Meta`) -- 1-byte fp8 tensors.
+    ``colsum`` (fp32 [N], EPI_NONE / EPI_ADD / EPI_MUL): accumulates the column sums of the bf16 output (a bias
+    gradient that would otherwise need its own pass over the tensor)."""
     if layout == NT:
         M, N = a.size(0), b.size(0)
     elif layout == NN:
@@ -75,7 +79,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, layout: int = NT, epi: int = EPI_N
     elif block_n is None:
         block_n = _pick_block_n(M, N)
     extension().gemm(a, b, out, layout, epi, bias, res, aux_out, k_splits, block_n, alpha, p_drop, seed, stream,
-                     scale_a, scale_b, a_e5m2, b_e5m2, push)
+                     scale_a, scale_b, a_e5m2, b_e5m2, push, colsum)
     _count()
     return out
 
@@ -354,9 +358,11 @@ def attention_bwd(qkv, seqlens, ctx, dctx, lse, heads: int, *, p_drop=0.0, seed=
     return dqkv if fp8 is None else (dqkv, q)
 
 
-def set_attention_options(bwd_pipe: Optional[bool] = None) -> None:
-    """``bwd_pipe``: force the software-pipelined S > 128 backward kernel on / off (None: follow B200_ATTN_BWD_PIPE)."""
-    extension().set_attention_options(-1 if bwd_pipe is None else int(bool(bwd_pipe)))
+def set_attention_options(bwd_pipe: Optional[bool] = None, row_kernels: Optional[bool] = None) -> None:
+    """``bwd_pipe``: force the software-pipelined S > 128 backward kernel on / off; ``row_kernels``: force the
+    round-2 thread-per-query-row kernels on / off (None: follow B200_ATTN_BWD_PIPE / B200_ATTN_ROW, both default on)."""
+    extension().set_attention_options(-1 if bwd_pipe is None else int(bool(bwd_pipe)),
+                                      -1 if row_kernels is None else int(bool(row_kernels)))
 
 
 # ---------------------------------------------------------------------------

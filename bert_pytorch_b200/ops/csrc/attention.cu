@@ -37,6 +37,13 @@ constexpr int ATT_BWD16_THREADS = 544; // streaming backward: 16 math warps (4 p
 constexpr int TILE = 128;          // query rows / key rows per block
 constexpr int HD = 64;             // head dim
 constexpr float LOG2E = 1.4426950408889634f;
+// -1: follow the environment (B200_ATTN_ROW, default on), 0 / 1: forced by attention_set_options
+static int g_attn_row = -1;
+static bool attn_row_enabled() {
+  if (g_attn_row >= 0) return g_attn_row != 0;
+  static const bool env_on = []() { const char* e = getenv("B200_ATTN_ROW"); return !(e && e[0] == '0'); }();
+  return env_on;
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -469,6 +476,487 @@ attn_fwd_single_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnA
   if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tS, 128);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Round-2 forward: one THREAD per query row, P stays in tensor memory, persistent CTAs.
+//
+// ncu on the kernels above (profiles/ncu_hot_kernels_r1.md): 23-25 instructions per score element at ~55 % issue
+// utilisation and 8-10 % tensor-pipe activity -- the softmax, not the MMA, is the cost, and half of it is overhead
+// of the two-threads-per-row mapping (two TMEM passes of 16-column loads, shared-memory exchanges and block
+// barriers for the row statistics, swizzled shared-memory stores of P, Philox key schedule and 16-bit field
+// extraction per element).  Here
+//   * thread r of the four softmax warps owns TMEM lane r = query row r: row max / row sum never leave the thread
+//     (no exchange, no barrier), 3-input max, 32-column TMEM loads with the next chunk in flight;
+//   * P (bf16) is written back into the first 64 columns of the S accumulator with tcgen05.st and feeds the PV MMA
+//     as a TMEM A operand -- no shared-memory round trip, no proxy fence, and the Q / K tiles are free for the next
+//     loads as soon as the S MMA has retired;
+//   * the PV result lands in columns [64, 128) of the same accumulator: 128 TMEM columns and 48 KB per CTA ->
+//     four (S <= 128) or three (streaming, 64 accumulator registers) co-resident CTAs per SM hide each other's
+//     dependent MMA -> softmax -> MMA chains;
+//   * CTAs are persistent over (batch, head, query block) items: TMEM allocation / barrier set-up once, the next
+//     item's Q and K tiles stream in under the current softmax;
+//   * dropout: 1 / keep_prob is folded into the exponent, the Philox round keys are precomputed, the 16-bit keep
+//     fields are compared in place (one ISETP per element, same bits as dropout_keep8 so the backward kernels agree).
+// ------------------------------------------------------------------------------------------------
+constexpr int ATT_ROW_THREADS = 160;   // warps 0-3: softmax rows (TMEM lane quarter == warp), warp 4: control
+
+struct PhiloxKeys { uint32_t a[7], b[7]; };
+__device__ __forceinline__ PhiloxKeys philox_keys(unsigned long long seed) {
+  PhiloxKeys k;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    k.a[i] = (uint32_t)seed + (uint32_t)i * Philox::kW0;
+    k.b[i] = (uint32_t)(seed >> 32) + (uint32_t)i * Philox::kW1;
+  }
+  return k;
+}
+// same value as Philox::gen(seed, idx, stream), round keys hoisted, 64-bit products (one IMAD.WIDE each)
+__device__ __forceinline__ uint4 philox7(const PhiloxKeys& k, uint64_t idx, uint32_t stream) {
+  uint32_t x = (uint32_t)idx, y = (uint32_t)(idx >> 32), z = stream, w = 0x5EEDu;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    const uint64_t p0 = (uint64_t)Philox::kA * x, p1 = (uint64_t)Philox::kB * z;
+    const uint32_t nx = (uint32_t)(p1 >> 32) ^ y ^ k.a[i];
+    const uint32_t nz = (uint32_t)(p0 >> 32) ^ w ^ k.b[i];
+    y = (uint32_t)p1;
+    w = (uint32_t)p0;
+    x = nx;
+    z = nz;
+  }
+  return make_uint4(x, y, z, w);
+}
+// element t (0..7) of a dropout group is kept iff its 16-bit field (word t/2, low half for even t) >= thresh16;
+// `T` = thresh16 << 16.  High halves compare in place, low halves after a 16-bit shift.
+__device__ __forceinline__ bool keep_bit(const uint4& r, int t, uint32_t T) {
+  const uint32_t wds[4] = {r.x, r.y, r.z, r.w};
+  const uint32_t w = wds[t >> 1];
+  return (t & 1) ? (w >= T) : ((w << 16) >= T);
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+// probabilities of one 32-key chunk of this thread's row: p' = 2^(s c - m + log2(1/keep)) (the dropout rescale rides
+// in the exponent), rowsum over the valid keys BEFORE dropout, dropped entries zeroed, packed bf16 -> 16 words.
+// NV: number of valid keys in the chunk (32 on the fast path; compile-time `FULL`)
+template <bool FULL, bool DROP>
+__device__ __forceinline__ void softmax_chunk(const uint32_t (&sv)[32], uint32_t (&pw)[16], float c_scale, float off,
+                                              float& rowsum, int nvalid, const PhiloxKeys& keys, uint64_t e8,
+                                              uint32_t stream, uint32_t T) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float pr[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      float e = ex2_approx(fmaf(__uint_as_float(sv[g * 8 + t]), c_scale, off));
+      if (!FULL && g * 8 + t >= nvalid) e = 0.f;
+      rowsum += e;
+      pr[t] = e;
+    }
+    if (DROP) {
+      const uint4 r = philox7(keys, e8 + (uint64_t)g, stream);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) pr[t] = keep_bit(r, t, T) ? pr[t] : 0.f;
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) pw[g * 4 + t] = pack_bf16(pr[2 * t], pr[2 * t + 1]);
+  }
+}
+
+// one 32-column chunk of the row maximum
+__device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], float mx, int nv) {
+  if (nv >= 32) {
+#pragma unroll
+    for (int t = 0; t < 32; t += 2) mx = max3(mx, __uint_as_float(v[t]), __uint_as_float(v[t + 1]));
+  } else if (nv > 0) {
+#pragma unroll
+    for (int t = 0; t < 32; ++t)
+      if (t < nv) mx = fmaxf(mx, __uint_as_float(v[t]));
+  }
+  return mx;
+}
+// row maximum over the 128 score columns of this thread's TMEM lane (the next chunk is in flight while one is reduced)
+__device__ __forceinline__ float row_max_128(uint32_t taddr, int kvalid) {
+  float mx = -INFINITY;
+  uint32_t a[32], b[32];
+  tmem_ld_32x32(taddr, a);
+  tmem_ld_wait();
+  tmem_ld_32x32(taddr + 32, b);
+  mx = chunk_max(a, mx, kvalid);
+  tmem_ld_wait();
+  tmem_ld_32x32(taddr + 64, a);
+  mx = chunk_max(b, mx, kvalid - 32);
+  tmem_ld_wait();
+  tmem_ld_32x32(taddr + 96, b);
+  mx = chunk_max(a, mx, kvalid - 64);
+  tmem_ld_wait();
+  mx = chunk_max(b, mx, kvalid - 96);
+  return mx;
+}
+// probabilities of the 128 score columns -> dropout -> bf16 -> tcgen05.st into columns [0, 64) of the same lane.
+// Words [16 c, 16 c + 16) of the P row overwrite S columns this thread has already consumed (chunk c + 1 starts at
+// column 32 (c + 1) >= 16 (c + 1)).  Returns the row sum of the (1 / keep_prob scaled) probabilities before dropout.
+__device__ __forceinline__ float row_softmax_128(uint32_t taddr, int kvalid, float c_scale, float off, bool drop,
+                                                 const PhiloxKeys& keys, uint64_t e8, uint32_t stream, uint32_t T) {
+  float rowsum = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t v[32], pw[16];
+    tmem_ld_32x32(taddr + c * 32, v);
+    tmem_ld_wait();
+    const int nv = kvalid - c * 32;
+    if (nv >= 32) {
+      if (drop) softmax_chunk<true, true>(v, pw, c_scale, off, rowsum, 32, keys, e8 + 4 * c, stream, T);
+      else softmax_chunk<true, false>(v, pw, c_scale, off, rowsum, 32, keys, e8 + 4 * c, stream, T);
+    } else if (nv > 0) {
+      if (drop) softmax_chunk<false, true>(v, pw, c_scale, off, rowsum, nv, keys, e8 + 4 * c, stream, T);
+      else softmax_chunk<false, false>(v, pw, c_scale, off, rowsum, nv, keys, e8 + 4 * c, stream, T);
+    } else {
+#pragma unroll
+      for (int t = 0; t < 16; ++t) pw[t] = 0u;
+    }
+    tmem_st_32x16(taddr + c * 16, pw);
+  }
+  return rowsum;
+}
+
+// ---- S <= 128: one key block per item; S, P and the P V result share 128 TMEM columns -> four CTAs per SM
+__global__ void __launch_bounds__(ATT_ROW_THREADS, 4)
+attn_fwd_row_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs p, const int n_items) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                      // 16 KB each, 128B swizzle
+  uint8_t* sK = smem + 16384;
+  uint8_t* sV = smem + 32768;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 49152);
+  uint64_t* qk_full = bars;                // Q and K tiles of an item landed
+  uint64_t* v_full = bars + 1;             // V tile landed
+  uint64_t* s_ready = bars + 2;            // S = Q K^T complete (Q and K are free)
+  uint64_t* p_ready = bars + 3;            // 128 threads: P is in tensor memory
+  uint64_t* o_ready = bars + 4;            // P V complete (V is free)
+  uint64_t* o_read = bars + 5;             // 128 threads: the P V result has been read out -> S may be overwritten
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 128) {
+    tma_prefetch_desc(&tmap_qkv);
+    mbar_init(qk_full, 1);
+    mbar_init(v_full, 1);
+    mbar_init(s_ready, 1);
+    mbar_init(p_ready, 128);
+    mbar_init(o_ready, 1);
+    mbar_init(o_read, 128);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tS = *tmem_slot, tO = tS + 64;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);  // Q K^T : both K-major
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, false, true);    // P V   : P from TMEM, V MN-major
+      const uint64_t dq = umma_smem_desc_sw128(smem_u32(sQ), 16, 1024);
+      const uint64_t dk = umma_smem_desc_sw128(smem_u32(sK), 16, 1024);
+      const uint32_t av = smem_u32(sV);
+      auto load_qk = [&](int item) {
+        const int b = item / p.h, head = item - b * p.h;
+        mbar_arrive_expect_tx(qk_full, 32768);
+        tma_load_2d(sQ, &tmap_qkv, qk_full, head * HD, b * p.S);
+        tma_load_2d(sK, &tmap_qkv, qk_full, p.H + head * HD, b * p.S);
+      };
+      auto load_v = [&](int item) {
+        const int b = item / p.h, head = item - b * p.h;
+        mbar_arrive_expect_tx(v_full, 16384);
+        tma_load_2d(sV, &tmap_qkv, v_full, 2 * p.H + head * HD, b * p.S);
+      };
+      int item = blockIdx.x;
+      if (item < n_items) { load_qk(item); load_v(item); }
+      for (uint32_t g = 0; item < n_items; item += gridDim.x, ++g) {
+        const int nitem = item + gridDim.x;
+        if (g > 0) mbar_wait(o_read, (g - 1) & 1);            // previous P V result drained out of [64, 128)
+        mbar_wait(qk_full, g & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) umma_bf16_ss(tS, dq + 2 * kk, dk + 2 * kk, idesc_s, kk > 0);
+        umma_commit(s_ready);
+        mbar_wait(s_ready, g & 1);                            // Q and K may be refilled: next item streams in under the softmax
+        if (nitem < n_items) load_qk(nitem);
+        mbar_wait(p_ready, g & 1);
+        mbar_wait(v_full, g & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < TILE / 16; ++kk)
+          umma_bf16_ts(tO, tS + kk * 8, umma_smem_desc_sw128(av + kk * 2048, 8192, 1024), idesc_o, kk > 0);
+        umma_commit(o_ready);
+        mbar_wait(o_ready, g & 1);                            // V may be refilled
+        if (nitem < n_items) load_v(nitem);
+      }
+    }
+  } else {
+    const int r = warp * 32 + lane;                            // query row == TMEM lane
+    const uint32_t lane_base = uint32_t(warp * 32) << 16;
+    const float c_scale = p.scale * LOG2E;
+    const bool drop = p.thresh16 != 0;
+    const float lk = drop ? log2f(p.inv_keep) : 0.f;           // 1 / keep_prob rides in the exponent
+    const uint32_t T = p.thresh16 << 16;
+    const PhiloxKeys keys = philox_keys(drop ? p.seed.value() : 0ull);
+    const bool q_ok = r < p.S;
+    uint32_t g = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++g) {
+      const int b = item / p.h, head = item - b * p.h;
+      const int seqlen = min(__ldg(p.seqlens + b), p.S);
+      const uint64_t e8row = (((uint64_t)item * p.S + (uint64_t)r) * (uint64_t)p.S) >> 3;   // dropout group base of the row
+      mbar_wait(s_ready, g & 1);
+      tc_fence_after();
+      const float m = fmaxf(row_max_128(tS + lane_base, seqlen) * c_scale, -1e30f);   // an all-padding row stays finite
+      const float l = row_softmax_128(tS + lane_base, seqlen, c_scale, lk - m, drop, keys, e8row, p.stream, T);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(p_ready);
+      const float inv_l = 1.f / l;                             // l carries the 1 / keep_prob of the exponent offset
+      __nv_bfloat16* dst = p.ctx + (size_t)(b * p.S + r) * p.H + head * HD;
+      float amax = 0.f;
+      const float qscale = p.f8.q ? p.f8.meta[1] : 0.f;
+      mbar_wait(o_ready, g & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t o[32];
+        tmem_ld_32x32(tO + lane_base + hh * 32, o);
+        tmem_ld_wait();
+        if (hh == 1) {                                         // accumulator drained: the next S MMA may go
+          tc_fence_before();
+          mbar_arrive(o_read);
+        }
+        if (q_ok) {
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq)
+            *reinterpret_cast<uint4*>(dst + hh * 32 + gq * 8) = make_uint4(
+                pack_bf16(__uint_as_float(o[gq * 8]) * inv_l, __uint_as_float(o[gq * 8 + 1]) * inv_l),
+                pack_bf16(__uint_as_float(o[gq * 8 + 2]) * inv_l, __uint_as_float(o[gq * 8 + 3]) * inv_l),
+                pack_bf16(__uint_as_float(o[gq * 8 + 4]) * inv_l, __uint_as_float(o[gq * 8 + 5]) * inv_l),
+                pack_bf16(__uint_as_float(o[gq * 8 + 6]) * inv_l, __uint_as_float(o[gq * 8 + 7]) * inv_l));
+          if (p.f8.q) emit_fp8_row<4>(p.f8, (size_t)(b * p.S + r) * p.H + head * HD + hh * 32, o, inv_l, qscale, amax);
+        }
+      }
+      if (p.f8.q && amax > 0.f) atomicMax(reinterpret_cast<int*>(p.f8.meta), __float_as_int(isfinite(amax) ? amax : 3.0e38f));
+      if (q_ok) p.lse[(size_t)item * p.S + r] = (m + log2f(l) - lk) * 0.6931471805599453f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tS, 128);
+  }
+}
+
+// ---- S > 128: streaming kernel.  Per CTA: 4 softmax warps (thread == query row), one MMA warp, one TMA warp.
+// TMEM: S | P in columns [0, 128), the output accumulator in [128, 192): the P V MMAs accumulate in tensor memory
+// and S_{j+1} = Q K_{j+1}^T is issued right behind P_j V_j (tcgen05 executes in issue order), so the scores of the
+// next key block are waiting when a softmax finishes -- the threads never wait for a P V.  The running maximum is
+// only raised when a block exceeds it by more than 2^8 (probabilities stay below 256, exact in the fp32 row sum /
+// accumulator); raising it rescales this thread's accumulator row in TMEM (tcgen05.ld -> mul -> tcgen05.st), which
+// after the first key block is rare.  K / V ride a two-stage ring.  256 TMEM columns, 80 KB -> two CTAs per SM.
+constexpr int ATT_STREAM_THREADS = 192;
+__global__ void __launch_bounds__(ATT_STREAM_THREADS, 2)
+attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs p, const int n_items, const int nqb) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                      // 16 KB
+  uint8_t* sK = smem + 16384;              // 2 x 16 KB
+  uint8_t* sV = smem + 16384 * 3;          // 2 x 16 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 16384 * 5);
+  uint64_t* q_full = bars;                 // once per item
+  uint64_t* q_empty = bars + 1;            // last S MMA of an item retired
+  uint64_t* k_full = bars + 2;             // [2]
+  uint64_t* k_empty = bars + 4;            // [2]
+  uint64_t* v_full = bars + 6;             // [2]
+  uint64_t* v_empty = bars + 8;            // [2]
+  uint64_t* s_ready = bars + 10;           // per key block
+  uint64_t* p_ready = bars + 11;           // 128 threads, per key block
+  uint64_t* o_ready = bars + 12;           // per item: last P V retired
+  uint64_t* o_read = bars + 13;            // 128 threads, per item: accumulator read out
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 128) {
+    tma_prefetch_desc(&tmap_qkv);
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+    }
+    mbar_init(s_ready, 1);
+    mbar_init(p_ready, 128);
+    mbar_init(o_ready, 1);
+    mbar_init(o_read, 128);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tS = *tmem_slot, tO = tS + 128;
+
+  auto coords = [&](int item, int& row0, int& qb, int& head, int& bh, int& seqlen, int& nkb) {
+    bh = item / nqb;
+    qb = item - bh * nqb;
+    const int b = bh / p.h;
+    head = bh - b * p.h;
+    row0 = b * p.S;
+    seqlen = min(__ldg(p.seqlens + b), p.S);
+    nkb = max(1, (seqlen + TILE - 1) / TILE);
+  };
+
+  if (warp == 5) {
+    if (lane == 0) {                       // ---------------- TMA producer
+      uint32_t g = 0, n = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+        int row0, qb, head, bh, seqlen, nkb;
+        coords(item, row0, qb, head, bh, seqlen, nkb);
+        if (n > 0) mbar_wait(q_empty, (n - 1) & 1);
+        mbar_arrive_expect_tx(q_full, 16384);
+        tma_load_2d(sQ, &tmap_qkv, q_full, head * HD, row0 + qb * TILE);
+        for (int j = 0; j < nkb; ++j, ++g) {
+          const int st = g & 1;
+          if (g >= 2) mbar_wait(&k_empty[st], ((g >> 1) - 1) & 1);
+          mbar_arrive_expect_tx(&k_full[st], 16384);
+          tma_load_2d(sK + st * 16384, &tmap_qkv, &k_full[st], p.H + head * HD, row0 + j * TILE);
+          if (g >= 2) mbar_wait(&v_empty[st], ((g >> 1) - 1) & 1);
+          mbar_arrive_expect_tx(&v_full[st], 16384);
+          tma_load_2d(sV + st * 16384, &tmap_qkv, &v_full[st], 2 * p.H + head * HD, row0 + j * TILE);
+        }
+      }
+    }
+  } else if (warp == 4) {
+    if (lane == 0) {                       // ---------------- MMA issuer
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, false, true);
+      const uint64_t dq = umma_smem_desc_sw128(smem_u32(sQ), 16, 1024);
+      uint32_t g = 0, n = 0;
+      auto issue_s = [&](uint32_t gg) {
+        const int st = gg & 1;
+        mbar_wait(&k_full[st], (gg >> 1) & 1);
+        tc_fence_after();
+        const uint64_t dk = umma_smem_desc_sw128(smem_u32(sK + st * 16384), 16, 1024);
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) umma_bf16_ss(tS, dq + 2 * kk, dk + 2 * kk, idesc_s, kk > 0);
+        umma_commit(s_ready);
+        umma_commit(&k_empty[st]);
+      };
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+        int row0, qb, head, bh, seqlen, nkb;
+        coords(item, row0, qb, head, bh, seqlen, nkb);
+        mbar_wait(q_full, n & 1);
+        issue_s(g);                                            // S_0 (the previous item's last P V is ahead of it in the pipe)
+        for (int j = 0; j < nkb; ++j, ++g) {
+          const int st = g & 1;
+          if (j == 0 && n > 0) mbar_wait(o_read, (n - 1) & 1); // previous item's accumulator has been read out
+          mbar_wait(p_ready, g & 1);
+          mbar_wait(&v_full[st], (g >> 1) & 1);
+          tc_fence_after();
+          const uint32_t av = smem_u32(sV + st * 16384);
+#pragma unroll
+          for (int kk = 0; kk < TILE / 16; ++kk)
+            umma_bf16_ts(tO, tS + kk * 8, umma_smem_desc_sw128(av + kk * 2048, 8192, 1024), idesc_o, (j > 0 || kk > 0));
+          umma_commit(&v_empty[st]);
+          if (j + 1 < nkb) {
+            issue_s(g + 1);                                    // right behind the P V: overwrites S | P in issue order
+          } else {
+            umma_commit(o_ready);
+            umma_commit(q_empty);
+          }
+        }
+      }
+    }
+  } else {
+    const int r = warp * 32 + lane;
+    const uint32_t lane_base = uint32_t(warp * 32) << 16;
+    const float c_scale = p.scale * LOG2E;
+    const bool drop = p.thresh16 != 0;
+    const float lk = drop ? log2f(p.inv_keep) : 0.f;
+    const uint32_t T = p.thresh16 << 16;
+    const PhiloxKeys keys = philox_keys(drop ? p.seed.value() : 0ull);
+    uint32_t g = 0, n = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+      int row0, qb, head, bh, seqlen, nkb;
+      coords(item, row0, qb, head, bh, seqlen, nkb);
+      const int q = qb * TILE + r;
+      const uint64_t e8row = (((uint64_t)bh * p.S + (uint64_t)q) * (uint64_t)p.S) >> 3;
+      float m = -INFINITY, l = 0.f;
+      for (int j = 0; j < nkb; ++j, ++g) {
+        const int kvalid = seqlen - j * TILE;
+        mbar_wait(s_ready, g & 1);
+        tc_fence_after();
+        const float mb = fmaxf(row_max_128(tS + lane_base, kvalid) * c_scale, -1e30f);
+        // lazy running maximum: keep the old reference while this block stays within 2^8 of it
+        const bool raise = mb > m + 8.f;
+        if (j > 0 && __any_sync(0xffffffffu, raise)) {         // rescale this thread's accumulator row (warp-uniform branch)
+          const float f = raise ? ex2_approx(m - mb) : 1.f;
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t o[32];
+            tmem_ld_32x32(tO + lane_base + hh * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int t = 0; t < 32; ++t) o[t] = __float_as_uint(__uint_as_float(o[t]) * f);
+            tmem_st_32x32(tO + lane_base + hh * 32, o);
+          }
+          l *= f;
+        }
+        if (raise) m = mb;
+        l += row_softmax_128(tS + lane_base, kvalid, c_scale, lk - m, drop, keys, e8row + (uint64_t)(j * (TILE / 8)),
+                             p.stream, T);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(p_ready);
+      }
+      // ---- epilogue: accumulator / row sum -> context
+      mbar_wait(o_ready, n & 1);
+      tc_fence_after();
+      const float inv_l = 1.f / l;
+      const bool q_ok = q < p.S;
+      __nv_bfloat16* dst = p.ctx + (size_t)(row0 + q) * p.H + head * HD;
+      float amax = 0.f;
+      const float qscale = p.f8.q ? p.f8.meta[1] : 0.f;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t o[32];
+        tmem_ld_32x32(tO + lane_base + hh * 32, o);
+        tmem_ld_wait();
+        if (hh == 1) {
+          tc_fence_before();
+          mbar_arrive(o_read);
+        }
+        if (q_ok) {
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq)
+            *reinterpret_cast<uint4*>(dst + hh * 32 + gq * 8) = make_uint4(
+                pack_bf16(__uint_as_float(o[gq * 8]) * inv_l, __uint_as_float(o[gq * 8 + 1]) * inv_l),
+                pack_bf16(__uint_as_float(o[gq * 8 + 2]) * inv_l, __uint_as_float(o[gq * 8 + 3]) * inv_l),
+                pack_bf16(__uint_as_float(o[gq * 8 + 4]) * inv_l, __uint_as_float(o[gq * 8 + 5]) * inv_l),
+                pack_bf16(__uint_as_float(o[gq * 8 + 6]) * inv_l, __uint_as_float(o[gq * 8 + 7]) * inv_l));
+          if (p.f8.q) emit_fp8_row<4>(p.f8, (size_t)(row0 + q) * p.H + head * HD + hh * 32, o, inv_l, qscale, amax);
+        }
+      }
+      if (p.f8.q && amax > 0.f) atomicMax(reinterpret_cast<int*>(p.f8.meta), __float_as_int(isfinite(amax) ? amax : 3.0e38f));
+      if (q_ok) p.lse[(size_t)bh * p.S + q] = (m + log2f(l) - lk) * 0.6931471805599453f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tS, 256);
   }
 }
 
@@ -1245,6 +1733,263 @@ attn_bwd_single_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gri
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Round-2 backward, S <= 128: one THREAD per query row (scores, dP, lse and delta of a row never leave the thread),
+// persistent CTAs.  Same MMA chain as attn_bwd_single_kernel (S = Q K^T, dP = dO V^T -> P~ -> dV = P~^T dO;
+// dS -> dK = dS^T Q, dQ = dS K; dV / dK / dQ overwrite the consumed S / dP accumulators; one 32 KB buffer carries P~
+// and then dS), but
+//   * 12 instead of ~33 instructions per score element: 1 / keep_prob in the exponent, dS = p' * select(keep,
+//     dP * scale + c, c) with the row constants folded, hoisted Philox keys, in-place 16-bit keep compares, no
+//     shared-memory exchange for delta = <dO, O> (one thread computes the whole row dot product);
+//   * the loop over (batch, head) items keeps TMEM / barriers alive, V of the next item streams in under the
+//     softmax-gradient math and Q / K / dO under the epilogue stores.
+// 96 KB, 256 TMEM columns, 160 threads -> two CTAs per SM.
+// ------------------------------------------------------------------------------------------------
+template <bool FULL, bool DROP>
+__device__ __forceinline__ void dsoftmax_chunk16(const uint32_t (&sv)[16], const uint32_t (&dv)[16], uint32_t (&pw)[8],
+                                                 uint32_t (&dw)[8], float c_scale, float off, float a, float bq, int nvalid,
+                                                 const PhiloxKeys& keys, uint64_t e8, uint32_t stream, uint32_t T) {
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    float pd[8], ds[8];
+    uint4 r = make_uint4(0, 0, 0, 0);
+    if (DROP) r = philox7(keys, e8 + (uint64_t)g, stream);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      float pr = ex2_approx(fmaf(__uint_as_float(sv[g * 8 + t]), c_scale, off));   // P / keep_prob
+      if (!FULL && g * 8 + t >= nvalid) pr = 0.f;
+      const float u = fmaf(__uint_as_float(dv[g * 8 + t]), a, bq);                   // (dP / keep - delta) scale keep
+      const bool kp = DROP ? keep_bit(r, t, T) : true;
+      pd[t] = kp ? pr : 0.f;
+      ds[t] = pr * (kp ? u : bq);
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      pw[g * 4 + t] = pack_bf16(pd[2 * t], pd[2 * t + 1]);
+      dw[g * 4 + t] = pack_bf16(ds[2 * t], ds[2 * t + 1]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(ATT_ROW_THREADS, 2)
+attn_bwd_row_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
+                    const AttnArgs p, const int n_items) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;                      // 16 KB each
+  uint8_t* sV = smem + 16384;
+  uint8_t* sQ = smem + 16384 * 2;
+  uint8_t* sDO = smem + 16384 * 3;
+  uint8_t* sP = smem + 16384 * 4;          // 32 KB: P~, later dS
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 16384 * 6);
+  uint64_t* qkd_full = bars;               // Q, K, dO of an item landed
+  uint64_t* v_full = bars + 1;             // V landed
+  uint64_t* sdp_ready = bars + 2;          // S and dP complete (V is free)
+  uint64_t* pd_ready = bars + 3;           // 128 threads: P~ is in shared memory, S / dP consumed
+  uint64_t* dv_done = bars + 4;            // dV MMA retired: the buffer may be overwritten with dS
+  uint64_t* ds_ready = bars + 5;           // 128 threads: dS is in shared memory
+  uint64_t* fin = bars + 6;                // dK, dQ complete (Q, K, dO, the buffer are free)
+  uint64_t* acc_read = bars + 7;           // 128 threads: dQ / dK / dV read out of tensor memory
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 128) {
+    tma_prefetch_desc(&tmap_qkv);
+    tma_prefetch_desc(&tmap_do);
+    mbar_init(qkd_full, 1);
+    mbar_init(v_full, 1);
+    mbar_init(sdp_ready, 1);
+    mbar_init(pd_ready, 128);
+    mbar_init(dv_done, 1);
+    mbar_init(ds_ready, 128);
+    mbar_init(fin, 1);
+    mbar_init(acc_read, 128);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tS = tmem, tDP = tmem + 128, tDV = tmem, tDK = tmem + 64, tDQ = tmem + 128;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      constexpr uint32_t id_kk = umma_idesc_bf16(128, 128, false, false);  // [q x keys], both K-major
+      constexpr uint32_t id_tt = umma_idesc_bf16(128, 64, true, true);     // [keys x d] = X^T Y, both MN-major
+      constexpr uint32_t id_kt = umma_idesc_bf16(128, 64, false, true);    // [q x d] = dS K, A K-major, B MN-major
+      const uint32_t aq = smem_u32(sQ), ado = smem_u32(sDO), ak = smem_u32(sK), av = smem_u32(sV), ap = smem_u32(sP);
+      auto load_qkd = [&](int item) {
+        const int b = item / p.h, head = item - b * p.h;
+        mbar_arrive_expect_tx(qkd_full, 49152);
+        tma_load_2d(sK, &tmap_qkv, qkd_full, p.H + head * HD, b * p.S);
+        tma_load_2d(sQ, &tmap_qkv, qkd_full, head * HD, b * p.S);
+        tma_load_2d(sDO, &tmap_do, qkd_full, head * HD, b * p.S);
+      };
+      auto load_v = [&](int item) {
+        const int b = item / p.h, head = item - b * p.h;
+        mbar_arrive_expect_tx(v_full, 16384);
+        tma_load_2d(sV, &tmap_qkv, v_full, 2 * p.H + head * HD, b * p.S);
+      };
+      int item = blockIdx.x;
+      if (item < n_items) { load_qkd(item); load_v(item); }
+      for (uint32_t g = 0; item < n_items; item += gridDim.x, ++g) {
+        const int nitem = item + gridDim.x;
+        const uint32_t ph = g & 1;
+        if (g > 0) mbar_wait(acc_read, (g - 1) & 1);           // previous dQ / dK / dV drained
+        mbar_wait(qkd_full, ph);
+        mbar_wait(v_full, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk)   // S = Q K^T
+          umma_bf16_ss(tS, umma_smem_desc_sw128(aq + kk * 32, 16, 1024), umma_smem_desc_sw128(ak + kk * 32, 16, 1024), id_kk, kk > 0);
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk)   // dP = dO V^T
+          umma_bf16_ss(tDP, umma_smem_desc_sw128(ado + kk * 32, 16, 1024), umma_smem_desc_sw128(av + kk * 32, 16, 1024), id_kk, kk > 0);
+        umma_commit(sdp_ready);
+        mbar_wait(sdp_ready, ph);                              // V is free: the next one streams in under the math
+        if (nitem < n_items) load_v(nitem);
+        mbar_wait(pd_ready, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < TILE / 16; ++kk)   // dV = P~^T dO -> S[0,64)
+          umma_bf16_ss(tDV, umma_smem_desc_sw128(ap + kk * 2048, 16384, 1024), umma_smem_desc_sw128(ado + kk * 2048, 8192, 1024), id_tt, kk > 0);
+        umma_commit(dv_done);
+        mbar_wait(ds_ready, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < TILE / 16; ++kk)   // dK = dS^T Q -> S[64,128)
+          umma_bf16_ss(tDK, umma_smem_desc_sw128(ap + kk * 2048, 16384, 1024), umma_smem_desc_sw128(aq + kk * 2048, 8192, 1024), id_tt, kk > 0);
+#pragma unroll
+        for (int kk = 0; kk < TILE / 16; ++kk)   // dQ = dS K -> dP[0,64)
+          umma_bf16_ss(tDQ, umma_smem_desc_sw128(ap + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                       umma_smem_desc_sw128(ak + kk * 2048, 8192, 1024), id_kt, kk > 0);
+        umma_commit(fin);
+        mbar_wait(fin, ph);                                    // Q, K, dO free: next item streams in under the epilogue
+        if (nitem < n_items) load_qkd(nitem);
+      }
+    }
+  } else {
+    const int r = warp * 32 + lane;                            // query row == key row of the epilogue == TMEM lane
+    const uint32_t lane_base = uint32_t(warp * 32) << 16;
+    const float c_scale = p.scale * LOG2E;
+    const bool drop = p.thresh16 != 0;
+    const float lk = drop ? log2f(p.inv_keep) : 0.f;
+    const uint32_t T = p.thresh16 << 16;
+    const PhiloxKeys keys = philox_keys(drop ? p.seed.value() : 0ull);
+    const bool row_ok = r < p.S;
+    const float qscale8 = p.f8.q ? p.f8.meta[1] : 0.f;
+    float amax8 = 0.f;
+    uint32_t g = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++g) {
+      const uint32_t ph = g & 1;
+      const int b = item / p.h, head = item - b * p.h;
+      const int seqlen = min(__ldg(p.seqlens + b), p.S);
+      const size_t tok = (size_t)b * p.S + r;
+      // this row's O (global, issued before any wait) and log-sum-exp
+      uint4 ov[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        ov[c] = row_ok ? __ldg(reinterpret_cast<const uint4*>(p.ctx + tok * p.H + head * HD + c * 8)) : make_uint4(0, 0, 0, 0);
+      const float lse2 = row_ok ? __ldg(p.lse + (size_t)item * p.S + r) * LOG2E : 0.f;
+      mbar_wait(qkd_full, ph);
+      float dlt = 0.f;                                         // delta = <dO, O> of the row
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint4 dv = *reinterpret_cast<const uint4*>(sDO + r * 128 + ((c ^ (r & 7)) << 4));
+        const uint32_t aw[4] = {ov[c].x, ov[c].y, ov[c].z, ov[c].w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 x = unpack_bf16(aw[t]), y = unpack_bf16(dw[t]);
+          dlt = fmaf(x.x, y.x, fmaf(x.y, y.y, dlt));
+        }
+      }
+      const float off = lk - lse2;                             // p' = 2^(s c + off) = P / keep_prob
+      const float a = p.scale;                                 // dS = p' * (keep ? dP * scale + bq : bq)
+      const float bq = -dlt * p.scale / p.inv_keep;
+      const int kvalid = row_ok ? seqlen : 0;                  // rows beyond the sequence contribute nothing
+      const uint64_t e8row = (((uint64_t)item * p.S + (uint64_t)r) * (uint64_t)p.S) >> 3;
+      uint32_t dsp[64];                                        // this row's 128 dS values, packed bf16
+      mbar_wait(sdp_ready, ph);
+      tc_fence_after();
+      {
+        uint32_t sv[2][16], dv[2][16];
+        tmem_ld_32x16(tS + lane_base, sv[0]);
+        tmem_ld_32x16(tDP + lane_base, dv[0]);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {                          // 16-column chunks, the next one in flight
+          tmem_ld_wait();
+          if (c + 1 < 8) {
+            tmem_ld_32x16(tS + lane_base + (c + 1) * 16, sv[(c + 1) & 1]);
+            tmem_ld_32x16(tDP + lane_base + (c + 1) * 16, dv[(c + 1) & 1]);
+          }
+          const int nv = kvalid - c * 16;
+          uint32_t pw[8];
+          uint32_t (&dw)[8] = *reinterpret_cast<uint32_t (*)[8]>(&dsp[c * 8]);
+          const uint64_t e8 = e8row + (uint64_t)(2 * c);
+          if (nv >= 16) {
+            if (drop) dsoftmax_chunk16<true, true>(sv[c & 1], dv[c & 1], pw, dw, c_scale, off, a, bq, 16, keys, e8, p.stream, T);
+            else dsoftmax_chunk16<true, false>(sv[c & 1], dv[c & 1], pw, dw, c_scale, off, a, bq, 16, keys, e8, p.stream, T);
+          } else if (nv > 0) {
+            if (drop) dsoftmax_chunk16<false, true>(sv[c & 1], dv[c & 1], pw, dw, c_scale, off, a, bq, nv, keys, e8, p.stream, T);
+            else dsoftmax_chunk16<false, false>(sv[c & 1], dv[c & 1], pw, dw, c_scale, off, a, bq, nv, keys, e8, p.stream, T);
+          } else {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) { pw[t] = 0u; dw[t] = 0u; }
+          }
+          *reinterpret_cast<uint4*>(sP + p_chunk_offset(r, c * 2)) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+          *reinterpret_cast<uint4*>(sP + p_chunk_offset(r, c * 2 + 1)) = make_uint4(pw[4], pw[5], pw[6], pw[7]);
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();                                       // S / dP reads retired before dV may overwrite S
+      mbar_arrive(pd_ready);
+      mbar_wait(dv_done, ph);                                  // the tensor core no longer reads P~
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        *reinterpret_cast<uint4*>(sP + p_chunk_offset(r, i)) = make_uint4(dsp[i * 4], dsp[i * 4 + 1], dsp[i * 4 + 2], dsp[i * 4 + 3]);
+      fence_proxy_async();
+      mbar_arrive(ds_ready);
+      mbar_wait(fin, ph);
+      tc_fence_after();
+      // ---- epilogue: this thread's rows of dQ (query r), dK and dV (key r)
+      __nv_bfloat16* drow = p.dqkv + tok * 3 * p.H + head * HD;
+#pragma unroll
+      for (int w = 0; w < 3; ++w) {
+        const uint32_t src = w == 0 ? tDQ : (w == 1 ? tDK : tDV);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t v[32];
+          tmem_ld_32x32(src + lane_base + hh * 32, v);
+          tmem_ld_wait();
+          if (w == 2 && hh == 1) {                             // accumulators drained: the next item's MMAs may go
+            tc_fence_before();
+            mbar_arrive(acc_read);
+          }
+          if (row_ok) {
+            __nv_bfloat16* dst = drow + w * p.H + hh * 32;
+#pragma unroll
+            for (int gq = 0; gq < 4; ++gq)
+              *reinterpret_cast<uint4*>(dst + gq * 8) = make_uint4(
+                  pack_bf16(__uint_as_float(v[gq * 8]), __uint_as_float(v[gq * 8 + 1])),
+                  pack_bf16(__uint_as_float(v[gq * 8 + 2]), __uint_as_float(v[gq * 8 + 3])),
+                  pack_bf16(__uint_as_float(v[gq * 8 + 4]), __uint_as_float(v[gq * 8 + 5])),
+                  pack_bf16(__uint_as_float(v[gq * 8 + 6]), __uint_as_float(v[gq * 8 + 7])));
+            if (p.f8.q) emit_fp8_row<4>(p.f8, tok * 3 * p.H + (size_t)(w * p.H + head * HD + hh * 32), v, 1.f, qscale8, amax8);
+          }
+        }
+      }
+    }
+    if (p.f8.q) fp8_amax_commit(p.f8, amax8);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
 // dq_acc (fp32 [B*S, H]) -> q slots of dqkv (bf16 [B*S, 3H])
 __global__ void __launch_bounds__(256)
 attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, long long rows, int H, const Fp8Out f8) {
@@ -1288,6 +2033,29 @@ void attention_fwd(const void* qkv, const int* seqlens, void* ctx, float* lse, i
   const int H = h * d;
   CUtensorMap tm = make_tmap_2d_bf16(qkv, 3 * H, (uint64_t)B * S, 3 * H, 64, TILE);
   dim3 grid((S + TILE - 1) / TILE, B * h);
+  if (attn_row_enabled()) {                      // round-2 kernels: thread per query row, P in TMEM, persistent CTAs
+    static int sms = 0;
+    if (sms == 0) {
+      int dev;
+      B200_CUDA_CHECK(cudaGetDevice(&dev));
+      B200_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int nqb = (S + TILE - 1) / TILE, n_items = nqb * B * h;
+    if (S <= TILE) {
+      constexpr int SMEMR = 16384 * 3 + 1024 + 128;
+      static bool once = false;
+      if (!once) { B200_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEMR)); once = true; }
+      const int g = n_items < sms * 4 ? n_items : sms * 4;
+      attn_fwd_row_kernel<<<g, ATT_ROW_THREADS, SMEMR, st>>>(tm, a, n_items);
+    } else {
+      constexpr int SMEMS = 16384 * 5 + 1024 + 256;
+      static bool once = false;
+      if (!once) { B200_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEMS)); once = true; }
+      const int g = n_items < sms * 2 ? n_items : sms * 2;
+      attn_fwd_stream_kernel<<<g, ATT_STREAM_THREADS, SMEMS, st>>>(tm, a, n_items, nqb);
+    }
+    return;
+  }
   static const bool single_ok = []() { const char* e = getenv("B200_ATTN_FWD_SINGLE"); return !(e && e[0] == '0'); }();
   if (S <= TILE && single_ok) {
     constexpr int SMEM1 = 16384 * 3 + 1024 + 64 + 2048;
@@ -1307,13 +2075,13 @@ void attention_fwd(const void* qkv, const int* seqlens, void* ctx, float* lse, i
   }
 }
 
-// -1: follow B200_ATTN_BWD_PIPE (default off until the variant has been measured), 0 / 1: forced by the caller
+// -1: follow B200_ATTN_BWD_PIPE (default on), 0 / 1: forced by the caller
 static int g_bwd_pipe = -1;
-void attention_set_options(int bwd_pipe) { g_bwd_pipe = bwd_pipe; }
+void attention_set_options(int bwd_pipe, int row_kernels) { g_bwd_pipe = bwd_pipe; g_attn_row = row_kernels; }
 static bool attn_bwd_pipe_enabled() {
   if (g_bwd_pipe >= 0) return g_bwd_pipe != 0;
-  static const bool env_on = []() { const char* e = getenv("B200_ATTN_BWD_PIPE"); return e && e[0] == '1'; }();
-  return env_on;
+  static const bool env_on = []() { const char* e = getenv("B200_ATTN_BWD_PIPE"); return !(e && e[0] == '0'); }();
+  return env_on;    // default on since round 2: 188 vs 208 us at 16 x 512 (profiles/attn_bench_r2_pipe.jsonl)
 }
 
 void attention_bwd(const void* qkv, const int* seqlens, const void* ctx, const void* dctx, const float* lse,
@@ -1342,6 +2110,24 @@ void attention_bwd(const void* qkv, const int* seqlens, const void* ctx, const v
   static bool once = false;
   if (!once) { B200_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); once = true; }
   dim3 grid(nkb, B * h);
+  if (nkb == 1 && single_ok && attn_row_enabled()) {       // round-2 kernel: thread per query row, persistent CTAs
+    static int sms = 0;
+    if (sms == 0) {
+      int dev;
+      B200_CUDA_CHECK(cudaGetDevice(&dev));
+      B200_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    constexpr int SMEMR = 16384 * 6 + 1024 + 128;
+    static bool oncer = false;
+    if (!oncer) {
+      B200_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEMR));
+      oncer = true;
+    }
+    const int n_items = B * h;
+    const int g = n_items < sms * 2 ? n_items : sms * 2;
+    attn_bwd_row_kernel<<<g, ATT_ROW_THREADS, SMEMR, st>>>(tq, td, a, n_items);
+    return;
+  }
   if (nkb == 1 && single_ok) {                 // S <= 128: the two-CTAs-per-SM variant
     constexpr int SMEM1 = 16384 * 6 + 1024 + 128 + 1024;
     static bool once1 = false;

@@ -77,7 +77,7 @@ inline float* opt_f32(const c10::optional<Tensor>& t) {
 void gemm(Tensor a, Tensor b, Tensor out, int64_t layout, int64_t epi, c10::optional<Tensor> bias,
           c10::optional<Tensor> res, c10::optional<Tensor> aux_out, int64_t k_splits, int64_t block_n, double alpha,
           double p_drop, int64_t seed, int64_t stream_id, c10::optional<Tensor> scale_a, c10::optional<Tensor> scale_b,
-          bool a_e5m2, bool b_e5m2, bool allow_push) {
+          bool a_e5m2, bool b_e5m2, bool allow_push, c10::optional<Tensor> colsum) {
   const bool fp8 = scale_a.has_value() && scale_a->defined();
   if (fp8) {
     TORCH_CHECK(a.is_cuda() && b.is_cuda() && a.element_size() == 1 && b.element_size() == 1 && a.stride(1) == 1 &&
@@ -131,10 +131,17 @@ void gemm(Tensor a, Tensor b, Tensor out, int64_t layout, int64_t epi, c10::opti
     c.res = res->data_ptr(); c.ldr = (int)res->stride(0);
   }
   const bool needs_bias = epi == b200::EPI_BIAS || epi == b200::EPI_BIAS_GELU || epi == b200::EPI_BIAS_DROP_RES ||
-                          epi == b200::EPI_BIAS_TANH;
+                          epi == b200::EPI_BIAS_TANH || epi == b200::EPI_BIAS_GELU_DG;
   TORCH_CHECK(!needs_bias || c.bias != nullptr, "this epilogue needs a bias");
-  TORCH_CHECK(epi != b200::EPI_BIAS_GELU || c.aux_out != nullptr, "bias+gelu needs aux_out");
+  TORCH_CHECK((epi != b200::EPI_BIAS_GELU && epi != b200::EPI_BIAS_GELU_DG) || c.aux_out != nullptr, "bias+gelu needs aux_out");
   TORCH_CHECK(epi != b200::EPI_DGELU || c.res != nullptr, "dgelu needs res (the pre-activation)");
+  TORCH_CHECK(epi != b200::EPI_MUL || c.res != nullptr, "mul needs res");
+  if (colsum.has_value() && colsum->defined()) {
+    TORCH_CHECK(epi == b200::EPI_NONE || epi == b200::EPI_ADD || epi == b200::EPI_MUL,
+                "column sums are fused into the plain / add / mul epilogues only");
+    TORCH_CHECK(colsum->numel() == N && colsum->is_contiguous(), "colsum length");
+    c.colsum = opt_f32(colsum);
+  }
   TORCH_CHECK(epi != b200::EPI_BIAS_DROP_RES || c.res != nullptr, "bias+dropout+residual needs res");
   c.k_splits = (int)k_splits;
   c.alpha = (float)alpha;
@@ -509,6 +516,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("arena_adam", &arena_adam);
   m.def("attention_fwd", &attention_fwd);
   m.def("attention_bwd", &attention_bwd);
-  m.def("set_attention_options", [](int64_t bwd_pipe) { b200::attention_set_options((int)bwd_pipe); });
+  m.def("set_attention_options", [](int64_t bwd_pipe, int64_t row) { b200::attention_set_options((int)bwd_pipe, (int)row); });
   m.def("fused_allreduce_lamb", &fused_allreduce_lamb);
 }

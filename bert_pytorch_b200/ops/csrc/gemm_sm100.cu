@@ -55,6 +55,7 @@ struct GemmArgs {
   const __nv_bfloat16* bias;
   const __nv_bfloat16* res;
   int ldr;
+  float* colsum;             // optional fp32 column sums of the bf16 output (bias gradients)
   Seed seed;
   unsigned int stream;
   unsigned int drop_thresh16;
@@ -155,7 +156,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint32_t taddr,
       continue;
     }
     // ---- bias (same 32 values for every lane: broadcast loads)
-    if (p.epi == EPI_BIAS || p.epi == EPI_BIAS_GELU || p.epi == EPI_BIAS_DROP_RES || p.epi == EPI_BIAS_TANH) {
+    if (p.epi == EPI_BIAS || p.epi == EPI_BIAS_GELU || p.epi == EPI_BIAS_DROP_RES || p.epi == EPI_BIAS_TANH ||
+        p.epi == EPI_BIAS_GELU_DG) {
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         if (g * 8 < ncols) {
@@ -182,10 +184,27 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint32_t taddr,
       }
 #pragma unroll
       for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+    } else if (p.epi == EPI_BIAS_GELU_DG) {
+      float dg[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const GeluParts gp = gelu_parts(f[j]);
+        dg[j] = fmaf(f[j] * 0.3989422804014327f, gp.e, gp.Phi);
+        f[j] *= gp.Phi;
+      }
+      if (row_ok) {
+        __nv_bfloat16* a = p.aux_out + ooff;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          if (g * 8 < ncols)
+            *reinterpret_cast<uint4*>(a + g * 8) =
+                make_uint4(pack_bf16(dg[g * 8], dg[g * 8 + 1]), pack_bf16(dg[g * 8 + 2], dg[g * 8 + 3]),
+                           pack_bf16(dg[g * 8 + 4], dg[g * 8 + 5]), pack_bf16(dg[g * 8 + 6], dg[g * 8 + 7]));
+      }
     } else if (p.epi == EPI_BIAS_TANH) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) f[j] = tanhf(f[j]);
-    } else if (p.epi == EPI_BIAS_DROP_RES || p.epi == EPI_ADD || p.epi == EPI_DGELU) {
+    } else if (p.epi == EPI_BIAS_DROP_RES || p.epi == EPI_ADD || p.epi == EPI_DGELU || p.epi == EPI_MUL) {
       if (p.epi == EPI_BIAS_DROP_RES && p.drop_thresh16 != 0 && row_ok) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -209,6 +228,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint32_t taddr,
               if (p.epi == EPI_DGELU) {
                 f[g * 8 + 2 * t] *= dgelu_erf(rr.x);
                 f[g * 8 + 2 * t + 1] *= dgelu_erf(rr.y);
+              } else if (p.epi == EPI_MUL) {
+                f[g * 8 + 2 * t] *= rr.x;
+                f[g * 8 + 2 * t + 1] *= rr.y;
               } else {
                 f[g * 8 + 2 * t] += rr.x;
                 f[g * 8 + 2 * t + 1] += rr.y;
@@ -217,6 +239,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint32_t taddr,
           }
         }
       }
+    }
+    if (p.colsum != nullptr && row_ok) {   // small-problem path: one atomic per element (the pair kernel reduces in smem)
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) atomicAdd(p.colsum + n0 + j, __bfloat162float(__float2bfloat16(f[j])));
     }
     if (row_ok) {
       __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + ooff;
@@ -463,6 +490,9 @@ __device__ __forceinline__ void staged_pass(const GemmArgs& p, uint8_t* sC, uint
               if (p.epi == EPI_DGELU) {
                 f[g * 8 + 2 * t] *= dgelu_erf(rr.x);
                 f[g * 8 + 2 * t + 1] *= dgelu_erf(rr.y);
+              } else if (p.epi == EPI_MUL) {
+                f[g * 8 + 2 * t] *= rr.x;
+                f[g * 8 + 2 * t + 1] *= rr.y;
               } else {
                 f[g * 8 + 2 * t] += rr.x;
                 f[g * 8 + 2 * t + 1] += rr.y;
@@ -477,6 +507,90 @@ __device__ __forceinline__ void staged_pass(const GemmArgs& p, uint8_t* sC, uint
       *reinterpret_cast<uint4*>(sC + cstage_offset(r, col0 + g * 8)) =
           make_uint4(pack_bf16(f[g * 8], f[g * 8 + 1]), pack_bf16(f[g * 8 + 2], f[g * 8 + 3]),
                      pack_bf16(f[g * 8 + 4], f[g * 8 + 5]), pack_bf16(f[g * 8 + 6], f[g * 8 + 7]));
+  }
+}
+
+// Column sums of the finished bf16 tile in the staging buffer (bias gradients fused into a dgrad GEMM): thread t
+// owns the column pair (t & 127) over the row half (t >> 7); a warp reads 128 contiguous (swizzle-permuted) bytes of
+// one row per step -> conflict free.  Rows beyond M hold zeros (TMA zero-fills the operands), so no row guard.
+__device__ __forceinline__ void staged_colsum(const GemmArgs& p, const uint8_t* sC, int n_base, int t) {
+  const int col = (t & 127) * 2, rh = t >> 7;
+  const int n = n_base + col;
+  if (n >= p.N) return;
+  const uint32_t base = (uint32_t)((col >> 6) * 16384) + (uint32_t)((col & 7) * 2);
+  const int ck = (col & 63) >> 3;
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+  for (int r = rh * 64; r < rh * 64 + 64; ++r) {
+    const float2 f = unpack_bf16(*reinterpret_cast<const uint32_t*>(sC + base + r * 128 + ((ck ^ (r & 7)) << 4)));
+    s0 += f.x;
+    s1 += f.y;
+  }
+  atomicAdd(p.colsum + n, s0);
+  atomicAdd(p.colsum + n + 1, s1);
+}
+
+// FFN-1 epilogue (EPI_BIAS_GELU_DG): x = acc + bias, out = gelu(x), aux = gelu'(x) -- the activation AND its derivative
+// leave the GEMM, so neither a GELU pass nor a GELU' pass over HBM exists any more (the backward epilogue multiplies).
+// Entirely warp local: every epilogue warp owns 8 KB of the staging buffer (two [32 rows x 64 columns] 128B-swizzled
+// boxes), fills them from its TMEM lane quarter, and its elected lane sends them off with two TMA stores; the only
+// wait is for the warp's own previous stores, one round (64 columns of math) earlier.  No CTA-wide barrier.
+__device__ __forceinline__ void gelu_dg_warp(const GemmArgs& p, const CUtensorMap* tmap_out, const CUtensorMap* tmap_aux,
+                                             uint8_t* sW, uint32_t taddr, int lane, int half, int n_tile0, int row_box0,
+                                             float alpha, uint32_t tmem_empty_addr) {
+#pragma unroll 1
+  for (int rnd = 0; rnd < 2; ++rnd) {
+    const int col0 = half * 128 + rnd * 64;
+    const int n0 = n_tile0 + col0;
+    const bool live = n0 < p.N;              // warp uniform
+    uint32_t gq[32], dq[32];
+    if (live) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int nn = n0 + c * 32;
+        uint4 bq[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          bq[g] = nn + g * 8 < p.N ? __ldg(reinterpret_cast<const uint4*>(p.bias + nn + g * 8)) : make_uint4(0, 0, 0, 0);
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + col0 + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint32_t w[4] = {bq[g].x, bq[g].y, bq[g].z, bq[g].w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 bb = unpack_bf16(w[t]);
+            const float x0 = fmaf(__uint_as_float(v[g * 8 + 2 * t]), alpha, bb.x);
+            const float x1 = fmaf(__uint_as_float(v[g * 8 + 2 * t + 1]), alpha, bb.y);
+            const GeluParts a0 = gelu_parts(x0), a1 = gelu_parts(x1);
+            gq[c * 16 + g * 4 + t] = pack_bf16(x0 * a0.Phi, x1 * a1.Phi);
+            dq[c * 16 + g * 4 + t] = pack_bf16(fmaf(x0 * 0.3989422804014327f, a0.e, a0.Phi),
+                                               fmaf(x1 * 0.3989422804014327f, a1.e, a1.Phi));
+          }
+        }
+      }
+    }
+    if (rnd == 1) {                          // this thread is done with the accumulator
+      tc_fence_before();
+      mbar_arrive_cluster(tmem_empty_addr);
+    }
+    if (!live) continue;
+    if (lane == 0) tma_store_wait_read<0>();  // the warp's previous boxes have left shared memory
+    __syncwarp();
+#pragma unroll
+    for (int ck = 0; ck < 8; ++ck) {
+      const uint32_t off = (uint32_t)(lane * 128 + ((ck ^ (lane & 7)) << 4));
+      *reinterpret_cast<uint4*>(sW + off) = make_uint4(gq[ck * 4], gq[ck * 4 + 1], gq[ck * 4 + 2], gq[ck * 4 + 3]);
+      *reinterpret_cast<uint4*>(sW + 4096 + off) = make_uint4(dq[ck * 4], dq[ck * 4 + 1], dq[ck * 4 + 2], dq[ck * 4 + 3]);
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(tmap_out, sW, n0, row_box0);
+      tma_store_2d(tmap_aux, sW + 4096, n0, row_box0);
+      tma_store_commit();
+    }
   }
 }
 
@@ -674,7 +788,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int half = (warp - 2) >> 2;
     const bool staged = !(p.epi == EPI_ACCUM_F32 || p.epi == EPI_F32);
     const bool use_res = staged && p.res != nullptr &&
-                         (p.epi == EPI_BIAS_DROP_RES || p.epi == EPI_ADD || p.epi == EPI_DGELU);
+                         (p.epi == EPI_BIAS_DROP_RES || p.epi == EPI_ADD || p.epi == EPI_DGELU || p.epi == EPI_MUL);
     const bool issuer = threadIdx.x == 64;   // first epilogue thread drives the staging tile's TMA traffic
     const int r = q * 32 + lane;             // row inside the CTA tile == TMEM lane
     const unsigned long long seed = p.drop_thresh16 != 0 ? p.seed.value() : 0ull;
@@ -706,6 +820,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), 0));
         continue;
       }
+      if (p.epi == EPI_BIAS_GELU_DG) {       // warp-local staging + stores, no CTA-wide barrier (see gelu_dg_warp)
+        gelu_dg_warp(p, &tmap_out, &tmap_aux, sC + (warp - 2) * 8192, taddr, lane, half, nb * PAIR_N, row0 + q * 32, alpha,
+                     mapa_shared(smem_u32(&tmem_empty[as]), 0));
+        continue;
+      }
       if (use_res) {
         mbar_wait(c_full, c_phase);
         c_phase ^= 1;
@@ -734,12 +853,19 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int j = 0; j < 4; ++j)
           if (nb * PAIR_N + j * 64 < p.N) tma_store_2d(&tmap_out, sC + j * 16384, nb * PAIR_N + j * 64, row0);
         tma_store_commit();
+      }
+      if (p.colsum != nullptr) staged_colsum(p, sC, nb * PAIR_N, (int)threadIdx.x - 64);   // while the stores drain
+      if (issuer) {
         tma_store_wait_read<0>();                         // staging tile free again
         if (use_res && si + 1 < nseg) load_res(seg_get(p, cluster_id, nclusters, si + 1).mn);
       }
       epi_bar_sync();                                     // nobody touches the staging tile before that
     }
-    if (staged && issuer) tma_store_wait<0>();
+    if (p.epi == EPI_BIAS_GELU_DG) {
+      if (lane == 0) tma_store_wait<0>();
+    } else if (staged && issuer) {
+      tma_store_wait<0>();
+    }
   }
 
   tc_fence_before();
@@ -862,6 +988,7 @@ static void launch(const GemmCall& c, cudaStream_t st) {
   p.out = c.out; p.ldo = c.ldo; p.aux_out = reinterpret_cast<__nv_bfloat16*>(c.aux_out);
   p.bias = reinterpret_cast<const __nv_bfloat16*>(c.bias);
   p.res = reinterpret_cast<const __nv_bfloat16*>(c.res); p.ldr = c.ldr;
+  p.colsum = c.colsum;
   p.seed = Seed{c.seed, c.seed_step}; p.stream = c.stream;
   float pd = c.p_drop;
   p.drop_thresh16 = pd > 0.f ? (unsigned)(pd * 65536.f + 0.5f) : 0u;
@@ -902,6 +1029,7 @@ static void launch_pair(const GemmCall& c, cudaStream_t st) {
   p.out = c.out; p.ldo = c.ldo; p.aux_out = reinterpret_cast<__nv_bfloat16*>(c.aux_out);
   p.bias = reinterpret_cast<const __nv_bfloat16*>(c.bias);
   p.res = reinterpret_cast<const __nv_bfloat16*>(c.res); p.ldr = c.ldr;
+  p.colsum = c.colsum;
   p.seed = Seed{c.seed, c.seed_step}; p.stream = c.stream;
   float pd = c.p_drop;
   p.drop_thresh16 = pd > 0.f ? (unsigned)(pd * 65536.f + 0.5f) : 0u;
@@ -941,8 +1069,10 @@ static void launch_pair(const GemmCall& c, cudaStream_t st) {
                         : make_tmap_2d(c.B, c.K, c.N, c.ldb, BK, 128, ES);
   const bool f32_out = c.epi == EPI_ACCUM_F32 || c.epi == EPI_F32;
   // output / pre-activation / residual tiles of one CTA travel as 4 boxes of [128 rows x 64 columns]
-  CUtensorMap to = f32_out ? ta : make_tmap_2d_bf16(c.out, c.N, c.M, c.ldo, 64, 128);
-  CUtensorMap tx = (c.aux_out != nullptr && !f32_out) ? make_tmap_2d_bf16(c.aux_out, c.N, c.M, c.ldo, 64, 128) : to;
+  // (EPI_BIAS_GELU_DG: every epilogue warp stores its own [32 rows x 64 columns] boxes)
+  const uint32_t obox = c.epi == EPI_BIAS_GELU_DG ? 32 : 128;
+  CUtensorMap to = f32_out ? ta : make_tmap_2d_bf16(c.out, c.N, c.M, c.ldo, 64, obox);
+  CUtensorMap tx = (c.aux_out != nullptr && !f32_out) ? make_tmap_2d_bf16(c.aux_out, c.N, c.M, c.ldo, 64, obox) : to;
   CUtensorMap tr = (c.res != nullptr && !f32_out) ? make_tmap_2d_bf16(c.res, c.N, c.M, c.ldr, 64, 128) : to;
   auto kern = gemm_pair_kernel<A_MN, B_MN, FP8>;
   static bool configured = false;

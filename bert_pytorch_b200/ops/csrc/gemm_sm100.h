@@ -22,6 +22,9 @@ enum GemmEpilogue : int {
   EPI_ACCUM_F32 = 6,      // out(fp32) += alpha*acc   (atomic when split-K)
   EPI_BIAS_TANH = 7,      // out = tanh(acc + bias)
   EPI_F32 = 8,            // out(fp32) = alpha*acc
+  EPI_BIAS_GELU_DG = 9,   // x = acc + bias ; out = gelu(x) ; aux_out = gelu'(x)   (FFN-1: the activation and its
+                          // derivative leave the GEMM together, the backward pass only multiplies -- K16)
+  EPI_MUL = 10,           // out = acc * res          (FFN-2 dgrad: res = gelu'(x) saved by EPI_BIAS_GELU_DG)
 };
 
 struct GemmCall {
@@ -35,6 +38,7 @@ struct GemmCall {
   void* aux_out = nullptr;
   const void* bias = nullptr;
   const void* res = nullptr; int ldr = 0;
+  float* colsum = nullptr;   // optional (bf16 epilogues): colsum[n] += sum_m out[m][n]  (bias gradients, fp32 atomics)
   int k_splits = 1;
   unsigned long long seed = 0; unsigned int stream = 0; float p_drop = 0.f;
   const unsigned long long* seed_step = nullptr;   // device step counter mixed into the seed (CUDA-graph replays)

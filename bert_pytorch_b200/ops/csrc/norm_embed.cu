@@ -392,6 +392,191 @@ ln_bwd2_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __rest
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Round-2 fast paths (H == CHUNKS * 256, no fp8 side output).  ncu on the kernels above: ~60 % issue-slot
+// utilisation at 15-22 % DRAM throughput -- they are instruction bound (per-row reductions, barriers and address
+// arithmetic amortised over only 8 elements per lane), so these variants cut instructions per element:
+//   forward : one warp owns a whole row (32 elements per lane): shuffle-only statistics, exact two-pass variance in
+//             registers, gamma / beta from shared memory (conflict-free float4 layout); ~8 instructions per element
+//   backward: same lane-owns-8-columns layout as ln_bwd2 (the column sums for dgamma / dbeta / dbias must stay in
+//             registers of a fixed lane) but without bounds predicates, with the per-row constants folded into two
+//             FFMAs per element, one 64-bit Philox counter computation per row.
+// ------------------------------------------------------------------------------------------------
+template <int CHUNKS>
+__global__ void __launch_bounds__(256)
+ln_fwd_row_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                  __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int M,
+                  float eps) {
+  constexpr int H = CHUNKS * 256;
+  __shared__ float4 sg[CHUNKS][2][32], sb[CHUNKS][2][32];   // [chunk][half of the lane's 8 columns][lane]
+  for (int i = threadIdx.x; i < CHUNKS * 64; i += blockDim.x) {
+    const int c = i >> 6, h = (i >> 5) & 1, l = i & 31;
+    sg[c][h][l] = __ldg(reinterpret_cast<const float4*>(gamma + c * 256 + l * 8 + h * 4));
+    sb[c][h][l] = __ldg(reinterpret_cast<const float4*>(beta + c * 256 + l * 8 + h * 4));
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int stride = gridDim.x * 8;
+  int row = blockIdx.x * 8 + warp;
+  uint4 nx[CHUNKS];
+  if (row < M) {
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) nx[c] = ld_stream16(x + (size_t)row * H + c * 256 + lane * 8);
+  }
+  for (; row < M; row += stride) {
+    float v[CHUNKS][8];
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) unpack8(nx[c], v[c]);
+    const int nrow = row + stride;
+    if (nrow < M) {                        // next row in flight while this one is reduced
+#pragma unroll
+      for (int c = 0; c < CHUNKS; ++c) nx[c] = ld_stream16(x + (size_t)nrow * H + c * 256 + lane * 8);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c)
+#pragma unroll
+      for (int t = 0; t < 8; ++t) s += v[c][t];
+    const float mean = warp_sum(s) * (1.0f / (float)H);
+    float q = 0.f;
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c)
+#pragma unroll
+      for (int t = 0; t < 8; ++t) { v[c][t] -= mean; q = fmaf(v[c][t], v[c][t], q); }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / (float)H) + eps);
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+      const float4 g0 = sg[c][0][lane], g1 = sg[c][1][lane], b0 = sb[c][0][lane], b1 = sb[c][1][lane];
+      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int t = 0; t < 8; ++t) v[c][t] = fmaf(v[c][t] * rstd, g[t], b[t]);
+      store8(y + (size_t)row * H + c * 256 + lane * 8, v[c]);
+    }
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+  }
+}
+
+template <int WPR, int GROUPS>
+__global__ void __launch_bounds__(GROUPS * WPR * 32)
+ln_bwd3_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+               __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dxd, float* __restrict__ partial, int M,
+               Seed seed_in, unsigned int drop_stream, unsigned int thresh16, float drop_scale) {
+  constexpr int H = WPR * 256;
+  __shared__ float2 xchg[GROUPS][2][WPR];
+  __shared__ float comb[GROUPS - 1 > 0 ? GROUPS - 1 : 1][3][H];
+  const unsigned long long seed = thresh16 != 0 ? seed_in.value() : 0ull;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int group = warp / WPR, wi = warp % WPR;
+  const int col = (wi * 32 + lane) * 8;
+  float g[8], ag[8], ab[8], ad[8];
+  {
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + col + 4));
+    g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
+  }
+#pragma unroll
+  for (int t = 0; t < 8; ++t) ag[t] = ab[t] = ad[t] = 0.f;
+  const int stride = gridDim.x * GROUPS;
+  int row = blockIdx.x * GROUPS + group;
+  uint4 nd = make_uint4(0, 0, 0, 0), nv = make_uint4(0, 0, 0, 0);
+  float nmu = 0.f, nrs = 0.f;
+  if (row < M) {
+    nd = ld_stream16(dy + (size_t)row * H + col);
+    nv = ld_stream16(x + (size_t)row * H + col);
+    nmu = __ldg(mean + row);
+    nrs = __ldg(rstd + row);
+  }
+  constexpr float invH = 1.0f / (float)H;
+  for (int it = 0; row < M; row += stride, ++it) {
+    float d[8], v[8];
+    unpack8(nd, d);
+    unpack8(nv, v);
+    const float rs = nrs, nmr = -nmu * nrs;
+    const int nrow = row + stride;
+    if (nrow < M) {                        // next row's loads are in flight across this row's barrier
+      nd = ld_stream16(dy + (size_t)nrow * H + col);
+      nv = ld_stream16(x + (size_t)nrow * H + col);
+      nmu = __ldg(mean + nrow);
+      nrs = __ldg(rstd + nrow);
+    }
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const float xh = fmaf(v[t], rs, nmr);
+      const float dg = d[t] * g[t];
+      ag[t] = fmaf(d[t], xh, ag[t]);
+      ab[t] += d[t];
+      s1 += dg;
+      s2 = fmaf(dg, xh, s2);
+      v[t] = xh;
+      d[t] = dg;
+    }
+    // row sums across the WPR warps of this group: one named barrier per row, slots double buffered by parity
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (WPR > 1) {
+      float2* slot = xchg[group][it & 1];
+      if (lane == 0) slot[wi] = make_float2(s1, s2);
+      asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(WPR * 32) : "memory");
+      s1 = 0.f; s2 = 0.f;
+#pragma unroll
+      for (int w = 0; w < WPR; ++w) { const float2 u = slot[w]; s1 += u.x; s2 += u.y; }
+    }
+    const float c1 = -rs * s1 * invH, c2 = -rs * s2 * invH;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) d[t] = fmaf(v[t], c2, fmaf(d[t], rs, c1));   // rs (dg - mean(dg) - xh mean(dg xh))
+    const size_t off = (size_t)row * H + col;
+    store8(dx + off, d);
+    if (dxd != nullptr) {
+      if (thresh16 != 0) {
+        const Keep8 keep = dropout_keep8(seed, drop_stream, (uint64_t)row * (uint64_t)(H / 8) + (uint64_t)(col >> 3), thresh16);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) d[t] = keep[t] ? d[t] * drop_scale : 0.f;
+      }
+#pragma unroll
+      for (int t = 0; t < 8; ++t) ad[t] += d[t];
+      store8(dxd + off, d);
+    }
+  }
+  // combine the row groups of the block in shared memory, then one atomic per column and quantity
+  if (GROUPS > 1) {
+    if (group > 0) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        comb[group - 1][0][col + t] = ag[t];
+        comb[group - 1][1][col + t] = ab[t];
+        comb[group - 1][2][col + t] = ad[t];
+      }
+    }
+    __syncthreads();
+    if (group == 0) {
+#pragma unroll
+      for (int gidx = 0; gidx < GROUPS - 1; ++gidx)
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          ag[t] += comb[gidx][0][col + t];
+          ab[t] += comb[gidx][1][col + t];
+          ad[t] += comb[gidx][2][col + t];
+        }
+    }
+  }
+  if (group == 0) {           // per-block partial column sums; colsum_finalize_kernel adds them into the gradient arena
+    // (444 blocks x 3072 same-address atomics at the end of the kernel serialise in L2: measured 2x slower)
+    float* dst = partial + (size_t)blockIdx.x * 3 * H + col;
+    *reinterpret_cast<float4*>(dst) = make_float4(ag[0], ag[1], ag[2], ag[3]);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(ag[4], ag[5], ag[6], ag[7]);
+    *reinterpret_cast<float4*>(dst + H) = make_float4(ab[0], ab[1], ab[2], ab[3]);
+    *reinterpret_cast<float4*>(dst + H + 4) = make_float4(ab[4], ab[5], ab[6], ab[7]);
+    *reinterpret_cast<float4*>(dst + 2 * H) = make_float4(ad[0], ad[1], ad[2], ad[3]);
+    *reinterpret_cast<float4*>(dst + 2 * H + 4) = make_float4(ad[4], ad[5], ad[6], ad[7]);
+  }
+}
+
 // dst[k][col] += sum over blocks of partial[block][k][col]   (k = 0..2, any dst may be null)
 // grid (ceil(H/32), 3, Z), 256 threads: warp w sums rows w, w+8, ... of a 32-column strip (coalesced 128 B
 // per row), then the 8 warps are combined through shared memory.  Z > 1 (B200_LN_FINALIZE_SPLIT, opt-in) cuts the
@@ -728,13 +913,31 @@ static inline int ln2_grid(int M) {     // 2 rows per block at a time; 4 residen
   return g < 148 * 4 ? g : 148 * 4;
 }
 
+static bool ln_fast_enabled() {
+  static const bool on = []() { const char* e = getenv("B200_LN_FAST"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 void layer_norm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int M,
                     int H, float eps, Seed seed, unsigned int stream, float p_drop, Fp8Out f8, cudaStream_t st) {
   unsigned int th; float sc;
   drop_params(p_drop, th, sc);
+  if (ln_fast_enabled() && th == 0 && f8.q == nullptr && H % 256 == 0 && H <= 1024) {   // warp-per-row fast path
+    int g = (M + 7) / 8;
+    if (g > 148 * 4) g = 148 * 4;
+    const __nv_bfloat16* xp = (const __nv_bfloat16*)x;
+    __nv_bfloat16* yp = (__nv_bfloat16*)y;
+    switch (H / 256) {
+      case 1: ln_fwd_row_kernel<1><<<g, 256, 0, st>>>(xp, gamma, beta, yp, mean, rstd, M, eps); break;
+      case 2: ln_fwd_row_kernel<2><<<g, 256, 0, st>>>(xp, gamma, beta, yp, mean, rstd, M, eps); break;
+      case 3: ln_fwd_row_kernel<3><<<g, 256, 0, st>>>(xp, gamma, beta, yp, mean, rstd, M, eps); break;
+      default: ln_fwd_row_kernel<4><<<g, 256, 0, st>>>(xp, gamma, beta, yp, mean, rstd, M, eps); break;
+    }
+    return;
+  }
   static const bool two_rows = []() { const char* e = getenv("B200_LN_ROWS"); return e && e[0] == '2'; }();
-  if (two_rows) {                        // opt-in: two rows per warp group and iteration (not yet measured)
-    int g4 = (M + 3) / 4;                // 76 registers x 256 threads -> 3 resident blocks per SM: one exact wave
+  if (two_rows) {                        // measured slower than one row (24.6 vs 22.6 us): kept for reference only
+    int g4 = (M + 3) / 4;
     if (g4 > 148 * 3) g4 = 148 * 3;
     DISPATCH_WPR(H, (ln_fwd2x2_kernel<WPR><<<g4, 2 * WPR * 32, 0, st>>>(
         (const __nv_bfloat16*)x, gamma, beta, (__nv_bfloat16*)y, mean, rstd, M, H, eps, seed, stream, th, sc, f8)));
@@ -759,15 +962,33 @@ void layer_norm_bwd(const void* dy, const void* x, const float* mean, const floa
                     cudaStream_t st) {
   unsigned int th; float sc;
   drop_params(p_drop, th, sc);
+  static const int split = []() {
+    const char* e = getenv("B200_LN_FINALIZE_SPLIT");
+    const int z = e ? atoi(e) : 8;       // 8 slices: 39.9 vs 44.0 us for the pair of launches (elt_bench, round 2)
+    return z < 1 ? 1 : (z > 32 ? 32 : z);
+  }();
+  if (ln_fast_enabled() && f8.q == nullptr && (in_stream == 0xFFFFFFFFu || th == 0) && H % 256 == 0 && H <= 1024) {
+    const __nv_bfloat16 *dyp = (const __nv_bfloat16*)dy, *xp = (const __nv_bfloat16*)x;
+    __nv_bfloat16 *dxp = (__nv_bfloat16*)dx, *dxdp = (__nv_bfloat16*)dxd;
+    const int wpr = H / 256;
+    const int groups = wpr == 4 ? 2 : (wpr == 3 ? 2 : (wpr == 2 ? 4 : 8));
+    int g = (M + groups - 1) / groups;
+    const int cap = ln2_bwd_grid(M);     // the workspace is sized for ln2_grid(M) >= this
+    if (g > cap) g = cap;
+    switch (wpr) {
+      case 1: ln_bwd3_kernel<1, 8><<<g, 256, 0, st>>>(dyp, xp, mean, rstd, gamma, dxp, dxdp, workspace, M, seed, drop_stream, th, sc); break;
+      case 2: ln_bwd3_kernel<2, 4><<<g, 256, 0, st>>>(dyp, xp, mean, rstd, gamma, dxp, dxdp, workspace, M, seed, drop_stream, th, sc); break;
+      case 3: ln_bwd3_kernel<3, 2><<<g, 192, 0, st>>>(dyp, xp, mean, rstd, gamma, dxp, dxdp, workspace, M, seed, drop_stream, th, sc); break;
+      default: ln_bwd3_kernel<4, 2><<<g, 256, 0, st>>>(dyp, xp, mean, rstd, gamma, dxp, dxdp, workspace, M, seed, drop_stream, th, sc); break;
+    }
+    dim3 g2((H + 31) / 32, 3, split);
+    colsum_finalize_kernel<<<g2, 256, 0, st>>>(workspace, g, H, dgamma, dbeta, dxd ? dbias : nullptr);
+    return;
+  }
   const int grid = ln2_bwd_grid(M);
   DISPATCH_WPR(H, (ln_bwd2_kernel<WPR><<<grid, 2 * WPR * 32, 0, st>>>(
       (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, gamma, (__nv_bfloat16*)dx, (__nv_bfloat16*)dxd,
       workspace, M, H, seed, drop_stream, in_stream, th, sc, f8)));
-  static const int split = []() {
-    const char* e = getenv("B200_LN_FINALIZE_SPLIT");
-    const int z = e ? atoi(e) : 1;
-    return z < 1 ? 1 : (z > 32 ? 32 : z);
-  }();
   dim3 g2((H + 31) / 32, 3, split);
   colsum_finalize_kernel<<<g2, 256, 0, st>>>(workspace, grid, H, dgamma, dbeta, dxd ? dbias : nullptr);
 }

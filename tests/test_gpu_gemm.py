@@ -130,3 +130,53 @@ def test_gemm_pair_many_tiles_and_tails():
         a, b = _rand(M, Kd), _rand(N, Kd)
         out = K_.gemm(a, b, layout=K_.NT, block_n=512)
         _check(out, a.float() @ b.float().t())
+
+
+def _gelu_and_grad(x):
+    x = x.double()
+    Phi = 0.5 * (1.0 + torch.erf(x / math.sqrt(2.0)))
+    phi = torch.exp(-0.5 * x * x) / math.sqrt(2.0 * math.pi)
+    return (x * Phi).float(), (Phi + x * phi).float()
+
+
+def _bf16_ulp_err(out, ref):
+    """|out - bf16(ref)| in units of bf16 ulps of the reference (floored at the ulp of 2^-14: below that the
+    activation is smaller than anything the next GEMM can resolve against O(1) neighbours)."""
+    ref = ref.float()
+    ulp = torch.exp2(torch.floor(torch.log2(ref.abs().clamp_min(2.0 ** -14))) - 7)
+    return ((out.float() - ref).abs() / ulp).max().item()
+
+
+@pytest.mark.parametrize("bn", [256, 512])
+@pytest.mark.parametrize("M,N,Kd", [(512, 1024, 256), (12288, 4096, 128), (300, 520, 64)])
+def test_gemm_bias_gelu_with_derivative(bn, M, N, Kd):
+    """EPI_BIAS_GELU_DG: out = gelu(x), aux = gelu'(x) with x = a b^T + bias (K16: both leave the FFN-1 epilogue)."""
+    K_ = _ops()
+    a, b, bias = _rand(M, Kd, scale=0.3), _rand(N, Kd, scale=0.3), _rand(N)
+    x = a.float() @ b.float().t() + bias.float()
+    g_ref, d_ref = _gelu_and_grad(x)
+    aux = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    out = K_.gemm(a, b, epi=K_.EPI_BIAS_GELU_DG, bias=bias, aux_out=aux, block_n=bn)
+    assert _bf16_ulp_err(out, g_ref) <= 1.01, _bf16_ulp_err(out, g_ref)
+    assert _bf16_ulp_err(aux, d_ref) <= 1.01, _bf16_ulp_err(aux, d_ref)
+
+
+@pytest.mark.parametrize("bn", [256, 512])
+@pytest.mark.parametrize("layout", ["NT", "NN"])
+def test_gemm_mul_and_colsum(bn, layout):
+    """EPI_MUL (+ fused column sums): the FFN-2 dgrad epilogue d_y1 = (d_y2 W2) * gelu'(x), bias gradient = colsum."""
+    K_ = _ops()
+    for (M, N, Kd) in [(512, 1024, 256), (12288, 4096, 64), (768, 520, 128)]:
+        a = _rand(M, Kd, scale=0.5)
+        b = _rand(N, Kd, scale=0.5) if layout == "NT" else _rand(Kd, N, scale=0.5)
+        res = _rand(M, N)
+        ref = (a.float() @ (b.float().t() if layout == "NT" else b.float())) * res.float()
+        cs = torch.randn(N, device="cuda")
+        cs0 = cs.clone()
+        out = K_.gemm(a, b, layout=getattr(K_, layout), epi=K_.EPI_MUL, res=res, colsum=cs, block_n=bn)
+        _check(out, ref)
+        want = cs0 + out.float().sum(0)
+        assert torch.allclose(cs, want, rtol=2e-3, atol=2e-2 * math.sqrt(M)), (cs - want).abs().max().item()
+        cs2 = torch.zeros(N, device="cuda")
+        out2 = K_.gemm(a, b, layout=getattr(K_, layout), epi=K_.EPI_ADD, res=res, colsum=cs2, block_n=bn)
+        assert torch.allclose(cs2, out2.float().sum(0), rtol=2e-3, atol=2e-2 * math.sqrt(M))

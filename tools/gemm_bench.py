@@ -81,6 +81,26 @@ def main():
                 mb_, msb = K.mx_quantize(b)
                 t = timeit(lambda: K.gemm_mx(ma, msa, mb_, msb))
                 rec["mxfp8_ms"], rec["mxfp8_tflops"] = round(t, 4), round(flops / t / 1e9, 1)
+        if "--epi" in sys.argv and name in ("ffn1_fwd", "ffn2_dgrad", "attn_out_fwd", "ffn2_fwd"):
+            # the fused epilogues the engine runs on this shape, against the plain bf16 store
+            o = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
+            if name == "ffn1_fwd":
+                bias, aux = torch.randn(n, device="cuda").bfloat16(), torch.empty_like(o)
+                t = timeit(lambda: K.gemm(a, b, layout=layout, out=o, epi=K.EPI_BIAS_GELU_DG, bias=bias, aux_out=aux))
+                rec["epi_bias_gelu_dg_tflops"] = round(flops / t / 1e9, 1)
+                t = timeit(lambda: K.gemm(a, b, layout=layout, out=o, epi=K.EPI_BIAS, bias=bias))
+                rec["epi_bias_tflops"] = round(flops / t / 1e9, 1)
+            elif name == "ffn2_dgrad":
+                res, cs = torch.randn(m, n, device="cuda").bfloat16(), torch.zeros(n, device="cuda")
+                t = timeit(lambda: K.gemm(a, b, layout=layout, out=o, epi=K.EPI_MUL, res=res, colsum=cs))
+                rec["epi_mul_colsum_tflops"] = round(flops / t / 1e9, 1)
+                t = timeit(lambda: K.gemm(a, b, layout=layout, out=o, epi=K.EPI_MUL, res=res))
+                rec["epi_mul_tflops"] = round(flops / t / 1e9, 1)
+            else:
+                bias, res = torch.randn(n, device="cuda").bfloat16(), torch.randn(m, n, device="cuda").bfloat16()
+                t = timeit(lambda: K.gemm(a, b, layout=layout, out=o, epi=K.EPI_BIAS_DROP_RES, bias=bias, res=res, p_drop=0.1,
+                                          seed=1, stream=3))
+                rec["epi_bias_drop_res_tflops"] = round(flops / t / 1e9, 1)
         out.append(rec)
         print(json.dumps(rec), flush=True)
 
