@@ -13,17 +13,22 @@ runs its stock fp16 autocast + GradScaler).  ``--phase 2`` selects seq 512 / mic
 Synthetic data of that shape, random-init weights (no network for corpora/checkpoints).
 
 One *step* = one optimizer step = ``--accum`` micro-batches (forward+backward each) + gradient
-reduction over the ranks + LAMB update.  Default ``--accum 32`` (3072 sequences/GPU/step): the shipped
-global batch of 65536 is 683 micro-batches per step on one GPU (~25 s/step), too long for a bench
-loop; a smaller accumulation only *raises* the optimizer/all-reduce share of a step, so the reported
-sequences/s is conservative w.r.t. the shipped config.  ``--global-batch 65536`` reproduces the shipped
-arithmetic exactly.  Per-GPU work is fixed as N grows -> weak scaling.
+reduction over the ranks + LAMB update.  Default accumulation = the shipped 8-GPU arithmetic of the config
+(`run_pretraining.py:218-228`: ceil(ceil(65536 / 8) / 96) = 86 micro-batches for phase 1, 256 for phase 2), i.e. on
+8 GPUs the default run IS global batch 65536; fewer GPUs keep the per-GPU work (weak scaling).
+``--global-batch G`` applies the shipped arithmetic to G for the actual world size.
+
+After the headline config (phase 1, bf16) the same process measures BASELINE.json's other GPU configs for a few
+steps each and reports them under ``extra.configs``: phase 2 (both arms), RoBERTa recipe with fp8 GEMM operands and
+phase 1 + K-FAC (this repo only).  ``--no-extras`` skips them.  At N > 1 the fused reduce-scatter + LAMB + all-gather
+kernel is first checked against NCCL all-reduce + single-GPU LAMB on the real arena (``extra.fused_parity_max_abs``)
+and its in-kernel timeline is reported (``extra.fused_step_timeline``).
 
 Timing: W >= 3 untimed warm-up steps, then exactly K steps bracketed by barrier + synchronize, CUDA
 events on the launching stream, max over ranks; an L2 flush (256 MB write) precedes every step and the
 per-step working set (~10 GB of activations) is far larger than the 126 MB L2 anyway; nvidia-smi
 clocks/throttle reasons are sampled during the timed region.
-``e2e`` repeats the measurement through the public training API (`pretrain.forward_backward_pass` /
+``e2e`` repeats the measurement (at most 6 timed steps) through the public training API (`pretrain.forward_backward_pass` /
 `take_optimizer_step`) with every micro-batch copied from pinned host memory inside the timed region and
 the loss read back to the host every optimizer step.
 """
@@ -59,13 +64,15 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--phase", type=int, default=1, choices=[1, 2])
-    ap.add_argument("--accum", type=int, default=32, help="micro-batches per optimizer step (ignored with --global-batch)")
+    ap.add_argument("--accum", type=int, default=0,
+                    help="micro-batches per optimizer step (default: the shipped 8-GPU arithmetic of the config: 86 / 256 / 64)")
     ap.add_argument("--global-batch", type=int, default=0, help="use the shipped ceil arithmetic for this global batch")
     ap.add_argument("--local-batch", type=int, default=0)
     ap.add_argument("--backend", default="fused", choices=["nccl", "fused"],
                     help="gradient reduction (ours): fused = one peer-memory kernel for reduce-scatter + LAMB + all-gather")
     ap.add_argument("--layers", type=int, default=0, help="debug only: fewer layers (marks the result invalid)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline config only (skip extra.configs)")
     ap.add_argument("--fp8", action="store_true", help="fp8 GEMM operands (separate config; the headline stays bf16)")
     ap.add_argument("--roberta", action="store_true",
                     help="RoBERTa-style recipe (seq 512, no NSP, cased vocabulary, linear decay) instead of --phase; ours only")
@@ -143,6 +150,49 @@ def max_over_ranks(x, dev):
     t = torch.tensor([x], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def min_over_ranks(x, dev):
+    return -max_over_ranks(-x, dev)
+
+
+def fused_parity(comm, arena, opt, dev, rank, world):
+    """Driver-side correctness proof of the fused reduce-scatter + LAMB + all-gather kernel (the driver's pytest box has
+    one GPU): one optimizer step on the REAL arena with per-rank pseudo-random gradients, once as NCCL all-reduce(avg)
+    + single-GPU arena LAMB and once through the peer-memory kernel; returns max |delta| over the bf16 weights every
+    rank holds afterwards and the fp32 master shard it owns, max over ranks.  State is restored."""
+    import torch
+    import torch.distributed as dist
+    from bert_pytorch_b200 import ops
+    P0, M0, V0 = arena.flat_param.clone(), arena.exp_avg.clone(), arena.exp_avg_sq.clone()
+    steps0 = [g.get("step", 0) for g in opt.param_groups]
+    gen = torch.Generator(device=dev).manual_seed(4242 + rank)
+    g = torch.randn(arena.numel, device=dev, generator=gen) * 0.05
+
+    def restore():
+        arena.flat_param.copy_(P0); arena.exp_avg.copy_(M0); arena.exp_avg_sq.copy_(V0)
+        for grp, st in zip(opt.param_groups, steps0):
+            grp["step"] = st
+        arena.flat_grad.zero_()
+    arena.flat_grad.copy_(g)
+    dist.all_reduce(arena.flat_grad)
+    arena.flat_grad.mul_(1.0 / world)
+    ops.arena_lamb_step(arena, opt)
+    ref = arena.flat_param.clone()
+    restore()
+    arena.flat_grad.copy_(g)
+    torch.cuda.synchronize(); dist.barrier()
+    comm.fused_lamb_step(opt, loss_scale=1.0)
+    torch.cuda.synchronize()
+    lo, hi = comm.lo, comm.hi
+    d_master = (arena.flat_param[lo:hi] - ref[lo:hi]).abs().max().item() if hi > lo else 0.0
+    d_shadow = (arena.flat_shadow.float() - ref.to(arena.flat_shadow.dtype).float()).abs().max().item()
+    restore()
+    arena.refresh_shadow()
+    if hasattr(comm, "_master_stale"):
+        comm._master_stale = False
+    torch.cuda.synchronize(); dist.barrier()
+    return {"fp32_master_shard": max_over_ranks(d_master, dev), "bf16_weights_all_ranks": max_over_ranks(d_shadow, dev)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -238,14 +288,23 @@ def run_ours(args, ph, B, accum, rank, world, dev):
         pretrain.take_optimizer_step(opt, precond, ddp, scaler)
         host_losses.append(float(window))
 
+    parity = None
+    if world > 1 and getattr(comm, "fuses_optimizer", False) and precond is None:
+        parity = fused_parity(comm, arena, opt, dev, rank, world)     # before anything is timed
     l0 = K.KERNEL_LAUNCHES
     ms, clocks = timed_steps(step_device, args.steps, args.warmup, flusher, dev)
+    timeline = None
+    if world > 1 and hasattr(comm, "timeline") and precond is None:
+        torch.cuda.synchronize()
+        tl = comm.timeline()                                          # last timed step, this rank
+        timeline = {k: [min_over_ranks(v, dev), max_over_ranks(v, dev)] for k, v in tl.items()}
     launches = (K.KERNEL_LAUNCHES - l0) * args.steps // (args.steps + args.warmup)
     e2e = None
     if not args.no_e2e:
-        ms_e2e, _ = timed_steps(step_e2e, args.steps, max(1, min(args.warmup, 2)), flusher, dev)
+        ke = min(args.steps, 6)
+        ms_e2e, _ = timed_steps(step_e2e, ke, max(1, min(args.warmup, 2)), flusher, dev)
         h2d = sum(t.numel() * t.element_size() for t in pool[0]) * accum
-        e2e = dict(ms=ms_e2e, h2d=h2d, d2h=4)
+        e2e = dict(ms=ms_e2e, h2d=h2d, d2h=4, steps=ke)
     final_loss = float(loss_acc) / max(1, (args.steps + args.warmup))
     torch.cuda.synchronize()
     opt_ms = [a.elapsed_time(b) for a, b in opt_events[args.warmup:args.warmup + args.steps]]
@@ -254,9 +313,15 @@ def run_ours(args, ph, B, accum, rank, world, dev):
             "fused reduce-scatter + LAMB + all-gather kernel, INCLUDING its wait for the slowest rank's backward "
             "(the kernel alone: tools/peer_check.py --big)" if getattr(comm, "fuses_optimizer", False) and world > 1
             else "LAMB kernels (all-reduce happens in the last micro-step)" if world > 1 else "LAMB kernels")
-    return ms, clocks, launches, e2e, dict(loss_mean=final_loss, backend=getattr(comm, "name", "single"),
-                                           optimizer_step_ms=None if opt_mean is None else round(opt_mean, 3),
-                                           optimizer_step_is=what)
+    extra = dict(loss_mean=final_loss, backend=getattr(comm, "name", "single"),
+                 optimizer_step_ms=None if opt_mean is None else round(opt_mean, 3), optimizer_step_is=what)
+    if parity is not None:
+        extra["fused_parity_max_abs"] = parity
+    if timeline is not None:
+        extra["fused_step_timeline"] = dict(timeline, note="[min, max] over ranks of the in-kernel %globaltimer split of the "
+                                            "last timed step; barrier_wait_ms = wait for the slowest rank's backward pass")
+    del ddp, model, arena, opt, comm, dev_pool, pool
+    return ms, clocks, launches, e2e, extra
 
 
 # ------------------------------------------------------------------------------------------------
@@ -320,10 +385,13 @@ def run_reference(args, ph, B, accum, rank, world, dev):
     ms, clocks = timed_steps(step_device, args.steps, args.warmup, flusher, dev)
     e2e = None
     if not args.no_e2e:
-        ms_e2e, _ = timed_steps(step_e2e, args.steps, max(1, min(args.warmup, 2)), flusher, dev)
+        ke = min(args.steps, 6)
+        ms_e2e, _ = timed_steps(step_e2e, ke, max(1, min(args.warmup, 2)), flusher, dev)
         h2d = sum(t.numel() * t.element_size() for t in pool[0]) * accum
-        e2e = dict(ms=ms_e2e, h2d=h2d, d2h=4 * accum)
-    return ms, clocks, 0, e2e, dict(backend="nccl-ddp", scaler=float(scaler.get_scale()))
+        e2e = dict(ms=ms_e2e, h2d=h2d, d2h=4 * accum, steps=ke)
+    extra = dict(backend="nccl-ddp", scaler=float(scaler.get_scale()))
+    del model, optimizer, dev_pool, pool
+    return ms, clocks, 0, e2e, extra
 
 
 def roofline(args, ph, seq_per_s_per_gpu: float) -> dict:
@@ -350,57 +418,52 @@ def roofline(args, ph, seq_per_s_per_gpu: float) -> dict:
         return {"error": repr(e)}
 
 
-def main():
-    args = parse()
-    if args.impl == "reference" and not os.path.exists(os.path.join(ROOT, "baseline", "_ref", "run_pretraining.py")):
-        print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref missing: the reference has no "
-                          "setup.py/pyproject.toml so pip cannot install it; copy /root/reference there"}))
-        return
-    import torch
-    if not torch.cuda.is_available():
-        print(json.dumps({"impl": args.impl, "unavailable": "no CUDA device"}))
-        return
+def shipped_accum(ph) -> int:
+    """Micro-batches per optimizer step of the shipped config on 8 GPUs (run_pretraining.py:218-228 arithmetic)."""
+    return math.ceil(math.ceil(ph["global_batch"] / 8) / ph["local_batch"])
+
+
+def run_config(args, rank, world, dev):
+    """One config on one arm -> the JSON record (rank 0 prints it)."""
     ph = dict(ROBERTA) if args.roberta else dict(PHASES[args.phase])
-    if (args.roberta or args.kfac) and args.impl != "ours":
-        print(json.dumps({"impl": args.impl, "unavailable": "--roberta / --kfac are measured for this repository only "
-                          "(the reference arm runs the two headline configs)"}))
-        return
-    rank, world, local, dev = dist_setup(args)
-    assert world == max(1, args.gpus) or world == 1, f"WORLD_SIZE={world} but --gpus {args.gpus}"
     B = args.local_batch or ph["local_batch"]
     if args.global_batch:
         accum = math.ceil(math.ceil(args.global_batch / world) / B)
     else:
-        accum = args.accum
+        accum = args.accum or shipped_accum(ph)
     global_batch = B * accum * world
     fn = run_reference if args.impl == "reference" else run_ours
     res = fn(args, ph, B, accum, rank, world, dev)
     if res is None:
-        if rank == 0:
-            print(json.dumps({"impl": "reference", "unavailable": "reference copy not found under baseline/_ref"}))
-        return
+        return None
     ms_local, clocks, launches, e2e, extra = res
     ms = max_over_ranks(ms_local, dev)
     value = global_batch / (ms / 1e3)
     extra = dict(extra)
     extra["roofline"] = roofline(args, ph, value / world)
+    ours = args.impl == "ours"
     out = {
         "metric": (f"RoBERTa-large recipe (seq{ph['seq']}, no NSP)" if args.roberta else f"BERT-large phase{args.phase} (seq{ph['seq']})")
         + (" + K-FAC" if args.kfac else "") + " pretraining sequences/sec, whole job, device-timed max over ranks",
         "value": round(value, 2), "unit": "sequences/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": ("fp8 GEMM operands (e4m3 fwd / e5m2 grads, per-tensor delayed scaling) + bf16" if args.fp8 else "bf16")
-        if args.impl == "ours" else "fp16 (reference stock AMP)", "data": "synthetic",
+        if ours else "fp16 (reference stock AMP)", "data": "synthetic",
         "impl": args.impl,
         "config": {"model": ("roberta-large-cased (BERT-large, no NSP) L24 H1024 A16 I4096 V29000" if args.roberta
                              else "bert-large-uncased L24 H1024 A16 I4096 V30528")
                    + (f" [DEBUG layers={args.layers}]" if args.layers else ""), "kfac": bool(args.kfac),
                    "global_batch": global_batch, "seq_len": ph["seq"], "local_batch": B, "accumulation_steps": accum,
-                   "max_predictions_per_seq": ph["max_pred"], "optimizer": "LAMB", "dropout": 0.1,
+                   "shipped_global_batch": ph["global_batch"], "max_predictions_per_seq": ph["max_pred"],
+                   "optimizer": "LAMB", "dropout": 0.1,
+                   "dtype": "bf16 operands, fp32 accumulate / master" + (" + fp8 GEMM operands" if args.fp8 else "") if ours
+                   else "fp16 autocast + GradScaler (stock)",
+                   "mlm_head": "masked-only (max_predictions_per_seq rows per sequence, same loss)" if ours
+                   else "dense (every position, as the reference computes it)",
                    "parallelism": f"dp{world}", "grad_reduction": extra.get("backend"),
                    "l2": "256MB L2 flush before every step; per-step working set (~10 GB activations) >> 126 MB L2",
-                   "note": "step = one optimizer step of accumulation_steps micro-batches incl. all-reduce + LAMB; "
-                           "shipped global batch 65536/32768 selectable with --global-batch"},
+                   "note": "step = one optimizer step of accumulation_steps micro-batches incl. gradient reduction + LAMB; "
+                           "default accumulation = shipped global batch on 8 GPUs (per-GPU work fixed: weak scaling)"},
         "clocks": {"sm_mhz": clocks.get("sm_mhz"), "sm_max_mhz": clocks.get("sm_max_mhz"),
                    "reasons": clocks.get("reasons"), "power_w_max": clocks.get("power_w_max"),
                    "samples": clocks.get("samples")},
@@ -411,7 +474,70 @@ def main():
         ms_e = max_over_ranks(e2e["ms"], dev)
         out["e2e"] = {"value": round(global_batch / (ms_e / 1e3), 2), "unit": "sequences/s",
                       "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"]),
-                      "ms_per_step": round(ms_e, 3)}
+                      "ms_per_step": round(ms_e, 3), "steps": int(e2e.get("steps", args.steps))}
+    return out
+
+
+def compact(rec: dict) -> dict:
+    """What extra.configs keeps of a sub-run."""
+    if rec is None:
+        return {"unavailable": "not measured"}
+    keep = {k: rec[k] for k in ("metric", "value", "unit", "ms_per_step", "steps", "warmup", "dtype", "gpu_launches") if k in rec}
+    keep["config"] = {k: rec["config"][k] for k in ("global_batch", "seq_len", "local_batch", "accumulation_steps", "kfac",
+                                                     "mlm_head", "grad_reduction") if k in rec["config"]}
+    keep["clocks"] = rec.get("clocks")
+    ex = rec.get("extra", {})
+    keep["extra"] = {k: ex[k] for k in ("loss_mean", "optimizer_step_ms", "roofline") if k in ex}
+    return keep
+
+
+def main():
+    args = parse()
+    if args.impl == "reference" and not os.path.exists(os.path.join(ROOT, "baseline", "_ref", "run_pretraining.py")):
+        print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref missing: the reference has no "
+                          "setup.py/pyproject.toml so pip cannot install it; copy /root/reference there"}))
+        return
+    import torch
+    if not torch.cuda.is_available():
+        print(json.dumps({"impl": args.impl, "unavailable": "no CUDA device"}))
+        return
+    if (args.roberta or args.kfac) and args.impl != "ours":
+        print(json.dumps({"impl": args.impl, "unavailable": "--roberta / --kfac are measured for this repository only "
+                          "(the reference arm runs the two headline configs)"}))
+        return
+    rank, world, local, dev = dist_setup(args)
+    assert world == max(1, args.gpus) or world == 1, f"WORLD_SIZE={world} but --gpus {args.gpus}"
+    out = run_config(args, rank, world, dev)
+    if out is None:
+        if rank == 0:
+            print(json.dumps({"impl": "reference", "unavailable": "reference copy not found under baseline/_ref"}))
+        return
+    headline = args.phase == 1 and not (args.roberta or args.kfac or args.fp8 or args.layers)
+    if headline and not args.no_extras:
+        # BASELINE.json configs #3-#5 in the same process, a few steps each (reduced accumulation: more optimizer /
+        # reduction share per unit compute than the shipped config, i.e. conservative)
+        import gc
+        import torch.distributed as dist
+        subs = [("phase2", dict(phase=2, accum=16))]
+        if args.impl == "ours":
+            subs += [("roberta_fp8", dict(roberta=True, fp8=True, accum=16)), ("kfac", dict(kfac=True, accum=16))]
+        configs = {}
+        for name, over in subs:
+            sub = argparse.Namespace(**vars(args))
+            sub.steps, sub.warmup, sub.no_e2e, sub.global_batch = min(args.steps, 4), 3, True, 0
+            for k, v in over.items():
+                setattr(sub, k, v)
+            gc.collect()
+            torch.cuda.empty_cache()
+            try:
+                if args.impl == "reference" and dist.is_initialized():   # the reference inits its own process group
+                    dist.barrier()
+                    dist.destroy_process_group()
+                    os.environ["MASTER_PORT"] = str(int(os.environ.get("MASTER_PORT", "29534")) + 7)
+                configs[name] = compact(run_config(sub, rank, world, dev))
+            except Exception as e:  # noqa: BLE001 - an extra config must never cost the headline line
+                configs[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        out["extra"]["configs"] = configs
     if rank == 0:
         print(json.dumps(out), flush=True)
     import torch.distributed as dist

@@ -260,6 +260,14 @@ class ShardedPretrainingDataset(torch.utils.data.Dataset):
             seg, imask = d["segment_ids"][lo:hi], d["input_mask"][lo:hi]
             masked = ids
             labels = labels_from_premasked(ids, d["masked_lm_positions"][lo:hi], d["masked_lm_ids"][lo:hi])
+            # legacy pre-masked shards carry their own number of targets: the fused MLM head compacts at most
+            # max_predictions_per_seq rows per sequence (static shapes), anything beyond would be dropped silently
+            #  -- refuse instead; the reference criterion would have used every label
+            if self.max_pred_per_seq > 0:
+                worst = int((labels >= 0).sum(axis=1).max()) if labels.size else 0
+                if worst > self.max_pred_per_seq:
+                    raise ValueError(f"pre-masked shard has {worst} masked tokens in one sequence but "
+                                     f"--max_predictions_per_seq is {self.max_pred_per_seq}; raise the flag")
         return [masked, seg, imask, labels, nsl]
 
     def _mask(self, ids, sp, rng):

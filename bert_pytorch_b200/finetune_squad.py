@@ -220,7 +220,12 @@ def main(argv=None) -> dict:
             scaler = GradScaler(init_scale=args.loss_scale if args.loss_scale else 2.0 ** 16,
                                 enabled=(compute_dtype == torch.float16), device=device)
         else:
+            # fp32 requested: plain PyTorch forward/backward on the fp32 master views (like finetune_ner); BertAdam
+            # is attached to the arena so zero_grad keeps p.grad inside flat_grad (what sync_gradients reduces) and
+            # every step refreshes the bf16 shadow that evaluation through the fused engine reads
+            model.bert.use_fused = False
             optimizer = BertAdam(groups, lr=args.learning_rate, warmup=args.warmup_proportion, t_total=total_steps)
+            optimizer.attach_arena(arena)
 
     summary: dict = {}
     global_step = 0

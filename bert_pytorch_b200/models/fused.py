@@ -565,8 +565,10 @@ class FusedPretrainer:
     def _max_pred(self, labels: torch.Tensor) -> int:
         # capacity of masked positions per sequence; fixed per run so shapes stay static
         if self.max_pred is None:
-            self.max_pred = min(labels.size(1), max(8, int((labels >= 0).sum(dim=1).max().item())))
-            self.max_pred = (self.max_pred + 7) // 8 * 8
+            # no --max_predictions_per_seq: the capacity is the sequence length (any batch fits; the static-shape head
+            # then costs S rows per sequence, so runners should always pass the flag -- data/dataset.py validates
+            # pre-masked shards against it)
+            self.max_pred = (labels.size(1) + 7) // 8 * 8
         return self.max_pred
 
     def _graph_ok(self) -> bool:

@@ -720,7 +720,7 @@ attn_fwd_row_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(p_ready);
-      const float inv_l = 1.f / l;                             // l carries the 1 / keep_prob of the exponent offset
+      const float inv_l = (drop ? p.inv_keep : 1.f) / l;       // l and the P V result both carry 1 / keep_prob
       __nv_bfloat16* dst = p.ctx + (size_t)(b * p.S + r) * p.H + head * HD;
       float amax = 0.f;
       const float qscale = p.f8.q ? p.f8.meta[1] : 0.f;
@@ -923,7 +923,7 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnA
       // ---- epilogue: accumulator / row sum -> context
       mbar_wait(o_ready, n & 1);
       tc_fence_after();
-      const float inv_l = 1.f / l;
+      const float inv_l = (drop ? p.inv_keep : 1.f) / l;       // l and the accumulator both carry 1 / keep_prob
       const bool q_ok = q < p.S;
       __nv_bfloat16* dst = p.ctx + (size_t)(row0 + q) * p.H + head * HD;
       float amax = 0.f;
@@ -2110,7 +2110,10 @@ void attention_bwd(const void* qkv, const int* seqlens, const void* ctx, const v
   static bool once = false;
   if (!once) { B200_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); once = true; }
   dim3 grid(nkb, B * h);
-  if (nkb == 1 && single_ok && attn_row_enabled()) {       // round-2 kernel: thread per query row, persistent CTAs
+  // the thread-per-row backward is correct but, with only four math warps per CTA, latency bound (ncu: 19 % issue
+  // utilisation, 103 vs 93 us): opt-in until it has the two-threads-per-row / TMEM-parked dS layout (NOTES.md)
+  static const bool bwd_row = []() { const char* e = getenv("B200_ATTN_BWD_ROW"); return e && e[0] == '1'; }();
+  if (nkb == 1 && single_ok && attn_row_enabled() && (bwd_row || g_attn_row == 1)) {       // round-2 kernel: thread per query row, persistent CTAs
     static int sms = 0;
     if (sms == 0) {
       int dev;

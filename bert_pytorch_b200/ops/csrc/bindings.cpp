@@ -379,6 +379,7 @@ void fused_allreduce_lamb(int64_t rank, int64_t world, bool use_multicast, std::
   L.chunk_tensor = chunk_tensor.data_ptr<int>(); L.chunk_start = (const long long*)chunk_start.data_ptr<int64_t>();
   L.chunk_len = chunk_len.data_ptr<int>(); L.nchunks = (int)chunk_tensor.numel(); L.ntensors = (int)decay_flag.numel();
   L.decay_flag = decay_flag.data_ptr<int>();
+  TORCH_CHECK(stats.numel() >= 16, "fused_allreduce_lamb: stats needs 16 floats ([8..15] carry the in-kernel timeline)");
   L.stats = stats.data_ptr<float>(); L.norms = norms.data_ptr<float>();
   L.grid_bar = reinterpret_cast<unsigned int*>(grid_bar.data_ptr<int>());
   L.epoch = (unsigned int)epoch;

@@ -120,11 +120,25 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_allreduce_lamb_kernel(
   float* lgrad = a.grad[a.rank];
   float* lparam = a.param[a.rank];
 
+  // in-kernel timeline: block 0 / thread 0 stamps %globaltimer after every phase into stats[8..15]
+  // (milliseconds since kernel entry): [8] wait for the slowest rank (barrier 0), [9] phase A (reduce-scatter),
+  // [10] sync 1, [11] phase B, [12] sync 2, [13] phase C (apply + all-gather), [14] zero + final barrier, [15] total
+  const unsigned long long t_enter = globaltimer_ns();
+  unsigned long long t_prev = t_enter;
+  auto stamp = [&](int slot) {
+    if (gtid == 0) {
+      const unsigned long long now = globaltimer_ns();
+      a.stats[slot] = (float)(now - t_prev) * 1e-6f;
+      t_prev = now;
+    }
+  };
+
   // ---- phase 0: everyone's gradients are complete
   if (gtid < 2 * a.ntensors) a.norms[gtid] = 0.f;
   if (gtid < 2) a.stats[gtid] = 0.f;
   peer_barrier(a, 0);
   grid_sync(a.grid_bar, gen);
+  stamp(8);
 
   // ---- phase A: reduce-scatter the own shard
   // Tensors flagged `prereduced` already hold the sum over the ranks in the owner's arena: their weight-gradient
@@ -196,6 +210,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_allreduce_lamb_kernel(
     if (bad) a.stats[1] = 1.f;
   }
   grid_sync(a.grid_bar, gen);
+  stamp(9);
 
   // ---- sync 1: exchange {sumsq, inf}
   if (blockIdx.x == 0 && threadIdx.x < a.world) {
@@ -216,6 +231,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_allreduce_lamb_kernel(
     a.stats[3] = inf;
   }
   grid_sync(a.grid_bar, gen);
+  stamp(10);
   const float gsumsq = a.stats[2];
   const bool skip = a.stats[3] != 0.f || !isfinite(gsumsq);
 
@@ -269,6 +285,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_allreduce_lamb_kernel(
     }
   }
   grid_sync(a.grid_bar, gen);
+  stamp(11);
 
   // ---- sync 2: exchange the per-tensor partial norms
   if (!skip && blockIdx.x == 0) {
@@ -281,6 +298,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_allreduce_lamb_kernel(
   }
   peer_barrier(a, 2);
   grid_sync(a.grid_bar, gen);
+  stamp(12);
 
   // ---- phase C: apply on the shard, push fp32 + bf16 to every rank, zero the local gradients
   if (!skip) {
@@ -350,6 +368,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_allreduce_lamb_kernel(
   // The update directions u live in the gradient arena: every block must be done with phase C before anyone
   // clears it (a missing barrier here silently dropped the update of late chunks).
   grid_sync(a.grid_bar, gen);
+  stamp(13);
   // zero the whole local gradient arena (all peers finished reading it: they passed barrier 1)
   {
     float4* g4 = reinterpret_cast<float4*>(lgrad);
@@ -358,6 +377,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_allreduce_lamb_kernel(
   }
   grid_sync(a.grid_bar, gen);
   peer_barrier(a, 3);
+  stamp(14);
+  if (gtid == 0) a.stats[15] = (float)(globaltimer_ns() - t_enter) * 1e-6f;
 }
 
 void fused_allreduce_lamb(const FusedLambLaunch& L, cudaStream_t st) {

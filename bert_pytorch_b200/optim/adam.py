@@ -148,4 +148,20 @@ class BertAdam(Optimizer):
                     update = update + group["weight_decay"] * p
                 p.add_(update, alpha=-self._scheduled_lr(group, st["step"]))
                 st["step"] += 1
+        arena = getattr(self, "_arena", None)
+        if arena is not None:               # parameters are arena views: the bf16 shadow (and cached fp8 copies) follow
+            arena.refresh_shadow()
         return loss
+
+    def attach_arena(self, arena) -> None:
+        """Parameters / gradients live in a :class:`ParamArena`: ``zero_grad`` must zero the arena in place (the
+        default ``set_to_none=True`` would detach ``p.grad`` from the buffer the data-parallel reduction and the fused
+        engine use) and every step refreshes the bf16 shadow the tensor-core kernels read."""
+        self._arena = arena
+
+    def zero_grad(self, set_to_none: Optional[bool] = None) -> None:
+        arena = getattr(self, "_arena", None)
+        if arena is not None:
+            arena.zero_grad()
+            return
+        super().zero_grad() if set_to_none is None else super().zero_grad(set_to_none=set_to_none)

@@ -120,7 +120,7 @@ class PeerComm(TorchComm):
         ops.extension().set_grad_peers(self.world_size, self.rank, list(self.grad_h.buffer_ptrs), arena.numel, per)
         self._prereduced = None               # int32 [T]: tensors whose reduction happens inside the backward
         self._pushed = False
-        self.stats = torch.zeros(4, dtype=torch.float32, device=dev)
+        self.stats = torch.zeros(16, dtype=torch.float32, device=dev)   # [0..3] sumsq / inf exchange, [8..15] in-kernel timeline (ms)
         self.norms = torch.zeros(2 * T, dtype=torch.float32, device=dev)
         self.grid_bar = torch.zeros(1, dtype=torch.int32, device=dev)
         dist.barrier(group=self.group)
@@ -131,7 +131,7 @@ class PeerComm(TorchComm):
         """Names of the tensors whose ENTIRE gradient is produced by fp32-accumulate GEMMs (the engine's
         weight-gradient launches): with push mode on in the last micro-step they arrive fully reduced at
         their owner and the fused step skips their peer reads."""
-        names = set(names)
+        names = set(names or ())
         flags = [1 if s.name in names else 0 for s in self.arena.slots]
         self._prereduced = torch.tensor(flags, dtype=torch.int32, device=self.device) if any(flags) else None
 
@@ -184,9 +184,25 @@ class PeerComm(TorchComm):
         self._master_stale = not self.push_master
         A.version += 1
         ops.api._count()
-        for g in optimizer.param_groups:       # bf16 path has no overflow; the fp16 path re-reads stats lazily
-            g["step"] = step
+        # apex semantics: the step counter (bias correction, LR schedule) advances only when the update was applied.
+        # With a loss scale in play the kernel may have skipped the step (inf agreed across the ranks, stats[3]);
+        # reading the flag is the one host sync of an fp16 step -- bf16 (loss_scale == 1) never reads it.
+        applied = True
+        if loss_scale != 1.0:
+            applied = float(self.stats[3]) == 0.0
+        if applied:
+            for g in optimizer.param_groups:
+                g["step"] = step
         self.last_stats = self.stats
+
+    TIMELINE_KEYS = ("barrier_wait_ms", "reduce_scatter_ms", "sync1_ms", "moments_ms", "sync2_ms", "apply_allgather_ms",
+                     "zero_final_barrier_ms", "kernel_total_ms")
+
+    def timeline(self) -> dict:
+        """In-kernel %globaltimer split of the last fused step on this rank (block 0): where the reduce-scatter + LAMB
+        + all-gather kernel spent its time; ``barrier_wait_ms`` is the wait for the slowest rank's backward pass."""
+        vals = self.stats[8:16].tolist()
+        return {k: round(float(v), 4) for k, v in zip(self.TIMELINE_KEYS, vals)}
 
     # -- general all-reduce through our own kernel (K-FAC factors etc.) -------------------------------------
     STAGE_FLOATS = 64 << 20          # 256 MB symmetric staging buffer, allocated on first use
@@ -336,13 +352,19 @@ class HierarchicalPeerComm(TorchComm):
         self.inner.adopt(arena)
 
     def set_prereduced(self, names) -> None:
-        self.inner.set_prereduced(names)
+        # GEMM -> reduce-scatter push is OFF in hierarchical mode: same-node peers would still be
+        # adding tiles into this rank's arena while the rail all-reduce below reads it -- the only cross-rank barrier
+        # of the push protocol sits inside the fused kernel, which runs after the rail reduction.
+        self.inner.set_prereduced(None)
 
     def begin_push(self) -> bool:
-        return self.inner.begin_push()
+        return False
 
     def end_push(self) -> None:
-        self.inner.end_push()
+        pass
+
+    def timeline(self) -> dict:
+        return self.inner.timeline()
 
     @torch.no_grad()
     def fused_lamb_step(self, optimizer, loss_scale: float = 1.0) -> None:

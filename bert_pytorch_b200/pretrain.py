@@ -454,7 +454,9 @@ def main(args) -> Tuple[int, float]:
             micro_ms, opt_ms = clock.intervals()[-2:]      # complete: the read-back above waited for the stream
             clock.reset()
             clock.mark()
-            logger.log(tag="train", step=global_step, epoch=epoch,
+            # reference: run_pretraining.py logs step = global_step + previous_phase_end_step, so phase-2 curves
+            # continue phase 1's axis in the same output_dir instead of overlapping it
+            logger.log(tag="train", step=global_step + args.previous_phase_end_step, epoch=epoch,
                        average_loss=average_loss, step_loss=float(last_loss) * acc,
                        learning_rate=optimizer.param_groups[0]["lr"],
                        samples_per_second=(acc * args.local_batch_size * get_world_size()) / max(step_time, 1e-9),

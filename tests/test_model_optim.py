@@ -245,3 +245,34 @@ def test_adam_matches_torch_adamw_with_bias_correction():
         w1.grad, w2.grad = g.clone(), g.clone()
         o1.step(); o2.step()
         assert (w1 - w2).abs().max().item() < 2e-6, i
+
+
+def test_bert_adam_attached_to_arena_keeps_gradients_in_the_arena():
+    """the fp32 SQuAD path pairs BertAdam with an arena-wrapped model.  torch's default
+    zero_grad(set_to_none=True) detached p.grad from arena.flat_grad after the first step, so the data-parallel
+    reduction (which works on flat_grad) synchronised a stale buffer.  Attached to the arena, zero_grad zeroes in
+    place, the views survive any number of steps and every step bumps arena.version (shadow refresh)."""
+    import torch
+    from bert_pytorch_b200.models.arena import ParamArena
+    from bert_pytorch_b200.optim.adam import BertAdam
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Tanh(), torch.nn.Linear(16, 4))
+    arena = ParamArena(model, device=torch.device("cpu"))
+    opt = BertAdam([{"params": list(model.parameters()), "weight_decay": 0.01}], lr=1e-2, warmup=0.1, t_total=10)
+    opt.attach_arena(arena)
+    x = torch.randn(5, 8)
+    for step in range(3):
+        before = arena.flat_param.clone()
+        v0 = arena.version
+        model(x).pow(2).sum().backward()
+        for s, p in zip(arena.slots, arena.params):
+            assert p.grad.data_ptr() == arena.flat_grad[s.offset:].data_ptr(), f"step {step}: {s.name} left the arena"
+        assert arena.flat_grad.abs().sum() > 0
+        opt.step()
+        opt.zero_grad()
+        assert arena.version > v0
+        if step > 0:                      # warm-up: the scheduled lr of the very first step is 0
+            assert not torch.equal(before, arena.flat_param)
+        assert float(arena.flat_grad.abs().sum()) == 0.0
+        for s, p in zip(arena.slots, arena.params):
+            assert p.grad is not None and p.grad.data_ptr() == arena.flat_grad[s.offset:].data_ptr()
