@@ -180,6 +180,12 @@ def wgrad_accumulate(dy: torch.Tensor, x: torch.Tensor, grad: torch.Tensor, alph
     if bn == 128 and k_out >= 256:
         bn = 256
     splits = wgrad_splits(n_out, k_out, dy.size(0) // (2 if fp8 else 1), bn)
+    if bn == 512 and not fp8 and not TAIL_SPLIT and not STREAM_K:
+        # round-2 measurement with the 7-stage operand ring (profiles/gemm_bench_r2_wgrad.jsonl): the 48-tile QKV
+        # weight gradient gains 6 % from the tail split (1179 vs 1110 TFLOP/s), the 64-tile FFN ones lose 18 %
+        tiles = ((n_out + 255) // 256) * ((k_out + 255) // 256)
+        if 40 <= tiles <= 56:
+            splits = -2
     if bn == 512 and TAIL_SPLIT:
         # fewer tiles than CTA pairs and a split-K grid that leaves > 7 % of the machine idle in its last wave:
         # tail split (cluster t runs the head of tile t's K range, the idle clusters share the tails; gemm_sm100.cu)

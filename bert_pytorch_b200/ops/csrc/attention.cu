@@ -502,38 +502,6 @@ attn_fwd_single_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnA
 // ------------------------------------------------------------------------------------------------
 constexpr int ATT_ROW_THREADS = 160;   // warps 0-3: softmax rows (TMEM lane quarter == warp), warp 4: control
 
-struct PhiloxKeys { uint32_t a[7], b[7]; };
-__device__ __forceinline__ PhiloxKeys philox_keys(unsigned long long seed) {
-  PhiloxKeys k;
-#pragma unroll
-  for (int i = 0; i < 7; ++i) {
-    k.a[i] = (uint32_t)seed + (uint32_t)i * Philox::kW0;
-    k.b[i] = (uint32_t)(seed >> 32) + (uint32_t)i * Philox::kW1;
-  }
-  return k;
-}
-// same value as Philox::gen(seed, idx, stream), round keys hoisted, 64-bit products (one IMAD.WIDE each)
-__device__ __forceinline__ uint4 philox7(const PhiloxKeys& k, uint64_t idx, uint32_t stream) {
-  uint32_t x = (uint32_t)idx, y = (uint32_t)(idx >> 32), z = stream, w = 0x5EEDu;
-#pragma unroll
-  for (int i = 0; i < 7; ++i) {
-    const uint64_t p0 = (uint64_t)Philox::kA * x, p1 = (uint64_t)Philox::kB * z;
-    const uint32_t nx = (uint32_t)(p1 >> 32) ^ y ^ k.a[i];
-    const uint32_t nz = (uint32_t)(p0 >> 32) ^ w ^ k.b[i];
-    y = (uint32_t)p1;
-    w = (uint32_t)p0;
-    x = nx;
-    z = nz;
-  }
-  return make_uint4(x, y, z, w);
-}
-// element t (0..7) of a dropout group is kept iff its 16-bit field (word t/2, low half for even t) >= thresh16;
-// `T` = thresh16 << 16.  High halves compare in place, low halves after a 16-bit shift.
-__device__ __forceinline__ bool keep_bit(const uint4& r, int t, uint32_t T) {
-  const uint32_t wds[4] = {r.x, r.y, r.z, r.w};
-  const uint32_t w = wds[t >> 1];
-  return (t & 1) ? (w >= T) : ((w << 16) >= T);
-}
 __device__ __forceinline__ float max3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));

@@ -45,6 +45,8 @@ struct Cfg {
   static constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
+constexpr int PAIR_M = 256, PAIR_N = 256, PAIR_STAGE = 32768;   // CTA-pair kernel (below)
+
 struct GemmArgs {
   int M, N, K;
   int m_blocks, n_blocks, k_blocks, k_splits, k_per_split;
@@ -56,6 +58,7 @@ struct GemmArgs {
   const __nv_bfloat16* res;
   int ldr;
   float* colsum;             // optional fp32 column sums of the bf16 output (bias gradients)
+  int warp_epi;              // pair kernel: warp-local staged epilogue (default) instead of the CTA-wide staging tile
   Seed seed;
   unsigned int stream;
   unsigned int drop_thresh16;
@@ -530,6 +533,155 @@ __device__ __forceinline__ void staged_colsum(const GemmArgs& p, const uint8_t* 
   atomicAdd(p.colsum + n + 1, s1);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Warp-local staged epilogue of the pair kernel (round 2; every bf16 epilogue except the legacy two-pass EPI_BIAS_GELU).
+// gemm_bench round 2: the CTA-wide staged epilogue cost the residual / dropout variants 11-32 % of the plain GEMM
+// (attn-out 515 vs 762 TFLOP/s): one staging tile per CTA means the residual of tile i+1 can only be requested after
+// tile i's stores have drained, and three CTA barriers per tile line the eight epilogue warps up behind the slowest.
+// Here every epilogue warp owns two [32 rows x 64 columns] boxes (128B swizzle, 8 KB of the staging buffer):
+//   * round k (64 columns) of a tile works in box k: the residual box arrives by TMA (per-warp mbarrier), each thread
+//     combines its accumulator row segment with its own row of the box IN PLACE, and the elected lane sends the box
+//     off with one TMA store;
+//   * both residual boxes of the NEXT tile are requested as soon as this tile's stores have been issued, i.e. a whole
+//     main loop ahead of their use;
+//   * optional column sums (bias gradients) are taken from the finished box by the warp itself and leave as one
+//     red.global.add.v2.f32 per lane and round.
+// No CTA-wide barrier anywhere.
+// ------------------------------------------------------------------------------------------------
+struct WarpEpi {
+  uint8_t* box;        // this warp's two boxes: box + k * 4096
+  uint64_t* rbar;      // this warp's two residual barriers
+  int q, half, lane;
+};
+
+__device__ __forceinline__ void warp_epi_request_res(const GemmArgs& p, const CUtensorMap* tmap_res, const WarpEpi& w,
+                                                     int mn, int rank, int k) {
+  const int nb = mn % p.n_blocks, mb = mn / p.n_blocks;
+  const int n0 = nb * PAIR_N + w.half * 128 + k * 64;
+  if (n0 >= p.N) return;
+  mbar_arrive_expect_tx(&w.rbar[k], 4096);
+  tma_load_2d(w.box + k * 4096, tmap_res, &w.rbar[k], n0, mb * PAIR_M + rank * 128 + w.q * 32);
+}
+
+__device__ __forceinline__ void warp_epi_tile(const GemmArgs& p, const CUtensorMap* tmap_out, const CUtensorMap* tmap_res,
+                                              const WarpEpi& w, uint32_t taddr, int mn, int next_mn, int rank, bool use_res,
+                                              uint32_t (&res_cnt)[2], float alpha, const PhiloxKeys& keys, uint32_t dropT,
+                                              uint32_t tmem_empty_addr) {
+  const int nb = mn % p.n_blocks, mb = mn / p.n_blocks;
+  const int row_box0 = mb * PAIR_M + rank * 128 + w.q * 32;
+  const int row = row_box0 + w.lane;
+  const int lane = w.lane;
+#pragma unroll 1
+  for (int k = 0; k < 2; ++k) {
+    const int col0 = w.half * 128 + k * 64;
+    const int n0 = nb * PAIR_N + col0;
+    const bool live = n0 < p.N;              // warp uniform
+    uint8_t* box = w.box + k * 4096;
+    if (live) {
+      if (use_res) {                          // a box barrier completes once per tile in which the box is live
+        mbar_wait(&w.rbar[k], res_cnt[k] & 1);
+        ++res_cnt[k];
+      } else {                                // the box still belongs to the previous tile's store of round k
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+      }
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int nn = n0 + c * 32;
+        uint4 bq[4];
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            bq[g] = nn + g * 8 < p.N ? __ldg(reinterpret_cast<const uint4*>(p.bias + nn + g * 8)) : make_uint4(0, 0, 0, 0);
+        }
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + col0 + c * 32, v);
+        tmem_ld_wait();
+        if (k == 1 && c == 1) {              // this thread is done with the accumulator
+          tc_fence_before();
+          mbar_arrive_cluster(tmem_empty_addr);
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float f[8];
+          if (p.bias != nullptr) {
+            const uint32_t bw[4] = {bq[g].x, bq[g].y, bq[g].z, bq[g].w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 bb = unpack_bf16(bw[t]);
+              f[2 * t] = fmaf(__uint_as_float(v[g * 8 + 2 * t]), alpha, bb.x);
+              f[2 * t + 1] = fmaf(__uint_as_float(v[g * 8 + 2 * t + 1]), alpha, bb.y);
+            }
+          } else {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) f[t] = __uint_as_float(v[g * 8 + t]) * alpha;
+          }
+          if (p.epi == EPI_BIAS_TANH) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) f[t] = tanhf(f[t]);
+          }
+          if (p.epi == EPI_BIAS_DROP_RES && dropT != 0) {
+            const uint64_t e8 = ((uint64_t)row * (uint64_t)p.N + (uint64_t)(nn + g * 8)) >> 3;
+            const uint4 r = philox7(keys, e8, p.stream);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) f[t] = keep_bit(r, t, dropT) ? f[t] * p.drop_scale : 0.f;
+          }
+          uint4* cell = reinterpret_cast<uint4*>(box + lane * 128 + (((c * 4 + g) ^ (lane & 7)) << 4));
+          if (use_res) {                      // own row of the residual box, replaced in place by the result
+            const uint4 u = *cell;
+            const uint32_t rw[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 rr = unpack_bf16(rw[t]);
+              if (p.epi == EPI_MUL) {
+                f[2 * t] *= rr.x;
+                f[2 * t + 1] *= rr.y;
+              } else if (p.epi == EPI_DGELU) {
+                f[2 * t] *= dgelu_erf(rr.x);
+                f[2 * t + 1] *= dgelu_erf(rr.y);
+              } else {
+                f[2 * t] += rr.x;
+                f[2 * t + 1] += rr.y;
+              }
+            }
+          }
+          *cell = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+        }
+      }
+    } else if (k == 1) {                     // nothing to drain in this round, but the accumulator must be released
+      tc_fence_before();
+      mbar_arrive_cluster(tmem_empty_addr);
+    }
+    if (!live) continue;
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(tmap_out, box, n0, row_box0);
+      tma_store_commit();
+    }
+    if (p.colsum != nullptr) {               // lane l owns columns 2l, 2l+1 of the box: 32 rows, conflict free
+      const int col = 2 * lane;
+      const uint32_t off = (uint32_t)((col & 7) * 2);
+      const int ck = col >> 3;
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) {
+        const float2 x = unpack_bf16(*reinterpret_cast<const uint32_t*>(box + r * 128 + ((ck ^ (r & 7)) << 4) + off));
+        s0 += x.x;
+        s1 += x.y;
+      }
+      if (n0 + col < p.N)
+        asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p.colsum + n0 + col), "f"(s0), "f"(s1) : "memory");
+    }
+  }
+  if (use_res && next_mn >= 0 && lane == 0) {   // both residual boxes of the next tile, a whole main loop ahead
+    tma_store_wait_read<1>();                   // round 0's store has left box 0
+    warp_epi_request_res(p, tmap_res, w, next_mn, rank, 0);
+    tma_store_wait_read<0>();
+    warp_epi_request_res(p, tmap_res, w, next_mn, rank, 1);
+  }
+}
+
 // FFN-1 epilogue (EPI_BIAS_GELU_DG): x = acc + bias, out = gelu(x), aux = gelu'(x) -- the activation AND its derivative
 // leave the GEMM, so neither a GELU pass nor a GELU' pass over HBM exists any more (the backward epilogue multiplies).
 // Entirely warp local: every epilogue warp owns 8 KB of the staging buffer (two [32 rows x 64 columns] 128B-swizzled
@@ -603,9 +755,11 @@ __device__ __forceinline__ void gelu_dg_warp(const GemmArgs& p, const CUtensorMa
 // issues MMAs; completion is multicast to both CTAs' barriers; both CTAs run the epilogue on their own
 // 128 accumulator rows (TMEM lanes).
 // ------------------------------------------------------------------------------------------------
-constexpr int PAIR_M = 256, PAIR_N = 256, PAIR_STAGE = 32768, PAIR_STAGES = 5;
 constexpr int PAIR_CSTAGE = 128 * PAIR_N * 2;   // bf16 output/residual staging tile of one CTA: 4 x [128 x 64] swizzled boxes
-constexpr int PAIR_SMEM = PAIR_STAGES * PAIR_STAGE + PAIR_CSTAGE + 1024 + 256;
+// operand ring: 5 stages next to the 64 KB staging tile of the bf16 epilogues, 7 stages for the fp32 (weight-gradient)
+// epilogues that write straight from registers -- same 230 912 bytes either way
+constexpr int PAIR_SMEM = 5 * PAIR_STAGE + PAIR_CSTAGE + 1024 + 512;
+static_assert(7 * PAIR_STAGE + 1024 + 512 <= PAIR_SMEM, "7-stage ring must fit");
 
 // Work decomposition of the pair kernel.  Classic: cluster c owns the (split, tile) units c, c + C, c + 2C, ...
 // Stream-K (accumulating fp32 epilogue only): the m_blocks * n_blocks * k_blocks iteration space is cut into C
@@ -666,20 +820,21 @@ __device__ __forceinline__ WorkSeg seg_get(const GemmArgs& p, int c, int C, int 
   return w;
 }
 
-template <bool A_MN, bool B_MN, bool FP8>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+template <bool A_MN, bool B_MN, bool FP8, int PAIR_STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)   // 10 warps: 3 on two of the SMSPs -> 168 registers
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_aux,
                  const __grid_constant__ CUtensorMap tmap_res, const GemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sC = smem + PAIR_STAGES * PAIR_STAGE;          // staging tile (1024-aligned)
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sC + PAIR_CSTAGE);
+  uint8_t* sC = smem + PAIR_STAGES * PAIR_STAGE;          // staging tile (1024-aligned; absent in the 7-stage variant)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sC + (PAIR_STAGES == 5 ? PAIR_CSTAGE : 0));
   uint64_t* empty_bar = full_bar + PAIR_STAGES;
   uint64_t* tmem_full = empty_bar + PAIR_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* c_full = tmem_empty + 2;                      // residual tile landed in the staging buffer
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(c_full + 1);
+  uint64_t* res_bar = c_full + 1;                         // [8 epilogue warps][2 boxes]: warp-local residual boxes landed
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(res_bar + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -700,6 +855,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_init(&tmem_empty[s], 2 * EPI_THREADS);   // the epilogue threads of both CTAs of the pair
     }
     mbar_init(c_full, 1);
+    for (int i = 0; i < 16; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc_2sm(tmem_base_slot, 512);
@@ -802,7 +958,22 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       for (int j = 0; j < 4; ++j)
         tma_load_2d(sC + j * 16384, &tmap_res, c_full, nb * PAIR_N + j * 64, mb * PAIR_M + (int)rank * 128);
     };
-    if (use_res && issuer && nseg > 0) load_res(seg_get(p, cluster_id, nclusters, 0).mn);
+    // warp-local staged epilogue (default for every bf16 epilogue but the legacy two-pass EPI_BIAS_GELU)
+    const bool warp_local = staged && p.warp_epi != 0 && p.epi != EPI_BIAS_GELU && p.epi != EPI_BIAS_GELU_DG;
+    WarpEpi we;
+    we.box = sC + (warp - 2) * 8192; we.rbar = res_bar + (warp - 2) * 2; we.q = q; we.half = half; we.lane = lane;
+    const PhiloxKeys keys = philox_keys(seed);
+    const uint32_t dropT = p.drop_thresh16 << 16;
+    uint32_t res_cnt[2] = {0u, 0u};
+    if (warp_local) {
+      if (use_res && nseg > 0 && lane == 0) {
+        const int mn0 = seg_get(p, cluster_id, nclusters, 0).mn;
+        warp_epi_request_res(p, &tmap_res, we, mn0, (int)rank, 0);
+        warp_epi_request_res(p, &tmap_res, we, mn0, (int)rank, 1);
+      }
+    } else if (use_res && issuer && nseg > 0) {
+      load_res(seg_get(p, cluster_id, nclusters, 0).mn);
+    }
     uint32_t tile_it = 0, c_phase = 0;
     for (int si = 0; si < nseg; ++si, ++tile_it) {
       const WorkSeg wseg = seg_get(p, cluster_id, nclusters, si);
@@ -818,6 +989,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         epilogue_tile<PAIR_N>(p, taddr, row, row < p.M, nb * PAIR_N, half * 4, half * 4 + 4, alpha, seed, wseg.kb0 == 0);
         tc_fence_before();
         mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), 0));
+        continue;
+      }
+      if (warp_local) {
+        const int next_mn = si + 1 < nseg ? seg_get(p, cluster_id, nclusters, si + 1).mn : -1;
+        warp_epi_tile(p, &tmap_out, &tmap_res, we, taddr, mn, next_mn, (int)rank, use_res, res_cnt, alpha, keys, dropT,
+                      mapa_shared(smem_u32(&tmem_empty[as]), 0));
         continue;
       }
       if (p.epi == EPI_BIAS_GELU_DG) {       // warp-local staging + stores, no CTA-wide barrier (see gelu_dg_warp)
@@ -861,7 +1038,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       epi_bar_sync();                                     // nobody touches the staging tile before that
     }
-    if (p.epi == EPI_BIAS_GELU_DG) {
+    if (p.epi == EPI_BIAS_GELU_DG || warp_local) {
       if (lane == 0) tma_store_wait<0>();
     } else if (staged && issuer) {
       tma_store_wait<0>();
@@ -995,6 +1172,7 @@ static void launch(const GemmCall& c, cudaStream_t st) {
   p.drop_scale = pd > 0.f ? 65536.f / (65536.f - (float)p.drop_thresh16) : 1.f;
   p.alpha = c.alpha;
   fill_peer(p, c);
+  p.warp_epi = 0;
   p.scale_a = nullptr; p.scale_b = nullptr; p.fp8_fmt = 0; p.stream_k = 0; p.k_main = 0;
   // operand maps
   CUtensorMap ta = A_MN ? make_tmap_2d_bf16(c.A, c.M, c.K, c.lda, 64, BLOCK_K)
@@ -1070,14 +1248,18 @@ static void launch_pair(const GemmCall& c, cudaStream_t st) {
   const bool f32_out = c.epi == EPI_ACCUM_F32 || c.epi == EPI_F32;
   // output / pre-activation / residual tiles of one CTA travel as 4 boxes of [128 rows x 64 columns]
   // (EPI_BIAS_GELU_DG: every epilogue warp stores its own [32 rows x 64 columns] boxes)
-  const uint32_t obox = c.epi == EPI_BIAS_GELU_DG ? 32 : 128;
+  static const bool warp_epi_on = []() { const char* e = getenv("B200_GEMM_WARP_EPI"); return e && e[0] == '1'; }();   // opt-in: measured 3-10 % slower than the CTA-wide staging tile (profiles/gemm_bench_r2_epi.jsonl)
+  p.warp_epi = (warp_epi_on && c.epi != EPI_BIAS_GELU) ? 1 : 0;
+  const uint32_t obox = (c.epi == EPI_BIAS_GELU_DG || p.warp_epi) ? 32 : 128;
   CUtensorMap to = f32_out ? ta : make_tmap_2d_bf16(c.out, c.N, c.M, c.ldo, 64, obox);
   CUtensorMap tx = (c.aux_out != nullptr && !f32_out) ? make_tmap_2d_bf16(c.aux_out, c.N, c.M, c.ldo, 64, obox) : to;
-  CUtensorMap tr = (c.res != nullptr && !f32_out) ? make_tmap_2d_bf16(c.res, c.N, c.M, c.ldr, 64, 128) : to;
-  auto kern = gemm_pair_kernel<A_MN, B_MN, FP8>;
+  CUtensorMap tr = (c.res != nullptr && !f32_out) ? make_tmap_2d_bf16(c.res, c.N, c.M, c.ldr, 64, obox) : to;
+  static const bool deep_ring = []() { const char* e = getenv("B200_GEMM_DEEP_RING"); return !(e && e[0] == '0'); }();
+  auto kern = (f32_out && deep_ring) ? gemm_pair_kernel<A_MN, B_MN, FP8, 7> : gemm_pair_kernel<A_MN, B_MN, FP8, 5>;
   static bool configured = false;
   if (!configured) {
-    B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
+    B200_CUDA_CHECK(cudaFuncSetAttribute(gemm_pair_kernel<A_MN, B_MN, FP8, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
+    B200_CUDA_CHECK(cudaFuncSetAttribute(gemm_pair_kernel<A_MN, B_MN, FP8, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
     configured = true;
   }
   const int tiles = p.m_blocks * p.n_blocks * p.k_splits;
