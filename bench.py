@@ -358,7 +358,17 @@ def run_reference(args, ph, B, accum, rank, world, dev):
     os.environ.setdefault("RANK", "0")
     os.environ.setdefault("WORLD_SIZE", "1")
     torch.manual_seed(args.seed + rank)
-    ns = R.setup_training(ns)                      # init_process_group('nccl'), batch arithmetic
+    import torch.distributed as dist
+    real_init = dist.init_process_group
+    if dist.is_initialized():
+        # second config in this process (extra.configs): the reference's setup_training() calls init_process_group
+        # unconditionally (run_pretraining.py:185); the group of the headline run is still alive, so that one call
+        # becomes a no-op -- re-initialising under torchrun's agent store hung a 2-GPU box for 10 minutes
+        dist.init_process_group = lambda *a, **k: None
+    try:
+        ns = R.setup_training(ns)                  # init_process_group('nccl'), batch arithmetic
+    finally:
+        dist.init_process_group = real_init
     assert ns.accumulation_steps == accum, (ns.accumulation_steps, accum)
     model, checkpoint, global_step, criterion, ns = R.prepare_model(ns)       # BertForPreTraining + DDP
     optimizer, preconditioner, lr_schedulers, scaler = R.prepare_optimizers(ns, model, checkpoint, global_step)
@@ -530,10 +540,6 @@ def main():
             gc.collect()
             torch.cuda.empty_cache()
             try:
-                if args.impl == "reference" and dist.is_initialized():   # the reference inits its own process group
-                    dist.barrier()
-                    dist.destroy_process_group()
-                    os.environ["MASTER_PORT"] = str(int(os.environ.get("MASTER_PORT", "29534")) + 7)
                 configs[name] = compact(run_config(sub, rank, world, dev))
             except Exception as e:  # noqa: BLE001 - an extra config must never cost the headline line
                 configs[name] = {"error": f"{type(e).__name__}: {e}"[:300]}

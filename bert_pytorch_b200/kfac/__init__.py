@@ -103,6 +103,7 @@ class KFAC:
                                   factor_update_freq=factor_update_freq, inv_update_freq=inv_update_freq)]
         self.skip_layers = [s.lower() for s in (skip_layers or [])]
         self.steps = 0
+        self.capture = True          # fused engine: whether the next forward/backward feeds tap() (see wants_data)
         self.layers: List[_Layer] = []
         self._by_module: Dict[int, _Layer] = {}
         self._handles = []
@@ -172,12 +173,24 @@ class KFAC:
             A = torch.cat([torch.cat([A, col.t()], dim=1),
                            torch.cat([col, torch.ones(1, 1, device=A.device)], dim=1)], dim=0)
         G = _factor(g) * (M / (scale * scale))
-        if layer.A_new is None or not self.accumulate_data and False:
+        if layer.A_new is None or not self.accumulate_data:
+            # accumulate_data=False (how the reference configures kfac_pytorch, run_pretraining.py:335): the factors of a
+            # step come from ONE micro-batch -- the latest tap replaces the previous one
             layer.A_new, layer.G_new, layer.n_new = A, G, 1
         else:
             layer.A_new += A
             layer.G_new += G
             layer.n_new += 1
+
+    def wants_data(self, last_micro_step: bool) -> bool:
+        """Whether the next forward/backward has to feed :meth:`tap`.  With ``accumulate_data=False`` only the last
+        micro-batch of an optimizer step whose factors are due counts, so every other micro-step runs without taps --
+        and therefore inside the captured CUDA graph (the taps are ~2x the FLOPs of the step itself for BERT-large:
+        two 4096^2 and eight 1024^2 factor GEMMs per layer)."""
+        due = self.steps % self.param_groups[0]["factor_update_freq"] == 0
+        if not due:
+            return False
+        return True if self.accumulate_data else bool(last_micro_step)
 
     # -- the step ----------------------------------------------------------------------------------------------
     def _workers(self, layer: _Layer):
@@ -237,18 +250,15 @@ class KFAC:
                     l.QG = torch.empty(n_g, n_g, dtype=self.inv_dtype, device=dev)
                     l.dG = torch.empty(n_g, dtype=self.inv_dtype, device=dev)
                 if comm.world_size > 1 and len(grad_workers) > 1:
-                    # (a rank outside the worker group still takes part in the world broadcast with scratch)
+                    # eigen-pairs travel inside the layer's gradient-worker GROUP only (HYBRID_OPT: half the ranks),
+                    # in inv_dtype (fp16 in the shipped recipe); ranks outside the group neither allocate nor receive
                     for key in ("QA", "dA", "QG", "dG"):
-                        t = getattr(l, key)
-                        if t is None:
-                            shape = {"QA": (l.A.size(0),) * 2, "dA": (l.A.size(0),), "QG": (l.G.size(0),) * 2,
-                                     "dG": (l.G.size(0),)}[key]
-                            t = torch.empty(shape, dtype=self.inv_dtype, device=l.A.device)
-                            comm.broadcast_(t, src=inv)
-                            if rank in grad_workers:
-                                setattr(l, key, t)
-                        else:
-                            comm.broadcast_(t, src=inv)
+                        shape = {"QA": (l.A.size(0),) * 2, "dA": (l.A.size(0),), "QG": (l.G.size(0),) * 2,
+                                 "dG": (l.G.size(0),)}[key]
+                        got = comm.broadcast_group_(getattr(l, key), inv, grad_workers, shape=shape, dtype=self.inv_dtype,
+                                                    device=l.A.device)
+                        if rank in grad_workers:
+                            setattr(l, key, got)
         # ---- precondition
         vg_sum = torch.zeros((), dtype=torch.float32, device=self.layers[0].module.weight.device) if self.layers else None
         updates: Dict[int, torch.Tensor] = {}
@@ -265,7 +275,12 @@ class KFAC:
             else:
                 P = torch.zeros_like(Wg)
             if comm.world_size > 1 and len(grad_workers) < comm.world_size:
-                comm.broadcast_(P, src=inv)
+                # preconditioned gradient: from the inverse worker to the ranks OUTSIDE the gradient-worker group only
+                receivers = [inv] + [r for r in range(comm.world_size) if r not in grad_workers]
+                got = comm.broadcast_group_(P if rank in receivers else None, inv, receivers, shape=tuple(P.shape),
+                                            dtype=P.dtype, device=P.device)
+                if rank in receivers:
+                    P = got
             updates[l.index] = P
             vg_sum += (P * Wg).sum() * (lr ** 2)
         if not updates:
@@ -273,8 +288,9 @@ class KFAC:
             return
         nu = 1.0
         if kl_clip is not None:
-            vg = float(vg_sum)
-            nu = min(1.0, math.sqrt(kl_clip / vg)) if vg > 0 else 1.0
+            # KL clip on the device: nu = min(1, sqrt(kl_clip / vg)) (1 where vg <= 0) -- no host read-back in the step
+            safe = vg_sum.clamp_min(1e-30)
+            nu = torch.where(vg_sum > 0, torch.sqrt(kl_clip / safe).clamp_(max=1.0), torch.ones_like(vg_sum))
         for l in self.layers:
             if l.index not in updates:
                 continue

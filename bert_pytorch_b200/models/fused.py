@@ -396,6 +396,8 @@ class FusedEncoderEngine:
         ph, pa, seed = sv.p_hidden, sv.p_attn, sv.seed
         d = d_out
         kfac = getattr(self.bert, "_kfac", None)      # K-FAC taps: the saved activations double as its statistics
+        if kfac is not None and not getattr(kfac, "capture", True):
+            kfac = None                               # this micro-step does not feed the factors (KFAC.wants_data)
         if sv.seg_len:                                    # recompute each segment from its saved input, then walk it back
             for lo in reversed(range(0, self.L, sv.seg_len)):
                 hi = min(self.L, lo + sv.seg_len)
@@ -572,8 +574,9 @@ class FusedPretrainer:
         return self.max_pred
 
     def _graph_ok(self) -> bool:
-        if not self.use_graphs or _use_sdpa() or getattr(self.model.bert, "_kfac", None) is not None:
-            return False                      # K-FAC taps keep Python-side state; the library attention path owns its RNG
+        kf = getattr(self.model.bert, "_kfac", None)
+        if not self.use_graphs or _use_sdpa() or (kf is not None and getattr(kf, "capture", True)):
+            return False                      # tapped micro-steps keep Python-side state; the library attention path owns its RNG
         return self.arena.device.type == "cuda"
 
     @torch.no_grad()
@@ -689,6 +692,8 @@ class FusedPretrainer:
             d_z = K.nsp_head_(pooled, A.shadow("cls.seq_relationship.weight"), nsp.bias, next_sentence_labels.long().view(-1),
                               grad_scale, loss, nsp.weight.grad, nsp.bias.grad)
             kf = getattr(self.model.bert, "_kfac", None)
+            if kf is not None and not getattr(kf, "capture", True):
+                kf = None
             if kf is not None:                     # the NSP classifier is an nn.Linear: K-FAC preconditions it; its output
                 with torch.no_grad():              # gradient is rebuilt here (K-FAC mode only, plain torch on [B, 2])
                     lg = pooled.float() @ A.shadow("cls.seq_relationship.weight").float().t() + nsp.bias

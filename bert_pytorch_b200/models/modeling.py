@@ -521,8 +521,25 @@ class BertModel(BertPreTrainedModel):
             self._engine = FusedEncoderEngine(self)
         return self._engine
 
+    def fusable_config(self) -> bool:
+        """Whether the sm_100a kernel program implements this configuration.  The reference model runs any
+        ``hidden_act`` of ``ACT2FN`` and any head size (src/modeling.py:118-139); the fused engine is specialised for
+        erf-GELU and head_dim 64 with H a multiple of 64 and S <= 512 -- everything else takes the plain PyTorch path
+        instead of raising (missing #4)."""
+        cfg = self.config
+        if cfg.hidden_act not in ("gelu", "bias_gelu"):
+            return False
+        H, h = cfg.hidden_size, cfg.num_attention_heads
+        if H % 64 != 0 or H // h != 64:
+            return os.environ.get("B200_ATTN", "native") == "sdpa" and H % 8 == 0
+        if cfg.intermediate_size % 8 != 0 or H > 8 * 256:
+            return False
+        return True
+
     def _can_fuse(self, input_ids: torch.Tensor) -> bool:
         if not (self.use_fused and input_ids.is_cuda):
+            return False
+        if not self.fusable_config() or input_ids.size(-1) > 512 or input_ids.size(-1) % 8 != 0:
             return False
         from .. import ops
         return ops.available()
@@ -564,8 +581,8 @@ class BertForPreTraining(BertPreTrainedModel):
     def pretrain_engine(self):
         """The fused sm_100a forward+backward engine for MLM(+NSP) training, or ``None`` when the
         model is not on a CUDA device / fusion is disabled (then the autograd path runs)."""
-        if not self.bert.use_fused:
-            return None
+        if not self.bert.use_fused or not self.bert.fusable_config():
+            return None                   # e.g. relu / swish FFN or head_dim != 64: the autograd oracle path trains it
         if not self.bert.embeddings.word_embeddings.weight.is_cuda:
             return None
         from .. import ops

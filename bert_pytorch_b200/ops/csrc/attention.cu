@@ -1958,6 +1958,256 @@ attn_bwd_row_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Backward, S <= 128, second layout (default): TWO threads per query row (64 key columns each, 8 math warps) with the
+// lean per-element math of attn_bwd_row_kernel, persistent CTAs, and dS PARKED IN TENSOR MEMORY.
+// ncu on the one-thread-per-row kernel: 19 % issue utilisation, long_scoreboard / barrier waits dominate -- four math
+// warps per CTA cannot hide the dependent MMA -> math -> MMA -> math -> MMA chain and the global loads of O / lse at
+// the head of an item, and the 64 registers of packed dS forced full unrolling (8720 instructions, instruction-cache
+// misses).  Here
+//   * every 16-column chunk's dS (8 packed words) is written back with tcgen05.st into the upper half of the thread's
+//     own, already consumed dP columns (chunks run right to left, so the target columns are always behind the read
+//     pointer) and copied to shared memory once the dV MMA has released the P~ buffer: no register array survives the
+//     chunk loop, which therefore stays rolled (small code, 16-byte shared-memory stores);
+//   * the O half-row and log-sum-exp of the NEXT item are fetched while this item waits for its last MMAs;
+//   * delta = <dO, O>: each thread of a row computes half, one shared-memory exchange + named barrier per item.
+// 96 KB, 256 TMEM columns, 288 threads -> two CTAs per SM (16 math warps per SM).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+
+__global__ void __launch_bounds__(ATT_BWD_THREADS, 2)
+attn_bwd_row2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
+                     const AttnArgs p, const int n_items) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;                      // 16 KB each
+  uint8_t* sV = smem + 16384;
+  uint8_t* sQ = smem + 16384 * 2;
+  uint8_t* sDO = smem + 16384 * 3;
+  uint8_t* sP = smem + 16384 * 4;          // 32 KB: P~, later dS
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 16384 * 6);
+  uint64_t* qkd_full = bars;               // Q, K, dO of an item landed
+  uint64_t* v_full = bars + 1;             // V landed
+  uint64_t* sdp_ready = bars + 2;          // S and dP complete (V is free)
+  uint64_t* pd_ready = bars + 3;           // 256 threads: P~ is in shared memory, S / dP consumed, dS parked
+  uint64_t* dv_done = bars + 4;            // dV MMA retired: the buffer may be overwritten with dS
+  uint64_t* ds_ready = bars + 5;           // 256 threads: dS is in shared memory
+  uint64_t* fin = bars + 6;                // dK, dQ complete (Q, K, dO, the buffer are free)
+  uint64_t* acc_read = bars + 7;           // 256 threads: dQ / dK / dV read out of tensor memory
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* xch = reinterpret_cast<float*>(bars + 10);   // [2 halves][128 rows]: partial delta
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 256) {
+    tma_prefetch_desc(&tmap_qkv);
+    tma_prefetch_desc(&tmap_do);
+    mbar_init(qkd_full, 1);
+    mbar_init(v_full, 1);
+    mbar_init(sdp_ready, 1);
+    mbar_init(pd_ready, 256);
+    mbar_init(dv_done, 1);
+    mbar_init(ds_ready, 256);
+    mbar_init(fin, 1);
+    mbar_init(acc_read, 256);
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tS = tmem, tDP = tmem + 128, tDV = tmem, tDK = tmem + 64, tDQ = tmem + 128;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      constexpr uint32_t id_kk = umma_idesc_bf16(128, 128, false, false);  // [q x keys], both K-major
+      constexpr uint32_t id_tt = umma_idesc_bf16(128, 64, true, true);     // [keys x d] = X^T Y, both MN-major
+      constexpr uint32_t id_kt = umma_idesc_bf16(128, 64, false, true);    // [q x d] = dS K, A K-major, B MN-major
+      const uint32_t aq = smem_u32(sQ), ado = smem_u32(sDO), ak = smem_u32(sK), av = smem_u32(sV), ap = smem_u32(sP);
+      auto load_qkd = [&](int item) {
+        const int b = item / p.h, head = item - b * p.h;
+        mbar_arrive_expect_tx(qkd_full, 49152);
+        tma_load_2d(sDO, &tmap_do, qkd_full, head * HD, b * p.S);
+        tma_load_2d(sK, &tmap_qkv, qkd_full, p.H + head * HD, b * p.S);
+        tma_load_2d(sQ, &tmap_qkv, qkd_full, head * HD, b * p.S);
+      };
+      auto load_v = [&](int item) {
+        const int b = item / p.h, head = item - b * p.h;
+        mbar_arrive_expect_tx(v_full, 16384);
+        tma_load_2d(sV, &tmap_qkv, v_full, 2 * p.H + head * HD, b * p.S);
+      };
+      int item = blockIdx.x;
+      if (item < n_items) { load_qkd(item); load_v(item); }
+      for (uint32_t g = 0; item < n_items; item += gridDim.x, ++g) {
+        const int nitem = item + gridDim.x;
+        const uint32_t ph = g & 1;
+        if (g > 0) mbar_wait(acc_read, (g - 1) & 1);           // previous dQ / dK / dV drained
+        mbar_wait(qkd_full, ph);
+        mbar_wait(v_full, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk)   // S = Q K^T
+          umma_bf16_ss(tS, umma_smem_desc_sw128(aq + kk * 32, 16, 1024), umma_smem_desc_sw128(ak + kk * 32, 16, 1024), id_kk, kk > 0);
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk)   // dP = dO V^T
+          umma_bf16_ss(tDP, umma_smem_desc_sw128(ado + kk * 32, 16, 1024), umma_smem_desc_sw128(av + kk * 32, 16, 1024), id_kk, kk > 0);
+        umma_commit(sdp_ready);
+        mbar_wait(sdp_ready, ph);                              // V is free: the next one streams in under the math
+        if (nitem < n_items) load_v(nitem);
+        mbar_wait(pd_ready, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < TILE / 16; ++kk)   // dV = P~^T dO -> S[0,64)
+          umma_bf16_ss(tDV, umma_smem_desc_sw128(ap + kk * 2048, 16384, 1024), umma_smem_desc_sw128(ado + kk * 2048, 8192, 1024), id_tt, kk > 0);
+        umma_commit(dv_done);
+        mbar_wait(ds_ready, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < TILE / 16; ++kk)   // dK = dS^T Q -> S[64,128)
+          umma_bf16_ss(tDK, umma_smem_desc_sw128(ap + kk * 2048, 16384, 1024), umma_smem_desc_sw128(aq + kk * 2048, 8192, 1024), id_tt, kk > 0);
+#pragma unroll
+        for (int kk = 0; kk < TILE / 16; ++kk)   // dQ = dS K -> dP[0,64)
+          umma_bf16_ss(tDQ, umma_smem_desc_sw128(ap + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                       umma_smem_desc_sw128(ak + kk * 2048, 8192, 1024), id_kt, kk > 0);
+        umma_commit(fin);
+        mbar_wait(fin, ph);                                    // Q, K, dO free: next item streams in under the epilogue
+        if (nitem < n_items) load_qkd(nitem);
+      }
+    }
+  } else {
+    const int r = (warp & 3) * 32 + lane;                      // query row == key row of the epilogue == TMEM lane
+    const int hf = warp >> 2;                                  // key-column half [64 hf, 64 hf + 64)
+    const uint32_t lane_base = uint32_t((warp & 3) * 32) << 16;
+    const float c_scale = p.scale * LOG2E;
+    const bool drop = p.thresh16 != 0;
+    const float lk = drop ? log2f(p.inv_keep) : 0.f;
+    const uint32_t T = p.thresh16 << 16;
+    const PhiloxKeys keys = philox_keys(drop ? p.seed.value() : 0ull);
+    const bool row_ok = r < p.S;
+    const float qscale8 = p.f8.q ? p.f8.meta[1] : 0.f;
+    const uint32_t tPark = tDP + lane_base + hf * 64 + 32;     // 32 words: this thread's 64 dS values, packed bf16
+    float amax8 = 0.f;
+    // O half-row (32 columns) and log-sum-exp of the first item
+    uint4 ov[4];
+    float lse_nat = 0.f;
+    auto fetch = [&](int item) {
+      const int b = item / p.h, head = item - b * p.h;
+      const __nv_bfloat16* src = p.ctx + ((size_t)b * p.S + r) * p.H + head * HD + hf * 32;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) ov[c] = row_ok ? __ldg(reinterpret_cast<const uint4*>(src + c * 8)) : make_uint4(0, 0, 0, 0);
+      lse_nat = row_ok ? __ldg(p.lse + (size_t)item * p.S + r) : 0.f;
+    };
+    if ((int)blockIdx.x < n_items) fetch(blockIdx.x);
+    uint32_t g = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++g) {
+      const uint32_t ph = g & 1;
+      const int b = item / p.h, head = item - b * p.h;
+      const int seqlen = min(__ldg(p.seqlens + b), p.S);
+      const size_t tok = (size_t)b * p.S + r;
+      mbar_wait(qkd_full, ph);
+      float part = 0.f;                                        // this thread's half of delta = <dO, O>
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint4 dv = *reinterpret_cast<const uint4*>(sDO + r * 128 + (((hf * 4 + c) ^ (r & 7)) << 4));
+        const uint32_t aw[4] = {ov[c].x, ov[c].y, ov[c].z, ov[c].w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 x = unpack_bf16(aw[t]), y = unpack_bf16(dw[t]);
+          part = fmaf(x.x, y.x, fmaf(x.y, y.y, part));
+        }
+      }
+      float* xb = xch + (g & 1) * 256;                         // double buffered by item parity
+      xb[hf * 128 + r] = part;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float dlt = xb[r] + xb[128 + r];
+      const float off = lk - lse_nat * LOG2E;                  // p' = 2^(s c + off) = P / keep_prob
+      const float a = p.scale;                                 // dS = p' * (keep ? dP * scale + bq : bq)
+      const float bq = -dlt * p.scale / p.inv_keep;
+      const int kvalid = row_ok ? seqlen : 0;                  // rows beyond the sequence contribute nothing
+      const uint64_t e8row = (((uint64_t)item * p.S + (uint64_t)r) * (uint64_t)p.S) >> 3;
+      mbar_wait(sdp_ready, ph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cl = 3; cl >= 0; --cl) {                        // right to left: parked dS lands in consumed columns only
+        const int c = hf * 4 + cl;                             // 16-column chunk of the row
+        uint32_t sv[16], dv[16], pw[8], dw[8];
+        tmem_ld_32x16(tS + lane_base + c * 16, sv);
+        tmem_ld_32x16(tDP + lane_base + c * 16, dv);
+        tmem_ld_wait();
+        const int nv = kvalid - c * 16;
+        const uint64_t e8 = e8row + (uint64_t)(2 * c);
+        if (nv >= 16) {
+          if (drop) dsoftmax_chunk16<true, true>(sv, dv, pw, dw, c_scale, off, a, bq, 16, keys, e8, p.stream, T);
+          else dsoftmax_chunk16<true, false>(sv, dv, pw, dw, c_scale, off, a, bq, 16, keys, e8, p.stream, T);
+        } else if (nv > 0) {
+          if (drop) dsoftmax_chunk16<false, true>(sv, dv, pw, dw, c_scale, off, a, bq, nv, keys, e8, p.stream, T);
+          else dsoftmax_chunk16<false, false>(sv, dv, pw, dw, c_scale, off, a, bq, nv, keys, e8, p.stream, T);
+        } else {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) { pw[t] = 0u; dw[t] = 0u; }
+        }
+        *reinterpret_cast<uint4*>(sP + p_chunk_offset(r, c * 2)) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+        *reinterpret_cast<uint4*>(sP + p_chunk_offset(r, c * 2 + 1)) = make_uint4(pw[4], pw[5], pw[6], pw[7]);
+        tmem_st_32x8(tPark + cl * 8, dw);
+      }
+      tmem_st_wait();
+      fence_proxy_async();
+      tc_fence_before();                                       // S / dP reads retired before dV may overwrite S
+      mbar_arrive(pd_ready);
+      mbar_wait(dv_done, ph);                                  // the tensor core no longer reads P~
+      tc_fence_after();
+      {
+        uint32_t w[32];
+        tmem_ld_32x32(tPark, w);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<uint4*>(sP + p_chunk_offset(r, hf * 8 + i)) = make_uint4(w[i * 4], w[i * 4 + 1], w[i * 4 + 2], w[i * 4 + 3]);
+      }
+      fence_proxy_async();
+      tc_fence_before();                                       // parked dS read out before dQ may overwrite dP[0,64)
+      mbar_arrive(ds_ready);
+      if (item + (int)gridDim.x < n_items) fetch(item + gridDim.x);   // next item's O / lse fly under the wait below
+      mbar_wait(fin, ph);
+      tc_fence_after();
+      // ---- epilogue: columns [32 hf, 32 hf + 32) of this row of dQ (query r), dK and dV (key r)
+      __nv_bfloat16* drow = p.dqkv + tok * 3 * p.H + head * HD + hf * 32;
+#pragma unroll
+      for (int w = 0; w < 3; ++w) {
+        const uint32_t src = w == 0 ? tDQ : (w == 1 ? tDK : tDV);
+        uint32_t v[32];
+        tmem_ld_32x32(src + lane_base + hf * 32, v);
+        tmem_ld_wait();
+        if (w == 2) {                                          // accumulators drained: the next item's MMAs may go
+          tc_fence_before();
+          mbar_arrive(acc_read);
+        }
+        if (row_ok) {
+          __nv_bfloat16* dst = drow + w * p.H;
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq)
+            *reinterpret_cast<uint4*>(dst + gq * 8) = make_uint4(
+                pack_bf16(__uint_as_float(v[gq * 8]), __uint_as_float(v[gq * 8 + 1])),
+                pack_bf16(__uint_as_float(v[gq * 8 + 2]), __uint_as_float(v[gq * 8 + 3])),
+                pack_bf16(__uint_as_float(v[gq * 8 + 4]), __uint_as_float(v[gq * 8 + 5])),
+                pack_bf16(__uint_as_float(v[gq * 8 + 6]), __uint_as_float(v[gq * 8 + 7])));
+          if (p.f8.q) emit_fp8_row<4>(p.f8, tok * 3 * p.H + (size_t)(w * p.H + head * HD + hf * 32), v, 1.f, qscale8, amax8);
+        }
+      }
+    }
+    if (p.f8.q) fp8_amax_commit(p.f8, amax8);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
 // dq_acc (fp32 [B*S, H]) -> q slots of dqkv (bf16 [B*S, 3H])
 __global__ void __launch_bounds__(256)
 attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, long long rows, int H, const Fp8Out f8) {
@@ -2080,8 +2330,26 @@ void attention_bwd(const void* qkv, const int* seqlens, const void* ctx, const v
   dim3 grid(nkb, B * h);
   // the thread-per-row backward is correct but, with only four math warps per CTA, latency bound (ncu: 19 % issue
   // utilisation, 103 vs 93 us): opt-in until it has the two-threads-per-row / TMEM-parked dS layout (NOTES.md)
-  static const bool bwd_row = []() { const char* e = getenv("B200_ATTN_BWD_ROW"); return e && e[0] == '1'; }();
-  if (nkb == 1 && single_ok && attn_row_enabled() && (bwd_row || g_attn_row == 1)) {       // round-2 kernel: thread per query row, persistent CTAs
+  static const int bwd_row = []() { const char* e = getenv("B200_ATTN_BWD_ROW"); return e ? atoi(e) : 2; }();
+  if (nkb == 1 && single_ok && attn_row_enabled() && bwd_row == 2) {   // two threads per row, dS parked in TMEM, persistent
+    static int sms = 0;
+    if (sms == 0) {
+      int dev;
+      B200_CUDA_CHECK(cudaGetDevice(&dev));
+      B200_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    constexpr int SMEM2 = 16384 * 6 + 1024 + 128 + 2048;
+    static bool once2 = false;
+    if (!once2) {
+      B200_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_row2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2));
+      once2 = true;
+    }
+    const int n_items = B * h;
+    const int g = n_items < sms * 2 ? n_items : sms * 2;
+    attn_bwd_row2_kernel<<<g, ATT_BWD_THREADS, SMEM2, st>>>(tq, td, a, n_items);
+    return;
+  }
+  if (nkb == 1 && single_ok && attn_row_enabled() && bwd_row == 1) {       // round-2 kernel: thread per query row, persistent CTAs
     static int sms = 0;
     if (sms == 0) {
       int dev;

@@ -48,6 +48,19 @@ class Comm:
     def broadcast_(self, t: torch.Tensor, src: int = 0) -> torch.Tensor:
         return t
 
+    def broadcast_group_(self, t: Optional[torch.Tensor], src: int, ranks, shape=None, dtype=None, device=None):
+        """Broadcast among the ranks in ``ranks`` only (K-FAC's gradient-worker groups: run_pretraining.py:321-345
+        drives kfac_pytorch with HYBRID_OPT).  EVERY rank of the communicator calls this, in the same order; a rank
+        outside ``ranks`` passes ``t=None`` and gets ``None`` back.  Default: a world broadcast in which outsiders
+        take part with a scratch tensor (what round 1 did everywhere); ``TorchComm`` uses real sub-groups."""
+        ranks = list(ranks)
+        if self.world_size == 1 or len(ranks) <= 1:
+            return t
+        member = self.rank in ranks
+        buf = t if t is not None else torch.empty(shape, dtype=dtype, device=device)
+        self.broadcast_(buf, src=src)
+        return buf if member else None
+
     def barrier(self) -> None:
         return None
 
@@ -105,6 +118,24 @@ class TorchComm(Comm):
 
     def broadcast_(self, t, src=0):
         dist.broadcast(t, src=src, group=self.group)
+        return t
+
+    def broadcast_group_(self, t, src, ranks, shape=None, dtype=None, device=None):
+        ranks = tuple(sorted(int(r) for r in ranks))
+        if self.world_size == 1 or len(ranks) <= 1:
+            return t
+        if len(ranks) == self.world_size:
+            return self.broadcast_(t, src=src)
+        if self.group is not None:          # nested communicators: keep the simple (correct) world-broadcast fallback
+            return super().broadcast_group_(t, src, ranks, shape, dtype, device)
+        groups = self.__dict__.setdefault("_subgroups", {})
+        g = groups.get(ranks)
+        if g is None:                        # collective: every rank creates every sub-group, in first-use order
+            g = dist.new_group(list(ranks))
+            groups[ranks] = g
+        if self.rank not in ranks:
+            return None
+        dist.broadcast(t, src=src, group=g)
         return t
 
     def barrier(self):

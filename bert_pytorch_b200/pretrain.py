@@ -335,6 +335,9 @@ def forward_backward_pass(model, criterion, scaler, batch, divisor, sync_grads=T
     if engine is not None:
         # fused sm_100a path: forward + backward in one call, grads accumulate into the arena
         comm = getattr(model, "comm", None)
+        kf = getattr(base.bert, "_kfac", None) if hasattr(base, "bert") else None
+        if kf is not None:                   # K-FAC statistics only where they count; all other micro-steps replay the graph
+            kf.capture = kf.wants_data(last_micro_step=sync_grads)
         push = (sync_grads and comm is not None and getattr(model, "defer_reduction", False)
                 and hasattr(comm, "begin_push") and comm.begin_push())
         engine.grad_push = bool(push)       # last micro-step: weight-gradient GEMMs reduce-scatter over NVLink

