@@ -75,7 +75,9 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--gradient_accumulation_steps", type=int, default=1)
     p.add_argument("--do_lower_case", action="store_true")
     p.add_argument("--local_rank", type=int, default=int(os.environ.get("LOCAL_RANK", -1)))
-    p.add_argument("--fp16", default=False, action="store_true")
+    p.add_argument("--fp16", default=False, action="store_true",
+                   help="reference flag (apex amp O2): 16-bit compute. The fused engine runs bf16 operands; with "
+                        "--loss_scale != 0 the fp16-style GradScaler semantics are kept (DESIGN.md section 2)")
     p.add_argument("--amp", default=False, action="store_true")
     p.add_argument("--loss_scale", type=float, default=0)
     p.add_argument("--version_2_with_negative", action="store_true")

@@ -244,7 +244,7 @@ void embedding_bwd_scatter(Tensor de, Tensor ids, c10::optional<Tensor> seg, Ten
   b200::embedding_bwd_scatter(de.data_ptr(), ids.data_ptr<int>(),
                               seg.has_value() && seg->defined() ? seg->data_ptr<int>() : nullptr,
                               gword.data_ptr<float>(), gpos.data_ptr<float>(), opt_f32(gtype), M, (int)S, H,
-                              cur_stream());
+                              gtype.has_value() && gtype->defined() ? (int)gtype->size(0) : 0, cur_stream());
 }
 
 void mlm_compact(Tensor labels, int64_t max_pred, Tensor idx, Tensor tgt, Tensor count) {

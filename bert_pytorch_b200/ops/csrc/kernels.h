@@ -21,7 +21,7 @@ void embedding_fwd(const int* ids, const int* seg, const void* word, const void*
                    const float* gamma, const float* beta, void* e_out, void* y, float* mean, float* rstd, int M, int S,
                    int H, float eps, Seed seed, unsigned int stream, float p_drop, cudaStream_t st);
 void embedding_bwd_scatter(const void* de, const int* ids, const int* seg, float* gword, float* gpos, float* gtype,
-                           int M, int S, int H, cudaStream_t st);
+                           int M, int S, int H, int type_rows, cudaStream_t st);
 void mlm_compact(const int* labels, int B, int S, int max_pred, int* idx, int* tgt, int* count, cudaStream_t st);
 void gather_rows(const void* src, const int* idx, void* dst, int n, int H, cudaStream_t st);
 void scatter_rows(const void* src, const int* idx, void* dst, int n, int H, cudaStream_t st);

@@ -801,7 +801,7 @@ embed_bwd_scatter_kernel(const __nv_bfloat16* __restrict__ de, const int* __rest
       f[2 * t] = p.x;
       f[2 * t + 1] = p.y;
     }
-    float* dst[3] = {gword + (size_t)ids[row] * H + col, gpos + (size_t)(row % S) * H + col,
+    float* dst[3] = {gword + (size_t)ids[row] * H + col, gpos ? gpos + (size_t)(row % S) * H + col : nullptr,
                      gtype ? gtype + (size_t)seg[row] * H + col : nullptr};
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -811,6 +811,51 @@ embed_bwd_scatter_kernel(const __nv_bfloat16* __restrict__ de, const int* __rest
       asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst[k] + 4), "f"(f[4]), "f"(f[5]),
                    "f"(f[6]), "f"(f[7]) : "memory");
     }
+  }
+}
+
+// Position / token-type gradients as REDUCTIONS instead of atomics (ncu round 2: the scatter kernel spent 269 us in
+// lg_throttle -- 12288 rows hammering the two token-type rows and 96 rows per position row).  Thread (s, 8 columns)
+// walks the batch dimension: the position row s has exactly one owner (plain read-modify-write), the two token-type
+// rows are reduced over the 8 positions of a block in shared memory and leave as one atomic per block and column.
+__global__ void __launch_bounds__(256)
+embed_bwd_postype_kernel(const __nv_bfloat16* __restrict__ de, const int* __restrict__ seg, float* __restrict__ gpos,
+                         float* __restrict__ gtype, int B, int S, int H) {
+  const int cg = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int col = blockIdx.x * 256 + cg * 8;
+  const int s = blockIdx.y * 8 + sl;
+  float ap[8], a1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) ap[j] = a1[j] = 0.f;
+  const bool live = col < H && s < S;
+  if (live) {
+#pragma unroll 4
+    for (int b = 0; b < B; ++b) {
+      const size_t row = (size_t)b * S + s;
+      float f[8];
+      unpack8(ld_stream16(de + row * H + col), f);
+      const float m = (seg != nullptr && seg[row] != 0) ? 1.f : 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { ap[j] += f[j]; a1[j] = fmaf(m, f[j], a1[j]); }
+    }
+    float4* gp = reinterpret_cast<float4*>(gpos + (size_t)s * H + col);
+    float4 x = gp[0], y = gp[1];
+    x.x += ap[0]; x.y += ap[1]; x.z += ap[2]; x.w += ap[3];
+    y.x += ap[4]; y.y += ap[5]; y.z += ap[6]; y.w += ap[7];
+    gp[0] = x; gp[1] = y;
+  }
+  if (gtype == nullptr) return;
+  __shared__ float sm[2][8][256];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sm[0][sl][cg * 8 + j] = live ? ap[j] - a1[j] : 0.f; sm[1][sl][cg * 8 + j] = live ? a1[j] : 0.f; }
+  __syncthreads();
+  const int c = threadIdx.x;
+  if (blockIdx.x * 256 + c < H) {
+    float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) { t0 += sm[0][r][c]; t1 += sm[1][r][c]; }
+    atomicAdd(gtype + blockIdx.x * 256 + c, t0);
+    atomicAdd(gtype + H + blockIdx.x * 256 + c, t1);
   }
 }
 
@@ -1020,10 +1065,18 @@ void embedding_fwd(const int* ids, const int* seg, const void* word, const void*
 }
 
 void embedding_bwd_scatter(const void* de, const int* ids, const int* seg, float* gword, float* gpos, float* gtype,
-                           int M, int S, int H, cudaStream_t st) {
+                           int M, int S, int H, int type_rows, cudaStream_t st) {
   const size_t work = (size_t)M * (H / 8);
   int grid = (int)((work + 255) / 256);
   if (grid > 148 * 16) grid = 148 * 16;
+  static const bool reduce_ok = []() { const char* e = getenv("B200_EMBED_REDUCE"); return !(e && e[0] == '0'); }();
+  if (reduce_ok && M % S == 0 && H % 8 == 0 && (gtype == nullptr || type_rows == 2)) {
+    // word rows: scatter with atomics (30 k rows, little contention); position / token-type rows: reductions
+    embed_bwd_scatter_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)de, ids, seg, gword, nullptr, nullptr, M, S, H);
+    dim3 g2((H + 255) / 256, (S + 7) / 8);
+    embed_bwd_postype_kernel<<<g2, 256, 0, st>>>((const __nv_bfloat16*)de, seg, gpos, gtype, M / S, S, H);
+    return;
+  }
   embed_bwd_scatter_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)de, ids, seg, gword, gpos, gtype, M, S, H);
 }
 

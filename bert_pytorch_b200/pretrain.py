@@ -67,7 +67,10 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--checkpoint_activations", default=False, action="store_true")
     p.add_argument("--log_prefix", type=str, default="logfile")
     p.add_argument("--seed", type=int, default=42)
-    p.add_argument("--fp16", default=False, action="store_true", help="fp16 autocast + dynamic loss scaling")
+    p.add_argument("--fp16", default=False, action="store_true",
+                   help="reference flag: dynamic loss scaling (GradScaler) on. On a B200 the fused engine multiplies bf16 "
+                        "operands either way -- fp16 selects the scaler semantics, not fp16 tensor-core operands "
+                        "(DESIGN.md section 2); the plain-PyTorch fallback path autocasts to fp16")
     # hyper-parameters
     p.add_argument("--learning_rate", default=5e-5, type=float)
     p.add_argument("--lr_decay", default="poly", type=str, choices=["poly", "linear"])
