@@ -40,6 +40,7 @@ import math
 import os
 import sys
 import tempfile
+import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -523,15 +524,38 @@ def main():
             print(json.dumps({"impl": "reference", "unavailable": "reference copy not found under baseline/_ref"}))
         return
     headline = args.phase == 1 and not (args.roberta or args.kfac or args.fp8 or args.layers)
+    # An extra config that fails on ONE rank leaves the others inside a collective: nothing after that point may
+    # depend on the process group.  Ranks signal through a flag file (one node), a watcher thread on every rank ends the
+    # process when it appears -- rank 0 prints the headline line (plus whatever extras finished) first.
+    import threading
+    state = {"out": out, "configs": None, "printed": False}
+    flag = os.path.join("/tmp", f"b200_bench_abort_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}")
+    lock = threading.Lock()
+
+    def emit():
+        with lock:
+            if rank == 0 and not state["printed"]:
+                if state["configs"] is not None:
+                    state["out"]["extra"]["configs"] = state["configs"]
+                print(json.dumps(state["out"]), flush=True)
+                state["printed"] = True
+
+    def watch():
+        while not os.path.exists(flag):
+            time.sleep(0.5)
+        emit()
+        os._exit(0)
+
+    if world > 1:
+        threading.Thread(target=watch, daemon=True).start()
     if headline and not args.no_extras:
         # BASELINE.json configs #3-#5 in the same process, a few steps each (reduced accumulation: more optimizer /
         # reduction share per unit compute than the shipped config, i.e. conservative)
         import gc
-        import torch.distributed as dist
         subs = [("phase2", dict(phase=2, accum=16))]
         if args.impl == "ours":
             subs += [("roberta_fp8", dict(roberta=True, fp8=True, accum=16)), ("kfac", dict(kfac=True, accum=16))]
-        configs = {}
+        configs = state["configs"] = {}
         for name, over in subs:
             sub = argparse.Namespace(**vars(args))
             sub.steps, sub.warmup, sub.no_e2e, sub.global_batch = min(args.steps, 4), 3, True, 0
@@ -543,12 +567,20 @@ def main():
                 configs[name] = compact(run_config(sub, rank, world, dev))
             except Exception as e:  # noqa: BLE001 - an extra config must never cost the headline line
                 configs[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
-        out["extra"]["configs"] = configs
-    if rank == 0:
-        print(json.dumps(out), flush=True)
+                if world > 1:       # the other ranks may be blocked in a collective: stop here, everywhere
+                    emit()
+                    open(flag, "w").close()
+                    time.sleep(2.0)
+                    os._exit(0)
+    emit() if rank == 0 else None
+    if world > 1:                   # a wedged communicator must not turn a finished measurement into a timeout
+        threading.Timer(30.0, lambda: os._exit(0)).start()
     import torch.distributed as dist
     if dist.is_initialized():
         dist.destroy_process_group()
+    if world > 1:
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -240,8 +240,9 @@ class KFAC:
                 if rank == inv:
                     dA, QA = torch.linalg.eigh(l.A.float())
                     dG, QG = torch.linalg.eigh(l.G.float())
-                    l.QA, l.dA = QA.to(self.inv_dtype), dA.clamp_(min=0.0).to(self.inv_dtype)
-                    l.QG, l.dG = QG.to(self.inv_dtype), dG.clamp_(min=0.0).to(self.inv_dtype)
+                    # eigh returns column-major eigenvector matrices: collectives need dense row-major payloads
+                    l.QA, l.dA = QA.to(self.inv_dtype).contiguous(), dA.clamp_(min=0.0).to(self.inv_dtype).contiguous()
+                    l.QG, l.dG = QG.to(self.inv_dtype).contiguous(), dG.clamp_(min=0.0).to(self.inv_dtype).contiguous()
                 elif rank in grad_workers and l.QA is None:
                     n_a, n_g = l.A.size(0), l.G.size(0)
                     dev = l.A.device
@@ -277,6 +278,7 @@ class KFAC:
             if comm.world_size > 1 and len(grad_workers) < comm.world_size:
                 # preconditioned gradient: from the inverse worker to the ranks OUTSIDE the gradient-worker group only
                 receivers = [inv] + [r for r in range(comm.world_size) if r not in grad_workers]
+                P = P.contiguous()
                 got = comm.broadcast_group_(P if rank in receivers else None, inv, receivers, shape=tuple(P.shape),
                                             dtype=P.dtype, device=P.device)
                 if rank in receivers:

@@ -537,6 +537,52 @@ class _EncoderFn(torch.autograd.Function):
         return torch.zeros(1, device=d_seq.device), None, None, None, None
 
 
+class _HeadLinearFn(torch.autograd.Function):
+    """y = x W^T + b for the small-N fine-tuning heads (QA: N = 2, token / sequence classifiers: N = num_labels,
+    multiple choice: N = 1; reference src/modeling.py:1127-1128, 1188-1189, 1256-1257, 1323-1326) on the tcgen05 GEMM:
+    N is padded to 8 output columns, forward NT with fp32 store, dgrad NN, wgrad TN with fp32 store -- the SQuAD / NER
+    steps then contain no library GEMM (K28 / K29 ran as torch ops = cuBLAS behind the bridge)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        shape = x.shape
+        xb = x.reshape(-1, shape[-1])
+        xb = (xb if xb.dtype == torch.bfloat16 else xb.to(torch.bfloat16)).contiguous()
+        n, H = weight.shape
+        npad = (n + 7) // 8 * 8
+        wp = torch.zeros(npad, H, dtype=torch.bfloat16, device=x.device)
+        wp[:n] = weight.detach().to(torch.bfloat16)
+        y = K.gemm(xb, wp, epi=K.EPI_F32, block_n=128)[:, :n]
+        if bias is not None:
+            y = y + bias.detach().float()
+        ctx.save_for_backward(xb, wp)
+        ctx.meta = (shape, n, x.dtype, bias is not None, weight.dtype)
+        return y.to(x.dtype if x.dtype != torch.float32 else torch.float32).view(*shape[:-1], n)
+
+    @staticmethod
+    def backward(ctx, gy):
+        xb, wp = ctx.saved_tensors
+        shape, n, xdtype, has_bias, wdtype = ctx.meta
+        go = gy.reshape(-1, n).float()
+        gop = torch.zeros(go.size(0), wp.size(0), dtype=torch.bfloat16, device=go.device)
+        gop[:, :n] = go
+        dx = K.gemm(gop, wp, layout=K.NN).to(xdtype).view(*shape)
+        dw = K.gemm(gop, xb, layout=K.TN, epi=K.EPI_F32, block_n=128)[:n].to(wdtype)
+        db = go.sum(0) if has_bias else None
+        return dx, dw, db
+
+
+def head_linear(linear: torch.nn.Linear, x: torch.Tensor) -> torch.Tensor:
+    """``linear(x)`` through :class:`_HeadLinearFn` when the sm_100a extension can serve it (CUDA, H % 8 == 0, at most
+    64 outputs, at least 128 rows -- smaller problems are launch bound either way), else the module itself."""
+    H = x.size(-1)
+    rows = x.numel() // max(H, 1)
+    if (x.is_cuda and ops.available() and H % 8 == 0 and linear.out_features <= 64 and rows >= 128
+            and os.environ.get("B200_HEAD_GEMM", "1") != "0"):
+        return _HeadLinearFn.apply(x, linear.weight, linear.bias)
+    return linear(x)
+
+
 class FusedPretrainer:
     """Forward + backward of ``BertForPreTraining`` + criterion as one kernel program.
 

@@ -668,6 +668,14 @@ class BertForMultipleChoice(BertPreTrainedModel):
         return logits
 
 
+def _head(linear: nn.Linear, x: torch.Tensor) -> torch.Tensor:
+    """Small-N head projection: the tcgen05 GEMM path on CUDA (models/fused.py:head_linear), ``linear(x)`` elsewhere."""
+    if x.is_cuda:
+        from .fused import head_linear
+        return head_linear(linear, x)
+    return linear(x)
+
+
 class BertForTokenClassification(BertPreTrainedModel):
     """Per-token classifier; the loss only counts positions with
     ``attention_mask == 1`` (src/modeling.py:1259-1268)."""
@@ -683,7 +691,7 @@ class BertForTokenClassification(BertPreTrainedModel):
     def forward(self, input_ids, token_type_ids=None, attention_mask=None, labels=None):
         layers, _ = self.bert(input_ids, token_type_ids, attention_mask)
         seq = layers[-1]
-        logits = self.classifier(self.dropout(seq))
+        logits = _head(self.classifier, self.dropout(seq))          # K29: own small-N GEMM on a B200
         if labels is not None:
             flat_logits = logits.view(-1, self.num_labels).float()
             flat_labels = labels.view(-1)
@@ -704,7 +712,7 @@ class BertForQuestionAnswering(BertPreTrainedModel):
     def forward(self, input_ids, token_type_ids=None, attention_mask=None):
         layers, _ = self.bert(input_ids, token_type_ids, attention_mask)
         seq = layers[-1]
-        logits = self.qa_outputs(seq)
+        logits = _head(self.qa_outputs, seq)                        # K28: own small-N GEMM on a B200
         start, end = logits.split(1, dim=-1)
         return start.squeeze(-1), end.squeeze(-1)
 

@@ -390,3 +390,26 @@ def test_kfac_taps_of_the_fused_engine_match_module_hooks():
     k_f.step()
     assert all(torch.isfinite(p.grad).all() for p in m_f.parameters() if p.grad is not None)
     assert not any("graph" in e for e in eng._graphs.values())      # Python-side taps: no graph capture with K-FAC
+
+
+@pytest.mark.parametrize("n,dtype", [(2, torch.bfloat16), (9, torch.bfloat16), (1, torch.float16), (5, torch.float32)])
+def test_small_n_head_linear_on_the_tcgen05_gemm(n, dtype):
+    """K28 / K29: the QA (N = 2) and classifier (N = num_labels) heads through _HeadLinearFn (N padded to 8, NT fp32-store
+    forward, NN dgrad, TN fp32 wgrad) against nn.Linear in fp32: outputs and all three gradients."""
+    from bert_pytorch_b200.models.fused import head_linear
+    torch.manual_seed(0)
+    M, H = 4 * 384, 256
+    lin = torch.nn.Linear(H, n).cuda()
+    x = (torch.randn(4, 384, H, device="cuda") * 0.5).to(dtype).requires_grad_(True)
+    y = head_linear(lin, x)
+    assert y.shape == (4, 384, n)
+    gy = torch.randn_like(y.float())
+    y.float().backward(gy)
+    xr = x.detach().float().requires_grad_(True)
+    wr = lin.weight.detach().to(torch.bfloat16).float().requires_grad_(True)       # the kernel multiplies bf16 operands
+    br = lin.bias.detach().clone().requires_grad_(True)
+    yr = xr.to(torch.bfloat16).float() @ wr.t() + br
+    yr.backward(gy)
+    assert (y.float() - yr).abs().max().item() < 2e-2 * max(1.0, yr.abs().max().item())
+    for got, want in ((x.grad.float(), xr.grad), (lin.weight.grad.float(), wr.grad), (lin.bias.grad.float(), br.grad)):
+        assert (got - want).abs().max().item() <= 2e-2 * max(want.abs().max().item(), 1e-3), (got - want).abs().max().item()

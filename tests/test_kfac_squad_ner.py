@@ -85,6 +85,67 @@ def test_kfac_kl_clip_and_distributed_equivalence():
         assert torch.allclose(g0, g1, atol=1e-6) and torch.allclose(g0, g2, atol=1e-6)
 
 
+def _kfac_gloo_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method="env://")
+    from bert_pytorch_b200.parallel import TorchComm
+    torch.manual_seed(0)
+    base = torch.nn.Sequential(torch.nn.Linear(6, 4), torch.nn.Tanh(), torch.nn.Linear(4, 3), torch.nn.Tanh(),
+                               torch.nn.Linear(3, 2)).train()
+    xs = [torch.randn(8, 6) for _ in range(world)]
+    comm = TorchComm()
+    k = kfac.KFAC(base, lr=1.0, kl_clip=1e-3, factor_update_freq=1, inv_update_freq=1, comm=comm,
+                  comm_method=kfac.CommMethod.HYBRID_OPT, grad_worker_fraction=0.5, inv_dtype=torch.float32)
+    for _ in range(2):                                   # second step: receivers re-use their allocated eigen buffers
+        for p in base.parameters():
+            p.grad = None
+        base(xs[rank]).pow(2).mean().backward()
+        for p in base.parameters():
+            comm.all_reduce_(p.grad, op="avg")
+        k.step()
+    q.put((rank, [p.grad.clone() for p in base.parameters()]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_kfac_hybrid_groups_over_gloo_four_ranks_match_single_process():
+    """HYBRID_OPT at 4 ranks = gradient-worker groups of 2 (reference recipe: run_pretraining.py:321-345): eigen-pairs go
+    to the group, preconditioned gradients to the ranks outside it, through real sub-group broadcasts (eigh hands back
+    column-major eigenvectors: the payloads must be made dense first -- the 4-GPU bench of round 2 tripped over that).
+    Every rank must end with the single-process result on the concatenated batch."""
+    import torch.multiprocessing as mp
+    world, port = 4, 29671
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_kfac_gloo_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+    for r in range(1, world):
+        for g0, g in zip(res[0][1], res[r][1]):
+            assert torch.allclose(g0, g, atol=1e-5), (r, (g0 - g).abs().max())
+    # single process, same data: factors are averages over micro-batches == averages over ranks
+    torch.manual_seed(0)
+    base = torch.nn.Sequential(torch.nn.Linear(6, 4), torch.nn.Tanh(), torch.nn.Linear(4, 3), torch.nn.Tanh(),
+                               torch.nn.Linear(3, 2)).train()
+    xs = [torch.randn(8, 6) for _ in range(world)]
+    k = kfac.KFAC(base, lr=1.0, kl_clip=1e-3, factor_update_freq=1, inv_update_freq=1, accumulate_data=True,
+                  inv_dtype=torch.float32)
+    for _ in range(2):
+        for p in base.parameters():
+            p.grad = None
+        for x in xs:
+            base(x).pow(2).mean().backward()         # unscaled micro-losses feed the taps exactly like one rank each
+        for p in base.parameters():
+            p.grad /= world
+        k.step()
+    for g0, g in zip(res[0][1], [p.grad for p in base.parameters()]):
+        assert torch.allclose(g0, g, atol=1e-4, rtol=1e-3), (g0 - g).abs().max()
+
+
 # ---------------------------------------------------------------------------------------------- SQuAD
 VOCAB = ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]", "the", "capital", "of", "france", "is", "paris", ".", "what", "?",
          "berlin", "germany", "and", "city", "a", "big", "##s", "river", "seine", "flows", "through", "who", "wrote",
