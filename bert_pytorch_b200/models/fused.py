@@ -71,6 +71,8 @@ class _LayerSaved:
     y1: torch.Tensor = None
     act: torch.Tensor = None
     pre2: torch.Tensor = None
+    mask1: torch.Tensor = None      # dropout keep bits of the two hidden-dropout sites (uint8 [M, H / 8]), written by the
+    mask2: torch.Tensor = None      # GEMM epilogues, read back by the LayerNorm backward kernels
     mean2: torch.Tensor = None
     rstd2: torch.Tensor = None
     sdpa: tuple = None
@@ -353,9 +355,16 @@ class FusedEncoderEngine:
                                            stream=_stream(l, SITE_ATTN_PROB), fp8=self._side(f"{l}.ctx"))
             ctx = ctx.view(M, H)
             ctx_q = q[0].view(M, H) if q else None
+        # keep bits of the hidden dropout leave the GEMM epilogue (1 bit per element) so that the LayerNorm backward does
+        # not have to run Philox again (60 of its 290 instructions per 8 elements) -- CTA-pair kernel, bf16 path only
+        keep_bits = (save and ph > 0 and not self.fp8 and H % 128 == 0 and K.pick_block_n(M, H) == 512
+                     and os.environ.get("B200_DROP_MASK", "1") != "0")
+        mask1 = torch.empty(M, H // 8, dtype=torch.uint8, device=x.device) if keep_bits else None
+        mask2 = torch.empty(M, H // 8, dtype=torch.uint8, device=x.device) if keep_bits else None
         pre1, ctx_op = self._lin(l, "ctx", "wo", ctx, self.w(pre + "attention.output.dense.weight"), xq=ctx_q,
                                  epi=K.EPI_BIAS_DROP_RES, bias=self.w(pre + "attention.output.dense.bias"), res=x,
-                                 p_drop=ph, seed=seed, stream=_stream(l, SITE_ATTN_OUT))
+                                 p_drop=ph, seed=seed, stream=_stream(l, SITE_ATTN_OUT),
+                                 **({"mask_out": mask1} if keep_bits else {}))
         # producers emit the fp8 copy of their output for the next GEMM (no separate quantise pass)
         x1, mean1, rstd1, *q = K.layer_norm_fwd(pre1, self.p(pre + "attention.output.LayerNorm.weight"),
                                                 self.p(pre + "attention.output.LayerNorm.bias"), save_stats=save,
@@ -375,7 +384,7 @@ class FusedEncoderEngine:
             act, *q = K.gelu_fwd(y1, fp8=side) if side else (K.gelu_fwd(y1),)
         pre2, act_op = self._lin(l, "act", "w2", act, self.w(pre + "output.dense.weight"), xq=q[0] if q else None,
                                  epi=K.EPI_BIAS_DROP_RES, bias=self.w(pre + "output.dense.bias"), res=x1, p_drop=ph,
-                                 seed=seed, stream=_stream(l, SITE_FFN_OUT))
+                                 seed=seed, stream=_stream(l, SITE_FFN_OUT), **({"mask_out": mask2} if keep_bits else {}))
         x2, mean2, rstd2, *q = K.layer_norm_fwd(pre2, self.p(pre + "output.LayerNorm.weight"),
                                                 self.p(pre + "output.LayerNorm.bias"), save_stats=save,
                                                 fp8=self._side(f"{l + 1}.x") if l + 1 < self.L else None)
@@ -384,6 +393,7 @@ class FusedEncoderEngine:
             ls.x, ls.qkv, ls.ctx, ls.lse = x, qkv, ctx, lse
             ls.pre1, ls.mean1, ls.rstd1, ls.x1 = pre1, mean1, rstd1, x1
             ls.y1, ls.act, ls.pre2, ls.mean2, ls.rstd2 = y1, act, pre2, mean2, rstd2
+            ls.mask1, ls.mask2 = mask1, mask2
             ls.x_op, ls.ctx_op, ls.x1_op, ls.act_op = x_op, ctx_op, x1_op, act_op   # wgrad operands (fp8 or bf16)
         return x2, ls, x2q
 
@@ -434,7 +444,7 @@ class FusedEncoderEngine:
             d, ls.pre2, ls.mean2, ls.rstd2, self.p(pre + "output.LayerNorm.weight"),
             dgamma=self.g(pre + "output.LayerNorm.weight"), dbeta=self.g(pre + "output.LayerNorm.bias"),
             dbias=self.g(pre + "output.dense.bias"), want_dropped=True, p_drop=ph, seed=seed,
-            drop_stream=_stream(l, SITE_FFN_OUT), fp8=self._side(f"{l}.d_y2"))
+            drop_stream=_stream(l, SITE_FFN_OUT), fp8=self._side(f"{l}.d_y2"), keep_mask=ls.mask2)
         if kfac is not None:
             kfac.tap(self.prefix + pre + "output.dense", ls.act, d_y2)
         # ---- FFN-2 / GELU'
@@ -460,7 +470,7 @@ class FusedEncoderEngine:
             dgamma=self.g(pre + "attention.output.LayerNorm.weight"),
             dbeta=self.g(pre + "attention.output.LayerNorm.bias"),
             dbias=self.g(pre + "attention.output.dense.bias"), want_dropped=True, p_drop=ph, seed=seed,
-            drop_stream=_stream(l, SITE_ATTN_OUT), fp8=self._side(f"{l}.d_yo"))
+            drop_stream=_stream(l, SITE_ATTN_OUT), fp8=self._side(f"{l}.d_yo"), keep_mask=ls.mask1)
         if kfac is not None:
             kfac.tap(self.prefix + pre + "attention.output.dense", ls.ctx, d_yo)
         # ---- attention output projection

@@ -32,6 +32,11 @@ STREAM_K = os.environ.get("B200_STREAM_K", "0") == "1"
 TAIL_SPLIT = os.environ.get("B200_TAIL_SPLIT", "0") == "1"
 
 
+def pick_block_n(M: int, N: int) -> int:
+    """The tile variant :func:`gemm` chooses for an [M, N] output (512 = CTA-pair kernel)."""
+    return _pick_block_n(M, N)
+
+
 def _count(n: int = 1) -> None:
     global KERNEL_LAUNCHES
     KERNEL_LAUNCHES += n
@@ -60,11 +65,13 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, layout: int = NT, epi: int = EPI_N
          block_n: Optional[int] = None, alpha: float = 1.0, p_drop: float = 0.0, seed: int = 0,
          stream: int = 0, scale_a: Optional[torch.Tensor] = None, scale_b: Optional[torch.Tensor] = None,
          a_e5m2: bool = False, b_e5m2: bool = False, push: bool = False,
-         colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
+         colsum: Optional[torch.Tensor] = None, mask_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """tcgen05 GEMM with a fused epilogue (see csrc/gemm_sm100.cu).  ``a``/``b`` are 2-D bf16, or -- with
     ``scale_a``/``scale_b`` (device inv-scale scalars from an :class:`Fp8Meta`) -- 1-byte fp8 tensors.
     ``colsum`` (fp32 [N], EPI_NONE / EPI_ADD / EPI_MUL): accumulates the column sums of the bf16 output (a bias
-    gradient that would otherwise need its own pass over the tensor)."""
+    gradient that would otherwise need its own pass over the tensor).  ``mask_out`` (uint8 [M, N / 8],
+    EPI_BIAS_DROP_RES on the CTA-pair kernel): receives the dropout keep bits, which :func:`layer_norm_bwd` can read
+    back (``keep_mask``) instead of regenerating them."""
     if layout == NT:
         M, N = a.size(0), b.size(0)
     elif layout == NN:
@@ -79,7 +86,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, layout: int = NT, epi: int = EPI_N
     elif block_n is None:
         block_n = _pick_block_n(M, N)
     extension().gemm(a, b, out, layout, epi, bias, res, aux_out, k_splits, block_n, alpha, p_drop, seed, stream,
-                     scale_a, scale_b, a_e5m2, b_e5m2, push, colsum)
+                     scale_a, scale_b, a_e5m2, b_e5m2, push, colsum, mask_out)
     _count()
     return out
 
@@ -246,15 +253,17 @@ NO_STREAM = 0xFFFFFFFF
 def layer_norm_bwd(dy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor, gamma: torch.Tensor, *,
                    dgamma: Optional[torch.Tensor], dbeta: Optional[torch.Tensor], dbias: Optional[torch.Tensor] = None,
                    want_dropped: bool = False, p_drop: float = 0.0, seed: int = 0, drop_stream: int = 0,
-                   in_stream: int = NO_STREAM, fp8=None):
+                   in_stream: int = NO_STREAM, fp8=None, keep_mask: Optional[torch.Tensor] = None):
     """Returns (dx, dx_dropped or None).  ``dgamma``/``dbeta``/``dbias`` are *accumulated into*.
+    ``keep_mask`` (uint8 [M, H / 8]): the keep bits of the ``drop_stream`` dropout as written by the producing GEMM
+    (``gemm(mask_out=...)``); without it the decisions are regenerated from the Philox stream (same bits).
     ``fp8=(meta, site)`` (with ``want_dropped``): also the fp8 copy of dx_dropped -> (dx, dxd, q)."""
     dx = torch.empty_like(x)
     dxd = torch.empty_like(x) if want_dropped else None
     M, H = x.numel() // x.size(-1), x.size(-1)
     q, rec, e5 = _fp8_side(fp8 if want_dropped else None, x)
     extension().layer_norm_bwd(dy, x, mean, rstd, gamma, dx, dxd, dgamma, dbeta, dbias, _ln_workspace(M, H, x.device),
-                               p_drop, seed, drop_stream, in_stream, q, rec, e5)
+                               p_drop, seed, drop_stream, in_stream, q, rec, e5, keep_mask)
     _count(2)
     return (dx, dxd) if fp8 is None else (dx, dxd, q)
 

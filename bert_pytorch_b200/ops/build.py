@@ -101,6 +101,11 @@ def build_cuda(verbose: bool = True) -> str:
         f"-L{os.path.join(cuda, 'lib64')}", "-lcudart", f"-Wl,-rpath,{torch_lib}",
         f"-Wl,-rpath,{os.path.join(cuda, 'lib64')}"]
     _run(link, os.path.join(BUILD, "link.log"))
+    # objects of earlier source revisions are dead weight (hundreds of MB that every gpurun snapshot would carry)
+    keep = {os.path.basename(o) for o in objs} | {os.path.basename(bind_obj)}
+    for f in os.listdir(BUILD):
+        if f.endswith(".o") and f not in keep:
+            os.remove(os.path.join(BUILD, f))
     if verbose:
         print(f"[build] {out}")
     return out

@@ -625,6 +625,8 @@ attn_fwd_row_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs
   __syncthreads();
   tc_fence_after();
   const uint32_t tS = *tmem_slot, tO = tS + 64;
+  pdl_trigger();
+  pdl_wait();                              // PDL: the set-up above overlapped the previous kernel's tail
 
   if (warp == 4) {
     if (lane == 0) {
@@ -2020,6 +2022,8 @@ attn_bwd_row2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tS = tmem, tDP = tmem + 128, tDV = tmem, tDK = tmem + 64, tDQ = tmem + 128;
+  pdl_trigger();
+  pdl_wait();                              // PDL: see attn_fwd_row_kernel
 
   if (warp == 8) {
     if (lane == 0) {
@@ -2264,7 +2268,7 @@ void attention_fwd(const void* qkv, const int* seqlens, void* ctx, float* lse, i
       static bool once = false;
       if (!once) { B200_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEMR)); once = true; }
       const int g = n_items < sms * 4 ? n_items : sms * 4;
-      attn_fwd_row_kernel<<<g, ATT_ROW_THREADS, SMEMR, st>>>(tm, a, n_items);
+      launch_pdl(attn_fwd_row_kernel, dim3(g), dim3(ATT_ROW_THREADS), SMEMR, st, tm, a, n_items);
     } else {
       constexpr int SMEMS = 16384 * 5 + 1024 + 256;
       static bool once = false;
@@ -2346,7 +2350,7 @@ void attention_bwd(const void* qkv, const int* seqlens, const void* ctx, const v
     }
     const int n_items = B * h;
     const int g = n_items < sms * 2 ? n_items : sms * 2;
-    attn_bwd_row2_kernel<<<g, ATT_BWD_THREADS, SMEM2, st>>>(tq, td, a, n_items);
+    launch_pdl(attn_bwd_row2_kernel, dim3(g), dim3(ATT_BWD_THREADS), SMEM2, st, tq, td, a, n_items);
     return;
   }
   if (nkb == 1 && single_ok && attn_row_enabled() && bwd_row == 1) {       // round-2 kernel: thread per query row, persistent CTAs

@@ -74,10 +74,12 @@ inline float* opt_f32(const c10::optional<Tensor>& t) {
 //   layout 0 (NT): a [M,K], b [N,K]     1 (NN): a [M,K], b [K,N]     2 (TN): a [K,M], b [K,N]
 // fp8 mode (scale_a/scale_b given): a/b are 1-byte e4m3 (or e5m2, per flag) tensors, row strides multiples of 16,
 // scale_* are the device inv_scale floats (views into the fp8 meta table); CTA-pair kernel only.
+static inline bool p_drop_is_zero(double p) { return !(p > 0.0); }
+
 void gemm(Tensor a, Tensor b, Tensor out, int64_t layout, int64_t epi, c10::optional<Tensor> bias,
           c10::optional<Tensor> res, c10::optional<Tensor> aux_out, int64_t k_splits, int64_t block_n, double alpha,
           double p_drop, int64_t seed, int64_t stream_id, c10::optional<Tensor> scale_a, c10::optional<Tensor> scale_b,
-          bool a_e5m2, bool b_e5m2, bool allow_push, c10::optional<Tensor> colsum) {
+          bool a_e5m2, bool b_e5m2, bool allow_push, c10::optional<Tensor> colsum, c10::optional<Tensor> mask_out) {
   const bool fp8 = scale_a.has_value() && scale_a->defined();
   if (fp8) {
     TORCH_CHECK(a.is_cuda() && b.is_cuda() && a.element_size() == 1 && b.element_size() == 1 && a.stride(1) == 1 &&
@@ -143,6 +145,13 @@ void gemm(Tensor a, Tensor b, Tensor out, int64_t layout, int64_t epi, c10::opti
     c.colsum = opt_f32(colsum);
   }
   TORCH_CHECK(epi != b200::EPI_BIAS_DROP_RES || c.res != nullptr, "bias+dropout+residual needs res");
+  if (mask_out.has_value() && mask_out->defined()) {
+    TORCH_CHECK(epi == b200::EPI_BIAS_DROP_RES && block_n == 512 && !p_drop_is_zero(p_drop), "mask_out: dropout epilogue of the CTA-pair kernel only");
+    TORCH_CHECK(mask_out->is_cuda() && mask_out->scalar_type() == at::kByte && mask_out->is_contiguous() &&
+                mask_out->numel() == M * (N / 8) && reinterpret_cast<uintptr_t>(mask_out->data_ptr()) % 16 == 0 && N % 128 == 0,
+                "mask_out: uint8 [M, N / 8], 16-byte aligned, N % 128 == 0");
+    c.mask_out = mask_out->data_ptr<uint8_t>();
+  }
   c.k_splits = (int)k_splits;
   c.alpha = (float)alpha;
   c.p_drop = (float)p_drop;
@@ -180,17 +189,23 @@ int64_t ln_bwd_workspace(int64_t M, int64_t H) { return b200::ln_bwd_workspace_f
 void layer_norm_bwd(Tensor dy, Tensor x, Tensor mean, Tensor rstd, Tensor gamma, Tensor dx, c10::optional<Tensor> dxd,
                     c10::optional<Tensor> dgamma, c10::optional<Tensor> dbeta, c10::optional<Tensor> dbias,
                     Tensor workspace, double p_drop, int64_t seed, int64_t drop_stream, int64_t in_stream,
-                    c10::optional<Tensor> q8, c10::optional<Tensor> meta8, bool e5m2) {
+                    c10::optional<Tensor> q8, c10::optional<Tensor> meta8, bool e5m2, c10::optional<Tensor> keep_mask) {
   check_bf16(dy, "dy"); check_bf16(x, "x"); check_bf16(dx, "dx");
   const int H = (int)x.size(-1), M = (int)(x.numel() / H);
   TORCH_CHECK(workspace.numel() >= b200::ln_bwd_workspace_floats(M, H), "LN workspace too small");
   c10::cuda::CUDAGuard guard(x.device());
   void* dxd_p = nullptr;
   if (dxd.has_value() && dxd->defined()) { check_bf16(*dxd, "dxd"); dxd_p = dxd->data_ptr(); }
+  const uint8_t* km = nullptr;
+  if (keep_mask.has_value() && keep_mask->defined()) {   // keep bits written by the producing GEMM (GemmCall::mask_out)
+    TORCH_CHECK(keep_mask->is_cuda() && keep_mask->scalar_type() == at::kByte && keep_mask->is_contiguous() &&
+                keep_mask->numel() == (int64_t)M * (H / 8), "keep_mask: uint8 [M, H / 8]");
+    km = keep_mask->data_ptr<uint8_t>();
+  }
   b200::layer_norm_bwd(dy.data_ptr(), x.data_ptr(), mean.data_ptr<float>(), rstd.data_ptr<float>(),
                        gamma.data_ptr<float>(), dx.data_ptr(), dxd_p, opt_f32(dgamma), opt_f32(dbeta), opt_f32(dbias),
                        workspace.data_ptr<float>(), M, H, mk_seed(seed), (unsigned)drop_stream,
-                       (unsigned)in_stream, (float)p_drop, mk_fp8(q8, meta8, e5m2, x.numel()), cur_stream());
+                       (unsigned)in_stream, (float)p_drop, mk_fp8(q8, meta8, e5m2, x.numel()), cur_stream(), km);
 }
 
 void gelu_fwd(Tensor x, Tensor y, c10::optional<Tensor> q8, c10::optional<Tensor> meta8, bool e5m2) {
@@ -482,9 +497,20 @@ void fp8_update(Tensor meta, Tensor is_e5m2, double margin_pow2) {
   b200::fp8_update(meta.data_ptr<float>(), (int)(meta.numel() / 4), is_e5m2.data_ptr<int>(), (float)margin_pow2, cur_stream());
 }
 
+// measurement knobs of the pair GEMM (tools/gemm_lab.py): flags as in GemmArgs::lab, stats = int64 CUDA tensor [74 * 4] or None
+void gemm_lab(int64_t flags, c10::optional<Tensor> stats) {
+  unsigned long long* sp = nullptr;
+  if (stats.has_value() && stats->defined()) {
+    TORCH_CHECK(stats->is_cuda() && stats->scalar_type() == at::kLong && stats->numel() >= 74 * 4, "gemm_lab stats");
+    sp = reinterpret_cast<unsigned long long*>(stats->data_ptr<int64_t>());
+  }
+  b200::gemm_lab((unsigned int)flags, sp);
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.def("gemm_lab", &gemm_lab);
   m.doc() = "bert_pytorch_b200 sm_100a kernels";
   m.def("gemm", &gemm);
   m.def("set_seed_step", &set_seed_step);

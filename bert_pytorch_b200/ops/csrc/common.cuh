@@ -31,6 +31,14 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+// Programmatic dependent launch (PDL): a kernel launched with launch_pdl() may become resident while its predecessor
+// in the stream is still draining; everything it does before pdl_wait() (barrier init, TMEM allocation, descriptor
+// prefetch) overlaps the predecessor's tail, pdl_wait() returns once the predecessor grid has completed and its
+// writes are visible.  pdl_trigger() lets the NEXT kernel's CTAs be scheduled as soon as every CTA of this grid has
+// started.  Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
@@ -98,6 +106,10 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int32_t c0, int32_t c1) {   // box -> L2 only
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0,
                                             int32_t c1, int32_t c2) {
@@ -170,6 +182,22 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait::ld that names the destination registers, so that no use of them can be scheduled above the wait when several
+// loads are kept in flight across other work (software-pipelined epilogues)
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                 "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                 "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait_dep16(uint32_t (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :: "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // 32 lanes x 32 consecutive fp32 columns: thread t of the warp gets row (lane base + t), v[j] = column j.
@@ -242,6 +270,13 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMa
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t mbar_cluster_addr,
+                                                int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {  // one warp in EACH CTA
@@ -436,6 +471,76 @@ __device__ __forceinline__ float dgelu_erf(float x) {
   return fmaf(x * 0.3989422804014327f, g.e, g.Phi);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Packed fp32 pairs (sm_100: FFMA2 / FMUL2 / FADD2 issue one instruction for two lanes of fp32 math).  The GEMM
+// epilogues are issue bound (K = 1024: the tensor cores finish one output element per SMSP and clock, i.e. 32
+// warp-instructions per element is ALL there is), so every FMA-class operation of the epilogue math runs two wide.
+// ------------------------------------------------------------------------------------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_pack_u(uint32_t lo, uint32_t hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ float2 f2_unpack(f32x2 v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_splat(float c) { return f2_pack(c, c); }
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_from_bf16x2(uint32_t w) {       // {lo, hi} bf16 -> two fp32 (exact)
+  return f2_pack_u(w << 16, w & 0xffff0000u);
+}
+__device__ __forceinline__ uint32_t f2_to_bf16x2(f32x2 v) {
+  const float2 f = f2_unpack(v);
+  return pack_bf16(f.x, f.y);
+}
+// gelu(x) and gelu'(x) of two values: the same arithmetic as gelu_parts(), FMA-class work two wide
+// (26 instructions per PAIR: 4 MUFU, 2 FFMA with |x|, 4 select, 2 pack, 14 packed -- 28 per element before)
+struct GeluDg2 { f32x2 g, dg; };
+__device__ __forceinline__ GeluDg2 gelu_dg2(f32x2 x) {
+  const float2 xf = f2_unpack(x);
+  float t0, t1, e0, e1;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(fmaf(fabsf(xf.x), 0.3275911f * 0.70710678118654752f, 1.0f)));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(fmaf(fabsf(xf.y), 0.3275911f * 0.70710678118654752f, 1.0f)));
+  const f32x2 t = f2_pack(t0, t1);
+  f32x2 poly = f2_fma(f2_splat(0.5f * 1.061405429f), t, f2_splat(0.5f * -1.453152027f));
+  poly = f2_fma(poly, t, f2_splat(0.5f * 1.421413741f));
+  poly = f2_fma(poly, t, f2_splat(0.5f * -0.284496736f));
+  poly = f2_fma(poly, t, f2_splat(0.5f * 0.254829592f));
+  const float2 s = f2_unpack(f2_mul(f2_mul(x, f2_splat(-0.5f * 1.4426950408889634f)), x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(s.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(s.y));
+  const f32x2 e = f2_pack(e0, e1);
+  const f32x2 h = f2_mul(f2_mul(poly, t), e);                          // 0.5 erfc(|x| / sqrt2)
+  const float2 hf = f2_unpack(h), omh = f2_unpack(f2_fma(h, f2_splat(-1.0f), f2_splat(1.0f)));
+  const f32x2 Phi = f2_pack(xf.x < 0.f ? hf.x : omh.x, xf.y < 0.f ? hf.y : omh.y);
+  GeluDg2 r;
+  r.g = f2_mul(x, Phi);
+  r.dg = f2_fma(f2_mul(x, f2_splat(0.3989422804014327f)), e, Phi);
+  return r;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -486,3 +591,22 @@ __device__ __forceinline__ void fp8_amax_commit(const Fp8Out& f, float amax) {
       abort();                                                                                  \
     }                                                                                           \
   } while (0)
+
+// launch with the programmatic-stream-serialization attribute (see pdl_wait above); B200_PDL=0 launches plainly
+#include <utility>
+namespace b200 {
+inline bool pdl_enabled() {
+  static const bool on = []() { const char* e = getenv("B200_PDL"); return e && e[0] == '1'; }();   // opt-in until measured
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  B200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...));
+}
+}  // namespace b200

@@ -38,6 +38,9 @@ struct GemmCall {
   void* aux_out = nullptr;
   const void* bias = nullptr;
   const void* res = nullptr; int ldr = 0;
+  // optional (EPI_BIAS_DROP_RES on the CTA-pair kernel): keep decisions of the dropout, one byte per 8 output columns
+  // ([M][N / 8], bit t = column 8 j + t kept) -- the LayerNorm backward reads them back instead of re-running Philox
+  unsigned char* mask_out = nullptr;
   float* colsum = nullptr;   // optional (bf16 epilogues): colsum[n] += sum_m out[m][n]  (bias gradients, fp32 atomics)
   int k_splits = 1;
   unsigned long long seed = 0; unsigned int stream = 0; float p_drop = 0.f;
@@ -55,6 +58,8 @@ struct GemmCall {
 };
 
 void gemm_bf16(const GemmCall& c, cudaStream_t st);
+// measurement knobs of the CTA-pair kernel (see GemmArgs::lab); stats: device buffer of 4 x 74 uint64 or nullptr
+void gemm_lab(unsigned int flags, unsigned long long* stats);
 
 CUtensorMap make_tmap_2d_bf16(const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
                               uint32_t box_outer);

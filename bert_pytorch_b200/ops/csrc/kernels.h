@@ -13,7 +13,7 @@ int ln_bwd_workspace_floats(int M, int H);
 void layer_norm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
                     void* dxd, float* dgamma, float* dbeta, float* dbias, float* workspace, int M, int H,
                     Seed seed, unsigned int drop_stream, unsigned int in_stream, float p_drop, Fp8Out f8,
-                    cudaStream_t st);
+                    cudaStream_t st, const uint8_t* keep_mask = nullptr);
 void gelu_fwd(const void* x, void* y, long long n, Fp8Out f8, cudaStream_t st);
 void dgelu_bwd(const void* dy, const void* x, void* dx, float* dbias, int M, int N, Fp8Out f8, cudaStream_t st);
 void colsum_bf16(const void* x, int M, int N, int ld, float* out, cudaStream_t st);

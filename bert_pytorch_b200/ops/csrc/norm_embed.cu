@@ -409,6 +409,8 @@ ln_fwd_row_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__
                   float eps) {
   constexpr int H = CHUNKS * 256;
   __shared__ float4 sg[CHUNKS][2][32], sb[CHUNKS][2][32];   // [chunk][half of the lane's 8 columns][lane]
+  pdl_trigger();
+  pdl_wait();
   for (int i = threadIdx.x; i < CHUNKS * 64; i += blockDim.x) {
     const int c = i >> 6, h = (i >> 5) & 1, l = i & 31;
     sg[c][h][l] = __ldg(reinterpret_cast<const float4*>(gamma + c * 256 + l * 8 + h * 4));
@@ -465,60 +467,71 @@ __global__ void __launch_bounds__(GROUPS * WPR * 32)
 ln_bwd3_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
                __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dxd, float* __restrict__ partial, int M,
-               Seed seed_in, unsigned int drop_stream, unsigned int thresh16, float drop_scale) {
+               Seed seed_in, unsigned int drop_stream, unsigned int thresh16, float drop_scale,
+               const uint8_t* __restrict__ keep_mask) {
+  // Round 2b: (1) all FMA-class work on packed fp32 pairs (FFMA2 / FMUL2 / FADD2: the kernel is issue bound -- 290
+  // instructions per 8-element slice before), (2) the dropout decisions of the residual branch are READ (one byte per
+  // 8 elements, written by the producing GEMM epilogue: GemmCall::mask_out) instead of regenerated with Philox
+  // (60 of the 290) whenever the caller has them.
   constexpr int H = WPR * 256;
   __shared__ float2 xchg[GROUPS][2][WPR];
   __shared__ float comb[GROUPS - 1 > 0 ? GROUPS - 1 : 1][3][H];
+  pdl_trigger();
+  pdl_wait();
   const unsigned long long seed = thresh16 != 0 ? seed_in.value() : 0ull;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int group = warp / WPR, wi = warp % WPR;
   const int col = (wi * 32 + lane) * 8;
-  float g[8], ag[8], ab[8], ad[8];
+  f32x2 g2[4], ag2[4], ab2[4], ad2[4];
   {
     const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col));
     const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + col + 4));
-    g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
+    g2[0] = f2_pack(g0.x, g0.y); g2[1] = f2_pack(g0.z, g0.w); g2[2] = f2_pack(g1.x, g1.y); g2[3] = f2_pack(g1.z, g1.w);
   }
 #pragma unroll
-  for (int t = 0; t < 8; ++t) ag[t] = ab[t] = ad[t] = 0.f;
+  for (int t = 0; t < 4; ++t) ag2[t] = ab2[t] = ad2[t] = 0ull;
   const int stride = gridDim.x * GROUPS;
   int row = blockIdx.x * GROUPS + group;
   uint4 nd = make_uint4(0, 0, 0, 0), nv = make_uint4(0, 0, 0, 0);
   float nmu = 0.f, nrs = 0.f;
+  uint32_t nmask = 0;
+  const bool use_mask = keep_mask != nullptr && dxd != nullptr && thresh16 != 0;
   if (row < M) {
     nd = ld_stream16(dy + (size_t)row * H + col);
     nv = ld_stream16(x + (size_t)row * H + col);
     nmu = __ldg(mean + row);
     nrs = __ldg(rstd + row);
+    if (use_mask) nmask = __ldg(keep_mask + (size_t)row * (H / 8) + (col >> 3));
   }
   constexpr float invH = 1.0f / (float)H;
   for (int it = 0; row < M; row += stride, ++it) {
-    float d[8], v[8];
-    unpack8(nd, d);
-    unpack8(nv, v);
+    const uint32_t dw[4] = {nd.x, nd.y, nd.z, nd.w}, vw[4] = {nv.x, nv.y, nv.z, nv.w};
     const float rs = nrs, nmr = -nmu * nrs;
+    const uint32_t mask = nmask;
     const int nrow = row + stride;
     if (nrow < M) {                        // next row's loads are in flight across this row's barrier
       nd = ld_stream16(dy + (size_t)nrow * H + col);
       nv = ld_stream16(x + (size_t)nrow * H + col);
       nmu = __ldg(mean + nrow);
       nrs = __ldg(rstd + nrow);
+      if (use_mask) nmask = __ldg(keep_mask + (size_t)nrow * (H / 8) + (col >> 3));
     }
-    float s1 = 0.f, s2 = 0.f;
+    const f32x2 rs2 = f2_splat(rs), nmr2 = f2_splat(nmr);
+    f32x2 xh[4], dg[4], s1p = 0ull, s2p = 0ull;
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      const float xh = fmaf(v[t], rs, nmr);
-      const float dg = d[t] * g[t];
-      ag[t] = fmaf(d[t], xh, ag[t]);
-      ab[t] += d[t];
-      s1 += dg;
-      s2 = fmaf(dg, xh, s2);
-      v[t] = xh;
-      d[t] = dg;
+    for (int t = 0; t < 4; ++t) {
+      const f32x2 d = f2_from_bf16x2(dw[t]);
+      xh[t] = f2_fma(f2_from_bf16x2(vw[t]), rs2, nmr2);
+      dg[t] = f2_mul(d, g2[t]);
+      ag2[t] = f2_fma(d, xh[t], ag2[t]);
+      ab2[t] = f2_add(ab2[t], d);
+      s1p = f2_add(s1p, dg[t]);
+      s2p = f2_fma(dg[t], xh[t], s2p);
     }
     // row sums across the WPR warps of this group: one named barrier per row, slots double buffered by parity
-    s1 = warp_sum(s1);
-    s2 = warp_sum(s2);
+    const float2 s1f = f2_unpack(s1p), s2f = f2_unpack(s2p);
+    float s1 = warp_sum(s1f.x + s1f.y);
+    float s2 = warp_sum(s2f.x + s2f.y);
     if (WPR > 1) {
       float2* slot = xchg[group][it & 1];
       if (lane == 0) slot[wi] = make_float2(s1, s2);
@@ -527,21 +540,35 @@ ln_bwd3_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __rest
 #pragma unroll
       for (int w = 0; w < WPR; ++w) { const float2 u = slot[w]; s1 += u.x; s2 += u.y; }
     }
-    const float c1 = -rs * s1 * invH, c2 = -rs * s2 * invH;
+    const f32x2 c1 = f2_splat(-rs * s1 * invH), c2 = f2_splat(-rs * s2 * invH);
+    f32x2 o[4];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) d[t] = fmaf(v[t], c2, fmaf(d[t], rs, c1));   // rs (dg - mean(dg) - xh mean(dg xh))
+    for (int t = 0; t < 4; ++t) o[t] = f2_fma(xh[t], c2, f2_fma(dg[t], rs2, c1));   // rs (dg - mean(dg) - xh mean(dg xh))
     const size_t off = (size_t)row * H + col;
-    store8(dx + off, d);
+    *reinterpret_cast<uint4*>(dx + off) = make_uint4(f2_to_bf16x2(o[0]), f2_to_bf16x2(o[1]), f2_to_bf16x2(o[2]), f2_to_bf16x2(o[3]));
     if (dxd != nullptr) {
       if (thresh16 != 0) {
-        const Keep8 keep = dropout_keep8(seed, drop_stream, (uint64_t)row * (uint64_t)(H / 8) + (uint64_t)(col >> 3), thresh16);
+        if (use_mask) {
 #pragma unroll
-        for (int t = 0; t < 8; ++t) d[t] = keep[t] ? d[t] * drop_scale : 0.f;
+          for (int t = 0; t < 4; ++t)
+            o[t] = f2_mul(o[t], f2_pack((mask >> (2 * t)) & 1u ? drop_scale : 0.f, (mask >> (2 * t + 1)) & 1u ? drop_scale : 0.f));
+        } else {
+          const Keep8 keep = dropout_keep8(seed, drop_stream, (uint64_t)row * (uint64_t)(H / 8) + (uint64_t)(col >> 3), thresh16);
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            o[t] = f2_mul(o[t], f2_pack(keep[2 * t] ? drop_scale : 0.f, keep[2 * t + 1] ? drop_scale : 0.f));
+        }
       }
 #pragma unroll
-      for (int t = 0; t < 8; ++t) ad[t] += d[t];
-      store8(dxd + off, d);
+      for (int t = 0; t < 4; ++t) ad2[t] = f2_add(ad2[t], o[t]);
+      *reinterpret_cast<uint4*>(dxd + off) = make_uint4(f2_to_bf16x2(o[0]), f2_to_bf16x2(o[1]), f2_to_bf16x2(o[2]), f2_to_bf16x2(o[3]));
     }
+  }
+  float ag[8], ab[8], ad[8];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float2 a = f2_unpack(ag2[t]), b = f2_unpack(ab2[t]), c = f2_unpack(ad2[t]);
+    ag[2 * t] = a.x; ag[2 * t + 1] = a.y; ab[2 * t] = b.x; ab[2 * t + 1] = b.y; ad[2 * t] = c.x; ad[2 * t + 1] = c.y;
   }
   // combine the row groups of the block in shared memory, then one atomic per column and quantity
   if (GROUPS > 1) {
@@ -585,6 +612,8 @@ ln_bwd3_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __rest
 __global__ void __launch_bounds__(256)
 colsum_finalize_kernel(const float* __restrict__ partial, int nblocks, int H, float* dgamma, float* dbeta,
                        float* dbias) {
+  pdl_trigger();
+  pdl_wait();
   const int qn = blockIdx.y;
   float* dst = qn == 0 ? dgamma : (qn == 1 ? dbeta : dbias);
   if (dst == nullptr) return;
@@ -615,6 +644,8 @@ colsum_finalize_kernel(const float* __restrict__ partial, int nblocks, int H, fl
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int M, int N, int ld,
                                                          float* __restrict__ out) {
   // block: 32 column-groups (8 cols each = 256 columns) x 8 row lanes
+  pdl_trigger();
+  pdl_wait();
   const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + cg * 8;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -973,10 +1004,10 @@ void layer_norm_fwd(const void* x, const float* gamma, const float* beta, void* 
     const __nv_bfloat16* xp = (const __nv_bfloat16*)x;
     __nv_bfloat16* yp = (__nv_bfloat16*)y;
     switch (H / 256) {
-      case 1: ln_fwd_row_kernel<1><<<g, 256, 0, st>>>(xp, gamma, beta, yp, mean, rstd, M, eps); break;
-      case 2: ln_fwd_row_kernel<2><<<g, 256, 0, st>>>(xp, gamma, beta, yp, mean, rstd, M, eps); break;
-      case 3: ln_fwd_row_kernel<3><<<g, 256, 0, st>>>(xp, gamma, beta, yp, mean, rstd, M, eps); break;
-      default: ln_fwd_row_kernel<4><<<g, 256, 0, st>>>(xp, gamma, beta, yp, mean, rstd, M, eps); break;
+      case 1: launch_pdl(ln_fwd_row_kernel<1>, dim3(g), dim3(256), 0, st, xp, gamma, beta, yp, mean, rstd, M, eps); break;
+      case 2: launch_pdl(ln_fwd_row_kernel<2>, dim3(g), dim3(256), 0, st, xp, gamma, beta, yp, mean, rstd, M, eps); break;
+      case 3: launch_pdl(ln_fwd_row_kernel<3>, dim3(g), dim3(256), 0, st, xp, gamma, beta, yp, mean, rstd, M, eps); break;
+      default: launch_pdl(ln_fwd_row_kernel<4>, dim3(g), dim3(256), 0, st, xp, gamma, beta, yp, mean, rstd, M, eps); break;
     }
     return;
   }
@@ -1004,7 +1035,7 @@ int ln_bwd_workspace_floats(int M, int H) { return ln2_grid(M) * 3 * H; }
 void layer_norm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
                     void* dxd, float* dgamma, float* dbeta, float* dbias, float* workspace, int M, int H,
                     Seed seed, unsigned int drop_stream, unsigned int in_stream, float p_drop, Fp8Out f8,
-                    cudaStream_t st) {
+                    cudaStream_t st, const uint8_t* keep_mask) {
   unsigned int th; float sc;
   drop_params(p_drop, th, sc);
   static const int split = []() {
@@ -1021,13 +1052,13 @@ void layer_norm_bwd(const void* dy, const void* x, const float* mean, const floa
     const int cap = ln2_bwd_grid(M);     // the workspace is sized for ln2_grid(M) >= this
     if (g > cap) g = cap;
     switch (wpr) {
-      case 1: ln_bwd3_kernel<1, 8><<<g, 256, 0, st>>>(dyp, xp, mean, rstd, gamma, dxp, dxdp, workspace, M, seed, drop_stream, th, sc); break;
-      case 2: ln_bwd3_kernel<2, 4><<<g, 256, 0, st>>>(dyp, xp, mean, rstd, gamma, dxp, dxdp, workspace, M, seed, drop_stream, th, sc); break;
-      case 3: ln_bwd3_kernel<3, 2><<<g, 192, 0, st>>>(dyp, xp, mean, rstd, gamma, dxp, dxdp, workspace, M, seed, drop_stream, th, sc); break;
-      default: ln_bwd3_kernel<4, 2><<<g, 256, 0, st>>>(dyp, xp, mean, rstd, gamma, dxp, dxdp, workspace, M, seed, drop_stream, th, sc); break;
+      case 1: launch_pdl(ln_bwd3_kernel<1, 8>, dim3(g), dim3(256), 0, st, dyp, xp, mean, rstd, gamma, dxp, dxdp, workspace, M, seed, drop_stream, th, sc, keep_mask); break;
+      case 2: launch_pdl(ln_bwd3_kernel<2, 4>, dim3(g), dim3(256), 0, st, dyp, xp, mean, rstd, gamma, dxp, dxdp, workspace, M, seed, drop_stream, th, sc, keep_mask); break;
+      case 3: launch_pdl(ln_bwd3_kernel<3, 2>, dim3(g), dim3(192), 0, st, dyp, xp, mean, rstd, gamma, dxp, dxdp, workspace, M, seed, drop_stream, th, sc, keep_mask); break;
+      default: launch_pdl(ln_bwd3_kernel<4, 2>, dim3(g), dim3(256), 0, st, dyp, xp, mean, rstd, gamma, dxp, dxdp, workspace, M, seed, drop_stream, th, sc, keep_mask); break;
     }
     dim3 g2((H + 31) / 32, 3, split);
-    colsum_finalize_kernel<<<g2, 256, 0, st>>>(workspace, g, H, dgamma, dbeta, dxd ? dbias : nullptr);
+    launch_pdl(colsum_finalize_kernel, g2, dim3(256), 0, st, (const float*)workspace, g, H, dgamma, dbeta, dxd ? dbias : (float*)nullptr);
     return;
   }
   const int grid = ln2_bwd_grid(M);
@@ -1035,12 +1066,12 @@ void layer_norm_bwd(const void* dy, const void* x, const float* mean, const floa
       (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, gamma, (__nv_bfloat16*)dx, (__nv_bfloat16*)dxd,
       workspace, M, H, seed, drop_stream, in_stream, th, sc, f8)));
   dim3 g2((H + 31) / 32, 3, split);
-  colsum_finalize_kernel<<<g2, 256, 0, st>>>(workspace, grid, H, dgamma, dbeta, dxd ? dbias : nullptr);
+  launch_pdl(colsum_finalize_kernel, g2, dim3(256), 0, st, (const float*)workspace, grid, H, dgamma, dbeta, dxd ? dbias : (float*)nullptr);
 }
 
 void colsum_bf16(const void* x, int M, int N, int ld, float* out, cudaStream_t st) {
   dim3 grid((N + 255) / 256, M >= 4096 ? 64 : (M >= 512 ? 16 : 1));
-  colsum_bf16_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, M, N, ld, out);
+  launch_pdl(colsum_bf16_kernel, grid, dim3(256), 0, st, (const __nv_bfloat16*)x, M, N, ld, out);
 }
 
 void gelu_fwd(const void* x, void* y, long long n, Fp8Out f8, cudaStream_t st) {

@@ -157,8 +157,10 @@ def test_gemm_bias_gelu_with_derivative(bn, M, N, Kd):
     g_ref, d_ref = _gelu_and_grad(x)
     aux = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
     out = K_.gemm(a, b, epi=K_.EPI_BIAS_GELU_DG, bias=bias, aux_out=aux, block_n=bn)
-    assert _bf16_ulp_err(out, g_ref) <= 1.25, _bf16_ulp_err(out, g_ref)   # 1 ulp + accumulation-order flips at bf16 ties
-    assert _bf16_ulp_err(aux, d_ref) <= 1.25, _bf16_ulp_err(aux, d_ref)
+    # 1 ulp + accumulation-order flips at bf16 ties + the 1.5e-7 ABSOLUTE error of the erfc polynomial, which is up to
+    # ~0.35 bf16 ulp of gelu(x) in the far negative tail (x ~ -4: |gelu| ~ 1e-4) -- seen as 1.34 over 50 M elements
+    assert _bf16_ulp_err(out, g_ref) <= 1.5, _bf16_ulp_err(out, g_ref)
+    assert _bf16_ulp_err(aux, d_ref) <= 1.5, _bf16_ulp_err(aux, d_ref)
 
 
 @pytest.mark.parametrize("bn", [256, 512])

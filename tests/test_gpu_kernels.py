@@ -59,6 +59,40 @@ def test_layer_norm_dropout_mask_consistency():
     assert (kept_fwd ^ kept_bwd).float().mean().item() < 1e-3
 
 
+def test_dropout_keep_bits_leave_the_gemm_and_feed_layer_norm_backward():
+    """Round 2b: the hidden-dropout decisions are written by the GEMM epilogue (1 bit per element, GemmCall::mask_out)
+    and read back by the LayerNorm backward instead of re-running Philox: the bits must describe the forward output,
+    and the backward with the mask must be BITWISE the backward that regenerates it."""
+    K = _api()
+    M, H = 1024, 1024
+    a = torch.randn(M, 64, device="cuda").to(torch.bfloat16)
+    w = torch.randn(H, 64, device="cuda").to(torch.bfloat16)
+    zeros_b = torch.zeros(H, device="cuda", dtype=torch.bfloat16)
+    res = torch.zeros(M, H, device="cuda", dtype=torch.bfloat16)
+    mask = torch.zeros(M, H // 8, dtype=torch.uint8, device="cuda")
+    fwd = K.gemm(a, w, epi=K.EPI_BIAS_DROP_RES, bias=zeros_b, res=res, p_drop=0.1, seed=77, stream=19, block_n=512,
+                 mask_out=mask)
+    ref = K.gemm(a, w, epi=K.EPI_BIAS_DROP_RES, bias=zeros_b, res=res, p_drop=0.1, seed=77, stream=19, block_n=512)
+    assert torch.equal(fwd, ref)                                          # writing the bits does not change the output
+    bits = ((mask.view(M, H // 8, 1) >> torch.arange(8, device="cuda", dtype=torch.uint8).view(1, 1, 8)) & 1).view(M, H).bool()
+    assert abs(1.0 - bits.float().mean().item() - 0.1) < 0.01
+    assert ((fwd != 0) ^ bits).float().mean().item() < 1e-3               # exact zeros of the product are the only mismatches
+    assert not (fwd[~bits] != 0).any()
+    x = torch.randn(M, H, device="cuda").to(torch.bfloat16)
+    g = torch.rand(H, device="cuda") + 0.5
+    y, mean, rstd = K.layer_norm_fwd(x, g, torch.zeros(H, device="cuda"))
+    dy = torch.randn(M, H, device="cuda").to(torch.bfloat16)
+    outs = []
+    for km in (None, mask):
+        dg, db, dbias = (torch.zeros(H, device="cuda") for _ in range(3))
+        dx, dxd = K.layer_norm_bwd(dy, x, mean, rstd, g, dgamma=dg, dbeta=db, dbias=dbias, want_dropped=True, p_drop=0.1,
+                                   seed=77, drop_stream=19, keep_mask=km)
+        outs.append((dx, dxd, dg, db, dbias))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])      # dx, dx_dropped: bitwise
+    for u, v in zip(outs[0][2:], outs[1][2:]):                # column sums finish with atomics: order-dependent rounding
+        assert torch.allclose(u, v, rtol=1e-4, atol=1e-3)
+
+
 def test_embedding_fwd_bwd():
     K = _api()
     B, S, H, V = 4, 32, 256, 1000

@@ -65,6 +65,18 @@ os.makedirs("gpurun_out", exist_ok=True)
 ordered.sort()
 per_step = len(ordered) // N
 last = ordered[-per_step:]
-json.dump({"phase": phase, "ordered_last_step": [[n, round(t, 1)] for _, n, t in last], "ms_per_micro_step_kernels": tot / N / 1e3,
+# wall span of the last micro-step on the device vs the time kernels were running: what launch gaps / tails cost
+t0 = last[0][0]
+end, busy, gaps = t0, 0.0, []
+for st, n, t in last:
+    if st > end:
+        gaps.append((st - end, n))
+    busy += max(0.0, st + t - max(end, st))
+    end = max(end, st + t)
+span = end - t0
+print(f"last micro-step: span {span / 1e3:.2f} ms, some kernel running {busy / 1e3:.2f} ms, idle {100 * (span - busy) / span:.1f}% "
+      f"in {len(gaps)} gaps (median {sorted(g for g, _ in gaps)[len(gaps) // 2] if gaps else 0:.1f} us)")
+json.dump({"phase": phase, "span_ms_last_step": span / 1e3, "busy_ms_last_step": busy / 1e3,
+           "ordered_last_step": [[n, round(t, 1), round(st - t0, 1)] for st, n, t in last], "ms_per_micro_step_kernels": tot / N / 1e3,
            "kernels": [{"name": n, "calls": c // N, "us_per_step": t / N} for n, (c, t) in rows]},
           open(f"gpurun_out/trace_step_p{phase}.json", "w"), indent=1)
