@@ -72,6 +72,7 @@ def build_cuda(verbose: bool = True) -> str:
         if not os.path.exists(path):
             continue
         flags = [f for f in NVCC_FLAGS if not (f == "--use_fast_math" and src in PRECISE)]
+        flags += os.environ.get("B200_NVCC_EXTRA", "").split()          # e.g. -DB200_GEMM_NO_LAB for A/B builds
         tag = _digest([path] + hdrs, " ".join(flags))
         obj = os.path.join(BUILD, f"{src}.{tag}.o")
         objs.append(obj)

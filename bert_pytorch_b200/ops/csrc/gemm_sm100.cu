@@ -916,6 +916,14 @@ __device__ __forceinline__ WorkSeg seg_get(const GemmArgs& p, int c, int C, int 
   return w;
 }
 
+// Measurement knobs compile to nothing with -DB200_GEMM_NO_LAB (A/B build: do the knobs themselves cost anything?)
+#ifdef B200_GEMM_NO_LAB
+#define LABV(p) 0u
+#define LABSTATS(p) ((unsigned long long*)nullptr)
+#else
+#define LABV(p) ((p).lab)
+#define LABSTATS(p) ((p).lab_stats)
+#endif
 // EC = epilogue class: every class is its own kernel, so the register allocation (168 per thread is the ceiling) and
 // the instruction footprint of one epilogue do not pay for the others (the single runtime-switched kernel spilled).
 enum { EC_F32 = 0, EC_GELU_DG = 1, EC_STAGED = 2 };
@@ -942,7 +950,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   // (8, 9) and the epilogue in warps 0..7: with the roles the other way round (round 1) every burst of epilogue math
   // delayed the issue loop (gemm_lab: K = 1024 tiles ran at 709 cycles per k-block with, 573 without the epilogue,
   // although the MMA issuer never waited for a free accumulator).  lab bit8 restores the old order for A/B runs.
-  const bool old_roles = (p.lab & 256u) != 0;
+  const bool old_roles = (LABV(p) & 256u) != 0;
   const int w_tma = old_roles ? 0 : 8, w_mma = old_roles ? 1 : 9;
   const int ew = old_roles ? warp - 2 : warp;          // epilogue warp index 0..7 (meaningless for the two feeders)
   const uint32_t rank = cluster_ctarank();
@@ -971,8 +979,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   cluster_sync_all();                    // peer barriers are initialised before anything remote touches them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
-  pdl_trigger();                         // the next kernel's CTAs may take this SM the moment this CTA leaves
-  pdl_wait();                            // PDL: everything above overlapped the previous kernel's tail
+  if (!(LABV(p) & 512u)) {
+    pdl_trigger();                       // the next kernel's CTAs may take this SM the moment this CTA leaves
+    pdl_wait();                          // PDL: everything above overlapped the previous kernel's tail
+  }
 
   const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
   const int nseg = seg_count(p, cluster_id, nclusters);
@@ -985,26 +995,26 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int nb = w.mn % p.n_blocks, mb = w.mn / p.n_blocks;
         const int kb0 = w.kb0, kb1 = w.kb1;
         const int m0 = mb * PAIR_M + (int)rank * 128, n0 = nb * PAIR_N + (int)rank * 128;
-        const int pf = (int)((p.lab >> 8) & 0xffu);
+        const int pf = (int)((LABV(p) >> 8) & 0xffu);
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % PAIR_STAGES;
           const uint32_t ph = (it / PAIR_STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * PAIR_STAGE;
           uint8_t* sb = sa + 16384;
-          if ((p.lab & 1u) && it >= (uint32_t)PAIR_STAGES) {          // lab: no refill, the MMAs re-read stale operands
+          if ((LABV(p) & 1u) && it >= (uint32_t)PAIR_STAGES) {          // lab: no refill, the MMAs re-read stale operands
             if (leader) mbar_arrive(&full_bar[s]);
             continue;
           }
           if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * PAIR_STAGE);
           const uint32_t fb = mapa_shared(smem_u32(&full_bar[s]), 0);
           int kbe = kb;
-          if (p.lab & 16u) {                                           // lab: every cluster walks K from its own offset
-            const int span = kb1 - kb0, off = (cluster_id * (int)((p.lab >> 16) & 0xffu)) % span;
+          if (LABV(p) & 16u) {                                           // lab: every cluster walks K from its own offset
+            const int span = kb1 - kb0, off = (cluster_id * (int)((LABV(p) >> 16) & 0xffu)) % span;
             kbe = kb0 + (kb - kb0 + off) % span;
           }
-          const int kc = (p.lab & 2u) ? (kb & 1) * BK : kbe * BK;
-          const int ma = (p.lab & 2u) ? (int)rank * 128 : m0, na = (p.lab & 2u) ? (int)rank * 128 : n0;
+          const int kc = (LABV(p) & 2u) ? (kb & 1) * BK : kbe * BK;
+          const int ma = (LABV(p) & 2u) ? (int)rank * 128 : m0, na = (LABV(p) & 2u) ? (int)rank * 128 : n0;
           if (pf > 0 && kb + pf < kb1 && !p.mn3d) {                               // pull the operands of k-block kb + pf into L2
             const int kp = (kb + pf) * BK;
             if constexpr (!A_MN) tma_prefetch_2d(&tmap_a, kp, ma);
@@ -1045,7 +1055,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       constexpr uint32_t A_KSTEP = A_MN ? (FP8 ? 4096u : 2048u) : 32u;
       constexpr uint32_t B_KSTEP = B_MN ? (FP8 ? 4096u : 2048u) : 32u;
       uint32_t it = 0, tile_it = 0;
-      const bool stats = p.lab_stats != nullptr;
+      const bool stats = LABSTATS(p) != nullptr;
       long long t_begin = 0, w_full = 0, w_tmem = 0;
       if (stats) t_begin = clock64();
       for (int si = 0; si < nseg; ++si, ++tile_it) {
@@ -1068,7 +1078,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const uint64_t db0 = B_MN ? umma_smem_desc_sw128(sb, 8192, 1024) : umma_smem_desc_sw128(sb, 16, 1024);
 #pragma unroll
           for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
-            if (p.lab & 64u) break;                 // lab: no MMAs at all -> the loop runs at the operand supply rate
+            if (LABV(p) & 64u) break;                 // lab: no MMAs at all -> the loop runs at the operand supply rate
             const uint64_t da = da0 + (uint64_t)((kk * A_KSTEP) >> 4);
             const uint64_t db = db0 + (uint64_t)((kk * B_KSTEP) >> 4);
             if constexpr (FP8) umma_fp8_ss_2sm(tmem_d, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
@@ -1079,7 +1089,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         umma_commit_2sm(&tmem_full[as], 3);      // both CTAs' epilogues may drain
       }
       if (stats) {
-        unsigned long long* o = p.lab_stats + 4 * cluster_id;
+        unsigned long long* o = LABSTATS(p) + 4 * cluster_id;
         o[0] = (unsigned long long)(clock64() - t_begin); o[1] = (unsigned long long)w_full;
         o[2] = (unsigned long long)w_tmem; o[3] = it;
       }
@@ -1087,7 +1097,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else {                               // ---------------- epilogue (both CTAs, own 128 rows)
     const int q = warp & 3;                  // TMEM lane quarter of this warp (hardware: warp id % 4)
     const int half = ew >> 2;
-    const bool staged = EC != EC_F32 && !(p.lab & 128u);   // lab bit7: register path
+    const bool staged = EC != EC_F32 && !(LABV(p) & 128u);   // lab bit7: register path
     const bool use_res = EC == EC_STAGED && staged && p.res != nullptr &&
                          (p.epi == EPI_BIAS_DROP_RES || p.epi == EPI_ADD || p.epi == EPI_DGELU || p.epi == EPI_MUL);
     const bool issuer = ew == 0 && lane == 0;   // first epilogue thread drives the staging tile's TMA traffic
@@ -1132,8 +1142,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int row0 = mb * PAIR_M + (int)rank * 128;
       const int row = row0 + r;
       const uint32_t taddr = tmem_base + as * PAIR_N + (uint32_t(q * 32) << 16);
-      if (p.lab & 12u) {                       // lab: bit2 = no epilogue at all, bit3 = drain the accumulator, store nothing
-        if (p.lab & 8u) {
+      if (LABV(p) & 12u) {                       // lab: bit2 = no epilogue at all, bit3 = drain the accumulator, store nothing
+        if (LABV(p) & 8u) {
           uint32_t acc = 0;
 #pragma unroll 1
           for (int c = half * 4; c < half * 4 + 4; ++c) {
@@ -1143,7 +1153,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 32; ++j) acc ^= v[j];
           }
-          if (acc == 0x12345678u && p.lab_stats != nullptr) p.lab_stats[0] = acc;
+          if (acc == 0x12345678u && LABSTATS(p) != nullptr) LABSTATS(p)[0] = acc;
         }
         tc_fence_before();
         mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), 0));
@@ -1308,6 +1318,11 @@ static CUtensorMap make_tmap_2d(const void* ptr, uint64_t inner, uint64_t outer,
 
 // MN-major bf16 operand as ONE box per CTA and stage: dims {64 mn (contiguous), K rows, MN / 64 groups}, box {64, BK, 2}
 // -> shared memory [2][BK][64], the layout the two 2-D boxes produce.  MN must be a multiple of 64.
+static CUtensorMapL2promotion mn_promotion() {     // measurement knob: B200_TMAP_PROMO=0..3 (none / 64 / 128 / 256 B)
+  static const int v = []() { const char* e = getenv("B200_TMAP_PROMO"); return e ? atoi(e) : 3; }();
+  return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+       : v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+}
 static CUtensorMap make_tmap_mn3d(const void* ptr, uint64_t mn, uint64_t k, uint64_t ld, uint32_t bk) {
   struct Key {
     const void* p; uint64_t mn, k, l; uint32_t bk;
@@ -1332,7 +1347,7 @@ static CUtensorMap make_tmap_mn3d(const void* ptr, uint64_t mn, uint64_t k, uint
   cuuint32_t box[3] = {64, bk, 2};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, mn_promotion(),
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { fprintf(stderr, "[b200] 3-D tensor map failed (%d)\n", (int)r); abort(); }
   if (cache.size() > 4096) cache.clear();
@@ -1355,7 +1370,7 @@ static int num_sms() {
   return n;
 }
 
-static unsigned int g_lab = 0;
+static unsigned int g_lab = []() { const char* e = getenv("B200_GEMM_LAB"); return e ? (unsigned int)strtoul(e, nullptr, 0) : 0u; }();
 static unsigned long long* g_lab_stats = nullptr;
 void gemm_lab(unsigned int flags, unsigned long long* stats) { g_lab = flags; g_lab_stats = stats; }
 
@@ -1489,7 +1504,8 @@ static void launch_pair(const GemmCall& c, cudaStream_t st) {
     configured = true;
   }
   const int tiles = p.m_blocks * p.n_blocks * p.k_splits;
-  const int pairs = num_sms() / 2;
+  int pairs = num_sms() / 2;
+  if ((p.lab >> 24) != 0 && (int)(p.lab >> 24) < pairs) pairs = (int)(p.lab >> 24);   // lab: fewer clusters (per-SM vs chip-wide supply)
   const int grid = p.stream_k ? 2 * pairs : 2 * (tiles < pairs ? tiles : pairs);
   if (grid <= 0) return;
   launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), PAIR_SMEM, st, ta, tb, to, tx, tr, p);

@@ -38,7 +38,9 @@ def main():
     variants = [("base", 0), ("norefill", 1), ("noepi", 4), ("ldonly", 8), ("norefill_noepi", 5), ("norefill_ldonly", 9),
                 ("stag1", 16 | (1 << 16)), ("stag4", 16 | (4 << 16)), ("stag13", 16 | (13 << 16)), ("box3d", 32),
                 ("box3d_stag4", 48 | (4 << 16)), ("nomma", 64 | 4), ("nomma_tile00", 64 | 4 | 2), ("nomma_box3d", 64 | 4 | 32),
-                ("direct_epi", 128), ("norefill_direct_epi", 129), ("oldroles", 256), ("oldroles_noepi", 256 | 4)]
+                ("direct_epi", 128), ("norefill_direct_epi", 129), ("oldroles", 256), ("oldroles_noepi", 256 | 4),
+                ("nomma_37", 64 | 4 | (37 << 24)), ("nomma_18", 64 | 4 | (18 << 24)), ("noepi_37", 4 | (37 << 24)),
+                ("base_37", 37 << 24)]
     if "--variants" in sys.argv:
         want = sys.argv[sys.argv.index("--variants") + 1].split(",")
         variants = [v for v in variants if v[0] in want]
@@ -81,6 +83,19 @@ def main():
             C.gemm_lab(0, None)
             print(json.dumps(rec), flush=True)
             f.write(json.dumps(rec) + "\n")
+        if "--wgrad" in sys.argv:               # the weight-gradient calls exactly as the engine issues them (split-K etc.)
+            for name, n_out, k_out in (("ffn1_wgrad", 4096, 1024), ("ffn2_wgrad", 1024, 4096), ("qkv_wgrad", 3072, 1024),
+                                       ("attn_out_wgrad", 1024, 1024)):
+                dy = torch.randn(M, n_out, device="cuda").bfloat16()
+                x = torch.randn(M, k_out, device="cuda").bfloat16()
+                grad = torch.zeros(n_out, k_out, device="cuda")
+                rec = {"name": name + "_engine", "splits": K.wgrad_splits(n_out, k_out, M, 512)}
+                for vname, flags in (("box3d", 0), ("box2d", 32), ("box3d_oldroles", 256), ("box2d_oldroles", 32 | 256)):
+                    C.gemm_lab(flags, None)
+                    rec[vname + "_ms"] = round(timeit(lambda: K.wgrad_accumulate(dy, x, grad)), 4)
+                C.gemm_lab(0, None)
+                print(json.dumps(rec), flush=True)
+                f.write(json.dumps(rec) + "\n")
         if "--epi" in sys.argv:                 # the fused epilogues of the engine, in issuer cycles per k-block
             def measure(run, flags=0):
                 C.gemm_lab(flags, None)
