@@ -166,6 +166,9 @@ class Fp8Meta:
         _count()
 
 
+WGRAD_WIDE = os.environ.get("B200_WGRAD_WIDE", "1") != "0"
+
+
 def wgrad_splits(n_out: int, k_out: int, reduce_len: int, block_n: int = 256) -> int:
     """Split-K factor for dW[n_out, k_out] so the grid covers the machine."""
     if block_n == 512:
@@ -186,6 +189,15 @@ def wgrad_accumulate(dy: torch.Tensor, x: torch.Tensor, grad: torch.Tensor, alph
     bn = 512 if fp8 else _pick_block_n(n_out, k_out)
     if bn == 128 and k_out >= 256:
         bn = 256
+    if bn == 512 and not fp8 and WGRAD_WIDE and k_out % 512 == 0:
+        # 256 x 512 tiles (two N = 256 MMAs per k-step share the A operand: a quarter fewer operand bytes per FLOP, which
+        # is what the MN-major TMA supply of the TN kernel is short of); fewer tiles than CTA pairs -> tail split
+        tiles = ((n_out + 255) // 256) * (k_out // 512)
+        kb = (dy.size(0) + 63) // 64
+        pairs = NUM_SMS // 2
+        splits = -2 if (tiles < pairs and kb * tiles // pairs >= 4) else 1
+        gemm(dy, x, layout=TN, epi=EPI_ACCUM_F32, out=grad, block_n=1024, alpha=alpha, k_splits=splits, push=push)
+        return
     splits = wgrad_splits(n_out, k_out, dy.size(0) // (2 if fp8 else 1), bn)
     if bn == 512 and not fp8 and not TAIL_SPLIT and not STREAM_K:
         # round-2 measurement with the 7-stage operand ring (profiles/gemm_bench_r2_wgrad.jsonl): the 48-tile QKV

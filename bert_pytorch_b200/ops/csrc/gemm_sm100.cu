@@ -31,7 +31,8 @@ namespace b200 {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;          // 64 bf16 = 128 B = one swizzle atom row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 320;     // warp0 TMA, warp1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+constexpr int NUM_THREADS = 320;     // single-CTA kernel: warp0 TMA, warp1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+constexpr int PAIR_THREADS = 352;    // pair kernel: warps 0..7 epilogue, 8 and 10 TMA producers (even / odd ring slots), 9 MMA
 constexpr int EPI_THREADS = 256;
 constexpr int SMEM_BUDGET = 196608;  // bytes for the operand ring (192 KB)
 
@@ -916,23 +917,35 @@ __device__ __forceinline__ WorkSeg seg_get(const GemmArgs& p, int c, int C, int 
   return w;
 }
 
-// Measurement knobs compile to nothing with -DB200_GEMM_NO_LAB (A/B build: do the knobs themselves cost anything?)
-#ifdef B200_GEMM_NO_LAB
-#define LABV(p) 0u
-#define LABSTATS(p) ((unsigned long long*)nullptr)
-#else
+// The measurement knobs (GemmArgs::lab, tools/gemm_lab.py) exist only in builds with -DB200_GEMM_LAB
+// (B200_NVCC_EXTRA=-DB200_GEMM_LAB python -m bert_pytorch_b200.ops.build): the handful of predicated instructions they
+// add to the single-thread TMA-producer and MMA-issuer loops cost the weight-gradient GEMM 19 % in situ (62.9 -> 74.8 us)
+// -- those two loops are the critical path of the kernel, every cycle of their period is a cycle the tensor cores wait.
+#ifdef B200_GEMM_LAB
 #define LABV(p) ((p).lab)
 #define LABSTATS(p) ((p).lab_stats)
+#else
+#define LABV(p) 0u
+#define LABSTATS(p) ((unsigned long long*)nullptr)
 #endif
 // EC = epilogue class: every class is its own kernel, so the register allocation (168 per thread is the ceiling) and
 // the instruction footprint of one epilogue do not pay for the others (the single runtime-switched kernel spilled).
 enum { EC_F32 = 0, EC_GELU_DG = 1, EC_STAGED = 2 };
-template <bool A_MN, bool B_MN, bool FP8, int EC>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)   // 10 warps: 3 on two of the SMSPs -> 168 registers
+// WIDE (fp32 epilogues only): a 256 x 512 tile per cluster -- two N = 256 MMAs per k-step share the A operand, the two
+// accumulators fill all 512 TMEM columns (no double buffering: a weight-gradient cluster owns one or two tiles with
+// K = 12288, there is nothing to overlap the epilogue with).  Operand bytes per FLOP drop by a quarter (48 KB instead of
+// 2 x 32 KB per 2 x 512 MMA cycles and CTA) -- which is what the TN kernel is short of: its MN-major TMA boxes arrive at
+// 46 B/clk per SM (gemm_lab 'nomma': 710 cycles per 32 KB stage, the same on 18 or 74 clusters), the 256 x 256 tile
+// needs 64.  Ring: 4 stages of 48 KB.
+template <bool A_MN, bool B_MN, bool FP8, int EC, bool WIDE = false>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)   // 11 warps: 3 on three of the SMSPs -> 168 registers
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_aux,
                  const __grid_constant__ CUtensorMap tmap_res, const GemmArgs p) {
-  constexpr int PAIR_STAGES = EC == EC_F32 ? 7 : 5;
+  static_assert(!WIDE || (EC == EC_F32 && !FP8), "the 256 x 512 tile serves the fp32 (weight-gradient) epilogues of the bf16 path");
+  constexpr int PAIR_STAGES = EC == EC_F32 ? (WIDE ? 4 : 7) : 5;
+  constexpr int PAIR_STAGE = WIDE ? 49152 : b200::PAIR_STAGE;        // bytes per CTA and stage: A 16 KB + B 16 / 32 KB
+  constexpr int TILE_N = WIDE ? 512 : PAIR_N;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sC = smem + PAIR_STAGES * PAIR_STAGE;          // staging tile (1024-aligned; absent in the 7-stage variant)
@@ -950,9 +963,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   // (8, 9) and the epilogue in warps 0..7: with the roles the other way round (round 1) every burst of epilogue math
   // delayed the issue loop (gemm_lab: K = 1024 tiles ran at 709 cycles per k-block with, 573 without the epilogue,
   // although the MMA issuer never waited for a free accumulator).  lab bit8 restores the old order for A/B runs.
-  const bool old_roles = (LABV(p) & 256u) != 0;
-  const int w_tma = old_roles ? 0 : 8, w_mma = old_roles ? 1 : 9;
-  const int ew = old_roles ? warp - 2 : warp;          // epilogue warp index 0..7 (meaningless for the two feeders)
+  // TWO producer warps (8: even iterations of the ring, 10: odd ones).  One producer's period is wait(empty) -> expect_tx
+  // -> 2..4 TMA instructions, ~130 + 175..290 cycles per instruction (gemm_lab 'nomma': 530 / 650 / 710 / 820 cycles per
+  // stage for 2 K-major / 1 + 1 / 2 three-dimensional / 4 two-dimensional MN-major boxes, the same on 18 and on 74
+  // clusters): above the 512 cycles the MMAs of a stage take for every layout but K-major.  Two threads overlap their
+  // issue latencies.
+  constexpr int w_tma = 8, w_mma = 9, w_tma2 = 10;
+  const int ew = warp;                                   // epilogue warp index 0..7 (meaningless for the feeders)
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   // elements per k-block: one 128-byte swizzle row of the operand type.  The fp8 variant moves the same bytes
@@ -987,16 +1004,18 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
   const int nseg = seg_count(p, cluster_id, nclusters);
 
-  if (warp == w_tma) {
-    if (lane == 0) {                     // ---------------- TMA producer (both CTAs)
+  if (warp == w_tma || warp == w_tma2) {
+    if (lane == 0) {                     // ---------------- TMA producers (both CTAs)
+      const uint32_t my_parity = warp == w_tma ? 0u : 1u;
       uint32_t it = 0;
       for (int si = 0; si < nseg; ++si) {
         const WorkSeg w = seg_get(p, cluster_id, nclusters, si);
         const int nb = w.mn % p.n_blocks, mb = w.mn / p.n_blocks;
         const int kb0 = w.kb0, kb1 = w.kb1;
-        const int m0 = mb * PAIR_M + (int)rank * 128, n0 = nb * PAIR_N + (int)rank * 128;
+        const int m0 = mb * PAIR_M + (int)rank * 128, n0 = nb * TILE_N + (int)rank * 128;
         const int pf = (int)((LABV(p) >> 8) & 0xffu);
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          if ((it & 1u) != my_parity) continue;               // the other producer's slot
           const int s = it % PAIR_STAGES;
           const uint32_t ph = (it / PAIR_STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
@@ -1033,15 +1052,20 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             tma_load_2d_2sm(sa, &tmap_a, fb, ma, kc);
             tma_load_2d_2sm(sa + 8192, &tmap_a, fb, ma + 64, kc);
           }
-          if constexpr (!B_MN) {
-            tma_load_2d_2sm(sb, &tmap_b, fb, kc, na);
-          } else if constexpr (FP8) {
-            tma_load_2d_2sm(sb, &tmap_b, fb, na, kc);
-          } else if (p.mn3d) {
-            tma_load_3d_2sm(sb, &tmap_b, fb, 0, kc, na >> 6);
-          } else {
-            tma_load_2d_2sm(sb, &tmap_b, fb, na, kc);
-            tma_load_2d_2sm(sb + 8192, &tmap_b, fb, na + 64, kc);
+#pragma unroll
+          for (int j = 0; j < (WIDE ? 2 : 1); ++j) {          // WIDE: this CTA's 128 columns of both N = 256 halves
+            uint8_t* sbj = sb + j * 16384;
+            const int naj = na + j * 256;
+            if constexpr (!B_MN) {
+              tma_load_2d_2sm(sbj, &tmap_b, fb, kc, naj);
+            } else if constexpr (FP8) {
+              tma_load_2d_2sm(sbj, &tmap_b, fb, naj, kc);
+            } else if (p.mn3d) {
+              tma_load_3d_2sm(sbj, &tmap_b, fb, 0, kc, naj >> 6);
+            } else {
+              tma_load_2d_2sm(sbj, &tmap_b, fb, naj, kc);
+              tma_load_2d_2sm(sbj + 8192, &tmap_b, fb, naj + 64, kc);
+            }
           }
         }
       }
@@ -1061,7 +1085,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       for (int si = 0; si < nseg; ++si, ++tile_it) {
         const WorkSeg w = seg_get(p, cluster_id, nclusters, si);
         const int kb0 = w.kb0, kb1 = w.kb1;
-        const uint32_t as = tile_it & 1, aph = (tile_it >> 1) & 1;
+        const uint32_t as = WIDE ? 0u : (tile_it & 1), aph = WIDE ? (tile_it & 1) : ((tile_it >> 1) & 1);
         if (stats) { const long long t0 = clock64(); mbar_wait(&tmem_empty[as], aph ^ 1); w_tmem += clock64() - t0; }
         else mbar_wait(&tmem_empty[as], aph ^ 1);
         tc_fence_after();
@@ -1083,6 +1107,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const uint64_t db = db0 + (uint64_t)((kk * B_KSTEP) >> 4);
             if constexpr (FP8) umma_fp8_ss_2sm(tmem_d, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
             else umma_bf16_ss_2sm(tmem_d, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+            if constexpr (WIDE)                        // second N = 256 half: same A, the B tile 16 KB further on
+              umma_bf16_ss_2sm(tmem_d + 256, da, db + (uint64_t)(16384 >> 4), idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
           }
           umma_commit_2sm(&empty_bar[s], 3);     // both CTAs may refill this slot
         }
@@ -1136,7 +1162,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const WorkSeg wseg = seg_get(p, cluster_id, nclusters, si);
       const int mn = wseg.mn;
       const int nb = mn % p.n_blocks, mb = mn / p.n_blocks;
-      const uint32_t as = tile_it & 1, aph = (tile_it >> 1) & 1;
+      const uint32_t as = WIDE ? 0u : (tile_it & 1), aph = WIDE ? (tile_it & 1) : ((tile_it >> 1) & 1);
       mbar_wait(&tmem_full[as], aph);
       tc_fence_after();
       const int row0 = mb * PAIR_M + (int)rank * 128;
@@ -1161,7 +1187,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       if (!staged) {
         if constexpr (EC != EC_GELU_DG) {
-          epilogue_tile<PAIR_N>(p, taddr, row, row < p.M, nb * PAIR_N, half * 4, half * 4 + 4, alpha, seed, wseg.kb0 == 0);
+#pragma unroll 1
+          for (int j = 0; j < (WIDE ? 2 : 1); ++j)
+            epilogue_tile<PAIR_N>(p, taddr + j * 256, row, row < p.M, nb * TILE_N + j * 256, half * 4, half * 4 + 4, alpha, seed,
+                                  wseg.kb0 == 0);
         }
         tc_fence_before();
         mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), 0));
@@ -1426,10 +1455,11 @@ static void launch(const GemmCall& c, cudaStream_t st) {
 template <bool A_MN, bool B_MN, bool FP8>
 static void launch_pair(const GemmCall& c, cudaStream_t st) {
   constexpr int BK = FP8 ? 128 : BLOCK_K;
+  const bool wide = !FP8 && c.block_n == 1024 && (c.epi == EPI_ACCUM_F32 || c.epi == EPI_F32);   // 256 x 512 tiles
   GemmArgs p;
   p.M = c.M; p.N = c.N; p.K = c.K;
   p.m_blocks = (c.M + PAIR_M - 1) / PAIR_M;
-  p.n_blocks = (c.N + PAIR_N - 1) / PAIR_N;
+  p.n_blocks = wide ? (c.N + 511) / 512 : (c.N + PAIR_N - 1) / PAIR_N;
   p.k_blocks = (c.K + BK - 1) / BK;
   p.k_splits = c.k_splits < 1 ? 1 : c.k_splits;
   if (p.k_splits > p.k_blocks) p.k_splits = p.k_blocks;
@@ -1496,8 +1526,13 @@ static void launch_pair(const GemmCall& c, cudaStream_t st) {
   auto kern = f32_out ? gemm_pair_kernel<A_MN, B_MN, FP8, EC_F32>
               : c.epi == EPI_BIAS_GELU_DG ? gemm_pair_kernel<A_MN, B_MN, FP8, EC_GELU_DG>
                                           : gemm_pair_kernel<A_MN, B_MN, FP8, EC_STAGED>;
+  if constexpr (!FP8) {
+    if (wide) kern = gemm_pair_kernel<A_MN, B_MN, false, EC_F32, true>;
+  }
   static bool configured = false;
   if (!configured) {
+    if constexpr (!FP8)
+      B200_CUDA_CHECK(cudaFuncSetAttribute(gemm_pair_kernel<A_MN, B_MN, false, EC_F32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
     B200_CUDA_CHECK(cudaFuncSetAttribute(gemm_pair_kernel<A_MN, B_MN, FP8, EC_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
     B200_CUDA_CHECK(cudaFuncSetAttribute(gemm_pair_kernel<A_MN, B_MN, FP8, EC_GELU_DG>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
     B200_CUDA_CHECK(cudaFuncSetAttribute(gemm_pair_kernel<A_MN, B_MN, FP8, EC_STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
@@ -1508,15 +1543,15 @@ static void launch_pair(const GemmCall& c, cudaStream_t st) {
   if ((p.lab >> 24) != 0 && (int)(p.lab >> 24) < pairs) pairs = (int)(p.lab >> 24);   // lab: fewer clusters (per-SM vs chip-wide supply)
   const int grid = p.stream_k ? 2 * pairs : 2 * (tiles < pairs ? tiles : pairs);
   if (grid <= 0) return;
-  launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), PAIR_SMEM, st, ta, tb, to, tx, tr, p);
+  launch_pdl(kern, dim3(grid), dim3(PAIR_THREADS), PAIR_SMEM, st, ta, tb, to, tx, tr, p);
 }
 
 void gemm_bf16(const GemmCall& c, cudaStream_t st) {
-  if (c.fp8 && c.block_n != 512) {
+  if (c.fp8 && c.block_n != 512 && c.block_n != 1024) {
     fprintf(stderr, "[b200] fp8 operands are implemented on the CTA-pair kernel only (block_n=512)\n");
     abort();
   }
-  if (c.block_n == 512) {   // CTA-pair 256 x 256 tiles
+  if (c.block_n == 512 || c.block_n == 1024) {   // CTA-pair 256 x 256 tiles (1024: 256 x 512 for the fp32 epilogues)
     switch (c.layout) {
       case GEMM_NT: c.fp8 ? launch_pair<false, false, true>(c, st) : launch_pair<false, false, false>(c, st); return;
       case GEMM_NN: c.fp8 ? launch_pair<false, true, true>(c, st) : launch_pair<false, true, false>(c, st); return;

@@ -81,6 +81,19 @@ def test_gemm_tn_tail_split(M, N, K):
     _check(out, base + a.float().t() @ b.float(), tol=1e-2)
 
 
+@pytest.mark.parametrize("M,N,K,splits", [(4096, 1024, 12288, -2), (1024, 4096, 4096, 1), (512, 512, 1024, -2), (768, 1536, 2048, 3),
+                                          (300, 1000, 520, 1)])
+def test_gemm_tn_wide_tiles(M, N, K, splits):
+    """256 x 512 tiles (block_n=1024: two N = 256 MMAs per k-step, all 512 TMEM columns, 4-stage ring of 48 KB) for the
+    fp32 weight-gradient epilogue, alone, with split-K and with the tail split; accumulates into ``out``."""
+    K_ = _ops()
+    a, b = _rand(K, M), _rand(K, N)
+    out = torch.randn(M, N, device="cuda")
+    ref = out.clone() + a.float().t() @ b.float()
+    K_.gemm(a, b, layout=K_.TN, epi=K_.EPI_ACCUM_F32, out=out, block_n=1024, k_splits=splits)
+    assert (out - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+
+
 @pytest.mark.parametrize("bn", [256, 512])
 def test_gemm_epilogues(bn):
     import functools
