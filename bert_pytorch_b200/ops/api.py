@@ -166,7 +166,9 @@ class Fp8Meta:
         _count()
 
 
-WGRAD_WIDE = os.environ.get("B200_WGRAD_WIDE", "1") != "0"
+# opt-in: 256 x 512 weight-gradient tiles measured faster in isolation (0.088 vs 0.096 ms, FFN shapes) but slower inside
+# the training step (74.5 vs 62.9 us per call, side stream off) -- profiles/README.md
+WGRAD_WIDE = os.environ.get("B200_WGRAD_WIDE", "0") == "1"
 
 
 def wgrad_splits(n_out: int, k_out: int, reduce_len: int, block_n: int = 256) -> int:

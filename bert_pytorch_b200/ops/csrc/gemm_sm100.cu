@@ -1008,16 +1008,16 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (lane == 0) {                     // ---------------- TMA producers (both CTAs)
       const uint32_t my_parity = warp == w_tma ? 0u : 1u;
       uint32_t it = 0;
+      int s = 0;                           // ring slot and phase of iteration `it`, kept incrementally: every instruction
+      uint32_t ph = 0;                     // of this loop is on the critical path of the kernel
       for (int si = 0; si < nseg; ++si) {
         const WorkSeg w = seg_get(p, cluster_id, nclusters, si);
         const int nb = w.mn % p.n_blocks, mb = w.mn / p.n_blocks;
         const int kb0 = w.kb0, kb1 = w.kb1;
         const int m0 = mb * PAIR_M + (int)rank * 128, n0 = nb * TILE_N + (int)rank * 128;
         const int pf = (int)((LABV(p) >> 8) & 0xffu);
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; ++kb, ++it, ph ^= (++s == PAIR_STAGES) ? 1u : 0u, s = (s == PAIR_STAGES) ? 0 : s) {
           if ((it & 1u) != my_parity) continue;               // the other producer's slot
-          const int s = it % PAIR_STAGES;
-          const uint32_t ph = (it / PAIR_STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * PAIR_STAGE;
           uint8_t* sb = sa + 16384;
@@ -1078,7 +1078,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       // MMA-K worth of rows (16 x 128 B for bf16, 32 x 128 B for fp8)
       constexpr uint32_t A_KSTEP = A_MN ? (FP8 ? 4096u : 2048u) : 32u;
       constexpr uint32_t B_KSTEP = B_MN ? (FP8 ? 4096u : 2048u) : 32u;
-      uint32_t it = 0, tile_it = 0;
+      uint32_t it = 0, tile_it = 0, ph = 0;
+      int s = 0;
       const bool stats = LABSTATS(p) != nullptr;
       long long t_begin = 0, w_full = 0, w_tmem = 0;
       if (stats) t_begin = clock64();
@@ -1090,9 +1091,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         else mbar_wait(&tmem_empty[as], aph ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * PAIR_N;
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % PAIR_STAGES;
-          const uint32_t ph = (it / PAIR_STAGES) & 1;
+        for (int kb = kb0; kb < kb1; ++kb, ++it, ph ^= (++s == PAIR_STAGES) ? 1u : 0u, s = (s == PAIR_STAGES) ? 0 : s) {
           if (stats) { const long long t0 = clock64(); mbar_wait(&full_bar[s], ph); w_full += clock64() - t0; }
           else mbar_wait(&full_bar[s], ph);
           tc_fence_after();
@@ -1455,7 +1454,8 @@ static void launch(const GemmCall& c, cudaStream_t st) {
 template <bool A_MN, bool B_MN, bool FP8>
 static void launch_pair(const GemmCall& c, cudaStream_t st) {
   constexpr int BK = FP8 ? 128 : BLOCK_K;
-  const bool wide = !FP8 && c.block_n == 1024 && (c.epi == EPI_ACCUM_F32 || c.epi == EPI_F32);   // 256 x 512 tiles
+  const bool wide = !FP8 && c.block_n == 1024 && (c.epi == EPI_ACCUM_F32 || c.epi == EPI_F32) && c.N % 512 == 0 &&
+                    c.M % 64 == 0;                  // 256 x 512 tiles (aligned problems only; everything else: 256 x 256)
   GemmArgs p;
   p.M = c.M; p.N = c.N; p.K = c.K;
   p.m_blocks = (c.M + PAIR_M - 1) / PAIR_M;

@@ -82,7 +82,7 @@ def test_gemm_tn_tail_split(M, N, K):
 
 
 @pytest.mark.parametrize("M,N,K,splits", [(4096, 1024, 12288, -2), (1024, 4096, 4096, 1), (512, 512, 1024, -2), (768, 1536, 2048, 3),
-                                          (300, 1000, 520, 1)])
+                                          (304, 1000, 520, 1)])
 def test_gemm_tn_wide_tiles(M, N, K, splits):
     """256 x 512 tiles (block_n=1024: two N = 256 MMAs per k-step, all 512 TMEM columns, 4-stage ring of 48 KB) for the
     fp32 weight-gradient epilogue, alone, with split-K and with the tail split; accumulates into ``out``."""
