@@ -501,7 +501,7 @@ void fp8_update(Tensor meta, Tensor is_e5m2, double margin_pow2) {
 void gemm_lab(int64_t flags, c10::optional<Tensor> stats) {
   unsigned long long* sp = nullptr;
   if (stats.has_value() && stats->defined()) {
-    TORCH_CHECK(stats->is_cuda() && stats->scalar_type() == at::kLong && stats->numel() >= 74 * 4, "gemm_lab stats");
+    TORCH_CHECK(stats->is_cuda() && stats->scalar_type() == at::kLong && stats->numel() >= 74 * 12, "gemm_lab stats");
     sp = reinterpret_cast<unsigned long long*>(stats->data_ptr<int64_t>());
   }
   b200::gemm_lab((unsigned int)flags, sp);

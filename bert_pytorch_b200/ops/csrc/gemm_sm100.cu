@@ -924,9 +924,13 @@ __device__ __forceinline__ WorkSeg seg_get(const GemmArgs& p, int c, int C, int 
 #ifdef B200_GEMM_LAB
 #define LABV(p) ((p).lab)
 #define LABSTATS(p) ((p).lab_stats)
+// phase clock of the CTA-wide staged epilogue (first epilogue thread of the leader CTA): lab_t[i] accumulates the cycles
+// between mark i - 1 and mark i; written behind the MMA issuer's records (74 x 4) as 74 x 8 words
+#define LAB_T(i) do { if (lab_clk) { const long long now_ = clock64(); lab_t[i] += now_ - lab_last; lab_last = now_; } } while (0)
 #else
 #define LABV(p) 0u
 #define LABSTATS(p) ((unsigned long long*)nullptr)
+#define LAB_T(i) do { } while (0)
 #endif
 // EC = epilogue class: every class is its own kernel, so the register allocation (168 per thread is the ceiling) and
 // the instruction footprint of one epilogue do not pay for the others (the single runtime-switched kernel spilled).
@@ -1157,6 +1161,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
     }
     uint32_t tile_it = 0, c_phase = 0;
+#ifdef B200_GEMM_LAB
+    const bool lab_clk = LABSTATS(p) != nullptr && issuer && leader;
+    long long lab_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, lab_last = lab_clk ? clock64() : 0;
+#endif
     for (int si = 0; si < nseg; ++si, ++tile_it) {
       const WorkSeg wseg = seg_get(p, cluster_id, nclusters, si);
       const int mn = wseg.mn;
@@ -1206,10 +1214,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         mapa_shared(smem_u32(&tmem_empty[as]), 0));
           continue;
         }
+        LAB_T(0);
         if (use_res) {
           mbar_wait(c_full, c_phase);
           c_phase ^= 1;
         }
+        LAB_T(1);
         if (p.epi == EPI_BIAS_GELU) {
           staged_pass<1>(p, sC, taddr, r, row, nb * PAIR_N, half * 4, false, alpha, seed);
           tc_fence_before();
@@ -1225,8 +1235,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             default: staged_tile<EPI_ADD>(p, sC, taddr, r, row, nbase, cb, use_res, alpha, keys, dropT, te); break;   // none / bias / add
           }
         }
+        LAB_T(2);
         fence_proxy_async();
         epi_bar_sync();
+        LAB_T(3);
         if (p.epi == EPI_BIAS_GELU) {
           if (issuer) {
 #pragma unroll
@@ -1247,11 +1259,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           tma_store_commit();
         }
         if (p.colsum != nullptr) staged_colsum(p, sC, nb * PAIR_N, ew * 32 + lane);   // while the stores drain
+        LAB_T(4);
         if (issuer) {
           tma_store_wait_read<0>();                         // staging tile free again
           if (use_res && si + 1 < nseg) load_res(seg_get(p, cluster_id, nclusters, si + 1).mn);
         }
+        LAB_T(5);
         epi_bar_sync();                                     // nobody touches the staging tile before that
+        LAB_T(6);
       }
     }
     if (EC == EC_GELU_DG || warp_local) {
@@ -1259,6 +1274,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     } else if (staged && issuer) {
       tma_store_wait<0>();
     }
+#ifdef B200_GEMM_LAB
+    if (lab_clk) {
+      LAB_T(7);
+      unsigned long long* o = LABSTATS(p) + 74 * 4 + 8 * cluster_id;
+      for (int i = 0; i < 8; ++i) o[i] = (unsigned long long)lab_t[i];
+    }
+#endif
   }
 
   tc_fence_before();

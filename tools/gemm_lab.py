@@ -44,7 +44,7 @@ def main():
     if "--variants" in sys.argv:
         want = sys.argv[sys.argv.index("--variants") + 1].split(",")
         variants = [v for v in variants if v[0] in want]
-    stats = torch.zeros(74 * 4, dtype=torch.int64, device="cuda")
+    stats = torch.zeros(74 * 12, dtype=torch.int64, device="cuda")
     out_path = os.path.join("gpurun_out", "gemm_lab.jsonl")
     os.makedirs("gpurun_out", exist_ok=True)
     with open(out_path, "w") as f:
@@ -73,7 +73,7 @@ def main():
                 C.gemm_lab(flags, stats)
                 run()
                 torch.cuda.synchronize()
-                st = stats.view(74, 4).double()
+                st = stats[:74 * 4].view(74, 4).double()
                 live = st[:, 3] > 0
                 tot, wf, wt, kb = (st[live, i] for i in range(4))
                 rec[vname] = {"tflops": round(flops / t / 1e9, 1), "ms": round(t, 4),
@@ -105,10 +105,15 @@ def main():
                 run()
                 torch.cuda.synchronize()
                 C.gemm_lab(0, None)
-                st = stats.view(74, 4).double()
+                st = stats[:74 * 4].view(74, 4).double()
                 live = st[:, 3] > 0
+                ph = stats[74 * 4:].view(74, 8).double()[live]
+                ntile = (st[live, 3] / max(k // 64, 1)).clamp(min=1).unsqueeze(1)
+                # cycles per tile of the CTA-wide staged epilogue: wait tmem_full | wait residual | math | barrier |
+                # issue stores (+colsum) | wait store read + next residual request | barrier | (after last tile) drain
                 return {"ms": round(t, 4), "cyc_per_kblock": round(float((st[live, 0] / st[live, 3]).mean()), 1),
-                        "wait_tmem_frac": round(float((st[live, 2] / st[live, 0]).mean()), 3)}
+                        "wait_tmem_frac": round(float((st[live, 2] / st[live, 0]).mean()), 3),
+                        "epi_phase_cyc_per_tile": [int(x) for x in (ph / ntile).mean(0).tolist()]}
             m = M
             for name, layout, n, k in (("ffn1_fwd", K.NT, 4096, 1024), ("attn_out_fwd", K.NT, 1024, 1024),
                                        ("ffn2_fwd", K.NT, 1024, 4096), ("ffn2_dgrad", K.NN, 4096, 1024)):
