@@ -359,12 +359,14 @@ class FusedEncoderEngine:
         # not have to run Philox again (60 of its 290 instructions per 8 elements) -- CTA-pair kernel, bf16 path only
         keep_bits = (save and ph > 0 and not self.fp8 and H % 128 == 0 and K.pick_block_n(M, H) == 512
                      and os.environ.get("B200_DROP_MASK", "1") != "0")
-        mask1 = torch.empty(M, H // 8, dtype=torch.uint8, device=x.device) if keep_bits else None
-        mask2 = torch.empty(M, H // 8, dtype=torch.uint8, device=x.device) if keep_bits else None
+        # ... and are GENERATED by their own kernel (K.dropout_mask: every warp of the machine on Philox) rather than by
+        # the two epilogue warps per SMSP of the GEMM: 9.6 k of the 13.6 k cycles per tile of that epilogue were Philox
+        mask1 = K.dropout_mask(M, H, ph, seed, _stream(l, SITE_ATTN_OUT), x.device) if keep_bits else None
+        mask2 = K.dropout_mask(M, H, ph, seed, _stream(l, SITE_FFN_OUT), x.device) if keep_bits else None
         pre1, ctx_op = self._lin(l, "ctx", "wo", ctx, self.w(pre + "attention.output.dense.weight"), xq=ctx_q,
                                  epi=K.EPI_BIAS_DROP_RES, bias=self.w(pre + "attention.output.dense.bias"), res=x,
                                  p_drop=ph, seed=seed, stream=_stream(l, SITE_ATTN_OUT),
-                                 **({"mask_out": mask1} if keep_bits else {}))
+                                 **({"mask_in": mask1} if keep_bits else {}))
         # producers emit the fp8 copy of their output for the next GEMM (no separate quantise pass)
         x1, mean1, rstd1, *q = K.layer_norm_fwd(pre1, self.p(pre + "attention.output.LayerNorm.weight"),
                                                 self.p(pre + "attention.output.LayerNorm.bias"), save_stats=save,
@@ -384,7 +386,7 @@ class FusedEncoderEngine:
             act, *q = K.gelu_fwd(y1, fp8=side) if side else (K.gelu_fwd(y1),)
         pre2, act_op = self._lin(l, "act", "w2", act, self.w(pre + "output.dense.weight"), xq=q[0] if q else None,
                                  epi=K.EPI_BIAS_DROP_RES, bias=self.w(pre + "output.dense.bias"), res=x1, p_drop=ph,
-                                 seed=seed, stream=_stream(l, SITE_FFN_OUT), **({"mask_out": mask2} if keep_bits else {}))
+                                 seed=seed, stream=_stream(l, SITE_FFN_OUT), **({"mask_in": mask2} if keep_bits else {}))
         x2, mean2, rstd2, *q = K.layer_norm_fwd(pre2, self.p(pre + "output.LayerNorm.weight"),
                                                 self.p(pre + "output.LayerNorm.bias"), save_stats=save,
                                                 fp8=self._side(f"{l + 1}.x") if l + 1 < self.L else None)

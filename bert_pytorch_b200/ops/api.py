@@ -65,7 +65,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, layout: int = NT, epi: int = EPI_N
          block_n: Optional[int] = None, alpha: float = 1.0, p_drop: float = 0.0, seed: int = 0,
          stream: int = 0, scale_a: Optional[torch.Tensor] = None, scale_b: Optional[torch.Tensor] = None,
          a_e5m2: bool = False, b_e5m2: bool = False, push: bool = False,
-         colsum: Optional[torch.Tensor] = None, mask_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+         colsum: Optional[torch.Tensor] = None, mask_out: Optional[torch.Tensor] = None,
+         mask_in: Optional[torch.Tensor] = None) -> torch.Tensor:
     """tcgen05 GEMM with a fused epilogue (see csrc/gemm_sm100.cu).  ``a``/``b`` are 2-D bf16, or -- with
     ``scale_a``/``scale_b`` (device inv-scale scalars from an :class:`Fp8Meta`) -- 1-byte fp8 tensors.
     ``colsum`` (fp32 [N], EPI_NONE / EPI_ADD / EPI_MUL): accumulates the column sums of the bf16 output (a bias
@@ -86,7 +87,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, layout: int = NT, epi: int = EPI_N
     elif block_n is None:
         block_n = _pick_block_n(M, N)
     extension().gemm(a, b, out, layout, epi, bias, res, aux_out, k_splits, block_n, alpha, p_drop, seed, stream,
-                     scale_a, scale_b, a_e5m2, b_e5m2, push, colsum, mask_out)
+                     scale_a, scale_b, a_e5m2, b_e5m2, push, colsum, mask_out, mask_in)
     _count()
     return out
 
@@ -262,6 +263,17 @@ def _ln_workspace(M: int, H: int, device: torch.device) -> torch.Tensor:
 
 
 NO_STREAM = 0xFFFFFFFF
+
+
+def dropout_mask(M: int, N: int, p_drop: float, seed: int, stream: int, device) -> torch.Tensor:
+    """uint8 [M, N / 8] keep bits of the dropout stream ``(seed, stream)`` over an [M, N] tensor -- the decisions the
+    kernels would draw themselves.  Feed it to ``gemm(..., mask_in=)`` (EPI_BIAS_DROP_RES) and to
+    ``layer_norm_bwd(..., keep_mask=)``: Philox then runs once per element, in a kernel that keeps the whole machine
+    busy, instead of in the latency-bound GEMM epilogue and again in the LayerNorm backward."""
+    out = torch.empty(M, N // 8, dtype=torch.uint8, device=device)
+    extension().dropout_mask(out, p_drop, seed, stream)
+    _count()
+    return out
 
 
 def layer_norm_bwd(dy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor, gamma: torch.Tensor, *,

@@ -79,7 +79,8 @@ static inline bool p_drop_is_zero(double p) { return !(p > 0.0); }
 void gemm(Tensor a, Tensor b, Tensor out, int64_t layout, int64_t epi, c10::optional<Tensor> bias,
           c10::optional<Tensor> res, c10::optional<Tensor> aux_out, int64_t k_splits, int64_t block_n, double alpha,
           double p_drop, int64_t seed, int64_t stream_id, c10::optional<Tensor> scale_a, c10::optional<Tensor> scale_b,
-          bool a_e5m2, bool b_e5m2, bool allow_push, c10::optional<Tensor> colsum, c10::optional<Tensor> mask_out) {
+          bool a_e5m2, bool b_e5m2, bool allow_push, c10::optional<Tensor> colsum, c10::optional<Tensor> mask_out,
+          c10::optional<Tensor> mask_in) {
   const bool fp8 = scale_a.has_value() && scale_a->defined();
   if (fp8) {
     TORCH_CHECK(a.is_cuda() && b.is_cuda() && a.element_size() == 1 && b.element_size() == 1 && a.stride(1) == 1 &&
@@ -151,6 +152,13 @@ void gemm(Tensor a, Tensor b, Tensor out, int64_t layout, int64_t epi, c10::opti
                 mask_out->numel() == M * (N / 8) && reinterpret_cast<uintptr_t>(mask_out->data_ptr()) % 16 == 0 && N % 128 == 0,
                 "mask_out: uint8 [M, N / 8], 16-byte aligned, N % 128 == 0");
     c.mask_out = mask_out->data_ptr<uint8_t>();
+  }
+  if (mask_in.has_value() && mask_in->defined()) {
+    TORCH_CHECK(epi == b200::EPI_BIAS_DROP_RES && block_n == 512 && !p_drop_is_zero(p_drop), "mask_in: dropout epilogue of the CTA-pair kernel only");
+    TORCH_CHECK(mask_in->is_cuda() && mask_in->scalar_type() == at::kByte && mask_in->is_contiguous() &&
+                mask_in->numel() == M * (N / 8) && reinterpret_cast<uintptr_t>(mask_in->data_ptr()) % 16 == 0 && N % 128 == 0,
+                "mask_in: uint8 [M, N / 8], 16-byte aligned, N % 128 == 0");
+    c.mask_in = mask_in->data_ptr<uint8_t>();
   }
   c.k_splits = (int)k_splits;
   c.alpha = (float)alpha;
@@ -507,9 +515,18 @@ void gemm_lab(int64_t flags, c10::optional<Tensor> stats) {
   b200::gemm_lab((unsigned int)flags, sp);
 }
 
+// keep bits of the dropout stream (seed, stream) for a [.., N] tensor of `out.numel() * 8` elements (see dropout_mask_kernel)
+void dropout_mask(Tensor out, double p_drop, int64_t seed, int64_t stream_id) {
+  TORCH_CHECK(out.is_cuda() && out.scalar_type() == at::kByte && out.is_contiguous() && out.numel() % 4 == 0 &&
+              reinterpret_cast<uintptr_t>(out.data_ptr()) % 16 == 0, "dropout_mask: uint8, contiguous, numel % 4 == 0");
+  c10::cuda::CUDAGuard guard(out.device());
+  b200::dropout_mask(out.data_ptr(), out.numel() * 8, mk_seed(seed), (unsigned)stream_id, (float)p_drop, cur_stream());
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.def("dropout_mask", &dropout_mask);
   m.def("gemm_lab", &gemm_lab);
   m.doc() = "bert_pytorch_b200 sm_100a kernels";
   m.def("gemm", &gemm);

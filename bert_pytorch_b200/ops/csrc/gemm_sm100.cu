@@ -60,6 +60,7 @@ struct GemmArgs {
   int ldr;
   float* colsum;             // optional fp32 column sums of the bf16 output (bias gradients)
   unsigned char* mask_out;   // optional dropout keep bits, [M][N / 8] bytes (GemmCall::mask_out)
+  const unsigned char* mask_in;   // the same bits as input: applied instead of generated (GemmCall::mask_in)
   int warp_epi;              // pair kernel: warp-local staged epilogue (default) instead of the CTA-wide staging tile
   Seed seed;
   unsigned int stream;
@@ -535,7 +536,12 @@ __device__ __forceinline__ void staged_tile(const GemmArgs& p, uint8_t* sC, uint
   const f32x2 alpha2 = f2_splat(alpha);
   const bool has_bias = p.bias != nullptr;
   const bool drop = EPI == EPI_BIAS_DROP_RES && dropT != 0;
-  uint32_t mbits[4] = {0u, 0u, 0u, 0u};      // keep bits of this thread's 128 columns (mask_out)
+  uint32_t mbits[4] = {0u, 0u, 0u, 0u};      // keep bits of this thread's 128 columns (mask_out / mask_in)
+  const bool bits_in = EPI == EPI_BIAS_DROP_RES && drop && p.mask_in != nullptr;
+  if (bits_in && row < p.M && n_w0 + 128 <= p.N) {                     // 16 bytes = this thread's 128 columns
+    const uint4 mw = __ldg(reinterpret_cast<const uint4*>(p.mask_in + (size_t)row * (size_t)(p.N >> 3) + (size_t)(n_w0 >> 3)));
+    mbits[0] = mw.x; mbits[1] = mw.y; mbits[2] = mw.z; mbits[3] = mw.w;
+  }
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     if (c >= nch) break;
@@ -566,7 +572,12 @@ __device__ __forceinline__ void staged_tile(const GemmArgs& p, uint8_t* sC, uint
         }
       }
       if constexpr (EPI == EPI_BIAS_DROP_RES) {
-        if (drop) {
+        if (bits_in) {
+          const uint32_t kb = (mbits[c] >> (g * 8)) & 0xffu;
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            x[t] = f2_mul(x[t], f2_pack((kb >> (2 * t)) & 1u ? p.drop_scale : 0.f, (kb >> (2 * t + 1)) & 1u ? p.drop_scale : 0.f));
+        } else if (drop) {
           const uint64_t e8 = ((uint64_t)row * (uint64_t)p.N + (uint64_t)(nn + g * 8)) >> 3;
           const uint4 rnd = philox7(keys, e8, p.stream);
           uint32_t kb = 0;
@@ -598,7 +609,7 @@ __device__ __forceinline__ void staged_tile(const GemmArgs& p, uint8_t* sC, uint
     }
   }
   if (nch == 0) { tc_fence_before(); mbar_arrive_cluster(tmem_empty_addr); }
-  if (drop && p.mask_out != nullptr && row < p.M && n_w0 < p.N) {      // 16 bytes = this thread's 128 columns
+  if (drop && !bits_in && p.mask_out != nullptr && row < p.M && n_w0 < p.N) {      // 16 bytes = this thread's 128 columns
     unsigned char* dst = p.mask_out + (size_t)row * (size_t)(p.N >> 3) + (size_t)(n_w0 >> 3);
     if (n_w0 + 128 <= p.N) *reinterpret_cast<uint4*>(dst) = make_uint4(mbits[0], mbits[1], mbits[2], mbits[3]);
     else {
@@ -1447,7 +1458,7 @@ static void launch(const GemmCall& c, cudaStream_t st) {
   p.out = c.out; p.ldo = c.ldo; p.aux_out = reinterpret_cast<__nv_bfloat16*>(c.aux_out);
   p.bias = reinterpret_cast<const __nv_bfloat16*>(c.bias);
   p.res = reinterpret_cast<const __nv_bfloat16*>(c.res); p.ldr = c.ldr;
-  p.colsum = c.colsum; p.mask_out = nullptr;
+  p.colsum = c.colsum; p.mask_out = nullptr; p.mask_in = nullptr;
   p.seed = Seed{c.seed, c.seed_step}; p.stream = c.stream;
   float pd = c.p_drop;
   p.drop_thresh16 = pd > 0.f ? (unsigned)(pd * 65536.f + 0.5f) : 0u;
@@ -1491,7 +1502,7 @@ static void launch_pair(const GemmCall& c, cudaStream_t st) {
   p.out = c.out; p.ldo = c.ldo; p.aux_out = reinterpret_cast<__nv_bfloat16*>(c.aux_out);
   p.bias = reinterpret_cast<const __nv_bfloat16*>(c.bias);
   p.res = reinterpret_cast<const __nv_bfloat16*>(c.res); p.ldr = c.ldr;
-  p.colsum = c.colsum; p.mask_out = c.mask_out;
+  p.colsum = c.colsum; p.mask_out = c.mask_out; p.mask_in = c.mask_in;
   p.seed = Seed{c.seed, c.seed_step}; p.stream = c.stream;
   float pd = c.p_drop;
   p.drop_thresh16 = pd > 0.f ? (unsigned)(pd * 65536.f + 0.5f) : 0u;

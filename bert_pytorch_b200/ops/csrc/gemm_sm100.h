@@ -41,6 +41,8 @@ struct GemmCall {
   // optional (EPI_BIAS_DROP_RES on the CTA-pair kernel): keep decisions of the dropout, one byte per 8 output columns
   // ([M][N / 8], bit t = column 8 j + t kept) -- the LayerNorm backward reads them back instead of re-running Philox
   unsigned char* mask_out = nullptr;
+  // the same bits as INPUT (written beforehand by dropout_mask()): the epilogue applies them instead of running Philox
+  const unsigned char* mask_in = nullptr;
   float* colsum = nullptr;   // optional (bf16 epilogues): colsum[n] += sum_m out[m][n]  (bias gradients, fp32 atomics)
   int k_splits = 1;
   unsigned long long seed = 0; unsigned int stream = 0; float p_drop = 0.f;

@@ -16,6 +16,8 @@ void layer_norm_bwd(const void* dy, const void* x, const float* mean, const floa
                     cudaStream_t st, const uint8_t* keep_mask = nullptr);
 void gelu_fwd(const void* x, void* y, long long n, Fp8Out f8, cudaStream_t st);
 void dgelu_bwd(const void* dy, const void* x, void* dx, float* dbias, int M, int N, Fp8Out f8, cudaStream_t st);
+// keep bits ([n_elems / 8] bytes, n_elems % 32 == 0) of the dropout stream (seed, stream): see dropout_mask_kernel
+void dropout_mask(void* out, long long n_elems, Seed seed, unsigned int stream, float p_drop, cudaStream_t st);
 void colsum_bf16(const void* x, int M, int N, int ld, float* out, cudaStream_t st);
 void embedding_fwd(const int* ids, const int* seg, const void* word, const void* pos, const void* type,
                    const float* gamma, const float* beta, void* e_out, void* y, float* mean, float* rstd, int M, int S,

@@ -1069,6 +1069,37 @@ void layer_norm_bwd(const void* dy, const void* x, const float* mean, const floa
   launch_pdl(colsum_finalize_kernel, g2, dim3(256), 0, st, (const float*)workspace, grid, H, dgamma, dbeta, dxd ? dbias : (float*)nullptr);
 }
 
+// Keep bits of one hidden-dropout site, one byte per 8 elements ([M][N / 8], bit t of byte j = element 8 j + t kept):
+// the same decisions as dropout_keep8(seed, stream, e8) with e8 = (row * N + col) / 8.  Generated here, with every warp
+// of the machine busy, instead of inside the GEMM epilogue that applies them (two epilogue warps per SMSP: the Philox
+// rounds were 9.6 k of the 13.6 k cycles the dropout + residual epilogue spent per tile -- gemm_lab phase clock -- against
+// 8.2 k cycles of MMAs per K = 1024 tile) and instead of being regenerated by the LayerNorm backward.
+__global__ void __launch_bounds__(256) dropout_mask_kernel(unsigned int* __restrict__ out, long long n_words, Seed seed_in,
+                                                           unsigned int stream, unsigned int thresh16) {
+  pdl_trigger();
+  const PhiloxKeys keys = philox_keys(seed_in.value());
+  const uint32_t T = thresh16 << 16;
+  for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += (long long)gridDim.x * blockDim.x) {
+    uint32_t bits = 0;                        // 32 elements = 4 groups of 8
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const uint4 r = philox7(keys, (uint64_t)(w * 4 + g), stream);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) bits |= (keep_bit(r, t, T) ? 1u : 0u) << (g * 8 + t);
+    }
+    out[w] = bits;
+  }
+}
+
+void dropout_mask(void* out, long long n_elems, Seed seed, unsigned int stream, float p_drop, cudaStream_t st) {
+  unsigned int th; float sc;
+  drop_params(p_drop, th, sc);
+  const long long n_words = n_elems / 32;
+  long long g = (n_words + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  if (g > 0) launch_pdl(dropout_mask_kernel, dim3((unsigned)g), dim3(256), 0, st, (unsigned int*)out, n_words, seed, stream, th);
+}
+
 void colsum_bf16(const void* x, int M, int N, int ld, float* out, cudaStream_t st) {
   dim3 grid((N + 255) / 256, M >= 4096 ? 64 : (M >= 512 ? 16 : 1));
   launch_pdl(colsum_bf16_kernel, grid, dim3(256), 0, st, (const __nv_bfloat16*)x, M, N, ld, out);

@@ -74,6 +74,11 @@ def test_dropout_keep_bits_leave_the_gemm_and_feed_layer_norm_backward():
                  mask_out=mask)
     ref = K.gemm(a, w, epi=K.EPI_BIAS_DROP_RES, bias=zeros_b, res=res, p_drop=0.1, seed=77, stream=19, block_n=512)
     assert torch.equal(fwd, ref)                                          # writing the bits does not change the output
+    # the same bits from the stand-alone generator (K.dropout_mask), and the epilogue applying them instead of Philox
+    gen = K.dropout_mask(M, H, 0.1, 77, 19, "cuda")
+    assert torch.equal(gen, mask)
+    via = K.gemm(a, w, epi=K.EPI_BIAS_DROP_RES, bias=zeros_b, res=res, p_drop=0.1, seed=77, stream=19, block_n=512, mask_in=gen)
+    assert torch.equal(via, ref)
     bits = ((mask.view(M, H // 8, 1) >> torch.arange(8, device="cuda", dtype=torch.uint8).view(1, 1, 8)) & 1).view(M, H).bool()
     assert abs(1.0 - bits.float().mean().item() - 0.1) < 0.01
     assert ((fwd != 0) ^ bits).float().mean().item() < 1e-3               # exact zeros of the product are the only mismatches
