@@ -418,6 +418,9 @@ __device__ __forceinline__ uint32_t cstage_offset(int r, int col) {   // col mul
   const int sub = col >> 6, ck = (col & 63) >> 3;
   return (uint32_t)(sub * 16384 + r * 128 + ((ck ^ (r & 7)) << 4));
 }
+__device__ __forceinline__ void half_bar_sync(int half) {    // the four epilogue warps of one column half (barriers 2, 3)
+  asm volatile("bar.sync %0, 128;" ::"r"(half + 2) : "memory");
+}
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
 
 // pass over this warp's 4 chunks; MODE 0: acc (+bias) (+dropout) (+res | *dgelu(res) | tanh) -> staging
@@ -530,20 +533,24 @@ __device__ __forceinline__ void staged_pass(const GemmArgs& p, uint8_t* sC, uint
 template <int EPI>
 __device__ __forceinline__ void staged_tile(const GemmArgs& p, uint8_t* sC, uint32_t taddr, int r, int row, int n_base,
                                             int col_begin, bool use_res, float alpha, const PhiloxKeys& keys, uint32_t dropT,
-                                            uint32_t tmem_empty_addr) {
+                                            uint32_t tmem_empty_addr, int c_lo = 0, int c_hi = 4, uint32_t* mbits_io = nullptr) {
+  // chunks [c_lo, c_hi) of this warp's four 32-column chunks (the box-pipelined epilogue calls it once per 64-column
+  // box); the accumulator is released after the read of chunk 3 (or of the last live chunk)
   const int n_w0 = n_base + col_begin;
   const int nch = n_w0 >= p.N ? 0 : min(4, (p.N - n_w0 + 31) >> 5);   // live 32-column chunks (warp uniform)
   const f32x2 alpha2 = f2_splat(alpha);
   const bool has_bias = p.bias != nullptr;
   const bool drop = EPI == EPI_BIAS_DROP_RES && dropT != 0;
-  uint32_t mbits[4] = {0u, 0u, 0u, 0u};      // keep bits of this thread's 128 columns (mask_out / mask_in)
+  uint32_t mlocal[4] = {0u, 0u, 0u, 0u};
+  uint32_t* mbits = mbits_io != nullptr ? mbits_io : mlocal;   // keep bits of this thread's 128 columns (mask_out / mask_in)
   const bool bits_in = EPI == EPI_BIAS_DROP_RES && drop && p.mask_in != nullptr;
-  if (bits_in && row < p.M && n_w0 + 128 <= p.N) {                     // 16 bytes = this thread's 128 columns
+  if (bits_in && c_lo == 0 && row < p.M && n_w0 + 128 <= p.N) {       // 16 bytes = this thread's 128 columns
     const uint4 mw = __ldg(reinterpret_cast<const uint4*>(p.mask_in + (size_t)row * (size_t)(p.N >> 3) + (size_t)(n_w0 >> 3)));
     mbits[0] = mw.x; mbits[1] = mw.y; mbits[2] = mw.z; mbits[3] = mw.w;
   }
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
+    if (c < c_lo || c >= c_hi) continue;
     if (c >= nch) break;
     const int col0 = col_begin + c * 32, nn = n_base + col0;
     uint4 bq[4];
@@ -608,14 +615,33 @@ __device__ __forceinline__ void staged_tile(const GemmArgs& p, uint8_t* sC, uint
                    "r"(f2_to_bf16x2(x[2])), "r"(f2_to_bf16x2(x[3])) : "memory");
     }
   }
-  if (nch == 0) { tc_fence_before(); mbar_arrive_cluster(tmem_empty_addr); }
-  if (drop && !bits_in && p.mask_out != nullptr && row < p.M && n_w0 < p.N) {      // 16 bytes = this thread's 128 columns
+  if (nch == 0 && c_lo == 0) { tc_fence_before(); mbar_arrive_cluster(tmem_empty_addr); }
+  if (c_hi == 4 && drop && !bits_in && p.mask_out != nullptr && row < p.M && n_w0 < p.N) {      // 16 bytes = this thread's 128 columns
     unsigned char* dst = p.mask_out + (size_t)row * (size_t)(p.N >> 3) + (size_t)(n_w0 >> 3);
     if (n_w0 + 128 <= p.N) *reinterpret_cast<uint4*>(dst) = make_uint4(mbits[0], mbits[1], mbits[2], mbits[3]);
     else {
       for (int j = 0; j < (p.N - n_w0) >> 3; ++j) dst[j] = (unsigned char)(mbits[j >> 2] >> ((j & 3) * 8));
     }
   }
+}
+
+// Column sums of one finished [128 rows x 64 columns] box of the staging tile by the 128 threads of its half: thread t
+// owns the column pair (t & 31) over the row quarter (t >> 5).
+__device__ __forceinline__ void staged_colsum_box(const GemmArgs& p, const uint8_t* box, int n_box, int t) {
+  const int col = (t & 31) * 2, rq = t >> 5;
+  const int n = n_box + col;
+  if (n >= p.N) return;
+  const uint32_t off = (uint32_t)((col & 7) * 2);
+  const int ck = col >> 3;
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+  for (int r = rq * 32; r < rq * 32 + 32; ++r) {
+    const float2 f = unpack_bf16(*reinterpret_cast<const uint32_t*>(box + r * 128 + ((ck ^ (r & 7)) << 4) + off));
+    s0 += f.x;
+    s1 += f.y;
+  }
+  atomicAdd(p.colsum + n, s0);
+  atomicAdd(p.colsum + n + 1, s1);
 }
 
 // Column sums of the finished bf16 tile in the staging buffer (bias gradients fused into a dgrad GEMM): thread t
@@ -1167,11 +1193,20 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           warp_epi_request_res(p, &tmap_res, we, mn0, (int)rank, 0);
           warp_epi_request_res(p, &tmap_res, we, mn0, (int)rank, 1);
         }
-      } else if (use_res && issuer && nseg > 0) {
-        load_res(seg_get(p, cluster_id, nclusters, 0).mn);
+      } else if (use_res && nseg > 0 && lane == 0 && (ew & 3) == 0) {   // the elected thread of each half: its two boxes
+        const int mn0 = seg_get(p, cluster_id, nclusters, 0).mn;
+        const int nb0 = mn0 % p.n_blocks, row00 = (mn0 / p.n_blocks) * PAIR_M + (int)rank * 128;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const int box = half * 2 + b, n_box = nb0 * PAIR_N + box * 64;
+          if (n_box < p.N) {
+            mbar_arrive_expect_tx(&res_bar[box], 16384);
+            tma_load_2d(sC + box * 16384, &tmap_res, &res_bar[box], n_box, row00);
+          }
+        }
       }
     }
-    uint32_t tile_it = 0, c_phase = 0;
+    uint32_t tile_it = 0, res_phase = 0;
 #ifdef B200_GEMM_LAB
     const bool lab_clk = LABSTATS(p) != nullptr && issuer && leader;
     long long lab_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, lab_last = lab_clk ? clock64() : 0;
@@ -1225,44 +1260,88 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         mapa_shared(smem_u32(&tmem_empty[as]), 0));
           continue;
         }
-        LAB_T(0);
-        if (use_res) {
-          mbar_wait(c_full, c_phase);
-          c_phase ^= 1;
-        }
-        LAB_T(1);
-        if (p.epi == EPI_BIAS_GELU) {
-          staged_pass<1>(p, sC, taddr, r, row, nb * PAIR_N, half * 4, false, alpha, seed);
-          tc_fence_before();
-          mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), 0));   // accumulator drained: MMA may reuse it
-        } else {                                  // staged_tile releases the accumulator itself
+        if (p.epi != EPI_BIAS_GELU) {
+          // ---- box-pipelined epilogue (default).  The staging tile is four [128 x 64] boxes; the four warps of a column
+          // half own two of them and work through them one after the other: residual box landed -> combine in place ->
+          // half barrier -> TMA store.  The store of box 0 drains, and the residual of the NEXT tile's box 0 streams in,
+          // while box 1 is being worked on -- the CTA-wide version (round 2a) waited 2.0 k cycles per tile for the store
+          // to read the tile and only then asked for the next residual (gemm_lab phase clock): K = 1024 GEMMs with
+          // three tiles per cluster ran at first main loop + 3 x epilogue.
           const uint32_t te = mapa_shared(smem_u32(&tmem_empty[as]), 0);
           const int nbase = nb * PAIR_N, cb = half * 128;
-          switch (p.epi) {
-            case EPI_BIAS_DROP_RES: staged_tile<EPI_BIAS_DROP_RES>(p, sC, taddr, r, row, nbase, cb, use_res, alpha, keys, dropT, te); break;
-            case EPI_MUL: staged_tile<EPI_MUL>(p, sC, taddr, r, row, nbase, cb, use_res, alpha, keys, dropT, te); break;
-            case EPI_DGELU: staged_tile<EPI_DGELU>(p, sC, taddr, r, row, nbase, cb, use_res, alpha, keys, dropT, te); break;
-            case EPI_BIAS_TANH: staged_tile<EPI_BIAS_TANH>(p, sC, taddr, r, row, nbase, cb, use_res, alpha, keys, dropT, te); break;
-            default: staged_tile<EPI_ADD>(p, sC, taddr, r, row, nbase, cb, use_res, alpha, keys, dropT, te); break;   // none / bias / add
+          const bool elected = (ew & 3) == 0 && lane == 0;             // first thread of this half
+          const int tq = (ew & 3) * 32 + lane;                         // thread index inside the half
+          uint32_t mbits[4] = {0u, 0u, 0u, 0u};
+#pragma unroll 1
+          for (int b = 0; b < 2; ++b) {
+            const int box = half * 2 + b;
+            const int n_box = nbase + box * 64;
+            const bool live = n_box < p.N;                             // uniform over the half
+            LAB_T(0);
+            if (use_res) {
+              if (live) mbar_wait(&res_bar[box], res_phase);
+            } else {
+              half_bar_sync(half);                                     // the elected thread has seen this box's previous store read it
+            }
+            LAB_T(1);
+            switch (p.epi) {
+              case EPI_BIAS_DROP_RES: staged_tile<EPI_BIAS_DROP_RES>(p, sC, taddr, r, row, nbase, cb, use_res, alpha, keys, dropT, te, 2 * b, 2 * b + 2, mbits); break;
+              case EPI_MUL: staged_tile<EPI_MUL>(p, sC, taddr, r, row, nbase, cb, use_res, alpha, keys, dropT, te, 2 * b, 2 * b + 2, mbits); break;
+              case EPI_DGELU: staged_tile<EPI_DGELU>(p, sC, taddr, r, row, nbase, cb, use_res, alpha, keys, dropT, te, 2 * b, 2 * b + 2, mbits); break;
+              case EPI_BIAS_TANH: staged_tile<EPI_BIAS_TANH>(p, sC, taddr, r, row, nbase, cb, use_res, alpha, keys, dropT, te, 2 * b, 2 * b + 2, mbits); break;
+              default: staged_tile<EPI_ADD>(p, sC, taddr, r, row, nbase, cb, use_res, alpha, keys, dropT, te, 2 * b, 2 * b + 2, mbits); break;
+            }
+            LAB_T(2);
+            fence_proxy_async();
+            half_bar_sync(half);                                       // the box is complete
+            LAB_T(3);
+            if (elected && live) {
+              tma_store_2d(&tmap_out, sC + box * 16384, n_box, row0);
+              tma_store_commit();
+            }
+            if (p.colsum != nullptr && live) staged_colsum_box(p, sC + box * 16384, n_box, tq);   // while the store drains
           }
+          LAB_T(4);
+          res_phase ^= 1;
+          if (elected) {                                               // boxes free again -> next tile's residual boxes
+            const bool more = use_res && si + 1 < nseg;
+            int nnb = 0, nrow0 = 0;
+            if (more) {
+              const int nmn = seg_get(p, cluster_id, nclusters, si + 1).mn;
+              nnb = nmn % p.n_blocks;
+              nrow0 = (nmn / p.n_blocks) * PAIR_M + (int)rank * 128;
+            }
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+              // box 0's store is the older of two bulk groups only if box 1 was stored too
+              if (b == 0 && nbase + (half * 2 + 1) * 64 < p.N) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+              const int box = half * 2 + b, n_box = nnb * PAIR_N + box * 64;
+              if (more && n_box < p.N) {
+                mbar_arrive_expect_tx(&res_bar[box], 16384);
+                tma_load_2d(sC + box * 16384, &tmap_res, &res_bar[box], n_box, nrow0);
+              }
+            }
+          }
+          LAB_T(5);
+          continue;
         }
-        LAB_T(2);
+        // ---- legacy two-pass EPI_BIAS_GELU (B200_FUSED_GELU=0): CTA-wide staging
+        staged_pass<1>(p, sC, taddr, r, row, nb * PAIR_N, half * 4, false, alpha, seed);
+        tc_fence_before();
+        mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), 0));   // accumulator drained: MMA may reuse it
         fence_proxy_async();
         epi_bar_sync();
-        LAB_T(3);
-        if (p.epi == EPI_BIAS_GELU) {
-          if (issuer) {
+        if (issuer) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (nb * PAIR_N + j * 64 < p.N) tma_store_2d(&tmap_aux, sC + j * 16384, nb * PAIR_N + j * 64, row0);
-            tma_store_commit();
-            tma_store_wait_read<0>();
-          }
-          epi_bar_sync();
-          staged_pass<2>(p, sC, taddr, r, row, nb * PAIR_N, half * 4, false, alpha, seed);
-          fence_proxy_async();
-          epi_bar_sync();
+          for (int j = 0; j < 4; ++j)
+            if (nb * PAIR_N + j * 64 < p.N) tma_store_2d(&tmap_aux, sC + j * 16384, nb * PAIR_N + j * 64, row0);
+          tma_store_commit();
+          tma_store_wait_read<0>();
         }
+        epi_bar_sync();
+        staged_pass<2>(p, sC, taddr, r, row, nb * PAIR_N, half * 4, false, alpha, seed);
+        fence_proxy_async();
+        epi_bar_sync();
         if (issuer) {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -1270,19 +1349,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           tma_store_commit();
         }
         if (p.colsum != nullptr) staged_colsum(p, sC, nb * PAIR_N, ew * 32 + lane);   // while the stores drain
-        LAB_T(4);
-        if (issuer) {
-          tma_store_wait_read<0>();                         // staging tile free again
-          if (use_res && si + 1 < nseg) load_res(seg_get(p, cluster_id, nclusters, si + 1).mn);
-        }
-        LAB_T(5);
-        epi_bar_sync();                                     // nobody touches the staging tile before that
-        LAB_T(6);
+        if (issuer) tma_store_wait_read<0>();                 // staging tile free again
+        epi_bar_sync();                                       // nobody touches the staging tile before that
       }
     }
     if (EC == EC_GELU_DG || warp_local) {
       if (lane == 0) tma_store_wait<0>();
-    } else if (staged && issuer) {
+    } else if (staged && lane == 0 && (ew & 3) == 0) {       // the elected thread of each half (ew == 0: also the legacy issuer)
       tma_store_wait<0>();
     }
 #ifdef B200_GEMM_LAB

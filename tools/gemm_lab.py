@@ -109,8 +109,8 @@ def main():
                 live = st[:, 3] > 0
                 ph = stats[74 * 4:].view(74, 8).double()[live]
                 ntile = (st[live, 3] / max(k // 64, 1)).clamp(min=1).unsqueeze(1)
-                # cycles per tile of the CTA-wide staged epilogue: wait tmem_full | wait residual | math | barrier |
-                # issue stores (+colsum) | wait store read + next residual request | barrier | (after last tile) drain
+                # cycles per tile of the box-pipelined epilogue (first thread of half 0, both boxes summed): wait tmem_full |
+                # wait residual / box free | math | half barrier | store (+colsum) | wait store read + next residual | - | drain
                 return {"ms": round(t, 4), "cyc_per_kblock": round(float((st[live, 0] / st[live, 3]).mean()), 1),
                         "wait_tmem_frac": round(float((st[live, 2] / st[live, 0]).mean()), 3),
                         "epi_phase_cyc_per_tile": [int(x) for x in (ph / ntile).mean(0).tolist()]}
@@ -140,6 +140,11 @@ def main():
                 else:
                     rec["bias_drop_res"] = measure(lambda: K.gemm(a, b, layout=layout, out=o, epi=K.EPI_BIAS_DROP_RES, bias=bias,
                                                                   res=res, p_drop=0.1, seed=1234, block_n=512))
+                    bits = K.dropout_mask(m, n, 0.1, 1234, 0, "cuda")
+                    rec["bias_drop_res_maskin"] = measure(lambda: K.gemm(a, b, layout=layout, out=o, epi=K.EPI_BIAS_DROP_RES,
+                                                                         bias=bias, res=res, p_drop=0.1, seed=1234, block_n=512,
+                                                                         mask_in=bits))
+                    rec["add_res"] = measure(lambda: K.gemm(a, b, layout=layout, out=o, epi=K.EPI_ADD, res=res, block_n=512))
                 print(json.dumps(rec), flush=True)
                 f.write(json.dumps(rec) + "\n")
 
