@@ -18,9 +18,9 @@ HOT = ["gemm_pair_kernel", "gemm_kernel", "gemm_mx", "attn_fwd_row_kernel", "att
        "attn_bwd_single_kernel", "attn_bwd_pipe_kernel", "attn_bwd_kernel", "ln_fwd_row_kernel", "ln_bwd3_kernel",
        "fused_allreduce_lamb_kernel", "peer_allreduce_kernel", "lamb_stage1_kernel", "lamb_stage2_kernel",
        "softmax_ce_kernel", "embed_fwd_kernel", "embed_bwd_scatter_kernel", "nsp_head_kernel", "colsum_finalize_kernel",
-       "kfac_"]
+       "kfac_", "dropout_mask_kernel", "attn_bwd_row2_kernel", "colsum_bf16_kernel"]
 MNEMONICS = ["UTCHMMA", "UTCQMMA", "UTCOMMA", "UTCCP", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAREDG", "UBLKCP", "LDGMC",
-             "STGMC", "MULTIMEM", "RED", "HMMA", "SYNCS", "UTCBAR"]
+             "STGMC", "MULTIMEM", "RED", "HMMA", "SYNCS", "UTCBAR", "FFMA2", "FMUL2", "FADD2"]
 
 
 def main():
@@ -33,7 +33,9 @@ def main():
         if not any(h in name for h in HOT):
             continue
         demangled = subprocess.run(["cu++filt", name], capture_output=True, text=True).stdout.strip() or name
-        short = re.sub(r"\(.*", "", demangled).replace("b200::", "").replace("void ", "")
+        short = re.sub(r"\(CUtensorMap.*|\((?!bool|int)[^<]*$", "", demangled).replace("b200::", "").replace("void ", "")
+        short = re.sub(r"\(bool\)|\(int\)", "", short)
+        short = re.sub(r"\(.*", "", short) if "<" not in short else short
         short = re.sub(r"[^A-Za-z0-9_<>,]+", "_", short).strip("_")[:90]
         ops = Counter()
         n_instr = 0
@@ -52,7 +54,7 @@ def main():
     with open(os.path.join(OUT, "INDEX.md"), "w") as f:
         f.write("# SASS of the hot sm_100a kernels (cuobjdump -sass of bert_pytorch_b200/ops/_C.so, one .sass.gz per kernel)\n\n")
         f.write("| kernel | instructions | tensor-core / TMA / peer mnemonics | file |\n|---|---|---|---|\n")
-        for short, n, ops, fn in sorted(index):
+        for short, n, ops, fn in sorted(index, key=lambda e: e[0]):
             f.write(f"| `{short}` | {n} | {', '.join(f'{k} {v}' for k, v in sorted(ops.items())) or '-'} | {fn} |\n")
     print(f"{len(index)} kernels -> {OUT}")
 

@@ -25,7 +25,8 @@ act = torch.randn(M, I, device="cuda").bfloat16()
 
 def run():
     K.gemm(x, wo, epi=K.EPI_NONE)                                                                      # plain
-    K.gemm(x, wo, epi=K.EPI_BIAS_DROP_RES, bias=bo, res=res, p_drop=0.1, seed=3, stream=2)             # attn-out
+    bits = K.dropout_mask(M, H, 0.1, 3, 2, "cuda")                                                     # keep bits of the site
+    K.gemm(x, wo, epi=K.EPI_BIAS_DROP_RES, bias=bo, res=res, p_drop=0.1, seed=3, stream=2, mask_in=bits)   # attn-out
     K.gemm(x, w1, epi=K.EPI_BIAS_GELU_DG, bias=b1, aux_out=aux)                                        # FFN-1
     K.gemm(dy, w2, layout=K.NN, epi=K.EPI_MUL, res=gp, colsum=cs)                                      # FFN-2 dgrad
     K.wgrad_accumulate(act, x, gw)                                                                     # FFN-1 wgrad (TN)
