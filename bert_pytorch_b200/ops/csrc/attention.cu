@@ -2097,19 +2097,21 @@ attn_bwd_row2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
     // O half-row (32 columns) and log-sum-exp of the first item
     uint4 ov[4];
     float lse_nat = 0.f;
-    auto fetch = [&](int item) {
-      const int b = item / p.h, head = item - b * p.h;
+    int seqlen_next = 0;                                         // sequence length of the item being fetched (ncu, round 2b:
+    auto fetch = [&](int item) {                                 // 6.7 % of the stall samples sat on this load, issued per item
+      const int b = item / p.h, head = item - b * p.h;           // right before its first use)
       const __nv_bfloat16* src = p.ctx + ((size_t)b * p.S + r) * p.H + head * HD + hf * 32;
 #pragma unroll
       for (int c = 0; c < 4; ++c) ov[c] = row_ok ? __ldg(reinterpret_cast<const uint4*>(src + c * 8)) : make_uint4(0, 0, 0, 0);
       lse_nat = row_ok ? __ldg(p.lse + (size_t)item * p.S + r) : 0.f;
+      seqlen_next = __ldg(p.seqlens + b);
     };
     if ((int)blockIdx.x < n_items) fetch(blockIdx.x);
     uint32_t g = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++g) {
       const uint32_t ph = g & 1;
       const int b = item / p.h, head = item - b * p.h;
-      const int seqlen = min(__ldg(p.seqlens + b), p.S);
+      const int seqlen = min(seqlen_next, p.S);
       const size_t tok = (size_t)b * p.S + r;
       mbar_wait(qkd_full, ph);
       float part = 0.f;                                        // this thread's half of delta = <dO, O>
@@ -2161,6 +2163,8 @@ attn_bwd_row2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
       fence_proxy_async();
       tc_fence_before();                                       // S / dP reads retired before dV may overwrite S
       mbar_arrive(pd_ready);
+      // the chunk registers are dead: the next item's O half-row, log-sum-exp and sequence length start their trip now
+      if (item + (int)gridDim.x < n_items) fetch(item + gridDim.x);
       mbar_wait(dv_done, ph);                                  // the tensor core no longer reads P~
       tc_fence_after();
       {
@@ -2174,7 +2178,6 @@ attn_bwd_row2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
       fence_proxy_async();
       tc_fence_before();                                       // parked dS read out before dQ may overwrite dP[0,64)
       mbar_arrive(ds_ready);
-      if (item + (int)gridDim.x < n_items) fetch(item + gridDim.x);   // next item's O / lse fly under the wait below
       mbar_wait(fin, ph);
       tc_fence_after();
       // ---- epilogue: columns [32 hf, 32 hf + 32) of this row of dQ (query r), dK and dV (key r)

@@ -10,7 +10,7 @@ from bert_pytorch_b200.ops import api as K  # noqa: E402
 
 H, h = 1024, 16
 cases = []
-for B, S in ((96, 128), (16, 512)):
+for B, S in ((96, 128),) if os.environ.get('NCU_PHASE1_ONLY') else ((96, 128), (16, 512)):
     qkv = (torch.randn(B, S, 3 * H, device="cuda") * 0.5).bfloat16()
     lens = torch.full((B,), S, device="cuda", dtype=torch.int32)
     cases.append((qkv, lens))

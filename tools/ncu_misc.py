@@ -43,7 +43,9 @@ def run():
     K.softmax_ce_(logits.clone(), tgt, cnt, 1.0, loss)
     K.embedding_bwd_scatter(de, ids, seg, gw, gp, gt, 128)
     y, mean, rstd = K.layer_norm_fwd(x, g, b)
-    K.layer_norm_bwd(de, x, mean, rstd, g, dgamma=dg, dbeta=db, dbias=dbias, want_dropped=True, p_drop=0.1, seed=3, drop_stream=5)
+    bits = K.dropout_mask(M, H, 0.1, 3, 5, dev)   # dropout_mask_kernel
+    K.layer_norm_bwd(de, x, mean, rstd, g, dgamma=dg, dbeta=db, dbias=dbias, want_dropped=True, p_drop=0.1, seed=3, drop_stream=5,
+                     keep_mask=bits)
 
 
 run(); run()
