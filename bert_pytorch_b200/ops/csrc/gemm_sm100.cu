@@ -1635,8 +1635,9 @@ static void launch_pair(const GemmCall& c, cudaStream_t st) {
   const bool f32_out = c.epi == EPI_ACCUM_F32 || c.epi == EPI_F32;
   // output / pre-activation / residual tiles of one CTA travel as 4 boxes of [128 rows x 64 columns]
   // (EPI_BIAS_GELU_DG: every epilogue warp stores its own [32 rows x 64 columns] boxes)
-  static const bool warp_epi_on = []() { const char* e = getenv("B200_GEMM_WARP_EPI"); return e && e[0] == '1'; }();   // opt-in: measured 3-10 % slower than the CTA-wide staging tile (profiles/gemm_bench_r2_epi.jsonl)
-  p.warp_epi = (warp_epi_on && c.epi != EPI_BIAS_GELU) ? 1 : 0;
+  // opt-in warp-local staged epilogue: B200_GEMM_WARP_EPI=1 (every layout) / =nt (forward GEMMs only)
+  static const int warp_epi_on = []() { const char* e = getenv("B200_GEMM_WARP_EPI"); return !e ? 0 : (e[0] == '1' ? 1 : (e[0] == 'n' ? 2 : 0)); }();
+  p.warp_epi = ((warp_epi_on == 1 || (warp_epi_on == 2 && !A_MN && !B_MN)) && c.epi != EPI_BIAS_GELU) ? 1 : 0;
   const uint32_t obox = (c.epi == EPI_BIAS_GELU_DG || p.warp_epi) ? 32 : 128;
   CUtensorMap to = f32_out ? ta : make_tmap_2d_bf16(c.out, c.N, c.M, c.ldo, 64, obox);
   CUtensorMap tx = (c.aux_out != nullptr && !f32_out) ? make_tmap_2d_bf16(c.aux_out, c.N, c.M, c.ldo, 64, obox) : to;
