@@ -563,9 +563,28 @@ def main():
                 setattr(sub, k, v)
             gc.collect()
             torch.cuda.empty_cache()
+            # an extra config that HANGS (a wedged collective) must not cost the headline line either: after `limit`
+            # seconds the flag file goes up, every rank's watcher prints what there is (rank 0) and leaves
+            limit = float(os.environ.get("B200_BENCH_EXTRA_TIMEOUT", "420"))
+
+            def _expired(name=name):
+                if state["configs"] is not None:
+                    state["configs"].setdefault(name, {"error": f"timeout: no result after {limit:.0f} s"})
+                try:
+                    open(flag, "w").close()
+                except OSError:
+                    pass
+                if world == 1:
+                    emit()
+                    os._exit(0)
+            guard = threading.Timer(limit, _expired)
+            guard.daemon = True
+            guard.start()
             try:
                 configs[name] = compact(run_config(sub, rank, world, dev))
+                guard.cancel()
             except Exception as e:  # noqa: BLE001 - an extra config must never cost the headline line
+                guard.cancel()
                 configs[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
                 if world > 1:       # the other ranks may be blocked in a collective: stop here, everywhere
                     emit()

@@ -1315,6 +1315,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
           LAB_T(4);
           res_phase ^= 1;
+          // the column sums READ the boxes after their stores went out: nobody may ask for the next residual (a TMA write
+          // into the same box) before every thread of the half is done with them (found by running the tests under
+          // compute-sanitizer's timing: profiles/compute_sanitizer_racecheck_r2b.log)
+          if (p.colsum != nullptr && use_res) half_bar_sync(half);
           if (elected) {                                               // boxes free again -> next tile's residual boxes
             const bool more = use_res && si + 1 < nseg;
             int nnb = 0, nrow0 = 0;
