@@ -625,7 +625,7 @@ attn_fwd_row_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs
   __syncthreads();
   tc_fence_after();
   const uint32_t tS = *tmem_slot, tO = tS + 64;
-  pdl_trigger();
+  pdl_trigger_small();
   pdl_wait();                              // PDL: the set-up above overlapped the previous kernel's tail
 
   if (warp == 4) {
@@ -2022,7 +2022,7 @@ attn_bwd_row2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tS = tmem, tDP = tmem + 128, tDV = tmem, tDK = tmem + 64, tDQ = tmem + 128;
-  pdl_trigger();
+  pdl_trigger_small();
   pdl_wait();                              // PDL: see attn_fwd_row_kernel
 
   if (warp == 8) {

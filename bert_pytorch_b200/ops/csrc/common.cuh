@@ -38,6 +38,12 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 // started.  Both are no-ops for a kernel launched without the attribute.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// the same for the kernels that are not persistent GEMMs; -DB200_PDL_GEMM_ONLY (A/B build) leaves only the GEMMs triggering
+__device__ __forceinline__ void pdl_trigger_small() {
+#ifndef B200_PDL_GEMM_ONLY
+  pdl_trigger();
+#endif
+}
 
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;

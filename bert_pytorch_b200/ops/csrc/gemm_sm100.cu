@@ -1369,10 +1369,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         epi_bar_sync();                                       // nobody touches the staging tile before that
       }
     }
+    // shared memory must outlive the TMA stores' READS of it; their global writes are complete when the grid is (the
+    // .read form is what CUTLASS epilogues wait for too) -- the full wait_group cost every bf16 GEMM its last ~1 us
     if (EC == EC_GELU_DG || warp_local) {
-      if (lane == 0) tma_store_wait<0>();
+      if (lane == 0) tma_store_wait_read<0>();
     } else if (staged && lane == 0 && (ew & 3) == 0) {       // the elected thread of each half (ew == 0: also the legacy issuer)
-      tma_store_wait<0>();
+      tma_store_wait_read<0>();
     }
 #ifdef B200_GEMM_LAB
     if (lab_clk) {

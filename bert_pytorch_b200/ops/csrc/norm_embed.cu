@@ -409,7 +409,7 @@ ln_fwd_row_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__
                   float eps) {
   constexpr int H = CHUNKS * 256;
   __shared__ float4 sg[CHUNKS][2][32], sb[CHUNKS][2][32];   // [chunk][half of the lane's 8 columns][lane]
-  pdl_trigger();
+  pdl_trigger_small();
   pdl_wait();
   for (int i = threadIdx.x; i < CHUNKS * 64; i += blockDim.x) {
     const int c = i >> 6, h = (i >> 5) & 1, l = i & 31;
@@ -476,7 +476,7 @@ ln_bwd3_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __rest
   constexpr int H = WPR * 256;
   __shared__ float2 xchg[GROUPS][2][WPR];
   __shared__ float comb[GROUPS - 1 > 0 ? GROUPS - 1 : 1][3][H];
-  pdl_trigger();
+  pdl_trigger_small();
   pdl_wait();
   const unsigned long long seed = thresh16 != 0 ? seed_in.value() : 0ull;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -612,7 +612,7 @@ ln_bwd3_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __rest
 __global__ void __launch_bounds__(256)
 colsum_finalize_kernel(const float* __restrict__ partial, int nblocks, int H, float* dgamma, float* dbeta,
                        float* dbias) {
-  pdl_trigger();
+  pdl_trigger_small();
   pdl_wait();
   const int qn = blockIdx.y;
   float* dst = qn == 0 ? dgamma : (qn == 1 ? dbeta : dbias);
@@ -644,7 +644,7 @@ colsum_finalize_kernel(const float* __restrict__ partial, int nblocks, int H, fl
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int M, int N, int ld,
                                                          float* __restrict__ out) {
   // block: 32 column-groups (8 cols each = 256 columns) x 8 row lanes
-  pdl_trigger();
+  pdl_trigger_small();
   pdl_wait();
   const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + cg * 8;
@@ -1076,7 +1076,7 @@ void layer_norm_bwd(const void* dy, const void* x, const float* mean, const floa
 // 8.2 k cycles of MMAs per K = 1024 tile) and instead of being regenerated by the LayerNorm backward.
 __global__ void __launch_bounds__(256) dropout_mask_kernel(unsigned int* __restrict__ out, long long n_words, Seed seed_in,
                                                            unsigned int stream, unsigned int thresh16) {
-  pdl_trigger();
+  pdl_trigger_small();
   const PhiloxKeys keys = philox_keys(seed_in.value());
   const uint32_t T = thresh16 << 16;
   for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += (long long)gridDim.x * blockDim.x) {
