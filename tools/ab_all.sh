@@ -1,4 +1,6 @@
 #!/bin/bash
+# needs: git worktree add -f _old <commit> && (cd _old && python -m bert_pytorch_b200.ops.build)   [ab_all.sh also: a _lab/
+# worktree built with B200_NVCC_EXTRA=-DB200_GEMM_LAB]; both directories are scratch (remove them afterwards)
 # tests of the GEMM, then same-box: old commit vs this tree (bench + additive per-kernel trace), then lab cycles
 export PYTHONUNBUFFERED=1
 timeout 400 python -m pytest tests/test_gpu_gemm.py tests/test_gpu_layer_grads.py tests/test_gpu_kernels.py -q -x 2>&1 | tail -4

@@ -1,4 +1,6 @@
 #!/bin/bash
+# needs: git worktree add -f _old <commit> && (cd _old && python -m bert_pytorch_b200.ops.build)   [ab_all.sh also: a _lab/
+# worktree built with B200_NVCC_EXTRA=-DB200_GEMM_LAB]; both directories are scratch (remove them afterwards)
 # same-box A/B of the headline micro-step: current tree vs the tree checked out under _old/ (git worktree of an earlier commit)
 export PYTHONUNBUFFERED=1
 show() { python - <<PY
