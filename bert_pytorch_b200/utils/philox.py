@@ -56,3 +56,12 @@ def keep_scale(p_drop: float) -> float:
         return 1.0
     thresh = int(p_drop * 65536.0 + 0.5)
     return 65536.0 / (65536.0 - thresh)
+
+
+def keep_bits(seed: int, stream: int, rows: int, cols: int, p_drop: float) -> np.ndarray:
+    """uint8 [rows, cols // 8]: the packed keep bits of a ``[rows, cols]`` dropout site exactly as ``dropout_mask_kernel``
+    writes them (ops/csrc/norm_embed.cu; ``ops.api.dropout_mask``): bit ``t`` of byte ``j`` of a row = element
+    ``8 j + t`` kept.  The GEMM epilogue (``mask_in``) and the LayerNorm backward (``keep_mask``) consume this layout."""
+    assert cols % 8 == 0
+    keep = keep_mask(seed, stream, rows * cols, p_drop).reshape(rows, cols // 8, 8)
+    return np.packbits(keep, axis=-1, bitorder="little").reshape(rows, cols // 8)

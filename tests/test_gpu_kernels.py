@@ -77,6 +77,8 @@ def test_dropout_keep_bits_leave_the_gemm_and_feed_layer_norm_backward():
     # the same bits from the stand-alone generator (K.dropout_mask), and the epilogue applying them instead of Philox
     gen = K.dropout_mask(M, H, 0.1, 77, 19, "cuda")
     assert torch.equal(gen, mask)
+    from bert_pytorch_b200.utils import philox                   # ... and the host twin of the generator
+    assert torch.equal(gen.cpu(), torch.from_numpy(philox.keep_bits(77, 19, M, H, 0.1)))
     via = K.gemm(a, w, epi=K.EPI_BIAS_DROP_RES, bias=zeros_b, res=res, p_drop=0.1, seed=77, stream=19, block_n=512, mask_in=gen)
     assert torch.equal(via, ref)
     bits = ((mask.view(M, H // 8, 1) >> torch.arange(8, device="cuda", dtype=torch.uint8).view(1, 1, 8)) & 1).view(M, H).bool()

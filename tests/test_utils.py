@@ -130,3 +130,19 @@ def test_attention_backward_pipeline_protocol_model():
             except AssertionError:
                 caught += 1
         assert caught >= 20, (mutate, caught)
+
+
+def test_host_keep_bits_pack_the_keep_mask_little_endian():
+    """utils/philox.keep_bits is the host twin of dropout_mask_kernel: bit t of byte j = element 8 j + t."""
+    import numpy as np
+    from bert_pytorch_b200.utils import philox
+    rows, cols, p = 5, 64, 0.1
+    keep = philox.keep_mask(1234, 19, rows * cols, p).reshape(rows, cols)
+    bits = philox.keep_bits(1234, 19, rows, cols, p)
+    assert bits.shape == (rows, cols // 8) and bits.dtype == np.uint8
+    for r in range(rows):
+        for c in range(cols):
+            assert bool((bits[r, c // 8] >> (c % 8)) & 1) == bool(keep[r, c])
+    assert philox.keep_bits(1, 2, 3, 16, 0.0).min() == 255          # p = 0 keeps everything
+    frac = 1.0 - philox.keep_mask(7, 3, 1 << 16, 0.1).mean()
+    assert abs(frac - 0.1) < 0.01
