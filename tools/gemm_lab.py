@@ -45,6 +45,16 @@ def main():
         want = sys.argv[sys.argv.index("--variants") + 1].split(",")
         variants = [v for v in variants if v[0] in want]
     stats = torch.zeros(74 * 12, dtype=torch.int64, device="cuda")
+    # the knobs and clocks exist in lab builds only (B200_NVCC_EXTRA=-DB200_GEMM_LAB python -m bert_pytorch_b200.ops.build)
+    probe_a, probe_b = torch.randn(512, 256, device="cuda").bfloat16(), torch.randn(512, 256, device="cuda").bfloat16()
+    C.gemm_lab(0, stats)
+    K.gemm(probe_a, probe_b, block_n=512)
+    torch.cuda.synchronize()
+    C.gemm_lab(0, None)
+    if int(stats.abs().sum()) == 0:
+        sys.exit("gemm_lab: this build has no measurement knobs -- rebuild with B200_NVCC_EXTRA=-DB200_GEMM_LAB "
+                 "(python -m bert_pytorch_b200.ops.build), ideally in a scratch worktree: the knobs cost the production "
+                 "kernels up to 19 %")
     out_path = os.path.join("gpurun_out", "gemm_lab.jsonl")
     os.makedirs("gpurun_out", exist_ok=True)
     with open(out_path, "w") as f:
