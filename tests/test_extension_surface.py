@@ -38,3 +38,16 @@ def test_build_script_lists_every_cuda_source():
     from bert_pytorch_b200.ops import build
     on_disk = sorted(f for f in os.listdir(build.CSRC) if f.endswith(".cu"))
     assert sorted(build.CUDA_SOURCES) == on_disk
+
+
+def test_tile_variant_heuristic_sends_the_bert_large_shapes_to_the_cta_pair_kernel():
+    """ops.api.pick_block_n: every GEMM of a BERT-large layer (and the vocabulary projection) runs on the 2-CTA
+    256 x 256 kernel; the fine-tuning heads (N padded to 8) and one-row-block problems fall back to single-CTA tiles."""
+    from bert_pytorch_b200.ops import api
+    for M, N in ((12288, 1024), (12288, 3072), (12288, 4096), (1920, 30528), (8192, 1024), (1024, 1024), (4096, 1024)):
+        assert api.pick_block_n(M, N) == 512, (M, N)
+    assert api.pick_block_n(12288, 8) == 128            # QA / token-classification heads
+    assert api.pick_block_n(96, 1024) in (128, 256)     # pooler: one 128-row block, whichever fills more SMs
+    assert api.pick_block_n(128, 4096) in (128, 256)
+    # the narrow variant only when it wastes (clearly) fewer SM slots in the last wave
+    assert api._pick_block_n(128, 148 * 128) == 128 or not api._PAIR_ENABLED
